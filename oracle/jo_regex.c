@@ -1,0 +1,727 @@
+/*
+ * ORACLE - TEST INFRASTRUCTURE ONLY (see jo_regex.h).  Backtracking matcher with the
+ * java.util.regex semantics used by GptBytePairEncoding.java:77-80.
+ */
+#include "jo_regex.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../jtokkit_b200/csrc/unicode_ranges.inc"
+
+/* ------------------------------------------------------------------ unicode classes */
+static int in_ranges(const uint32_t (*r)[2], int n, uint32_t cp) {
+	int lo = 0, hi = n - 1;
+	while (lo <= hi) {
+		int mid = (lo + hi) >> 1;
+		if (cp < r[mid][0]) hi = mid - 1;
+		else if (cp > r[mid][1]) lo = mid + 1;
+		else return 1;
+	}
+	return 0;
+}
+int jo_uc_is_letter(uint32_t cp) { return in_ranges(JTK_UC_L, JTK_UC_L_COUNT, cp); }
+int jo_uc_is_number(uint32_t cp) { return in_ranges(JTK_UC_N, JTK_UC_N_COUNT, cp); }
+int jo_uc_is_space(uint32_t cp) { return in_ranges(JTK_UC_WS, JTK_UC_WS_COUNT, cp); }
+
+/* ------------------------------------------------------------------ node tree */
+enum { N_SET, N_ANY, N_CAT, N_ALT, N_REP, N_LOOK, N_EMPTY, N_BOL, N_EOL };
+enum { C_L = 1, C_N, C_SPACE, C_DIGIT, C_WORD };
+enum { Q_GREEDY, Q_LAZY, Q_POSSESSIVE };
+
+typedef struct cls_item {
+	int kind; /* C_* */
+	int neg;
+} cls_item;
+
+typedef struct node {
+	int type;
+	/* N_SET */
+	int neg, ci;
+	int nranges, ncls;
+	uint32_t (*ranges)[2];
+	cls_item *cls;
+	/* N_CAT / N_ALT */
+	int nkids;
+	struct node **kids;
+	/* N_REP / N_LOOK */
+	struct node *sub;
+	int min, max, mode; /* max < 0: unbounded */
+	int look_neg;
+} node;
+
+struct jo_regex {
+	node *root;
+	int flags;
+	node **all;
+	int nall, call;
+};
+
+typedef struct parser {
+	const uint32_t *p;
+	int n, i;
+	int flags; /* pattern-level flags */
+	jo_regex *re;
+	char *err;
+	int errlen;
+	int failed;
+} parser;
+
+static void fail(parser *ps, const char *msg) {
+	if (!ps->failed && ps->err && ps->errlen > 0) snprintf(ps->err, (size_t) ps->errlen, "%s (at pattern index %d)", msg, ps->i);
+	ps->failed = 1;
+}
+
+static node *new_node(parser *ps, int type) {
+	node *nd = (node *) calloc(1, sizeof(node));
+	nd->type = type;
+	jo_regex *re = ps->re;
+	if (re->nall == re->call) {
+		re->call = re->call ? re->call * 2 : 64;
+		re->all = (node **) realloc(re->all, sizeof(node *) * (size_t) re->call);
+	}
+	re->all[re->nall++] = nd;
+	return nd;
+}
+
+static void add_kid(node *nd, node *kid) {
+	nd->kids = (node **) realloc(nd->kids, sizeof(node *) * (size_t) (nd->nkids + 1));
+	nd->kids[nd->nkids++] = kid;
+}
+static void add_range(node *nd, uint32_t lo, uint32_t hi) {
+	nd->ranges = (uint32_t(*)[2]) realloc(nd->ranges, sizeof(uint32_t[2]) * (size_t) (nd->nranges + 1));
+	nd->ranges[nd->nranges][0] = lo;
+	nd->ranges[nd->nranges][1] = hi;
+	nd->nranges++;
+}
+static void add_cls(node *nd, int kind, int neg) {
+	nd->cls = (cls_item *) realloc(nd->cls, sizeof(cls_item) * (size_t) (nd->ncls + 1));
+	nd->cls[nd->ncls].kind = kind;
+	nd->cls[nd->ncls].neg = neg;
+	nd->ncls++;
+}
+
+static int peek(parser *ps) { return ps->i < ps->n ? (int) ps->p[ps->i] : -1; }
+static int eat(parser *ps, int c) {
+	if (peek(ps) == c) {
+		ps->i++;
+		return 1;
+	}
+	return 0;
+}
+
+static node *parse_alt(parser *ps, int ci);
+
+static int hexval(int c) {
+	if (c >= '0' && c <= '9') return c - '0';
+	if (c >= 'a' && c <= 'f') return c - 'a' + 10;
+	if (c >= 'A' && c <= 'F') return c - 'A' + 10;
+	return -1;
+}
+
+/* Parses the part after a backslash.  Either adds a class item / range to `set` and returns 1,
+ * or fails.  `*lit` receives a literal code point (>=0) when the escape denotes a single char. */
+static int parse_escape(parser *ps, node *set, int *lit) {
+	int c = peek(ps);
+	*lit = -1;
+	if (c < 0) {
+		fail(ps, "dangling backslash");
+		return 0;
+	}
+	ps->i++;
+	switch (c) {
+	case 'r': *lit = '\r'; return 1;
+	case 'n': *lit = '\n'; return 1;
+	case 't': *lit = '\t'; return 1;
+	case 'f': *lit = '\f'; return 1;
+	case 'a': *lit = 7; return 1;
+	case 'e': *lit = 27; return 1;
+	case '0': { /* octal \0n, \0nn, \0mnn */
+		int v = 0, k = 0;
+		while (k < 3 && peek(ps) >= '0' && peek(ps) <= '7') {
+			int nv = v * 8 + (peek(ps) - '0');
+			if (nv > 0377) break;
+			v = nv;
+			ps->i++;
+			k++;
+		}
+		if (!k) {
+			fail(ps, "bad octal escape");
+			return 0;
+		}
+		*lit = v;
+		return 1;
+	}
+	case 'x': {
+		int v = 0;
+		if (eat(ps, '{')) {
+			int k = 0;
+			while (hexval(peek(ps)) >= 0) {
+				v = v * 16 + hexval(peek(ps));
+				ps->i++;
+				k++;
+			}
+			if (!k || !eat(ps, '}') || v > 0x10FFFF) {
+				fail(ps, "bad \\x{...} escape");
+				return 0;
+			}
+		} else {
+			for (int k = 0; k < 2; k++) {
+				if (hexval(peek(ps)) < 0) {
+					fail(ps, "bad \\xhh escape");
+					return 0;
+				}
+				v = v * 16 + hexval(peek(ps));
+				ps->i++;
+			}
+		}
+		*lit = v;
+		return 1;
+	}
+	case 'u': {
+		int v = 0;
+		for (int k = 0; k < 4; k++) {
+			if (hexval(peek(ps)) < 0) {
+				fail(ps, "bad \\uhhhh escape");
+				return 0;
+			}
+			v = v * 16 + hexval(peek(ps));
+			ps->i++;
+		}
+		*lit = v;
+		return 1;
+	}
+	case 's': add_cls(set, C_SPACE, 0); return 1;
+	case 'S': add_cls(set, C_SPACE, 1); return 1;
+	case 'd':
+	case 'D':
+	case 'w':
+	case 'W':
+		if (ps->flags & JO_RE_UNICODE_CHARACTER_CLASS) {
+			fail(ps, "\\d and \\w under UNICODE_CHARACTER_CLASS are not supported");
+			return 0;
+		}
+		add_cls(set, (c == 'd' || c == 'D') ? C_DIGIT : C_WORD, c == 'D' || c == 'W');
+		return 1;
+	case 'p':
+	case 'P': {
+		int neg = (c == 'P');
+		char name[32];
+		int k = 0;
+		if (eat(ps, '{')) {
+			if (eat(ps, '^')) neg = !neg;
+			while (peek(ps) >= 0 && peek(ps) != '}' && k < 31) name[k++] = (char) ps->p[ps->i++];
+			if (!eat(ps, '}')) {
+				fail(ps, "unterminated \\p{...}");
+				return 0;
+			}
+		} else if (peek(ps) >= 0) {
+			name[k++] = (char) ps->p[ps->i++];
+		}
+		name[k] = 0;
+		if (!strcmp(name, "L") || !strcmp(name, "IsL") || !strcmp(name, "gc=L") || !strcmp(name, "general_category=L")) add_cls(set, C_L, neg);
+		else if (!strcmp(name, "N") || !strcmp(name, "IsN") || !strcmp(name, "gc=N") || !strcmp(name, "general_category=N")) add_cls(set, C_N, neg);
+		else {
+			fail(ps, "unsupported \\p{...} property (only L and N are supported)");
+			return 0;
+		}
+		return 1;
+	}
+	default:
+		if ((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || (c >= '1' && c <= '9')) {
+			fail(ps, "unsupported escape sequence");
+			return 0;
+		}
+		*lit = c; /* escaped punctuation */
+		return 1;
+	}
+}
+
+static node *parse_class(parser *ps, int ci) {
+	node *set = new_node(ps, N_SET);
+	set->ci = ci;
+	if (eat(ps, '^')) set->neg = 1;
+	int first = 1;
+	for (;;) {
+		int c = peek(ps);
+		if (c < 0) {
+			fail(ps, "unterminated character class");
+			return set;
+		}
+		if (c == ']' && !first) {
+			ps->i++;
+			break;
+		}
+		first = 0;
+		int lit = -1;
+		if (c == '[') {
+			fail(ps, "nested character classes are not supported");
+			return set;
+		}
+		if (c == '&' && ps->i + 1 < ps->n && ps->p[ps->i + 1] == '&') {
+			fail(ps, "class intersection is not supported");
+			return set;
+		}
+		ps->i++;
+		if (c == '\\') {
+			if (!parse_escape(ps, set, &lit)) return set;
+			if (lit < 0) continue; /* class item added */
+		} else {
+			lit = c;
+		}
+		/* range? */
+		if (peek(ps) == '-' && ps->i + 1 < ps->n && ps->p[ps->i + 1] != ']') {
+			ps->i++;
+			int hi = peek(ps);
+			ps->i++;
+			if (hi == '\\') {
+				int l2 = -1;
+				if (!parse_escape(ps, set, &l2)) return set;
+				if (l2 < 0) {
+					fail(ps, "bad range end in character class");
+					return set;
+				}
+				hi = l2;
+			}
+			if (hi < lit) {
+				fail(ps, "illegal character range");
+				return set;
+			}
+			add_range(set, (uint32_t) lit, (uint32_t) hi);
+		} else {
+			add_range(set, (uint32_t) lit, (uint32_t) lit);
+		}
+	}
+	return set;
+}
+
+static node *parse_atom(parser *ps, int *ci) {
+	int c = peek(ps);
+	if (c == '(') {
+		ps->i++;
+		int sub_ci = *ci;
+		if (eat(ps, '?')) {
+			if (eat(ps, ':')) {
+				/* plain non-capturing */
+			} else if (peek(ps) == '!' || peek(ps) == '=') {
+				int neg = (peek(ps) == '!');
+				ps->i++;
+				node *lk = new_node(ps, N_LOOK);
+				lk->look_neg = neg;
+				lk->sub = parse_alt(ps, sub_ci);
+				if (!eat(ps, ')')) fail(ps, "missing ) after look-ahead");
+				return lk;
+			} else if (peek(ps) == '<') {
+				fail(ps, "look-behind / named groups are not supported");
+				return new_node(ps, N_EMPTY);
+			} else {
+				/* inline flags: (?i) (?-i) (?iu:...) */
+				int on = 1, seen = 0;
+				while (peek(ps) >= 0 && peek(ps) != ')' && peek(ps) != ':') {
+					int f = peek(ps);
+					ps->i++;
+					seen = 1;
+					if (f == '-') on = 0;
+					else if (f == 'i') sub_ci = on;
+					else if (f == 'u' || f == 'U') { /* UNICODE_CASE / UNICODE_CHARACTER_CLASS inline: pattern-level only */
+						if (on) ps->flags |= (f == 'u') ? JO_RE_UNICODE_CASE : (JO_RE_UNICODE_CHARACTER_CLASS | JO_RE_UNICODE_CASE);
+					} else {
+						fail(ps, "unsupported inline flag");
+						return new_node(ps, N_EMPTY);
+					}
+				}
+				if (!seen) {
+					fail(ps, "bad group syntax");
+					return new_node(ps, N_EMPTY);
+				}
+				if (eat(ps, ')')) { /* (?i) applies to the remainder of the enclosing group */
+					*ci = sub_ci;
+					return new_node(ps, N_EMPTY);
+				}
+				if (!eat(ps, ':')) {
+					fail(ps, "bad inline flag group");
+					return new_node(ps, N_EMPTY);
+				}
+			}
+		}
+		node *g = parse_alt(ps, sub_ci);
+		if (!eat(ps, ')')) fail(ps, "missing )");
+		return g;
+	}
+	if (c == '[') {
+		ps->i++;
+		return parse_class(ps, *ci);
+	}
+	if (c == '.') {
+		ps->i++;
+		return new_node(ps, N_ANY);
+	}
+	if (c == '^') {
+		ps->i++;
+		return new_node(ps, N_BOL);
+	}
+	if (c == '$') {
+		ps->i++;
+		return new_node(ps, N_EOL);
+	}
+	if (c == '\\') {
+		ps->i++;
+		int nc = peek(ps);
+		if (nc == 'b' || nc == 'B' || nc == 'A' || nc == 'z' || nc == 'Z' || nc == 'G' || nc == 'R' || nc == 'X' || nc == 'Q' || nc == 'h' || nc == 'H' || nc == 'v' || nc == 'V' ||
+		    (nc >= '1' && nc <= '9') || nc == 'k') {
+			fail(ps, "unsupported escape (boundary / back-reference / quoting)");
+			return new_node(ps, N_EMPTY);
+		}
+		node *set = new_node(ps, N_SET);
+		set->ci = *ci;
+		int lit = -1;
+		if (!parse_escape(ps, set, &lit)) return set;
+		if (lit >= 0) add_range(set, (uint32_t) lit, (uint32_t) lit);
+		return set;
+	}
+	if (c == '*' || c == '+' || c == '?') {
+		fail(ps, "dangling quantifier");
+		return new_node(ps, N_EMPTY);
+	}
+	/* literal */
+	ps->i++;
+	node *set = new_node(ps, N_SET);
+	set->ci = *ci;
+	add_range(set, (uint32_t) c, (uint32_t) c);
+	return set;
+}
+
+static node *parse_quantified(parser *ps, int *ci) {
+	node *atom = parse_atom(ps, ci);
+	for (;;) {
+		int c = peek(ps);
+		int min, max;
+		if (c == '*') {
+			min = 0;
+			max = -1;
+			ps->i++;
+		} else if (c == '+') {
+			min = 1;
+			max = -1;
+			ps->i++;
+		} else if (c == '?') {
+			min = 0;
+			max = 1;
+			ps->i++;
+		} else if (c == '{') {
+			int save = ps->i;
+			ps->i++;
+			int a = 0, k = 0;
+			while (peek(ps) >= '0' && peek(ps) <= '9') {
+				a = a * 10 + (peek(ps) - '0');
+				ps->i++;
+				k++;
+			}
+			if (!k) {
+				ps->i = save;
+				fail(ps, "bad {n,m} quantifier");
+				return atom;
+			}
+			min = a;
+			max = a;
+			if (eat(ps, ',')) {
+				max = -1;
+				int b = 0, kb = 0;
+				while (peek(ps) >= '0' && peek(ps) <= '9') {
+					b = b * 10 + (peek(ps) - '0');
+					ps->i++;
+					kb++;
+				}
+				if (kb) max = b;
+			}
+			if (!eat(ps, '}') || (max >= 0 && max < min)) {
+				fail(ps, "bad {n,m} quantifier");
+				return atom;
+			}
+		} else {
+			return atom;
+		}
+		node *rep = new_node(ps, N_REP);
+		rep->sub = atom;
+		rep->min = min;
+		rep->max = max;
+		rep->mode = Q_GREEDY;
+		if (eat(ps, '?')) rep->mode = Q_LAZY;
+		else if (eat(ps, '+')) rep->mode = Q_POSSESSIVE;
+		if (atom->type == N_LOOK || atom->type == N_EMPTY || atom->type == N_BOL || atom->type == N_EOL) {
+			fail(ps, "quantifier on a zero-width construct is not supported");
+			return atom;
+		}
+		atom = rep;
+	}
+}
+
+static node *parse_cat(parser *ps, int ci) {
+	node *cat = new_node(ps, N_CAT);
+	while (!ps->failed) {
+		int c = peek(ps);
+		if (c < 0 || c == '|' || c == ')') break;
+		add_kid(cat, parse_quantified(ps, &ci));
+	}
+	return cat;
+}
+
+static node *parse_alt(parser *ps, int ci) {
+	node *first = parse_cat(ps, ci);
+	if (peek(ps) != '|') return first;
+	node *alt = new_node(ps, N_ALT);
+	add_kid(alt, first);
+	while (!ps->failed && eat(ps, '|')) add_kid(alt, parse_cat(ps, ci));
+	return alt;
+}
+
+jo_regex *jo_regex_compile(const char *pattern, int flags, char *err, int errlen) {
+	size_t blen = strlen(pattern);
+	uint32_t *cps = (uint32_t *) malloc(sizeof(uint32_t) * (blen + 1));
+	int n = 0;
+	for (size_t i = 0; i < blen;) {
+		unsigned char b = (unsigned char) pattern[i];
+		uint32_t cp;
+		int len;
+		if (b < 0x80) {
+			cp = b;
+			len = 1;
+		} else if ((b & 0xE0) == 0xC0) {
+			cp = b & 0x1F;
+			len = 2;
+		} else if ((b & 0xF0) == 0xE0) {
+			cp = b & 0x0F;
+			len = 3;
+		} else {
+			cp = b & 0x07;
+			len = 4;
+		}
+		for (int k = 1; k < len && i + (size_t) k < blen; k++) cp = (cp << 6) | ((unsigned char) pattern[i + (size_t) k] & 0x3F);
+		cps[n++] = cp;
+		i += (size_t) len;
+	}
+	jo_regex *re = (jo_regex *) calloc(1, sizeof(jo_regex));
+	if (flags & JO_RE_UNICODE_CHARACTER_CLASS) flags |= JO_RE_UNICODE_CASE; /* Pattern.java: the flag implies UNICODE_CASE */
+	parser ps;
+	memset(&ps, 0, sizeof(ps));
+	ps.p = cps;
+	ps.n = n;
+	ps.flags = flags;
+	ps.re = re;
+	ps.err = err;
+	ps.errlen = errlen;
+	re->root = parse_alt(&ps, (flags & JO_RE_CASE_INSENSITIVE) ? 1 : 0);
+	if (!ps.failed && ps.i < ps.n) fail(&ps, "unmatched )");
+	re->flags = ps.flags;
+	free(cps);
+	if (ps.failed) {
+		jo_regex_free(re);
+		return NULL;
+	}
+	return re;
+}
+
+void jo_regex_free(jo_regex *re) {
+	if (!re) return;
+	for (int i = 0; i < re->nall; i++) {
+		free(re->all[i]->ranges);
+		free(re->all[i]->cls);
+		free(re->all[i]->kids);
+		free(re->all[i]);
+	}
+	free(re->all);
+	free(re);
+}
+
+/* ------------------------------------------------------------------ matching */
+typedef struct mctx {
+	const jo_regex *re;
+	const uint32_t *s;
+	int64_t n;
+} mctx;
+
+static int cls_match(int kind, uint32_t cp, int ucc) {
+	switch (kind) {
+	case C_L: return jo_uc_is_letter(cp);
+	case C_N: return jo_uc_is_number(cp);
+	case C_SPACE:
+		if (ucc) return jo_uc_is_space(cp);
+		return cp == ' ' || (cp >= 0x09 && cp <= 0x0D);
+	case C_DIGIT: /* \d and \w under UNICODE_CHARACTER_CLASS need Nd / Alphabetic tables the oracle does not
+	               * carry; such patterns are rejected in parse_escape, so only the ASCII meaning is left. */
+		return cp >= '0' && cp <= '9';
+	case C_WORD:
+		return (cp >= 'a' && cp <= 'z') || (cp >= 'A' && cp <= 'Z') || (cp >= '0' && cp <= '9') || cp == '_';
+	}
+	return 0;
+}
+
+static int set_match_one(const node *nd, uint32_t cp, int ucc) {
+	for (int i = 0; i < nd->nranges; i++)
+		if (cp >= nd->ranges[i][0] && cp <= nd->ranges[i][1]) return 1;
+	for (int i = 0; i < nd->ncls; i++)
+		if (cls_match(nd->cls[i].kind, cp, ucc) != nd->cls[i].neg) return 1;
+	return 0;
+}
+
+/* Case-insensitive comparison as java.util.regex does it for single characters: ASCII letters fold
+ * onto each other; with UNICODE_CASE, Character.toLowerCase(Character.toUpperCase(c)) additionally
+ * folds U+017F (long s) onto s and U+212A (Kelvin sign) onto k. */
+static int set_match(const mctx *m, const node *nd, uint32_t cp) {
+	int ucc = (m->re->flags & JO_RE_UNICODE_CHARACTER_CLASS) != 0;
+	int r = set_match_one(nd, cp, ucc);
+	if (!r && nd->ci) {
+		if (cp >= 'a' && cp <= 'z') r = set_match_one(nd, cp - 32, ucc);
+		else if (cp >= 'A' && cp <= 'Z') r = set_match_one(nd, cp + 32, ucc);
+		if (!r && (m->re->flags & JO_RE_UNICODE_CASE)) {
+			if (cp == 0x17F) r = set_match_one(nd, 's', ucc) || set_match_one(nd, 'S', ucc);
+			else if (cp == 0x212A) r = set_match_one(nd, 'k', ucc) || set_match_one(nd, 'K', ucc);
+			else if (cp == 's' || cp == 'S') r = set_match_one(nd, 0x17F, ucc);
+			else if (cp == 'k' || cp == 'K') r = set_match_one(nd, 0x212A, ucc);
+		}
+	}
+	return r != nd->neg;
+}
+
+static int is_line_term(uint32_t c) { return c == '\n' || c == '\r' || c == 0x85 || c == 0x2028 || c == 0x2029; }
+
+/* continuation frames */
+typedef struct kont {
+	const node *nd; /* node to run next (plain frame) or the N_REP node (rep frame) */
+	int is_rep;
+	int count;      /* rep frame: iterations completed when this frame resumes */
+	int64_t start;  /* rep frame: position where the last iteration began (empty-iteration guard) */
+	const struct kont *next;
+} kont;
+
+static int64_t m_node(const mctx *m, const node *nd, int64_t i, const kont *k);
+static int64_t m_rep(const mctx *m, const node *rep, int64_t i, int count, const kont *k);
+
+static int64_t run_k(const mctx *m, const kont *k, int64_t i) {
+	if (!k) return i;
+	if (k->is_rep) {
+		if (i == k->start) return run_k(m, k->next, i); /* an empty iteration ends the loop */
+		return m_rep(m, k->nd, i, k->count, k->next);
+	}
+	return m_node(m, k->nd, i, k->next);
+}
+
+static int single_width(const node *nd) { return nd->type == N_SET || nd->type == N_ANY; }
+
+static int sw_match(const mctx *m, const node *nd, int64_t i) {
+	if (i >= m->n) return 0;
+	if (nd->type == N_ANY) return !is_line_term(m->s[i]);
+	return set_match(m, nd, m->s[i]);
+}
+
+static int64_t m_rep(const mctx *m, const node *rep, int64_t i, int count, const kont *k) {
+	const node *atom = rep->sub;
+	if (single_width(atom)) {
+		/* count how many the atom can take, then hand back one at a time (greedy) */
+		int64_t lim = rep->max < 0 ? m->n - i : rep->max;
+		int64_t c = 0;
+		if (rep->mode == Q_LAZY) {
+			for (;;) {
+				if (c >= rep->min) {
+					int64_t r = run_k(m, k, i + c);
+					if (r >= 0) return r;
+				}
+				if (c >= lim || !sw_match(m, atom, i + c)) return -1;
+				c++;
+			}
+		}
+		while (c < lim && sw_match(m, atom, i + c)) c++;
+		if (c < rep->min) return -1;
+		if (rep->mode == Q_POSSESSIVE) return run_k(m, k, i + c);
+		for (; c >= rep->min; c--) {
+			int64_t r = run_k(m, k, i + c);
+			if (r >= 0) return r;
+		}
+		return -1;
+	}
+	/* general sub-expression */
+	kont again;
+	again.nd = rep;
+	again.is_rep = 1;
+	again.count = count + 1;
+	again.start = i;
+	again.next = k;
+	if (rep->mode == Q_LAZY) {
+		if (count >= rep->min) {
+			int64_t r = run_k(m, k, i);
+			if (r >= 0) return r;
+		}
+		if (rep->max < 0 || count < rep->max) return m_node(m, atom, i, &again);
+		return -1;
+	}
+	if (rep->max < 0 || count < rep->max) {
+		int64_t r = m_node(m, atom, i, &again);
+		if (r >= 0) return r;
+	}
+	if (count >= rep->min) return run_k(m, k, i);
+	return -1;
+}
+
+static int64_t m_cat(const mctx *m, const node *cat, int idx, int64_t i, const kont *k) {
+	if (idx == cat->nkids) return run_k(m, k, i);
+	if (idx == cat->nkids - 1) return m_node(m, cat->kids[idx], i, k);
+	/* one plain continuation frame per later kid, on the stack (patterns are small) */
+	kont frames[64];
+	int nk = cat->nkids - idx - 1;
+	if (nk > 64) return -1;
+	for (int j = nk - 1; j >= 0; j--) {
+		frames[j].nd = cat->kids[idx + 1 + j];
+		frames[j].is_rep = 0;
+		frames[j].count = 0;
+		frames[j].start = 0;
+		frames[j].next = (j == nk - 1) ? k : &frames[j + 1];
+	}
+	return m_node(m, cat->kids[idx], i, &frames[0]);
+}
+
+static int64_t m_node(const mctx *m, const node *nd, int64_t i, const kont *k) {
+	switch (nd->type) {
+	case N_EMPTY: return run_k(m, k, i);
+	case N_SET:
+	case N_ANY:
+		if (!sw_match(m, nd, i)) return -1;
+		return run_k(m, k, i + 1);
+	case N_BOL:
+		if (i != 0) return -1;
+		return run_k(m, k, i);
+	case N_EOL: /* Java '$' without MULTILINE: at end, or before a final line terminator */
+		if (i == m->n || (i == m->n - 1 && is_line_term(m->s[i])) || (i == m->n - 2 && m->s[i] == '\r' && m->s[i + 1] == '\n')) return run_k(m, k, i);
+		return -1;
+	case N_CAT: return m_cat(m, nd, 0, i, k);
+	case N_ALT:
+		for (int b = 0; b < nd->nkids; b++) {
+			int64_t r = m_node(m, nd->kids[b], i, k);
+			if (r >= 0) return r;
+		}
+		return -1;
+	case N_REP: return m_rep(m, nd, i, 0, k);
+	case N_LOOK: {
+		int64_t r = m_node(m, nd->sub, i, NULL);
+		if ((r >= 0) == (nd->look_neg != 0)) return -1;
+		return run_k(m, k, i);
+	}
+	}
+	return -1;
+}
+
+int jo_regex_search(const jo_regex *re, const uint32_t *cps, int64_t n, int64_t from, int64_t *ms, int64_t *me) {
+	mctx m;
+	m.re = re;
+	m.s = cps;
+	m.n = n;
+	for (int64_t st = from; st <= n; st++) {
+		int64_t r = m_node(&m, re->root, st, NULL);
+		if (r >= 0) {
+			*ms = st;
+			*me = r;
+			return 1;
+		}
+	}
+	return 0;
+}

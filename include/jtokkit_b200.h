@@ -1,0 +1,163 @@
+/*
+ * jtokkit_b200 - C ABI of the B200-native JTokkit encode path.
+ *
+ * This header is the drop-in boundary: the functions below are exactly what a JTokkit-side FFI
+ * (Panama FFM or JNI) binds in place of the pure-Java engine
+ *   com.knuddels.jtokkit.GptBytePairEncoding            (lib/src/main/java/com/knuddels/jtokkit/GptBytePairEncoding.java)
+ * that EncodingFactory.fromParameters (EncodingFactory.java:117-119) constructs.  Plain C types only,
+ * no exceptions cross the boundary, no CUDA or torch types appear in the signatures (streams and device
+ * pointers travel as void* / raw pointers).
+ *
+ * There is NO CPU fallback: every encode/decode entry point runs CUDA kernels compiled for sm_100a and
+ * fails with JTK_E_CUDA when no usable device exists.
+ */
+#ifndef JTOKKIT_B200_H
+#define JTOKKIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- return codes --------------------------------------------------------------------------- */
+#define JTK_OK 0
+#define JTK_E_ARG (-1)                 /* bad argument (null pointer, offsets not monotone, ...) */
+#define JTK_E_CUDA (-2)                /* CUDA error or no device; see jtk_last_error() */
+#define JTK_E_PATTERN_UNSUPPORTED (-3) /* split pattern outside the supported set; registration fails, nothing runs on the CPU */
+#define JTK_E_NOMEM (-4)
+#define JTK_E_CAPACITY (-5)            /* caller-provided output buffer too small */
+
+/* ---- per-document status (bit flags), mapped back to the reference's exceptions by the host shim - */
+#define JTK_DOC_OK 0
+#define JTK_DOC_HAS_SPECIAL 1   /* text.contains(specialToken): UnsupportedOperationException, GptBytePairEncoding.java:52-56 */
+#define JTK_DOC_UNKNOWN_BYTES 2 /* a final part is not in the vocabulary: IllegalArgumentException, TokenEncoder.java:64-71 */
+#define JTK_DOC_UNKNOWN_ID 4    /* decode: IllegalArgumentException("Unknown token for decoding"), GptBytePairEncoding.java:313 */
+
+/* ---- encode flags ---------------------------------------------------------------------------- */
+#define JTK_ENCODE_ORDINARY 0u /* encodeOrdinary: GptBytePairEncoding.java:61-64,71-103 */
+#define JTK_CHECK_SPECIAL 1u   /* encode: adds the special-token guard of encodeInternal, :47-59 */
+#define JTK_COUNT_ONLY 2u      /* countTokens / countTokensOrdinary, :121-129: token offsets only, no ids */
+
+/* java.util.regex.Pattern flag bits accepted in jtk_params.pattern_flags (EncodingFactory.java:129) */
+#define JTK_RE_CASE_INSENSITIVE 0x02
+#define JTK_RE_UNICODE_CASE 0x40
+#define JTK_RE_UNICODE_CHARACTER_CLASS 0x100
+
+typedef struct jtk_encoding jtk_encoding; /* immutable after create; any thread may use it concurrently */
+typedef struct jtk_result jtk_result;     /* library-owned result of a host-buffer batch call */
+
+/*
+ * Registration input = com.knuddels.jtokkit.api.GptBytePairEncodingParams (api/GptBytePairEncodingParams.java:36-46)
+ * flattened by the host shim: pattern.pattern() as UTF-8 + pattern.flags(); Map<byte[],Integer> encoder as
+ * (vocab_bytes, vocab_off[vocab_size+1], vocab_ranks[vocab_size]); Map<String,Integer> specialTokensEncoder as
+ * UTF-8 (special_bytes, special_off[special_size+1], special_ids[special_size]).  Empty maps are legal
+ * (BaseEncodingRegistryTest.java:110-125).  Everything is copied; the caller keeps ownership.
+ */
+typedef struct jtk_params {
+	const char *name;
+	const char *pattern;
+	int32_t pattern_flags;
+	const uint8_t *vocab_bytes;
+	const int64_t *vocab_off;
+	const int32_t *vocab_ranks;
+	int64_t vocab_size;
+	const uint8_t *special_bytes;
+	const int64_t *special_off;
+	const int32_t *special_ids;
+	int64_t special_size;
+} jtk_params;
+
+/* Replaces `new GptBytePairEncoding(params)` (GptBytePairEncoding.java:30-35, reached from
+ * EncodingFactory.fromParameters :117-119 and AbstractEncodingRegistry.registerGptBytePairEncoding :63-66).
+ * Compiles the split pattern into device tables, flattens the vocabulary into the byte-keyed piece table and
+ * the pair table, and replicates them on every listed device (devices == NULL: device 0 only). */
+int jtk_encoding_create(const jtk_params *params, const int *devices, int ndev, jtk_encoding **out);
+
+/* Replaces EncodingFactory.r50kBase/p50kBase/p50kEdit/cl100kBase (EncodingFactory.java:60-109) including
+ * loadMergeableRanks (:139-164): `name` selects pattern + special tokens, `tiktoken_path` is the vocabulary
+ * file in the reference's resource format ("<base64> <rank>\n"). */
+int jtk_encoding_create_builtin(const char *name, const char *tiktoken_path, const int *devices, int ndev, jtk_encoding **out);
+
+void jtk_encoding_destroy(jtk_encoding *enc);
+const char *jtk_encoding_name(const jtk_encoding *enc); /* Encoding.getName(), api/Encoding.java:189 */
+int jtk_encoding_num_devices(const jtk_encoding *enc);
+
+/*
+ * The new batch entry point (the shape of the JMH harness' encodeAll(Encoding, List<String>),
+ * benchmark/.../AbstractBenchmark.java:37).  Documents are the UTF-8 bytes utf8[doc_off[d] .. doc_off[d+1]),
+ * doc_off[0] == 0.  HOST buffers; host<->device copies happen inside the call, documents are sharded over the
+ * encoding's devices by byte-balanced contiguous ranges.  Replaces Encoding.encode / encodeOrdinary /
+ * countTokens / countTokensOrdinary (api/Encoding.java:29,80,127,147) for a whole batch.
+ */
+int jtk_encode_batch(jtk_encoding *enc, const uint8_t *utf8, const int64_t *doc_off, int64_t ndocs, uint32_t flags, jtk_result **out);
+
+int64_t jtk_result_num_docs(const jtk_result *r);
+int64_t jtk_result_num_tokens(const jtk_result *r);
+const int32_t *jtk_result_ids(const jtk_result *r);           /* num_tokens ids, NULL for JTK_COUNT_ONLY */
+const int64_t *jtk_result_token_offsets(const jtk_result *r); /* ndocs + 1 */
+const int32_t *jtk_result_doc_status(const jtk_result *r);    /* ndocs, JTK_DOC_* bits */
+double jtk_result_device_ms(const jtk_result *r);             /* kernel time (CUDA events), max over devices */
+int64_t jtk_result_gpu_launches(const jtk_result *r);         /* kernels launched for this batch */
+void jtk_result_free(jtk_result *r);
+
+/*
+ * Device-resident variant: all pointers are device memory on `device` (one of the encoding's devices),
+ * work is enqueued on `cuda_stream` (a cudaStream_t passed as void*, NULL = default stream) and the call
+ * returns after the stream has been synchronised once to read back the totals.
+ *   d_ids        capacity ids_capacity (nbytes is always enough; NULL allowed with JTK_COUNT_ONLY)
+ *   d_tok_off    ndocs + 1 token offsets
+ *   d_doc_status ndocs status words (must be zeroed by the caller or by a previous call; bits are OR-ed in)
+ */
+typedef struct jtk_device_info {
+	int64_t num_tokens;
+	int64_t num_long_pieces; /* pieces longer than the in-tile limit, handled by the long-piece kernels */
+	int64_t gpu_launches;
+	int32_t reserved;
+} jtk_device_info;
+
+int jtk_encode_batch_device(jtk_encoding *enc, int device, const uint8_t *d_utf8, int64_t nbytes, const int64_t *d_doc_off, int64_t ndocs,
+                            uint32_t flags, int32_t *d_ids, int64_t ids_capacity, int64_t *d_tok_off, int32_t *d_doc_status, void *cuda_stream,
+                            jtk_device_info *info);
+
+/* Debug / test entry: the piece boundaries the split kernel finds (replaces the matcher.find() loop alone,
+ * GptBytePairEncoding.java:77-80).  d_piece_flags receives one byte per input byte: 1 where a piece starts. */
+int jtk_split_batch_device(jtk_encoding *enc, int device, const uint8_t *d_utf8, int64_t nbytes, const int64_t *d_doc_off, int64_t ndocs,
+                           uint8_t *d_piece_flags, void *cuda_stream);
+
+/*
+ * Replaces Encoding.decodeBytes (api/Encoding.java:181; GptBytePairEncoding.java:136-151,302-314) for a batch:
+ * ids[tok_off[d] .. tok_off[d+1]) -> bytes.  HOST buffers.  The result reuses jtk_result: jtk_result_bytes /
+ * jtk_result_byte_offsets; unknown ids set JTK_DOC_UNKNOWN_ID and the first offending id per document is
+ * reported through jtk_result_bad_ids.  (String construction, i.e. Encoding.decode's new String(bytes, UTF_8),
+ * stays on the JVM side.)
+ */
+int jtk_decode_batch(jtk_encoding *enc, const int32_t *ids, const int64_t *tok_off, int64_t ndocs, jtk_result **out);
+const uint8_t *jtk_result_bytes(const jtk_result *r);
+const int64_t *jtk_result_byte_offsets(const jtk_result *r); /* ndocs + 1 */
+const int32_t *jtk_result_bad_ids(const jtk_result *r);      /* ndocs */
+
+/*
+ * Replaces Encoding.encode(String, int maxTokens) / encodeOrdinary(String, int) (api/Encoding.java:61,107;
+ * GptBytePairEncoding.java:42-45,66-69,79,90-100,110-119) for one text: full device encode, clip to
+ * maxTokens, then the reference's back-off to a token prefix that decodes to a prefix of the text.
+ * *ids is malloc'ed by the library (free with jtk_free); returns JTK_OK and *doc_status.
+ */
+int jtk_encode_max_tokens(jtk_encoding *enc, const uint8_t *utf8, int64_t nbytes, int32_t max_tokens, uint32_t flags, int32_t **ids,
+                          int64_t *num_ids, int32_t *truncated, int32_t *doc_status);
+void jtk_free(void *p);
+
+/* Pinned host memory for callers that want the fast H2D/D2H path (FFM callers wrap it in a MemorySegment). */
+void *jtk_host_alloc(int64_t nbytes);
+void jtk_host_free(void *p);
+
+/* Thread-local description of the last error returned on this thread. */
+const char *jtk_last_error(void);
+
+/* Library / build identification ("jtokkit_b200 <version> sm_100a unicode <ver>"). */
+const char *jtk_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JTOKKIT_B200_H */

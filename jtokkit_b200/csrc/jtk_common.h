@@ -1,0 +1,145 @@
+/*
+ * Shared between host table construction and the device kernels.
+ *
+ * Everything here is the device-side replacement of the reference's L0 layer:
+ *   TokenEncoder.java:16-17     two HashMaps                 -> piece tables A/B, pair table, token byte store
+ *   java.util.regex.Pattern     compiled split pattern       -> code point class tables + a rule kind
+ */
+#ifndef JTK_COMMON_H
+#define JTK_COMMON_H
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define JTK_HD __host__ __device__ __forceinline__
+#else
+#define JTK_HD inline
+#endif
+
+/* ---- code point classes (4 bits) ---------------------------------------------------------------
+ * The split patterns (EncodingFactory.java:63,105) only distinguish \p{L}, \p{N}, \s (with ' ' and
+ * [\r\n] singled out), the apostrophe, "everything else", and - for the contraction alternatives
+ * 's|'t|'re|'ve|'m|'ll|'d - eight letters.  A continuation byte carries its lead byte's class plus
+ * JTK_CONT so that "class of the previous character" is a single byte read. */
+enum {
+	JTK_C_O = 0,   /* other: [^\s\p{L}\p{N}] */
+	JTK_C_AP = 1,  /* apostrophe (also "other") */
+	JTK_C_SP = 2,  /* U+0020 */
+	JTK_C_NL = 3,  /* \r \n (cl100k only; folded into WO for the x50k pattern) */
+	JTK_C_WO = 4,  /* any other White_Space */
+	JTK_C_N = 5,   /* \p{N} */
+	JTK_C_L = 6,   /* \p{L} without a contraction role */
+	JTK_C_LS = 7,  /* s (cl100k: also S and U+017F) */
+	JTK_C_LT = 8,
+	JTK_C_LM = 9,
+	JTK_C_LD = 10,
+	JTK_C_LR = 11,
+	JTK_C_LV = 12,
+	JTK_C_LL = 13,
+	JTK_C_LE = 14,
+	JTK_C_NONE = 15 /* no character: before a document's first / after its last */
+};
+#define JTK_CONT 0x80
+#define JTK_CLS_MASK 0x0F
+
+JTK_HD bool jtk_is_letter(int c) { return c >= JTK_C_L && c <= JTK_C_LE; }
+JTK_HD bool jtk_is_space(int c) { return c >= JTK_C_SP && c <= JTK_C_WO; }
+JTK_HD bool jtk_is_other(int c) { return c <= JTK_C_AP; }
+
+/* ---- split rule kinds ("compiled pattern") ---------------------------------------------------- */
+enum {
+	JTK_PAT_X50K = 1,  /* r50k_base / p50k_base / p50k_edit, EncodingFactory.java:63,77,91 */
+	JTK_PAT_CL100K = 2 /* cl100k_base, EncodingFactory.java:105 */
+};
+
+#define JTK_RANK_MAX 0x7fffffff                  /* Integer.MAX_VALUE sentinel, GptBytePairEncoding.java:208 */
+#define JTK_PSEUDO_BASE ((int32_t) 0x80000000)   /* id of a single byte that is not in the vocabulary: PSEUDO_BASE + byte */
+#define JTK_INLINE_KEY_MAX 11                    /* piece table A stores keys of up to 11 bytes inline */
+
+/* ---- tile geometry (overridable so that the host-side emulator in tests/ can use tiny tiles) ---------- */
+#ifndef JTK_TILE
+#define JTK_TILE 8192       /* bytes owned by one tile */
+#endif
+#define JTK_NT (JTK_TILE / 16) /* threads per CTA: 16 bytes each */
+#ifndef JTK_BACK_HALO
+#define JTK_BACK_HALO 64    /* context bytes before the tile */
+#endif
+#ifndef JTK_LONG_PIECE
+#define JTK_LONG_PIECE 1024 /* pieces longer than this go to the long-piece kernels */
+#endif
+#define JTK_FWD_HALO (JTK_LONG_PIECE + 16) /* a piece starting in the tile ends inside the halo or is long */
+#define JTK_REGION (JTK_BACK_HALO + JTK_TILE + JTK_FWD_HALO)
+#define JTK_REGION_CHUNKS (JTK_REGION / 16)
+#define JTK_SHORT_PIECE 32  /* thread-per-piece merge up to this length, warp-per-piece above */
+
+/* 16-byte table slots */
+struct jtk_slot {
+	uint32_t x, y, z, w;
+};
+
+/* Device tables of one encoding on one device (all pointers are device memory). */
+struct jtk_tables {
+	int32_t pattern_kind;
+	int32_t max_token_len;
+	/* code point -> class: ASCII direct, the rest two-level (cp >> 8 -> block, block * 256 + low byte) */
+	const uint8_t *ascii_cls;   /* 128 */
+	const uint16_t *cp_stage1;  /* 0x1100 */
+	const uint8_t *cp_stage2;   /* nblocks * 256 */
+	/* whole-piece lookup (GptBytePairEncoding.java:81-83), keys <= 11 bytes: slot = {b0-3, b4-7, b8-10 | len << 24, rank} */
+	const jtk_slot *tab_a;
+	uint32_t mask_a;            /* bucket count - 1; a bucket is two consecutive slots (32 B) */
+	/* whole-piece lookup, keys of 12..max_token_len bytes: slot = {hash lo, hash hi, rank, token index}, verified against tok_bytes */
+	const jtk_slot *tab_b;
+	uint32_t mask_b;
+	const uint8_t *tok_bytes;   /* concatenated token bytes, by token index */
+	const uint32_t *tok_off;    /* ntokens + 1 */
+	/* merge loop (GptBytePairEncoding.java:200-300) re-keyed on (id left, id right) -> rank of the concatenation */
+	const int32_t *byte_id;     /* 256: rank of the single byte or JTK_PSEUDO_BASE + byte */
+	const int32_t *bytepair;    /* 65536: rank of the two-byte token b0 b1, or JTK_RANK_MAX */
+	const jtk_slot *pair;       /* slot = {id left, id right, rank, 1} ; empty slot has w == 0 */
+	uint32_t mask_p;
+	/* special-token guard (GptBytePairEncoding.java:52-56) */
+	int32_t nspecial;
+	int32_t special_has_empty;  /* "".contains: every document is flagged */
+	const uint8_t *special_bytes;
+	const uint32_t *special_off; /* nspecial + 1 */
+	uint32_t special_first[8];   /* bitmap of first bytes */
+	/* decode (GptBytePairEncoding.java:136-151,302-314): id -> token index, open addressing {id, token index + 1} */
+	const uint32_t *dec_keys;    /* pairs (id, index + 1), 0 in the second word = empty */
+	uint32_t mask_d;
+	const uint8_t *dec_bytes;    /* ordinary tokens followed by special-token strings */
+	const uint32_t *dec_off;
+};
+
+/* ---- hashing (identical on host and device) ---------------------------------------------------- */
+JTK_HD uint32_t jtk_hash3(uint32_t a, uint32_t b, uint32_t c) {
+	uint32_t h = a * 0x9E3779B1u;
+	h ^= (b + 0x7F4A7C15u) * 0x85EBCA77u;
+	h ^= (c + 0x165667B1u) * 0xC2B2AE3Du;
+	h ^= h >> 15;
+	h *= 0x2C1B3C6Du;
+	h ^= h >> 13;
+	return h;
+}
+
+JTK_HD uint32_t jtk_hash_pair(int32_t l, int32_t r) {
+	uint32_t h = (uint32_t) l * 0x9E3779B1u;
+	h ^= ((uint32_t) r + 0x7F4A7C15u) * 0x85EBCA77u;
+	h ^= h >> 15;
+	h *= 0x2C1B3C6Du;
+	h ^= h >> 13;
+	return h;
+}
+
+/* 64-bit byte-string hash for table B (FNV-1a over bytes, then a finaliser) */
+JTK_HD uint64_t jtk_hash_bytes_step(uint64_t h, uint8_t b) { return (h ^ b) * 0x100000001B3ull; }
+JTK_HD uint64_t jtk_hash_bytes_init() { return 0xCBF29CE484222325ull; }
+JTK_HD uint64_t jtk_hash_bytes_final(uint64_t h, uint32_t len) {
+	h ^= (uint64_t) len * 0x9E3779B97F4A7C15ull;
+	h ^= h >> 29;
+	h *= 0xBF58476D1CE4E5B9ull;
+	h ^= h >> 32;
+	return h;
+}
+
+#endif /* JTK_COMMON_H */

@@ -1,0 +1,622 @@
+/*
+ * Per-tile building blocks of the encode kernel, written as __host__ __device__ functions over a
+ * jtk_tile_ctx so that the same code runs inside the CUDA kernel (shared memory arrays) and inside the
+ * host-side tile emulator that tests/ use to fuzz the split rules against the oracle.
+ *
+ * What each block replaces in the reference (GptBytePairEncoding.java):
+ *   jtk_classify_chunk / jtk_boundary_chunk : the matcher.find() loop, :77-80 (split patterns EncodingFactory.java:63,105)
+ *   jtk_special_at                          : text.contains(specialToken), :52-56
+ *   jtk_lookup_piece                        : encoder.containsDecodedToken / encode fast path, :81-83
+ *   jtk_merge_short                         : bytePairMerge + getRank, :200-300
+ */
+#ifndef JTK_DEVICE_CUH
+#define JTK_DEVICE_CUH
+
+#include "jtk_common.h"
+
+struct jtk_tile_ctx {
+	/* region arrays (shared memory on the device); region index r <-> global byte g0 + r */
+	uint8_t *sb;     /* JTK_REGION + 16 input bytes (zero padded) */
+	uint8_t *cls;    /* JTK_REGION + 16 class bytes */
+	uint32_t *bmask; /* piece-start bits, (JTK_REGION + 32) / 32 + 1 words */
+	uint32_t *dmask; /* document-start bits, same size; the end of the input counts as a document start */
+	int32_t *tok;    /* JTK_TILE + JTK_FWD_HALO token staging, indexed by r - JTK_BACK_HALO */
+	int32_t *rk;     /* same size: pair ranks during merging, then per-piece token counts */
+	/* geometry */
+	int64_t g0;      /* global position of region index 0 (negative for the first tile) */
+	int64_t total;   /* total input bytes */
+	int32_t rs;      /* first usable region index (>= -g0, not in the middle of a character) */
+	int32_t carry_n; /* \p{N} characters immediately before region index rs in the same document */
+	/* global inputs (for the rare walks that leave the region) */
+	const uint8_t *gbytes;
+	const int64_t *doc_off;
+	int64_t ndocs;
+	const jtk_tables *T;
+};
+
+#define JTK_MASK_WORDS ((JTK_REGION + 32) / 32 + 1)
+
+JTK_HD bool jtk_docstart(const jtk_tile_ctx &c, int r) { return (c.dmask[r >> 5] >> (r & 31)) & 1u; }
+JTK_HD int jtk_cls(const jtk_tile_ctx &c, int r) { return c.cls[r] & JTK_CLS_MASK; }
+
+#if defined(__CUDA_ARCH__)
+#define JTK_SMEM_OR(p, v) atomicOr((p), (v))
+#else
+#define JTK_SMEM_OR(p, v) (*(p) |= (v))
+#endif
+
+/* ---------------------------------------------------------------------------------------------
+ * region set-up
+ * ------------------------------------------------------------------------------------------- */
+/* Copies the 16 input bytes of region chunk `chunk` (the pad chunk JTK_REGION_CHUNKS included) into c.sb;
+ * positions outside [0, total) read as zero.  c.gbytes must be 16-byte aligned. */
+JTK_HD void jtk_load_chunk(jtk_tile_ctx &c, int chunk) {
+	const int64_t g = c.g0 + 16 * (int64_t) chunk;
+	uint8_t *dst = c.sb + 16 * chunk;
+	if (g >= 0 && g + 16 <= c.total) {
+#if defined(__CUDA_ARCH__)
+		*reinterpret_cast<uint4 *>(dst) = __ldg(reinterpret_cast<const uint4 *>(c.gbytes + g));
+#else
+		for (int i = 0; i < 16; i++) dst[i] = c.gbytes[g + i];
+#endif
+	} else {
+		for (int i = 0; i < 16; i++) dst[i] = (g + i >= 0 && g + i < c.total) ? c.gbytes[g + i] : (uint8_t) 0;
+	}
+}
+
+/* Sets the document-start bits of documents first_doc + tid, first_doc + tid + nthreads, ... that fall into
+ * the region.  doc_off[ndocs] == total is marked too: the end of the input ends the last piece. */
+JTK_HD void jtk_mark_docstarts(jtk_tile_ctx &c, int64_t first_doc, int tid, int nthreads) {
+	for (int64_t d = first_doc + tid; d <= c.ndocs; d += nthreads) {
+		const int64_t r = c.doc_off[d] - c.g0;
+		if (r > JTK_REGION + 16) break;
+		if (r >= 0) JTK_SMEM_OR(&c.dmask[r >> 5], 1u << (r & 31));
+	}
+}
+
+/* First usable region index: not before the input, not inside a character that began before the region. */
+JTK_HD int jtk_region_first(const jtk_tile_ctx &c) {
+	int rs = c.g0 < 0 ? (int) -c.g0 : 0;
+	const int lim = rs + 3;
+	while (rs < lim && (c.sb[rs] & 0xC0) == 0x80 && !jtk_docstart(c, rs)) rs++;
+	return rs;
+}
+
+/* \\p{N} carry into the region (see jtk_count_n_before); call after classification. */
+JTK_HD int jtk_global_count_n_before(const jtk_tile_ctx &c, int64_t g);
+JTK_HD int jtk_region_carry_n(const jtk_tile_ctx &c) {
+	if (c.T->pattern_kind != JTK_PAT_CL100K) return 0;
+	if (jtk_docstart(c, c.rs) || c.g0 + c.rs <= 0) return 0;
+	if (jtk_cls(c, c.rs) != JTK_C_N) return 0;
+	return jtk_global_count_n_before(c, c.g0 + c.rs);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * code point classification
+ * ------------------------------------------------------------------------------------------- */
+JTK_HD int jtk_cp_class(const jtk_tables &T, uint32_t cp) {
+	if (cp < 128) return T.ascii_cls[cp];
+	if (cp >= 0x110000u) return JTK_C_O;
+	return T.cp_stage2[((uint32_t) T.cp_stage1[cp >> 8] << 8) | (cp & 255u)];
+}
+
+/* Length a UTF-8 lead byte announces (1 for ASCII, stray continuation bytes and invalid leads). */
+JTK_HD int jtk_lead_len(uint8_t b) {
+	if (b < 0xC0) return 1;
+	if (b < 0xE0) return 2;
+	if (b < 0xF0) return 3;
+	if (b < 0xF8) return 4;
+	return 1;
+}
+
+/* Character whose lead byte is at `p` in the byte array `s` (positions < limit are readable, document starts
+ * are given by `is_start(p)`).  Returns its class; *len receives its byte length.  A lead byte whose
+ * continuation bytes are missing is a one-byte "other" character, as is a stray continuation byte
+ * (input from String.getBytes(UTF_8) never contains either). */
+template <typename StartFn>
+JTK_HD int jtk_decode_char(const jtk_tables &T, const uint8_t *s, int64_t p, int64_t limit, StartFn is_start, int *len) {
+	uint8_t b = s[p];
+	*len = 1;
+	if (b < 0x80) return T.ascii_cls[b];
+	int n = jtk_lead_len(b);
+	if (n == 1) return JTK_C_O;
+	uint32_t cp = b & (0xFFu >> (n + 1));
+	for (int k = 1; k < n; k++) {
+		if (p + k >= limit || is_start(p + k)) return JTK_C_O;
+		uint8_t cb = s[p + k];
+		if ((cb & 0xC0) != 0x80) return JTK_C_O;
+		cp = (cp << 6) | (cb & 0x3Fu);
+	}
+	*len = n;
+	return jtk_cp_class(T, cp);
+}
+
+struct jtk_region_start {
+	const jtk_tile_ctx *c;
+	JTK_HD bool operator()(int64_t r) const { return jtk_docstart(*c, (int) r); }
+};
+
+/* Classifies the 16 bytes of chunk `chunk` (region indices 16*chunk ..) into c.cls. */
+JTK_HD void jtk_classify_chunk(jtk_tile_ctx &c, int chunk) {
+	const jtk_tables &T = *c.T;
+	const int r0 = chunk * 16;
+	jtk_region_start is_start{&c};
+	int cur = JTK_C_O, rem = 0;
+	/* a character may have started in the previous chunk */
+	if ((c.sb[r0] & 0xC0) == 0x80 && !jtk_docstart(c, r0)) {
+		for (int k = 1; k <= 3 && r0 - k >= c.rs; k++) {
+			uint8_t b = c.sb[r0 - k];
+			if ((b & 0xC0) == 0x80) {
+				if (jtk_docstart(c, r0 - k)) break;
+				continue;
+			}
+			int len;
+			int cl = jtk_decode_char(T, c.sb, r0 - k, JTK_REGION + 16, is_start, &len);
+			if (len > k) {
+				cur = cl;
+				rem = len - k;
+			}
+			break;
+		}
+	}
+	uint8_t out[16];
+	for (int i = 0; i < 16; i++) {
+		const int r = r0 + i;
+		const uint8_t b = c.sb[r];
+		if (rem > 0) { /* inside a validated character */
+			out[i] = (uint8_t) (cur | JTK_CONT);
+			rem--;
+			continue;
+		}
+		if (b < 0x80) {
+			out[i] = T.ascii_cls[b];
+		} else {
+			int len;
+			cur = jtk_decode_char(T, c.sb, r, JTK_REGION + 16, is_start, &len);
+			rem = len - 1;
+			out[i] = (uint8_t) cur;
+		}
+	}
+	for (int i = 0; i < 16; i++) c.cls[r0 + i] = out[i];
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * walks that may leave the region (rare): plain global-memory versions
+ * ------------------------------------------------------------------------------------------- */
+/* largest document start <= g */
+JTK_HD int64_t jtk_doc_floor(const jtk_tile_ctx &c, int64_t g) {
+	int64_t lo = 0, hi = c.ndocs; /* doc_off[lo] <= g */
+	while (lo < hi) {
+		int64_t mid = (lo + hi + 1) >> 1;
+		if (c.doc_off[mid] <= g) lo = mid;
+		else hi = mid - 1;
+	}
+	return c.doc_off[lo];
+}
+/* smallest document start > g (the end of the input is one) */
+JTK_HD int64_t jtk_doc_ceil(const jtk_tile_ctx &c, int64_t g) {
+	int64_t lo = 0, hi = c.ndocs; /* answer index in [lo, hi] */
+	while (lo < hi) {
+		int64_t mid = (lo + hi) >> 1;
+		if (c.doc_off[mid] > g) hi = mid;
+		else lo = mid + 1;
+	}
+	return c.doc_off[lo] > g ? c.doc_off[lo] : c.total;
+}
+
+struct jtk_never_start {
+	JTK_HD bool operator()(int64_t) const { return false; }
+};
+
+/* Class of the character that ends at global position g (exclusive) inside the document starting at doc_lo;
+ * *lead receives its first byte.  g > doc_lo required. */
+JTK_HD int jtk_global_char_before(const jtk_tile_ctx &c, int64_t g, int64_t doc_lo, int64_t *lead) {
+	int64_t p = g - 1;
+	int k = 0;
+	while (k < 3 && p > doc_lo && (c.gbytes[p] & 0xC0) == 0x80) {
+		p--;
+		k++;
+	}
+	int len;
+	int cl = jtk_decode_char(*c.T, c.gbytes, p, g, jtk_never_start(), &len);
+	if (p + len != g) { /* malformed tail: the last byte stands alone */
+		*lead = g - 1;
+		return jtk_decode_char(*c.T, c.gbytes, g - 1, g, jtk_never_start(), &len);
+	}
+	*lead = p;
+	return cl;
+}
+
+/* \p{N} characters immediately before global position g in its document (mod 3 is all that matters). */
+JTK_HD int jtk_global_count_n_before(const jtk_tile_ctx &c, int64_t g) {
+	int64_t lo = jtk_doc_floor(c, g);
+	int k = 0;
+	while (g > lo) {
+		int64_t lead;
+		if (jtk_global_char_before(c, g, lo, &lead) != JTK_C_N) break;
+		k = (k + 1) % 3;
+		g = lead;
+	}
+	return k;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * split rules
+ * ------------------------------------------------------------------------------------------- */
+/* lead index of the character that ends right before region index r (r > c.rs, no document start at r) */
+JTK_HD int jtk_prev_lead(const jtk_tile_ctx &c, int r) {
+	int p = r - 1;
+	while (p > c.rs && (c.cls[p] & JTK_CONT)) p--;
+	return p;
+}
+JTK_HD int jtk_char_len(const jtk_tile_ctx &c, int r) {
+	int len = 1;
+	while (len < 4 && (c.cls[r + len] & JTK_CONT)) len++;
+	return len;
+}
+
+/* An "other" character (incl. the apostrophe) at lead index r starts a piece unless it continues an
+ * other-run or is taken by the optional leading space of ` ?[^\s\p{L}\p{N}]+`. */
+JTK_HD bool jtk_other_is_start(const jtk_tile_ctx &c, int r) {
+	if (jtk_docstart(c, r)) return true;
+	int pc = jtk_cls(c, r - 1);
+	return !(jtk_is_other(pc) || pc == JTK_C_SP);
+}
+
+/* cur and prev are letters: did one of 's 't 'm 'd 're 've 'll end exactly before r? */
+JTK_HD bool jtk_ends_contraction(const jtk_tile_ctx &c, int r) {
+	int r1 = jtk_prev_lead(c, r);
+	int k1 = jtk_cls(c, r1);
+	bool single = (k1 >= JTK_C_LS && k1 <= JTK_C_LD);
+	bool second = (k1 == JTK_C_LE || k1 == JTK_C_LL);
+	if (!single && !second) return false;
+	if (jtk_docstart(c, r1)) return false;
+	int r2 = jtk_prev_lead(c, r1);
+	int k2 = jtk_cls(c, r2);
+	if (single) return k2 == JTK_C_AP && jtk_other_is_start(c, r2);
+	if (!((k1 == JTK_C_LE && (k2 == JTK_C_LR || k2 == JTK_C_LV)) || (k1 == JTK_C_LL && k2 == JTK_C_LL))) return false;
+	if (jtk_docstart(c, r2)) return false;
+	int r3 = jtk_prev_lead(c, r2);
+	return jtk_cls(c, r3) == JTK_C_AP && jtk_other_is_start(c, r3);
+}
+
+/* x50k: does a contraction alternative match at the apostrophe at lead index r? */
+JTK_HD bool jtk_contraction_starts(const jtk_tile_ctx &c, int r) {
+	if (jtk_docstart(c, r + 1)) return false;
+	int k1 = jtk_cls(c, r + 1);
+	if (k1 >= JTK_C_LS && k1 <= JTK_C_LD) return true;
+	if (k1 != JTK_C_LR && k1 != JTK_C_LV && k1 != JTK_C_LL) return false;
+	int n1 = jtk_char_len(c, r + 1);
+	if (jtk_docstart(c, r + 1 + n1)) return false;
+	int k2 = jtk_cls(c, r + 1 + n1);
+	return (k1 == JTK_C_LL) ? (k2 == JTK_C_LL) : (k2 == JTK_C_LE);
+}
+
+/* cl100k: scanning forward from the character at lead index r (a non-NL whitespace character), does a
+ * \r or \n occur before the whitespace run ends?  (`\s*[\r\n]+` takes the run up to its last NL.) */
+JTK_HD bool jtk_nl_ahead(const jtk_tile_ctx &c, int r) {
+	int p = r + jtk_char_len(c, r);
+	for (;;) {
+		if (p >= JTK_REGION) break;
+		if (jtk_docstart(c, p)) return false;
+		int k = jtk_cls(c, p);
+		if (k == JTK_C_NL) return true;
+		if (k != JTK_C_SP && k != JTK_C_WO) return false;
+		p += jtk_char_len(c, p);
+	}
+	/* left the region: continue in global memory */
+	int64_t g = c.g0 + p;
+	int64_t hi = jtk_doc_ceil(c, g - 1);
+	while (g < hi) {
+		int len;
+		int k = jtk_decode_char(*c.T, c.gbytes, g, hi, jtk_never_start(), &len);
+		if (k == JTK_C_NL) return true;
+		if (k != JTK_C_SP && k != JTK_C_WO) return false;
+		g += len;
+	}
+	return false;
+}
+
+/* cl100k: walking back from lead index r over \r\n characters, is the first other character an "other"
+ * one?  (Then those NLs were taken by the `[\r\n]*` tail of ` ?[^\s\p{L}\p{N}]+[\r\n]*`.) */
+JTK_HD bool jtk_nl_absorbed(const jtk_tile_ctx &c, int r) {
+	int p = r;
+	for (;;) {
+		if (jtk_docstart(c, p)) return false;
+		if (p <= c.rs) break;
+		p = jtk_prev_lead(c, p);
+		int k = jtk_cls(c, p);
+		if (k != JTK_C_NL) return jtk_is_other(k);
+	}
+	int64_t g = c.g0 + p;
+	int64_t lo = jtk_doc_floor(c, g);
+	while (g > lo) {
+		int64_t lead;
+		int k = jtk_global_char_before(c, g, lo, &lead);
+		if (k != JTK_C_NL) return jtk_is_other(k);
+		g = lead;
+	}
+	return false;
+}
+
+/* \p{N} characters immediately before lead index r in the same document, mod 3 */
+JTK_HD int jtk_count_n_before(const jtk_tile_ctx &c, int r) {
+	int k = 0, p = r;
+	for (;;) {
+		if (jtk_docstart(c, p)) return k;
+		if (p <= c.rs) return (k + c.carry_n) % 3;
+		p = jtk_prev_lead(c, p);
+		if (jtk_cls(c, p) != JTK_C_N) return k;
+		k = (k + 1) % 3;
+	}
+}
+
+/* Is region index r (a lead byte that is not a document start) the first byte of a piece?
+ * nrun: running count (mod 3) of \p{N} characters right before r, or -1 when not yet known. */
+JTK_HD bool jtk_is_piece_start(const jtk_tile_ctx &c, int r, int cur, int *nrun) {
+	const int prev = jtk_cls(c, r - 1);
+	const bool cl100k = c.T->pattern_kind == JTK_PAT_CL100K;
+	if (jtk_is_letter(cur)) {
+		if (jtk_is_letter(prev)) return jtk_ends_contraction(c, r);
+		if (cl100k) {
+			if (prev == JTK_C_N || prev == JTK_C_NL) return true;
+			if (jtk_is_space(prev)) return false; /* [^\r\n\p{L}\p{N}]?\p{L}+ takes the whitespace character */
+			return !jtk_other_is_start(c, jtk_prev_lead(c, r));
+		}
+		if (prev == JTK_C_SP) return false; /* ` ?\p{L}+` */
+		if (prev == JTK_C_AP) {
+			int rp = r - 1;
+			return !(jtk_other_is_start(c, rp) && jtk_contraction_starts(c, rp));
+		}
+		return true;
+	}
+	if (cur == JTK_C_N) {
+		if (cl100k) { /* \p{N}{1,3}: runs are cut in threes from their start */
+			if (prev != JTK_C_N) return true;
+			if (*nrun < 0) *nrun = jtk_count_n_before(c, r);
+			return *nrun == 0;
+		}
+		return !(prev == JTK_C_N || prev == JTK_C_SP); /* ` ?\p{N}+` */
+	}
+	if (jtk_is_other(cur)) return !(jtk_is_other(prev) || prev == JTK_C_SP);
+	if (cur == JTK_C_NL) return jtk_is_letter(prev) || prev == JTK_C_N; /* cl100k only: after "other" it belongs to [\r\n]*, inside whitespace to \s*[\r\n]+ */
+	/* SP / WO */
+	if (!jtk_is_space(prev)) return true;
+	int nr = r + jtk_char_len(c, r);
+	if (!jtk_docstart(c, nr) && !jtk_is_space(jtk_cls(c, nr))) return true; /* \s+(?!\S) gives the last whitespace character back */
+	if (prev == JTK_C_NL) {
+		if (!jtk_nl_ahead(c, r)) return true; /* \s*[\r\n]+ ended right before r */
+		return jtk_nl_absorbed(c, r);         /* ... or the NLs before r belong to the preceding "other" piece */
+	}
+	return false;
+}
+
+/* Piece-start bits for the 16 positions of chunk `chunk`. */
+JTK_HD uint32_t jtk_boundary_chunk(const jtk_tile_ctx &c, int chunk) {
+	const int r0 = chunk * 16;
+	uint32_t bits = 0;
+	int nrun = -1;
+	for (int i = 0; i < 16; i++) {
+		const int r = r0 + i;
+		if (r < c.rs) continue;
+		if (jtk_docstart(c, r)) {
+			bits |= 1u << i;
+			nrun = 0;
+			if (c.g0 + r >= c.total) break;
+			if (jtk_cls(c, r) == JTK_C_N && !(c.cls[r] & JTK_CONT)) nrun = 1;
+			continue;
+		}
+		if (c.g0 + r >= c.total) break;
+		const int cb = c.cls[r];
+		if (cb & JTK_CONT) continue;
+		const int cur = cb & JTK_CLS_MASK;
+		if (jtk_is_piece_start(c, r, cur, &nrun)) bits |= 1u << i;
+		if (cur == JTK_C_N) {
+			if (nrun < 0) nrun = jtk_count_n_before(c, r);
+			nrun = (nrun + 1) % 3;
+		} else {
+			nrun = 0;
+		}
+	}
+	return bits;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * special-token guard
+ * ------------------------------------------------------------------------------------------- */
+/* Does any special token start at global position g (document ends at doc_hi)? */
+JTK_HD bool jtk_special_at(const jtk_tables &T, const uint8_t *gbytes, int64_t g, int64_t doc_hi) {
+	for (int s = 0; s < T.nspecial; s++) {
+		uint32_t a = T.special_off[s], b = T.special_off[s + 1];
+		uint32_t len = b - a;
+		if (len == 0 || g + len > doc_hi) continue;
+		uint32_t i = 0;
+		while (i < len && gbytes[g + i] == T.special_bytes[a + i]) i++;
+		if (i == len) return true;
+	}
+	return false;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * table lookups
+ * ------------------------------------------------------------------------------------------- */
+/* whole-piece lookup for keys of 1..11 bytes; returns the rank or JTK_RANK_MAX */
+JTK_HD int32_t jtk_lookup_a(const jtk_tables &T, uint32_t w0, uint32_t w1, uint32_t w2) {
+	uint32_t b = jtk_hash3(w0, w1, w2) & T.mask_a;
+	for (;;) {
+		const jtk_slot s0 = T.tab_a[2 * b], s1 = T.tab_a[2 * b + 1];
+		if (s0.x == w0 && s0.y == w1 && s0.z == w2) return (int32_t) s0.w;
+		if (s0.z == 0) return JTK_RANK_MAX;
+		if (s1.x == w0 && s1.y == w1 && s1.z == w2) return (int32_t) s1.w;
+		if (s1.z == 0) return JTK_RANK_MAX;
+		b = (b + 1) & T.mask_a;
+	}
+}
+
+/* whole-piece lookup for keys of 12..max_token_len bytes, verified byte by byte */
+JTK_HD int32_t jtk_lookup_b(const jtk_tables &T, const uint8_t *p, uint32_t n) {
+	uint64_t h = jtk_hash_bytes_init();
+	for (uint32_t i = 0; i < n; i++) h = jtk_hash_bytes_step(h, p[i]);
+	h = jtk_hash_bytes_final(h, n);
+	const uint32_t lo = (uint32_t) h, hi = (uint32_t) (h >> 32);
+	uint32_t b = lo & T.mask_b;
+	for (;;) {
+		for (int j = 0; j < 2; j++) {
+			const jtk_slot s = T.tab_b[2 * b + j];
+			if (s.w == 0) return JTK_RANK_MAX;
+			if (s.x == lo && s.y == hi) {
+				const uint32_t a = T.tok_off[s.w - 1], e = T.tok_off[s.w];
+				if (e - a == n) {
+					uint32_t i = 0;
+					while (i < n && T.tok_bytes[a + i] == p[i]) i++;
+					if (i == n) return (int32_t) s.z;
+				}
+			}
+		}
+		b = (b + 1) & T.mask_b;
+	}
+}
+
+/* rank of the concatenation of two parts, or JTK_RANK_MAX (getRank, GptBytePairEncoding.java:285-300) */
+JTK_HD int32_t jtk_lookup_pair(const jtk_tables &T, int32_t l, int32_t r) {
+	uint32_t b = jtk_hash_pair(l, r) & T.mask_p;
+	for (;;) {
+		const jtk_slot s0 = T.pair[2 * b], s1 = T.pair[2 * b + 1];
+		if (s0.w == 0) return JTK_RANK_MAX;
+		if (s0.x == (uint32_t) l && s0.y == (uint32_t) r) return (int32_t) s0.z;
+		if (s1.w == 0) return JTK_RANK_MAX;
+		if (s1.x == (uint32_t) l && s1.y == (uint32_t) r) return (int32_t) s1.z;
+		b = (b + 1) & T.mask_p;
+	}
+}
+
+/* Whole-piece lookup of the n bytes at p (n >= 1): rank or JTK_RANK_MAX. */
+JTK_HD int32_t jtk_lookup_piece(const jtk_tables &T, const uint8_t *p, int n) {
+	if (n == 1) {
+		int32_t id = T.byte_id[p[0]];
+		return id < JTK_PSEUDO_BASE + 256 ? JTK_RANK_MAX : id;
+	}
+	if (n <= JTK_INLINE_KEY_MAX) {
+		uint32_t w0 = 0, w1 = 0, w2 = (uint32_t) n << 24;
+		for (int i = 0; i < n; i++) {
+			uint32_t v = (uint32_t) p[i] << (8 * (i & 3));
+			if (i < 4) w0 |= v;
+			else if (i < 8) w1 |= v;
+			else w2 |= v;
+		}
+		return jtk_lookup_a(T, w0, w1, w2);
+	}
+	if (n > T.max_token_len) return JTK_RANK_MAX;
+	return jtk_lookup_b(T, p, (uint32_t) n);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * bytePairMerge for one piece of 2..32 bytes by one thread (GptBytePairEncoding.java:200-275)
+ * tok / rk: n staging slots each.  Returns the token count; tokens end up in tok[0..count).
+ * *unknown is set when a final part is a byte that is not in the vocabulary.
+ * ------------------------------------------------------------------------------------------- */
+JTK_HD int jtk_merge_short(const jtk_tables &T, const uint8_t *p, int n, int32_t *tok, int32_t *rk, bool *unknown) {
+	for (int k = 0; k < n; k++) {
+		tok[k] = T.byte_id[p[k]];
+		rk[k] = (k + 1 < n) ? T.bytepair[((uint32_t) p[k] << 8) | p[k + 1]] : JTK_RANK_MAX;
+	}
+	uint32_t alive = (n >= 32) ? 0xFFFFFFFFu : ((1u << n) - 1u);
+	for (;;) {
+		/* leftmost strict minimum (:232-240) */
+		int32_t mr = JTK_RANK_MAX;
+		int mi = -1;
+		for (uint32_t m = alive; m;) {
+#if defined(__CUDA_ARCH__)
+			int k = __ffs((int) m) - 1;
+#else
+			int k = __builtin_ctz(m);
+#endif
+			m &= m - 1;
+			int32_t r = rk[k];
+			if (r < mr) {
+				mr = r;
+				mi = k;
+			}
+		}
+		if (mi < 0) break; /* :247,260-262 */
+		const uint32_t above = alive & ~((2u << mi) - 1u); /* parts after mi */
+#if defined(__CUDA_ARCH__)
+		const int nx = __ffs((int) above) - 1;
+#else
+		const int nx = __builtin_ctz(above);
+#endif
+		const uint32_t above2 = above & (above - 1);
+		const uint32_t below = alive & ((1u << mi) - 1u);
+		tok[mi] = mr; /* rank == id of the merged token */
+		alive &= ~(1u << nx);
+		rk[nx] = JTK_RANK_MAX;
+		if (above2) {
+#if defined(__CUDA_ARCH__)
+			const int nn = __ffs((int) above2) - 1;
+#else
+			const int nn = __builtin_ctz(above2);
+#endif
+			rk[mi] = jtk_lookup_pair(T, mr, tok[nn]); /* :254 */
+		} else {
+			rk[mi] = JTK_RANK_MAX;
+		}
+		if (below) {
+#if defined(__CUDA_ARCH__)
+			const int pv = 31 - __clz((int) below);
+#else
+			const int pv = 31 - __builtin_clz(below);
+#endif
+			rk[pv] = jtk_lookup_pair(T, tok[pv], mr); /* :255-257 */
+		}
+	}
+	int cnt = 0;
+	for (uint32_t m = alive; m;) {
+#if defined(__CUDA_ARCH__)
+		int k = __ffs((int) m) - 1;
+#else
+		int k = __builtin_ctz(m);
+#endif
+		m &= m - 1;
+		int32_t t = tok[k];
+		if (t < JTK_PSEUDO_BASE + 256) *unknown = true;
+		tok[cnt++] = t;
+	}
+	return cnt;
+}
+
+/* Sequential bytePairMerge for any length (used by the host-side emulator for pieces the device handles
+ * with the warp-cooperative loop); nxt is an n+1 scratch array. */
+JTK_HD int jtk_merge_seq(const jtk_tables &T, const uint8_t *p, int n, int32_t *tok, int32_t *rk, int32_t *nxt, bool *unknown) {
+	for (int k = 0; k < n; k++) {
+		tok[k] = T.byte_id[p[k]];
+		rk[k] = (k + 1 < n) ? T.bytepair[((uint32_t) p[k] << 8) | p[k + 1]] : JTK_RANK_MAX;
+		nxt[k] = k + 1;
+	}
+	for (;;) {
+		int32_t mr = JTK_RANK_MAX;
+		int mi = -1, pv = -1, mpv = -1;
+		for (int k = 0; k < n; pv = k, k = nxt[k])
+			if (rk[k] < mr) {
+				mr = rk[k];
+				mi = k;
+				mpv = pv;
+			}
+		if (mi < 0) break;
+		int nx = nxt[mi], nn = nxt[nx];
+		tok[mi] = mr;
+		nxt[mi] = nn;
+		rk[mi] = (nn < n) ? jtk_lookup_pair(T, mr, tok[nn]) : JTK_RANK_MAX;
+		if (mpv >= 0) rk[mpv] = jtk_lookup_pair(T, tok[mpv], mr);
+	}
+	int cnt = 0;
+	for (int k = 0; k < n;) {
+		int32_t t = tok[k];
+		int nk = nxt[k];
+		if (t < JTK_PSEUDO_BASE + 256) *unknown = true;
+		tok[cnt++] = t;
+		k = nk;
+	}
+	return cnt;
+}
+
+#endif /* JTK_DEVICE_CUH */

@@ -1,0 +1,87 @@
+/*
+ * Kernel-side declarations shared between jtk_kernels.cu and the C ABI implementation.
+ */
+#ifndef JTK_KERNELS_CUH
+#define JTK_KERNELS_CUH
+
+#include <cuda_runtime.h>
+
+#include "jtk_common.h"
+
+/* A piece longer than JTK_LONG_PIECE bytes, deferred by the tile kernel. */
+struct jtk_long_piece {
+	int64_t start;     /* global byte position */
+	int64_t end;       /* filled by jtk_long_bounds_kernel */
+	int64_t insert_at; /* index in the tile kernel's id stream where its tokens belong */
+	int64_t count;     /* tokens produced by the long-piece kernel */
+	int64_t scratch;   /* offset of its scratch area (in parts) */
+	int32_t doc;       /* unused by the kernels; for diagnostics */
+	int32_t flags;
+};
+
+/* Header read back by the host after a batch. */
+struct jtk_batch_header {
+	unsigned long long total_tokens;
+	unsigned int n_long;
+	unsigned int overflow;   /* ids capacity exceeded */
+	unsigned int ticket;     /* tile ticket counter */
+	unsigned int long_next;  /* work counter of the long-piece kernel */
+	unsigned int violations; /* long-piece rounds that had to fall back to one-merge-at-a-time */
+	unsigned int pad;
+};
+
+struct jtk_encode_args {
+	jtk_tables T;
+	const uint8_t *bytes;
+	int64_t total;
+	const int64_t *doc_off;
+	int64_t ndocs;
+	const int32_t *tile_first_doc;
+	int64_t ntiles;
+	unsigned long long *desc; /* chained-scan descriptors, one per tile */
+	jtk_batch_header *hdr;
+	int32_t *ids;
+	int64_t ids_cap;
+	int64_t *tok_off;
+	int32_t *doc_status;
+	uint32_t flags;
+	jtk_long_piece *long_list;
+	int64_t long_cap;
+	int64_t *tile_first_b; /* per tile: first piece start in the tile (global position) or -1 */
+	uint8_t *piece_flags;  /* debug: one byte per input byte, 1 where a piece starts (nullable) */
+};
+
+#define JTK_SMEM_BYTES                                                                                                              \
+	(2 * (JTK_REGION + 16) + 2 * 4 * (((JTK_REGION + 32) / 32 + 1)) + 2 * 4 * (JTK_TILE + JTK_FWD_HALO) + 2 * ((JTK_TILE + JTK_FWD_HALO) / 2) + \
+	 4 * JTK_NT + 256)
+
+cudaError_t jtk_launch_tile_first_doc(const int64_t *doc_off, int64_t ndocs, int64_t ntiles, int32_t *out, cudaStream_t st);
+cudaError_t jtk_launch_encode_tiles(const jtk_encode_args &a, int num_sms, cudaStream_t st);
+cudaError_t jtk_launch_finalize(const jtk_encode_args &a, cudaStream_t st);
+cudaError_t jtk_encode_kernel_setup();
+
+/* long-piece path */
+cudaError_t jtk_launch_long_bounds(const jtk_encode_args &a, unsigned int n_long, cudaStream_t st);
+cudaError_t jtk_launch_long_merge(const jtk_encode_args &a, unsigned int n_long, int32_t *scr_tok, int32_t *scr_rk, int32_t *scr_nxt, int32_t *scr_prv,
+                                  int num_sms, cudaStream_t st);
+cudaError_t jtk_launch_long_insert(const jtk_encode_args &a, unsigned int n_long, const int32_t *scr_tok, const int32_t *ids_in, int32_t *ids_out,
+                                   int64_t total_in, cudaStream_t st);
+cudaError_t jtk_launch_long_fix_offsets(const jtk_encode_args &a, unsigned int n_long, cudaStream_t st);
+
+/* decode path */
+struct jtk_decode_args {
+	jtk_tables T;
+	const int32_t *ids;
+	int64_t nids;
+	const int64_t *tok_off;
+	int64_t ndocs;
+	int64_t *id_byte_off; /* nids + 1: exclusive scan of token byte lengths */
+	uint8_t *out;
+	int64_t *byte_off; /* ndocs + 1 */
+	int32_t *doc_status;
+	int32_t *bad_ids;
+};
+cudaError_t jtk_launch_decode_lengths(const jtk_decode_args &a, cudaStream_t st);
+cudaError_t jtk_launch_decode_gather(const jtk_decode_args &a, cudaStream_t st);
+
+#endif

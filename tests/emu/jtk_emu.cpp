@@ -1,0 +1,171 @@
+/*
+ * TEST INFRASTRUCTURE ONLY: a host-side emulator of the tile kernel's per-tile logic.
+ * It drives the very same __host__ __device__ building blocks (jtk_device.cuh) that the CUDA kernel
+ * uses - region set-up, classification, split rules, table lookups, thread-level merge - tile by tile
+ * on the CPU, so the split rules and the halo / carry logic can be fuzzed against the oracle without a
+ * GPU.  It is compiled with tiny tiles (see tests/emu/Makefile) to hit tile edges constantly.
+ * The product never links this file.
+ */
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../jtokkit_b200/csrc/jtk_device.cuh"
+#include "../../jtokkit_b200/csrc/jtk_tables.h"
+
+struct emu_encoding {
+	jtk_host_tables host;
+	jtk_tables view;
+};
+
+extern "C" {
+
+emu_encoding *emu_create(const jtk_params *p, char *err, int errlen) {
+	emu_encoding *e = new emu_encoding();
+	std::string msg;
+	int rc = jtk_build_host_tables(p, &e->host, &msg);
+	if (rc != JTK_OK) {
+		snprintf(err, (size_t) errlen, "%d: %s", rc, msg.c_str());
+		delete e;
+		return nullptr;
+	}
+	e->view = jtk_host_view(e->host);
+	return e;
+}
+
+void emu_destroy(emu_encoding *e) { delete e; }
+
+int emu_tile() { return JTK_TILE; }
+
+/* stats for tests: table sizes and probe lengths */
+void emu_stats(const emu_encoding *e, int64_t *out) {
+	out[0] = e->host.n_tokens;
+	out[1] = e->host.n_pairs;
+	out[2] = e->host.max_probe_a;
+	out[3] = e->host.max_probe_b;
+	out[4] = e->host.max_probe_p;
+	out[5] = (int64_t) e->host.cp_stage2.size() / 256;
+	out[6] = e->host.max_token_len;
+}
+
+struct emu_tile_state {
+	std::vector<uint8_t> sb, cls;
+	std::vector<uint32_t> bmask, dmask;
+	std::vector<int32_t> tok, rk;
+	jtk_tile_ctx c;
+	emu_tile_state() : sb(JTK_REGION + 16), cls(JTK_REGION + 16), bmask(JTK_MASK_WORDS), dmask(JTK_MASK_WORDS), tok(JTK_TILE + JTK_FWD_HALO), rk(JTK_TILE + JTK_FWD_HALO) {
+		c.sb = sb.data();
+		c.cls = cls.data();
+		c.bmask = bmask.data();
+		c.dmask = dmask.data();
+		c.tok = tok.data();
+		c.rk = rk.data();
+	}
+	/* the kernel's phases P1-P3 for one tile */
+	void run(int64_t tile) {
+		c.g0 = tile * JTK_TILE - JTK_BACK_HALO;
+		c.rs = 0;
+		c.carry_n = 0;
+		std::fill(bmask.begin(), bmask.end(), 0u);
+		std::fill(dmask.begin(), dmask.end(), 0u);
+		for (int ch = 0; ch <= JTK_REGION_CHUNKS; ch++) jtk_load_chunk(c, ch);
+		int64_t first_doc = 0;
+		while (first_doc <= c.ndocs && c.doc_off[first_doc] < c.g0) first_doc++;
+		for (int t = 0; t < JTK_NT; t++) jtk_mark_docstarts(c, first_doc, t, JTK_NT);
+		c.rs = jtk_region_first(c);
+		for (int ch = 0; ch <= JTK_REGION_CHUNKS; ch++) jtk_classify_chunk(c, ch);
+		c.carry_n = jtk_region_carry_n(c);
+		for (int ch = JTK_BACK_HALO / 16; ch < JTK_REGION_CHUNKS; ch++) ((uint16_t *) bmask.data())[ch] = (uint16_t) jtk_boundary_chunk(c, ch);
+	}
+	bool bit(int r) const { return (bmask[(size_t) (r >> 5)] >> (r & 31)) & 1u; }
+};
+
+/*
+ * Runs every tile.  Pass 1 computes the piece-start flags tile by tile (region set-up, classification,
+ * carries, split rules - exactly the kernel's phases P1-P3) and checks that the flags a tile computes for its
+ * forward halo agree with the owner tile's; pass 2 encodes every piece with the kernel's lookup and merge
+ * functions.  piece_flags / ids / tok_off / status are nullable.  Returns the token count, or a negative
+ * number when a halo view disagrees with the owner tile.
+ */
+int64_t emu_run(const emu_encoding *e, const uint8_t *bytes, int64_t total, const int64_t *doc_off, int64_t ndocs, uint32_t flags,
+                uint8_t *piece_flags, int32_t *ids, int64_t *tok_off, int32_t *status) {
+	std::vector<uint8_t> in((size_t) total + 64, 0); /* 16-byte aligned copy of the input, as the device buffer is */
+	if (total) memcpy(in.data(), bytes, (size_t) total);
+	std::vector<uint8_t> start((size_t) total + 1, 0), halo((size_t) total + 1, 2);
+	const int64_t ntiles = (total + JTK_TILE - 1) / JTK_TILE;
+	emu_tile_state t;
+	t.c.total = total;
+	t.c.gbytes = in.data();
+	t.c.doc_off = doc_off;
+	t.c.ndocs = ndocs;
+	t.c.T = &e->view;
+	int64_t halo_mismatch = 0;
+	for (int64_t tile = 0; tile < ntiles; tile++) {
+		t.run(tile);
+		for (int r = JTK_BACK_HALO; r < JTK_BACK_HALO + JTK_TILE + JTK_LONG_PIECE + 1; r++) {
+			const int64_t g = t.c.g0 + r;
+			if (g >= total) break;
+			const uint8_t b = t.bit(r) ? 1 : 0;
+			if (r < JTK_BACK_HALO + JTK_TILE) {
+				start[(size_t) g] = b;
+				if (halo[(size_t) g] != 2 && halo[(size_t) g] != b) halo_mismatch++;
+			} else if (halo[(size_t) g] == 2) {
+				halo[(size_t) g] = b;
+			} else if (halo[(size_t) g] != b) {
+				halo_mismatch++;
+			}
+		}
+	}
+	if (halo_mismatch) return -1000000 - halo_mismatch;
+	start[(size_t) total] = 1;
+	if (piece_flags)
+		for (int64_t g = 0; g < total; g++) piece_flags[g] = start[(size_t) g];
+
+	int64_t out_pos = 0, next_doc = 0;
+	t.c.g0 = 0;
+	for (int64_t g = 0; g < total; g++) {
+		if ((flags & JTK_CHECK_SPECIAL) && status) {
+			uint8_t by = in[(size_t) g];
+			if ((e->view.special_first[by >> 5] >> (by & 31)) & 1u) {
+				int64_t hi = jtk_doc_ceil(t.c, g);
+				if (jtk_special_at(e->view, in.data(), g, hi)) {
+					int64_t d = 0;
+					while (d + 1 <= ndocs && doc_off[d + 1] <= g) d++;
+					status[d] |= JTK_DOC_HAS_SPECIAL;
+				}
+			}
+		}
+		while (tok_off && next_doc <= ndocs && doc_off[next_doc] <= g) tok_off[next_doc++] = out_pos;
+		if (!start[(size_t) g] || !ids) continue;
+		int64_t eg = g + 1;
+		while (!start[(size_t) eg]) eg++;
+		const int64_t n = eg - g;
+		const uint8_t *p = in.data() + g;
+		bool unknown = false;
+		if (n == 1) {
+			int32_t id = e->view.byte_id[p[0]];
+			if (id < JTK_PSEUDO_BASE + 256) unknown = true;
+			ids[out_pos++] = id;
+		} else {
+			int32_t whole = jtk_lookup_piece(e->view, p, (int) n);
+			if (whole != JTK_RANK_MAX) {
+				ids[out_pos++] = whole;
+			} else {
+				std::vector<int32_t> t2((size_t) n), r2((size_t) n), nx((size_t) n + 1);
+				int cnt;
+				if (n <= JTK_SHORT_PIECE) cnt = jtk_merge_short(e->view, p, (int) n, t2.data(), r2.data(), &unknown);
+				else cnt = jtk_merge_seq(e->view, p, (int) n, t2.data(), r2.data(), nx.data(), &unknown);
+				for (int k = 0; k < cnt; k++) ids[out_pos++] = t2[(size_t) k];
+			}
+		}
+		if (unknown && status) {
+			int64_t d = 0;
+			while (d + 1 <= ndocs && doc_off[d + 1] <= g) d++;
+			status[d] |= JTK_DOC_UNKNOWN_BYTES;
+		}
+	}
+	while (tok_off && next_doc <= ndocs) tok_off[next_doc++] = out_pos;
+	return out_pos;
+}
+}

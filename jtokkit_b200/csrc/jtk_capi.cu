@@ -1,0 +1,1056 @@
+/*
+ * C ABI implementation (include/jtokkit_b200.h): registration, the device-resident batch call, the
+ * host-buffer batch call with chunked H2D / kernel / D2H pipelining and document sharding over devices.
+ * There is no CPU encode path in this file: every entry point ends in kernel launches.
+ */
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "jtk_kernels.cuh"
+#include "jtk_tables.h"
+
+/* ------------------------------------------------------------------ error plumbing */
+static thread_local std::string g_last_error;
+static int set_error(int code, const std::string &msg) {
+	g_last_error = msg;
+	return code;
+}
+#define CUDA_TRY(expr)                                                                                             \
+	do {                                                                                                           \
+		cudaError_t _e = (expr);                                                                                   \
+		if (_e != cudaSuccess) return set_error(JTK_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+	} while (0)
+
+extern "C" const char *jtk_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char *jtk_version(void) {
+	static const std::string v = std::string("jtokkit_b200 0.1 sm_100a unicode ") + jtk_unicode_version();
+	return v.c_str();
+}
+
+/* ------------------------------------------------------------------ per-device state */
+struct jtk_workspace {
+	/* sized for ntiles_cap tiles / long_cap long pieces */
+	int64_t ntiles_cap = 0, long_cap = 0;
+	int32_t *tile_first_doc = nullptr;
+	unsigned long long *desc = nullptr;
+	int64_t *tile_first_b = nullptr;
+	jtk_long_piece *long_list = nullptr;
+	jtk_batch_header *hdr = nullptr;      /* device */
+	jtk_batch_header *hdr_host = nullptr; /* pinned */
+	/* buffers of the host-buffer path */
+	int64_t in_cap = 0, docs_cap = 0;
+	uint8_t *d_in = nullptr;
+	int64_t *d_doc_off = nullptr;
+	int32_t *d_ids = nullptr;
+	int64_t *d_tok_off = nullptr;
+	int32_t *d_status = nullptr;
+	cudaStream_t stream = nullptr;
+};
+
+struct jtk_device_state {
+	int device = 0;
+	int num_sms = 0;
+	jtk_tables T;
+	std::vector<void *> allocs;
+	std::mutex mu;
+	std::vector<jtk_workspace *> free_ws;
+};
+
+struct jtk_pinned_buf {
+	void *p = nullptr;
+	int64_t cap = 0;
+};
+
+struct jtk_encoding {
+	std::string name;
+	jtk_host_tables host;
+	std::vector<jtk_device_state *> devs;
+	std::mutex pool_mu;
+	std::vector<jtk_pinned_buf> pinned_pool; /* result buffers returned by jtk_result_free */
+	int64_t chunk_bytes = 64ll << 20;
+};
+
+struct jtk_result {
+	jtk_encoding *enc = nullptr;
+	int64_t ndocs = 0, ntokens = 0, nbytes = 0;
+	jtk_pinned_buf ids, tok_off, status, bytes, byte_off, bad_ids;
+	double device_ms = 0;
+	int64_t launches = 0;
+};
+
+static int device_index(const jtk_encoding *e, int device) {
+	for (size_t i = 0; i < e->devs.size(); i++)
+		if (e->devs[i]->device == device) return (int) i;
+	return -1;
+}
+
+template <typename Tv>
+static int upload(jtk_device_state *ds, const std::vector<Tv> &v, const Tv **out) {
+	void *p = nullptr;
+	size_t bytes = std::max<size_t>(v.size() * sizeof(Tv), 16);
+	CUDA_TRY(cudaMalloc(&p, bytes));
+	ds->allocs.push_back(p);
+	if (!v.empty()) CUDA_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(Tv), cudaMemcpyHostToDevice));
+	*out = reinterpret_cast<const Tv *>(p);
+	return JTK_OK;
+}
+
+static int init_device(jtk_encoding *e, int device) {
+	jtk_device_state *ds = new jtk_device_state();
+	e->devs.push_back(ds);
+	ds->device = device;
+	CUDA_TRY(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10) return set_error(JTK_E_CUDA, "device is not sm_100-class (this library only carries sm_100a code)");
+	ds->num_sms = prop.multiProcessorCount;
+	const jtk_host_tables &h = e->host;
+	jtk_tables &T = ds->T;
+	memset(&T, 0, sizeof(T));
+	T.pattern_kind = h.pattern_kind;
+	T.max_token_len = h.max_token_len;
+	int rc;
+#define UP(field) \
+	if ((rc = upload(ds, h.field, &T.field)) != JTK_OK) return rc
+	UP(ascii_cls);
+	UP(cp_stage1);
+	UP(cp_stage2);
+	UP(tab_a);
+	UP(tab_b);
+	UP(tok_bytes);
+	UP(tok_off);
+	UP(byte_id);
+	UP(bytepair);
+	UP(pair);
+	UP(special_bytes);
+	UP(special_off);
+	UP(dec_keys);
+	UP(dec_bytes);
+	UP(dec_off);
+#undef UP
+	T.mask_a = h.mask_a;
+	T.mask_b = h.mask_b;
+	T.mask_p = h.mask_p;
+	T.mask_d = h.mask_d;
+	T.nspecial = h.nspecial;
+	T.special_has_empty = h.special_has_empty;
+	memcpy(T.special_first, h.special_first, sizeof(T.special_first));
+	CUDA_TRY(jtk_encode_kernel_setup());
+	return JTK_OK;
+}
+
+/* ------------------------------------------------------------------ registration */
+extern "C" int jtk_encoding_create(const jtk_params *params, const int *devices, int ndev, jtk_encoding **out) {
+	if (!params || !out) return set_error(JTK_E_ARG, "params / out is null");
+	*out = nullptr;
+	jtk_encoding *e = new jtk_encoding();
+	std::string err;
+	int rc = jtk_build_host_tables(params, &e->host, &err);
+	if (rc != JTK_OK) {
+		delete e;
+		return set_error(rc, err);
+	}
+	e->name = e->host.name;
+	if (const char *env = getenv("JTK_CHUNK_MB")) {
+		long mb = atol(env);
+		if (mb >= 1) e->chunk_bytes = (int64_t) mb << 20;
+	}
+	int count = 0;
+	cudaError_t ce = cudaGetDeviceCount(&count);
+	if (ce != cudaSuccess || count == 0) {
+		delete e;
+		return set_error(JTK_E_CUDA, std::string("no CUDA device: ") + (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0") +
+		                                 " (jtokkit_b200 has no CPU fallback)");
+	}
+	std::vector<int> devs;
+	if (!devices || ndev <= 0) devs.push_back(0);
+	else devs.assign(devices, devices + ndev);
+	for (int d : devs) {
+		if (d < 0 || d >= count) {
+			jtk_encoding_destroy(e);
+			return set_error(JTK_E_ARG, "device index out of range");
+		}
+		rc = init_device(e, d);
+		if (rc != JTK_OK) {
+			std::string keep = g_last_error;
+			jtk_encoding_destroy(e);
+			return set_error(rc, keep);
+		}
+	}
+	*out = e;
+	return JTK_OK;
+}
+
+extern "C" int jtk_encoding_create_builtin(const char *name, const char *tiktoken_path, const int *devices, int ndev, jtk_encoding **out) {
+	if (!name || !tiktoken_path || !out) return set_error(JTK_E_ARG, "name / path / out is null");
+	const jtk_builtin_def *def = jtk_find_builtin(name);
+	if (!def) return set_error(JTK_E_ARG, std::string("unknown predefined encoding: ") + name);
+	std::vector<uint8_t> bytes;
+	std::vector<int64_t> off;
+	std::vector<int32_t> ranks;
+	std::string err;
+	int rc = jtk_load_tiktoken_file(tiktoken_path, &bytes, &off, &ranks, &err);
+	if (rc != JTK_OK) return set_error(rc, err);
+	std::vector<uint8_t> sb;
+	std::vector<int64_t> so(1, 0);
+	std::vector<int32_t> sid;
+	for (int i = 0; i < def->nspecial; i++) {
+		sb.insert(sb.end(), def->special[i], def->special[i] + strlen(def->special[i]));
+		so.push_back((int64_t) sb.size());
+		sid.push_back(def->special_ids[i]);
+	}
+	jtk_params p;
+	p.name = def->name;
+	p.pattern = def->pattern;
+	p.pattern_flags = JTK_RE_UNICODE_CHARACTER_CLASS; /* EncodingFactory.java:129 */
+	p.vocab_bytes = bytes.data();
+	p.vocab_off = off.data();
+	p.vocab_ranks = ranks.data();
+	p.vocab_size = (int64_t) ranks.size();
+	p.special_bytes = sb.data();
+	p.special_off = so.data();
+	p.special_ids = sid.data();
+	p.special_size = def->nspecial;
+	return jtk_encoding_create(&p, devices, ndev, out);
+}
+
+static void free_workspace(jtk_workspace *w) {
+	if (!w) return;
+	cudaFree(w->tile_first_doc);
+	cudaFree(w->desc);
+	cudaFree(w->tile_first_b);
+	cudaFree(w->long_list);
+	cudaFree(w->hdr);
+	cudaFreeHost(w->hdr_host);
+	cudaFree(w->d_in);
+	cudaFree(w->d_doc_off);
+	cudaFree(w->d_ids);
+	cudaFree(w->d_tok_off);
+	cudaFree(w->d_status);
+	if (w->stream) cudaStreamDestroy(w->stream);
+	delete w;
+}
+
+extern "C" void jtk_encoding_destroy(jtk_encoding *e) {
+	if (!e) return;
+	for (jtk_device_state *ds : e->devs) {
+		cudaSetDevice(ds->device);
+		for (jtk_workspace *w : ds->free_ws) free_workspace(w);
+		for (void *p : ds->allocs) cudaFree(p);
+		delete ds;
+	}
+	for (jtk_pinned_buf &b : e->pinned_pool) cudaFreeHost(b.p);
+	delete e;
+}
+
+extern "C" const char *jtk_encoding_name(const jtk_encoding *e) { return e ? e->name.c_str() : ""; }
+extern "C" int jtk_encoding_num_devices(const jtk_encoding *e) { return e ? (int) e->devs.size() : 0; }
+
+/* ------------------------------------------------------------------ workspaces */
+static jtk_workspace *acquire_ws(jtk_device_state *ds) {
+	std::lock_guard<std::mutex> lk(ds->mu);
+	if (!ds->free_ws.empty()) {
+		jtk_workspace *w = ds->free_ws.back();
+		ds->free_ws.pop_back();
+		return w;
+	}
+	return new jtk_workspace();
+}
+static void release_ws(jtk_device_state *ds, jtk_workspace *w) {
+	std::lock_guard<std::mutex> lk(ds->mu);
+	ds->free_ws.push_back(w);
+}
+
+static int ensure_ws_tiles(jtk_workspace *w, int64_t ntiles, int64_t long_cap) {
+	if (!w->hdr) {
+		CUDA_TRY(cudaMalloc(&w->hdr, sizeof(jtk_batch_header)));
+		CUDA_TRY(cudaHostAlloc(&w->hdr_host, sizeof(jtk_batch_header), cudaHostAllocDefault));
+	}
+	if (ntiles > w->ntiles_cap) {
+		cudaFree(w->tile_first_doc);
+		cudaFree(w->desc);
+		cudaFree(w->tile_first_b);
+		w->tile_first_doc = nullptr;
+		w->desc = nullptr;
+		w->tile_first_b = nullptr;
+		w->ntiles_cap = 0;
+		int64_t cap = ntiles + ntiles / 4 + 16;
+		CUDA_TRY(cudaMalloc(&w->tile_first_doc, sizeof(int32_t) * cap));
+		CUDA_TRY(cudaMalloc(&w->desc, sizeof(unsigned long long) * cap));
+		CUDA_TRY(cudaMalloc(&w->tile_first_b, sizeof(int64_t) * cap));
+		w->ntiles_cap = cap;
+	}
+	if (long_cap > w->long_cap) {
+		cudaFree(w->long_list);
+		w->long_list = nullptr;
+		w->long_cap = 0;
+		int64_t cap = long_cap + long_cap / 4 + 16;
+		CUDA_TRY(cudaMalloc(&w->long_list, sizeof(jtk_long_piece) * cap));
+		w->long_cap = cap;
+	}
+	return JTK_OK;
+}
+
+/* ------------------------------------------------------------------ the device-resident batch */
+static int run_long_pieces(jtk_device_state *ds, jtk_workspace *w, jtk_encode_args &a, unsigned n_long, cudaStream_t st, jtk_device_info *info) {
+	CUDA_TRY(jtk_launch_long_bounds(a, n_long, st));
+	std::vector<jtk_long_piece> list(n_long);
+	CUDA_TRY(cudaMemcpyAsync(list.data(), a.long_list, sizeof(jtk_long_piece) * n_long, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	std::sort(list.begin(), list.end(), [](const jtk_long_piece &x, const jtk_long_piece &y) { return x.start < y.start; });
+	int64_t parts = 0;
+	for (jtk_long_piece &lp : list) {
+		lp.scratch = parts;
+		parts += lp.end - lp.start;
+		if (lp.end - lp.start > 0x7ffffff0ll) return set_error(JTK_E_ARG, "a single piece exceeds 2 GiB");
+	}
+	int32_t *scr = nullptr;
+	CUDA_TRY(cudaMalloc(&scr, sizeof(int32_t) * 4 * (size_t) parts));
+	int32_t *scr_tok = scr, *scr_rk = scr + parts, *scr_nxt = scr + 2 * parts, *scr_prv = scr + 3 * parts;
+	int rc = JTK_OK;
+	int64_t *d_cum = nullptr;
+	int32_t *ids2 = nullptr;
+	do {
+		cudaError_t ce;
+#define LTRY(expr)                                                                              \
+	if ((ce = (expr)) != cudaSuccess) {                                                         \
+		rc = set_error(JTK_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(ce));        \
+		break;                                                                                  \
+	}
+		LTRY(cudaMemcpyAsync(a.long_list, list.data(), sizeof(jtk_long_piece) * n_long, cudaMemcpyHostToDevice, st));
+		LTRY(jtk_launch_long_merge(a, n_long, scr_tok, scr_rk, scr_nxt, scr_prv, ds->num_sms, st));
+		LTRY(cudaMemcpyAsync(list.data(), a.long_list, sizeof(jtk_long_piece) * n_long, cudaMemcpyDeviceToHost, st));
+		LTRY(cudaMemcpyAsync(w->hdr_host, a.hdr, sizeof(jtk_batch_header), cudaMemcpyDeviceToHost, st));
+		LTRY(cudaStreamSynchronize(st));
+		std::vector<int64_t> cum(n_long + 1, 0);
+		for (unsigned i = 0; i < n_long; i++) cum[i + 1] = cum[i] + list[i].count;
+		const int64_t total_in = info->num_tokens, total_out = total_in + cum[n_long];
+		LTRY(cudaMalloc(&d_cum, sizeof(int64_t) * (n_long + 1)));
+		LTRY(cudaMemcpyAsync(d_cum, cum.data(), sizeof(int64_t) * (n_long + 1), cudaMemcpyHostToDevice, st));
+		if (!(a.flags & JTK_COUNT_ONLY) && a.ids) {
+			if (total_out > a.ids_cap) {
+				rc = set_error(JTK_E_CAPACITY, "ids buffer too small");
+				break;
+			}
+			LTRY(cudaMalloc(&ids2, sizeof(int32_t) * (size_t) std::max<int64_t>(total_out, 1)));
+			LTRY(jtk_launch_long_insert(a.long_list, d_cum, n_long, scr_tok, a.ids, ids2, total_in, st));
+			LTRY(cudaMemcpyAsync(a.ids, ids2, sizeof(int32_t) * (size_t) total_out, cudaMemcpyDeviceToDevice, st));
+			info->gpu_launches += 1;
+		}
+		if (a.tok_off) {
+			LTRY(jtk_launch_long_fix_offsets(a.long_list, d_cum, n_long, a.doc_off, a.ndocs, a.tok_off, st));
+			info->gpu_launches += 1;
+		}
+		LTRY(cudaStreamSynchronize(st));
+		info->num_tokens = total_out;
+		info->gpu_launches += 2;
+		info->reserved = (int32_t) w->hdr_host->violations;
+#undef LTRY
+	} while (0);
+	cudaFree(scr);
+	cudaFree(d_cum);
+	cudaFree(ids2);
+	return rc;
+}
+
+static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspace *w, const uint8_t *d_utf8, int64_t nbytes, const int64_t *d_doc_off,
+                              int64_t ndocs, uint32_t flags, int32_t *d_ids, int64_t ids_capacity, int64_t *d_tok_off, int32_t *d_doc_status,
+                              uint8_t *d_piece_flags, cudaStream_t st, jtk_device_info *info, bool sync_and_long) {
+	(void) e;
+	if (nbytes < 0 || ndocs < 0) return set_error(JTK_E_ARG, "negative size");
+	if ((reinterpret_cast<uintptr_t>(d_utf8) & 15) != 0) return set_error(JTK_E_ARG, "d_utf8 must be 16-byte aligned");
+	const int64_t ntiles = (nbytes + JTK_TILE - 1) / JTK_TILE;
+	const int64_t long_cap = nbytes / (JTK_LONG_PIECE + 1) + 1;
+	int rc = ensure_ws_tiles(w, ntiles, long_cap);
+	if (rc != JTK_OK) return rc;
+	jtk_encode_args a;
+	memset(&a, 0, sizeof(a));
+	a.T = ds->T;
+	a.bytes = d_utf8;
+	a.total = nbytes;
+	a.doc_off = d_doc_off;
+	a.ndocs = ndocs;
+	a.tile_first_doc = w->tile_first_doc;
+	a.ntiles = ntiles;
+	a.desc = w->desc;
+	a.hdr = w->hdr;
+	a.ids = d_ids;
+	a.ids_cap = ids_capacity;
+	a.tok_off = d_tok_off;
+	a.doc_status = d_doc_status;
+	a.flags = flags;
+	a.long_list = w->long_list;
+	a.long_cap = w->long_cap;
+	a.tile_first_b = w->tile_first_b;
+	a.piece_flags = d_piece_flags;
+	CUDA_TRY(cudaMemsetAsync(w->hdr, 0, sizeof(jtk_batch_header), st));
+	if (ntiles > 0) CUDA_TRY(cudaMemsetAsync(w->desc, 0, sizeof(unsigned long long) * ntiles, st));
+	CUDA_TRY(jtk_launch_tile_first_doc(d_doc_off, ndocs, ntiles, w->tile_first_doc, st));
+	CUDA_TRY(jtk_launch_encode_tiles(a, ds->num_sms, st));
+	CUDA_TRY(jtk_launch_finalize(a, st));
+	info->gpu_launches = (ntiles > 0 ? 2 : 0) + 1;
+	CUDA_TRY(cudaMemcpyAsync(w->hdr_host, w->hdr, sizeof(jtk_batch_header), cudaMemcpyDeviceToHost, st));
+	if (!sync_and_long) return JTK_OK;
+	CUDA_TRY(cudaStreamSynchronize(st));
+	info->num_tokens = (int64_t) w->hdr_host->total_tokens;
+	info->num_long_pieces = w->hdr_host->n_long;
+	info->reserved = 0;
+	if (w->hdr_host->overflow) return set_error(JTK_E_CAPACITY, "ids buffer too small");
+	if (w->hdr_host->n_long > 0) {
+		if ((int64_t) w->hdr_host->n_long > w->long_cap) return set_error(JTK_E_NOMEM, "long piece list overflow");
+		rc = run_long_pieces(ds, w, a, w->hdr_host->n_long, st, info);
+		if (rc != JTK_OK) return rc;
+	}
+	if ((flags & JTK_CHECK_SPECIAL) && ds->T.special_has_empty && d_doc_status && ndocs > 0) {
+		/* "".contains(...) is true for every text: flag every document (pathological registration) */
+		std::vector<int32_t> ones((size_t) ndocs, JTK_DOC_HAS_SPECIAL);
+		CUDA_TRY(cudaMemcpyAsync(d_doc_status, ones.data(), sizeof(int32_t) * ndocs, cudaMemcpyHostToDevice, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+	}
+	return JTK_OK;
+}
+
+extern "C" int jtk_encode_batch_device(jtk_encoding *e, int device, const uint8_t *d_utf8, int64_t nbytes, const int64_t *d_doc_off, int64_t ndocs,
+                                       uint32_t flags, int32_t *d_ids, int64_t ids_capacity, int64_t *d_tok_off, int32_t *d_doc_status,
+                                       void *cuda_stream, jtk_device_info *info) {
+	if (!e || !info || !d_doc_off || (nbytes > 0 && !d_utf8)) return set_error(JTK_E_ARG, "null argument");
+	int di = device_index(e, device);
+	if (di < 0) return set_error(JTK_E_ARG, "device is not one of the encoding's devices");
+	jtk_device_state *ds = e->devs[(size_t) di];
+	CUDA_TRY(cudaSetDevice(device));
+	jtk_workspace *w = acquire_ws(ds);
+	memset(info, 0, sizeof(*info));
+	int rc = encode_device_impl(e, ds, w, d_utf8, nbytes, d_doc_off, ndocs, flags, d_ids, ids_capacity, d_tok_off, d_doc_status, nullptr,
+	                            reinterpret_cast<cudaStream_t>(cuda_stream), info, true);
+	release_ws(ds, w);
+	return rc;
+}
+
+extern "C" int jtk_split_batch_device(jtk_encoding *e, int device, const uint8_t *d_utf8, int64_t nbytes, const int64_t *d_doc_off, int64_t ndocs,
+                                      uint8_t *d_piece_flags, void *cuda_stream) {
+	if (!e || !d_doc_off || !d_piece_flags || (nbytes > 0 && !d_utf8)) return set_error(JTK_E_ARG, "null argument");
+	int di = device_index(e, device);
+	if (di < 0) return set_error(JTK_E_ARG, "device is not one of the encoding's devices");
+	jtk_device_state *ds = e->devs[(size_t) di];
+	CUDA_TRY(cudaSetDevice(device));
+	jtk_workspace *w = acquire_ws(ds);
+	jtk_device_info info;
+	memset(&info, 0, sizeof(info));
+	int rc = encode_device_impl(e, ds, w, d_utf8, nbytes, d_doc_off, ndocs, JTK_COUNT_ONLY, nullptr, 0, nullptr, nullptr, d_piece_flags,
+	                            reinterpret_cast<cudaStream_t>(cuda_stream), &info, true);
+	release_ws(ds, w);
+	return rc;
+}
+
+/* ------------------------------------------------------------------ pinned buffer pool */
+static int pinned_get(jtk_encoding *e, int64_t bytes, jtk_pinned_buf *out) {
+	bytes = std::max<int64_t>(bytes, 64);
+	{
+		std::lock_guard<std::mutex> lk(e->pool_mu);
+		int best = -1;
+		for (size_t i = 0; i < e->pinned_pool.size(); i++)
+			if (e->pinned_pool[i].cap >= bytes && (best < 0 || e->pinned_pool[i].cap < e->pinned_pool[(size_t) best].cap)) best = (int) i;
+		if (best >= 0) {
+			*out = e->pinned_pool[(size_t) best];
+			e->pinned_pool.erase(e->pinned_pool.begin() + best);
+			return JTK_OK;
+		}
+	}
+	out->p = nullptr;
+	out->cap = bytes;
+	CUDA_TRY(cudaHostAlloc(&out->p, (size_t) bytes, cudaHostAllocPortable));
+	return JTK_OK;
+}
+static void pinned_put(jtk_encoding *e, jtk_pinned_buf &b) {
+	if (!b.p) return;
+	std::lock_guard<std::mutex> lk(e->pool_mu);
+	e->pinned_pool.push_back(b);
+	b.p = nullptr;
+	b.cap = 0;
+	/* keep the pool bounded: drop the smallest buffers beyond 12 entries */
+	while (e->pinned_pool.size() > 12) {
+		size_t m = 0;
+		for (size_t i = 1; i < e->pinned_pool.size(); i++)
+			if (e->pinned_pool[i].cap < e->pinned_pool[m].cap) m = i;
+		cudaFreeHost(e->pinned_pool[m].p);
+		e->pinned_pool.erase(e->pinned_pool.begin() + (long) m);
+	}
+}
+
+extern "C" void *jtk_host_alloc(int64_t nbytes) {
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, (size_t) std::max<int64_t>(nbytes, 64), cudaHostAllocPortable) != cudaSuccess) {
+		set_error(JTK_E_CUDA, "cudaHostAlloc failed");
+		return nullptr;
+	}
+	return p;
+}
+extern "C" void jtk_host_free(void *p) {
+	if (p) cudaFreeHost(p);
+}
+extern "C" void jtk_free(void *p) { free(p); }
+
+/* ------------------------------------------------------------------ the host-buffer batch */
+struct shard_job {
+	jtk_encoding *e;
+	jtk_device_state *ds;
+	const uint8_t *utf8;
+	const int64_t *doc_off;
+	int64_t d_begin, d_end; /* documents [d_begin, d_end) */
+	uint32_t flags;
+	/* outputs */
+	std::vector<int64_t> chunk_doc_begin, chunk_tokens;
+	jtk_pinned_buf ids;      /* this shard's ids */
+	int64_t ntokens = 0;
+	int64_t *tok_off_out;    /* points into the result's tok_off: entries d_begin .. d_end (shard-local, rebased later) */
+	int32_t *status_out;
+	double device_ms = 0;
+	int64_t launches = 0;
+	int rc = JTK_OK;
+	std::string err;
+};
+
+static int ensure_ws_io(jtk_workspace *w, int64_t nbytes, int64_t ndocs, bool want_ids) {
+	if (!w->stream) CUDA_TRY(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+	if (nbytes > w->in_cap) {
+		cudaFree(w->d_in);
+		cudaFree(w->d_ids);
+		w->d_in = nullptr;
+		w->d_ids = nullptr;
+		w->in_cap = 0;
+		int64_t cap = nbytes + nbytes / 8 + 4096;
+		CUDA_TRY(cudaMalloc(&w->d_in, (size_t) cap + 64));
+		w->in_cap = cap;
+	}
+	if (want_ids && !w->d_ids) CUDA_TRY(cudaMalloc(&w->d_ids, sizeof(int32_t) * (size_t) (w->in_cap + 16)));
+	if (ndocs > w->docs_cap) {
+		cudaFree(w->d_doc_off);
+		cudaFree(w->d_tok_off);
+		cudaFree(w->d_status);
+		w->d_doc_off = nullptr;
+		w->d_tok_off = nullptr;
+		w->d_status = nullptr;
+		w->docs_cap = 0;
+		int64_t cap = ndocs + ndocs / 8 + 1024;
+		CUDA_TRY(cudaMalloc(&w->d_doc_off, sizeof(int64_t) * (size_t) (cap + 1)));
+		CUDA_TRY(cudaMalloc(&w->d_tok_off, sizeof(int64_t) * (size_t) (cap + 1)));
+		CUDA_TRY(cudaMalloc(&w->d_status, sizeof(int32_t) * (size_t) (cap + 1)));
+		w->docs_cap = cap;
+	}
+	return JTK_OK;
+}
+
+/* One shard = one device.  Chunks of whole documents are pipelined over two workspaces (streams):
+ * while chunk k's ids travel device->host, chunk k+1 is already copied in and encoded. */
+static void run_shard(shard_job *job) {
+	jtk_encoding *e = job->e;
+	jtk_device_state *ds = job->ds;
+	auto fail = [&](int rc) {
+		job->rc = rc;
+		job->err = g_last_error;
+	};
+	if (cudaSetDevice(ds->device) != cudaSuccess) return fail(set_error(JTK_E_CUDA, "cudaSetDevice failed"));
+	const int64_t *off = job->doc_off;
+	const bool want_ids = !(job->flags & JTK_COUNT_ONLY);
+	/* chunk boundaries */
+	std::vector<int64_t> cb;
+	cb.push_back(job->d_begin);
+	while (cb.back() < job->d_end) {
+		int64_t d = cb.back();
+		const int64_t lim = off[d] + e->chunk_bytes;
+		int64_t hi = std::upper_bound(off + d + 1, off + job->d_end + 1, lim) - off - 1; /* last doc end <= lim */
+		if (hi <= d) hi = d + 1;                                                             /* a single oversized document */
+		cb.push_back(hi);
+	}
+	const size_t nchunks = cb.size() - 1;
+	const int64_t shard_bytes = off[job->d_end] - off[job->d_begin];
+	if (want_ids) {
+		/* expected ~0.23 tokens per byte; the pool buffer grows if a shard needs more */
+		int rc = pinned_get(e, sizeof(int32_t) * std::max<int64_t>(shard_bytes / 3 + 1024, 1024), &job->ids);
+		if (rc != JTK_OK) return fail(rc);
+	}
+	jtk_workspace *ws[2] = {acquire_ws(ds), acquire_ws(ds)};
+	cudaEvent_t ev0[2] = {nullptr, nullptr}, ev1[2] = {nullptr, nullptr};
+	std::vector<int64_t> rebase; /* per chunk: host-side doc_off copy rebased to the chunk */
+	std::vector<jtk_pinned_buf> stage_off(2);
+	int rc = JTK_OK;
+	jtk_device_info infos[2];
+	memset(infos, 0, sizeof(infos));
+	auto finish_chunk = [&](size_t k) -> int {
+		/* chunk k's kernels are queued on ws[k & 1]; wait for its header, run the long path if needed, copy out */
+		jtk_workspace *w = ws[k & 1];
+		const int64_t d0 = cb[k], d1 = cb[k + 1], nd = d1 - d0;
+		const int64_t cbytes = off[d1] - off[d0];
+		CUDA_TRY(cudaStreamSynchronize(w->stream));
+		float ms = 0;
+		cudaEventElapsedTime(&ms, ev0[k & 1], ev1[k & 1]);
+		job->device_ms += ms;
+		jtk_device_info &info = infos[k & 1];
+		info.num_tokens = (int64_t) w->hdr_host->total_tokens;
+		info.num_long_pieces = w->hdr_host->n_long;
+		if (w->hdr_host->overflow) return set_error(JTK_E_CAPACITY, "internal ids buffer too small");
+		if (w->hdr_host->n_long > 0) {
+			jtk_encode_args a;
+			memset(&a, 0, sizeof(a));
+			a.T = ds->T;
+			a.bytes = w->d_in;
+			a.total = cbytes;
+			a.doc_off = w->d_doc_off;
+			a.ndocs = nd;
+			a.ntiles = (cbytes + JTK_TILE - 1) / JTK_TILE;
+			a.tile_first_doc = w->tile_first_doc;
+			a.desc = w->desc;
+			a.hdr = w->hdr;
+			a.ids = want_ids ? w->d_ids : nullptr;
+			a.ids_cap = w->in_cap;
+			a.tok_off = w->d_tok_off;
+			a.doc_status = w->d_status;
+			a.flags = job->flags;
+			a.long_list = w->long_list;
+			a.long_cap = w->long_cap;
+			a.tile_first_b = w->tile_first_b;
+			cudaEvent_t l0, l1;
+			cudaEventCreate(&l0);
+			cudaEventCreate(&l1);
+			cudaEventRecord(l0, w->stream);
+			int r2 = run_long_pieces(ds, w, a, w->hdr_host->n_long, w->stream, &info);
+			cudaEventRecord(l1, w->stream);
+			cudaEventSynchronize(l1);
+			float lms = 0;
+			cudaEventElapsedTime(&lms, l0, l1);
+			job->device_ms += lms;
+			cudaEventDestroy(l0);
+			cudaEventDestroy(l1);
+			if (r2 != JTK_OK) return r2;
+		}
+		job->launches += info.gpu_launches;
+		const int64_t ntok = info.num_tokens;
+		if (want_ids) {
+			if ((job->ntokens + ntok) * (int64_t) sizeof(int32_t) > job->ids.cap) {
+				jtk_pinned_buf bigger;
+				int r2 = pinned_get(e, std::max<int64_t>((job->ntokens + ntok) * 4 * 3 / 2, job->ids.cap * 2), &bigger);
+				if (r2 != JTK_OK) return r2;
+				memcpy(bigger.p, job->ids.p, (size_t) job->ntokens * 4);
+				pinned_put(e, job->ids);
+				job->ids = bigger;
+			}
+			CUDA_TRY(cudaMemcpyAsync(static_cast<int32_t *>(job->ids.p) + job->ntokens, w->d_ids, sizeof(int32_t) * (size_t) ntok, cudaMemcpyDeviceToHost,
+			                         w->stream));
+		}
+		/* token offsets and statuses: to pinned staging, then rebased into the result on the host */
+		jtk_pinned_buf &so = stage_off[k & 1];
+		const int64_t need = (int64_t) sizeof(int64_t) * (nd + 1) + (int64_t) sizeof(int32_t) * (nd + 1);
+		if (so.cap < need) {
+			pinned_put(e, so);
+			int r2 = pinned_get(e, need + need / 4, &so);
+			if (r2 != JTK_OK) return r2;
+		}
+		int64_t *h_tok = static_cast<int64_t *>(so.p);
+		int32_t *h_st = reinterpret_cast<int32_t *>(h_tok + nd + 1);
+		CUDA_TRY(cudaMemcpyAsync(h_tok, w->d_tok_off, sizeof(int64_t) * (size_t) (nd + 1), cudaMemcpyDeviceToHost, w->stream));
+		if (nd > 0) CUDA_TRY(cudaMemcpyAsync(h_st, w->d_status, sizeof(int32_t) * (size_t) nd, cudaMemcpyDeviceToHost, w->stream));
+		CUDA_TRY(cudaStreamSynchronize(w->stream));
+		const int64_t base = job->ntokens;
+		for (int64_t i = 0; i < nd; i++) {
+			job->tok_off_out[d0 - job->d_begin + i] = h_tok[i] + base;
+			job->status_out[d0 - job->d_begin + i] = h_st[i];
+		}
+		job->ntokens += ntok;
+		job->tok_off_out[d1 - job->d_begin] = job->ntokens;
+		job->chunk_tokens.push_back(ntok);
+		return JTK_OK;
+	};
+	for (int i = 0; i < 2 && rc == JTK_OK; i++) {
+		if (cudaEventCreate(&ev0[i]) != cudaSuccess || cudaEventCreate(&ev1[i]) != cudaSuccess) rc = set_error(JTK_E_CUDA, "cudaEventCreate failed");
+	}
+	for (size_t k = 0; k < nchunks && rc == JTK_OK; k++) {
+		jtk_workspace *w = ws[k & 1];
+		const int64_t d0 = cb[k], d1 = cb[k + 1], nd = d1 - d0;
+		const int64_t b0 = off[d0], cbytes = off[d1] - b0;
+		rc = ensure_ws_io(w, cbytes, nd, want_ids);
+		if (rc != JTK_OK) break;
+		/* chunk-relative document offsets (the kernels require doc_off[0] == 0) */
+		rebase.resize((size_t) nd + 1);
+		for (int64_t i = 0; i <= nd; i++) rebase[(size_t) i] = off[d0 + i] - b0;
+		cudaError_t ce = cudaMemcpyAsync(w->d_doc_off, rebase.data(), sizeof(int64_t) * (size_t) (nd + 1), cudaMemcpyHostToDevice, w->stream);
+		if (ce == cudaSuccess) ce = cudaStreamSynchronize(w->stream); /* rebase is reused for the next chunk */
+		if (ce == cudaSuccess && cbytes > 0) ce = cudaMemcpyAsync(w->d_in, job->utf8 + b0, (size_t) cbytes, cudaMemcpyHostToDevice, w->stream);
+		if (ce == cudaSuccess && nd > 0) ce = cudaMemsetAsync(w->d_status, 0, sizeof(int32_t) * (size_t) nd, w->stream);
+		if (ce != cudaSuccess) {
+			rc = set_error(JTK_E_CUDA, std::string("H2D: ") + cudaGetErrorString(ce));
+			break;
+		}
+		cudaEventRecord(ev0[k & 1], w->stream);
+		rc = encode_device_impl(e, ds, w, w->d_in, cbytes, w->d_doc_off, nd, job->flags, want_ids ? w->d_ids : nullptr, w->in_cap, w->d_tok_off, w->d_status,
+		                        nullptr, w->stream, &infos[k & 1], false);
+		cudaEventRecord(ev1[k & 1], w->stream);
+		if (rc != JTK_OK) break;
+		if (k >= 1) rc = finish_chunk(k - 1);
+	}
+	if (rc == JTK_OK && nchunks >= 1) rc = finish_chunk(nchunks - 1);
+	if (nchunks == 0) job->tok_off_out[0] = 0;
+	for (int i = 0; i < 2; i++) {
+		if (ws[i]->stream) cudaStreamSynchronize(ws[i]->stream);
+		if (ev0[i]) cudaEventDestroy(ev0[i]);
+		if (ev1[i]) cudaEventDestroy(ev1[i]);
+		release_ws(ds, ws[i]);
+		pinned_put(e, stage_off[(size_t) i]);
+	}
+	if (rc != JTK_OK) fail(rc);
+}
+
+extern "C" int jtk_encode_batch(jtk_encoding *e, const uint8_t *utf8, const int64_t *doc_off, int64_t ndocs, uint32_t flags, jtk_result **out) {
+	if (!e || !doc_off || !out || ndocs < 0) return set_error(JTK_E_ARG, "null argument");
+	*out = nullptr;
+	if (doc_off[0] != 0) return set_error(JTK_E_ARG, "doc_off[0] must be 0");
+	for (int64_t d = 0; d < ndocs; d++)
+		if (doc_off[d + 1] < doc_off[d]) return set_error(JTK_E_ARG, "doc_off is not monotone");
+	const int64_t total = doc_off[ndocs];
+	if (total > 0 && !utf8) return set_error(JTK_E_ARG, "utf8 is null");
+	jtk_result *r = new jtk_result();
+	r->enc = e;
+	r->ndocs = ndocs;
+	int rc = pinned_get(e, sizeof(int64_t) * (ndocs + 1), &r->tok_off);
+	if (rc == JTK_OK) rc = pinned_get(e, sizeof(int32_t) * (ndocs + 1), &r->status);
+	if (rc != JTK_OK) {
+		jtk_result_free(r);
+		return rc;
+	}
+	/* byte-balanced contiguous document ranges, one per device */
+	const int G = (int) e->devs.size();
+	std::vector<shard_job> jobs((size_t) G);
+	std::vector<int64_t> cut((size_t) G + 1, 0);
+	for (int g = 1; g < G; g++) {
+		const int64_t target = total / G * g;
+		cut[(size_t) g] = std::max<int64_t>(cut[(size_t) g - 1], std::lower_bound(doc_off, doc_off + ndocs + 1, target) - doc_off);
+		if (cut[(size_t) g] > ndocs) cut[(size_t) g] = ndocs;
+	}
+	cut[(size_t) G] = ndocs;
+	std::vector<std::vector<int64_t>> shard_off((size_t) G);
+	std::vector<std::vector<int32_t>> shard_st((size_t) G);
+	for (int g = 0; g < G; g++) {
+		shard_job &j = jobs[(size_t) g];
+		j.e = e;
+		j.ds = e->devs[(size_t) g];
+		j.utf8 = utf8;
+		j.doc_off = doc_off;
+		j.d_begin = cut[(size_t) g];
+		j.d_end = cut[(size_t) g + 1];
+		j.flags = flags;
+		shard_off[(size_t) g].assign((size_t) (j.d_end - j.d_begin) + 1, 0);
+		shard_st[(size_t) g].assign((size_t) (j.d_end - j.d_begin) + 1, 0);
+		j.tok_off_out = shard_off[(size_t) g].data();
+		j.status_out = shard_st[(size_t) g].data();
+	}
+	if (G == 1) {
+		run_shard(&jobs[0]);
+	} else {
+		std::vector<std::thread> th;
+		for (int g = 0; g < G; g++) th.emplace_back(run_shard, &jobs[(size_t) g]);
+		for (auto &t : th) t.join();
+	}
+	for (int g = 0; g < G; g++)
+		if (jobs[(size_t) g].rc != JTK_OK) {
+			rc = jobs[(size_t) g].rc;
+			std::string msg = jobs[(size_t) g].err;
+			for (int k = 0; k < G; k++) pinned_put(e, jobs[(size_t) k].ids);
+			jtk_result_free(r);
+			return set_error(rc, msg);
+		}
+	/* the host only concatenates per-device arrays and rebases token offsets */
+	int64_t total_tokens = 0;
+	for (int g = 0; g < G; g++) total_tokens += jobs[(size_t) g].ntokens;
+	r->ntokens = total_tokens;
+	int64_t *tok_off = static_cast<int64_t *>(r->tok_off.p);
+	int32_t *status = static_cast<int32_t *>(r->status.p);
+	int64_t base = 0;
+	for (int g = 0; g < G; g++) {
+		shard_job &j = jobs[(size_t) g];
+		const int64_t nd = j.d_end - j.d_begin;
+		for (int64_t i = 0; i < nd; i++) {
+			tok_off[j.d_begin + i] = j.tok_off_out[i] + base;
+			status[j.d_begin + i] = j.status_out[i];
+		}
+		base += j.ntokens;
+		r->device_ms = std::max(r->device_ms, j.device_ms);
+		r->launches += j.launches;
+	}
+	tok_off[ndocs] = total_tokens;
+	if ((flags & JTK_CHECK_SPECIAL) && e->host.special_has_empty) /* "".contains(...) is true for every text */
+		for (int64_t d = 0; d < ndocs; d++) status[d] |= JTK_DOC_HAS_SPECIAL;
+	if (!(flags & JTK_COUNT_ONLY)) {
+		if (G == 1) {
+			r->ids = jobs[0].ids;
+			jobs[0].ids.p = nullptr;
+		} else {
+			rc = pinned_get(e, sizeof(int32_t) * std::max<int64_t>(total_tokens, 1), &r->ids);
+			if (rc != JTK_OK) {
+				for (int k = 0; k < G; k++) pinned_put(e, jobs[(size_t) k].ids);
+				jtk_result_free(r);
+				return rc;
+			}
+			int64_t pos = 0;
+			for (int g = 0; g < G; g++) {
+				memcpy(static_cast<int32_t *>(r->ids.p) + pos, jobs[(size_t) g].ids.p, sizeof(int32_t) * (size_t) jobs[(size_t) g].ntokens);
+				pos += jobs[(size_t) g].ntokens;
+				pinned_put(e, jobs[(size_t) g].ids);
+			}
+		}
+	}
+	*out = r;
+	return JTK_OK;
+}
+
+extern "C" int64_t jtk_result_num_docs(const jtk_result *r) { return r ? r->ndocs : 0; }
+extern "C" int64_t jtk_result_num_tokens(const jtk_result *r) { return r ? r->ntokens : 0; }
+extern "C" const int32_t *jtk_result_ids(const jtk_result *r) { return r ? static_cast<const int32_t *>(r->ids.p) : nullptr; }
+extern "C" const int64_t *jtk_result_token_offsets(const jtk_result *r) { return r ? static_cast<const int64_t *>(r->tok_off.p) : nullptr; }
+extern "C" const int32_t *jtk_result_doc_status(const jtk_result *r) { return r ? static_cast<const int32_t *>(r->status.p) : nullptr; }
+extern "C" double jtk_result_device_ms(const jtk_result *r) { return r ? r->device_ms : 0; }
+extern "C" int64_t jtk_result_gpu_launches(const jtk_result *r) { return r ? r->launches : 0; }
+extern "C" const uint8_t *jtk_result_bytes(const jtk_result *r) { return r ? static_cast<const uint8_t *>(r->bytes.p) : nullptr; }
+extern "C" const int64_t *jtk_result_byte_offsets(const jtk_result *r) { return r ? static_cast<const int64_t *>(r->byte_off.p) : nullptr; }
+extern "C" const int32_t *jtk_result_bad_ids(const jtk_result *r) { return r ? static_cast<const int32_t *>(r->bad_ids.p) : nullptr; }
+
+extern "C" void jtk_result_free(jtk_result *r) {
+	if (!r) return;
+	jtk_encoding *e = r->enc;
+	pinned_put(e, r->ids);
+	pinned_put(e, r->tok_off);
+	pinned_put(e, r->status);
+	pinned_put(e, r->bytes);
+	pinned_put(e, r->byte_off);
+	pinned_put(e, r->bad_ids);
+	delete r;
+}
+
+/* ------------------------------------------------------------------ decode */
+/* Runs the decode kernels on the encoding's first device.  On success *h_bytes (pinned) holds the bytes,
+ * h_id_off (optional, nids + 1) the byte offset of every token, r->byte_off / status / bad_ids per document. */
+static int decode_impl(jtk_encoding *e, const int32_t *ids, const int64_t *tok_off, int64_t ndocs, jtk_result *r, std::vector<int64_t> *h_id_off) {
+	jtk_device_state *ds = e->devs[0];
+	CUDA_TRY(cudaSetDevice(ds->device));
+	const int64_t nids = tok_off[ndocs];
+	if (tok_off[0] != 0) return set_error(JTK_E_ARG, "tok_off[0] must be 0");
+	for (int64_t d = 0; d < ndocs; d++)
+		if (tok_off[d + 1] < tok_off[d]) return set_error(JTK_E_ARG, "tok_off is not monotone");
+	cudaStream_t st;
+	CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+	int32_t *d_ids = nullptr, *d_idx = nullptr, *d_status = nullptr, *d_bad = nullptr;
+	int64_t *d_tok_off = nullptr, *d_id_off = nullptr, *d_sums = nullptr, *d_total = nullptr, *d_byte_off = nullptr;
+	unsigned long long *d_badpos = nullptr;
+	uint8_t *d_out = nullptr;
+	int rc = JTK_OK;
+	const int64_t nb = jtk_scan_blocks(nids + 1);
+	do {
+		cudaError_t ce;
+#define DTRY(expr)                                                                       \
+	if ((ce = (expr)) != cudaSuccess) {                                                  \
+		rc = set_error(JTK_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(ce)); \
+		break;                                                                           \
+	}
+		DTRY(cudaMalloc(&d_ids, sizeof(int32_t) * (size_t) std::max<int64_t>(nids, 1)));
+		DTRY(cudaMalloc(&d_idx, sizeof(int32_t) * (size_t) std::max<int64_t>(nids, 1)));
+		DTRY(cudaMalloc(&d_tok_off, sizeof(int64_t) * (size_t) (ndocs + 1)));
+		DTRY(cudaMalloc(&d_id_off, sizeof(int64_t) * (size_t) (nids + 1)));
+		DTRY(cudaMalloc(&d_sums, sizeof(int64_t) * (size_t) (nb + 1)));
+		DTRY(cudaMalloc(&d_total, sizeof(int64_t)));
+		DTRY(cudaMalloc(&d_byte_off, sizeof(int64_t) * (size_t) (ndocs + 1)));
+		DTRY(cudaMalloc(&d_status, sizeof(int32_t) * (size_t) (ndocs + 1)));
+		DTRY(cudaMalloc(&d_bad, sizeof(int32_t) * (size_t) (ndocs + 1)));
+		DTRY(cudaMalloc(&d_badpos, sizeof(unsigned long long) * (size_t) (ndocs + 1)));
+		if (nids > 0) DTRY(cudaMemcpyAsync(d_ids, ids, sizeof(int32_t) * (size_t) nids, cudaMemcpyHostToDevice, st));
+		DTRY(cudaMemcpyAsync(d_tok_off, tok_off, sizeof(int64_t) * (size_t) (ndocs + 1), cudaMemcpyHostToDevice, st));
+		DTRY(cudaMemsetAsync(d_badpos, 0xFF, sizeof(unsigned long long) * (size_t) (ndocs + 1), st));
+		DTRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t) * (size_t) (ndocs + 1), st));
+		DTRY(cudaMemsetAsync(d_id_off + nids, 0, sizeof(int64_t), st));
+		jtk_decode_args a;
+		memset(&a, 0, sizeof(a));
+		a.T = ds->T;
+		a.ids = d_ids;
+		a.nids = nids;
+		a.tok_off = d_tok_off;
+		a.ndocs = ndocs;
+		a.id_byte_off = d_id_off;
+		a.byte_off = d_byte_off;
+		a.doc_status = d_status;
+		a.bad_ids = d_bad;
+		DTRY(jtk_launch_decode_lengths(a, d_idx, d_badpos, d_sums, d_total, st));
+		int64_t total = 0;
+		DTRY(cudaMemcpyAsync(&total, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+		DTRY(cudaStreamSynchronize(st));
+		DTRY(cudaMalloc(&d_out, (size_t) std::max<int64_t>(total, 1)));
+		a.out = d_out;
+		DTRY(jtk_launch_decode_gather(a, d_idx, d_badpos, st));
+		r->nbytes = total;
+		r->launches = (nids > 0 ? 1 : 0) + 4;
+		if ((rc = pinned_get(e, total, &r->bytes)) != JTK_OK) break;
+		if ((rc = pinned_get(e, sizeof(int64_t) * (ndocs + 1), &r->byte_off)) != JTK_OK) break;
+		if ((rc = pinned_get(e, sizeof(int32_t) * (ndocs + 1), &r->status)) != JTK_OK) break;
+		if ((rc = pinned_get(e, sizeof(int32_t) * (ndocs + 1), &r->bad_ids)) != JTK_OK) break;
+		if (total > 0) DTRY(cudaMemcpyAsync(r->bytes.p, d_out, (size_t) total, cudaMemcpyDeviceToHost, st));
+		DTRY(cudaMemcpyAsync(r->byte_off.p, d_byte_off, sizeof(int64_t) * (size_t) (ndocs + 1), cudaMemcpyDeviceToHost, st));
+		DTRY(cudaMemcpyAsync(r->status.p, d_status, sizeof(int32_t) * (size_t) (ndocs + 1), cudaMemcpyDeviceToHost, st));
+		DTRY(cudaMemcpyAsync(r->bad_ids.p, d_bad, sizeof(int32_t) * (size_t) (ndocs + 1), cudaMemcpyDeviceToHost, st));
+		if (h_id_off) {
+			h_id_off->resize((size_t) nids + 1);
+			DTRY(cudaMemcpyAsync(h_id_off->data(), d_id_off, sizeof(int64_t) * (size_t) (nids + 1), cudaMemcpyDeviceToHost, st));
+		}
+		DTRY(cudaStreamSynchronize(st));
+#undef DTRY
+	} while (0);
+	cudaFree(d_ids);
+	cudaFree(d_idx);
+	cudaFree(d_tok_off);
+	cudaFree(d_id_off);
+	cudaFree(d_sums);
+	cudaFree(d_total);
+	cudaFree(d_byte_off);
+	cudaFree(d_status);
+	cudaFree(d_bad);
+	cudaFree(d_badpos);
+	cudaFree(d_out);
+	cudaStreamDestroy(st);
+	return rc;
+}
+
+extern "C" int jtk_decode_batch(jtk_encoding *e, const int32_t *ids, const int64_t *tok_off, int64_t ndocs, jtk_result **out) {
+	if (!e || !tok_off || !out || ndocs < 0) return set_error(JTK_E_ARG, "null argument");
+	*out = nullptr;
+	if (tok_off[ndocs] > 0 && !ids) return set_error(JTK_E_ARG, "ids is null");
+	jtk_result *r = new jtk_result();
+	r->enc = e;
+	r->ndocs = ndocs;
+	r->ntokens = tok_off[ndocs];
+	int rc = decode_impl(e, ids, tok_off, ndocs, r, nullptr);
+	if (rc != JTK_OK) {
+		std::string keep = g_last_error;
+		jtk_result_free(r);
+		return set_error(rc, keep);
+	}
+	*out = r;
+	return JTK_OK;
+}
+
+/* ------------------------------------------------------------------ encode(text, maxTokens) */
+/* new String(bytes, UTF_8) as the JDK decodes it: UTF-16 code units, one U+FFFD per malformed or truncated
+ * sequence (the JDK is not part of /root/reference; this is what String.startsWith in the reference's
+ * back-off loop, GptBytePairEncoding.java:90-100, compares).  In the JTokkit integration this loop runs in the
+ * Java shim with the JVM's own decoder; this C version serves non-JVM callers. */
+static void java_utf16(const uint8_t *src, int64_t sl, std::vector<uint16_t> *dst) {
+	dst->clear();
+	const uint16_t REPL = 0xFFFD;
+	auto nc = [](uint8_t b) { return (b & 0xC0) != 0x80; };
+	int64_t sp = 0;
+	while (sp < sl) {
+		uint8_t b1 = src[sp++];
+		if (b1 < 0x80) {
+			dst->push_back(b1);
+		} else if ((b1 & 0xE0) == 0xC0 && (b1 & 0x1E) != 0) {
+			if (sp >= sl) {
+				dst->push_back(REPL);
+				break;
+			}
+			uint8_t b2 = src[sp++];
+			if (nc(b2)) {
+				dst->push_back(REPL);
+				sp--;
+			} else dst->push_back((uint16_t) (((b1 & 0x1F) << 6) | (b2 & 0x3F)));
+		} else if ((b1 & 0xF0) == 0xE0) {
+			if (sp + 1 < sl) {
+				uint8_t b2 = src[sp], b3 = src[sp + 1];
+				if ((b1 == 0xE0 && (b2 & 0xE0) == 0x80) || nc(b2) || nc(b3)) {
+					dst->push_back(REPL);
+					sp += ((b1 == 0xE0 && (b2 & 0xE0) == 0x80) || nc(b2)) ? 0 : 1;
+				} else {
+					uint16_t c = (uint16_t) (((b1 & 0x0F) << 12) | ((b2 & 0x3F) << 6) | (b3 & 0x3F));
+					dst->push_back((c >= 0xD800 && c <= 0xDFFF) ? REPL : c);
+					sp += 2;
+				}
+				continue;
+			}
+			dst->push_back(REPL);
+			if (sp < sl && ((b1 == 0xE0 && (src[sp] & 0xE0) == 0x80) || nc(src[sp]))) continue;
+			break;
+		} else if ((b1 & 0xF8) == 0xF0) {
+			if (sp + 2 < sl) {
+				uint8_t b2 = src[sp], b3 = src[sp + 1], b4 = src[sp + 2];
+				uint32_t uc = ((uint32_t) (b1 & 0x07) << 18) | ((uint32_t) (b2 & 0x3F) << 12) | ((uint32_t) (b3 & 0x3F) << 6) | (b4 & 0x3F);
+				if (nc(b2) || nc(b3) || nc(b4) || uc < 0x10000 || uc > 0x10FFFF) {
+					dst->push_back(REPL);
+					if (b1 > 0xF4 || (b1 == 0xF0 && (b2 < 0x90 || b2 > 0xBF)) || (b1 == 0xF4 && (b2 & 0xF0) != 0x80) || nc(b2)) sp += 0;
+					else if (nc(b3)) sp += 1;
+					else sp += 2;
+				} else {
+					uc -= 0x10000;
+					dst->push_back((uint16_t) (0xD800 + (uc >> 10)));
+					dst->push_back((uint16_t) (0xDC00 + (uc & 0x3FF)));
+					sp += 3;
+				}
+				continue;
+			}
+			dst->push_back(REPL);
+			if (b1 > 0xF4 || (sp < sl && ((b1 == 0xF0 && (src[sp] < 0x90 || src[sp] > 0xBF)) || (b1 == 0xF4 && (src[sp] & 0xF0) != 0x80) || nc(src[sp])))) continue;
+			sp++;
+			if (sp < sl && nc(src[sp])) continue;
+			break;
+		} else {
+			dst->push_back(REPL);
+		}
+	}
+}
+
+extern "C" int jtk_encode_max_tokens(jtk_encoding *e, const uint8_t *utf8, int64_t nbytes, int32_t max_tokens, uint32_t flags, int32_t **ids,
+                                     int64_t *num_ids, int32_t *truncated, int32_t *doc_status) {
+	if (!e || !ids || !num_ids || !truncated || !doc_status || nbytes < 0 || (nbytes > 0 && !utf8)) return set_error(JTK_E_ARG, "null argument");
+	*ids = nullptr;
+	*num_ids = 0;
+	*truncated = 0;
+	*doc_status = 0;
+	/* full device encode (the reference stops the find loop early, :79; the first min(maxTokens, total) tokens are the same) */
+	const int64_t doc_off[2] = {0, nbytes};
+	jtk_result *r = nullptr;
+	int rc = jtk_encode_batch(e, utf8, doc_off, 1, flags & ~JTK_COUNT_ONLY, &r);
+	if (rc != JTK_OK) return rc;
+	*doc_status = jtk_result_doc_status(r)[0];
+	int64_t k = std::min<int64_t>(std::max<int32_t>(max_tokens, 0), jtk_result_num_tokens(r));
+	std::vector<int32_t> tok(jtk_result_ids(r), jtk_result_ids(r) + k);
+	jtk_result_free(r);
+	if (*doc_status & JTK_DOC_HAS_SPECIAL) return JTK_OK; /* the shim throws UnsupportedOperationException */
+	/* decode the clipped prefix once on the device; token byte offsets give every shorter prefix */
+	jtk_result dr;
+	dr.enc = e;
+	const int64_t tok_off[2] = {0, k};
+	std::vector<int64_t> id_off;
+	rc = decode_impl(e, tok.data(), tok_off, 1, &dr, &id_off);
+	std::vector<uint8_t> dbytes;
+	if (rc == JTK_OK) dbytes.assign(static_cast<uint8_t *>(dr.bytes.p), static_cast<uint8_t *>(dr.bytes.p) + dr.nbytes);
+	pinned_put(e, dr.bytes);
+	pinned_put(e, dr.byte_off);
+	pinned_put(e, dr.status);
+	pinned_put(e, dr.bad_ids);
+	if (rc != JTK_OK) return rc;
+	std::vector<uint16_t> t16, d16;
+	java_utf16(utf8, nbytes, &t16);
+	int64_t keep = 0;
+	for (int64_t drop = 0; drop <= k; drop++) { /* :90-100 */
+		java_utf16(dbytes.data(), id_off[(size_t) (k - drop)], &d16);
+		if (d16.size() <= t16.size() && std::equal(d16.begin(), d16.end(), t16.begin())) {
+			keep = k - drop;
+			*truncated = t16.size() > d16.size();
+			break;
+		}
+	}
+	*ids = static_cast<int32_t *>(malloc(sizeof(int32_t) * (size_t) std::max<int64_t>(keep, 1)));
+	if (!*ids) return set_error(JTK_E_NOMEM, "malloc failed");
+	memcpy(*ids, tok.data(), sizeof(int32_t) * (size_t) keep);
+	*num_ids = keep;
+	return JTK_OK;
+}

@@ -6,6 +6,7 @@
 
 #include <cuda_runtime.h>
 
+#include "../../include/jtokkit_b200.h"
 #include "jtk_common.h"
 
 /* A piece longer than JTK_LONG_PIECE bytes, deferred by the tile kernel. */
@@ -64,9 +65,11 @@ cudaError_t jtk_encode_kernel_setup();
 cudaError_t jtk_launch_long_bounds(const jtk_encode_args &a, unsigned int n_long, cudaStream_t st);
 cudaError_t jtk_launch_long_merge(const jtk_encode_args &a, unsigned int n_long, int32_t *scr_tok, int32_t *scr_rk, int32_t *scr_nxt, int32_t *scr_prv,
                                   int num_sms, cudaStream_t st);
-cudaError_t jtk_launch_long_insert(const jtk_encode_args &a, unsigned int n_long, const int32_t *scr_tok, const int32_t *ids_in, int32_t *ids_out,
-                                   int64_t total_in, cudaStream_t st);
-cudaError_t jtk_launch_long_fix_offsets(const jtk_encode_args &a, unsigned int n_long, cudaStream_t st);
+/* list: device copy sorted by start with scratch offsets filled; cum[i] = tokens of long pieces 0..i-1 (n_long + 1 entries) */
+cudaError_t jtk_launch_long_insert(const jtk_long_piece *list, const int64_t *cum, unsigned int n_long, const int32_t *scr_tok, const int32_t *ids_in,
+                                   int32_t *ids_out, int64_t total_in, cudaStream_t st);
+cudaError_t jtk_launch_long_fix_offsets(const jtk_long_piece *list, const int64_t *cum, unsigned int n_long, const int64_t *doc_off, int64_t ndocs,
+                                        int64_t *tok_off, cudaStream_t st);
 
 /* decode path */
 struct jtk_decode_args {
@@ -81,7 +84,11 @@ struct jtk_decode_args {
 	int32_t *doc_status;
 	int32_t *bad_ids;
 };
-cudaError_t jtk_launch_decode_lengths(const jtk_decode_args &a, cudaStream_t st);
-cudaError_t jtk_launch_decode_gather(const jtk_decode_args &a, cudaStream_t st);
+int64_t jtk_scan_blocks(int64_t n);
+/* tok_index: nids scratch; bad_pos: ndocs entries preset to ~0; block_sums: jtk_scan_blocks(nids + 1) scratch;
+ * total: device int64 receiving the byte count.  id_byte_off[nids] must be zero on entry. */
+cudaError_t jtk_launch_decode_lengths(const jtk_decode_args &a, int32_t *tok_index, unsigned long long *bad_pos, int64_t *block_sums, int64_t *total,
+                                      cudaStream_t st);
+cudaError_t jtk_launch_decode_gather(const jtk_decode_args &a, const int32_t *tok_index, const unsigned long long *bad_pos, cudaStream_t st);
 
 #endif

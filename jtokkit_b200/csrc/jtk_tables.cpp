@@ -25,6 +25,8 @@ static const jtk_builtin_def BUILTINS[] = {
      {100257, 100258, 100259, 100260, 100276}},
 };
 
+const char *jtk_unicode_version() { return JTK_UNICODE_VERSION; }
+
 const jtk_builtin_def *jtk_find_builtin(const char *name) {
 	for (const jtk_builtin_def &b : BUILTINS)
 		if (!strcmp(b.name, name)) return &b;
@@ -219,8 +221,8 @@ int jtk_build_host_tables(const jtk_params *p, jtk_host_tables *t, std::string *
 			return JTK_E_ARG;
 		}
 		int32_t rank = p->vocab_ranks[i];
-		if (rank == JTK_RANK_MAX || (rank >= JTK_PSEUDO_BASE && rank < JTK_PSEUDO_BASE + 256)) {
-			*err = "a rank equals Integer.MAX_VALUE or falls into the reserved range [INT_MIN, INT_MIN+255]";
+		if (rank >= JTK_RANK_MAX - 1 || (rank >= JTK_PSEUDO_BASE && rank < JTK_PSEUDO_BASE + 256)) {
+			*err = "a rank is >= Integer.MAX_VALUE - 1 or falls into the reserved range [INT_MIN, INT_MIN+255]";
 			return JTK_E_ARG;
 		}
 		std::string key((const char *) p->vocab_bytes + a, (size_t) (b - a));

@@ -67,4 +67,7 @@ struct jtk_builtin_def {
 };
 const jtk_builtin_def *jtk_find_builtin(const char *name);
 
+/* Unicode version of the generated class tables (unicode_ranges.inc). */
+const char *jtk_unicode_version();
+
 #endif

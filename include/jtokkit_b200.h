@@ -38,6 +38,7 @@ extern "C" {
 #define JTK_ENCODE_ORDINARY 0u /* encodeOrdinary: GptBytePairEncoding.java:61-64,71-103 */
 #define JTK_CHECK_SPECIAL 1u   /* encode: adds the special-token guard of encodeInternal, :47-59 */
 #define JTK_COUNT_ONLY 2u      /* countTokens / countTokensOrdinary, :121-129: token offsets only, no ids */
+#define JTK_TIME_KERNEL 0x100u /* device-resident call only: bracket the tile kernel with CUDA events (jtk_device_info.tile_kernel_ms) */
 
 /* java.util.regex.Pattern flag bits accepted in jtk_params.pattern_flags (EncodingFactory.java:129) */
 #define JTK_RE_CASE_INSENSITIVE 0x02
@@ -114,6 +115,7 @@ typedef struct jtk_device_info {
 	int64_t num_long_pieces; /* pieces longer than the in-tile limit, handled by the long-piece kernels */
 	int64_t gpu_launches;
 	int32_t reserved;
+	float tile_kernel_ms; /* duration of the dominant kernel (jtk_encode_tiles_kernel) when JTK_TIME_KERNEL is set, else 0 */
 } jtk_device_info;
 
 int jtk_encode_batch_device(jtk_encoding *enc, int device, const uint8_t *d_utf8, int64_t nbytes, const int64_t *d_doc_off, int64_t ndocs,

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "libjtokkit_b200.so")
 
 JTK_OK, JTK_E_ARG, JTK_E_CUDA, JTK_E_PATTERN_UNSUPPORTED, JTK_E_NOMEM, JTK_E_CAPACITY = 0, -1, -2, -3, -4, -5
 DOC_OK, DOC_HAS_SPECIAL, DOC_UNKNOWN_BYTES, DOC_UNKNOWN_ID = 0, 1, 2, 4
-ENCODE_ORDINARY, CHECK_SPECIAL, COUNT_ONLY = 0, 1, 2
+ENCODE_ORDINARY, CHECK_SPECIAL, COUNT_ONLY, TIME_KERNEL = 0, 1, 2, 0x100
 RE_CASE_INSENSITIVE, RE_UNICODE_CASE, RE_UNICODE_CHARACTER_CLASS = 0x02, 0x40, 0x100
 
 
@@ -22,7 +22,8 @@ class JtkParams(C.Structure):
 
 
 class JtkDeviceInfo(C.Structure):
-    _fields_ = [("num_tokens", C.c_int64), ("num_long_pieces", C.c_int64), ("gpu_launches", C.c_int64), ("reserved", C.c_int32)]
+    _fields_ = [("num_tokens", C.c_int64), ("num_long_pieces", C.c_int64), ("gpu_launches", C.c_int64), ("reserved", C.c_int32),
+                ("tile_kernel_ms", C.c_float)]
 
 
 # every symbol include/jtokkit_b200.h declares: (restype, argtypes)

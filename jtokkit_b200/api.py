@@ -185,6 +185,20 @@ class BatchResult:
         self.doc_status = doc_status
         self.device_ms = device_ms
         self.gpu_launches = gpu_launches
+        self._handle = None  # C result kept alive for zero-copy views (encode_packed(copy=False))
+
+    def close(self):
+        """Returns the pinned result buffers to the library (only needed for copy=False results)."""
+        if self._handle is not None:
+            h, self._handle = self._handle, None
+            self.ids = self.token_offsets = self.doc_status = None
+            _capi.lib().jtk_result_free(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def __len__(self):
         return self.token_offsets.size - 1
@@ -271,24 +285,43 @@ class Encoding:
         blob, off = pack_documents(texts)
         return self.encode_packed(blob, off, ordinary=ordinary, count_only=count_only)
 
-    def encode_packed(self, utf8, doc_off, ordinary=False, count_only=False):
-        """HOST arrays in, HOST arrays out; host<->device copies happen inside the C call."""
+    def encode_packed(self, utf8, doc_off, ordinary=False, count_only=False, copy=True):
+        """HOST arrays in, HOST arrays out; host<->device copies happen inside the C call.
+        copy=False returns views into the library's pinned result buffers (valid until BatchResult.close())."""
         utf8 = np.ascontiguousarray(utf8, dtype=np.uint8)
         doc_off = np.ascontiguousarray(doc_off, dtype=np.int64)
         flags = (0 if ordinary else _capi.CHECK_SPECIAL) | (_capi.COUNT_ONLY if count_only else 0)
         r = C.c_void_p()
         _capi.check(_capi.lib().jtk_encode_batch(self._h, _ptr(utf8), _ptr(doc_off), doc_off.size - 1, flags, C.byref(r)))
         L = _capi.lib()
-        try:
-            nd, nt = L.jtk_result_num_docs(r), L.jtk_result_num_tokens(r)
-            ids = None
-            if not count_only:
-                ids = np.ctypeslib.as_array(C.cast(L.jtk_result_ids(r), C.POINTER(C.c_int32)), shape=(max(nt, 1),))[:nt].copy()
-            tok_off = np.ctypeslib.as_array(C.cast(L.jtk_result_token_offsets(r), C.POINTER(C.c_int64)), shape=(nd + 1,)).copy()
-            status = np.ctypeslib.as_array(C.cast(L.jtk_result_doc_status(r), C.POINTER(C.c_int32)), shape=(max(nd, 1),))[:nd].copy()
-            return BatchResult(ids, tok_off, status, L.jtk_result_device_ms(r), L.jtk_result_gpu_launches(r))
-        finally:
+        nd, nt = L.jtk_result_num_docs(r), L.jtk_result_num_tokens(r)
+        ids = None
+        if not count_only:
+            ids = np.ctypeslib.as_array(C.cast(L.jtk_result_ids(r), C.POINTER(C.c_int32)), shape=(max(nt, 1),))[:nt]
+        tok_off = np.ctypeslib.as_array(C.cast(L.jtk_result_token_offsets(r), C.POINTER(C.c_int64)), shape=(nd + 1,))
+        status = np.ctypeslib.as_array(C.cast(L.jtk_result_doc_status(r), C.POINTER(C.c_int32)), shape=(max(nd, 1),))[:nd]
+        res = BatchResult(ids, tok_off, status, L.jtk_result_device_ms(r), L.jtk_result_gpu_launches(r))
+        if copy:
+            res.ids = None if ids is None else ids.copy()
+            res.token_offsets, res.doc_status = tok_off.copy(), status.copy()
             L.jtk_result_free(r)
+        else:
+            res._handle = r
+        return res
+
+    def encode_device(self, d_utf8, d_doc_off, d_ids, d_tok_off, d_status, ordinary=False, count_only=False, time_kernel=False, device=None):
+        """Device-resident batch: torch CUDA tensors in and out (uint8 bytes, int64 offsets, int32 ids, int64 token
+        offsets, int32 status), enqueued on torch's current stream.  Returns (num_tokens, num_long_pieces, gpu_launches,
+        tile_kernel_ms)."""
+        import torch
+        dev = d_utf8.device.index if device is None else device
+        flags = (0 if ordinary else _capi.CHECK_SPECIAL) | (_capi.COUNT_ONLY if count_only else 0) | (_capi.TIME_KERNEL if time_kernel else 0)
+        info = _capi.JtkDeviceInfo()
+        _capi.check(_capi.lib().jtk_encode_batch_device(
+            self._h, dev, d_utf8.data_ptr(), d_utf8.numel(), d_doc_off.data_ptr(), d_doc_off.numel() - 1, flags,
+            d_ids.data_ptr() if d_ids is not None else None, d_ids.numel() if d_ids is not None else 0, d_tok_off.data_ptr(),
+            d_status.data_ptr() if d_status is not None else None, torch.cuda.current_stream(dev).cuda_stream, C.byref(info)))
+        return info.num_tokens, info.num_long_pieces, info.gpu_launches, info.tile_kernel_ms
 
     def encode_ordinary_batch(self, texts):
         return self.encode_batch(texts, ordinary=True)

@@ -39,7 +39,10 @@ struct jtk_workspace {
 	/* sized for ntiles_cap tiles / long_cap long pieces */
 	int64_t ntiles_cap = 0, long_cap = 0;
 	int32_t *tile_first_doc = nullptr;
-	unsigned long long *desc = nullptr;
+	int32_t *tile_count = nullptr;
+	int64_t *tile_base = nullptr;
+	int32_t *stage = nullptr; /* tile-local token staging, ntiles * (JTK_TILE + JTK_FWD_HALO) */
+	int64_t stage_tiles = 0;
 	int64_t *tile_first_b = nullptr;
 	jtk_long_piece *long_list = nullptr;
 	jtk_batch_header *hdr = nullptr;      /* device */
@@ -75,6 +78,7 @@ struct jtk_encoding {
 	std::mutex pool_mu;
 	std::vector<jtk_pinned_buf> pinned_pool; /* result buffers returned by jtk_result_free */
 	int64_t chunk_bytes = 64ll << 20;
+	std::atomic<int64_t> tokens_per_kib{440}; /* running maximum of tokens per KiB seen, sizes the pinned result buffers */
 };
 
 struct jtk_result {
@@ -224,7 +228,9 @@ extern "C" int jtk_encoding_create_builtin(const char *name, const char *tiktoke
 static void free_workspace(jtk_workspace *w) {
 	if (!w) return;
 	cudaFree(w->tile_first_doc);
-	cudaFree(w->desc);
+	cudaFree(w->tile_count);
+	cudaFree(w->tile_base);
+	cudaFree(w->stage);
 	cudaFree(w->tile_first_b);
 	cudaFree(w->long_list);
 	cudaFree(w->hdr);
@@ -268,24 +274,35 @@ static void release_ws(jtk_device_state *ds, jtk_workspace *w) {
 	ds->free_ws.push_back(w);
 }
 
-static int ensure_ws_tiles(jtk_workspace *w, int64_t ntiles, int64_t long_cap) {
+static int ensure_ws_tiles(jtk_workspace *w, int64_t ntiles, int64_t long_cap, bool want_stage) {
 	if (!w->hdr) {
 		CUDA_TRY(cudaMalloc(&w->hdr, sizeof(jtk_batch_header)));
 		CUDA_TRY(cudaHostAlloc(&w->hdr_host, sizeof(jtk_batch_header), cudaHostAllocDefault));
 	}
 	if (ntiles > w->ntiles_cap) {
 		cudaFree(w->tile_first_doc);
-		cudaFree(w->desc);
+		cudaFree(w->tile_count);
+		cudaFree(w->tile_base);
 		cudaFree(w->tile_first_b);
 		w->tile_first_doc = nullptr;
-		w->desc = nullptr;
+		w->tile_count = nullptr;
+		w->tile_base = nullptr;
 		w->tile_first_b = nullptr;
 		w->ntiles_cap = 0;
 		int64_t cap = ntiles + ntiles / 4 + 16;
 		CUDA_TRY(cudaMalloc(&w->tile_first_doc, sizeof(int32_t) * cap));
-		CUDA_TRY(cudaMalloc(&w->desc, sizeof(unsigned long long) * cap));
+		CUDA_TRY(cudaMalloc(&w->tile_count, sizeof(int32_t) * cap));
+		CUDA_TRY(cudaMalloc(&w->tile_base, sizeof(int64_t) * (cap + 1)));
 		CUDA_TRY(cudaMalloc(&w->tile_first_b, sizeof(int64_t) * cap));
 		w->ntiles_cap = cap;
+	}
+	if (want_stage && ntiles > w->stage_tiles) {
+		cudaFree(w->stage);
+		w->stage = nullptr;
+		w->stage_tiles = 0;
+		int64_t cap = ntiles + ntiles / 8 + 4;
+		CUDA_TRY(cudaMalloc(&w->stage, sizeof(int32_t) * (size_t) cap * (JTK_TILE + JTK_FWD_HALO)));
+		w->stage_tiles = cap;
 	}
 	if (long_cap > w->long_cap) {
 		cudaFree(w->long_list);
@@ -368,7 +385,8 @@ static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspa
 	if ((reinterpret_cast<uintptr_t>(d_utf8) & 15) != 0) return set_error(JTK_E_ARG, "d_utf8 must be 16-byte aligned");
 	const int64_t ntiles = (nbytes + JTK_TILE - 1) / JTK_TILE;
 	const int64_t long_cap = nbytes / (JTK_LONG_PIECE + 1) + 1;
-	int rc = ensure_ws_tiles(w, ntiles, long_cap);
+	const bool want_stage = !(flags & JTK_COUNT_ONLY) && d_ids != nullptr;
+	int rc = ensure_ws_tiles(w, ntiles, long_cap, want_stage);
 	if (rc != JTK_OK) return rc;
 	jtk_encode_args a;
 	memset(&a, 0, sizeof(a));
@@ -379,7 +397,9 @@ static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspa
 	a.ndocs = ndocs;
 	a.tile_first_doc = w->tile_first_doc;
 	a.ntiles = ntiles;
-	a.desc = w->desc;
+	a.tile_count = w->tile_count;
+	a.tile_base = w->tile_base;
+	a.stage = want_stage ? w->stage : nullptr;
 	a.hdr = w->hdr;
 	a.ids = d_ids;
 	a.ids_cap = ids_capacity;
@@ -391,14 +411,26 @@ static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspa
 	a.tile_first_b = w->tile_first_b;
 	a.piece_flags = d_piece_flags;
 	CUDA_TRY(cudaMemsetAsync(w->hdr, 0, sizeof(jtk_batch_header), st));
-	if (ntiles > 0) CUDA_TRY(cudaMemsetAsync(w->desc, 0, sizeof(unsigned long long) * ntiles, st));
 	CUDA_TRY(jtk_launch_tile_first_doc(d_doc_off, ndocs, ntiles, w->tile_first_doc, st));
+	cudaEvent_t k0 = nullptr, k1 = nullptr;
+	const bool time_kernel = (flags & JTK_TIME_KERNEL) && sync_and_long;
+	if (time_kernel) {
+		CUDA_TRY(cudaEventCreate(&k0));
+		CUDA_TRY(cudaEventCreate(&k1));
+		CUDA_TRY(cudaEventRecord(k0, st));
+	}
 	CUDA_TRY(jtk_launch_encode_tiles(a, ds->num_sms, st));
-	CUDA_TRY(jtk_launch_finalize(a, st));
-	info->gpu_launches = (ntiles > 0 ? 2 : 0) + 1;
+	if (time_kernel) CUDA_TRY(cudaEventRecord(k1, st));
+	CUDA_TRY(jtk_launch_scan_gather(a, ds->num_sms, st));
+	info->gpu_launches = (ntiles > 0 ? 2 : 0) + 2;
 	CUDA_TRY(cudaMemcpyAsync(w->hdr_host, w->hdr, sizeof(jtk_batch_header), cudaMemcpyDeviceToHost, st));
 	if (!sync_and_long) return JTK_OK;
 	CUDA_TRY(cudaStreamSynchronize(st));
+	if (time_kernel) {
+		cudaEventElapsedTime(&info->tile_kernel_ms, k0, k1);
+		cudaEventDestroy(k0);
+		cudaEventDestroy(k1);
+	}
 	info->num_tokens = (int64_t) w->hdr_host->total_tokens;
 	info->num_long_pieces = w->hdr_host->n_long;
 	info->reserved = 0;
@@ -572,8 +604,8 @@ static void run_shard(shard_job *job) {
 	const size_t nchunks = cb.size() - 1;
 	const int64_t shard_bytes = off[job->d_end] - off[job->d_begin];
 	if (want_ids) {
-		/* expected ~0.23 tokens per byte; the pool buffer grows if a shard needs more */
-		int rc = pinned_get(e, sizeof(int32_t) * std::max<int64_t>(shard_bytes / 3 + 1024, 1024), &job->ids);
+		/* sized from the densest batch seen so far; the buffer grows if a shard needs more */
+		int rc = pinned_get(e, sizeof(int32_t) * (shard_bytes / 1024 * e->tokens_per_kib.load() + 4096), &job->ids);
 		if (rc != JTK_OK) return fail(rc);
 	}
 	jtk_workspace *ws[2] = {acquire_ws(ds), acquire_ws(ds)};
@@ -606,7 +638,9 @@ static void run_shard(shard_job *job) {
 			a.ndocs = nd;
 			a.ntiles = (cbytes + JTK_TILE - 1) / JTK_TILE;
 			a.tile_first_doc = w->tile_first_doc;
-			a.desc = w->desc;
+			a.tile_count = w->tile_count;
+			a.tile_base = w->tile_base;
+			a.stage = want_ids ? w->stage : nullptr;
 			a.hdr = w->hdr;
 			a.ids = want_ids ? w->d_ids : nullptr;
 			a.ids_cap = w->in_cap;
@@ -635,7 +669,9 @@ static void run_shard(shard_job *job) {
 		if (want_ids) {
 			if ((job->ntokens + ntok) * (int64_t) sizeof(int32_t) > job->ids.cap) {
 				jtk_pinned_buf bigger;
-				int r2 = pinned_get(e, std::max<int64_t>((job->ntokens + ntok) * 4 * 3 / 2, job->ids.cap * 2), &bigger);
+				const int64_t done_bytes = std::max<int64_t>(off[d1] - off[job->d_begin], 1);
+				const int64_t projected = (job->ntokens + ntok) * shard_bytes / done_bytes; /* tokens if the rest is as dense */
+				int r2 = pinned_get(e, sizeof(int32_t) * (projected + projected / 8 + 4096), &bigger);
 				if (r2 != JTK_OK) return r2;
 				memcpy(bigger.p, job->ids.p, (size_t) job->ntokens * 4);
 				pinned_put(e, job->ids);
@@ -663,6 +699,12 @@ static void run_shard(shard_job *job) {
 			job->status_out[d0 - job->d_begin + i] = h_st[i];
 		}
 		job->ntokens += ntok;
+		{
+			const int64_t per_kib = ntok * 1024 / std::max<int64_t>(cbytes, 1024) + 8;
+			int64_t cur = e->tokens_per_kib.load();
+			while (per_kib > cur && !e->tokens_per_kib.compare_exchange_weak(cur, per_kib)) {
+			}
+		}
 		job->tok_off_out[d1 - job->d_begin] = job->ntokens;
 		job->chunk_tokens.push_back(ntok);
 		return JTK_OK;

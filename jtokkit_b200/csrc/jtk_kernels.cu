@@ -24,15 +24,9 @@ constexpr int NWARPS = NT / 32;
 constexpr int TOKN = JTK_TILE + JTK_FWD_HALO;
 constexpr int QCAP = TOKN / 2;
 constexpr int BH = JTK_BACK_HALO;
-constexpr unsigned long long DESC_PREFIX = 1ull << 63;
-constexpr unsigned long long DESC_AGG = 1ull << 62;
-constexpr unsigned long long DESC_VALUE = (1ull << 62) - 1;
 
 /* indices into the small shared "misc" array */
-enum { M_TILE = 0, M_NSHORT, M_NMED, M_SHORT_NEXT, M_MED_NEXT, M_RS, M_CARRY, M_TOTAL, M_BASE_LO, M_BASE_HI, M_WSUM = 16 };
-
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) { return *reinterpret_cast<const volatile unsigned long long *>(p); }
-__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long *>(p) = v; }
+enum { M_TILE = 0, M_NSHORT, M_NMED, M_SHORT_NEXT, M_MED_NEXT, M_RS, M_CARRY, M_TOTAL, M_WSUM = 16 };
 
 /* first set bit in [from, limit] of a bit array, or -1 */
 __device__ __forceinline__ int next_bit(const uint32_t *bm, int from, int limit) {
@@ -147,40 +141,6 @@ __device__ int merge_warp(const jtk_tables &T, const uint8_t *p, int n, int32_t 
 	}
 	if (__any_sync(full, unk)) *unknown = true;
 	return out;
-}
-
-/* ---------------------------------------------------------------------------------------------
- * decoupled look-back over per-tile token counts; executed by warp 0.  Returns the exclusive prefix.
- * ------------------------------------------------------------------------------------------- */
-__device__ long long chain_prefix(unsigned long long *desc, long long tile, unsigned long long agg) {
-	const unsigned full = 0xFFFFFFFFu;
-	const int lane = threadIdx.x & 31;
-	if (tile == 0) {
-		if (lane == 0) st_volatile_u64(desc, DESC_PREFIX | agg);
-		return 0;
-	}
-	if (lane == 0) st_volatile_u64(desc + tile, DESC_AGG | agg);
-	unsigned long long running = 0;
-	long long look = tile - 1;
-	for (;;) {
-		const long long idx = look - lane;
-		unsigned long long v = idx >= 0 ? ld_volatile_u64(desc + idx) : DESC_PREFIX;
-		const unsigned inval = __ballot_sync(full, (v & (DESC_PREFIX | DESC_AGG)) == 0);
-		const unsigned pref = __ballot_sync(full, (v & DESC_PREFIX) != 0);
-		const int first_pref = pref ? __ffs((int) pref) - 1 : 32;
-		const unsigned needed = first_pref >= 31 ? full : ((2u << first_pref) - 1u);
-		if (inval & needed) {
-			__nanosleep(40);
-			continue;
-		}
-		unsigned long long c = (lane <= first_pref) ? (v & DESC_VALUE) : 0ull;
-		for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(full, c, o);
-		running += c;
-		if (first_pref < 32) break;
-		look -= 32;
-	}
-	if (lane == 0) st_volatile_u64(desc + tile, DESC_PREFIX | (running + agg));
-	return (long long) running;
 }
 
 /* ---------------------------------------------------------------------------------------------
@@ -347,7 +307,8 @@ __global__ void __launch_bounds__(JTK_NT, 2) jtk_encode_tiles_kernel(const __gri
 		}
 		__syncthreads();
 
-		/* ---- P6: token counts -> block scan -> chained scan -> write ids and document token offsets ---- */
+		/* ---- P6: token counts -> block scan -> tile-local placement.  Tokens go to this tile's slice of the staging
+		 * buffer; jtk_tile_scan_kernel + jtk_gather_kernel place them globally, so no CTA ever waits for another. ---- */
 		int mycount = 0;
 		for (uint32_t m = mybits; m;) {
 			const int i = __ffs((int) m) - 1;
@@ -369,13 +330,7 @@ __global__ void __launch_bounds__(JTK_NT, 2) jtk_encode_tiles_kernel(const __gri
 				if (lane >= o) v += y;
 			}
 			if (lane < NWARPS) misc[M_WSUM + lane] = (uint32_t) v;
-			const int tile_total = __shfl_sync(0xFFFFFFFFu, v, NWARPS - 1);
-			const long long base = chain_prefix(a.desc, tile, (unsigned long long) tile_total);
-			if (lane == 0) {
-				misc[M_TOTAL] = (uint32_t) tile_total;
-				misc[M_BASE_LO] = (uint32_t) (unsigned long long) base;
-				misc[M_BASE_HI] = (uint32_t) ((unsigned long long) base >> 32);
-			}
+			if (lane == NWARPS - 1) a.tile_count[tile] = v;
 			/* first piece start of the tile, for the long-piece bounds kernel */
 			int fb = 0x7fffffff;
 			for (int w = BH / 32 + lane; w < (BH + JTK_TILE) / 32; w += 32) {
@@ -388,12 +343,10 @@ __global__ void __launch_bounds__(JTK_NT, 2) jtk_encode_tiles_kernel(const __gri
 		__syncthreads();
 		const int excl = x - mycount + (warp ? (int) misc[M_WSUM + warp - 1] : 0);
 		chunk_pref[tid] = (uint32_t) excl;
-		const long long base = (long long) (((unsigned long long) misc[M_BASE_HI] << 32) | misc[M_BASE_LO]);
-		const bool write_ids = !(a.flags & JTK_COUNT_ONLY) && a.ids != nullptr;
-		if (write_ids && base + (long long) misc[M_TOTAL] > a.ids_cap) {
-			if (tid == 0) a.hdr->overflow = 1;
-		} else {
-			long long pos = base + excl;
+		const bool write_ids = !(a.flags & JTK_COUNT_ONLY) && a.stage != nullptr;
+		{
+			int32_t *dst = a.stage + tile * (long long) TOKN;
+			int pos = excl;
 			for (uint32_t m = mybits; m;) {
 				const int i = __ffs((int) m) - 1;
 				m &= m - 1;
@@ -406,7 +359,7 @@ __global__ void __launch_bounds__(JTK_NT, 2) jtk_encode_tiles_kernel(const __gri
 						lp.start = gbase + i;
 						const int e = next_bit(bmask, r0 + i + 1, JTK_REGION - 1);
 						lp.end = e < 0 ? -1 : c.g0 + e;
-						lp.insert_at = pos;
+						lp.insert_at = pos; /* tile-local; jtk_long_bounds_kernel adds the tile's base */
 						lp.count = 0;
 						lp.scratch = 0;
 						lp.doc = 0;
@@ -416,12 +369,13 @@ __global__ void __launch_bounds__(JTK_NT, 2) jtk_encode_tiles_kernel(const __gri
 					continue;
 				}
 				if (write_ids)
-					for (int k = 0; k < cnt; k++) a.ids[pos + k] = tok[s + k];
+					for (int k = 0; k < cnt; k++) dst[pos + k] = tok[s + k];
 				pos += cnt;
 			}
 		}
 		__syncthreads(); /* chunk_pref complete */
-		/* token offsets of the documents that start in this tile (the end of the input included) */
+		/* tile-local token offsets of the documents that start in this tile (the end of the input included);
+		 * jtk_gather_kernel adds the tile's base */
 		if (a.tok_off) {
 			for (int64_t d = first_doc + tid; d <= a.ndocs; d += NT) {
 				const int64_t g = a.doc_off[d];
@@ -429,7 +383,7 @@ __global__ void __launch_bounds__(JTK_NT, 2) jtk_encode_tiles_kernel(const __gri
 				if (g < tb) continue;
 				const int s = (int) (g - tb);
 				const int ch = s >> 4;
-				long long off = base + chunk_pref[ch];
+				long long off = chunk_pref[ch];
 				uint32_t bits = reinterpret_cast<const uint16_t *>(bmask)[BH / 16 + ch] & ((1u << (s & 15)) - 1u);
 				for (; bits;) {
 					const int i = __ffs((int) bits) - 1;
@@ -457,19 +411,63 @@ __global__ void jtk_tile_first_doc_kernel(const int64_t *doc_off, int64_t ndocs,
 	out[t] = (int32_t) lo;
 }
 
-/* totals + token offsets of the (empty) documents that start at the very end of the input */
-__global__ void jtk_finalize_kernel(const jtk_encode_args a) {
-	unsigned long long total_tokens = 0;
-	if (a.ntiles > 0) total_tokens = ld_volatile_u64(a.desc + (a.ntiles - 1)) & DESC_VALUE;
-	if (threadIdx.x == 0 && blockIdx.x == 0) a.hdr->total_tokens = total_tokens;
-	if (!a.tok_off) return;
-	int64_t lo = 0, hi = a.ndocs; /* first d with doc_off[d] >= total */
-	while (lo < hi) {
-		int64_t mid = (lo + hi) >> 1;
-		if (a.doc_off[mid] >= a.total) hi = mid;
-		else lo = mid + 1;
+/* exclusive scan of the per-tile token counts (one block; ntiles is ~131k per GiB) + batch totals */
+__global__ void __launch_bounds__(1024, 1) jtk_tile_scan_kernel(const jtk_encode_args a) {
+	__shared__ long long s_w[32];
+	__shared__ long long s_carry;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid == 0) s_carry = 0;
+	__syncthreads();
+	for (int64_t base = 0; base < a.ntiles; base += 1024) {
+		const int64_t i = base + tid;
+		const long long val = i < a.ntiles ? a.tile_count[i] : 0;
+		long long x = val;
+		for (int o = 1; o < 32; o <<= 1) {
+			long long y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+			if (lane >= o) x += y;
+		}
+		if (lane == 31) s_w[warp] = x;
+		__syncthreads();
+		if (warp == 0) {
+			long long w = s_w[lane];
+			for (int o = 1; o < 32; o <<= 1) {
+				long long y = __shfl_up_sync(0xFFFFFFFFu, w, o);
+				if (lane >= o) w += y;
+			}
+			s_w[lane] = w;
+		}
+		__syncthreads();
+		const long long excl = s_carry + x - val + (warp ? s_w[warp - 1] : 0);
+		if (i < a.ntiles) a.tile_base[i] = excl;
+		__syncthreads();
+		if (tid == 1023) s_carry = excl + val;
+		__syncthreads();
 	}
-	for (int64_t d = lo + blockIdx.x * (int64_t) blockDim.x + threadIdx.x; d <= a.ndocs; d += (int64_t) gridDim.x * blockDim.x) a.tok_off[d] = (int64_t) total_tokens;
+	if (tid == 0) {
+		a.tile_base[a.ntiles] = s_carry;
+		a.hdr->total_tokens = (unsigned long long) s_carry;
+		if (!(a.flags & JTK_COUNT_ONLY) && a.ids && s_carry > a.ids_cap) a.hdr->overflow = 1;
+	}
+}
+
+/* staging -> final ids (one CTA per tile, coalesced both ways) and tile-local -> global document token offsets */
+__global__ void __launch_bounds__(256) jtk_gather_kernel(const jtk_encode_args a) {
+	const bool write_ids = !(a.flags & JTK_COUNT_ONLY) && a.ids != nullptr && a.stage != nullptr && !a.hdr->overflow;
+	if (write_ids) {
+		for (int64_t t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+			const int32_t *src = a.stage + t * (long long) TOKN;
+			int32_t *dst = a.ids + a.tile_base[t];
+			const int n = a.tile_count[t];
+			for (int k = threadIdx.x; k < n; k += blockDim.x) dst[k] = src[k];
+		}
+	}
+	if (a.tok_off) {
+		const long long total_tokens = a.tile_base[a.ntiles];
+		for (int64_t d = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; d <= a.ndocs; d += (int64_t) gridDim.x * blockDim.x) {
+			const int64_t t = a.doc_off[d] / JTK_TILE;
+			a.tok_off[d] = t >= a.ntiles ? total_tokens : a.tok_off[d] + a.tile_base[t];
+		}
+	}
 }
 
 /* =============================================================================================
@@ -486,6 +484,7 @@ __global__ void jtk_long_bounds_kernel(const jtk_encode_args a, unsigned int n_l
 	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n_long) return;
 	jtk_long_piece lp = a.long_list[i];
+	a.long_list[i].insert_at = lp.insert_at + a.tile_base[lp.start / JTK_TILE];
 	if (lp.end < 0) {
 		int64_t end = a.total;
 		for (int64_t t = lp.start / JTK_TILE + 1; t < a.ntiles; t++) {
@@ -794,8 +793,10 @@ cudaError_t jtk_launch_encode_tiles(const jtk_encode_args &a, int num_sms, cudaS
 	return cudaGetLastError();
 }
 
-cudaError_t jtk_launch_finalize(const jtk_encode_args &a, cudaStream_t st) {
-	jtk_finalize_kernel<<<8, 256, 0, st>>>(a);
+cudaError_t jtk_launch_scan_gather(const jtk_encode_args &a, int num_sms, cudaStream_t st) {
+	jtk_tile_scan_kernel<<<1, 1024, 0, st>>>(a);
+	int64_t grid = std::max<int64_t>(std::min<int64_t>(std::max<int64_t>(a.ntiles, (a.ndocs + 256) / 256), (int64_t) num_sms * 16), 1);
+	jtk_gather_kernel<<<(unsigned) grid, 256, 0, st>>>(a);
 	return cudaGetLastError();
 }
 

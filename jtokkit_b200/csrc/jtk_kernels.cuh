@@ -39,7 +39,9 @@ struct jtk_encode_args {
 	int64_t ndocs;
 	const int32_t *tile_first_doc;
 	int64_t ntiles;
-	unsigned long long *desc; /* chained-scan descriptors, one per tile */
+	int32_t *tile_count;   /* tokens produced by each tile */
+	int64_t *tile_base;    /* ntiles + 1: exclusive scan of tile_count */
+	int32_t *stage;        /* ntiles * (JTK_TILE + JTK_FWD_HALO) tile-local token staging (nullable with JTK_COUNT_ONLY) */
 	jtk_batch_header *hdr;
 	int32_t *ids;
 	int64_t ids_cap;
@@ -58,7 +60,7 @@ struct jtk_encode_args {
 
 cudaError_t jtk_launch_tile_first_doc(const int64_t *doc_off, int64_t ndocs, int64_t ntiles, int32_t *out, cudaStream_t st);
 cudaError_t jtk_launch_encode_tiles(const jtk_encode_args &a, int num_sms, cudaStream_t st);
-cudaError_t jtk_launch_finalize(const jtk_encode_args &a, cudaStream_t st);
+cudaError_t jtk_launch_scan_gather(const jtk_encode_args &a, int num_sms, cudaStream_t st);
 cudaError_t jtk_encode_kernel_setup();
 
 /* long-piece path */

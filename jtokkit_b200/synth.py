@@ -89,14 +89,45 @@ def _script_words(tokens, script, rng, want):
     return words
 
 
+_SHORT_WORDS = {"a", "i", "of", "to", "in", "is", "it", "on", "at", "by", "an", "as", "be", "or", "we", "he", "so", "do", "if", "my", "no", "up",
+                "me", "us", "am", "go"}
+
+
 def _english_words(tokens, want=ZIPF_K):
+    """Space-prefixed letters-only tokens in rank order.  Low ranks are dominated by merge fragments (" t", " th",
+    " c"); those are dropped (one- and two-letter tokens unless real words, longer ones without a vowel) so that
+    the word-length distribution is English-like."""
     words = []
     for t in tokens:
         if len(t) >= 2 and t[:1] == b" " and t[1:].isalpha() and t[1:].isascii():
-            words.append(t[1:].decode("ascii"))
+            w = t[1:].decode("ascii")
+            lw = w.lower()
+            if len(w) <= 2 and lw not in _SHORT_WORDS:
+                continue
+            if len(w) >= 3 and not any(c in "aeiouy" for c in lw):
+                continue
+            words.append(w)
             if len(words) >= want:
                 break
     return words
+
+
+_DIACRITICS = {"a": "áàäâã", "e": "éèêë", "i": "íï", "o": "óöôõ", "u": "úü", "c": "ç", "n": "ñ", "s": "ß", "y": "ý"}
+
+
+def _latin_words(tokens, rng, want):
+    """Western-European-looking words: English word shapes with about every second word carrying a diacritic."""
+    base = _english_words(tokens, want)
+    out = []
+    for i, w in enumerate(base):
+        if i % 2 == 0:
+            pos = [k for k, c in enumerate(w) if c in _DIACRITICS]
+            if pos:
+                k = pos[int(rng.integers(len(pos)))]
+                alt = _DIACRITICS[w[k]]
+                w = w[:k] + alt[int(rng.integers(len(alt)))] + w[k + 1:]
+        out.append(w)
+    return out
 
 
 CONTRACTIONS = ["'s", "'t", "'re", "'ll", "'ve", "'m", "'d"]
@@ -141,7 +172,12 @@ class ItemTables:
         self.langs = [m[0] for m in MULTILINGUAL_MIX]
         items, base, size = [], np.zeros((len(self.langs), len(KINDS)), dtype=np.int64), np.zeros((len(self.langs), len(KINDS)), dtype=np.int64)
         for li, lang in enumerate(self.langs):
-            words = _english_words(tokens) if lang == "english" else _script_words(tokens, lang, rng, 4000)
+            if lang == "english":
+                words = _english_words(tokens)
+            elif lang == "latin":
+                words = _latin_words(tokens, rng, 8000)
+            else:
+                words = _script_words(tokens, lang, rng, 4000)
             rendered = _render(lang, words, rng)
             for ki, kind in enumerate(KINDS):
                 base[li, ki] = len(items)

@@ -114,8 +114,8 @@ class OracleEncoding:
             raise ValueError("oracle: cannot compile pattern: " + err.value.decode())
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().jo_destroy(self._h)
+        if getattr(self, "_h", None) and _LIB is not None:
+            _LIB.jo_destroy(self._h)
             self._h = None
 
     @staticmethod

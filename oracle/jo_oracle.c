@@ -31,7 +31,9 @@ typedef struct vocab {
 	int64_t *off;     /* nkeys + 1 */
 	int32_t *rank;    /* nkeys */
 	int64_t nkeys;
-	int64_t *slots;   /* open addressing: index into keys or -1 */
+	int64_t *slots;   /* bucket heads: index into keys or -1 (chained like java.util.HashMap) */
+	int64_t *chain;   /* next key in the same bucket or -1 */
+	uint32_t *khash;  /* cached hash per key, as HashMap.Node.hash */
 	uint64_t mask;
 	int64_t maxlen;
 	/* inverse map: rank -> key index (sorted by rank) */
@@ -47,14 +49,13 @@ static uint64_t spread(uint32_t h) { /* HashMap.hash() spreading */ return (uint
 
 static int64_t vocab_find(const vocab *v, const uint8_t *p, int64_t n) {
 	if (v->nkeys == 0 || n > v->maxlen) return -1;
-	uint64_t s = spread(bytes_hash(p, n)) & v->mask;
-	for (;;) {
-		int64_t k = v->slots[s];
-		if (k < 0) return -1;
+	const uint32_t h = (uint32_t) spread(bytes_hash(p, n));
+	for (int64_t k = v->slots[h & v->mask]; k >= 0; k = v->chain[k]) {
+		if (v->khash[k] != h) continue;
 		int64_t len = v->off[k + 1] - v->off[k];
 		if (len == n && memcmp(v->bytes + v->off[k], p, (size_t) n) == 0) return k;
-		s = (s + 1) & v->mask;
 	}
+	return -1;
 }
 
 static int cmp_rank_idx(const void *a, const void *b, void *ctx) {
@@ -72,9 +73,11 @@ static void vocab_build(vocab *v, const uint8_t *keys, const int64_t *key_off, c
 	v->rank = (int32_t *) malloc(sizeof(int32_t) * (size_t) (nkeys ? nkeys : 1));
 	v->off[0] = 0;
 	uint64_t cap = 16;
-	while (cap < (uint64_t) nkeys * 2 + 2) cap <<= 1;
+	while (cap * 3 < (uint64_t) nkeys * 4 + 4) cap <<= 1; /* HashMap load factor 0.75 */
 	v->mask = cap - 1;
 	v->slots = (int64_t *) malloc(sizeof(int64_t) * cap);
+	v->chain = (int64_t *) malloc(sizeof(int64_t) * (size_t) (nkeys ? nkeys : 1));
+	v->khash = (uint32_t *) malloc(sizeof(uint32_t) * (size_t) (nkeys ? nkeys : 1));
 	for (uint64_t i = 0; i < cap; i++) v->slots[i] = -1;
 	/* Map.put semantics: a later duplicate key replaces the earlier value (TokenEncoder.java:41-44). */
 	int64_t m = 0, pos = 0;
@@ -93,9 +96,10 @@ static void vocab_build(vocab *v, const uint8_t *keys, const int64_t *key_off, c
 		pos += len;
 		v->off[m + 1] = pos;
 		v->rank[m] = ranks[i];
-		uint64_t s = spread(bytes_hash(p, len)) & v->mask;
-		while (v->slots[s] >= 0) s = (s + 1) & v->mask;
-		v->slots[s] = m;
+		const uint32_t h = (uint32_t) spread(bytes_hash(p, len));
+		v->khash[m] = h;
+		v->chain[m] = v->slots[h & v->mask];
+		v->slots[h & v->mask] = m;
 		m++;
 	}
 	v->nkeys = m;
@@ -126,6 +130,8 @@ static void vocab_free(vocab *v) {
 	free(v->off);
 	free(v->rank);
 	free(v->slots);
+	free(v->chain);
+	free(v->khash);
 	free(v->by_rank);
 }
 
@@ -291,9 +297,13 @@ static int64_t emit_parts(const vocab *v, const uint8_t *piece, const int64_t *i
 
 static int64_t merge_literal(const vocab *v, const uint8_t *piece, int64_t n, int32_t *out, int64_t cap) {
 	int64_t nparts = n + 1;
-	int64_t *idx = (int64_t *) malloc(sizeof(int64_t) * (size_t) nparts);
-	int32_t *rk = (int32_t *) malloc(sizeof(int32_t) * (size_t) nparts);
-	uint8_t *scratch = (uint8_t *) malloc((size_t) (v->maxlen + 1));
+	int64_t idx_small[130];
+	int32_t rk_small[130];
+	uint8_t scratch_small[264];
+	const int small = nparts <= 130 && v->maxlen < 264;
+	int64_t *idx = small ? idx_small : (int64_t *) malloc(sizeof(int64_t) * (size_t) nparts);
+	int32_t *rk = small ? rk_small : (int32_t *) malloc(sizeof(int32_t) * (size_t) nparts);
+	uint8_t *scratch = small ? scratch_small : (uint8_t *) malloc((size_t) (v->maxlen + 1));
 	for (int64_t i = 0; i < nparts; i++) {
 		idx[i] = i;
 		rk[i] = RANK_MAX;
@@ -316,9 +326,11 @@ static int64_t merge_literal(const vocab *v, const uint8_t *piece, int64_t n, in
 		nparts--;
 	}
 	int64_t r = emit_parts(v, piece, idx, nparts, out, cap);
-	free(idx);
-	free(rk);
-	free(scratch);
+	if (!small) {
+		free(idx);
+		free(rk);
+		free(scratch);
+	}
 	return r;
 }
 

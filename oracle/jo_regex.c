@@ -21,9 +21,23 @@ static int in_ranges(const uint32_t (*r)[2], int n, uint32_t cp) {
 	}
 	return 0;
 }
-int jo_uc_is_letter(uint32_t cp) { return in_ranges(JTK_UC_L, JTK_UC_L_COUNT, cp); }
-int jo_uc_is_number(uint32_t cp) { return in_ranges(JTK_UC_N, JTK_UC_N_COUNT, cp); }
-int jo_uc_is_space(uint32_t cp) { return in_ranges(JTK_UC_WS, JTK_UC_WS_COUNT, cp); }
+
+/* one flag byte per code point (1 = \p{L}, 2 = \p{N}, 4 = White_Space), filled on first use */
+static uint8_t *uc_flags;
+static void uc_init(void) {
+	uint8_t *t = (uint8_t *) calloc(0x110000, 1);
+	for (uint32_t cp = 0; cp < 0x110000; cp++)
+		t[cp] = (uint8_t) ((in_ranges(JTK_UC_L, JTK_UC_L_COUNT, cp) ? 1 : 0) | (in_ranges(JTK_UC_N, JTK_UC_N_COUNT, cp) ? 2 : 0) |
+		                   (in_ranges(JTK_UC_WS, JTK_UC_WS_COUNT, cp) ? 4 : 0));
+	if (!__sync_bool_compare_and_swap(&uc_flags, NULL, t)) free(t);
+}
+static inline uint8_t uc_get(uint32_t cp) {
+	if (!uc_flags) uc_init();
+	return cp < 0x110000 ? uc_flags[cp] : 0;
+}
+int jo_uc_is_letter(uint32_t cp) { return uc_get(cp) & 1; }
+int jo_uc_is_number(uint32_t cp) { return (uc_get(cp) >> 1) & 1; }
+int jo_uc_is_space(uint32_t cp) { return (uc_get(cp) >> 2) & 1; }
 
 /* ------------------------------------------------------------------ node tree */
 enum { N_SET, N_ANY, N_CAT, N_ALT, N_REP, N_LOOK, N_EMPTY, N_BOL, N_EOL };
@@ -49,6 +63,11 @@ typedef struct node {
 	struct node *sub;
 	int min, max, mode; /* max < 0: unbounded */
 	int look_neg;
+	/* matcher-side caches (no semantic content): which ASCII characters the node can start with / match */
+	uint32_t first[4];   /* ASCII characters a match of this node may begin with */
+	int first_other;     /* may begin with a non-ASCII character */
+	int nullable;        /* may match the empty string */
+	uint32_t amap[4];    /* N_SET: ASCII characters the set accepts (case folding and negation applied) */
 } node;
 
 struct jo_regex {
@@ -112,6 +131,7 @@ static int eat(parser *ps, int c) {
 }
 
 static node *parse_alt(parser *ps, int ci);
+static void jo_regex_prepare(jo_regex *re);
 
 static int hexval(int c) {
 	if (c >= '0' && c <= '9') return c - '0';
@@ -519,6 +539,7 @@ jo_regex *jo_regex_compile(const char *pattern, int flags, char *err, int errlen
 		jo_regex_free(re);
 		return NULL;
 	}
+	jo_regex_prepare(re);
 	return re;
 }
 
@@ -611,8 +632,71 @@ static int single_width(const node *nd) { return nd->type == N_SET || nd->type =
 
 static int sw_match(const mctx *m, const node *nd, int64_t i) {
 	if (i >= m->n) return 0;
-	if (nd->type == N_ANY) return !is_line_term(m->s[i]);
-	return set_match(m, nd, m->s[i]);
+	const uint32_t c = m->s[i];
+	if (nd->type == N_ANY) return !is_line_term(c);
+	if (c < 128) return (nd->amap[c >> 5] >> (c & 31)) & 1u;
+	return set_match(m, nd, c);
+}
+
+/* first-character sets: a pure prefilter, a branch that cannot start at the current character is skipped
+ * exactly as it would have failed */
+static void compute_first(const mctx *m, node *nd) {
+	memset(nd->first, 0, sizeof(nd->first));
+	nd->first_other = 0;
+	nd->nullable = 0;
+	switch (nd->type) {
+	case N_SET:
+		for (uint32_t c = 0; c < 128; c++)
+			if (set_match(m, nd, c)) nd->amap[c >> 5] |= 1u << (c & 31);
+		memcpy(nd->first, nd->amap, sizeof(nd->first));
+		nd->first_other = 1;
+		break;
+	case N_ANY:
+		memset(nd->first, 0xFF, sizeof(nd->first));
+		nd->first_other = 1;
+		break;
+	case N_EMPTY:
+	case N_BOL:
+	case N_EOL:
+		nd->nullable = 1;
+		break;
+	case N_LOOK:
+		compute_first(m, nd->sub);
+		nd->nullable = 1;
+		break;
+	case N_REP:
+		compute_first(m, nd->sub);
+		memcpy(nd->first, nd->sub->first, sizeof(nd->first));
+		nd->first_other = nd->sub->first_other;
+		nd->nullable = nd->min == 0 || nd->sub->nullable;
+		break;
+	case N_ALT:
+		for (int k = 0; k < nd->nkids; k++) {
+			compute_first(m, nd->kids[k]);
+			for (int w = 0; w < 4; w++) nd->first[w] |= nd->kids[k]->first[w];
+			nd->first_other |= nd->kids[k]->first_other;
+			nd->nullable |= nd->kids[k]->nullable;
+		}
+		break;
+	case N_CAT:
+		nd->nullable = 1;
+		for (int k = 0; k < nd->nkids; k++) {
+			compute_first(m, nd->kids[k]);
+			if (nd->nullable) {
+				for (int w = 0; w < 4; w++) nd->first[w] |= nd->kids[k]->first[w];
+				nd->first_other |= nd->kids[k]->first_other;
+			}
+			if (!nd->kids[k]->nullable) nd->nullable = 0;
+		}
+		break;
+	}
+}
+
+static int can_start(const mctx *m, const node *nd, int64_t i) {
+	if (nd->nullable) return 1;
+	if (i >= m->n) return 0;
+	const uint32_t c = m->s[i];
+	return c < 128 ? (int) ((nd->first[c >> 5] >> (c & 31)) & 1u) : nd->first_other;
 }
 
 static int64_t m_rep(const mctx *m, const node *rep, int64_t i, int count, const kont *k) {
@@ -696,6 +780,7 @@ static int64_t m_node(const mctx *m, const node *nd, int64_t i, const kont *k) {
 	case N_CAT: return m_cat(m, nd, 0, i, k);
 	case N_ALT:
 		for (int b = 0; b < nd->nkids; b++) {
+			if (!can_start(m, nd->kids[b], i)) continue;
 			int64_t r = m_node(m, nd->kids[b], i, k);
 			if (r >= 0) return r;
 		}
@@ -710,12 +795,21 @@ static int64_t m_node(const mctx *m, const node *nd, int64_t i, const kont *k) {
 	return -1;
 }
 
+static void jo_regex_prepare(jo_regex *re) {
+	mctx m;
+	m.re = re;
+	m.s = NULL;
+	m.n = 0;
+	compute_first(&m, re->root);
+}
+
 int jo_regex_search(const jo_regex *re, const uint32_t *cps, int64_t n, int64_t from, int64_t *ms, int64_t *me) {
 	mctx m;
 	m.re = re;
 	m.s = cps;
 	m.n = n;
 	for (int64_t st = from; st <= n; st++) {
+		if (!can_start(&m, re->root, st)) continue;
 		int64_t r = m_node(&m, re->root, st, NULL);
 		if (r >= 0) {
 			*ms = st;

@@ -39,10 +39,13 @@ struct jtk_workspace {
 	/* sized for ntiles_cap tiles / long_cap long pieces */
 	int64_t ntiles_cap = 0, long_cap = 0;
 	int32_t *tile_first_doc = nullptr;
-	int32_t *tile_count = nullptr;
+	int32_t *tile_count = nullptr, *npieces = nullptr, *nslow = nullptr;
 	int64_t *tile_base = nullptr;
-	int32_t *stage = nullptr; /* tile-local token staging, ntiles * (JTK_TILE + JTK_FWD_HALO) */
-	int64_t stage_tiles = 0;
+	/* per sub-batch: piece records, merged-token staging, unresolved-piece lists */
+	int64_t sub_tiles = 0;
+	int32_t *rec = nullptr, *slowtok = nullptr;
+	uint16_t *slowq = nullptr;
+	std::vector<cudaEvent_t> kev; /* event pairs around the split+lookup kernel of every sub-batch (JTK_TIME_KERNEL) */
 	int64_t *tile_first_b = nullptr;
 	jtk_long_piece *long_list = nullptr;
 	jtk_batch_header *hdr = nullptr;      /* device */
@@ -229,8 +232,13 @@ static void free_workspace(jtk_workspace *w) {
 	if (!w) return;
 	cudaFree(w->tile_first_doc);
 	cudaFree(w->tile_count);
+	cudaFree(w->npieces);
+	cudaFree(w->nslow);
 	cudaFree(w->tile_base);
-	cudaFree(w->stage);
+	cudaFree(w->rec);
+	cudaFree(w->slowtok);
+	cudaFree(w->slowq);
+	for (cudaEvent_t ev : w->kev) cudaEventDestroy(ev);
 	cudaFree(w->tile_first_b);
 	cudaFree(w->long_list);
 	cudaFree(w->hdr);
@@ -274,7 +282,16 @@ static void release_ws(jtk_device_state *ds, jtk_workspace *w) {
 	ds->free_ws.push_back(w);
 }
 
-static int ensure_ws_tiles(jtk_workspace *w, int64_t ntiles, int64_t long_cap, bool want_stage) {
+static int64_t sub_batch_tiles() {
+	static const int64_t v = [] {
+		const char *env = getenv("JTK_SUB_TILES");
+		long n = env ? atol(env) : 0;
+		return (int64_t) (n >= 64 ? n : JTK_DEFAULT_SUB_TILES);
+	}();
+	return v;
+}
+
+static int ensure_ws_tiles(jtk_workspace *w, int64_t ntiles, int64_t long_cap) {
 	if (!w->hdr) {
 		CUDA_TRY(cudaMalloc(&w->hdr, sizeof(jtk_batch_header)));
 		CUDA_TRY(cudaHostAlloc(&w->hdr_host, sizeof(jtk_batch_header), cudaHostAllocDefault));
@@ -282,27 +299,35 @@ static int ensure_ws_tiles(jtk_workspace *w, int64_t ntiles, int64_t long_cap, b
 	if (ntiles > w->ntiles_cap) {
 		cudaFree(w->tile_first_doc);
 		cudaFree(w->tile_count);
+		cudaFree(w->npieces);
+		cudaFree(w->nslow);
 		cudaFree(w->tile_base);
 		cudaFree(w->tile_first_b);
-		w->tile_first_doc = nullptr;
-		w->tile_count = nullptr;
+		w->tile_first_doc = w->tile_count = w->npieces = w->nslow = nullptr;
 		w->tile_base = nullptr;
 		w->tile_first_b = nullptr;
 		w->ntiles_cap = 0;
 		int64_t cap = ntiles + ntiles / 4 + 16;
 		CUDA_TRY(cudaMalloc(&w->tile_first_doc, sizeof(int32_t) * cap));
 		CUDA_TRY(cudaMalloc(&w->tile_count, sizeof(int32_t) * cap));
+		CUDA_TRY(cudaMalloc(&w->npieces, sizeof(int32_t) * cap));
+		CUDA_TRY(cudaMalloc(&w->nslow, sizeof(int32_t) * cap));
 		CUDA_TRY(cudaMalloc(&w->tile_base, sizeof(int64_t) * (cap + 1)));
 		CUDA_TRY(cudaMalloc(&w->tile_first_b, sizeof(int64_t) * cap));
 		w->ntiles_cap = cap;
 	}
-	if (want_stage && ntiles > w->stage_tiles) {
-		cudaFree(w->stage);
-		w->stage = nullptr;
-		w->stage_tiles = 0;
-		int64_t cap = ntiles + ntiles / 8 + 4;
-		CUDA_TRY(cudaMalloc(&w->stage, sizeof(int32_t) * (size_t) cap * (JTK_TILE + JTK_FWD_HALO)));
-		w->stage_tiles = cap;
+	const int64_t sub = std::min<int64_t>(std::max<int64_t>(ntiles, 1), sub_batch_tiles());
+	if (sub > w->sub_tiles) {
+		cudaFree(w->rec);
+		cudaFree(w->slowtok);
+		cudaFree(w->slowq);
+		w->rec = w->slowtok = nullptr;
+		w->slowq = nullptr;
+		w->sub_tiles = 0;
+		CUDA_TRY(cudaMalloc(&w->rec, sizeof(int32_t) * (size_t) sub * JTK_RECN));
+		CUDA_TRY(cudaMalloc(&w->slowtok, sizeof(int32_t) * (size_t) sub * JTK_RECN));
+		CUDA_TRY(cudaMalloc(&w->slowq, sizeof(uint16_t) * (size_t) sub * JTK_QCAP));
+		w->sub_tiles = sub;
 	}
 	if (long_cap > w->long_cap) {
 		cudaFree(w->long_list);
@@ -313,6 +338,22 @@ static int ensure_ws_tiles(jtk_workspace *w, int64_t ntiles, int64_t long_cap, b
 		w->long_cap = cap;
 	}
 	return JTK_OK;
+}
+
+static void fill_args(jtk_encode_args &a, const jtk_device_state *ds, const jtk_workspace *w) {
+	a.T = ds->T;
+	a.tile_first_doc = w->tile_first_doc;
+	a.npieces = w->npieces;
+	a.nslow = w->nslow;
+	a.tile_count = w->tile_count;
+	a.tile_base = w->tile_base;
+	a.tile_first_b = w->tile_first_b;
+	a.rec = w->rec;
+	a.slowtok = w->slowtok;
+	a.slowq = w->slowq;
+	a.hdr = w->hdr;
+	a.long_list = w->long_list;
+	a.long_cap = w->long_cap;
 }
 
 /* ------------------------------------------------------------------ the device-resident batch */
@@ -385,51 +426,50 @@ static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspa
 	if ((reinterpret_cast<uintptr_t>(d_utf8) & 15) != 0) return set_error(JTK_E_ARG, "d_utf8 must be 16-byte aligned");
 	const int64_t ntiles = (nbytes + JTK_TILE - 1) / JTK_TILE;
 	const int64_t long_cap = nbytes / (JTK_LONG_PIECE + 1) + 1;
-	const bool want_stage = !(flags & JTK_COUNT_ONLY) && d_ids != nullptr;
-	int rc = ensure_ws_tiles(w, ntiles, long_cap, want_stage);
+	int rc = ensure_ws_tiles(w, ntiles, long_cap);
 	if (rc != JTK_OK) return rc;
 	jtk_encode_args a;
 	memset(&a, 0, sizeof(a));
-	a.T = ds->T;
+	fill_args(a, ds, w);
 	a.bytes = d_utf8;
 	a.total = nbytes;
 	a.doc_off = d_doc_off;
 	a.ndocs = ndocs;
-	a.tile_first_doc = w->tile_first_doc;
 	a.ntiles = ntiles;
-	a.tile_count = w->tile_count;
-	a.tile_base = w->tile_base;
-	a.stage = want_stage ? w->stage : nullptr;
-	a.hdr = w->hdr;
 	a.ids = d_ids;
 	a.ids_cap = ids_capacity;
 	a.tok_off = d_tok_off;
 	a.doc_status = d_doc_status;
 	a.flags = flags;
-	a.long_list = w->long_list;
-	a.long_cap = w->long_cap;
-	a.tile_first_b = w->tile_first_b;
 	a.piece_flags = d_piece_flags;
 	CUDA_TRY(cudaMemsetAsync(w->hdr, 0, sizeof(jtk_batch_header), st));
 	CUDA_TRY(jtk_launch_tile_first_doc(d_doc_off, ndocs, ntiles, w->tile_first_doc, st));
-	cudaEvent_t k0 = nullptr, k1 = nullptr;
 	const bool time_kernel = (flags & JTK_TIME_KERNEL) && sync_and_long;
-	if (time_kernel) {
-		CUDA_TRY(cudaEventCreate(&k0));
-		CUDA_TRY(cudaEventCreate(&k1));
-		CUDA_TRY(cudaEventRecord(k0, st));
+	const int64_t sub = w->sub_tiles;
+	const int64_t nsub = (ntiles + sub - 1) / sub;
+	if (time_kernel)
+		while ((int64_t) w->kev.size() < 2 * nsub) {
+			cudaEvent_t ev;
+			CUDA_TRY(cudaEventCreate(&ev));
+			w->kev.push_back(ev);
+		}
+	for (int64_t i = 0; i < nsub; i++) {
+		a.tile_begin = i * sub;
+		a.tile_end = std::min<int64_t>(ntiles, (i + 1) * sub);
+		CUDA_TRY(jtk_launch_sub_batch(a, ds->num_sms, time_kernel ? w->kev[(size_t) (2 * i)] : nullptr, time_kernel ? w->kev[(size_t) (2 * i + 1)] : nullptr, st));
 	}
-	CUDA_TRY(jtk_launch_encode_tiles(a, ds->num_sms, st));
-	if (time_kernel) CUDA_TRY(cudaEventRecord(k1, st));
-	CUDA_TRY(jtk_launch_scan_gather(a, ds->num_sms, st));
-	info->gpu_launches = (ntiles > 0 ? 2 : 0) + 2;
+	CUDA_TRY(jtk_launch_finalize(a, st));
+	info->gpu_launches = (ntiles > 0 ? 1 : 0) + 4 * nsub + 1;
 	CUDA_TRY(cudaMemcpyAsync(w->hdr_host, w->hdr, sizeof(jtk_batch_header), cudaMemcpyDeviceToHost, st));
 	if (!sync_and_long) return JTK_OK;
 	CUDA_TRY(cudaStreamSynchronize(st));
 	if (time_kernel) {
-		cudaEventElapsedTime(&info->tile_kernel_ms, k0, k1);
-		cudaEventDestroy(k0);
-		cudaEventDestroy(k1);
+		info->tile_kernel_ms = 0;
+		for (int64_t i = 0; i < nsub; i++) {
+			float ms = 0;
+			cudaEventElapsedTime(&ms, w->kev[(size_t) (2 * i)], w->kev[(size_t) (2 * i + 1)]);
+			info->tile_kernel_ms += ms;
+		}
 	}
 	info->num_tokens = (int64_t) w->hdr_host->total_tokens;
 	info->num_long_pieces = w->hdr_host->n_long;
@@ -631,25 +671,17 @@ static void run_shard(shard_job *job) {
 		if (w->hdr_host->n_long > 0) {
 			jtk_encode_args a;
 			memset(&a, 0, sizeof(a));
-			a.T = ds->T;
+			fill_args(a, ds, w);
 			a.bytes = w->d_in;
 			a.total = cbytes;
 			a.doc_off = w->d_doc_off;
 			a.ndocs = nd;
 			a.ntiles = (cbytes + JTK_TILE - 1) / JTK_TILE;
-			a.tile_first_doc = w->tile_first_doc;
-			a.tile_count = w->tile_count;
-			a.tile_base = w->tile_base;
-			a.stage = want_ids ? w->stage : nullptr;
-			a.hdr = w->hdr;
 			a.ids = want_ids ? w->d_ids : nullptr;
 			a.ids_cap = w->in_cap;
 			a.tok_off = w->d_tok_off;
 			a.doc_status = w->d_status;
 			a.flags = job->flags;
-			a.long_list = w->long_list;
-			a.long_cap = w->long_cap;
-			a.tile_first_b = w->tile_first_b;
 			cudaEvent_t l0, l1;
 			cudaEventCreate(&l0);
 			cudaEventCreate(&l1);

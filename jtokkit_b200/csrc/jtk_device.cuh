@@ -41,8 +41,12 @@ JTK_HD int jtk_cls(const jtk_tile_ctx &c, int r) { return c.cls[r] & JTK_CLS_MAS
 
 #if defined(__CUDA_ARCH__)
 #define JTK_SMEM_OR(p, v) atomicOr((p), (v))
+JTK_HD int jtk_ctz(uint32_t m) { return __ffs((int) m) - 1; }
+JTK_HD int jtk_clz(uint32_t m) { return __clz((int) m); }
 #else
 #define JTK_SMEM_OR(p, v) (*(p) |= (v))
+JTK_HD int jtk_ctz(uint32_t m) { return __builtin_ctz(m); }
+JTK_HD int jtk_clz(uint32_t m) { return __builtin_clz(m); }
 #endif
 
 /* ---------------------------------------------------------------------------------------------
@@ -512,13 +516,14 @@ JTK_HD int32_t jtk_lookup_piece(const jtk_tables &T, const uint8_t *p, int n) {
 
 /* ---------------------------------------------------------------------------------------------
  * bytePairMerge for one piece of 2..32 bytes by one thread (GptBytePairEncoding.java:200-275)
- * tok / rk: n staging slots each.  Returns the token count; tokens end up in tok[0..count).
+ * tok / rk: n staging slots each, element k at index k * stride (the kernel interleaves the slots of the threads of
+ * a CTA so that slot k of every thread falls into a different bank).  Returns the token count; tokens end up in slots 0..count-1.
  * *unknown is set when a final part is a byte that is not in the vocabulary.
  * ------------------------------------------------------------------------------------------- */
-JTK_HD int jtk_merge_short(const jtk_tables &T, const uint8_t *p, int n, int32_t *tok, int32_t *rk, bool *unknown) {
+JTK_HD int jtk_merge_short(const jtk_tables &T, const uint8_t *p, int n, int32_t *tok, int32_t *rk, int stride, bool *unknown) {
 	for (int k = 0; k < n; k++) {
-		tok[k] = T.byte_id[p[k]];
-		rk[k] = (k + 1 < n) ? T.bytepair[((uint32_t) p[k] << 8) | p[k + 1]] : JTK_RANK_MAX;
+		tok[k * stride] = T.byte_id[p[k]];
+		rk[k * stride] = (k + 1 < n) ? T.bytepair[((uint32_t) p[k] << 8) | p[k + 1]] : JTK_RANK_MAX;
 	}
 	uint32_t alive = (n >= 32) ? 0xFFFFFFFFu : ((1u << n) - 1u);
 	for (;;) {
@@ -526,13 +531,9 @@ JTK_HD int jtk_merge_short(const jtk_tables &T, const uint8_t *p, int n, int32_t
 		int32_t mr = JTK_RANK_MAX;
 		int mi = -1;
 		for (uint32_t m = alive; m;) {
-#if defined(__CUDA_ARCH__)
-			int k = __ffs((int) m) - 1;
-#else
-			int k = __builtin_ctz(m);
-#endif
+			const int k = jtk_ctz(m);
 			m &= m - 1;
-			int32_t r = rk[k];
+			const int32_t r = rk[k * stride];
 			if (r < mr) {
 				mr = r;
 				mi = k;
@@ -540,46 +541,25 @@ JTK_HD int jtk_merge_short(const jtk_tables &T, const uint8_t *p, int n, int32_t
 		}
 		if (mi < 0) break; /* :247,260-262 */
 		const uint32_t above = alive & ~((2u << mi) - 1u); /* parts after mi */
-#if defined(__CUDA_ARCH__)
-		const int nx = __ffs((int) above) - 1;
-#else
-		const int nx = __builtin_ctz(above);
-#endif
+		const int nx = jtk_ctz(above);
 		const uint32_t above2 = above & (above - 1);
 		const uint32_t below = alive & ((1u << mi) - 1u);
-		tok[mi] = mr; /* rank == id of the merged token */
+		tok[mi * stride] = mr; /* rank == id of the merged token */
 		alive &= ~(1u << nx);
-		rk[nx] = JTK_RANK_MAX;
-		if (above2) {
-#if defined(__CUDA_ARCH__)
-			const int nn = __ffs((int) above2) - 1;
-#else
-			const int nn = __builtin_ctz(above2);
-#endif
-			rk[mi] = jtk_lookup_pair(T, mr, tok[nn]); /* :254 */
-		} else {
-			rk[mi] = JTK_RANK_MAX;
-		}
+		rk[nx * stride] = JTK_RANK_MAX;
+		rk[mi * stride] = above2 ? jtk_lookup_pair(T, mr, tok[jtk_ctz(above2) * stride]) : JTK_RANK_MAX; /* :254 */
 		if (below) {
-#if defined(__CUDA_ARCH__)
-			const int pv = 31 - __clz((int) below);
-#else
-			const int pv = 31 - __builtin_clz(below);
-#endif
-			rk[pv] = jtk_lookup_pair(T, tok[pv], mr); /* :255-257 */
+			const int pv = 31 - jtk_clz(below);
+			rk[pv * stride] = jtk_lookup_pair(T, tok[pv * stride], mr); /* :255-257 */
 		}
 	}
 	int cnt = 0;
 	for (uint32_t m = alive; m;) {
-#if defined(__CUDA_ARCH__)
-		int k = __ffs((int) m) - 1;
-#else
-		int k = __builtin_ctz(m);
-#endif
+		const int k = jtk_ctz(m);
 		m &= m - 1;
-		int32_t t = tok[k];
+		const int32_t t = tok[k * stride];
 		if (t < JTK_PSEUDO_BASE + 256) *unknown = true;
-		tok[cnt++] = t;
+		tok[(cnt++) * stride] = t;
 	}
 	return cnt;
 }

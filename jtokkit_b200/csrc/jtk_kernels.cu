@@ -1,12 +1,19 @@
 /*
  * sm_100a kernels of the JTokkit encode path.
  *
- * jtk_encode_tiles_kernel is the hot path: ONE pass over the input.  A persistent CTA takes 8 KiB tiles by
- * ticket, stages the tile plus halos in shared memory with 16-byte loads, classifies code points, evaluates
- * the split rules into a piece-start bitmask, resolves ~94 % of the pieces with one probe of the byte-keyed
- * piece table (L2 resident), merges the rest (thread per short piece, warp per medium piece) against the
- * pair table, and places the tile's ids with a decoupled look-back scan over per-tile token counts, so the
- * only HBM traffic is the input bytes in and the ids / document token offsets out.
+ * The batch is processed in sub-batches of tiles (8 KiB of input each) so that the intermediates stay close to
+ * the L2; per sub-batch four uniform kernels run back to back on one stream, none of them waits for another CTA:
+ *
+ *   jtk_split_lookup_kernel  persistent CTAs take tiles by ticket: stage tile + halos in shared memory (16-byte
+ *                            loads), classify code points, evaluate the split rules into a piece-start bitmask,
+ *                            list the piece starts, then ONE PIECE PER THREAD probe the byte-keyed piece table
+ *                            (L2 resident).  Output: one int32 record per piece (the token id, or "needs merging"
+ *                            with start/length), the tile's list of pieces that need merging, counts.
+ *   jtk_merge_kernel         one CTA per tile: the tile's unresolved pieces, sorted by length, run the exact
+ *                            bytePairMerge loop (thread per short piece, warp per medium piece) against the pair table.
+ *   jtk_tile_scan_kernel     exclusive scan of the per-tile token counts.
+ *   jtk_gather_kernel        one CTA per tile: per-piece token counts -> block scan -> ids written at their final
+ *                            position, document token offsets resolved.
  *
  * Reference code this replaces: GptBytePairEncoding.encodeOrdinaryInternal / bytePairMerge / getRank
  * (GptBytePairEncoding.java:71-103,200-300) and the special-token guard of encodeInternal (:52-56).
@@ -21,12 +28,22 @@ namespace {
 
 constexpr int NT = JTK_NT;
 constexpr int NWARPS = NT / 32;
-constexpr int TOKN = JTK_TILE + JTK_FWD_HALO;
-constexpr int QCAP = TOKN / 2;
+constexpr int RECN = JTK_RECN;
+constexpr int QCAP = JTK_QCAP;
 constexpr int BH = JTK_BACK_HALO;
+constexpr int TC = JTK_TILE / 16;  /* 16-byte chunks per tile */
+constexpr int CPT = TC / NT;       /* chunks per thread in the piece-listing step */
+static_assert(TC % NT == 0, "threads per CTA must divide the chunks per tile");
+
+/* piece records: a token id, or (id space is limited to >= JTK_REC_MIN_ID at registration) a payload */
+constexpr int32_t REC_BASE = (int32_t) 0x80000000;
+constexpr uint32_t REC_LONG = 1u << 24;
+__device__ __forceinline__ bool rec_is_id(int32_t r) { return r >= JTK_REC_MIN_ID; }
+__device__ __forceinline__ int32_t rec_make(int s, int m) { return REC_BASE + (int32_t) (((uint32_t) s << 11) | (uint32_t) (m - 1)); }
+__device__ __forceinline__ uint32_t rec_payload(int32_t r) { return (uint32_t) (r - REC_BASE); }
 
 /* indices into the small shared "misc" array */
-enum { M_TILE = 0, M_NSHORT, M_NMED, M_SHORT_NEXT, M_MED_NEXT, M_RS, M_CARRY, M_TOTAL, M_WSUM = 16 };
+enum { M_TILE = 0, M_NSLOW, M_RS, M_CARRY, M_HITS, M_WSUM = 16 };
 
 /* first set bit in [from, limit] of a bit array, or -1 */
 __device__ __forceinline__ int next_bit(const uint32_t *bm, int from, int limit) {
@@ -56,6 +73,32 @@ __device__ int64_t doc_of(const jtk_encode_args &a, int64_t g) {
 
 __device__ void flag_doc(const jtk_encode_args &a, int64_t g, int bit) {
 	if (a.doc_status && a.ndocs > 0) atomicOr(a.doc_status + doc_of(a, g), bit);
+}
+
+/* block-wide exclusive scan of one int per thread; *total receives the block sum.  wsum: NTHREADS/32 ints of shared memory. */
+template <int NTHREADS>
+__device__ __forceinline__ int block_exclusive_scan(int v, int *wsum, int *total) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int x = v;
+	for (int o = 1; o < 32; o <<= 1) {
+		int y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+		if (lane >= o) x += y;
+	}
+	if (lane == 31) wsum[warp] = x;
+	__syncthreads();
+	if (warp == 0) {
+		int w = lane < NTHREADS / 32 ? wsum[lane] : 0;
+		for (int o = 1; o < 32; o <<= 1) {
+			int y = __shfl_up_sync(0xFFFFFFFFu, w, o);
+			if (lane >= o) w += y;
+		}
+		if (lane < NTHREADS / 32) wsum[lane] = w;
+	}
+	__syncthreads();
+	const int excl = x - v + (warp ? wsum[warp - 1] : 0);
+	*total = wsum[NTHREADS / 32 - 1];
+	__syncthreads(); /* wsum may be reused by the caller */
+	return excl;
 }
 
 /* ---------------------------------------------------------------------------------------------
@@ -144,23 +187,20 @@ __device__ int merge_warp(const jtk_tables &T, const uint8_t *p, int n, int32_t 
 }
 
 /* ---------------------------------------------------------------------------------------------
- * the tile kernel
+ * kernel 1: split + whole-piece lookup
  * ------------------------------------------------------------------------------------------- */
-__global__ void __launch_bounds__(JTK_NT, 2) jtk_encode_tiles_kernel(const __grid_constant__ jtk_encode_args a) {
+__global__ void __launch_bounds__(JTK_NT, 2) jtk_split_lookup_kernel(const __grid_constant__ jtk_encode_args a) {
 	extern __shared__ __align__(16) uint8_t smem[];
 	uint8_t *sb = smem;
 	uint8_t *cls = sb + (JTK_REGION + 16);
 	uint32_t *bmask = reinterpret_cast<uint32_t *>(cls + (JTK_REGION + 16));
 	uint32_t *dmask = bmask + JTK_MASK_WORDS;
-	int32_t *tok = reinterpret_cast<int32_t *>(dmask + JTK_MASK_WORDS);
-	int32_t *rk = tok + TOKN;
-	uint16_t *slowq = reinterpret_cast<uint16_t *>(rk + TOKN);
-	uint32_t *chunk_pref = reinterpret_cast<uint32_t *>(slowq + QCAP);
-	uint32_t *misc = chunk_pref + NT;
+	uint16_t *plist = reinterpret_cast<uint16_t *>(dmask + JTK_MASK_WORDS); /* region index of every piece start, in order */
+	uint32_t *chunk_pref = reinterpret_cast<uint32_t *>(plist + RECN);      /* pieces before each 16-byte chunk */
+	uint32_t *misc = chunk_pref + TC;
 
 	const int tid = threadIdx.x;
 	const int lane = tid & 31;
-	const int warp = tid >> 5;
 	const jtk_tables &T = a.T;
 
 	jtk_tile_ctx c;
@@ -168,8 +208,8 @@ __global__ void __launch_bounds__(JTK_NT, 2) jtk_encode_tiles_kernel(const __gri
 	c.cls = cls;
 	c.bmask = bmask;
 	c.dmask = dmask;
-	c.tok = tok;
-	c.rk = rk;
+	c.tok = nullptr;
+	c.rk = nullptr;
 	c.total = a.total;
 	c.gbytes = a.bytes;
 	c.doc_off = a.doc_off;
@@ -178,17 +218,16 @@ __global__ void __launch_bounds__(JTK_NT, 2) jtk_encode_tiles_kernel(const __gri
 
 	for (;;) {
 		/* ---- P0: take a tile ---- */
-		__syncthreads(); /* previous iteration's readers of misc / staging are done */
+		__syncthreads();
 		if (tid == 0) {
 			misc[M_TILE] = atomicAdd(&a.hdr->ticket, 1u);
-			misc[M_NSHORT] = 0;
-			misc[M_NMED] = 0;
-			misc[M_SHORT_NEXT] = 0;
-			misc[M_MED_NEXT] = 0;
+			misc[M_NSLOW] = 0;
+			misc[M_HITS] = 0;
 		}
 		__syncthreads();
-		const long long tile = misc[M_TILE];
-		if (tile >= a.ntiles) break;
+		const long long tile = a.tile_begin + (long long) misc[M_TILE];
+		if (tile >= a.tile_end) break;
+		const long long lt = tile - a.tile_begin; /* index into the per-sub-batch buffers */
 		const int64_t tb = tile * (int64_t) JTK_TILE;
 		c.g0 = tb - BH;
 		c.rs = 0;
@@ -218,164 +257,107 @@ __global__ void __launch_bounds__(JTK_NT, 2) jtk_encode_tiles_kernel(const __gri
 		/* ---- P3: split rules -> piece-start bits; special-token guard ---- */
 		for (int ch = BH / 16 + tid; ch < JTK_REGION_CHUNKS; ch += NT) reinterpret_cast<uint16_t *>(bmask)[ch] = (uint16_t) jtk_boundary_chunk(c, ch);
 		if ((a.flags & JTK_CHECK_SPECIAL) && T.nspecial > 0) {
-			const int r0 = BH + tid * 16;
-			for (int i = 0; i < 16; i++) {
-				const int64_t g = c.g0 + r0 + i;
-				if (g >= a.total) break;
-				const uint8_t b = sb[r0 + i];
-				if ((T.special_first[b >> 5] >> (b & 31)) & 1u) {
-					if (jtk_special_at(T, a.bytes, g, jtk_doc_ceil(c, g))) flag_doc(a, g, JTK_DOC_HAS_SPECIAL);
+			for (int ch = tid; ch < TC; ch += NT) {
+				const int r0 = BH + ch * 16;
+				for (int i = 0; i < 16; i++) {
+					const int64_t g = c.g0 + r0 + i;
+					if (g >= a.total) break;
+					const uint8_t b = sb[r0 + i];
+					if ((T.special_first[b >> 5] >> (b & 31)) & 1u) {
+						if (jtk_special_at(T, a.bytes, g, jtk_doc_ceil(c, g))) flag_doc(a, g, JTK_DOC_HAS_SPECIAL);
+					}
 				}
 			}
 		}
 		__syncthreads();
 
-		/* ---- P4: whole-piece lookup for the pieces that start in this thread's 16 bytes ---- */
-		const int r0 = BH + tid * 16;
-		const int64_t gbase = tb + tid * 16;
-		uint32_t mybits = reinterpret_cast<const uint16_t *>(bmask)[BH / 16 + tid];
-		if (gbase >= a.total) mybits = 0;
-		else if (gbase + 16 > a.total) mybits &= (1u << (int) (a.total - gbase)) - 1u;
-		if (a.piece_flags) {
-			for (int i = 0; i < 16 && gbase + i < a.total; i++) a.piece_flags[gbase + i] = (mybits >> i) & 1u;
-		}
-		for (uint32_t m = mybits; m;) {
-			const int i = __ffs((int) m) - 1;
-			m &= m - 1;
-			const int r = r0 + i;
-			const int s = r - BH;
-			const int e = next_bit(bmask, r + 1, r + JTK_LONG_PIECE);
-			if (e < 0) { /* longer than JTK_LONG_PIECE: deferred to the long-piece kernels */
-				rk[s] = -1;
-				continue;
-			}
-			const int n = e - r;
-			const uint8_t *p = sb + r;
-			if (n == 1) {
-				const int32_t id = T.byte_id[p[0]];
-				if (id < JTK_PSEUDO_BASE + 256) flag_doc(a, gbase + i, JTK_DOC_UNKNOWN_BYTES);
-				tok[s] = id;
-				rk[s] = 1;
-				continue;
-			}
-			const int32_t id = jtk_lookup_piece(T, p, n);
-			if (id != JTK_RANK_MAX) {
-				tok[s] = id;
-				rk[s] = 1;
-			} else {
-				rk[s] = n;
-				if (n <= JTK_SHORT_PIECE) slowq[atomicAdd(&misc[M_NSHORT], 1u)] = (uint16_t) s;
-				else slowq[QCAP - 1 - atomicAdd(&misc[M_NMED], 1u)] = (uint16_t) s;
-			}
-		}
-		__syncthreads();
-
-		/* ---- P5: merge loops.  Medium pieces one per warp, short pieces one per thread, both handed out dynamically ---- */
-		{
-			const unsigned nmed = misc[M_NMED], nshort = misc[M_NSHORT];
-			for (;;) {
-				unsigned j = 0;
-				if (lane == 0) j = atomicAdd(&misc[M_MED_NEXT], 1u);
-				j = __shfl_sync(0xFFFFFFFFu, j, 0);
-				if (j >= nmed) break;
-				const int s = slowq[QCAP - 1 - j];
-				const int n = rk[s];
-				__syncwarp();
-				bool unk = false;
-				const int cnt = merge_warp(T, sb + BH + s, n, tok + s, rk + s, &unk);
-				__syncwarp();
-				if (lane == 0) {
-					rk[s] = cnt;
-					if (unk) flag_doc(a, tb + s, JTK_DOC_UNKNOWN_BYTES);
-				}
-			}
-			for (;;) {
-				unsigned base = 0;
-				if (lane == 0) base = atomicAdd(&misc[M_SHORT_NEXT], 32u);
-				base = __shfl_sync(0xFFFFFFFFu, base, 0);
-				if (base >= nshort) break;
-				const unsigned j = base + lane;
-				if (j < nshort) {
-					const int s = slowq[j];
-					const int n = rk[s];
-					bool unk = false;
-					const int cnt = jtk_merge_short(T, sb + BH + s, n, tok + s, rk + s, &unk);
-					rk[s] = cnt;
-					if (unk) flag_doc(a, tb + s, JTK_DOC_UNKNOWN_BYTES);
-				}
-			}
-		}
-		__syncthreads();
-
-		/* ---- P6: token counts -> block scan -> tile-local placement.  Tokens go to this tile's slice of the staging
-		 * buffer; jtk_tile_scan_kernel + jtk_gather_kernel place them globally, so no CTA ever waits for another. ---- */
+		/* ---- P4a: list the piece starts of the tile in order (thread owns CPT consecutive chunks) ---- */
+		uint32_t bits[CPT];
 		int mycount = 0;
-		for (uint32_t m = mybits; m;) {
-			const int i = __ffs((int) m) - 1;
-			m &= m - 1;
-			const int cnt = rk[r0 + i - BH];
-			mycount += cnt > 0 ? cnt : 0;
+		for (int j = 0; j < CPT; j++) {
+			const int ch = tid * CPT + j;
+			const int64_t gbase = tb + ch * 16;
+			uint32_t m = reinterpret_cast<const uint16_t *>(bmask)[BH / 16 + ch];
+			if (gbase >= a.total) m = 0;
+			else if (gbase + 16 > a.total) m &= (1u << (int) (a.total - gbase)) - 1u;
+			bits[j] = m;
+			mycount += __popc(m);
+			if (a.piece_flags)
+				for (int i = 0; i < 16 && gbase + i < a.total; i++) a.piece_flags[gbase + i] = (m >> i) & 1u;
 		}
-		int x = mycount;
-		for (int o = 1; o < 32; o <<= 1) {
-			int y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-			if (lane >= o) x += y;
-		}
-		if (lane == 31) misc[M_WSUM + warp] = (uint32_t) x;
-		__syncthreads();
-		if (warp == 0) {
-			int v = lane < NWARPS ? (int) misc[M_WSUM + lane] : 0;
-			for (int o = 1; o < 32; o <<= 1) {
-				int y = __shfl_up_sync(0xFFFFFFFFu, v, o);
-				if (lane >= o) v += y;
-			}
-			if (lane < NWARPS) misc[M_WSUM + lane] = (uint32_t) v;
-			if (lane == NWARPS - 1) a.tile_count[tile] = v;
-			/* first piece start of the tile, for the long-piece bounds kernel */
-			int fb = 0x7fffffff;
-			for (int w = BH / 32 + lane; w < (BH + JTK_TILE) / 32; w += 32) {
-				uint32_t bits = bmask[w];
-				if (bits) fb = min(fb, (w << 5) + __ffs((int) bits) - 1);
-			}
-			fb = __reduce_min_sync(0xFFFFFFFFu, fb);
-			if (lane == 0) a.tile_first_b[tile] = fb == 0x7fffffff ? -1 : c.g0 + fb;
-		}
-		__syncthreads();
-		const int excl = x - mycount + (warp ? (int) misc[M_WSUM + warp - 1] : 0);
-		chunk_pref[tid] = (uint32_t) excl;
-		const bool write_ids = !(a.flags & JTK_COUNT_ONLY) && a.stage != nullptr;
-		{
-			int32_t *dst = a.stage + tile * (long long) TOKN;
-			int pos = excl;
-			for (uint32_t m = mybits; m;) {
+		int npieces;
+		int base = block_exclusive_scan<NT>(mycount, reinterpret_cast<int *>(misc + M_WSUM), &npieces);
+		for (int j = 0; j < CPT; j++) {
+			const int ch = tid * CPT + j;
+			chunk_pref[ch] = (uint32_t) base;
+			for (uint32_t m = bits[j]; m;) {
 				const int i = __ffs((int) m) - 1;
 				m &= m - 1;
-				const int s = r0 + i - BH;
-				const int cnt = rk[s];
-				if (cnt < 0) {
+				plist[base++] = (uint16_t) (BH + ch * 16 + i);
+			}
+		}
+		if (tid == 0) {
+			/* first piece start of the tile (the end of the input counts), for the long-piece bounds kernel */
+			const int fb = next_bit(bmask, BH, BH + JTK_TILE - 1);
+			a.tile_first_b[tile] = fb < 0 ? -1 : c.g0 + fb;
+			a.npieces[tile] = npieces;
+		}
+		__syncthreads();
+
+		/* ---- P4b: one piece per thread: whole-piece lookup (GptBytePairEncoding.java:81-83) ---- */
+		int32_t *rec = a.rec + lt * (long long) RECN;
+		int hits = 0;
+		for (int q0 = 0; q0 < npieces; q0 += NT) {
+			const int q = q0 + tid;
+			if (q < npieces) {
+				const int r = plist[q];
+				const int s = r - BH;
+				int e = (q + 1 < npieces) ? (int) plist[q + 1] : next_bit(bmask, r + 1, r + JTK_LONG_PIECE);
+				if (e >= 0 && e - r > JTK_LONG_PIECE) e = -1;
+				int32_t out;
+				if (e < 0) { /* longer than JTK_LONG_PIECE: deferred to the long-piece kernels */
 					const unsigned idx = atomicAdd(&a.hdr->n_long, 1u);
 					if ((int64_t) idx < a.long_cap) {
 						jtk_long_piece lp;
-						lp.start = gbase + i;
-						const int e = next_bit(bmask, r0 + i + 1, JTK_REGION - 1);
-						lp.end = e < 0 ? -1 : c.g0 + e;
-						lp.insert_at = pos; /* tile-local; jtk_long_bounds_kernel adds the tile's base */
+						lp.start = tb + s;
+						const int e2 = next_bit(bmask, r + 1, JTK_REGION - 1);
+						lp.end = e2 < 0 ? -1 : c.g0 + e2;
+						lp.insert_at = 0; /* set by the gather kernel */
 						lp.count = 0;
 						lp.scratch = 0;
 						lp.doc = 0;
 						lp.flags = 0;
 						a.long_list[idx] = lp;
 					}
-					continue;
+					a.slowtok[lt * (long long) RECN + s] = (int32_t) idx;
+					out = REC_BASE + (int32_t) (REC_LONG | ((uint32_t) s << 11));
+				} else {
+					const int n = e - r;
+					const uint8_t *p = sb + r;
+					if (n == 1) {
+						out = T.byte_id[p[0]];
+						if (out < JTK_PSEUDO_BASE + 256) {
+							flag_doc(a, tb + s, JTK_DOC_UNKNOWN_BYTES);
+							out = JTK_REC_MIN_ID; /* the document is in error; keep the record a plain id */
+						}
+						hits++;
+					} else {
+						out = jtk_lookup_piece(T, p, n);
+						if (out != JTK_RANK_MAX) {
+							hits++;
+						} else {
+							out = rec_make(s, n);
+							a.slowq[lt * (long long) QCAP + atomicAdd(&misc[M_NSLOW], 1u)] = (uint16_t) q;
+						}
+					}
 				}
-				if (write_ids)
-					for (int k = 0; k < cnt; k++) dst[pos + k] = tok[s + k];
-				pos += cnt;
+				rec[q] = out;
 			}
 		}
-		__syncthreads(); /* chunk_pref complete */
-		/* tile-local token offsets of the documents that start in this tile (the end of the input included);
-		 * jtk_gather_kernel adds the tile's base */
+		hits = __reduce_add_sync(0xFFFFFFFFu, hits);
+		if (lane == 0) atomicAdd(&misc[M_HITS], (uint32_t) hits);
+		/* tile-local piece index of the documents that start in this tile (the end of the input included);
+		 * jtk_gather_kernel turns it into a token offset */
 		if (a.tok_off) {
 			for (int64_t d = first_doc + tid; d <= a.ndocs; d += NT) {
 				const int64_t g = a.doc_off[d];
@@ -383,16 +365,207 @@ __global__ void __launch_bounds__(JTK_NT, 2) jtk_encode_tiles_kernel(const __gri
 				if (g < tb) continue;
 				const int s = (int) (g - tb);
 				const int ch = s >> 4;
-				long long off = chunk_pref[ch];
-				uint32_t bits = reinterpret_cast<const uint16_t *>(bmask)[BH / 16 + ch] & ((1u << (s & 15)) - 1u);
-				for (; bits;) {
-					const int i = __ffs((int) bits) - 1;
-					bits &= bits - 1;
-					const int cnt = rk[(ch << 4) + i];
-					off += cnt > 0 ? cnt : 0;
-				}
-				a.tok_off[d] = off;
+				uint32_t m = reinterpret_cast<const uint16_t *>(bmask)[BH / 16 + ch] & ((1u << (s & 15)) - 1u);
+				const int64_t gbase = tb + ch * 16;
+				if (gbase + 16 > a.total) m &= (1u << (int) (a.total - gbase)) - 1u;
+				a.tok_off[d] = (int64_t) chunk_pref[ch] + __popc(m);
 			}
+		}
+		__syncthreads();
+		if (tid == 0) {
+			a.nslow[tile] = (int32_t) misc[M_NSLOW];
+			a.tile_count[tile] = (int32_t) misc[M_HITS];
+		}
+	}
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * kernel 2: bytePairMerge for the pieces the lookup did not resolve (GptBytePairEncoding.java:85, 200-300)
+ * One CTA per tile.  The tile's unresolved pieces are counting-sorted by length so that the threads of a warp run
+ * merge loops of similar length; tokens go to the tile's slice of slowtok at the piece's byte position.
+ * ------------------------------------------------------------------------------------------- */
+constexpr int MNT = 128;
+constexpr int MNW = MNT / 32;
+
+__global__ void __launch_bounds__(MNT) jtk_merge_kernel(const __grid_constant__ jtk_encode_args a) {
+	__shared__ uint16_t s_order[QCAP];
+	__shared__ int s_hist[36], s_cursor[36];
+	__shared__ int32_t s_scr[2 * JTK_SHORT_PIECE * MNT]; /* short: tok / rk interleaved by thread; medium: per-warp tok / rk */
+	__shared__ int s_sum;
+	static_assert(2 * JTK_SHORT_PIECE * MNT >= MNW * 2 * JTK_LONG_PIECE, "medium scratch must fit");
+	const jtk_tables &T = a.T;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const long long tile = a.tile_begin + blockIdx.x;
+	if (tile >= a.tile_end) return;
+	const int S = a.nslow[tile];
+	if (S == 0) return;
+	const long long lt = tile - a.tile_begin;
+	const int64_t tb = tile * (int64_t) JTK_TILE;
+	int32_t *rec = a.rec + lt * (long long) RECN;
+	const uint16_t *sq = a.slowq + lt * (long long) QCAP;
+	int32_t *stok = a.slowtok + lt * (long long) RECN;
+	const bool write_tok = !(a.flags & JTK_COUNT_ONLY);
+
+	if (tid < 36) s_hist[tid] = 0;
+	if (tid == 0) s_sum = 0;
+	__syncthreads();
+	for (int k = tid; k < S; k += MNT) {
+		const int n = (int) (rec_payload(rec[sq[k]]) & 0x7FFu) + 1;
+		atomicAdd(&s_hist[n <= JTK_SHORT_PIECE ? n : JTK_SHORT_PIECE + 1], 1);
+	}
+	__syncthreads();
+	if (tid == 0) {
+		int run = 0;
+		for (int b = 0; b < 36; b++) {
+			s_cursor[b] = run;
+			run += s_hist[b];
+		}
+	}
+	__syncthreads();
+	const int nshort = s_cursor[JTK_SHORT_PIECE + 1];
+	for (int k = tid; k < S; k += MNT) {
+		const int q = sq[k];
+		const int n = (int) (rec_payload(rec[q]) & 0x7FFu) + 1;
+		s_order[atomicAdd(&s_cursor[n <= JTK_SHORT_PIECE ? n : JTK_SHORT_PIECE + 1], 1)] = (uint16_t) q;
+	}
+	__syncthreads();
+
+	int sum = 0;
+	/* short pieces: one thread each, scratch interleaved by thread (bank = thread) */
+	for (int i = tid; i < nshort; i += MNT) {
+		const int q = s_order[i];
+		const uint32_t pl = rec_payload(rec[q]);
+		const int s = (int) (pl >> 11), n = (int) (pl & 0x7FFu) + 1;
+		bool unk = false;
+		int32_t *tk = s_scr + tid, *rk = s_scr + JTK_SHORT_PIECE * MNT + tid;
+		const int cnt = jtk_merge_short(T, a.bytes + tb + s, n, tk, rk, MNT, &unk);
+		if (write_tok)
+			for (int k = 0; k < cnt; k++) stok[s + k] = tk[k * MNT];
+		rec[q] = rec_make(s, cnt);
+		sum += cnt;
+		if (unk) flag_doc(a, tb + s, JTK_DOC_UNKNOWN_BYTES);
+	}
+	__syncthreads();
+	/* medium pieces: one warp each */
+	for (int j = nshort + warp; j < S; j += MNW) {
+		const int q = s_order[j];
+		const uint32_t pl = rec_payload(rec[q]);
+		const int s = (int) (pl >> 11), n = (int) (pl & 0x7FFu) + 1;
+		bool unk = false;
+		int32_t *tk = s_scr + warp * 2 * JTK_LONG_PIECE, *rk = tk + JTK_LONG_PIECE;
+		const int cnt = merge_warp(T, a.bytes + tb + s, n, tk, rk, &unk);
+		__syncwarp();
+		if (write_tok)
+			for (int k = lane; k < cnt; k += 32) stok[s + k] = tk[k];
+		__syncwarp();
+		if (lane == 0) {
+			rec[q] = rec_make(s, cnt);
+			sum += cnt;
+			if (unk) flag_doc(a, tb + s, JTK_DOC_UNKNOWN_BYTES);
+		}
+	}
+	sum = __reduce_add_sync(0xFFFFFFFFu, sum);
+	if (lane == 0) atomicAdd(&s_sum, sum);
+	__syncthreads();
+	if (tid == 0) a.tile_count[tile] += s_sum;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * kernel 3: exclusive scan of the per-tile token counts of the sub-batch, continuing the batch total
+ * ------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(1024, 1) jtk_tile_scan_kernel(const jtk_encode_args a) {
+	__shared__ long long s_w[32];
+	__shared__ long long s_carry;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid == 0) s_carry = (long long) a.hdr->total_tokens;
+	__syncthreads();
+	for (int64_t base = a.tile_begin; base < a.tile_end; base += 1024) {
+		const int64_t i = base + tid;
+		const long long val = i < a.tile_end ? a.tile_count[i] : 0;
+		long long x = val;
+		for (int o = 1; o < 32; o <<= 1) {
+			long long y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+			if (lane >= o) x += y;
+		}
+		if (lane == 31) s_w[warp] = x;
+		__syncthreads();
+		if (warp == 0) {
+			long long w = s_w[lane];
+			for (int o = 1; o < 32; o <<= 1) {
+				long long y = __shfl_up_sync(0xFFFFFFFFu, w, o);
+				if (lane >= o) w += y;
+			}
+			s_w[lane] = w;
+		}
+		__syncthreads();
+		const long long excl = s_carry + x - val + (warp ? s_w[warp - 1] : 0);
+		if (i < a.tile_end) a.tile_base[i] = excl;
+		__syncthreads();
+		if (tid == 1023) s_carry = excl + val;
+		__syncthreads();
+	}
+	if (tid == 0) {
+		a.tile_base[a.tile_end] = s_carry;
+		a.hdr->total_tokens = (unsigned long long) s_carry;
+		a.hdr->ticket = 0; /* the next sub-batch starts its tickets at zero */
+		if (!(a.flags & JTK_COUNT_ONLY) && a.ids && s_carry > a.ids_cap) a.hdr->overflow = 1;
+	}
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * kernel 4: ids to their final position (one CTA per tile) + document token offsets
+ * ------------------------------------------------------------------------------------------- */
+constexpr int GNT = 256;
+
+__global__ void __launch_bounds__(GNT) jtk_gather_kernel(const __grid_constant__ jtk_encode_args a) {
+	__shared__ uint32_t s_prefix[RECN + 1]; /* tokens before each piece of the tile */
+	__shared__ int s_w[GNT / 32];
+	const int tid = threadIdx.x;
+	const long long tile = a.tile_begin + blockIdx.x;
+	if (tile >= a.tile_end) return;
+	const long long lt = tile - a.tile_begin;
+	const int64_t tb = tile * (int64_t) JTK_TILE;
+	const int P = a.npieces[tile];
+	const long long base = a.tile_base[tile];
+	const int32_t *rec = a.rec + lt * (long long) RECN;
+	const int32_t *stok = a.slowtok + lt * (long long) RECN;
+	const bool write_ids = !(a.flags & JTK_COUNT_ONLY) && a.ids != nullptr && !a.hdr->overflow;
+	int carry = 0;
+	for (int q0 = 0; q0 < P; q0 += GNT) {
+		const int q = q0 + tid;
+		int32_t r = 0;
+		int cnt = 0;
+		if (q < P) {
+			r = rec[q];
+			if (rec_is_id(r)) cnt = 1;
+			else if (!(rec_payload(r) & REC_LONG)) cnt = (int) (rec_payload(r) & 0x7FFu) + 1;
+		}
+		int round_total;
+		const int excl = carry + block_exclusive_scan<GNT>(cnt, s_w, &round_total);
+		if (q < P) {
+			s_prefix[q] = (uint32_t) excl;
+			if (rec_is_id(r)) {
+				if (write_ids) a.ids[base + excl] = r;
+			} else {
+				const uint32_t pl = rec_payload(r);
+				const int s = (int) ((pl >> 11) & 0x1FFFu);
+				if (pl & REC_LONG) {
+					a.long_list[stok[s]].insert_at = base + excl;
+				} else if (write_ids) {
+					for (int k = 0; k < cnt; k++) a.ids[base + excl + k] = stok[s + k];
+				}
+			}
+		}
+		carry += round_total;
+	}
+	if (tid == 0) s_prefix[P] = (uint32_t) carry;
+	__syncthreads();
+	if (a.tok_off) {
+		for (int64_t d = a.tile_first_doc[tile] + tid; d <= a.ndocs; d += GNT) {
+			const int64_t g = a.doc_off[d];
+			if (g >= tb + JTK_TILE) break;
+			if (g < tb) continue;
+			a.tok_off[d] = base + s_prefix[a.tok_off[d]];
 		}
 	}
 }
@@ -411,63 +584,18 @@ __global__ void jtk_tile_first_doc_kernel(const int64_t *doc_off, int64_t ndocs,
 	out[t] = (int32_t) lo;
 }
 
-/* exclusive scan of the per-tile token counts (one block; ntiles is ~131k per GiB) + batch totals */
-__global__ void __launch_bounds__(1024, 1) jtk_tile_scan_kernel(const jtk_encode_args a) {
-	__shared__ long long s_w[32];
-	__shared__ long long s_carry;
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	if (tid == 0) s_carry = 0;
-	__syncthreads();
-	for (int64_t base = 0; base < a.ntiles; base += 1024) {
-		const int64_t i = base + tid;
-		const long long val = i < a.ntiles ? a.tile_count[i] : 0;
-		long long x = val;
-		for (int o = 1; o < 32; o <<= 1) {
-			long long y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-			if (lane >= o) x += y;
-		}
-		if (lane == 31) s_w[warp] = x;
-		__syncthreads();
-		if (warp == 0) {
-			long long w = s_w[lane];
-			for (int o = 1; o < 32; o <<= 1) {
-				long long y = __shfl_up_sync(0xFFFFFFFFu, w, o);
-				if (lane >= o) w += y;
-			}
-			s_w[lane] = w;
-		}
-		__syncthreads();
-		const long long excl = s_carry + x - val + (warp ? s_w[warp - 1] : 0);
-		if (i < a.ntiles) a.tile_base[i] = excl;
-		__syncthreads();
-		if (tid == 1023) s_carry = excl + val;
-		__syncthreads();
+/* token offsets of the (empty) documents that start at the very end of the input when it ends on a tile boundary */
+__global__ void jtk_finalize_kernel(const jtk_encode_args a) {
+	if (!a.tok_off) return;
+	const long long total_tokens = (long long) a.hdr->total_tokens;
+	const int64_t covered = a.ntiles * (int64_t) JTK_TILE;
+	int64_t lo = 0, hi = a.ndocs + 1; /* first d with doc_off[d] >= covered */
+	while (lo < hi) {
+		int64_t mid = (lo + hi) >> 1;
+		if (a.doc_off[mid] >= covered) hi = mid;
+		else lo = mid + 1;
 	}
-	if (tid == 0) {
-		a.tile_base[a.ntiles] = s_carry;
-		a.hdr->total_tokens = (unsigned long long) s_carry;
-		if (!(a.flags & JTK_COUNT_ONLY) && a.ids && s_carry > a.ids_cap) a.hdr->overflow = 1;
-	}
-}
-
-/* staging -> final ids (one CTA per tile, coalesced both ways) and tile-local -> global document token offsets */
-__global__ void __launch_bounds__(256) jtk_gather_kernel(const jtk_encode_args a) {
-	const bool write_ids = !(a.flags & JTK_COUNT_ONLY) && a.ids != nullptr && a.stage != nullptr && !a.hdr->overflow;
-	if (write_ids) {
-		for (int64_t t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
-			const int32_t *src = a.stage + t * (long long) TOKN;
-			int32_t *dst = a.ids + a.tile_base[t];
-			const int n = a.tile_count[t];
-			for (int k = threadIdx.x; k < n; k += blockDim.x) dst[k] = src[k];
-		}
-	}
-	if (a.tok_off) {
-		const long long total_tokens = a.tile_base[a.ntiles];
-		for (int64_t d = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; d <= a.ndocs; d += (int64_t) gridDim.x * blockDim.x) {
-			const int64_t t = a.doc_off[d] / JTK_TILE;
-			a.tok_off[d] = t >= a.ntiles ? total_tokens : a.tok_off[d] + a.tile_base[t];
-		}
-	}
+	for (int64_t d = lo + blockIdx.x * (int64_t) blockDim.x + threadIdx.x; d <= a.ndocs; d += (int64_t) gridDim.x * blockDim.x) a.tok_off[d] = total_tokens;
 }
 
 /* =============================================================================================
@@ -484,7 +612,6 @@ __global__ void jtk_long_bounds_kernel(const jtk_encode_args a, unsigned int n_l
 	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n_long) return;
 	jtk_long_piece lp = a.long_list[i];
-	a.long_list[i].insert_at = lp.insert_at + a.tile_base[lp.start / JTK_TILE];
 	if (lp.end < 0) {
 		int64_t end = a.total;
 		for (int64_t t = lp.start / JTK_TILE + 1; t < a.ntiles; t++) {
@@ -776,7 +903,7 @@ __global__ void jtk_long_fix_offsets_kernel(const jtk_long_piece *list, const in
  * launch wrappers
  * ============================================================================================= */
 cudaError_t jtk_encode_kernel_setup() {
-	return cudaFuncSetAttribute(jtk_encode_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JTK_SMEM_BYTES);
+	return cudaFuncSetAttribute(jtk_split_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JTK_SMEM_BYTES);
 }
 
 cudaError_t jtk_launch_tile_first_doc(const int64_t *doc_off, int64_t ndocs, int64_t ntiles, int32_t *out, cudaStream_t st) {
@@ -785,18 +912,23 @@ cudaError_t jtk_launch_tile_first_doc(const int64_t *doc_off, int64_t ndocs, int
 	return cudaGetLastError();
 }
 
-cudaError_t jtk_launch_encode_tiles(const jtk_encode_args &a, int num_sms, cudaStream_t st) {
-	if (a.ntiles <= 0) return cudaSuccess;
+/* the four kernels of one sub-batch [a.tile_begin, a.tile_end) */
+cudaError_t jtk_launch_sub_batch(const jtk_encode_args &a, int num_sms, cudaEvent_t k0, cudaEvent_t k1, cudaStream_t st) {
+	const int64_t nt = a.tile_end - a.tile_begin;
+	if (nt <= 0) return cudaSuccess;
 	int64_t grid = (int64_t) num_sms * 2;
-	if (grid > a.ntiles) grid = a.ntiles;
-	jtk_encode_tiles_kernel<<<(unsigned) grid, JTK_NT, JTK_SMEM_BYTES, st>>>(a);
+	if (grid > nt) grid = nt;
+	if (k0) cudaEventRecord(k0, st);
+	jtk_split_lookup_kernel<<<(unsigned) grid, JTK_NT, JTK_SMEM_BYTES, st>>>(a);
+	if (k1) cudaEventRecord(k1, st);
+	jtk_merge_kernel<<<(unsigned) nt, MNT, 0, st>>>(a);
+	jtk_tile_scan_kernel<<<1, 1024, 0, st>>>(a);
+	jtk_gather_kernel<<<(unsigned) nt, GNT, 0, st>>>(a);
 	return cudaGetLastError();
 }
 
-cudaError_t jtk_launch_scan_gather(const jtk_encode_args &a, int num_sms, cudaStream_t st) {
-	jtk_tile_scan_kernel<<<1, 1024, 0, st>>>(a);
-	int64_t grid = std::max<int64_t>(std::min<int64_t>(std::max<int64_t>(a.ntiles, (a.ndocs + 256) / 256), (int64_t) num_sms * 16), 1);
-	jtk_gather_kernel<<<(unsigned) grid, 256, 0, st>>>(a);
+cudaError_t jtk_launch_finalize(const jtk_encode_args &a, cudaStream_t st) {
+	jtk_finalize_kernel<<<8, 256, 0, st>>>(a);
 	return cudaGetLastError();
 }
 

@@ -31,17 +31,30 @@ struct jtk_batch_header {
 	unsigned int pad;
 };
 
+#define JTK_RECN (JTK_TILE + JTK_FWD_HALO) /* per-tile slots of rec / slowtok: pieces + unresolved pieces <= JTK_RECN */
+#define JTK_QCAP (JTK_RECN / 2)            /* an unresolved piece has at least two bytes */
+#define JTK_REC_MIN_ID (-(1 << 30))        /* token ids below this are rejected at registration; the space encodes piece records */
+#define JTK_DEFAULT_SUB_TILES 4096         /* tiles per sub-batch: 32 MiB of input, intermediates stay around the L2 size */
+
 struct jtk_encode_args {
 	jtk_tables T;
 	const uint8_t *bytes;
 	int64_t total;
 	const int64_t *doc_off;
 	int64_t ndocs;
-	const int32_t *tile_first_doc;
 	int64_t ntiles;
-	int32_t *tile_count;   /* tokens produced by each tile */
+	int64_t tile_begin, tile_end; /* the sub-batch */
+	/* per tile, whole batch */
+	const int32_t *tile_first_doc;
+	int32_t *npieces;      /* pieces that start in the tile */
+	int32_t *nslow;        /* of those, pieces the whole-piece lookup did not resolve */
+	int32_t *tile_count;   /* tokens produced by the tile */
 	int64_t *tile_base;    /* ntiles + 1: exclusive scan of tile_count */
-	int32_t *stage;        /* ntiles * (JTK_TILE + JTK_FWD_HALO) tile-local token staging (nullable with JTK_COUNT_ONLY) */
+	int64_t *tile_first_b; /* first piece start in the tile (global position) or -1 */
+	/* per tile of the sub-batch (index tile - tile_begin) */
+	int32_t *rec;          /* JTK_RECN per tile: one record per piece, in order */
+	int32_t *slowtok;      /* JTK_RECN per tile: tokens of merged pieces at the piece's tile-local byte position */
+	uint16_t *slowq;       /* JTK_QCAP per tile: piece indices of the unresolved pieces */
 	jtk_batch_header *hdr;
 	int32_t *ids;
 	int64_t ids_cap;
@@ -50,17 +63,15 @@ struct jtk_encode_args {
 	uint32_t flags;
 	jtk_long_piece *long_list;
 	int64_t long_cap;
-	int64_t *tile_first_b; /* per tile: first piece start in the tile (global position) or -1 */
 	uint8_t *piece_flags;  /* debug: one byte per input byte, 1 where a piece starts (nullable) */
 };
 
-#define JTK_SMEM_BYTES                                                                                                              \
-	(2 * (JTK_REGION + 16) + 2 * 4 * (((JTK_REGION + 32) / 32 + 1)) + 2 * 4 * (JTK_TILE + JTK_FWD_HALO) + 2 * ((JTK_TILE + JTK_FWD_HALO) / 2) + \
-	 4 * JTK_NT + 256)
+#define JTK_SMEM_BYTES (2 * (JTK_REGION + 16) + 2 * 4 * (((JTK_REGION + 32) / 32 + 1)) + 2 * JTK_RECN + 4 * (JTK_TILE / 16) + 256)
 
 cudaError_t jtk_launch_tile_first_doc(const int64_t *doc_off, int64_t ndocs, int64_t ntiles, int32_t *out, cudaStream_t st);
-cudaError_t jtk_launch_encode_tiles(const jtk_encode_args &a, int num_sms, cudaStream_t st);
-cudaError_t jtk_launch_scan_gather(const jtk_encode_args &a, int num_sms, cudaStream_t st);
+/* the four kernels of one sub-batch; k0/k1 (nullable) bracket the split+lookup kernel */
+cudaError_t jtk_launch_sub_batch(const jtk_encode_args &a, int num_sms, cudaEvent_t k0, cudaEvent_t k1, cudaStream_t st);
+cudaError_t jtk_launch_finalize(const jtk_encode_args &a, cudaStream_t st);
 cudaError_t jtk_encode_kernel_setup();
 
 /* long-piece path */

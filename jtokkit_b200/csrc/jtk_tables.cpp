@@ -221,8 +221,8 @@ int jtk_build_host_tables(const jtk_params *p, jtk_host_tables *t, std::string *
 			return JTK_E_ARG;
 		}
 		int32_t rank = p->vocab_ranks[i];
-		if (rank >= JTK_RANK_MAX - 1 || (rank >= JTK_PSEUDO_BASE && rank < JTK_PSEUDO_BASE + 256)) {
-			*err = "a rank is >= Integer.MAX_VALUE - 1 or falls into the reserved range [INT_MIN, INT_MIN+255]";
+		if (rank >= JTK_RANK_MAX - 1 || rank < -(1 << 30)) {
+			*err = "token ids must lie in [-2^30, Integer.MAX_VALUE - 2] (the rest of the int range encodes device-side records)";
 			return JTK_E_ARG;
 		}
 		std::string key((const char *) p->vocab_bytes + a, (size_t) (b - a));

@@ -154,7 +154,7 @@ int64_t emu_run(const emu_encoding *e, const uint8_t *bytes, int64_t total, cons
 			} else {
 				std::vector<int32_t> t2((size_t) n), r2((size_t) n), nx((size_t) n + 1);
 				int cnt;
-				if (n <= JTK_SHORT_PIECE) cnt = jtk_merge_short(e->view, p, (int) n, t2.data(), r2.data(), &unknown);
+				if (n <= JTK_SHORT_PIECE) cnt = jtk_merge_short(e->view, p, (int) n, t2.data(), r2.data(), 1, &unknown);
 				else cnt = jtk_merge_seq(e->view, p, (int) n, t2.data(), r2.data(), nx.data(), &unknown);
 				for (int k = 0; k < cnt; k++) ids[out_pos++] = t2[(size_t) k];
 			}

@@ -45,6 +45,7 @@ struct jtk_workspace {
 	int64_t sub_tiles = 0;
 	int32_t *rec = nullptr, *slowtok = nullptr;
 	uint16_t *slowq = nullptr;
+	uint32_t *med8 = nullptr, *med32 = nullptr;
 	std::vector<cudaEvent_t> kev; /* event pairs around the split+lookup kernel of every sub-batch (JTK_TIME_KERNEL) */
 	int64_t *tile_first_b = nullptr;
 	jtk_long_piece *long_list = nullptr;
@@ -65,6 +66,8 @@ struct jtk_device_state {
 	int num_sms = 0;
 	jtk_tables T;
 	std::vector<void *> allocs;
+	const void *l2_base = nullptr; /* hot tables: L2 access-policy window */
+	size_t l2_bytes = 0;
 	std::mutex mu;
 	std::vector<jtk_workspace *> free_ws;
 };
@@ -98,16 +101,23 @@ static int device_index(const jtk_encoding *e, int device) {
 	return -1;
 }
 
-template <typename Tv>
-static int upload(jtk_device_state *ds, const std::vector<Tv> &v, const Tv **out) {
-	void *p = nullptr;
-	size_t bytes = std::max<size_t>(v.size() * sizeof(Tv), 16);
-	CUDA_TRY(cudaMalloc(&p, bytes));
-	ds->allocs.push_back(p);
-	if (!v.empty()) CUDA_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(Tv), cudaMemcpyHostToDevice));
-	*out = reinterpret_cast<const Tv *>(p);
-	return JTK_OK;
-}
+/* All tables of an encoding live in ONE device allocation so that a single L2 access-policy window can pin them
+ * (persisting hits, streaming misses for everything else): the piece table, pair table and byte-pair table are probed
+ * once or twice per piece and must not be evicted by the input / id streams. */
+struct table_arena {
+	std::vector<std::pair<const void *, size_t>> parts;
+	std::vector<size_t> offsets;
+	size_t total = 0;
+	template <typename Tv>
+	size_t add(const std::vector<Tv> &v) {
+		size_t bytes = std::max<size_t>(v.size() * sizeof(Tv), 16);
+		size_t off = total;
+		parts.emplace_back(v.data(), v.size() * sizeof(Tv));
+		offsets.push_back(off);
+		total = (off + bytes + 255) & ~(size_t) 255;
+		return off;
+	}
+};
 
 static int init_device(jtk_encoding *e, int device) {
 	jtk_device_state *ds = new jtk_device_state();
@@ -123,25 +133,33 @@ static int init_device(jtk_encoding *e, int device) {
 	memset(&T, 0, sizeof(T));
 	T.pattern_kind = h.pattern_kind;
 	T.max_token_len = h.max_token_len;
-	int rc;
-#define UP(field) \
-	if ((rc = upload(ds, h.field, &T.field)) != JTK_OK) return rc
-	UP(ascii_cls);
-	UP(cp_stage1);
-	UP(cp_stage2);
-	UP(tab_a);
-	UP(tab_b);
-	UP(tok_bytes);
-	UP(tok_off);
-	UP(byte_id);
-	UP(bytepair);
-	UP(pair);
-	UP(special_bytes);
-	UP(special_off);
-	UP(dec_keys);
-	UP(dec_bytes);
-	UP(dec_off);
-#undef UP
+	table_arena ar;
+	/* hot tables first: they form the persisting window */
+	const size_t o_tab_a = ar.add(h.tab_a), o_pair = ar.add(h.pair), o_bytepair = ar.add(h.bytepair), o_byte_id = ar.add(h.byte_id);
+	const size_t o_ascii = ar.add(h.ascii_cls), o_st1 = ar.add(h.cp_stage1), o_st2 = ar.add(h.cp_stage2), o_tab_b = ar.add(h.tab_b);
+	const size_t hot_bytes = ar.total;
+	const size_t o_tokb = ar.add(h.tok_bytes), o_toko = ar.add(h.tok_off), o_spb = ar.add(h.special_bytes), o_spo = ar.add(h.special_off);
+	const size_t o_deck = ar.add(h.dec_keys), o_decb = ar.add(h.dec_bytes), o_deco = ar.add(h.dec_off);
+	uint8_t *base = nullptr;
+	CUDA_TRY(cudaMalloc(&base, ar.total));
+	ds->allocs.push_back(base);
+	for (size_t i = 0; i < ar.parts.size(); i++)
+		if (ar.parts[i].second) CUDA_TRY(cudaMemcpy(base + ar.offsets[i], ar.parts[i].first, ar.parts[i].second, cudaMemcpyHostToDevice));
+	T.tab_a = reinterpret_cast<const jtk_slot *>(base + o_tab_a);
+	T.pair = reinterpret_cast<const jtk_slot *>(base + o_pair);
+	T.bytepair = reinterpret_cast<const int32_t *>(base + o_bytepair);
+	T.byte_id = reinterpret_cast<const int32_t *>(base + o_byte_id);
+	T.ascii_cls = base + o_ascii;
+	T.cp_stage1 = reinterpret_cast<const uint16_t *>(base + o_st1);
+	T.cp_stage2 = base + o_st2;
+	T.tab_b = reinterpret_cast<const jtk_slot *>(base + o_tab_b);
+	T.tok_bytes = base + o_tokb;
+	T.tok_off = reinterpret_cast<const uint32_t *>(base + o_toko);
+	T.special_bytes = base + o_spb;
+	T.special_off = reinterpret_cast<const uint32_t *>(base + o_spo);
+	T.dec_keys = reinterpret_cast<const uint32_t *>(base + o_deck);
+	T.dec_bytes = base + o_decb;
+	T.dec_off = reinterpret_cast<const uint32_t *>(base + o_deco);
 	T.mask_a = h.mask_a;
 	T.mask_b = h.mask_b;
 	T.mask_p = h.mask_p;
@@ -149,6 +167,27 @@ static int init_device(jtk_encoding *e, int device) {
 	T.nspecial = h.nspecial;
 	T.special_has_empty = h.special_has_empty;
 	memcpy(T.special_first, h.special_first, sizeof(T.special_first));
+	{
+		int nfirst = 0, first = 0;
+		for (int b = 0; b < 256; b++)
+			if ((h.special_first[b >> 5] >> (b & 31)) & 1u) {
+				nfirst++;
+				first = b;
+			}
+		T.special_first_single = (nfirst == 1 && first != 0) ? (uint32_t) first : 0u;
+	}
+	/* L2 persisting window over the hot tables (bounded by what the device allows) */
+	ds->l2_base = base;
+	ds->l2_bytes = std::min<size_t>(hot_bytes, (size_t) std::max(prop.accessPolicyMaxWindowSize, 0));
+	if (prop.persistingL2CacheMaxSize > 0 && ds->l2_bytes > 0) {
+		size_t want = std::min<size_t>((size_t) prop.persistingL2CacheMaxSize, ds->l2_bytes + (ds->l2_bytes >> 2));
+		if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
+			cudaGetLastError();
+			ds->l2_bytes = 0;
+		}
+	} else {
+		ds->l2_bytes = 0;
+	}
 	CUDA_TRY(jtk_encode_kernel_setup());
 	return JTK_OK;
 }
@@ -238,6 +277,8 @@ static void free_workspace(jtk_workspace *w) {
 	cudaFree(w->rec);
 	cudaFree(w->slowtok);
 	cudaFree(w->slowq);
+	cudaFree(w->med8);
+	cudaFree(w->med32);
 	for (cudaEvent_t ev : w->kev) cudaEventDestroy(ev);
 	cudaFree(w->tile_first_b);
 	cudaFree(w->long_list);
@@ -321,12 +362,17 @@ static int ensure_ws_tiles(jtk_workspace *w, int64_t ntiles, int64_t long_cap) {
 		cudaFree(w->rec);
 		cudaFree(w->slowtok);
 		cudaFree(w->slowq);
+		cudaFree(w->med8);
+		cudaFree(w->med32);
 		w->rec = w->slowtok = nullptr;
 		w->slowq = nullptr;
+		w->med8 = w->med32 = nullptr;
 		w->sub_tiles = 0;
 		CUDA_TRY(cudaMalloc(&w->rec, sizeof(int32_t) * (size_t) sub * JTK_RECN));
 		CUDA_TRY(cudaMalloc(&w->slowtok, sizeof(int32_t) * (size_t) sub * JTK_RECN));
 		CUDA_TRY(cudaMalloc(&w->slowq, sizeof(uint16_t) * (size_t) sub * JTK_QCAP));
+		CUDA_TRY(cudaMalloc(&w->med8, sizeof(uint32_t) * (size_t) sub * JTK_MED8_PER_TILE));
+		CUDA_TRY(cudaMalloc(&w->med32, sizeof(uint32_t) * (size_t) sub * JTK_MED32_PER_TILE));
 		w->sub_tiles = sub;
 	}
 	if (long_cap > w->long_cap) {
@@ -351,9 +397,13 @@ static void fill_args(jtk_encode_args &a, const jtk_device_state *ds, const jtk_
 	a.rec = w->rec;
 	a.slowtok = w->slowtok;
 	a.slowq = w->slowq;
+	a.med8 = w->med8;
+	a.med32 = w->med32;
 	a.hdr = w->hdr;
 	a.long_list = w->long_list;
 	a.long_cap = w->long_cap;
+	a.l2_base = ds->l2_base;
+	a.l2_bytes = ds->l2_bytes;
 }
 
 /* ------------------------------------------------------------------ the device-resident batch */
@@ -459,7 +509,7 @@ static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspa
 		CUDA_TRY(jtk_launch_sub_batch(a, ds->num_sms, time_kernel ? w->kev[(size_t) (2 * i)] : nullptr, time_kernel ? w->kev[(size_t) (2 * i + 1)] : nullptr, st));
 	}
 	CUDA_TRY(jtk_launch_finalize(a, st));
-	info->gpu_launches = (ntiles > 0 ? 1 : 0) + 4 * nsub + 1;
+	info->gpu_launches = (ntiles > 0 ? 1 : 0) + 5 * nsub + 1;
 	CUDA_TRY(cudaMemcpyAsync(w->hdr_host, w->hdr, sizeof(jtk_batch_header), cudaMemcpyDeviceToHost, st));
 	if (!sync_and_long) return JTK_OK;
 	CUDA_TRY(cudaStreamSynchronize(st));

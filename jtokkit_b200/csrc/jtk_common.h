@@ -104,6 +104,7 @@ struct jtk_tables {
 	const uint8_t *special_bytes;
 	const uint32_t *special_off; /* nspecial + 1 */
 	uint32_t special_first[8];   /* bitmap of first bytes */
+	uint32_t special_first_single; /* that byte when exactly one non-zero first byte occurs, else 0 */
 	/* decode (GptBytePairEncoding.java:136-151,302-314): id -> token index, open addressing {id, token index + 1} */
 	const uint32_t *dec_keys;    /* pairs (id, index + 1), 0 in the second word = empty */
 	uint32_t mask_d;

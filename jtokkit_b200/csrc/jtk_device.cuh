@@ -32,6 +32,7 @@ struct jtk_tile_ctx {
 	const int64_t *doc_off;
 	int64_t ndocs;
 	const jtk_tables *T;
+	const uint8_t *ascii_lut; /* T->ascii_cls or a shared-memory copy of it */
 };
 
 #define JTK_MASK_WORDS ((JTK_REGION + 32) / 32 + 1)
@@ -144,6 +145,20 @@ struct jtk_region_start {
 JTK_HD void jtk_classify_chunk(jtk_tile_ctx &c, int chunk) {
 	const jtk_tables &T = *c.T;
 	const int r0 = chunk * 16;
+	{
+		/* fast path: sixteen ASCII bytes are sixteen table reads (a character cannot straddle into an ASCII chunk) */
+		const uint32_t *w = reinterpret_cast<const uint32_t *>(c.sb + r0);
+		const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+		if (((w0 | w1 | w2 | w3) & 0x80808080u) == 0) {
+			uint32_t *o = reinterpret_cast<uint32_t *>(c.cls + r0);
+			const uint8_t *lut = c.ascii_lut;
+			o[0] = lut[w0 & 0xFF] | (lut[(w0 >> 8) & 0xFF] << 8) | (lut[(w0 >> 16) & 0xFF] << 16) | ((uint32_t) lut[w0 >> 24] << 24);
+			o[1] = lut[w1 & 0xFF] | (lut[(w1 >> 8) & 0xFF] << 8) | (lut[(w1 >> 16) & 0xFF] << 16) | ((uint32_t) lut[w1 >> 24] << 24);
+			o[2] = lut[w2 & 0xFF] | (lut[(w2 >> 8) & 0xFF] << 8) | (lut[(w2 >> 16) & 0xFF] << 16) | ((uint32_t) lut[w2 >> 24] << 24);
+			o[3] = lut[w3 & 0xFF] | (lut[(w3 >> 8) & 0xFF] << 8) | (lut[(w3 >> 16) & 0xFF] << 16) | ((uint32_t) lut[w3 >> 24] << 24);
+			return;
+		}
+	}
 	jtk_region_start is_start{&c};
 	int cur = JTK_C_O, rem = 0;
 	/* a character may have started in the previous chunk */
@@ -269,11 +284,11 @@ JTK_HD bool jtk_other_is_start(const jtk_tile_ctx &c, int r) {
 
 /* cur and prev are letters: did one of 's 't 'm 'd 're 've 'll end exactly before r? */
 JTK_HD bool jtk_ends_contraction(const jtk_tile_ctx &c, int r) {
-	int r1 = jtk_prev_lead(c, r);
-	int k1 = jtk_cls(c, r1);
-	bool single = (k1 >= JTK_C_LS && k1 <= JTK_C_LD);
-	bool second = (k1 == JTK_C_LE || k1 == JTK_C_LL);
+	const int k1 = jtk_cls(c, r - 1); /* continuation bytes carry their character's class */
+	const bool single = (k1 >= JTK_C_LS && k1 <= JTK_C_LD);
+	const bool second = (k1 == JTK_C_LE || k1 == JTK_C_LL);
 	if (!single && !second) return false;
+	const int r1 = jtk_prev_lead(c, r);
 	if (jtk_docstart(c, r1)) return false;
 	int r2 = jtk_prev_lead(c, r1);
 	int k2 = jtk_cls(c, r2);
@@ -395,10 +410,141 @@ JTK_HD bool jtk_is_piece_start(const jtk_tile_ctx &c, int r, int cur, int *nrun)
 	return false;
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * bit-parallel split rules for an all-ASCII neighbourhood
+ * The window is the 24 bytes [r0 - 4, r0 + 20) around chunk r0 .. r0 + 15; bit i of every mask stands for window
+ * position i, so "class of the previous character" is a left shift by one.  Preconditions (else the per-position
+ * rules below run): the window holds ASCII only, lies inside the usable region and the input, and contains no
+ * document start.  The formulas are the rules of jtk_is_piece_start written as boolean algebra; the emulator test
+ * (tests/test_emu_cpu.py) fuzzes both paths against the oracle.
+ * ------------------------------------------------------------------------------------------- */
+/* bit b of each of the four class bytes of w -> 4 mask bits */
+JTK_HD uint32_t jtk_plane4(uint32_t w, int b) { return (((w >> b) & 0x01010101u) * 0x01020408u) >> 24; }
+
+/* spread `seed` forward (towards higher positions) through runs of `run`: result has every position reachable from a
+ * seed bit by stepping +1 while staying inside run */
+JTK_HD uint32_t jtk_spread_up(uint32_t seed, uint32_t run) {
+	uint32_t f = seed | ((seed << 1) & run);
+	uint32_t m = run & (run << 1);
+	f |= (f << 2) & m;
+	m &= m << 2;
+	f |= (f << 4) & m;
+	m &= m << 4;
+	f |= (f << 8) & m;
+	m &= m << 8;
+	f |= (f << 16) & m;
+	return f;
+}
+/* same towards lower positions */
+JTK_HD uint32_t jtk_spread_down(uint32_t seed, uint32_t run) {
+	uint32_t f = seed | ((seed >> 1) & run);
+	uint32_t m = run & (run >> 1);
+	f |= (f >> 2) & m;
+	m &= m >> 2;
+	f |= (f >> 4) & m;
+	m &= m >> 4;
+	f |= (f >> 8) & m;
+	m &= m >> 8;
+	f |= (f >> 16) & m;
+	return f;
+}
+
+JTK_HD bool jtk_boundary_fast(const jtk_tile_ctx &c, int chunk, uint32_t *out) {
+	const int r0 = chunk * 16;
+	const int ws = r0 - 4; /* window start */
+	if (ws < c.rs || c.g0 + r0 + 20 > c.total) return false;
+	const uint32_t *bw = reinterpret_cast<const uint32_t *>(c.sb + ws);
+	if (((bw[0] | bw[1] | bw[2] | bw[3] | bw[4] | bw[5]) & 0x80808080u) != 0) return false;
+	{ /* document starts in [ws, ws + 24] */
+		const int wi = ws >> 5, sh = ws & 31;
+		uint32_t d = c.dmask[wi] >> sh;
+		if (sh > 7) d |= c.dmask[wi + 1] << (32 - sh);
+		if (d & 0x1FFFFFFu) return false;
+	}
+	const uint32_t *cw = reinterpret_cast<const uint32_t *>(c.cls + ws);
+	uint32_t P0 = 0, P1 = 0, P2 = 0, P3 = 0;
+	for (int k = 0; k < 6; k++) {
+		const uint32_t w = cw[k];
+		P0 |= jtk_plane4(w, 0) << (4 * k);
+		P1 |= jtk_plane4(w, 1) << (4 * k);
+		P2 |= jtk_plane4(w, 2) << (4 * k);
+		P3 |= jtk_plane4(w, 3) << (4 * k);
+	}
+	const uint32_t ALL = 0xFFFFFFu;
+	/* class masks from the four bit planes of the class code (jtk_common.h) */
+	const uint32_t O_ = ~P3 & ~P2 & ~P1 & ALL;          /* 0, 1 */
+	const uint32_t AP = O_ & P0;                          /* 1 */
+	const uint32_t SP = ~P3 & ~P2 & P1 & ~P0 & ALL;      /* 2 */
+	const uint32_t NL = ~P3 & ~P2 & P1 & P0;              /* 3 */
+	const uint32_t WO = ~P3 & P2 & ~P1 & ~P0 & ALL;      /* 4 */
+	const uint32_t N = ~P3 & P2 & ~P1 & P0;               /* 5 */
+	const uint32_t L = (P3 | (P2 & P1)) & ALL;            /* 6 .. 14 */
+	const uint32_t S1 = (~P3 & P2 & P1 & P0) | (P3 & ~P2 & ~(P1 & P0)); /* 7 .. 10: s t m d */
+	const uint32_t RV = (P3 & ~P2 & P1 & P0) | (P3 & P2 & ~P1 & ~P0);   /* 11, 12: r v */
+	const uint32_t LL = P3 & P2 & ~P1 & P0;               /* 13 */
+	const uint32_t LE = P3 & P2 & P1 & ~P0;               /* 14 */
+	const uint32_t Ostart = O_ & ~((O_ | SP) << 1);
+	const uint32_t APs = AP & Ostart;
+	const uint32_t CE = (L << 1) & (((S1 << 1) & (APs << 2)) | ((((LE << 1) & (RV << 2)) | ((LL << 1) & (LL << 2))) & (APs << 3)));
+	uint32_t B;
+	if (c.T->pattern_kind == JTK_PAT_CL100K) {
+		const uint32_t Wn = SP | WO, W = Wn | NL;
+		const uint32_t BL = L & ((N << 1) | (NL << 1) | ((O_ << 1) & ~(Ostart << 1)) | CE);
+		const uint32_t BNL = NL & ((L | N) << 1);
+		uint32_t BW = Wn & (~(W << 1) | (~W >> 1));
+		const uint32_t cand = Wn & (NL << 1) & ~BW & 0xFFFF0u; /* after an NL, followed by whitespace: needs the two run scans */
+		if (cand) {
+			/* does a \r\n come before the whitespace run ends?  unknown when the run leaves the window */
+			const uint32_t hit = jtk_spread_down(NL, Wn), edge = jtk_spread_down(Wn & 0x800000u, Wn);
+			const uint32_t nla = hit >> 1;
+			if (cand & (edge >> 1) & ~nla) return false;
+			BW |= cand & ~nla;
+			const uint32_t cand2 = cand & nla;
+			if (cand2) {
+				/* are the NLs before it the tail of an "other" piece?  unknown when the NL run reaches the window start */
+				const uint32_t tail = jtk_spread_up(O_, NL) & NL, open = jtk_spread_up(NL & 1u, NL);
+				if (cand2 & (open << 1)) return false;
+				BW |= cand2 & (tail << 1);
+			}
+		}
+		/* \p{N}{1,3}: every third position of a digit run starts a piece */
+		uint32_t BN = 0;
+		if (N & 0xFFFF0u) {
+			uint32_t T0 = N & ~(N << 1);
+			if (N & 1u) { /* the run of window position 0 began earlier: its phase comes from a walk */
+				T0 &= ~1u;
+				const int k = jtk_count_n_before(c, ws);
+				const int o = (3 - k) % 3;
+				const uint32_t run0 = jtk_spread_up(1u, N);
+				T0 |= (1u << o) & run0;
+			}
+			const uint32_t C3 = N & (N << 1) & (N << 2) & (N << 3);
+			uint32_t T = T0 | ((T0 << 3) & C3);
+			const uint32_t C6 = C3 & (C3 << 3);
+			T |= (T << 6) & C6;
+			const uint32_t C12 = C6 & (C6 << 6);
+			T |= (T << 12) & C12;
+			BN = T & N;
+		}
+		B = BL | Ostart | BNL | BW | BN;
+	} else {
+		const uint32_t W = SP | WO | NL;
+		const uint32_t CS = APs & ((S1 >> 1) | ((RV >> 1) & (LE >> 2)) | ((LL >> 1) & (LL >> 2)));
+		const uint32_t BL = L & (CE | ~((L | SP | CS) << 1));
+		const uint32_t BN = N & ~((N | SP) << 1);
+		const uint32_t BW = W & (~(W << 1) | (~W >> 1));
+		B = BL | Ostart | BN | BW;
+	}
+	*out = (B >> 4) & 0xFFFFu;
+	return true;
+}
+
 /* Piece-start bits for the 16 positions of chunk `chunk`. */
 JTK_HD uint32_t jtk_boundary_chunk(const jtk_tile_ctx &c, int chunk) {
 	const int r0 = chunk * 16;
 	uint32_t bits = 0;
+	if (jtk_boundary_fast(c, chunk, &bits)) return bits;
+	bits = 0;
 	int nrun = -1;
 	for (int i = 0; i < 16; i++) {
 		const int r = r0 + i;
@@ -482,16 +628,31 @@ JTK_HD int32_t jtk_lookup_b(const jtk_tables &T, const uint8_t *p, uint32_t n) {
 }
 
 /* rank of the concatenation of two parts, or JTK_RANK_MAX (getRank, GptBytePairEncoding.java:285-300) */
-JTK_HD int32_t jtk_lookup_pair(const jtk_tables &T, int32_t l, int32_t r) {
-	uint32_t b = jtk_hash_pair(l, r) & T.mask_p;
+JTK_HD int32_t jtk_pair_resolve(const jtk_tables &T, uint32_t b, const jtk_slot &f0, const jtk_slot &f1, int32_t l, int32_t r) {
+	jtk_slot s0 = f0, s1 = f1;
 	for (;;) {
-		const jtk_slot s0 = T.pair[2 * b], s1 = T.pair[2 * b + 1];
 		if (s0.w == 0) return JTK_RANK_MAX;
 		if (s0.x == (uint32_t) l && s0.y == (uint32_t) r) return (int32_t) s0.z;
 		if (s1.w == 0) return JTK_RANK_MAX;
 		if (s1.x == (uint32_t) l && s1.y == (uint32_t) r) return (int32_t) s1.z;
 		b = (b + 1) & T.mask_p;
+		s0 = T.pair[2 * b];
+		s1 = T.pair[2 * b + 1];
 	}
+}
+
+JTK_HD int32_t jtk_lookup_pair(const jtk_tables &T, int32_t l, int32_t r) {
+	const uint32_t b = jtk_hash_pair(l, r) & T.mask_p;
+	return jtk_pair_resolve(T, b, T.pair[2 * b], T.pair[2 * b + 1], l, r);
+}
+
+/* The two rank probes of one merge step (:254-257) with all four slot loads in flight together. */
+JTK_HD void jtk_lookup_pair2(const jtk_tables &T, int32_t l1, int32_t r1, int32_t l2, int32_t r2, int32_t *o1, int32_t *o2) {
+	const uint32_t b1 = jtk_hash_pair(l1, r1) & T.mask_p, b2 = jtk_hash_pair(l2, r2) & T.mask_p;
+	const jtk_slot a0 = T.pair[2 * b1], a1 = T.pair[2 * b1 + 1];
+	const jtk_slot c0 = T.pair[2 * b2], c1 = T.pair[2 * b2 + 1];
+	*o1 = jtk_pair_resolve(T, b1, a0, a1, l1, r1);
+	*o2 = jtk_pair_resolve(T, b2, c0, c1, l2, r2);
 }
 
 /* Whole-piece lookup of the n bytes at p (n >= 1): rank or JTK_RANK_MAX. */
@@ -501,13 +662,19 @@ JTK_HD int32_t jtk_lookup_piece(const jtk_tables &T, const uint8_t *p, int n) {
 		return id < JTK_PSEUDO_BASE + 256 ? JTK_RANK_MAX : id;
 	}
 	if (n <= JTK_INLINE_KEY_MAX) {
-		uint32_t w0 = 0, w1 = 0, w2 = (uint32_t) n << 24;
-		for (int i = 0; i < n; i++) {
-			uint32_t v = (uint32_t) p[i] << (8 * (i & 3));
-			if (i < 4) w0 |= v;
-			else if (i < 8) w1 |= v;
-			else w2 |= v;
-		}
+		/* three unaligned key words from four aligned loads (the staging buffer is padded), then masked to n bytes */
+		const uint32_t *aw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t) 3);
+		const int sh = (int) (reinterpret_cast<uintptr_t>(p) & 3) * 8;
+		const uint32_t a0 = aw[0], a1 = aw[1], a2 = aw[2], a3 = aw[3];
+		uint32_t w0 = sh ? (a0 >> sh) | (a1 << (32 - sh)) : a0;
+		uint32_t w1 = sh ? (a1 >> sh) | (a2 << (32 - sh)) : a1;
+		uint32_t w2 = sh ? (a2 >> sh) | (a3 << (32 - sh)) : a2;
+		if (n < 4) w0 &= (1u << (8 * n)) - 1u;
+		if (n <= 4) w1 = 0;
+		else if (n < 8) w1 &= (1u << (8 * (n - 4))) - 1u;
+		if (n <= 8) w2 = 0;
+		else w2 &= (1u << (8 * (n - 8))) - 1u;
+		w2 |= (uint32_t) n << 24;
 		return jtk_lookup_a(T, w0, w1, w2);
 	}
 	if (n > T.max_token_len) return JTK_RANK_MAX;
@@ -547,10 +714,18 @@ JTK_HD int jtk_merge_short(const jtk_tables &T, const uint8_t *p, int n, int32_t
 		tok[mi * stride] = mr; /* rank == id of the merged token */
 		alive &= ~(1u << nx);
 		rk[nx * stride] = JTK_RANK_MAX;
-		rk[mi * stride] = above2 ? jtk_lookup_pair(T, mr, tok[jtk_ctz(above2) * stride]) : JTK_RANK_MAX; /* :254 */
-		if (below) {
+		if (above2 && below) { /* both neighbours exist: issue the two probes together (:254-257) */
 			const int pv = 31 - jtk_clz(below);
-			rk[pv * stride] = jtk_lookup_pair(T, tok[pv * stride], mr); /* :255-257 */
+			int32_t r_right, r_left;
+			jtk_lookup_pair2(T, mr, tok[jtk_ctz(above2) * stride], tok[pv * stride], mr, &r_right, &r_left);
+			rk[mi * stride] = r_right;
+			rk[pv * stride] = r_left;
+		} else {
+			rk[mi * stride] = above2 ? jtk_lookup_pair(T, mr, tok[jtk_ctz(above2) * stride]) : JTK_RANK_MAX; /* :254 */
+			if (below) {
+				const int pv = 31 - jtk_clz(below);
+				rk[pv * stride] = jtk_lookup_pair(T, tok[pv * stride], mr); /* :255-257 */
+			}
 		}
 	}
 	int cnt = 0;

@@ -21,6 +21,7 @@
 #include "jtk_kernels.cuh"
 
 #include <algorithm>
+#include <cstring>
 
 #include "jtk_device.cuh"
 
@@ -102,23 +103,27 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *wsum, int *total
 }
 
 /* ---------------------------------------------------------------------------------------------
- * bytePairMerge for one piece of 33..JTK_LONG_PIECE bytes by one warp (GptBytePairEncoding.java:200-275).
- * Position k is owned by lane k & 31 (row k >> 5), so rank scans are bank-conflict free; the argmin over
- * adjacent pair ranks is a REDUX min over per-lane minima, neighbours are found with REDUX over per-lane
- * alive masks, and the two rank probes of a merge (:254-257) are issued by two lanes in parallel.
+ * bytePairMerge for one piece of 33..JTK_LONG_PIECE bytes by a group of G = 2^LOG2G lanes
+ * (GptBytePairEncoding.java:200-275).  Position k is owned by group lane k % G (row k / G, at most 32 rows), so
+ * rank scans are bank-conflict free; the argmin over adjacent pair ranks is a REDUX min over per-lane minima,
+ * neighbours are found with REDUX over per-lane alive masks, and the two rank probes of a merge (:254-257) are
+ * issued by two lanes in parallel.  Several groups share a warp (G = 8: four pieces per warp).
  * ------------------------------------------------------------------------------------------- */
-__device__ int merge_warp(const jtk_tables &T, const uint8_t *p, int n, int32_t *tok, int32_t *rk, bool *unknown) {
-	const unsigned full = 0xFFFFFFFFu;
+template <int LOG2G>
+__device__ int merge_group(const jtk_tables &T, const uint8_t *p, int n, int32_t *tok, int32_t *rk, bool *unknown) {
+	constexpr int G = 1 << LOG2G;
 	const int lane = threadIdx.x & 31;
-	for (int k = lane; k < n; k += 32) {
+	const int gl = lane & (G - 1);
+	const unsigned gmask = G == 32 ? 0xFFFFFFFFu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+	for (int k = gl; k < n; k += G) {
 		tok[k] = T.byte_id[p[k]];
 		rk[k] = (k + 1 < n) ? T.bytepair[((uint32_t) p[k] << 8) | p[k + 1]] : JTK_RANK_MAX;
 	}
-	__syncwarp();
-	const int rows = (n + 31) >> 5;
+	__syncwarp(gmask);
+	const int rows = (n + G - 1) >> LOG2G;
 	uint32_t alive = 0;
 	for (int j = 0; j < rows; j++)
-		if ((j << 5) + lane < n) alive |= 1u << j;
+		if ((j << LOG2G) + gl < n) alive |= 1u << j;
 	int32_t lr = JTK_RANK_MAX;
 	int lk = 0x7fffffff;
 	auto rescan = [&]() {
@@ -127,7 +132,7 @@ __device__ int merge_warp(const jtk_tables &T, const uint8_t *p, int n, int32_t 
 		for (uint32_t m = alive; m;) {
 			int j = __ffs((int) m) - 1;
 			m &= m - 1;
-			int k = (j << 5) + lane;
+			int k = (j << LOG2G) + gl;
 			int32_t r = rk[k];
 			if (r < lr) {
 				lr = r;
@@ -137,52 +142,52 @@ __device__ int merge_warp(const jtk_tables &T, const uint8_t *p, int n, int32_t 
 	};
 	rescan();
 	for (;;) {
-		const int32_t mr = __reduce_min_sync(full, lr);
+		const int32_t mr = __reduce_min_sync(gmask, lr);
 		if (mr == JTK_RANK_MAX) break;
-		const int mi = __reduce_min_sync(full, lr == mr ? lk : 0x7fffffff); /* leftmost minimum (:232-240) */
+		const int mi = __reduce_min_sync(gmask, lr == mr ? lk : 0x7fffffff); /* leftmost minimum (:232-240) */
 		/* next alive position after k / previous alive position before k */
 		auto next_alive = [&](int k) {
-			int j0 = (k >> 5) + (lane <= (k & 31) ? 1 : 0);
+			int j0 = (k >> LOG2G) + (gl <= (k & (G - 1)) ? 1 : 0);
 			uint32_t m = j0 >= 32 ? 0u : (alive & (0xFFFFFFFFu << j0));
-			int cand = m ? (((__ffs((int) m) - 1) << 5) + lane) : 0x7fffffff;
-			return __reduce_min_sync(full, cand);
+			int cand = m ? (((__ffs((int) m) - 1) << LOG2G) + gl) : 0x7fffffff;
+			return __reduce_min_sync(gmask, cand);
 		};
 		auto prev_alive = [&](int k) {
-			int j1 = (k >> 5) - (lane < (k & 31) ? 0 : 1);
+			int j1 = (k >> LOG2G) - (gl < (k & (G - 1)) ? 0 : 1);
 			uint32_t m = j1 < 0 ? 0u : (alive & (j1 >= 31 ? 0xFFFFFFFFu : ((2u << j1) - 1u)));
-			int cand = m ? (((31 - __clz((int) m)) << 5) + lane) : -1;
-			return __reduce_max_sync(full, cand);
+			int cand = m ? (((31 - __clz((int) m)) << LOG2G) + gl) : -1;
+			return __reduce_max_sync(gmask, cand);
 		};
 		const int nx = next_alive(mi);
 		const int nn = next_alive(nx);
 		const int pv = prev_alive(mi);
-		if (lane == (mi & 31)) tok[mi] = mr;
-		if (lane == (nx & 31)) {
-			alive &= ~(1u << (nx >> 5));
+		if (gl == (mi & (G - 1))) tok[mi] = mr;
+		if (gl == (nx & (G - 1))) {
+			alive &= ~(1u << (nx >> LOG2G));
 			rk[nx] = JTK_RANK_MAX;
 		}
-		__syncwarp();
-		if (lane == 0) rk[mi] = (nn != 0x7fffffff) ? jtk_lookup_pair(T, mr, tok[nn]) : JTK_RANK_MAX;
-		if (lane == 1 && pv >= 0) rk[pv] = jtk_lookup_pair(T, tok[pv], mr);
-		__syncwarp();
-		if (lane == (mi & 31) || lane == (nx & 31) || (pv >= 0 && lane == (pv & 31))) rescan();
+		__syncwarp(gmask);
+		if (gl == 0) rk[mi] = (nn != 0x7fffffff) ? jtk_lookup_pair(T, mr, tok[nn]) : JTK_RANK_MAX;
+		if (gl == 1 && pv >= 0) rk[pv] = jtk_lookup_pair(T, tok[pv], mr);
+		__syncwarp(gmask);
+		if (gl == (mi & (G - 1)) || gl == (nx & (G - 1)) || (pv >= 0 && gl == (pv & (G - 1)))) rescan();
 	}
 	/* compact the surviving parts to the front of tok[] */
 	int out = 0;
 	bool unk = false;
 	for (int j = 0; j < rows; j++) {
 		const bool a = (alive >> j) & 1u;
-		const int32_t v = a ? tok[(j << 5) + lane] : 0;
-		const unsigned b = __ballot_sync(full, a);
-		__syncwarp();
+		const int32_t v = a ? tok[(j << LOG2G) + gl] : 0;
+		const unsigned b = __ballot_sync(gmask, a) & gmask;
+		__syncwarp(gmask);
 		if (a) {
 			tok[out + __popc(b & ((1u << lane) - 1u))] = v;
 			if (v < JTK_PSEUDO_BASE + 256) unk = true;
 		}
 		out += __popc(b);
-		__syncwarp();
+		__syncwarp(gmask);
 	}
-	if (__any_sync(full, unk)) *unknown = true;
+	if (__any_sync(gmask, unk)) *unknown = true;
 	return out;
 }
 
@@ -198,10 +203,12 @@ __global__ void __launch_bounds__(JTK_NT, 2) jtk_split_lookup_kernel(const __gri
 	uint16_t *plist = reinterpret_cast<uint16_t *>(dmask + JTK_MASK_WORDS); /* region index of every piece start, in order */
 	uint32_t *chunk_pref = reinterpret_cast<uint32_t *>(plist + RECN);      /* pieces before each 16-byte chunk */
 	uint32_t *misc = chunk_pref + TC;
+	uint8_t *s_ascii = reinterpret_cast<uint8_t *>(misc + 64); /* ASCII class table, 128 bytes */
 
 	const int tid = threadIdx.x;
 	const int lane = tid & 31;
 	const jtk_tables &T = a.T;
+	if (tid < 128) s_ascii[tid] = T.ascii_cls[tid];
 
 	jtk_tile_ctx c;
 	c.sb = sb;
@@ -215,6 +222,9 @@ __global__ void __launch_bounds__(JTK_NT, 2) jtk_split_lookup_kernel(const __gri
 	c.doc_off = a.doc_off;
 	c.ndocs = a.ndocs;
 	c.T = &T;
+	c.ascii_lut = s_ascii;
+	/* the special-token guard only has to look at bytes that can start a special token */
+	const bool check_special = (a.flags & JTK_CHECK_SPECIAL) && T.nspecial > 0;
 
 	for (;;) {
 		/* ---- P0: take a tile ---- */
@@ -256,9 +266,19 @@ __global__ void __launch_bounds__(JTK_NT, 2) jtk_split_lookup_kernel(const __gri
 
 		/* ---- P3: split rules -> piece-start bits; special-token guard ---- */
 		for (int ch = BH / 16 + tid; ch < JTK_REGION_CHUNKS; ch += NT) reinterpret_cast<uint16_t *>(bmask)[ch] = (uint16_t) jtk_boundary_chunk(c, ch);
-		if ((a.flags & JTK_CHECK_SPECIAL) && T.nspecial > 0) {
+		if (check_special) {
 			for (int ch = tid; ch < TC; ch += NT) {
 				const int r0 = BH + ch * 16;
+				if (T.special_first_single) { /* one candidate first byte (built-ins: '<'): SWAR "has byte" test on the 16 bytes */
+					const uint32_t *w = reinterpret_cast<const uint32_t *>(sb + r0);
+					const uint32_t pat = T.special_first_single * 0x01010101u;
+					uint32_t any = 0;
+					for (int k = 0; k < 4; k++) {
+						const uint32_t x = w[k] ^ pat;
+						any |= (x - 0x01010101u) & ~x & 0x80808080u;
+					}
+					if (!any) continue;
+				}
 				for (int i = 0; i < 16; i++) {
 					const int64_t g = c.g0 + r0 + i;
 					if (g >= a.total) break;
@@ -347,7 +367,9 @@ __global__ void __launch_bounds__(JTK_NT, 2) jtk_split_lookup_kernel(const __gri
 							hits++;
 						} else {
 							out = rec_make(s, n);
-							a.slowq[lt * (long long) QCAP + atomicAdd(&misc[M_NSLOW], 1u)] = (uint16_t) q;
+							if (n <= JTK_SHORT_PIECE) a.slowq[lt * (long long) QCAP + atomicAdd(&misc[M_NSLOW], 1u)] = (uint16_t) q;
+							else if (n <= JTK_GROUP8_PIECE) a.med8[atomicAdd(&a.hdr->n_med8, 1u)] = ((uint32_t) lt << 14) | (uint32_t) q;
+							else a.med32[atomicAdd(&a.hdr->n_med32, 1u)] = ((uint32_t) lt << 14) | (uint32_t) q;
 						}
 					}
 				}
@@ -380,21 +402,20 @@ __global__ void __launch_bounds__(JTK_NT, 2) jtk_split_lookup_kernel(const __gri
 }
 
 /* ---------------------------------------------------------------------------------------------
- * kernel 2: bytePairMerge for the pieces the lookup did not resolve (GptBytePairEncoding.java:85, 200-300)
- * One CTA per tile.  The tile's unresolved pieces are counting-sorted by length so that the threads of a warp run
- * merge loops of similar length; tokens go to the tile's slice of slowtok at the piece's byte position.
+ * kernel 2a: bytePairMerge for the short pieces (2..32 bytes) the lookup did not resolve
+ * (GptBytePairEncoding.java:85, 200-300).  One CTA per tile, one thread per piece.  The tile's unresolved pieces are
+ * counting-sorted by length so that the threads of a warp run merge loops of similar length; tokens go to the
+ * tile's slice of slowtok at the piece's byte position.
  * ------------------------------------------------------------------------------------------- */
 constexpr int MNT = 128;
-constexpr int MNW = MNT / 32;
 
-__global__ void __launch_bounds__(MNT) jtk_merge_kernel(const __grid_constant__ jtk_encode_args a) {
+__global__ void __launch_bounds__(MNT) jtk_merge_short_kernel(const __grid_constant__ jtk_encode_args a) {
 	__shared__ uint16_t s_order[QCAP];
-	__shared__ int s_hist[36], s_cursor[36];
-	__shared__ int32_t s_scr[2 * JTK_SHORT_PIECE * MNT]; /* short: tok / rk interleaved by thread; medium: per-warp tok / rk */
+	__shared__ int s_hist[JTK_SHORT_PIECE + 2], s_cursor[JTK_SHORT_PIECE + 2];
+	__shared__ int32_t s_scr[2 * JTK_SHORT_PIECE * MNT]; /* tok / rk, slot k of thread t at k * MNT + t (bank = thread) */
 	__shared__ int s_sum;
-	static_assert(2 * JTK_SHORT_PIECE * MNT >= MNW * 2 * JTK_LONG_PIECE, "medium scratch must fit");
 	const jtk_tables &T = a.T;
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int tid = threadIdx.x, lane = tid & 31;
 	const long long tile = a.tile_begin + blockIdx.x;
 	if (tile >= a.tile_end) return;
 	const int S = a.nslow[tile];
@@ -406,33 +427,27 @@ __global__ void __launch_bounds__(MNT) jtk_merge_kernel(const __grid_constant__ 
 	int32_t *stok = a.slowtok + lt * (long long) RECN;
 	const bool write_tok = !(a.flags & JTK_COUNT_ONLY);
 
-	if (tid < 36) s_hist[tid] = 0;
+	if (tid < JTK_SHORT_PIECE + 2) s_hist[tid] = 0;
 	if (tid == 0) s_sum = 0;
 	__syncthreads();
-	for (int k = tid; k < S; k += MNT) {
-		const int n = (int) (rec_payload(rec[sq[k]]) & 0x7FFu) + 1;
-		atomicAdd(&s_hist[n <= JTK_SHORT_PIECE ? n : JTK_SHORT_PIECE + 1], 1);
-	}
+	for (int k = tid; k < S; k += MNT) atomicAdd(&s_hist[(rec_payload(rec[sq[k]]) & 0x7FFu) + 1], 1);
 	__syncthreads();
 	if (tid == 0) {
 		int run = 0;
-		for (int b = 0; b < 36; b++) {
+		for (int b = 0; b < JTK_SHORT_PIECE + 2; b++) {
 			s_cursor[b] = run;
 			run += s_hist[b];
 		}
 	}
 	__syncthreads();
-	const int nshort = s_cursor[JTK_SHORT_PIECE + 1];
 	for (int k = tid; k < S; k += MNT) {
 		const int q = sq[k];
-		const int n = (int) (rec_payload(rec[q]) & 0x7FFu) + 1;
-		s_order[atomicAdd(&s_cursor[n <= JTK_SHORT_PIECE ? n : JTK_SHORT_PIECE + 1], 1)] = (uint16_t) q;
+		s_order[atomicAdd(&s_cursor[(rec_payload(rec[q]) & 0x7FFu) + 1], 1)] = (uint16_t) q;
 	}
 	__syncthreads();
 
 	int sum = 0;
-	/* short pieces: one thread each, scratch interleaved by thread (bank = thread) */
-	for (int i = tid; i < nshort; i += MNT) {
+	for (int i = tid; i < S; i += MNT) {
 		const int q = s_order[i];
 		const uint32_t pl = rec_payload(rec[q]);
 		const int s = (int) (pl >> 11), n = (int) (pl & 0x7FFu) + 1;
@@ -445,29 +460,88 @@ __global__ void __launch_bounds__(MNT) jtk_merge_kernel(const __grid_constant__ 
 		sum += cnt;
 		if (unk) flag_doc(a, tb + s, JTK_DOC_UNKNOWN_BYTES);
 	}
-	__syncthreads();
-	/* medium pieces: one warp each */
-	for (int j = nshort + warp; j < S; j += MNW) {
-		const int q = s_order[j];
-		const uint32_t pl = rec_payload(rec[q]);
-		const int s = (int) (pl >> 11), n = (int) (pl & 0x7FFu) + 1;
-		bool unk = false;
-		int32_t *tk = s_scr + warp * 2 * JTK_LONG_PIECE, *rk = tk + JTK_LONG_PIECE;
-		const int cnt = merge_warp(T, a.bytes + tb + s, n, tk, rk, &unk);
-		__syncwarp();
-		if (write_tok)
-			for (int k = lane; k < cnt; k += 32) stok[s + k] = tk[k];
-		__syncwarp();
-		if (lane == 0) {
-			rec[q] = rec_make(s, cnt);
-			sum += cnt;
-			if (unk) flag_doc(a, tb + s, JTK_DOC_UNKNOWN_BYTES);
-		}
-	}
 	sum = __reduce_add_sync(0xFFFFFFFFu, sum);
 	if (lane == 0) atomicAdd(&s_sum, sum);
 	__syncthreads();
-	if (tid == 0) a.tile_count[tile] += s_sum;
+	if (tid == 0) atomicAdd(&a.tile_count[tile], s_sum);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * kernel 2b: bytePairMerge for the medium pieces (33..JTK_LONG_PIECE bytes) of the whole sub-batch, taken from two
+ * global lists by persistent lane groups: 8 lanes per piece up to 256 bytes, a full warp above.
+ * ------------------------------------------------------------------------------------------- */
+constexpr int GNTM = 128;
+
+__global__ void __launch_bounds__(GNTM) jtk_merge_medium_kernel(const __grid_constant__ jtk_encode_args a) {
+	__shared__ int32_t s_scr[(GNTM / 32) * 2 * JTK_LONG_PIECE]; /* per warp: tok[1024] rk[1024]; per 8-lane group a quarter of each */
+	const jtk_tables &T = a.T;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const bool write_tok = !(a.flags & JTK_COUNT_ONLY);
+	int32_t *wtok = s_scr + warp * 2 * JTK_LONG_PIECE, *wrk = wtok + JTK_LONG_PIECE;
+	/* 8-lane groups */
+	{
+		const unsigned n8 = a.hdr->n_med8;
+		const int g = lane >> 3, gl = lane & 7;
+		const unsigned gmask = 0xFFu << (g * 8);
+		int32_t *tk = wtok + g * JTK_GROUP8_PIECE, *rk = wrk + g * JTK_GROUP8_PIECE;
+		for (;;) {
+			unsigned idx = 0;
+			if (gl == 0) idx = atomicAdd(&a.hdr->cursor8, 1u);
+			idx = __shfl_sync(gmask, idx, g * 8);
+			if (idx >= n8) break;
+			const uint32_t e = a.med8[idx];
+			const long long lt = e >> 14;
+			const int q = (int) (e & 0x3FFFu);
+			int32_t *rec = a.rec + lt * (long long) RECN;
+			const uint32_t pl = rec_payload(rec[q]);
+			const int s = (int) (pl >> 11), n = (int) (pl & 0x7FFu) + 1;
+			const int64_t tb = (a.tile_begin + lt) * (int64_t) JTK_TILE;
+			bool unk = false;
+			const int cnt = merge_group<3>(T, a.bytes + tb + s, n, tk, rk, &unk);
+			__syncwarp(gmask);
+			if (write_tok) {
+				int32_t *stok = a.slowtok + lt * (long long) RECN + s;
+				for (int k = gl; k < cnt; k += 8) stok[k] = tk[k];
+			}
+			__syncwarp(gmask);
+			if (gl == 0) {
+				rec[q] = rec_make(s, cnt);
+				atomicAdd(&a.tile_count[a.tile_begin + lt], cnt);
+				if (unk) flag_doc(a, tb + s, JTK_DOC_UNKNOWN_BYTES);
+			}
+		}
+	}
+	__syncwarp();
+	/* whole warps */
+	{
+		const unsigned n32 = a.hdr->n_med32;
+		for (;;) {
+			unsigned idx = 0;
+			if (lane == 0) idx = atomicAdd(&a.hdr->cursor32, 1u);
+			idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
+			if (idx >= n32) break;
+			const uint32_t e = a.med32[idx];
+			const long long lt = e >> 14;
+			const int q = (int) (e & 0x3FFFu);
+			int32_t *rec = a.rec + lt * (long long) RECN;
+			const uint32_t pl = rec_payload(rec[q]);
+			const int s = (int) (pl >> 11), n = (int) (pl & 0x7FFu) + 1;
+			const int64_t tb = (a.tile_begin + lt) * (int64_t) JTK_TILE;
+			bool unk = false;
+			const int cnt = merge_group<5>(T, a.bytes + tb + s, n, wtok, wrk, &unk);
+			__syncwarp();
+			if (write_tok) {
+				int32_t *stok = a.slowtok + lt * (long long) RECN + s;
+				for (int k = lane; k < cnt; k += 32) stok[k] = wtok[k];
+			}
+			__syncwarp();
+			if (lane == 0) {
+				rec[q] = rec_make(s, cnt);
+				atomicAdd(&a.tile_count[a.tile_begin + lt], cnt);
+				if (unk) flag_doc(a, tb + s, JTK_DOC_UNKNOWN_BYTES);
+			}
+		}
+	}
 }
 
 /* ---------------------------------------------------------------------------------------------
@@ -507,7 +581,8 @@ __global__ void __launch_bounds__(1024, 1) jtk_tile_scan_kernel(const jtk_encode
 	if (tid == 0) {
 		a.tile_base[a.tile_end] = s_carry;
 		a.hdr->total_tokens = (unsigned long long) s_carry;
-		a.hdr->ticket = 0; /* the next sub-batch starts its tickets at zero */
+		a.hdr->ticket = 0; /* the next sub-batch starts its tickets and medium-piece lists at zero */
+		a.hdr->n_med8 = a.hdr->n_med32 = a.hdr->cursor8 = a.hdr->cursor32 = 0;
 		if (!(a.flags & JTK_COUNT_ONLY) && a.ids && s_carry > a.ids_cap) a.hdr->overflow = 1;
 	}
 }
@@ -918,10 +993,36 @@ cudaError_t jtk_launch_sub_batch(const jtk_encode_args &a, int num_sms, cudaEven
 	if (nt <= 0) return cudaSuccess;
 	int64_t grid = (int64_t) num_sms * 2;
 	if (grid > nt) grid = nt;
+	/* the table-probing kernels run with the hot tables pinned in L2 (persisting hits, streaming misses) */
+	cudaLaunchAttribute attr[1];
+	unsigned nattr = 0;
+	if (a.l2_bytes > 0) {
+		attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+		attr[0].val.accessPolicyWindow.base_ptr = const_cast<void *>(a.l2_base);
+		attr[0].val.accessPolicyWindow.num_bytes = a.l2_bytes;
+		attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+		attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+		attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+		nattr = 1;
+	}
+	cudaLaunchConfig_t cfg;
+	memset(&cfg, 0, sizeof(cfg));
+	cfg.stream = st;
+	cfg.attrs = attr;
+	cfg.numAttrs = nattr;
 	if (k0) cudaEventRecord(k0, st);
-	jtk_split_lookup_kernel<<<(unsigned) grid, JTK_NT, JTK_SMEM_BYTES, st>>>(a);
+	cfg.gridDim = dim3((unsigned) grid);
+	cfg.blockDim = dim3(JTK_NT);
+	cfg.dynamicSmemBytes = JTK_SMEM_BYTES;
+	cudaLaunchKernelEx(&cfg, jtk_split_lookup_kernel, a);
 	if (k1) cudaEventRecord(k1, st);
-	jtk_merge_kernel<<<(unsigned) nt, MNT, 0, st>>>(a);
+	cfg.dynamicSmemBytes = 0;
+	cfg.gridDim = dim3((unsigned) nt);
+	cfg.blockDim = dim3(MNT);
+	cudaLaunchKernelEx(&cfg, jtk_merge_short_kernel, a);
+	cfg.gridDim = dim3((unsigned) (num_sms * 6));
+	cfg.blockDim = dim3(GNTM);
+	cudaLaunchKernelEx(&cfg, jtk_merge_medium_kernel, a);
 	jtk_tile_scan_kernel<<<1, 1024, 0, st>>>(a);
 	jtk_gather_kernel<<<(unsigned) nt, GNT, 0, st>>>(a);
 	return cudaGetLastError();

@@ -28,12 +28,17 @@ struct jtk_batch_header {
 	unsigned int ticket;     /* tile ticket counter */
 	unsigned int long_next;  /* work counter of the long-piece kernel */
 	unsigned int violations; /* long-piece rounds that had to fall back to one-merge-at-a-time */
+	unsigned int n_med8, n_med32;   /* medium pieces of the current sub-batch (33..256 bytes / 257..JTK_LONG_PIECE bytes) */
+	unsigned int cursor8, cursor32; /* work counters of jtk_merge_medium_kernel */
 	unsigned int pad;
 };
 
 #define JTK_RECN (JTK_TILE + JTK_FWD_HALO) /* per-tile slots of rec / slowtok: pieces + unresolved pieces <= JTK_RECN */
 #define JTK_QCAP (JTK_RECN / 2)            /* an unresolved piece has at least two bytes */
 #define JTK_REC_MIN_ID (-(1 << 30))        /* token ids below this are rejected at registration; the space encodes piece records */
+#define JTK_GROUP8_PIECE 256                /* up to this length a medium piece is merged by 8 lanes, above by a warp */
+#define JTK_MED8_PER_TILE (JTK_RECN / (JTK_SHORT_PIECE + 1) + 1)
+#define JTK_MED32_PER_TILE (JTK_RECN / (JTK_GROUP8_PIECE + 1) + 1)
 #define JTK_DEFAULT_SUB_TILES 4096         /* tiles per sub-batch: 32 MiB of input, intermediates stay around the L2 size */
 
 struct jtk_encode_args {
@@ -54,7 +59,9 @@ struct jtk_encode_args {
 	/* per tile of the sub-batch (index tile - tile_begin) */
 	int32_t *rec;          /* JTK_RECN per tile: one record per piece, in order */
 	int32_t *slowtok;      /* JTK_RECN per tile: tokens of merged pieces at the piece's tile-local byte position */
-	uint16_t *slowq;       /* JTK_QCAP per tile: piece indices of the unresolved pieces */
+	uint16_t *slowq;       /* JTK_QCAP per tile: piece indices of the unresolved short pieces (<= JTK_SHORT_PIECE bytes) */
+	uint32_t *med8;        /* JTK_MED8_PER_TILE per tile: (tile index << 14 | piece index) of unresolved pieces of 33..256 bytes */
+	uint32_t *med32;       /* JTK_MED32_PER_TILE per tile: same for 257..JTK_LONG_PIECE bytes */
 	jtk_batch_header *hdr;
 	int32_t *ids;
 	int64_t ids_cap;
@@ -64,9 +71,12 @@ struct jtk_encode_args {
 	jtk_long_piece *long_list;
 	int64_t long_cap;
 	uint8_t *piece_flags;  /* debug: one byte per input byte, 1 where a piece starts (nullable) */
+	/* host side only: L2 access-policy window over the hot tables (0 bytes = none) */
+	const void *l2_base;
+	size_t l2_bytes;
 };
 
-#define JTK_SMEM_BYTES (2 * (JTK_REGION + 16) + 2 * 4 * (((JTK_REGION + 32) / 32 + 1)) + 2 * JTK_RECN + 4 * (JTK_TILE / 16) + 256)
+#define JTK_SMEM_BYTES (2 * (JTK_REGION + 16) + 2 * 4 * (((JTK_REGION + 32) / 32 + 1)) + 2 * JTK_RECN + 4 * (JTK_TILE / 16) + 256 + 128)
 
 cudaError_t jtk_launch_tile_first_doc(const int64_t *doc_off, int64_t ndocs, int64_t ntiles, int32_t *out, cudaStream_t st);
 /* the four kernels of one sub-batch; k0/k1 (nullable) bracket the split+lookup kernel */

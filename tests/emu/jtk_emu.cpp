@@ -100,6 +100,7 @@ int64_t emu_run(const emu_encoding *e, const uint8_t *bytes, int64_t total, cons
 	t.c.doc_off = doc_off;
 	t.c.ndocs = ndocs;
 	t.c.T = &e->view;
+	t.c.ascii_lut = e->view.ascii_cls;
 	int64_t halo_mismatch = 0;
 	for (int64_t tile = 0; tile < ntiles; tile++) {
 		t.run(tile);

@@ -1,13 +1,14 @@
 #!/usr/bin/env python3
 """Summarise an .ncu-rep of the tile kernel: headline metrics, stall reasons, per-function instruction / sample shares.
-Usage: tools/ncu_summary.py gpurun_out/prof.ncu-rep [nbytes]"""
+Usage: tools/ncu_summary.py gpurun_out/prof.ncu-rep [nbytes [kernel-regex]]"""
 import collections, csv, io, re, subprocess, sys, os
 
 rep = sys.argv[1]
+KFILTER = ["-k", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def run(args):
-    return subprocess.run(["ncu", "-i", rep] + args, capture_output=True, text=True).stdout
+    return subprocess.run(["ncu", "-i", rep] + KFILTER + args, capture_output=True, text=True).stdout
 
 raw = list(csv.reader(io.StringIO(run(["--page", "raw", "--csv"]))))
 hdr, vals = raw[0], raw[2] if len(raw) > 2 else raw[1]

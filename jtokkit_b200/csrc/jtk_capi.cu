@@ -45,7 +45,7 @@ struct jtk_workspace {
 	int64_t sub_tiles = 0;
 	int32_t *rec = nullptr, *slowtok = nullptr;
 	uint16_t *slowq = nullptr;
-	uint32_t *med8 = nullptr, *med32 = nullptr;
+	uint32_t *med8 = nullptr, *med32 = nullptr, *shortlist = nullptr;
 	std::vector<cudaEvent_t> kev; /* event pairs around the split+lookup kernel of every sub-batch (JTK_TIME_KERNEL) */
 	int64_t *tile_first_b = nullptr;
 	jtk_long_piece *long_list = nullptr;
@@ -279,6 +279,7 @@ static void free_workspace(jtk_workspace *w) {
 	cudaFree(w->slowq);
 	cudaFree(w->med8);
 	cudaFree(w->med32);
+	cudaFree(w->shortlist);
 	for (cudaEvent_t ev : w->kev) cudaEventDestroy(ev);
 	cudaFree(w->tile_first_b);
 	cudaFree(w->long_list);
@@ -364,15 +365,17 @@ static int ensure_ws_tiles(jtk_workspace *w, int64_t ntiles, int64_t long_cap) {
 		cudaFree(w->slowq);
 		cudaFree(w->med8);
 		cudaFree(w->med32);
+		cudaFree(w->shortlist);
 		w->rec = w->slowtok = nullptr;
 		w->slowq = nullptr;
-		w->med8 = w->med32 = nullptr;
+		w->med8 = w->med32 = w->shortlist = nullptr;
 		w->sub_tiles = 0;
 		CUDA_TRY(cudaMalloc(&w->rec, sizeof(int32_t) * (size_t) sub * JTK_RECN));
 		CUDA_TRY(cudaMalloc(&w->slowtok, sizeof(int32_t) * (size_t) sub * JTK_RECN));
 		CUDA_TRY(cudaMalloc(&w->slowq, sizeof(uint16_t) * (size_t) sub * JTK_QCAP));
 		CUDA_TRY(cudaMalloc(&w->med8, sizeof(uint32_t) * (size_t) sub * JTK_MED8_PER_TILE));
 		CUDA_TRY(cudaMalloc(&w->med32, sizeof(uint32_t) * (size_t) sub * JTK_MED32_PER_TILE));
+		CUDA_TRY(cudaMalloc(&w->shortlist, sizeof(uint32_t) * (size_t) sub * JTK_QCAP));
 		w->sub_tiles = sub;
 	}
 	if (long_cap > w->long_cap) {
@@ -399,6 +402,7 @@ static void fill_args(jtk_encode_args &a, const jtk_device_state *ds, const jtk_
 	a.slowq = w->slowq;
 	a.med8 = w->med8;
 	a.med32 = w->med32;
+	a.shortlist = w->shortlist;
 	a.hdr = w->hdr;
 	a.long_list = w->long_list;
 	a.long_cap = w->long_cap;
@@ -509,7 +513,7 @@ static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspa
 		CUDA_TRY(jtk_launch_sub_batch(a, ds->num_sms, time_kernel ? w->kev[(size_t) (2 * i)] : nullptr, time_kernel ? w->kev[(size_t) (2 * i + 1)] : nullptr, st));
 	}
 	CUDA_TRY(jtk_launch_finalize(a, st));
-	info->gpu_launches = (ntiles > 0 ? 1 : 0) + 5 * nsub + 1;
+	info->gpu_launches = (ntiles > 0 ? 1 : 0) + 8 * nsub + 1;
 	CUDA_TRY(cudaMemcpyAsync(w->hdr_host, w->hdr, sizeof(jtk_batch_header), cudaMemcpyDeviceToHost, st));
 	if (!sync_and_long) return JTK_OK;
 	CUDA_TRY(cudaStreamSynchronize(st));

@@ -44,7 +44,7 @@ __device__ __forceinline__ int32_t rec_make(int s, int m) { return REC_BASE + (i
 __device__ __forceinline__ uint32_t rec_payload(int32_t r) { return (uint32_t) (r - REC_BASE); }
 
 /* indices into the small shared "misc" array */
-enum { M_TILE = 0, M_NSLOW, M_RS, M_CARRY, M_HITS, M_WSUM = 16 };
+enum { M_TILE = 0, M_NSLOW, M_RS, M_CARRY, M_HITS, M_WSUM = 16, M_HIST = 32 /* .. M_HIST + 33 */ };
 
 /* first set bit in [from, limit] of a bit array, or -1 */
 __device__ __forceinline__ int next_bit(const uint32_t *bm, int from, int limit) {
@@ -234,6 +234,7 @@ __global__ void __launch_bounds__(JTK_NT, 2) jtk_split_lookup_kernel(const __gri
 			misc[M_NSLOW] = 0;
 			misc[M_HITS] = 0;
 		}
+		if (tid <= JTK_SHORT_PIECE) misc[M_HIST + tid] = 0;
 		__syncthreads();
 		const long long tile = a.tile_begin + (long long) misc[M_TILE];
 		if (tile >= a.tile_end) break;
@@ -367,7 +368,10 @@ __global__ void __launch_bounds__(JTK_NT, 2) jtk_split_lookup_kernel(const __gri
 							hits++;
 						} else {
 							out = rec_make(s, n);
-							if (n <= JTK_SHORT_PIECE) a.slowq[lt * (long long) QCAP + atomicAdd(&misc[M_NSLOW], 1u)] = (uint16_t) q;
+							if (n <= JTK_SHORT_PIECE) {
+								a.slowq[lt * (long long) QCAP + atomicAdd(&misc[M_NSLOW], 1u)] = (uint16_t) q;
+								atomicAdd(&misc[M_HIST + n], 1u);
+							}
 							else if (n <= JTK_GROUP8_PIECE) a.med8[atomicAdd(&a.hdr->n_med8, 1u)] = ((uint32_t) lt << 14) | (uint32_t) q;
 							else a.med32[atomicAdd(&a.hdr->n_med32, 1u)] = ((uint32_t) lt << 14) | (uint32_t) q;
 						}
@@ -398,72 +402,89 @@ __global__ void __launch_bounds__(JTK_NT, 2) jtk_split_lookup_kernel(const __gri
 			a.nslow[tile] = (int32_t) misc[M_NSLOW];
 			a.tile_count[tile] = (int32_t) misc[M_HITS];
 		}
+		if (tid <= JTK_SHORT_PIECE && misc[M_HIST + tid]) atomicAdd(&a.hdr->short_cnt[tid], misc[M_HIST + tid]);
 	}
 }
 
 /* ---------------------------------------------------------------------------------------------
- * kernel 2a: bytePairMerge for the short pieces (2..32 bytes) the lookup did not resolve
- * (GptBytePairEncoding.java:85, 200-300).  One CTA per tile, one thread per piece.  The tile's unresolved pieces are
- * counting-sorted by length so that the threads of a warp run merge loops of similar length; tokens go to the
- * tile's slice of slowtok at the piece's byte position.
+ * kernels 2a: bytePairMerge for the short pieces (2..32 bytes) the lookup did not resolve
+ * (GptBytePairEncoding.java:85, 200-300).  The unresolved short pieces of the whole sub-batch are counting-sorted by
+ * length into one global list (offsets kernel + scatter kernel), then persistent warps take 32 consecutive entries
+ * at a time, one thread per piece: every warp is full and its threads run merge loops of the same length.
+ * Tokens go to the tile's slice of slowtok at the piece's byte position.
  * ------------------------------------------------------------------------------------------- */
-constexpr int MNT = 128;
+__global__ void jtk_short_offsets_kernel(const jtk_encode_args a) {
+	if (threadIdx.x != 0) return;
+	unsigned run = 0;
+	for (int n = 0; n <= JTK_SHORT_PIECE; n++) {
+		a.hdr->short_base[n] = run;
+		a.hdr->short_cur[n] = run;
+		run += a.hdr->short_cnt[n];
+	}
+	a.hdr->short_base[JTK_SHORT_PIECE + 1] = run;
+	a.hdr->short_next[0] = 0;
+	a.hdr->short_next[1] = a.hdr->short_base[17];
+}
 
-__global__ void __launch_bounds__(MNT) jtk_merge_short_kernel(const __grid_constant__ jtk_encode_args a) {
-	__shared__ uint16_t s_order[QCAP];
-	__shared__ int s_hist[JTK_SHORT_PIECE + 2], s_cursor[JTK_SHORT_PIECE + 2];
-	__shared__ int32_t s_scr[2 * JTK_SHORT_PIECE * MNT]; /* tok / rk, slot k of thread t at k * MNT + t (bank = thread) */
-	__shared__ int s_sum;
-	const jtk_tables &T = a.T;
-	const int tid = threadIdx.x, lane = tid & 31;
+constexpr int SNT = 128;
+
+__global__ void __launch_bounds__(SNT) jtk_short_scatter_kernel(const __grid_constant__ jtk_encode_args a) {
+	__shared__ unsigned s_hist[JTK_SHORT_PIECE + 1], s_cur[JTK_SHORT_PIECE + 1];
+	const int tid = threadIdx.x;
 	const long long tile = a.tile_begin + blockIdx.x;
 	if (tile >= a.tile_end) return;
 	const int S = a.nslow[tile];
 	if (S == 0) return;
 	const long long lt = tile - a.tile_begin;
-	const int64_t tb = tile * (int64_t) JTK_TILE;
-	int32_t *rec = a.rec + lt * (long long) RECN;
+	const int32_t *rec = a.rec + lt * (long long) RECN;
 	const uint16_t *sq = a.slowq + lt * (long long) QCAP;
-	int32_t *stok = a.slowtok + lt * (long long) RECN;
-	const bool write_tok = !(a.flags & JTK_COUNT_ONLY);
+	if (tid <= JTK_SHORT_PIECE) s_hist[tid] = 0;
+	__syncthreads();
+	for (int k = tid; k < S; k += SNT) atomicAdd(&s_hist[(rec_payload(rec[sq[k]]) & 0x7FFu) + 1], 1u);
+	__syncthreads();
+	if (tid <= JTK_SHORT_PIECE) s_cur[tid] = s_hist[tid] ? atomicAdd(&a.hdr->short_cur[tid], s_hist[tid]) : 0u; /* reserve a range per length */
+	__syncthreads();
+	for (int k = tid; k < S; k += SNT) {
+		const int q = sq[k];
+		const int n = (int) (rec_payload(rec[q]) & 0x7FFu) + 1;
+		a.shortlist[atomicAdd(&s_cur[n], 1u)] = ((uint32_t) lt << 14) | (uint32_t) q;
+	}
+}
 
-	if (tid < JTK_SHORT_PIECE + 2) s_hist[tid] = 0;
-	if (tid == 0) s_sum = 0;
-	__syncthreads();
-	for (int k = tid; k < S; k += MNT) atomicAdd(&s_hist[(rec_payload(rec[sq[k]]) & 0x7FFu) + 1], 1);
-	__syncthreads();
-	if (tid == 0) {
-		int run = 0;
-		for (int b = 0; b < JTK_SHORT_PIECE + 2; b++) {
-			s_cursor[b] = run;
-			run += s_hist[b];
+/* NSLOT = 16: pieces of 2..16 bytes; NSLOT = 32: pieces of 17..32 bytes (twice the shared memory per thread) */
+template <int NSLOT, int NTHREADS>
+__global__ void __launch_bounds__(NTHREADS) jtk_merge_short_kernel(const __grid_constant__ jtk_encode_args a) {
+	__shared__ int32_t s_scr[2 * NSLOT * NTHREADS]; /* tok / rk, slot k of thread t at k * NTHREADS + t (bank = thread) */
+	const jtk_tables &T = a.T;
+	const int tid = threadIdx.x, lane = tid & 31;
+	const bool write_tok = !(a.flags & JTK_COUNT_ONLY);
+	const unsigned end = NSLOT == 16 ? a.hdr->short_base[17] : a.hdr->short_base[JTK_SHORT_PIECE + 1];
+	unsigned *cursor = &a.hdr->short_next[NSLOT == 16 ? 0 : 1];
+	int32_t *tk = s_scr + tid, *rk = s_scr + NSLOT * NTHREADS + tid;
+	for (;;) {
+		unsigned idx = 0;
+		if (lane == 0) idx = atomicAdd(cursor, 32u);
+		idx = __shfl_sync(0xFFFFFFFFu, idx, 0) + lane;
+		if (idx - lane >= end) break;
+		if (idx < end) {
+			const uint32_t e = a.shortlist[idx];
+			const long long lt = e >> 14;
+			const int q = (int) (e & 0x3FFFu);
+			int32_t *rec = a.rec + lt * (long long) RECN;
+			const uint32_t pl = rec_payload(rec[q]);
+			const int s = (int) (pl >> 11), n = (int) (pl & 0x7FFu) + 1;
+			const int64_t tb = (a.tile_begin + lt) * (int64_t) JTK_TILE;
+			bool unk = false;
+			const int cnt = jtk_merge_short(T, a.bytes + tb + s, n, tk, rk, NTHREADS, &unk);
+			if (write_tok) {
+				int32_t *stok = a.slowtok + lt * (long long) RECN + s;
+				for (int k = 0; k < cnt; k++) stok[k] = tk[k * NTHREADS];
+			}
+			rec[q] = rec_make(s, cnt);
+			atomicAdd(&a.tile_count[a.tile_begin + lt], cnt);
+			if (unk) flag_doc(a, tb + s, JTK_DOC_UNKNOWN_BYTES);
 		}
 	}
-	__syncthreads();
-	for (int k = tid; k < S; k += MNT) {
-		const int q = sq[k];
-		s_order[atomicAdd(&s_cursor[(rec_payload(rec[q]) & 0x7FFu) + 1], 1)] = (uint16_t) q;
-	}
-	__syncthreads();
-
-	int sum = 0;
-	for (int i = tid; i < S; i += MNT) {
-		const int q = s_order[i];
-		const uint32_t pl = rec_payload(rec[q]);
-		const int s = (int) (pl >> 11), n = (int) (pl & 0x7FFu) + 1;
-		bool unk = false;
-		int32_t *tk = s_scr + tid, *rk = s_scr + JTK_SHORT_PIECE * MNT + tid;
-		const int cnt = jtk_merge_short(T, a.bytes + tb + s, n, tk, rk, MNT, &unk);
-		if (write_tok)
-			for (int k = 0; k < cnt; k++) stok[s + k] = tk[k * MNT];
-		rec[q] = rec_make(s, cnt);
-		sum += cnt;
-		if (unk) flag_doc(a, tb + s, JTK_DOC_UNKNOWN_BYTES);
-	}
-	sum = __reduce_add_sync(0xFFFFFFFFu, sum);
-	if (lane == 0) atomicAdd(&s_sum, sum);
-	__syncthreads();
-	if (tid == 0) atomicAdd(&a.tile_count[tile], s_sum);
 }
 
 /* ---------------------------------------------------------------------------------------------
@@ -583,6 +604,7 @@ __global__ void __launch_bounds__(1024, 1) jtk_tile_scan_kernel(const jtk_encode
 		a.hdr->total_tokens = (unsigned long long) s_carry;
 		a.hdr->ticket = 0; /* the next sub-batch starts its tickets and medium-piece lists at zero */
 		a.hdr->n_med8 = a.hdr->n_med32 = a.hdr->cursor8 = a.hdr->cursor32 = 0;
+		for (int n = 0; n <= JTK_SHORT_PIECE; n++) a.hdr->short_cnt[n] = 0;
 		if (!(a.flags & JTK_COUNT_ONLY) && a.ids && s_carry > a.ids_cap) a.hdr->overflow = 1;
 	}
 }
@@ -606,29 +628,43 @@ __global__ void __launch_bounds__(GNT) jtk_gather_kernel(const __grid_constant__
 	const int32_t *stok = a.slowtok + lt * (long long) RECN;
 	const bool write_ids = !(a.flags & JTK_COUNT_ONLY) && a.ids != nullptr && !a.hdr->overflow;
 	int carry = 0;
-	for (int q0 = 0; q0 < P; q0 += GNT) {
-		const int q = q0 + tid;
-		int32_t r = 0;
-		int cnt = 0;
-		if (q < P) {
-			r = rec[q];
-			if (rec_is_id(r)) cnt = 1;
-			else if (!(rec_payload(r) & REC_LONG)) cnt = (int) (rec_payload(r) & 0x7FFu) + 1;
+	constexpr int IPT = 8; /* consecutive pieces per thread and round: one block scan per 2048 pieces */
+	for (int q0 = 0; q0 < P; q0 += GNT * IPT) {
+		const int qb = q0 + tid * IPT;
+		int32_t r[IPT];
+		int cnt[IPT];
+		int mine = 0;
+#pragma unroll
+		for (int j = 0; j < IPT; j++) {
+			const int q = qb + j;
+			r[j] = 0;
+			cnt[j] = 0;
+			if (q < P) {
+				r[j] = rec[q];
+				if (rec_is_id(r[j])) cnt[j] = 1;
+				else if (!(rec_payload(r[j]) & REC_LONG)) cnt[j] = (int) (rec_payload(r[j]) & 0x7FFu) + 1;
+			}
+			mine += cnt[j];
 		}
 		int round_total;
-		const int excl = carry + block_exclusive_scan<GNT>(cnt, s_w, &round_total);
-		if (q < P) {
-			s_prefix[q] = (uint32_t) excl;
-			if (rec_is_id(r)) {
-				if (write_ids) a.ids[base + excl] = r;
-			} else {
-				const uint32_t pl = rec_payload(r);
-				const int s = (int) ((pl >> 11) & 0x1FFFu);
-				if (pl & REC_LONG) {
-					a.long_list[stok[s]].insert_at = base + excl;
-				} else if (write_ids) {
-					for (int k = 0; k < cnt; k++) a.ids[base + excl + k] = stok[s + k];
+		int excl = carry + block_exclusive_scan<GNT>(mine, s_w, &round_total);
+#pragma unroll
+		for (int j = 0; j < IPT; j++) {
+			const int q = qb + j;
+			if (q < P) {
+				s_prefix[q] = (uint32_t) excl;
+				if (rec_is_id(r[j])) {
+					if (write_ids) a.ids[base + excl] = r[j];
+				} else {
+					const uint32_t pl = rec_payload(r[j]);
+					const int s = (int) ((pl >> 11) & 0x1FFFu);
+					if (pl & REC_LONG) {
+						a.long_list[stok[s]].insert_at = base + excl;
+					} else if (write_ids) {
+						for (int k = 0; k < cnt[j]; k++) a.ids[base + excl + k] = stok[s + k];
+					}
 				}
+				excl += cnt[j];
 			}
 		}
 		carry += round_total;
@@ -1017,9 +1053,14 @@ cudaError_t jtk_launch_sub_batch(const jtk_encode_args &a, int num_sms, cudaEven
 	cudaLaunchKernelEx(&cfg, jtk_split_lookup_kernel, a);
 	if (k1) cudaEventRecord(k1, st);
 	cfg.dynamicSmemBytes = 0;
-	cfg.gridDim = dim3((unsigned) nt);
-	cfg.blockDim = dim3(MNT);
-	cudaLaunchKernelEx(&cfg, jtk_merge_short_kernel, a);
+	jtk_short_offsets_kernel<<<1, 32, 0, st>>>(a);
+	jtk_short_scatter_kernel<<<(unsigned) nt, SNT, 0, st>>>(a);
+	cfg.gridDim = dim3((unsigned) (num_sms * 6));
+	cfg.blockDim = dim3(256);
+	cudaLaunchKernelEx(&cfg, jtk_merge_short_kernel<16, 256>, a);
+	cfg.gridDim = dim3((unsigned) (num_sms * 6));
+	cfg.blockDim = dim3(128);
+	cudaLaunchKernelEx(&cfg, jtk_merge_short_kernel<32, 128>, a);
 	cfg.gridDim = dim3((unsigned) (num_sms * 6));
 	cfg.blockDim = dim3(GNTM);
 	cudaLaunchKernelEx(&cfg, jtk_merge_medium_kernel, a);

@@ -30,6 +30,10 @@ struct jtk_batch_header {
 	unsigned int violations; /* long-piece rounds that had to fall back to one-merge-at-a-time */
 	unsigned int n_med8, n_med32;   /* medium pieces of the current sub-batch (33..256 bytes / 257..JTK_LONG_PIECE bytes) */
 	unsigned int cursor8, cursor32; /* work counters of jtk_merge_medium_kernel */
+	unsigned int short_cnt[JTK_SHORT_PIECE + 2];  /* unresolved short pieces of the sub-batch by length */
+	unsigned int short_base[JTK_SHORT_PIECE + 2]; /* exclusive scan of short_cnt */
+	unsigned int short_cur[JTK_SHORT_PIECE + 2];  /* scatter cursors */
+	unsigned int short_next[2];                   /* work counters of the two jtk_merge_short_kernel launches */
 	unsigned int pad;
 };
 
@@ -39,7 +43,7 @@ struct jtk_batch_header {
 #define JTK_GROUP8_PIECE 256                /* up to this length a medium piece is merged by 8 lanes, above by a warp */
 #define JTK_MED8_PER_TILE (JTK_RECN / (JTK_SHORT_PIECE + 1) + 1)
 #define JTK_MED32_PER_TILE (JTK_RECN / (JTK_GROUP8_PIECE + 1) + 1)
-#define JTK_DEFAULT_SUB_TILES 4096         /* tiles per sub-batch: 32 MiB of input, intermediates stay around the L2 size */
+#define JTK_DEFAULT_SUB_TILES 16384        /* tiles per sub-batch: 128 MiB of input (measured: larger sub-batches win over L2 locality) */
 
 struct jtk_encode_args {
 	jtk_tables T;
@@ -60,6 +64,7 @@ struct jtk_encode_args {
 	int32_t *rec;          /* JTK_RECN per tile: one record per piece, in order */
 	int32_t *slowtok;      /* JTK_RECN per tile: tokens of merged pieces at the piece's tile-local byte position */
 	uint16_t *slowq;       /* JTK_QCAP per tile: piece indices of the unresolved short pieces (<= JTK_SHORT_PIECE bytes) */
+	uint32_t *shortlist;   /* JTK_QCAP per tile (one list for the sub-batch): unresolved short pieces sorted by length */
 	uint32_t *med8;        /* JTK_MED8_PER_TILE per tile: (tile index << 14 | piece index) of unresolved pieces of 33..256 bytes */
 	uint32_t *med32;       /* JTK_MED32_PER_TILE per tile: same for 257..JTK_LONG_PIECE bytes */
 	jtk_batch_header *hdr;

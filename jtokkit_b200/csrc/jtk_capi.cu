@@ -513,7 +513,7 @@ static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspa
 		CUDA_TRY(jtk_launch_sub_batch(a, ds->num_sms, time_kernel ? w->kev[(size_t) (2 * i)] : nullptr, time_kernel ? w->kev[(size_t) (2 * i + 1)] : nullptr, st));
 	}
 	CUDA_TRY(jtk_launch_finalize(a, st));
-	info->gpu_launches = (ntiles > 0 ? 1 : 0) + 8 * nsub + 1;
+	info->gpu_launches = (ntiles > 0 ? 1 : 0) + 9 * nsub + 1;
 	CUDA_TRY(cudaMemcpyAsync(w->hdr_host, w->hdr, sizeof(jtk_batch_header), cudaMemcpyDeviceToHost, st));
 	if (!sync_and_long) return JTK_OK;
 	CUDA_TRY(cudaStreamSynchronize(st));

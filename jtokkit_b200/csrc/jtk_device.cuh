@@ -682,23 +682,44 @@ JTK_HD int32_t jtk_lookup_piece(const jtk_tables &T, const uint8_t *p, int n) {
 }
 
 /* ---------------------------------------------------------------------------------------------
- * bytePairMerge for one piece of 2..32 bytes by one thread (GptBytePairEncoding.java:200-275)
+ * bytePairMerge for one piece of 2..JTK_SHORT_PIECE bytes by one thread (GptBytePairEncoding.java:200-275)
  * tok / rk: n staging slots each, element k at index k * stride (the kernel interleaves the slots of the threads of
  * a CTA so that slot k of every thread falls into a different bank).  Returns the token count; tokens end up in slots 0..count-1.
  * *unknown is set when a final part is a byte that is not in the vocabulary.
  * ------------------------------------------------------------------------------------------- */
-JTK_HD int jtk_merge_short(const jtk_tables &T, const uint8_t *p, int n, int32_t *tok, int32_t *rk, int stride, bool *unknown) {
+JTK_HD int jtk_ctz64(uint64_t m) {
+#if defined(__CUDA_ARCH__)
+	return __ffsll((long long) m) - 1;
+#else
+	return __builtin_ctzll(m);
+#endif
+}
+JTK_HD int jtk_clz64(uint64_t m) {
+#if defined(__CUDA_ARCH__)
+	return __clzll((long long) m);
+#else
+	return __builtin_clzll(m);
+#endif
+}
+
+/* MaskT = uint32_t for pieces up to 32 bytes, uint64_t up to 64 bytes */
+template <typename MaskT>
+JTK_HD int jtk_merge_short_t(const jtk_tables &T, const uint8_t *p, int n, int32_t *tok, int32_t *rk, int stride, bool *unknown) {
+	constexpr int BITS = (int) sizeof(MaskT) * 8;
+	const MaskT ONE = 1;
+	auto ctz = [](MaskT m) { return sizeof(MaskT) == 8 ? jtk_ctz64((uint64_t) m) : jtk_ctz((uint32_t) m); };
+	auto top = [](MaskT m) { return sizeof(MaskT) == 8 ? 63 - jtk_clz64((uint64_t) m) : 31 - jtk_clz((uint32_t) m); };
 	for (int k = 0; k < n; k++) {
 		tok[k * stride] = T.byte_id[p[k]];
 		rk[k * stride] = (k + 1 < n) ? T.bytepair[((uint32_t) p[k] << 8) | p[k + 1]] : JTK_RANK_MAX;
 	}
-	uint32_t alive = (n >= 32) ? 0xFFFFFFFFu : ((1u << n) - 1u);
+	MaskT alive = (n >= BITS) ? ~(MaskT) 0 : ((ONE << n) - ONE);
 	for (;;) {
 		/* leftmost strict minimum (:232-240) */
 		int32_t mr = JTK_RANK_MAX;
 		int mi = -1;
-		for (uint32_t m = alive; m;) {
-			const int k = jtk_ctz(m);
+		for (MaskT m = alive; m;) {
+			const int k = ctz(m);
 			m &= m - 1;
 			const int32_t r = rk[k * stride];
 			if (r < mr) {
@@ -707,36 +728,41 @@ JTK_HD int jtk_merge_short(const jtk_tables &T, const uint8_t *p, int n, int32_t
 			}
 		}
 		if (mi < 0) break; /* :247,260-262 */
-		const uint32_t above = alive & ~((2u << mi) - 1u); /* parts after mi */
-		const int nx = jtk_ctz(above);
-		const uint32_t above2 = above & (above - 1);
-		const uint32_t below = alive & ((1u << mi) - 1u);
+		const MaskT above = alive & ~(((ONE << mi) << 1) - ONE); /* parts after mi */
+		const int nx = ctz(above);
+		const MaskT above2 = above & (above - 1);
+		const MaskT below = alive & ((ONE << mi) - ONE);
 		tok[mi * stride] = mr; /* rank == id of the merged token */
-		alive &= ~(1u << nx);
+		alive &= ~(ONE << nx);
 		rk[nx * stride] = JTK_RANK_MAX;
 		if (above2 && below) { /* both neighbours exist: issue the two probes together (:254-257) */
-			const int pv = 31 - jtk_clz(below);
+			const int pv = top(below);
 			int32_t r_right, r_left;
-			jtk_lookup_pair2(T, mr, tok[jtk_ctz(above2) * stride], tok[pv * stride], mr, &r_right, &r_left);
+			jtk_lookup_pair2(T, mr, tok[ctz(above2) * stride], tok[pv * stride], mr, &r_right, &r_left);
 			rk[mi * stride] = r_right;
 			rk[pv * stride] = r_left;
 		} else {
-			rk[mi * stride] = above2 ? jtk_lookup_pair(T, mr, tok[jtk_ctz(above2) * stride]) : JTK_RANK_MAX; /* :254 */
+			rk[mi * stride] = above2 ? jtk_lookup_pair(T, mr, tok[ctz(above2) * stride]) : JTK_RANK_MAX; /* :254 */
 			if (below) {
-				const int pv = 31 - jtk_clz(below);
+				const int pv = top(below);
 				rk[pv * stride] = jtk_lookup_pair(T, tok[pv * stride], mr); /* :255-257 */
 			}
 		}
 	}
 	int cnt = 0;
-	for (uint32_t m = alive; m;) {
-		const int k = jtk_ctz(m);
+	for (MaskT m = alive; m;) {
+		const int k = ctz(m);
 		m &= m - 1;
 		const int32_t t = tok[k * stride];
 		if (t < JTK_PSEUDO_BASE + 256) *unknown = true;
 		tok[(cnt++) * stride] = t;
 	}
 	return cnt;
+}
+
+JTK_HD int jtk_merge_short(const jtk_tables &T, const uint8_t *p, int n, int32_t *tok, int32_t *rk, int stride, bool *unknown) {
+	if (n <= 32) return jtk_merge_short_t<uint32_t>(T, p, n, tok, rk, stride, unknown);
+	return jtk_merge_short_t<uint64_t>(T, p, n, tok, rk, stride, unknown);
 }
 
 /* Sequential bytePairMerge for any length (used by the host-side emulator for pieces the device handles

@@ -44,7 +44,8 @@ __device__ __forceinline__ int32_t rec_make(int s, int m) { return REC_BASE + (i
 __device__ __forceinline__ uint32_t rec_payload(int32_t r) { return (uint32_t) (r - REC_BASE); }
 
 /* indices into the small shared "misc" array */
-enum { M_TILE = 0, M_NSLOW, M_RS, M_CARRY, M_HITS, M_WSUM = 16, M_HIST = 32 /* .. M_HIST + 33 */ };
+enum { M_TILE = 0, M_NSLOW, M_RS, M_CARRY, M_HITS, M_WSUM = 16, M_HIST = 48 /* .. M_HIST + JTK_SHORT_PIECE */, M_WORDS = 128 };
+static_assert(M_HIST + JTK_SHORT_PIECE + 1 <= M_WORDS, "misc too small");
 
 /* first set bit in [from, limit] of a bit array, or -1 */
 __device__ __forceinline__ int next_bit(const uint32_t *bm, int from, int limit) {
@@ -109,6 +110,32 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *wsum, int *total
  * neighbours are found with REDUX over per-lane alive masks, and the two rank probes of a merge (:254-257) are
  * issued by two lanes in parallel.  Several groups share a warp (G = 8: four pieces per warp).
  * ------------------------------------------------------------------------------------------- */
+/* min / max over the G lanes of a group; full warps use the hardware REDUX, smaller groups a xor-shuffle butterfly */
+template <int G>
+__device__ __forceinline__ int group_min(unsigned gmask, int v) {
+	if (G == 32) return __reduce_min_sync(gmask, v);
+#pragma unroll
+	for (int o = G / 2; o; o >>= 1) v = min(v, __shfl_xor_sync(gmask, v, o));
+	return v;
+}
+template <int G>
+__device__ __forceinline__ int group_max(unsigned gmask, int v) {
+	if (G == 32) return __reduce_max_sync(gmask, v);
+#pragma unroll
+	for (int o = G / 2; o; o >>= 1) v = max(v, __shfl_xor_sync(gmask, v, o));
+	return v;
+}
+/* leftmost minimum in one pass: key = rank (signed, high word) : position (low word) */
+template <int G>
+__device__ __forceinline__ long long group_min64(unsigned gmask, long long v) {
+#pragma unroll
+	for (int o = G / 2; o; o >>= 1) {
+		const long long y = __shfl_xor_sync(gmask, v, o);
+		v = y < v ? y : v;
+	}
+	return v;
+}
+
 template <int LOG2G>
 __device__ int merge_group(const jtk_tables &T, const uint8_t *p, int n, int32_t *tok, int32_t *rk, bool *unknown) {
 	constexpr int G = 1 << LOG2G;
@@ -142,21 +169,22 @@ __device__ int merge_group(const jtk_tables &T, const uint8_t *p, int n, int32_t
 	};
 	rescan();
 	for (;;) {
-		const int32_t mr = __reduce_min_sync(gmask, lr);
+		const long long best = group_min64<G>(gmask, ((long long) lr << 32) | (unsigned) lk); /* leftmost minimum (:232-240) */
+		const int32_t mr = (int32_t) (best >> 32);
 		if (mr == JTK_RANK_MAX) break;
-		const int mi = __reduce_min_sync(gmask, lr == mr ? lk : 0x7fffffff); /* leftmost minimum (:232-240) */
+		const int mi = (int) (unsigned) best;
 		/* next alive position after k / previous alive position before k */
 		auto next_alive = [&](int k) {
 			int j0 = (k >> LOG2G) + (gl <= (k & (G - 1)) ? 1 : 0);
 			uint32_t m = j0 >= 32 ? 0u : (alive & (0xFFFFFFFFu << j0));
 			int cand = m ? (((__ffs((int) m) - 1) << LOG2G) + gl) : 0x7fffffff;
-			return __reduce_min_sync(gmask, cand);
+			return group_min<G>(gmask, cand);
 		};
 		auto prev_alive = [&](int k) {
 			int j1 = (k >> LOG2G) - (gl < (k & (G - 1)) ? 0 : 1);
 			uint32_t m = j1 < 0 ? 0u : (alive & (j1 >= 31 ? 0xFFFFFFFFu : ((2u << j1) - 1u)));
 			int cand = m ? (((31 - __clz((int) m)) << LOG2G) + gl) : -1;
-			return __reduce_max_sync(gmask, cand);
+			return group_max<G>(gmask, cand);
 		};
 		const int nx = next_alive(mi);
 		const int nn = next_alive(nx);
@@ -203,7 +231,7 @@ __global__ void __launch_bounds__(JTK_NT, 2) jtk_split_lookup_kernel(const __gri
 	uint16_t *plist = reinterpret_cast<uint16_t *>(dmask + JTK_MASK_WORDS); /* region index of every piece start, in order */
 	uint32_t *chunk_pref = reinterpret_cast<uint32_t *>(plist + RECN);      /* pieces before each 16-byte chunk */
 	uint32_t *misc = chunk_pref + TC;
-	uint8_t *s_ascii = reinterpret_cast<uint8_t *>(misc + 64); /* ASCII class table, 128 bytes */
+	uint8_t *s_ascii = reinterpret_cast<uint8_t *>(misc + M_WORDS); /* ASCII class table, 128 bytes */
 
 	const int tid = threadIdx.x;
 	const int lane = tid & 31;
@@ -424,6 +452,7 @@ __global__ void jtk_short_offsets_kernel(const jtk_encode_args a) {
 	a.hdr->short_base[JTK_SHORT_PIECE + 1] = run;
 	a.hdr->short_next[0] = 0;
 	a.hdr->short_next[1] = a.hdr->short_base[17];
+	a.hdr->short_next[2] = a.hdr->short_base[33];
 }
 
 constexpr int SNT = 128;
@@ -451,15 +480,15 @@ __global__ void __launch_bounds__(SNT) jtk_short_scatter_kernel(const __grid_con
 	}
 }
 
-/* NSLOT = 16: pieces of 2..16 bytes; NSLOT = 32: pieces of 17..32 bytes (twice the shared memory per thread) */
+/* NSLOT = 16 / 32 / 64: pieces of 2..16 / 17..32 / 33..64 bytes; NSLOT * NTHREADS is constant (32 KiB of scratch) */
 template <int NSLOT, int NTHREADS>
 __global__ void __launch_bounds__(NTHREADS) jtk_merge_short_kernel(const __grid_constant__ jtk_encode_args a) {
 	__shared__ int32_t s_scr[2 * NSLOT * NTHREADS]; /* tok / rk, slot k of thread t at k * NTHREADS + t (bank = thread) */
 	const jtk_tables &T = a.T;
 	const int tid = threadIdx.x, lane = tid & 31;
 	const bool write_tok = !(a.flags & JTK_COUNT_ONLY);
-	const unsigned end = NSLOT == 16 ? a.hdr->short_base[17] : a.hdr->short_base[JTK_SHORT_PIECE + 1];
-	unsigned *cursor = &a.hdr->short_next[NSLOT == 16 ? 0 : 1];
+	const unsigned end = a.hdr->short_base[NSLOT + 1];
+	unsigned *cursor = &a.hdr->short_next[NSLOT == 16 ? 0 : NSLOT == 32 ? 1 : 2];
 	int32_t *tk = s_scr + tid, *rk = s_scr + NSLOT * NTHREADS + tid;
 	for (;;) {
 		unsigned idx = 0;
@@ -475,7 +504,8 @@ __global__ void __launch_bounds__(NTHREADS) jtk_merge_short_kernel(const __grid_
 			const int s = (int) (pl >> 11), n = (int) (pl & 0x7FFu) + 1;
 			const int64_t tb = (a.tile_begin + lt) * (int64_t) JTK_TILE;
 			bool unk = false;
-			const int cnt = jtk_merge_short(T, a.bytes + tb + s, n, tk, rk, NTHREADS, &unk);
+			const int cnt = NSLOT <= 32 ? jtk_merge_short_t<uint32_t>(T, a.bytes + tb + s, n, tk, rk, NTHREADS, &unk)
+			                            : jtk_merge_short_t<uint64_t>(T, a.bytes + tb + s, n, tk, rk, NTHREADS, &unk);
 			if (write_tok) {
 				int32_t *stok = a.slowtok + lt * (long long) RECN + s;
 				for (int k = 0; k < cnt; k++) stok[k] = tk[k * NTHREADS];
@@ -1061,6 +1091,9 @@ cudaError_t jtk_launch_sub_batch(const jtk_encode_args &a, int num_sms, cudaEven
 	cfg.gridDim = dim3((unsigned) (num_sms * 6));
 	cfg.blockDim = dim3(128);
 	cudaLaunchKernelEx(&cfg, jtk_merge_short_kernel<32, 128>, a);
+	cfg.gridDim = dim3((unsigned) (num_sms * 6));
+	cfg.blockDim = dim3(64);
+	cudaLaunchKernelEx(&cfg, jtk_merge_short_kernel<64, 64>, a);
 	cfg.gridDim = dim3((unsigned) (num_sms * 6));
 	cfg.blockDim = dim3(GNTM);
 	cudaLaunchKernelEx(&cfg, jtk_merge_medium_kernel, a);

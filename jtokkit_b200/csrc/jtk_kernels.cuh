@@ -33,7 +33,7 @@ struct jtk_batch_header {
 	unsigned int short_cnt[JTK_SHORT_PIECE + 2];  /* unresolved short pieces of the sub-batch by length */
 	unsigned int short_base[JTK_SHORT_PIECE + 2]; /* exclusive scan of short_cnt */
 	unsigned int short_cur[JTK_SHORT_PIECE + 2];  /* scatter cursors */
-	unsigned int short_next[2];                   /* work counters of the two jtk_merge_short_kernel launches */
+	unsigned int short_next[4];                   /* work counters of the three jtk_merge_short_kernel launches */
 	unsigned int pad;
 };
 
@@ -81,7 +81,7 @@ struct jtk_encode_args {
 	size_t l2_bytes;
 };
 
-#define JTK_SMEM_BYTES (2 * (JTK_REGION + 16) + 2 * 4 * (((JTK_REGION + 32) / 32 + 1)) + 2 * JTK_RECN + 4 * (JTK_TILE / 16) + 256 + 128)
+#define JTK_SMEM_BYTES (2 * (JTK_REGION + 16) + 2 * 4 * (((JTK_REGION + 32) / 32 + 1)) + 2 * JTK_RECN + 4 * (JTK_TILE / 16) + 512 + 128)
 
 cudaError_t jtk_launch_tile_first_doc(const int64_t *doc_off, int64_t ndocs, int64_t ntiles, int32_t *out, cudaStream_t st);
 /* the four kernels of one sub-batch; k0/k1 (nullable) bracket the split+lookup kernel */

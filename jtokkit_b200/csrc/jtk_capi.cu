@@ -644,7 +644,6 @@ struct shard_job {
 };
 
 static int ensure_ws_io(jtk_workspace *w, int64_t nbytes, int64_t ndocs, bool want_ids) {
-	if (!w->stream) CUDA_TRY(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
 	if (nbytes > w->in_cap) {
 		cudaFree(w->d_in);
 		cudaFree(w->d_ids);
@@ -673,8 +672,9 @@ static int ensure_ws_io(jtk_workspace *w, int64_t nbytes, int64_t ndocs, bool wa
 	return JTK_OK;
 }
 
-/* One shard = one device.  Chunks of whole documents are pipelined over two workspaces (streams):
- * while chunk k's ids travel device->host, chunk k+1 is already copied in and encoded. */
+/* One shard = one device.  Chunks of whole documents run through a three-stage pipeline on three streams
+ * (copy-in, compute, copy-out) over three workspaces: while chunk k is encoded, chunk k+1 is copied in and the ids
+ * of chunk k-1 are copied out, so PCIe in both directions and the SMs are busy at the same time. */
 static void run_shard(shard_job *job) {
 	jtk_encoding *e = job->e;
 	jtk_device_state *ds = job->ds;
@@ -702,23 +702,57 @@ static void run_shard(shard_job *job) {
 		int rc = pinned_get(e, sizeof(int32_t) * (shard_bytes / 1024 * e->tokens_per_kib.load() + 4096), &job->ids);
 		if (rc != JTK_OK) return fail(rc);
 	}
-	jtk_workspace *ws[2] = {acquire_ws(ds), acquire_ws(ds)};
-	cudaEvent_t ev0[2] = {nullptr, nullptr}, ev1[2] = {nullptr, nullptr};
-	std::vector<int64_t> rebase; /* per chunk: host-side doc_off copy rebased to the chunk */
-	std::vector<jtk_pinned_buf> stage_off(2);
-	int rc = JTK_OK;
-	jtk_device_info infos[2];
+	constexpr int NS = 3;
+	jtk_workspace *ws[NS];
+	cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+	cudaEvent_t ev_in[NS], ev_k0[NS], ev_k1[NS], ev_out[NS];
+	jtk_pinned_buf stage_off[NS], stage_doc[NS];
+	jtk_device_info infos[NS];
+	int64_t out_chunk[NS]; /* chunk whose copy-out is in flight on the slot, -1 = none */
+	int64_t out_base[NS];
 	memset(infos, 0, sizeof(infos));
-	auto finish_chunk = [&](size_t k) -> int {
-		/* chunk k's kernels are queued on ws[k & 1]; wait for its header, run the long path if needed, copy out */
-		jtk_workspace *w = ws[k & 1];
+	int rc = JTK_OK;
+	for (int i = 0; i < NS; i++) {
+		ws[i] = acquire_ws(ds);
+		ev_in[i] = ev_k0[i] = ev_k1[i] = ev_out[i] = nullptr;
+		out_chunk[i] = -1;
+		out_base[i] = 0;
+	}
+	if (cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking) != cudaSuccess)
+		rc = set_error(JTK_E_CUDA, "cudaStreamCreate failed");
+	for (int i = 0; i < NS && rc == JTK_OK; i++)
+		if (cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&ev_k0[i]) != cudaSuccess ||
+		    cudaEventCreate(&ev_k1[i]) != cudaSuccess || cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming) != cudaSuccess)
+			rc = set_error(JTK_E_CUDA, "cudaEventCreate failed");
+
+	/* the copy-out of a slot has landed: rebase its token offsets / statuses into the shard's arrays */
+	auto retire = [&](int slot) -> int {
+		if (out_chunk[slot] < 0) return JTK_OK;
+		CUDA_TRY(cudaEventSynchronize(ev_out[slot]));
+		const size_t k = (size_t) out_chunk[slot];
+		const int64_t d0 = cb[k], nd = cb[k + 1] - d0;
+		const int64_t *h_tok = static_cast<const int64_t *>(stage_off[slot].p);
+		const int32_t *h_st = reinterpret_cast<const int32_t *>(h_tok + nd + 1);
+		const int64_t base = out_base[slot];
+		for (int64_t i = 0; i < nd; i++) {
+			job->tok_off_out[d0 - job->d_begin + i] = h_tok[i] + base;
+			job->status_out[d0 - job->d_begin + i] = h_st[i];
+		}
+		out_chunk[slot] = -1;
+		return JTK_OK;
+	};
+	/* chunk k has been encoded on its slot: read the totals, run the long-piece path if needed, start the copy-out */
+	auto copy_out = [&](size_t k) -> int {
+		const int slot = (int) (k % NS);
+		jtk_workspace *w = ws[slot];
 		const int64_t d0 = cb[k], d1 = cb[k + 1], nd = d1 - d0;
 		const int64_t cbytes = off[d1] - off[d0];
-		CUDA_TRY(cudaStreamSynchronize(w->stream));
+		CUDA_TRY(cudaEventSynchronize(ev_k1[slot]));
 		float ms = 0;
-		cudaEventElapsedTime(&ms, ev0[k & 1], ev1[k & 1]);
+		cudaEventElapsedTime(&ms, ev_k0[slot], ev_k1[slot]);
 		job->device_ms += ms;
-		jtk_device_info &info = infos[k & 1];
+		jtk_device_info &info = infos[slot];
 		info.num_tokens = (int64_t) w->hdr_host->total_tokens;
 		info.num_long_pieces = w->hdr_host->n_long;
 		if (w->hdr_host->overflow) return set_error(JTK_E_CAPACITY, "internal ids buffer too small");
@@ -739,9 +773,9 @@ static void run_shard(shard_job *job) {
 			cudaEvent_t l0, l1;
 			cudaEventCreate(&l0);
 			cudaEventCreate(&l1);
-			cudaEventRecord(l0, w->stream);
-			int r2 = run_long_pieces(ds, w, a, w->hdr_host->n_long, w->stream, &info);
-			cudaEventRecord(l1, w->stream);
+			cudaEventRecord(l0, s_comp);
+			int r2 = run_long_pieces(ds, w, a, w->hdr_host->n_long, s_comp, &info);
+			cudaEventRecord(l1, s_comp);
 			cudaEventSynchronize(l1);
 			float lms = 0;
 			cudaEventElapsedTime(&lms, l0, l1);
@@ -754,6 +788,12 @@ static void run_shard(shard_job *job) {
 		const int64_t ntok = info.num_tokens;
 		if (want_ids) {
 			if ((job->ntokens + ntok) * (int64_t) sizeof(int32_t) > job->ids.cap) {
+				/* rare: the shard is denser than anything seen before; finish the copies in flight, then move to a bigger buffer */
+				for (int i = 0; i < NS; i++) {
+					int r2 = retire(i);
+					if (r2 != JTK_OK) return r2;
+				}
+				CUDA_TRY(cudaStreamSynchronize(s_out));
 				jtk_pinned_buf bigger;
 				const int64_t done_bytes = std::max<int64_t>(off[d1] - off[job->d_begin], 1);
 				const int64_t projected = (job->ntokens + ntok) * shard_bytes / done_bytes; /* tokens if the rest is as dense */
@@ -763,11 +803,9 @@ static void run_shard(shard_job *job) {
 				pinned_put(e, job->ids);
 				job->ids = bigger;
 			}
-			CUDA_TRY(cudaMemcpyAsync(static_cast<int32_t *>(job->ids.p) + job->ntokens, w->d_ids, sizeof(int32_t) * (size_t) ntok, cudaMemcpyDeviceToHost,
-			                         w->stream));
+			CUDA_TRY(cudaMemcpyAsync(static_cast<int32_t *>(job->ids.p) + job->ntokens, w->d_ids, sizeof(int32_t) * (size_t) ntok, cudaMemcpyDeviceToHost, s_out));
 		}
-		/* token offsets and statuses: to pinned staging, then rebased into the result on the host */
-		jtk_pinned_buf &so = stage_off[k & 1];
+		jtk_pinned_buf &so = stage_off[slot];
 		const int64_t need = (int64_t) sizeof(int64_t) * (nd + 1) + (int64_t) sizeof(int32_t) * (nd + 1);
 		if (so.cap < need) {
 			pinned_put(e, so);
@@ -776,14 +814,11 @@ static void run_shard(shard_job *job) {
 		}
 		int64_t *h_tok = static_cast<int64_t *>(so.p);
 		int32_t *h_st = reinterpret_cast<int32_t *>(h_tok + nd + 1);
-		CUDA_TRY(cudaMemcpyAsync(h_tok, w->d_tok_off, sizeof(int64_t) * (size_t) (nd + 1), cudaMemcpyDeviceToHost, w->stream));
-		if (nd > 0) CUDA_TRY(cudaMemcpyAsync(h_st, w->d_status, sizeof(int32_t) * (size_t) nd, cudaMemcpyDeviceToHost, w->stream));
-		CUDA_TRY(cudaStreamSynchronize(w->stream));
-		const int64_t base = job->ntokens;
-		for (int64_t i = 0; i < nd; i++) {
-			job->tok_off_out[d0 - job->d_begin + i] = h_tok[i] + base;
-			job->status_out[d0 - job->d_begin + i] = h_st[i];
-		}
+		CUDA_TRY(cudaMemcpyAsync(h_tok, w->d_tok_off, sizeof(int64_t) * (size_t) (nd + 1), cudaMemcpyDeviceToHost, s_out));
+		if (nd > 0) CUDA_TRY(cudaMemcpyAsync(h_st, w->d_status, sizeof(int32_t) * (size_t) nd, cudaMemcpyDeviceToHost, s_out));
+		CUDA_TRY(cudaEventRecord(ev_out[slot], s_out));
+		out_chunk[slot] = (int64_t) k;
+		out_base[slot] = job->ntokens;
 		job->ntokens += ntok;
 		{
 			const int64_t per_kib = ntok * 1024 / std::max<int64_t>(cbytes, 1024) + 8;
@@ -795,42 +830,59 @@ static void run_shard(shard_job *job) {
 		job->chunk_tokens.push_back(ntok);
 		return JTK_OK;
 	};
-	for (int i = 0; i < 2 && rc == JTK_OK; i++) {
-		if (cudaEventCreate(&ev0[i]) != cudaSuccess || cudaEventCreate(&ev1[i]) != cudaSuccess) rc = set_error(JTK_E_CUDA, "cudaEventCreate failed");
-	}
+
 	for (size_t k = 0; k < nchunks && rc == JTK_OK; k++) {
-		jtk_workspace *w = ws[k & 1];
+		const int slot = (int) (k % NS);
+		jtk_workspace *w = ws[slot];
 		const int64_t d0 = cb[k], d1 = cb[k + 1], nd = d1 - d0;
 		const int64_t b0 = off[d0], cbytes = off[d1] - b0;
+		rc = retire(slot); /* the slot's previous copy-out must have landed before its buffers are reused */
+		if (rc != JTK_OK) break;
 		rc = ensure_ws_io(w, cbytes, nd, want_ids);
 		if (rc != JTK_OK) break;
-		/* chunk-relative document offsets (the kernels require doc_off[0] == 0) */
-		rebase.resize((size_t) nd + 1);
-		for (int64_t i = 0; i <= nd; i++) rebase[(size_t) i] = off[d0 + i] - b0;
-		cudaError_t ce = cudaMemcpyAsync(w->d_doc_off, rebase.data(), sizeof(int64_t) * (size_t) (nd + 1), cudaMemcpyHostToDevice, w->stream);
-		if (ce == cudaSuccess) ce = cudaStreamSynchronize(w->stream); /* rebase is reused for the next chunk */
-		if (ce == cudaSuccess && cbytes > 0) ce = cudaMemcpyAsync(w->d_in, job->utf8 + b0, (size_t) cbytes, cudaMemcpyHostToDevice, w->stream);
-		if (ce == cudaSuccess && nd > 0) ce = cudaMemsetAsync(w->d_status, 0, sizeof(int32_t) * (size_t) nd, w->stream);
+		/* chunk-relative document offsets (the kernels require doc_off[0] == 0), staged in pinned memory */
+		jtk_pinned_buf &sd = stage_doc[slot];
+		if (sd.cap < (int64_t) sizeof(int64_t) * (nd + 1)) {
+			pinned_put(e, sd);
+			rc = pinned_get(e, (int64_t) sizeof(int64_t) * (nd + 1) * 5 / 4, &sd);
+			if (rc != JTK_OK) break;
+		}
+		int64_t *rebase = static_cast<int64_t *>(sd.p);
+		for (int64_t i = 0; i <= nd; i++) rebase[i] = off[d0 + i] - b0;
+		cudaError_t ce = cudaMemcpyAsync(w->d_doc_off, rebase, sizeof(int64_t) * (size_t) (nd + 1), cudaMemcpyHostToDevice, s_in);
+		if (ce == cudaSuccess && cbytes > 0) ce = cudaMemcpyAsync(w->d_in, job->utf8 + b0, (size_t) cbytes, cudaMemcpyHostToDevice, s_in);
+		if (ce == cudaSuccess && nd > 0) ce = cudaMemsetAsync(w->d_status, 0, sizeof(int32_t) * (size_t) nd, s_in);
+		if (ce == cudaSuccess) ce = cudaEventRecord(ev_in[slot], s_in);
+		if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s_comp, ev_in[slot], 0);
 		if (ce != cudaSuccess) {
 			rc = set_error(JTK_E_CUDA, std::string("H2D: ") + cudaGetErrorString(ce));
 			break;
 		}
-		cudaEventRecord(ev0[k & 1], w->stream);
+		cudaEventRecord(ev_k0[slot], s_comp);
 		rc = encode_device_impl(e, ds, w, w->d_in, cbytes, w->d_doc_off, nd, job->flags, want_ids ? w->d_ids : nullptr, w->in_cap, w->d_tok_off, w->d_status,
-		                        nullptr, w->stream, &infos[k & 1], false);
-		cudaEventRecord(ev1[k & 1], w->stream);
+		                        nullptr, s_comp, &infos[slot], false);
+		cudaEventRecord(ev_k1[slot], s_comp);
 		if (rc != JTK_OK) break;
-		if (k >= 1) rc = finish_chunk(k - 1);
+		if (k >= 1) rc = copy_out(k - 1);
 	}
-	if (rc == JTK_OK && nchunks >= 1) rc = finish_chunk(nchunks - 1);
+	if (rc == JTK_OK && nchunks >= 1) rc = copy_out(nchunks - 1);
+	for (int i = 0; i < NS && rc == JTK_OK; i++) rc = retire(i);
 	if (nchunks == 0) job->tok_off_out[0] = 0;
-	for (int i = 0; i < 2; i++) {
-		if (ws[i]->stream) cudaStreamSynchronize(ws[i]->stream);
-		if (ev0[i]) cudaEventDestroy(ev0[i]);
-		if (ev1[i]) cudaEventDestroy(ev1[i]);
+	if (s_in) cudaStreamSynchronize(s_in);
+	if (s_comp) cudaStreamSynchronize(s_comp);
+	if (s_out) cudaStreamSynchronize(s_out);
+	for (int i = 0; i < NS; i++) {
+		if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+		if (ev_k0[i]) cudaEventDestroy(ev_k0[i]);
+		if (ev_k1[i]) cudaEventDestroy(ev_k1[i]);
+		if (ev_out[i]) cudaEventDestroy(ev_out[i]);
 		release_ws(ds, ws[i]);
-		pinned_put(e, stage_off[(size_t) i]);
+		pinned_put(e, stage_off[i]);
+		pinned_put(e, stage_doc[i]);
 	}
+	if (s_in) cudaStreamDestroy(s_in);
+	if (s_comp) cudaStreamDestroy(s_comp);
+	if (s_out) cudaStreamDestroy(s_out);
 	if (rc != JTK_OK) fail(rc);
 }
 

@@ -89,6 +89,18 @@ def dist_setup(n_gpus):
     return rank, world, local
 
 
+def reduce_over_ranks(stats, world):
+    """(max over ranks, sum over ranks) of a 1-D float64 tensor; times use the max, work uses the sum."""
+    if world <= 1:
+        return stats, stats
+    import torch.distributed as dist
+    mx = stats.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    sm = stats.clone()
+    dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    return mx, sm
+
+
 def cpu_port_throughput(utf8_np, doc_off_np, sample_bytes, threads):
     """Times the oracle port (reference algorithm restatement) with `threads` host threads on the first documents of the
     corpus up to sample_bytes.  Returns (tokens/s, bytes, tokens, seconds, ids, counts)."""
@@ -215,13 +227,7 @@ def run_ours(args):
     # ---- reduce over ranks: time = max, tokens / bytes = sum
     stats = torch.tensor([dev_ms, e2e_s, float(ntok), float(nbytes), float(launches), float(ndocs), float(sum(kernel_ms) / len(kernel_ms))],
                          dtype=torch.float64, device=dev)
-    if world > 1:
-        mx = stats.clone()
-        torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)
-        sm = stats.clone()
-        torch.distributed.all_reduce(sm, op=torch.distributed.ReduceOp.SUM)
-    else:
-        mx, sm = stats, stats
+    mx, sm = reduce_over_ranks(stats, world)
     if rank != 0:
         return
     dev_ms_max, e2e_s_max = float(mx[0]), float(mx[1])
@@ -269,7 +275,8 @@ def run_ours(args):
                 "ms_per_step": e2e_s_max / args.steps * 1e3, "api": "jtk_encode_batch (host buffers, pinned input)"},
         "gpu_launches": launches_all,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "jtk_encode_tiles_kernel", "kernel_ms": kms, "algorithmic_bytes_per_launch": int(algo_bytes), "peak_source": peak_src,
+                     "kernel": "jtk_split_lookup_kernel", "kernel_ms": kms, "launches_per_step": int(launches // args.steps),
+                     "frac_whole_step": algo_bytes / (dev_ms / args.steps * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": int(algo_bytes), "peak_source": peak_src,
                      "frac_of_nominal_8000": achieved / 8000.0},
         "cpu_baseline": cpu,
         "parity": parity,

@@ -1,0 +1,70 @@
+"""The C-ABI library loads and exports every symbol include/jtokkit_b200.h declares (no compute calls: there is no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "jtokkit_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(jtk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    from jtokkit_b200 import _capi
+    lib = _capi.lib()
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), "missing export: " + n
+    assert sorted(_capi.SIGNATURES.keys()) == names  # the ctypes binding covers the whole header
+    assert b"sm_100a" in lib.jtk_version() and b"15.0.0" in lib.jtk_version()
+
+
+def test_header_is_plain_c():
+    """extern "C", plain pointers and sizes, no torch / CUDA types in the signatures."""
+    text = open(os.path.join(ROOT, "include", "jtokkit_b200.h")).read()
+    assert 'extern "C"' in text
+    code = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    for banned in ["torch", "cudaStream_t", "at::", "std::", "#include <cuda"]:
+        assert banned not in code
+    import subprocess
+    subprocess.check_call(["gcc", "-std=c99", "-fsyntax-only", "-x", "c", os.path.join(ROOT, "include", "jtokkit_b200.h")])
+
+
+def test_registration_fails_loudly_without_a_gpu():
+    """No CPU fallback: without a CUDA device registration returns JTK_E_CUDA (on the GPU box this test is skipped)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import jtokkit_b200 as jt
+    from jtokkit_b200 import _capi
+    with pytest.raises(_capi.JtkError) as ei:
+        jt.EncodingFactory.cl100k_base()
+    assert ei.value.code == _capi.JTK_E_CUDA
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_unsupported_pattern_is_rejected_at_registration():
+    """Patterns outside the device pattern compiler fail at registration (they never run on the CPU instead)."""
+    import jtokkit_b200 as jt
+    params = jt.GptBytePairEncodingParams("custom", jt.Pattern.compile(r"\w+|\s+"), {b"a": 0}, {})
+    with pytest.raises(ValueError):
+        jt.EncodingFactory.from_parameters(params)
+
+
+def test_product_does_not_import_the_oracle():
+    """The oracle is test infrastructure: nothing under jtokkit_b200/ may import, include, link or load it."""
+    loaders = ("import", "#include", "dlopen", "CDLL", "subprocess", "-l")
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "jtokkit_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                for line in open(os.path.join(dirpath, f), errors="replace"):
+                    if "oracle" in line.lower():
+                        assert not any(tok in line for tok in loaders), (f, line)

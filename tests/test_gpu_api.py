@@ -1,0 +1,146 @@
+"""GPU tests of the API mirror: registries (BaseEncodingRegistryTest.java), batch entry points, decode, error behaviour."""
+import numpy as np
+import pytest
+
+from conftest import ENCODING_NAMES, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def registry():
+    import jtokkit_b200 as jt
+    return jt.Encodings.new_lazy_encoding_registry()
+
+
+def test_registry_lookups(registry, gpu_encodings):
+    """BaseEncodingRegistryTest.java:34-96: by type, name, model type, model name and the gpt-4 / gpt-3.5-turbo prefix rules."""
+    import jtokkit_b200 as jt
+    for t in jt.EncodingType:
+        enc = registry.get_encoding(t)
+        assert enc.get_name() == t.get_name()
+        assert registry.get_encoding(t.get_name()) is enc
+    for m in jt.ModelType:
+        assert registry.get_encoding_for_model(m).get_name() == m.get_encoding_type().get_name()
+        assert registry.get_encoding_for_model(m.get_name()).get_name() == m.get_encoding_type().get_name()
+    for name, expect in [("gpt-4-32k-0314", "cl100k_base"), ("gpt-4-0314", "cl100k_base"), ("gpt-3.5-turbo-0301", "cl100k_base"),
+                         ("gpt-3.5-turbo-16k-0613", "cl100k_base")]:
+        assert registry.get_encoding_for_model(name).get_name() == expect
+    assert registry.get_encoding("unknown") is None and registry.get_encoding_for_model("unknown-model") is None  # :136-141
+
+
+def test_registry_registration(registry):
+    """:98-134: custom encodings, registerGptBytePairEncoding with the predefined patterns, duplicates -> IllegalStateException."""
+    import jtokkit_b200 as jt
+
+    class DummyEncoding:
+        def get_name(self):
+            return "dummy"
+
+    registry.register_custom_encoding(DummyEncoding())
+    assert registry.get_encoding("dummy").get_name() == "dummy"
+    with pytest.raises(RuntimeError):
+        registry.register_custom_encoding(DummyEncoding())
+    p = jt.EncodingFactory.predefined_params(jt.EncodingType.R50K_BASE)
+    p.name = "my_r50k"
+    registry.register_gpt_byte_pair_encoding(p)
+    assert registry.get_encoding("my_r50k").encode("hello world") == registry.get_encoding(jt.EncodingType.R50K_BASE).encode("hello world")
+    with pytest.raises(RuntimeError):
+        registry.register_gpt_byte_pair_encoding(p)
+    # empty maps are legal registration input (BaseEncodingRegistryTest.java:110-125 registers two empty maps)
+    empty = jt.GptBytePairEncodingParams("empty_maps", jt.EncodingFactory.predefined_params(jt.EncodingType.CL100K_BASE).get_pattern(), {}, {})
+    registry.register_gpt_byte_pair_encoding(empty)
+    with pytest.raises(ValueError):  # every byte is unknown: IllegalArgumentException from TokenEncoder.encode
+        registry.get_encoding("empty_maps").encode("a")
+    assert registry.get_encoding("empty_maps").encode("") == []
+    # an arbitrary pattern is outside the device pattern compiler: registration fails, nothing falls back to the CPU
+    with pytest.raises(ValueError):
+        registry.register_gpt_byte_pair_encoding(jt.GptBytePairEncodingParams("test", jt.Pattern.compile("test"), {}, {}))
+
+
+def test_default_registry_is_eager():
+    import jtokkit_b200 as jt
+    reg = jt.Encodings.new_default_encoding_registry()
+    assert sorted(reg._encodings) == sorted(ENCODING_NAMES)  # DefaultEncodingRegistry.java:16-20
+    lazy = jt.Encodings.new_lazy_encoding_registry()
+    assert lazy._encodings == {}                             # LazyEncodingRegistryTest.java:17-23
+    assert lazy.get_encoding_for_model("gpt-4").get_name() == "cl100k_base" and list(lazy._encodings) == ["cl100k_base"]
+
+
+@pytest.mark.parametrize("name", ENCODING_NAMES)
+def test_golden_roundtrip_and_counts(name, gpu_encodings):
+    """<Enc>Test.java:31-37 (decode(encode(x)) == x) as batches; countTokens == encode(x).size() (GptBytePairEncoding.java:121-129)."""
+    enc = gpu_encodings[name]
+    rows = load_golden(name)
+    texts = [r[0] for r in rows]
+    res = enc.encode_batch(texts)
+    back = enc.decode_bytes_batch(res.to_lists())
+    assert [b.decode("utf-8") for b in back] == texts
+    counts = enc.count_tokens_batch(texts)
+    assert counts.tolist() == [len(r[1]) for r in rows]
+    assert enc.count_tokens_ordinary(texts[5]) == len(rows[5][1])
+
+
+def test_special_token_guard_per_document(gpu_encodings):
+    """encodeInternal :52-56 - one bad document does not poison the batch; p50k_edit guards four strings, r50k one."""
+    from jtokkit_b200 import _capi
+    docs = ["plain", "has <|endoftext|> inside", "<|fim_prefix|>", "almost <|endoftext| >", "", "<|endofprompt|>", "tail <|endoftext|>"]
+    expect = {"cl100k_base": [0, 1, 1, 0, 0, 1, 1], "p50k_edit": [0, 1, 1, 0, 0, 0, 1], "r50k_base": [0, 1, 0, 0, 0, 0, 1]}
+    for name, exp in expect.items():
+        res = gpu_encodings[name].encode_batch(docs)
+        assert [int(bool(s & _capi.DOC_HAS_SPECIAL)) for s in res.doc_status] == exp, name
+        ordinary = gpu_encodings[name].encode_ordinary_batch(docs)
+        assert not ordinary.doc_status.any()
+        assert ordinary.to_lists() == res.to_lists()  # the guard only flags; ids are the encodeOrdinary ids
+    with pytest.raises(NotImplementedError):
+        gpu_encodings["cl100k_base"].count_tokens("x <|fim_suffix|>")
+
+
+def test_custom_vocabulary_unknown_bytes_and_duplicates(oracles):
+    """A vocabulary without all single bytes: parts that are not tokens raise IllegalArgumentException (TokenEncoder.java:64-71);
+    pairs still merge through byte parts that are not tokens themselves."""
+    import jtokkit_b200 as jt
+    from oracle import jo
+    pat = jt.EncodingFactory.predefined_params(jt.EncodingType.CL100K_BASE).get_pattern()
+    vocab = {b"a": 5, b"b": 7, b"ab": 3, b"abc": 1, b" ": 9, b" a": 2, b"xy": 11, b"xyz": 4, b"-5": -5}
+    enc = jt.Encoding(jt.GptBytePairEncodingParams("tiny", pat, vocab, {"<s>": 100}))
+    orc = jo.OracleEncoding("tiny", pat.pattern(), pat.flags(), vocab, {"<s>": 100})
+    for text in ["ab", "abab a", "abc", "aab", " a ab", "xy", "xyz", "xyzxy"]:
+        assert enc.encode(text) == orc.encode(text), text
+    for text in ["abd", "q", "x"]:
+        with pytest.raises(ValueError):
+            enc.encode(text)
+        with pytest.raises(ValueError):
+            orc.encode(text)
+    assert enc.decode([3, 100, 1]) == "ab<s>abc"  # special tokens decode to their string (GptBytePairEncoding.java:307-310)
+    with pytest.raises(NotImplementedError):
+        enc.encode("a<s>")
+
+
+def test_ragged_and_empty_batches(gpu_encodings, oracles):
+    enc, orc = gpu_encodings["cl100k_base"], oracles["cl100k_base"]
+    assert enc.encode_batch([]).to_lists() == []
+    assert enc.encode_batch(["", "", ""]).to_lists() == [[], [], []]
+    docs = ["", "a", "", "", "hello world " * 800, "", "x"]
+    res = enc.encode_batch(docs)
+    assert res.to_lists() == [orc.encode(d) for d in docs]
+    assert res.token_offsets[0] == 0 and res.token_offsets[-1] == res.ids.size
+    # documents that end exactly on tile boundaries (8 KiB) and a batch that ends on one
+    docs = ["a" * 8192, "b c " * 2048, "", "d" * 8191, "e"]
+    assert enc.encode_batch(docs).to_lists() == [orc.encode(d) for d in docs]
+    docs = ["wor d" * 1638 + "xy"]
+    assert len(docs[0]) == 8192 and enc.encode_batch(docs).to_lists() == [orc.encode(docs[0])]
+
+
+def test_max_tokens_variants_match_oracle(gpu_encodings, oracles):
+    """encode(text, maxTokens) incl. the back-off loop (:90-100): multi-byte characters split across tokens, limits <= 0."""
+    enc, orc = gpu_encodings["cl100k_base"], oracles["cl100k_base"]
+    texts = ["I love \U0001F355\U0001F355 pizza", "日本語のテキストです", "नमस्ते दुनिया", "a", "", "x" * 50, "�� mixed �"]
+    for t in texts:
+        for m in [-1, 0, 1, 2, 3, 5, 8, 1000]:
+            r = enc.encode(t, m)
+            assert (r.get_tokens(), r.is_truncated()) == orc.encode_max(t, m), (t, m)
+            ro = enc.encode_ordinary(t, m)
+            assert (ro.get_tokens(), ro.is_truncated()) == orc.encode_max(t, m, ordinary=True)
+    r = enc.encode(None, 5)
+    assert r.get_tokens() == [] and not r.is_truncated()

@@ -1,0 +1,144 @@
+"""The oracle (oracle/) against the reference's own golden vectors and against independent implementations.
+
+This is what pins the oracle: tests/golden/*_encodings.csv are the reference's fixtures
+(lib/src/test/resources, asserted by lib/src/test/java/com/knuddels/jtokkit/reference/*Test.java:19-111)."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from conftest import ENCODING_NAMES, load_golden
+
+
+@pytest.mark.parametrize("name", ENCODING_NAMES)
+def test_golden_rows(name, oracles):
+    """encode == column 2, encode(x, 10) == column 3 + truncated flag, decode(encode(x)) == x, encodeOrdinary likewise."""
+    from oracle import jo
+    o = oracles[name]
+    rows = load_golden(name)
+    assert len(rows) == 423
+    for inp, full, ten in rows:
+        assert o.encode(inp, jo.MERGE_LITERAL) == full
+        assert o.encode_ordinary(inp, jo.MERGE_HEAP) == full
+        got10, trunc = o.encode_max(inp, 10)
+        assert got10 == ten and trunc == (len(full) > len(ten))
+        got10o, trunco = o.encode_max(inp, 10, ordinary=True)
+        assert got10o == ten and trunco == trunc
+        assert o.decode_bytes(full).decode("utf-8") == inp
+        assert inp.startswith(o.decode_bytes(got10).decode("utf-8"))
+
+
+def test_documented_known_answers(oracles):
+    o = oracles["cl100k_base"]
+    assert o.encode("This is a sample sentence.") == [2028, 374, 264, 6205, 11914, 13]  # README.md:83-84
+    assert o.encode("hello world") == [15339, 1917]  # api/Encoding.java:18-19
+    assert o.encode_ordinary("hello <|endoftext|> world") == [15339, 83739, 8862, 728, 428, 91, 29, 1917]  # :73-74
+    with pytest.raises(NotImplementedError):
+        o.encode("hello <|endoftext|> world")
+    assert o.encode_max("I love \U0001F355", 4) == ([40, 3021], True)  # usage.md:96-97
+    assert o.encode_max("This is a sample sentence.", 3) == ([2028, 374, 264], True)  # usage.md:90-91
+    assert o.decode_bytes([15339, 1917]) == b"hello world"  # api/Encoding.java:170-171
+    with pytest.raises(ValueError):
+        o.decode_bytes([15339, 100261])
+    assert o.encode_max("abc", 0) == ([], True) and o.encode_max("", 5) == ([], False) and o.encode_max("abc", -3) == ([], True)
+    for special in ["<|endoftext|>", "<|fim_prefix|>", "<|endofprompt|>"]:  # <Enc>Test.java:105-111
+        assert o.decode_bytes(o.encode_ordinary(special)).decode() == special
+
+
+@pytest.mark.parametrize("name", ["cl100k_base", "r50k_base"])
+def test_heap_merge_equals_literal_loop(name, oracles):
+    """The sub-quadratic merge used for long pieces is the same function as the reference's O(n^2) loop."""
+    from oracle import jo
+    o = oracles[name]
+    rng = random.Random(4)
+    vocab = [k for k in list(o.ranks.keys())[:20000] if k]
+    for _ in range(1500):
+        mode = rng.random()
+        if mode < 0.3:
+            piece = bytes(rng.choice(b"abcdefghijklmnopqrstuvwxyz") for _ in range(rng.randint(1, 120)))
+        elif mode < 0.6:
+            piece = b"".join(rng.choice(vocab) for _ in range(rng.randint(1, 30)))
+        elif mode < 0.8:
+            piece = bytes(rng.randrange(256) for _ in range(rng.randint(1, 80)))
+        else:
+            piece = rng.choice([b"a", b"ab", b" ", b"\n", b"!", b"abc"]) * rng.randint(1, 200)
+        assert o.merge_piece(piece, jo.MERGE_HEAP) == o.merge_piece(piece, jo.MERGE_LITERAL), piece
+
+
+ALPH = list("abcdefghijklmnopqrstuvwxyzSTREVMLD   \n\r\t'''!!?.,;:-0123456789") + [
+    "é", "ß", "ſ", "Ж", "я", "中", "文", "あ", "カ", " ", "　", " ", "١", "٢", "½", "🍕", "‍", "️", "्", "ा", "ก", "ั", "한", "😀", "ñ", "—", "“"]
+
+
+@pytest.mark.parametrize("name", ["cl100k_base", "r50k_base"])
+def test_differential_vs_tiktoken_and_regex(name, oracles):
+    """Second opinions: tiktoken (the upstream JTokkit mirrors, benchmark/bench.py:16-28) built from the same vocabulary file and
+    the reference's regex string, and the `regex` module for the split alone.  Code points are limited to old, stable ones."""
+    tiktoken = pytest.importorskip("tiktoken")
+    regex = pytest.importorskip("regex")
+    from tiktoken.load import load_tiktoken_bpe
+    from oracle import jo
+    pat, fname, _ = jo.BUILTIN[name]
+    tk = tiktoken.Encoding(name, pat_str=pat, mergeable_ranks=load_tiktoken_bpe(os.path.join(jo.DATA, fname)), special_tokens={})
+    rx = regex.compile(pat)
+    o = oracles[name]
+    rng = random.Random(1)
+    for _ in range(6000):
+        s = "".join(rng.choice(ALPH) for _ in range(rng.randint(0, 40)))
+        assert o.encode_ordinary(s, jo.MERGE_LITERAL) == tk.encode_ordinary(s), s
+        cum = [0]
+        for ch in s:
+            cum.append(cum[-1] + len(ch.encode()))
+        assert o.split(s) == [(cum[m.start()], cum[m.end()]) for m in rx.finditer(s)], s
+
+
+def test_custom_patterns_follow_java_regex_semantics(oracles):
+    """registerGptBytePairEncoding accepts arbitrary patterns (BaseEncodingRegistryTest.java:110-125): the oracle's matcher
+    skips unmatched characters, advances past empty matches and honours ordered alternation."""
+    from oracle import jo
+    o = jo.OracleEncoding("t", "test", 0, {}, {})
+    assert o.split("a test of tests") == [(2, 6), (10, 14)]
+    assert o.encode_ordinary("no match here") == []
+    o2 = jo.OracleEncoding("t2", "a|ab|b*", 0, {b"a": 0, b"b": 1, b"ab": 2}, {})
+    assert o2.split("abb") == [(0, 1), (1, 3), (3, 3)]
+    assert o2.encode_ordinary("abb") == [0, 1, 1]
+    o3 = jo.OracleEncoding("t3", r"(?i:x+)(?!y)|\s+", 0, {}, {})
+    assert o3.split("XXy xx") == [(0, 1), (3, 4), (4, 6)]
+    with pytest.raises(ValueError):
+        jo.OracleEncoding("bad", r"(?<=a)b", 0, {}, {})
+
+
+def test_batch_thread_pool_matches_single_calls(oracles):
+    o = oracles["cl100k_base"]
+    docs = ["hello world", "", "I love \U0001F355", "x" * 700, "a <|endoftext|> b", "tabs\tand\nnewlines\r\n  indented"]
+    blobs = [d.encode() for d in docs]
+    off = np.zeros(len(docs) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(b) for b in blobs])
+    ids, tok_off, counts = o.encode_batch_compact(np.frombuffer(b"".join(blobs), dtype=np.uint8), off, 4, check_special=True)
+    for d, s in enumerate(docs):
+        if "<|endoftext|>" in s:
+            assert counts[d] == -1
+        else:
+            assert ids[tok_off[d]:tok_off[d + 1]].tolist() == o.encode(s)
+
+
+def test_java_utf16_decoding_of_truncated_sequences():
+    """new String(bytes, UTF_8): a truncated trailing sequence is ONE U+FFFD (what the back-off loop compares)."""
+    import ctypes as C
+    from oracle import jo
+    lib = jo.lib()
+    lib.jo_java_utf8_to_utf16.restype = C.c_int64
+    lib.jo_java_utf8_to_utf16.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+
+    def dec(b):
+        src = np.frombuffer(b, dtype=np.uint8)
+        out = np.zeros(len(b) + 1, dtype=np.uint16)
+        n = lib.jo_java_utf8_to_utf16(src.ctypes.data_as(C.c_void_p), len(b), out.ctypes.data_as(C.c_void_p))
+        return out[:n].tolist()
+
+    assert dec("aé".encode()) == [0x61, 0xE9]
+    assert dec(b"a\xe2\x82") == [0x61, 0xFFFD]          # truncated 3-byte sequence
+    assert dec(b"a\xf0\x9f\x8d") == [0x61, 0xFFFD]      # truncated 4-byte sequence
+    assert dec("🍕".encode()) == [0xD83C, 0xDF55]       # surrogate pair
+    assert dec(b"\x80a") == [0xFFFD, 0x61]              # stray continuation byte
+    assert dec(b"\xe2\x28\xa1") == [0xFFFD, 0x28, 0xFFFD]

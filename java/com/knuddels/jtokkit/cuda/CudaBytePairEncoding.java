@@ -1,0 +1,259 @@
+package com.knuddels.jtokkit.cuda;
+
+import com.knuddels.jtokkit.api.Encoding;
+import com.knuddels.jtokkit.api.EncodingResult;
+import com.knuddels.jtokkit.api.GptBytePairEncodingParams;
+
+import java.lang.foreign.Arena;
+import java.lang.foreign.MemoryLayout;
+import java.lang.foreign.MemorySegment;
+import java.lang.foreign.StructLayout;
+import java.nio.charset.StandardCharsets;
+import java.util.ArrayList;
+import java.util.Collections;
+import java.util.List;
+import java.util.Map;
+
+import static java.lang.foreign.ValueLayout.ADDRESS;
+import static java.lang.foreign.ValueLayout.JAVA_BYTE;
+import static java.lang.foreign.ValueLayout.JAVA_INT;
+import static java.lang.foreign.ValueLayout.JAVA_LONG;
+
+/**
+ * Drop-in replacement for com.knuddels.jtokkit.GptBytePairEncoding (same Encoding contract, same exceptions) that forwards to
+ * libjtokkit_b200.so.  NOT COMPILED HERE (no JDK in the image).  EncodingFactory.fromParameters (EncodingFactory.java:117-119)
+ * becomes {@code return new CudaBytePairEncoding(parameters);}.
+ */
+public final class CudaBytePairEncoding implements Encoding, AutoCloseable {
+	private static final StructLayout PARAMS = MemoryLayout.structLayout(
+			ADDRESS.withName("name"), ADDRESS.withName("pattern"), JAVA_INT.withName("pattern_flags"), MemoryLayout.paddingLayout(4),
+			ADDRESS.withName("vocab_bytes"), ADDRESS.withName("vocab_off"), ADDRESS.withName("vocab_ranks"), JAVA_LONG.withName("vocab_size"),
+			ADDRESS.withName("special_bytes"), ADDRESS.withName("special_off"), ADDRESS.withName("special_ids"), JAVA_LONG.withName("special_size"));
+
+	private final String name;
+	private final MemorySegment handle;
+
+	public CudaBytePairEncoding(final GptBytePairEncodingParams params) {
+		this.name = params.getName();
+		try (Arena arena = Arena.ofConfined()) {
+			final MemorySegment p = arena.allocate(PARAMS);
+			p.set(ADDRESS, 0, arena.allocateFrom(params.getName()));
+			p.set(ADDRESS, 8, arena.allocateFrom(params.getPattern().pattern()));
+			p.set(JAVA_INT, 16, params.getPattern().flags());
+			// Map<byte[], Integer> -> (bytes, offsets, ranks)
+			final Map<byte[], Integer> enc = params.getEncoder();
+			long total = 0;
+			for (final byte[] k : enc.keySet()) total += k.length;
+			final MemorySegment vb = arena.allocate(Math.max(total, 1)), vo = arena.allocate(JAVA_LONG, enc.size() + 1L), vr = arena.allocate(JAVA_INT, Math.max(enc.size(), 1));
+			long pos = 0;
+			int i = 0;
+			for (final Map.Entry<byte[], Integer> e : enc.entrySet()) {
+				vo.setAtIndex(JAVA_LONG, i, pos);
+				MemorySegment.copy(e.getKey(), 0, vb, JAVA_BYTE, pos, e.getKey().length);
+				vr.setAtIndex(JAVA_INT, i, e.getValue());
+				pos += e.getKey().length;
+				i++;
+			}
+			vo.setAtIndex(JAVA_LONG, i, pos);
+			p.set(ADDRESS, 24, vb);
+			p.set(ADDRESS, 32, vo);
+			p.set(ADDRESS, 40, vr);
+			p.set(JAVA_LONG, 48, enc.size());
+			// Map<String, Integer> special tokens -> UTF-8 (bytes, offsets, ids)
+			final Map<String, Integer> sp = params.getSpecialTokensEncoder();
+			final List<byte[]> sk = new ArrayList<>();
+			long stotal = 0;
+			for (final String k : sp.keySet()) {
+				final byte[] b = k.getBytes(StandardCharsets.UTF_8);
+				sk.add(b);
+				stotal += b.length;
+			}
+			final MemorySegment sb = arena.allocate(Math.max(stotal, 1)), so = arena.allocate(JAVA_LONG, sp.size() + 1L), si = arena.allocate(JAVA_INT, Math.max(sp.size(), 1));
+			pos = 0;
+			i = 0;
+			for (final Map.Entry<String, Integer> e : sp.entrySet()) {
+				so.setAtIndex(JAVA_LONG, i, pos);
+				MemorySegment.copy(sk.get(i), 0, sb, JAVA_BYTE, pos, sk.get(i).length);
+				si.setAtIndex(JAVA_INT, i, e.getValue());
+				pos += sk.get(i).length;
+				i++;
+			}
+			so.setAtIndex(JAVA_LONG, i, pos);
+			p.set(ADDRESS, 56, sb);
+			p.set(ADDRESS, 64, so);
+			p.set(ADDRESS, 72, si);
+			p.set(JAVA_LONG, 80, sp.size());
+			final MemorySegment out = arena.allocate(ADDRESS);
+			final int rc = (int) JtkNative.ENCODING_CREATE.invokeExact(p, MemorySegment.NULL, 0, out);
+			if (rc == JtkNative.JTK_E_PATTERN_UNSUPPORTED) throw new IllegalArgumentException("split pattern not supported on the device: " + JtkNative.lastError());
+			if (rc != JtkNative.JTK_OK) throw new IllegalStateException(JtkNative.lastError());
+			this.handle = out.get(ADDRESS, 0);
+		} catch (final RuntimeException e) {
+			throw e;
+		} catch (final Throwable t) {
+			throw new IllegalStateException(t);
+		}
+	}
+
+	/** The new batch entry point: primitive arrays, no boxing. ids of document d are ids[offsets[d] .. offsets[d+1]). */
+	public static final class Batch {
+		public final int[] ids;
+		public final long[] tokenOffsets;
+		public final int[] docStatus;
+
+		Batch(final int[] ids, final long[] tokenOffsets, final int[] docStatus) {
+			this.ids = ids;
+			this.tokenOffsets = tokenOffsets;
+			this.docStatus = docStatus;
+		}
+	}
+
+	public Batch encodeBatch(final List<String> texts, final boolean ordinary, final boolean countOnly) {
+		try (Arena arena = Arena.ofConfined()) {
+			// String.getBytes(UTF_8), exactly as ImmutableByteArray.from (ImmutableByteArray.java:16-19): lone surrogates become '?'.
+			// Never GetStringUTFChars / modified UTF-8.
+			final byte[][] utf8 = new byte[texts.size()][];
+			long total = 0;
+			for (int d = 0; d < utf8.length; d++) {
+				utf8[d] = texts.get(d) == null ? new byte[0] : texts.get(d).getBytes(StandardCharsets.UTF_8);
+				total += utf8[d].length;
+			}
+			final MemorySegment bytes = arena.allocate(Math.max(total, 1), 16), off = arena.allocate(JAVA_LONG, utf8.length + 1L);
+			long pos = 0;
+			for (int d = 0; d < utf8.length; d++) {
+				off.setAtIndex(JAVA_LONG, d, pos);
+				MemorySegment.copy(utf8[d], 0, bytes, JAVA_BYTE, pos, utf8[d].length);
+				pos += utf8[d].length;
+			}
+			off.setAtIndex(JAVA_LONG, utf8.length, pos);
+			final MemorySegment out = arena.allocate(ADDRESS);
+			final int flags = (ordinary ? 0 : JtkNative.CHECK_SPECIAL) | (countOnly ? JtkNative.COUNT_ONLY : 0);
+			final int rc = (int) JtkNative.ENCODE_BATCH.invokeExact(handle, bytes, off, (long) utf8.length, flags, out);
+			if (rc != JtkNative.JTK_OK) throw new IllegalStateException(JtkNative.lastError());
+			final MemorySegment r = out.get(ADDRESS, 0);
+			try {
+				final long n = (long) JtkNative.RESULT_NUM_TOKENS.invokeExact(r);
+				final int[] ids = countOnly ? new int[0] : ((MemorySegment) JtkNative.RESULT_IDS.invokeExact(r)).reinterpret(4 * n).toArray(JAVA_INT);
+				final long[] tok = ((MemorySegment) JtkNative.RESULT_TOKEN_OFFSETS.invokeExact(r)).reinterpret(8L * (utf8.length + 1)).toArray(JAVA_LONG);
+				final int[] st = ((MemorySegment) JtkNative.RESULT_DOC_STATUS.invokeExact(r)).reinterpret(4L * utf8.length).toArray(JAVA_INT);
+				return new Batch(ids, tok, st);
+			} finally {
+				JtkNative.RESULT_FREE.invokeExact(r);
+			}
+		} catch (final RuntimeException e) {
+			throw e;
+		} catch (final Throwable t) {
+			throw new IllegalStateException(t);
+		}
+	}
+
+	private static void raise(final int status) {
+		// the reference's exception types and messages (GptBytePairEncoding.java:54, TokenEncoder.java:67)
+		if ((status & JtkNative.DOC_HAS_SPECIAL) != 0) throw new UnsupportedOperationException("Encoding special tokens is not supported yet.");
+		if ((status & JtkNative.DOC_UNKNOWN_BYTES) != 0) throw new IllegalArgumentException("Unknown token for encoding");
+	}
+
+	private List<Integer> encodeOne(final String text, final boolean ordinary) {
+		if (text == null) return Collections.emptyList(); // GptBytePairEncoding.java:48-50,72-74
+		final Batch b = encodeBatch(Collections.singletonList(text), ordinary, false);
+		raise(b.docStatus[0]);
+		final List<Integer> out = new ArrayList<>(b.ids.length);
+		for (final int id : b.ids) out.add(id);
+		return out;
+	}
+
+	@Override
+	public List<Integer> encode(final String text) {
+		return encodeOne(text, false);
+	}
+
+	@Override
+	public List<Integer> encodeOrdinary(final String text) {
+		return encodeOne(text, true);
+	}
+
+	/** encode(text, maxTokens): full device encode, clip, then the reference's back-off loop verbatim (:90-100) with the JVM's own decoder. */
+	private EncodingResult encodeMax(final String text, final int maxTokens, final boolean ordinary) {
+		if (text == null) return new EncodingResult(Collections.emptyList(), false);
+		final List<Integer> all = encodeOne(text, ordinary);
+		final List<Integer> out = all.subList(0, Math.max(0, Math.min(maxTokens, all.size())));
+		for (int tokensToRemove = 0; tokensToRemove <= out.size(); tokensToRemove++) {
+			final List<Integer> tokens = out.subList(0, out.size() - tokensToRemove);
+			final String decoded = decode(tokens);
+			if (text.startsWith(decoded)) return new EncodingResult(tokens, text.length() > decoded.length());
+		}
+		return new EncodingResult(out, false);
+	}
+
+	@Override
+	public EncodingResult encode(final String text, final int maxTokens) {
+		return encodeMax(text, maxTokens, false);
+	}
+
+	@Override
+	public EncodingResult encodeOrdinary(final String text, final int maxTokens) {
+		return encodeMax(text, maxTokens, true);
+	}
+
+	@Override
+	public int countTokens(final String text) {
+		if (text == null) return 0;
+		final Batch b = encodeBatch(Collections.singletonList(text), false, true);
+		raise(b.docStatus[0]);
+		return (int) b.tokenOffsets[1];
+	}
+
+	@Override
+	public int countTokensOrdinary(final String text) {
+		if (text == null) return 0;
+		return (int) encodeBatch(Collections.singletonList(text), true, true).tokenOffsets[1];
+	}
+
+	@Override
+	public byte[] decodeBytes(final List<Integer> tokens) {
+		try (Arena arena = Arena.ofConfined()) {
+			final MemorySegment ids = arena.allocate(JAVA_INT, Math.max(tokens.size(), 1)), off = arena.allocate(JAVA_LONG, 2);
+			for (int i = 0; i < tokens.size(); i++) ids.setAtIndex(JAVA_INT, i, tokens.get(i));
+			off.setAtIndex(JAVA_LONG, 0, 0L);
+			off.setAtIndex(JAVA_LONG, 1, tokens.size());
+			final MemorySegment out = arena.allocate(ADDRESS);
+			final int rc = (int) JtkNative.DECODE_BATCH.invokeExact(handle, ids, off, 1L, out);
+			if (rc != JtkNative.JTK_OK) throw new IllegalStateException(JtkNative.lastError());
+			final MemorySegment r = out.get(ADDRESS, 0);
+			try {
+				final int st = ((MemorySegment) JtkNative.RESULT_DOC_STATUS.invokeExact(r)).reinterpret(4).get(JAVA_INT, 0);
+				if ((st & JtkNative.DOC_UNKNOWN_ID) != 0) {
+					final int bad = ((MemorySegment) JtkNative.RESULT_BAD_IDS.invokeExact(r)).reinterpret(4).get(JAVA_INT, 0);
+					throw new IllegalArgumentException("Unknown token for decoding: " + bad); // GptBytePairEncoding.java:313
+				}
+				final long n = ((MemorySegment) JtkNative.RESULT_BYTE_OFFSETS.invokeExact(r)).reinterpret(16).getAtIndex(JAVA_LONG, 1);
+				return ((MemorySegment) JtkNative.RESULT_BYTES.invokeExact(r)).reinterpret(n).toArray(JAVA_BYTE);
+			} finally {
+				JtkNative.RESULT_FREE.invokeExact(r);
+			}
+		} catch (final RuntimeException e) {
+			throw e;
+		} catch (final Throwable t) {
+			throw new IllegalStateException(t);
+		}
+	}
+
+	@Override
+	public String decode(final List<Integer> tokens) {
+		return new String(decodeBytes(tokens), StandardCharsets.UTF_8); // keeps the JVM's U+FFFD behaviour (:131-134)
+	}
+
+	@Override
+	public String getName() {
+		return name;
+	}
+
+	@Override
+	public void close() {
+		try {
+			JtkNative.ENCODING_DESTROY.invokeExact(handle);
+		} catch (final Throwable t) {
+			throw new IllegalStateException(t);
+		}
+	}
+}

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libjtokkit_b200.so")
+LIB_PATH = os.environ.get("JTK_LIB", os.path.join(HERE, "libjtokkit_b200.so"))  # JTK_LIB: development override for A/B builds
 
 JTK_OK, JTK_E_ARG, JTK_E_CUDA, JTK_E_PATTERN_UNSUPPORTED, JTK_E_NOMEM, JTK_E_CAPACITY = 0, -1, -2, -3, -4, -5
 DOC_OK, DOC_HAS_SPECIAL, DOC_UNKNOWN_BYTES, DOC_UNKNOWN_ID = 0, 1, 2, 4

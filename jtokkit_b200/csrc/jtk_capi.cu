@@ -145,7 +145,7 @@ static int init_device(jtk_encoding *e, int device) {
 	ds->allocs.push_back(base);
 	for (size_t i = 0; i < ar.parts.size(); i++)
 		if (ar.parts[i].second) CUDA_TRY(cudaMemcpy(base + ar.offsets[i], ar.parts[i].first, ar.parts[i].second, cudaMemcpyHostToDevice));
-	T.tab_a = reinterpret_cast<const jtk_slot *>(base + o_tab_a);
+	T.tab_a = reinterpret_cast<const jtk_slot_a *>(base + o_tab_a);
 	T.pair = reinterpret_cast<const jtk_slot *>(base + o_pair);
 	T.bytepair = reinterpret_cast<const int32_t *>(base + o_bytepair);
 	T.byte_id = reinterpret_cast<const int32_t *>(base + o_byte_id);

@@ -54,7 +54,7 @@ enum {
 
 #define JTK_RANK_MAX 0x7fffffff                  /* Integer.MAX_VALUE sentinel, GptBytePairEncoding.java:208 */
 #define JTK_PSEUDO_BASE ((int32_t) 0x80000000)   /* id of a single byte that is not in the vocabulary: PSEUDO_BASE + byte */
-#define JTK_INLINE_KEY_MAX 11                    /* piece table A stores keys of up to 11 bytes inline */
+#define JTK_INLINE_KEY_MAX 24                    /* piece table A stores keys of up to 24 bytes inline */
 
 /* ---- tile geometry (overridable so that the host-side emulator in tests/ can use tiny tiles) ---------- */
 #ifndef JTK_TILE
@@ -76,6 +76,12 @@ enum {
 struct jtk_slot {
 	uint32_t x, y, z, w;
 };
+/* 32-byte slot of piece table A: 24 key bytes (zero padded), key length, rank; one slot per 32-byte sector */
+struct alignas(16) jtk_slot_a {
+	uint32_t k[6];
+	uint32_t len; /* 0 = empty */
+	uint32_t rank;
+};
 
 /* Device tables of one encoding on one device (all pointers are device memory). */
 struct jtk_tables {
@@ -85,10 +91,10 @@ struct jtk_tables {
 	const uint8_t *ascii_cls;   /* 128 */
 	const uint16_t *cp_stage1;  /* 0x1100 */
 	const uint8_t *cp_stage2;   /* nblocks * 256 */
-	/* whole-piece lookup (GptBytePairEncoding.java:81-83), keys <= 11 bytes: slot = {b0-3, b4-7, b8-10 | len << 24, rank} */
-	const jtk_slot *tab_a;
-	uint32_t mask_a;            /* bucket count - 1; a bucket is two consecutive slots (32 B) */
-	/* whole-piece lookup, keys of 12..max_token_len bytes: slot = {hash lo, hash hi, rank, token index}, verified against tok_bytes */
+	/* whole-piece lookup (GptBytePairEncoding.java:81-83), keys <= 24 bytes inline */
+	const jtk_slot_a *tab_a;
+	uint32_t mask_a;            /* slot count - 1 (linear probing) */
+	/* whole-piece lookup, keys of 25..max_token_len bytes: slot = {hash lo, hash hi, rank, token index}, verified against tok_bytes */
 	const jtk_slot *tab_b;
 	uint32_t mask_b;
 	const uint8_t *tok_bytes;   /* concatenated token bytes, by token index */
@@ -117,6 +123,22 @@ JTK_HD uint32_t jtk_hash3(uint32_t a, uint32_t b, uint32_t c) {
 	uint32_t h = a * 0x9E3779B1u;
 	h ^= (b + 0x7F4A7C15u) * 0x85EBCA77u;
 	h ^= (c + 0x165667B1u) * 0xC2B2AE3Du;
+	h ^= h >> 15;
+	h *= 0x2C1B3C6Du;
+	h ^= h >> 13;
+	return h;
+}
+
+/* hash of an inline key (six words; unused words are zero) */
+JTK_HD uint32_t jtk_hash6(const uint32_t *k, uint32_t len) {
+	uint32_t h = (k[0] + len) * 0x9E3779B1u;
+	h ^= (k[1] + 0x7F4A7C15u) * 0x85EBCA77u;
+	h = (h << 13) | (h >> 19);
+	h ^= (k[2] + 0x165667B1u) * 0xC2B2AE3Du;
+	h ^= (k[3] + 0x27D4EB2Fu) * 0x9E3779B1u;
+	h = (h << 11) | (h >> 21);
+	h ^= (k[4] + 0x85EBCA6Bu) * 0x85EBCA77u;
+	h ^= (k[5] + 0xC2B2AE35u) * 0xC2B2AE3Du;
 	h ^= h >> 15;
 	h *= 0x2C1B3C6Du;
 	h ^= h >> 13;

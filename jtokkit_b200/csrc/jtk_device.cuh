@@ -141,24 +141,26 @@ struct jtk_region_start {
 	JTK_HD bool operator()(int64_t r) const { return jtk_docstart(*c, (int) r); }
 };
 
-/* Classifies the 16 bytes of chunk `chunk` (region indices 16*chunk ..) into c.cls. */
-JTK_HD void jtk_classify_chunk(jtk_tile_ctx &c, int chunk) {
+/* Fast classification of chunk `chunk`: sixteen ASCII bytes are sixteen table reads (a character cannot straddle into an
+ * ASCII chunk).  Returns false when the chunk holds a non-ASCII byte. */
+JTK_HD bool jtk_classify_fast(jtk_tile_ctx &c, int chunk) {
+	const int r0 = chunk * 16;
+	const uint32_t *w = reinterpret_cast<const uint32_t *>(c.sb + r0);
+	const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+	if (((w0 | w1 | w2 | w3) & 0x80808080u) != 0) return false;
+	uint32_t *o = reinterpret_cast<uint32_t *>(c.cls + r0);
+	const uint8_t *lut = c.ascii_lut;
+	o[0] = lut[w0 & 0xFF] | (lut[(w0 >> 8) & 0xFF] << 8) | (lut[(w0 >> 16) & 0xFF] << 16) | ((uint32_t) lut[w0 >> 24] << 24);
+	o[1] = lut[w1 & 0xFF] | (lut[(w1 >> 8) & 0xFF] << 8) | (lut[(w1 >> 16) & 0xFF] << 16) | ((uint32_t) lut[w1 >> 24] << 24);
+	o[2] = lut[w2 & 0xFF] | (lut[(w2 >> 8) & 0xFF] << 8) | (lut[(w2 >> 16) & 0xFF] << 16) | ((uint32_t) lut[w2 >> 24] << 24);
+	o[3] = lut[w3 & 0xFF] | (lut[(w3 >> 8) & 0xFF] << 8) | (lut[(w3 >> 16) & 0xFF] << 16) | ((uint32_t) lut[w3 >> 24] << 24);
+	return true;
+}
+
+/* General classification of the 16 bytes of chunk `chunk` (region indices 16*chunk ..) into c.cls: UTF-8 decoding. */
+JTK_HD void jtk_classify_generic(jtk_tile_ctx &c, int chunk) {
 	const jtk_tables &T = *c.T;
 	const int r0 = chunk * 16;
-	{
-		/* fast path: sixteen ASCII bytes are sixteen table reads (a character cannot straddle into an ASCII chunk) */
-		const uint32_t *w = reinterpret_cast<const uint32_t *>(c.sb + r0);
-		const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
-		if (((w0 | w1 | w2 | w3) & 0x80808080u) == 0) {
-			uint32_t *o = reinterpret_cast<uint32_t *>(c.cls + r0);
-			const uint8_t *lut = c.ascii_lut;
-			o[0] = lut[w0 & 0xFF] | (lut[(w0 >> 8) & 0xFF] << 8) | (lut[(w0 >> 16) & 0xFF] << 16) | ((uint32_t) lut[w0 >> 24] << 24);
-			o[1] = lut[w1 & 0xFF] | (lut[(w1 >> 8) & 0xFF] << 8) | (lut[(w1 >> 16) & 0xFF] << 16) | ((uint32_t) lut[w1 >> 24] << 24);
-			o[2] = lut[w2 & 0xFF] | (lut[(w2 >> 8) & 0xFF] << 8) | (lut[(w2 >> 16) & 0xFF] << 16) | ((uint32_t) lut[w2 >> 24] << 24);
-			o[3] = lut[w3 & 0xFF] | (lut[(w3 >> 8) & 0xFF] << 8) | (lut[(w3 >> 16) & 0xFF] << 16) | ((uint32_t) lut[w3 >> 24] << 24);
-			return;
-		}
-	}
 	jtk_region_start is_start{&c};
 	int cur = JTK_C_O, rem = 0;
 	/* a character may have started in the previous chunk */
@@ -197,6 +199,10 @@ JTK_HD void jtk_classify_chunk(jtk_tile_ctx &c, int chunk) {
 		}
 	}
 	for (int i = 0; i < 16; i++) c.cls[r0 + i] = out[i];
+}
+
+JTK_HD void jtk_classify_chunk(jtk_tile_ctx &c, int chunk) {
+	if (!jtk_classify_fast(c, chunk)) jtk_classify_generic(c, chunk);
 }
 
 /* ---------------------------------------------------------------------------------------------
@@ -540,11 +546,9 @@ JTK_HD bool jtk_boundary_fast(const jtk_tile_ctx &c, int chunk, uint32_t *out) {
 }
 
 /* Piece-start bits for the 16 positions of chunk `chunk`. */
-JTK_HD uint32_t jtk_boundary_chunk(const jtk_tile_ctx &c, int chunk) {
+JTK_HD uint32_t jtk_boundary_generic(const jtk_tile_ctx &c, int chunk) {
 	const int r0 = chunk * 16;
 	uint32_t bits = 0;
-	if (jtk_boundary_fast(c, chunk, &bits)) return bits;
-	bits = 0;
 	int nrun = -1;
 	for (int i = 0; i < 16; i++) {
 		const int r = r0 + i;
@@ -571,6 +575,12 @@ JTK_HD uint32_t jtk_boundary_chunk(const jtk_tile_ctx &c, int chunk) {
 	return bits;
 }
 
+JTK_HD uint32_t jtk_boundary_chunk(const jtk_tile_ctx &c, int chunk) {
+	uint32_t bits = 0;
+	if (jtk_boundary_fast(c, chunk, &bits)) return bits;
+	return jtk_boundary_generic(c, chunk);
+}
+
 /* ---------------------------------------------------------------------------------------------
  * special-token guard
  * ------------------------------------------------------------------------------------------- */
@@ -590,20 +600,18 @@ JTK_HD bool jtk_special_at(const jtk_tables &T, const uint8_t *gbytes, int64_t g
 /* ---------------------------------------------------------------------------------------------
  * table lookups
  * ------------------------------------------------------------------------------------------- */
-/* whole-piece lookup for keys of 1..11 bytes; returns the rank or JTK_RANK_MAX */
-JTK_HD int32_t jtk_lookup_a(const jtk_tables &T, uint32_t w0, uint32_t w1, uint32_t w2) {
-	uint32_t b = jtk_hash3(w0, w1, w2) & T.mask_a;
+/* whole-piece lookup for keys of 2..24 bytes (six zero-padded key words); returns the rank or JTK_RANK_MAX */
+JTK_HD int32_t jtk_lookup_a(const jtk_tables &T, const uint32_t *k, uint32_t len) {
+	uint32_t b = jtk_hash6(k, len) & T.mask_a;
 	for (;;) {
-		const jtk_slot s0 = T.tab_a[2 * b], s1 = T.tab_a[2 * b + 1];
-		if (s0.x == w0 && s0.y == w1 && s0.z == w2) return (int32_t) s0.w;
-		if (s0.z == 0) return JTK_RANK_MAX;
-		if (s1.x == w0 && s1.y == w1 && s1.z == w2) return (int32_t) s1.w;
-		if (s1.z == 0) return JTK_RANK_MAX;
+		const jtk_slot_a s = T.tab_a[b]; /* 32 bytes, one sector: two 16-byte loads */
+		if (s.len == 0) return JTK_RANK_MAX;
+		if (s.len == len && s.k[0] == k[0] && s.k[1] == k[1] && s.k[2] == k[2] && s.k[3] == k[3] && s.k[4] == k[4] && s.k[5] == k[5]) return (int32_t) s.rank;
 		b = (b + 1) & T.mask_a;
 	}
 }
 
-/* whole-piece lookup for keys of 12..max_token_len bytes, verified byte by byte */
+/* whole-piece lookup for keys of 25..max_token_len bytes, verified byte by byte */
 JTK_HD int32_t jtk_lookup_b(const jtk_tables &T, const uint8_t *p, uint32_t n) {
 	uint64_t h = jtk_hash_bytes_init();
 	for (uint32_t i = 0; i < n; i++) h = jtk_hash_bytes_step(h, p[i]);
@@ -662,20 +670,24 @@ JTK_HD int32_t jtk_lookup_piece(const jtk_tables &T, const uint8_t *p, int n) {
 		return id < JTK_PSEUDO_BASE + 256 ? JTK_RANK_MAX : id;
 	}
 	if (n <= JTK_INLINE_KEY_MAX) {
-		/* three unaligned key words from four aligned loads (the staging buffer is padded), then masked to n bytes */
+		/* six unaligned key words from seven aligned loads (the staging buffer is padded), masked to n bytes */
 		const uint32_t *aw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t) 3);
 		const int sh = (int) (reinterpret_cast<uintptr_t>(p) & 3) * 8;
-		const uint32_t a0 = aw[0], a1 = aw[1], a2 = aw[2], a3 = aw[3];
-		uint32_t w0 = sh ? (a0 >> sh) | (a1 << (32 - sh)) : a0;
-		uint32_t w1 = sh ? (a1 >> sh) | (a2 << (32 - sh)) : a1;
-		uint32_t w2 = sh ? (a2 >> sh) | (a3 << (32 - sh)) : a2;
-		if (n < 4) w0 &= (1u << (8 * n)) - 1u;
-		if (n <= 4) w1 = 0;
-		else if (n < 8) w1 &= (1u << (8 * (n - 4))) - 1u;
-		if (n <= 8) w2 = 0;
-		else w2 &= (1u << (8 * (n - 8))) - 1u;
-		w2 |= (uint32_t) n << 24;
-		return jtk_lookup_a(T, w0, w1, w2);
+		uint32_t a[7];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (int i = 0; i < 7; i++) a[i] = aw[i];
+		uint32_t k[6];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (int i = 0; i < 6; i++) {
+			const uint32_t w = sh ? (a[i] >> sh) | (a[i + 1] << (32 - sh)) : a[i];
+			const int rem = n - 4 * i; /* key bytes that belong to word i */
+			k[i] = rem >= 4 ? w : rem <= 0 ? 0u : (w & ((1u << (8 * rem)) - 1u));
+		}
+		return jtk_lookup_a(T, k, (uint32_t) n);
 	}
 	if (n > T.max_token_len) return JTK_RANK_MAX;
 	return jtk_lookup_b(T, p, (uint32_t) n);

@@ -25,6 +25,10 @@
 
 #include "jtk_device.cuh"
 
+#ifndef JTK_DEFER_SLOW
+#define JTK_DEFER_SLOW 0 /* 1: process chunks that miss the ASCII fast paths in a dense second pass (measured slower: it serialises the slow chunks behind a barrier) */
+#endif
+
 namespace {
 
 constexpr int NT = JTK_NT;
@@ -44,7 +48,7 @@ __device__ __forceinline__ int32_t rec_make(int s, int m) { return REC_BASE + (i
 __device__ __forceinline__ uint32_t rec_payload(int32_t r) { return (uint32_t) (r - REC_BASE); }
 
 /* indices into the small shared "misc" array */
-enum { M_TILE = 0, M_NSLOW, M_RS, M_CARRY, M_HITS, M_WSUM = 16, M_HIST = 48 /* .. M_HIST + JTK_SHORT_PIECE */, M_WORDS = 128 };
+enum { M_TILE = 0, M_NSLOW, M_RS, M_CARRY, M_HITS, M_NDEFER, M_WSUM = 16, M_HIST = 48 /* .. M_HIST + JTK_SHORT_PIECE */, M_WORDS = 128 };
 static_assert(M_HIST + JTK_SHORT_PIECE + 1 <= M_WORDS, "misc too small");
 
 /* first set bit in [from, limit] of a bit array, or -1 */
@@ -261,6 +265,7 @@ __global__ void __launch_bounds__(JTK_NT, 2) jtk_split_lookup_kernel(const __gri
 			misc[M_TILE] = atomicAdd(&a.hdr->ticket, 1u);
 			misc[M_NSLOW] = 0;
 			misc[M_HITS] = 0;
+			misc[M_NDEFER] = 0;
 		}
 		if (tid <= JTK_SHORT_PIECE) misc[M_HIST + tid] = 0;
 		__syncthreads();
@@ -286,15 +291,39 @@ __global__ void __launch_bounds__(JTK_NT, 2) jtk_split_lookup_kernel(const __gri
 		__syncthreads();
 		c.rs = (int) misc[M_RS];
 
-		/* ---- P2: code point classes ---- */
-		for (int ch = tid; ch <= JTK_REGION_CHUNKS; ch += NT) jtk_classify_chunk(c, ch);
+		/* ---- P2: code point classes.  Chunks the ASCII fast path cannot take are collected and then processed densely,
+		 * one per thread, so that a single non-ASCII chunk does not drag its whole warp through the slow path ---- */
+#if JTK_DEFER_SLOW
+		for (int ch = tid; ch <= JTK_REGION_CHUNKS; ch += NT)
+			if (!jtk_classify_fast(c, ch)) plist[atomicAdd(&misc[M_NDEFER], 1u)] = (uint16_t) ch;
 		__syncthreads();
-		if (tid == 0) misc[M_CARRY] = (uint32_t) jtk_region_carry_n(c);
+		for (int i = tid; i < (int) misc[M_NDEFER]; i += NT) jtk_classify_generic(c, plist[i]);
+#else
+		for (int ch = tid; ch <= JTK_REGION_CHUNKS; ch += NT) jtk_classify_chunk(c, ch);
+#endif
+		__syncthreads();
+		if (tid == 0) {
+			misc[M_CARRY] = (uint32_t) jtk_region_carry_n(c);
+			misc[M_NDEFER] = 0;
+		}
 		__syncthreads();
 		c.carry_n = (int) misc[M_CARRY];
 
-		/* ---- P3: split rules -> piece-start bits; special-token guard ---- */
+		/* ---- P3: split rules -> piece-start bits (same two-step scheme); special-token guard ---- */
+#if JTK_DEFER_SLOW
+		for (int ch = BH / 16 + tid; ch < JTK_REGION_CHUNKS; ch += NT) {
+			uint32_t bits;
+			if (jtk_boundary_fast(c, ch, &bits)) reinterpret_cast<uint16_t *>(bmask)[ch] = (uint16_t) bits;
+			else plist[atomicAdd(&misc[M_NDEFER], 1u)] = (uint16_t) ch;
+		}
+		__syncthreads();
+		for (int i = tid; i < (int) misc[M_NDEFER]; i += NT) {
+			const int ch = plist[i];
+			reinterpret_cast<uint16_t *>(bmask)[ch] = (uint16_t) jtk_boundary_generic(c, ch);
+		}
+#else
 		for (int ch = BH / 16 + tid; ch < JTK_REGION_CHUNKS; ch += NT) reinterpret_cast<uint16_t *>(bmask)[ch] = (uint16_t) jtk_boundary_chunk(c, ch);
+#endif
 		if (check_special) {
 			for (int ch = tid; ch < TC; ch += NT) {
 				const int r0 = BH + ch * 16;

@@ -177,11 +177,11 @@ static int bucket_insert(std::vector<jtk_slot> &tab, uint32_t mask, uint32_t has
 	}
 }
 
-static void pack_inline_key(const uint8_t *p, int n, uint32_t w[3]) {
-	uint8_t buf[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+static void pack_inline_key(const uint8_t *p, int n, uint32_t w[6]) {
+	uint8_t buf[24];
+	memset(buf, 0, sizeof(buf));
 	memcpy(buf, p, (size_t) n);
-	buf[11] = (uint8_t) n;
-	memcpy(w, buf, 12);
+	memcpy(w, buf, 24);
 }
 
 int jtk_build_host_tables(const jtk_params *p, jtk_host_tables *t, std::string *err) {
@@ -255,9 +255,9 @@ int jtk_build_host_tables(const jtk_params *p, jtk_host_tables *t, std::string *
 		else if (len > JTK_INLINE_KEY_MAX) n_b++;
 	}
 
-	/* table A: inline keys */
-	t->mask_a = pow2_at_least((uint64_t) (n_a / 0.8) + 1) - 1; /* two slots per bucket, load <= 0.4 */
-	t->tab_a.assign(2 * (size_t) (t->mask_a + 1), jtk_slot{0, 0, 0, 0});
+	/* table A: inline keys, one 32-byte slot per probe, load <= 0.5 */
+	t->mask_a = pow2_at_least((uint64_t) (n_a / 0.5) + 1) - 1;
+	t->tab_a.assign((size_t) t->mask_a + 1, jtk_slot_a{{0, 0, 0, 0, 0, 0}, 0, 0});
 	/* table B: hashed long keys, w = token index + 1 (0 = empty) */
 	t->mask_b = pow2_at_least((uint64_t) (n_b / 0.8) + 1) - 1;
 	t->tab_b.assign(2 * (size_t) (t->mask_b + 1), jtk_slot{0, 0, 0, 0});
@@ -266,10 +266,17 @@ int jtk_build_host_tables(const jtk_params *p, jtk_host_tables *t, std::string *
 		const uint8_t *kb = t->tok_bytes.data() + t->tok_off[(size_t) k];
 		if (len == 0) continue; /* an empty key can only match an empty piece, which emits nothing on this path */
 		if (len <= JTK_INLINE_KEY_MAX) {
-			uint32_t w[3];
-			pack_inline_key(kb, (int) len, w);
-			jtk_slot s{w[0], w[1], w[2], (uint32_t) t->tok_rank[(size_t) k]};
-			int pr = bucket_insert(t->tab_a, t->mask_a, jtk_hash3(w[0], w[1], w[2]), s, [](const jtk_slot &x) { return x.z == 0; });
+			jtk_slot_a s;
+			pack_inline_key(kb, (int) len, s.k);
+			s.len = len;
+			s.rank = (uint32_t) t->tok_rank[(size_t) k];
+			uint32_t b = jtk_hash6(s.k, len) & t->mask_a;
+			int pr = 1;
+			while (t->tab_a[b].len != 0) {
+				b = (b + 1) & t->mask_a;
+				pr++;
+			}
+			t->tab_a[b] = s;
 			t->max_probe_a = std::max(t->max_probe_a, pr);
 		} else {
 			uint64_t h = jtk_hash_bytes_init();

@@ -22,7 +22,7 @@ struct jtk_host_tables {
 	std::vector<uint8_t> ascii_cls;
 	std::vector<uint16_t> cp_stage1;
 	std::vector<uint8_t> cp_stage2;
-	std::vector<jtk_slot> tab_a;
+	std::vector<jtk_slot_a> tab_a;
 	uint32_t mask_a = 0;
 	std::vector<jtk_slot> tab_b;
 	uint32_t mask_b = 0;

@@ -76,4 +76,4 @@ def test_table_statistics():
         e = emu.EmuEncoding(name, pat, 0x100, jo.load_tiktoken(os.path.join(jo.DATA, fname)), special)
         st = e.stats()
         assert st[0] == ntok and st[1] == npairs
-        assert st[2] <= 16 and st[4] <= 16  # longest probe sequences (buckets)
+        assert st[2] <= 40 and st[4] <= 16  # longest probe sequences (piece table slots / pair table buckets)

@@ -61,6 +61,13 @@ struct jtk_workspace {
 	cudaStream_t stream = nullptr;
 };
 
+/* per-call piece memo buffer (see jtk_memo_entry); pooled per device, an epoch per buffer makes old entries invisible */
+struct jtk_memo_buf {
+	jtk_memo_entry *p = nullptr;
+	uint32_t epoch = 0;
+};
+constexpr uint32_t JTK_MEMO_ENTRIES = 1u << 18; /* 16 MiB */
+
 struct jtk_device_state {
 	int device = 0;
 	int num_sms = 0;
@@ -70,6 +77,7 @@ struct jtk_device_state {
 	size_t l2_bytes = 0;
 	std::mutex mu;
 	std::vector<jtk_workspace *> free_ws;
+	std::vector<jtk_memo_buf *> free_memo;
 };
 
 struct jtk_pinned_buf {
@@ -299,6 +307,10 @@ extern "C" void jtk_encoding_destroy(jtk_encoding *e) {
 	for (jtk_device_state *ds : e->devs) {
 		cudaSetDevice(ds->device);
 		for (jtk_workspace *w : ds->free_ws) free_workspace(w);
+		for (jtk_memo_buf *m : ds->free_memo) {
+			cudaFree(m->p);
+			delete m;
+		}
 		for (void *p : ds->allocs) cudaFree(p);
 		delete ds;
 	}
@@ -331,6 +343,46 @@ static int64_t sub_batch_tiles() {
 		return (int64_t) (n >= 64 ? n : JTK_DEFAULT_SUB_TILES);
 	}();
 	return v;
+}
+
+static bool memo_enabled() {
+	static const bool v = [] {
+		const char *env = getenv("JTK_MEMO");
+		return !(env && env[0] == '0');
+	}();
+	return v;
+}
+
+/* A memo buffer for one call; nullptr (memo off) when disabled or out of memory. */
+static jtk_memo_buf *acquire_memo(jtk_device_state *ds) {
+	if (!memo_enabled()) return nullptr;
+	jtk_memo_buf *m = nullptr;
+	{
+		std::lock_guard<std::mutex> lk(ds->mu);
+		if (!ds->free_memo.empty()) {
+			m = ds->free_memo.back();
+			ds->free_memo.pop_back();
+		}
+	}
+	if (!m) {
+		m = new jtk_memo_buf();
+		if (cudaMalloc(&m->p, sizeof(jtk_memo_entry) * JTK_MEMO_ENTRIES) != cudaSuccess || cudaMemset(m->p, 0, sizeof(jtk_memo_entry) * JTK_MEMO_ENTRIES) != cudaSuccess) {
+			cudaGetLastError();
+			cudaFree(m->p);
+			delete m;
+			return nullptr;
+		}
+	}
+	if (++m->epoch >= 0xFFFFFFu) {
+		cudaMemset(m->p, 0, sizeof(jtk_memo_entry) * JTK_MEMO_ENTRIES);
+		m->epoch = 1;
+	}
+	return m;
+}
+static void release_memo(jtk_device_state *ds, jtk_memo_buf *m) {
+	if (!m) return;
+	std::lock_guard<std::mutex> lk(ds->mu);
+	ds->free_memo.push_back(m);
 }
 
 static int ensure_ws_tiles(jtk_workspace *w, int64_t ntiles, int64_t long_cap) {
@@ -474,7 +526,7 @@ static int run_long_pieces(jtk_device_state *ds, jtk_workspace *w, jtk_encode_ar
 
 static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspace *w, const uint8_t *d_utf8, int64_t nbytes, const int64_t *d_doc_off,
                               int64_t ndocs, uint32_t flags, int32_t *d_ids, int64_t ids_capacity, int64_t *d_tok_off, int32_t *d_doc_status,
-                              uint8_t *d_piece_flags, cudaStream_t st, jtk_device_info *info, bool sync_and_long) {
+                              uint8_t *d_piece_flags, cudaStream_t st, jtk_device_info *info, bool sync_and_long, const jtk_memo_buf *memo) {
 	(void) e;
 	if (nbytes < 0 || ndocs < 0) return set_error(JTK_E_ARG, "negative size");
 	if ((reinterpret_cast<uintptr_t>(d_utf8) & 15) != 0) return set_error(JTK_E_ARG, "d_utf8 must be 16-byte aligned");
@@ -496,6 +548,11 @@ static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspa
 	a.doc_status = d_doc_status;
 	a.flags = flags;
 	a.piece_flags = d_piece_flags;
+	if (memo) {
+		a.memo = memo->p;
+		a.memo_mask = JTK_MEMO_ENTRIES - 1;
+		a.memo_epoch = memo->epoch;
+	}
 	CUDA_TRY(cudaMemsetAsync(w->hdr, 0, sizeof(jtk_batch_header), st));
 	CUDA_TRY(jtk_launch_tile_first_doc(d_doc_off, ndocs, ntiles, w->tile_first_doc, st));
 	const bool time_kernel = (flags & JTK_TIME_KERNEL) && sync_and_long;
@@ -552,9 +609,11 @@ extern "C" int jtk_encode_batch_device(jtk_encoding *e, int device, const uint8_
 	jtk_device_state *ds = e->devs[(size_t) di];
 	CUDA_TRY(cudaSetDevice(device));
 	jtk_workspace *w = acquire_ws(ds);
+	jtk_memo_buf *memo = acquire_memo(ds);
 	memset(info, 0, sizeof(*info));
 	int rc = encode_device_impl(e, ds, w, d_utf8, nbytes, d_doc_off, ndocs, flags, d_ids, ids_capacity, d_tok_off, d_doc_status, nullptr,
-	                            reinterpret_cast<cudaStream_t>(cuda_stream), info, true);
+	                            reinterpret_cast<cudaStream_t>(cuda_stream), info, true, memo);
+	release_memo(ds, memo);
 	release_ws(ds, w);
 	return rc;
 }
@@ -570,7 +629,7 @@ extern "C" int jtk_split_batch_device(jtk_encoding *e, int device, const uint8_t
 	jtk_device_info info;
 	memset(&info, 0, sizeof(info));
 	int rc = encode_device_impl(e, ds, w, d_utf8, nbytes, d_doc_off, ndocs, JTK_COUNT_ONLY, nullptr, 0, nullptr, nullptr, d_piece_flags,
-	                            reinterpret_cast<cudaStream_t>(cuda_stream), &info, true);
+	                            reinterpret_cast<cudaStream_t>(cuda_stream), &info, true, nullptr);
 	release_ws(ds, w);
 	return rc;
 }
@@ -703,6 +762,7 @@ static void run_shard(shard_job *job) {
 		if (rc != JTK_OK) return fail(rc);
 	}
 	constexpr int NS = 3;
+	jtk_memo_buf *memo = acquire_memo(ds); /* shared by all chunks of this call on this device */
 	jtk_workspace *ws[NS];
 	cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
 	cudaEvent_t ev_in[NS], ev_k0[NS], ev_k1[NS], ev_out[NS];
@@ -860,7 +920,7 @@ static void run_shard(shard_job *job) {
 		}
 		cudaEventRecord(ev_k0[slot], s_comp);
 		rc = encode_device_impl(e, ds, w, w->d_in, cbytes, w->d_doc_off, nd, job->flags, want_ids ? w->d_ids : nullptr, w->in_cap, w->d_tok_off, w->d_status,
-		                        nullptr, s_comp, &infos[slot], false);
+		                        nullptr, s_comp, &infos[slot], false, memo);
 		cudaEventRecord(ev_k1[slot], s_comp);
 		if (rc != JTK_OK) break;
 		if (k >= 1) rc = copy_out(k - 1);
@@ -883,6 +943,7 @@ static void run_shard(shard_job *job) {
 	if (s_in) cudaStreamDestroy(s_in);
 	if (s_comp) cudaStreamDestroy(s_comp);
 	if (s_out) cudaStreamDestroy(s_out);
+	release_memo(ds, memo);
 	if (rc != JTK_OK) fail(rc);
 }
 

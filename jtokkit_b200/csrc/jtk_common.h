@@ -83,6 +83,19 @@ struct alignas(16) jtk_slot_a {
 	uint32_t rank;
 };
 
+/* Per-call piece memo (direct mapped): the tokens bytePairMerge produced for a short piece, so that later occurrences of
+ * the same piece in the same call cost one probe instead of a merge loop.  Filled by the merge kernel, read by the
+ * split+lookup kernels of later sub-batches / chunks of the SAME call (stream ordered, never concurrently); entries of
+ * earlier calls are recognised by their epoch and treated as empty.  Results are identical with or without it. */
+#define JTK_MEMO_MAX_PIECE 16
+#define JTK_MEMO_MAX_TOKENS 10
+struct alignas(64) jtk_memo_entry {
+	uint32_t key[4];
+	uint32_t meta;  /* epoch << 8 | state (0 empty, 1 being written, 2 valid) */
+	uint32_t n_cnt; /* piece length | token count << 8 */
+	int32_t tok[JTK_MEMO_MAX_TOKENS];
+};
+
 /* Device tables of one encoding on one device (all pointers are device memory). */
 struct jtk_tables {
 	int32_t pattern_kind;

@@ -600,14 +600,34 @@ JTK_HD bool jtk_special_at(const jtk_tables &T, const uint8_t *gbytes, int64_t g
 /* ---------------------------------------------------------------------------------------------
  * table lookups
  * ------------------------------------------------------------------------------------------- */
-/* whole-piece lookup for keys of 2..24 bytes (six zero-padded key words); returns the rank or JTK_RANK_MAX */
-JTK_HD int32_t jtk_lookup_a(const jtk_tables &T, const uint32_t *k, uint32_t len) {
-	uint32_t b = jtk_hash6(k, len) & T.mask_a;
+/* whole-piece lookup for keys of 2..24 bytes (six zero-padded key words, h = jtk_hash6(k, len)); the rank or JTK_RANK_MAX */
+JTK_HD int32_t jtk_lookup_a(const jtk_tables &T, const uint32_t *k, uint32_t len, uint32_t h) {
+	uint32_t b = h & T.mask_a;
 	for (;;) {
 		const jtk_slot_a s = T.tab_a[b]; /* 32 bytes, one sector: two 16-byte loads */
 		if (s.len == 0) return JTK_RANK_MAX;
 		if (s.len == len && s.k[0] == k[0] && s.k[1] == k[1] && s.k[2] == k[2] && s.k[3] == k[3] && s.k[4] == k[4] && s.k[5] == k[5]) return (int32_t) s.rank;
 		b = (b + 1) & T.mask_a;
+	}
+}
+
+/* Six zero-padded key words of the n <= 24 bytes at p: unaligned words from seven aligned loads (the staging buffer is
+ * padded; p + 27 must be readable), masked to n bytes. */
+JTK_HD void jtk_build_key(const uint8_t *p, int n, uint32_t *k) {
+	const uint32_t *aw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t) 3);
+	const int sh = (int) (reinterpret_cast<uintptr_t>(p) & 3) * 8;
+	uint32_t a[7];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+	for (int i = 0; i < 7; i++) a[i] = aw[i];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+	for (int i = 0; i < 6; i++) {
+		const uint32_t w = sh ? (a[i] >> sh) | (a[i + 1] << (32 - sh)) : a[i];
+		const int rem = n - 4 * i; /* key bytes that belong to word i */
+		k[i] = rem >= 4 ? w : rem <= 0 ? 0u : (w & ((1u << (8 * rem)) - 1u));
 	}
 }
 
@@ -670,24 +690,9 @@ JTK_HD int32_t jtk_lookup_piece(const jtk_tables &T, const uint8_t *p, int n) {
 		return id < JTK_PSEUDO_BASE + 256 ? JTK_RANK_MAX : id;
 	}
 	if (n <= JTK_INLINE_KEY_MAX) {
-		/* six unaligned key words from seven aligned loads (the staging buffer is padded), masked to n bytes */
-		const uint32_t *aw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t) 3);
-		const int sh = (int) (reinterpret_cast<uintptr_t>(p) & 3) * 8;
-		uint32_t a[7];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-		for (int i = 0; i < 7; i++) a[i] = aw[i];
 		uint32_t k[6];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-		for (int i = 0; i < 6; i++) {
-			const uint32_t w = sh ? (a[i] >> sh) | (a[i + 1] << (32 - sh)) : a[i];
-			const int rem = n - 4 * i; /* key bytes that belong to word i */
-			k[i] = rem >= 4 ? w : rem <= 0 ? 0u : (w & ((1u << (8 * rem)) - 1u));
-		}
-		return jtk_lookup_a(T, k, (uint32_t) n);
+		jtk_build_key(p, n, k);
+		return jtk_lookup_a(T, k, (uint32_t) n, jtk_hash6(k, (uint32_t) n));
 	}
 	if (n > T.max_token_len) return JTK_RANK_MAX;
 	return jtk_lookup_b(T, p, (uint32_t) n);

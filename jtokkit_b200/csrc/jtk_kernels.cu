@@ -420,16 +420,42 @@ __global__ void __launch_bounds__(JTK_NT, 2) jtk_split_lookup_kernel(const __gri
 						}
 						hits++;
 					} else {
-						out = jtk_lookup_piece(T, p, n);
+						uint32_t key[6];
+						uint32_t h = 0;
+						if (n <= JTK_INLINE_KEY_MAX) {
+							jtk_build_key(p, n, key);
+							h = jtk_hash6(key, (uint32_t) n);
+							out = jtk_lookup_a(T, key, (uint32_t) n, h);
+						} else {
+							out = n > T.max_token_len ? JTK_RANK_MAX : jtk_lookup_b(T, p, (uint32_t) n);
+						}
 						if (out != JTK_RANK_MAX) {
 							hits++;
 						} else {
 							out = rec_make(s, n);
-							if (n <= JTK_SHORT_PIECE) {
+							bool memo_hit = false;
+							if (n <= JTK_MEMO_MAX_PIECE && a.memo) { /* has this call merged the same piece before? */
+								const jtk_memo_entry *me = a.memo + ((h * 0x9E3779B1u) >> 8 & a.memo_mask);
+								const uint4 q0 = *reinterpret_cast<const uint4 *>(me), q1 = *(reinterpret_cast<const uint4 *>(me) + 1);
+								if (q1.x == ((a.memo_epoch << 8) | 2u) && (q1.y & 0xFFu) == (uint32_t) n && q0.x == key[0] && q0.y == key[1] && q0.z == key[2] &&
+								    q0.w == key[3]) {
+									const int cnt = (int) (q1.y >> 8);
+									int32_t *stok = a.slowtok + lt * (long long) RECN + s;
+									if (!(a.flags & JTK_COUNT_ONLY)) {
+										stok[0] = (int32_t) q1.z;
+										if (cnt > 1) stok[1] = (int32_t) q1.w;
+										for (int k = 2; k < cnt; k++) stok[k] = me->tok[k];
+									}
+									out = rec_make(s, cnt);
+									hits += cnt;
+									memo_hit = true;
+								}
+							}
+							if (memo_hit) {
+							} else if (n <= JTK_SHORT_PIECE) {
 								a.slowq[lt * (long long) QCAP + atomicAdd(&misc[M_NSLOW], 1u)] = (uint16_t) q;
 								atomicAdd(&misc[M_HIST + n], 1u);
-							}
-							else if (n <= JTK_GROUP8_PIECE) a.med8[atomicAdd(&a.hdr->n_med8, 1u)] = ((uint32_t) lt << 14) | (uint32_t) q;
+							} else if (n <= JTK_GROUP8_PIECE) a.med8[atomicAdd(&a.hdr->n_med8, 1u)] = ((uint32_t) lt << 14) | (uint32_t) q;
 							else a.med32[atomicAdd(&a.hdr->n_med32, 1u)] = ((uint32_t) lt << 14) | (uint32_t) q;
 						}
 					}
@@ -542,6 +568,23 @@ __global__ void __launch_bounds__(NTHREADS) jtk_merge_short_kernel(const __grid_
 			rec[q] = rec_make(s, cnt);
 			atomicAdd(&a.tile_count[a.tile_begin + lt], cnt);
 			if (unk) flag_doc(a, tb + s, JTK_DOC_UNKNOWN_BYTES);
+			if (NSLOT == 16 && a.memo && !unk && cnt <= JTK_MEMO_MAX_TOKENS) { /* remember the result for later occurrences in this call */
+				uint32_t key[6] = {0, 0, 0, 0, 0, 0};
+				const uint8_t *pb = a.bytes + tb + s;
+				for (int k = 0; k < n; k++) key[k >> 2] |= (uint32_t) pb[k] << (8 * (k & 3));
+				jtk_memo_entry *me = a.memo + ((jtk_hash6(key, (uint32_t) n) * 0x9E3779B1u) >> 8 & a.memo_mask);
+				const uint32_t old = me->meta;
+				if ((old >> 8) != a.memo_epoch && atomicCAS(&me->meta, old, (a.memo_epoch << 8) | 1u) == old) {
+					me->key[0] = key[0];
+					me->key[1] = key[1];
+					me->key[2] = key[2];
+					me->key[3] = key[3];
+					me->n_cnt = (uint32_t) n | ((uint32_t) cnt << 8);
+					for (int k = 0; k < cnt; k++) me->tok[k] = tk[k * NTHREADS];
+					__threadfence();
+					me->meta = (a.memo_epoch << 8) | 2u;
+				}
+			}
 		}
 	}
 }

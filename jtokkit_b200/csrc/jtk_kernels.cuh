@@ -76,6 +76,8 @@ struct jtk_encode_args {
 	jtk_long_piece *long_list;
 	int64_t long_cap;
 	uint8_t *piece_flags;  /* debug: one byte per input byte, 1 where a piece starts (nullable) */
+	jtk_memo_entry *memo;  /* per-call piece memo (nullable) */
+	uint32_t memo_mask, memo_epoch;
 	/* host side only: L2 access-policy window over the hot tables (0 bytes = none) */
 	const void *l2_base;
 	size_t l2_bytes;

@@ -417,14 +417,16 @@ JTK_HD bool jtk_is_piece_start(const jtk_tile_ctx &c, int r, int cur, int *nrun)
 }
 
 /* ---------------------------------------------------------------------------------------------
- * bit-parallel split rules for an all-ASCII neighbourhood
- * The window is the 24 bytes [r0 - 4, r0 + 20) around chunk r0 .. r0 + 15; bit i of every mask stands for window
- * position i, so "class of the previous character" is a left shift by one.  Preconditions (else the per-position
- * rules below run): the window holds ASCII only, lies inside the usable region and the input, and contains no
- * document start.  The formulas are the rules of jtk_is_piece_start written as boolean algebra; the emulator test
+ * bit-parallel split rules
+ * The window is the 32 bytes [r0 - 8, r0 + 24) around chunk r0 .. r0 + 15; bit i of every mask stands for window byte
+ * i.  Continuation bytes carry their character's class, so "class of the previous character" is a left shift by one
+ * even in multi-byte text; piece starts are only reported on lead bytes.  Preconditions (else the per-position rules
+ * below run): the window lies inside the usable region and the input, contains no document start, and its whitespace,
+ * digits and contraction letters are all ASCII (U+3000, Arabic-Indic digits, U+017F ... take the slow path).
+ * The formulas are the rules of jtk_is_piece_start written as boolean algebra; the emulator test
  * (tests/test_emu_cpu.py) fuzzes both paths against the oracle.
  * ------------------------------------------------------------------------------------------- */
-/* bit b of each of the four class bytes of w -> 4 mask bits */
+/* bit b of each of the four bytes of w -> 4 mask bits */
 JTK_HD uint32_t jtk_plane4(uint32_t w, int b) { return (((w >> b) & 0x01010101u) * 0x01020408u) >> 24; }
 
 /* spread `seed` forward (towards higher positions) through runs of `run`: result has every position reachable from a
@@ -457,51 +459,54 @@ JTK_HD uint32_t jtk_spread_down(uint32_t seed, uint32_t run) {
 
 JTK_HD bool jtk_boundary_fast(const jtk_tile_ctx &c, int chunk, uint32_t *out) {
 	const int r0 = chunk * 16;
-	const int ws = r0 - 4; /* window start */
-	if (ws < c.rs || c.g0 + r0 + 20 > c.total) return false;
-	const uint32_t *bw = reinterpret_cast<const uint32_t *>(c.sb + ws);
-	if (((bw[0] | bw[1] | bw[2] | bw[3] | bw[4] | bw[5]) & 0x80808080u) != 0) return false;
-	{ /* document starts in [ws, ws + 24] */
+	const int ws = r0 - 8; /* window start */
+	if (ws < c.rs || c.g0 + r0 + 24 > c.total) return false;
+	{ /* document starts in [ws, ws + 32] */
 		const int wi = ws >> 5, sh = ws & 31;
 		uint32_t d = c.dmask[wi] >> sh;
-		if (sh > 7) d |= c.dmask[wi + 1] << (32 - sh);
-		if (d & 0x1FFFFFFu) return false;
+		if (sh) d |= c.dmask[wi + 1] << (32 - sh);
+		if (d | (c.dmask[(ws + 32) >> 5] >> ((ws + 32) & 31) & 1u)) return false;
 	}
+	const uint32_t *bw = reinterpret_cast<const uint32_t *>(c.sb + ws);
 	const uint32_t *cw = reinterpret_cast<const uint32_t *>(c.cls + ws);
-	uint32_t P0 = 0, P1 = 0, P2 = 0, P3 = 0;
-	for (int k = 0; k < 6; k++) {
+	uint32_t P0 = 0, P1 = 0, P2 = 0, P3 = 0, CONT = 0, HB = 0;
+	for (int k = 0; k < 8; k++) {
 		const uint32_t w = cw[k];
 		P0 |= jtk_plane4(w, 0) << (4 * k);
 		P1 |= jtk_plane4(w, 1) << (4 * k);
 		P2 |= jtk_plane4(w, 2) << (4 * k);
 		P3 |= jtk_plane4(w, 3) << (4 * k);
+		CONT |= jtk_plane4(w, 7) << (4 * k);
+		HB |= jtk_plane4(bw[k], 7) << (4 * k);
 	}
-	const uint32_t ALL = 0xFFFFFFu;
 	/* class masks from the four bit planes of the class code (jtk_common.h) */
-	const uint32_t O_ = ~P3 & ~P2 & ~P1 & ALL;          /* 0, 1 */
+	const uint32_t O_ = ~P3 & ~P2 & ~P1;                  /* 0, 1 */
 	const uint32_t AP = O_ & P0;                          /* 1 */
-	const uint32_t SP = ~P3 & ~P2 & P1 & ~P0 & ALL;      /* 2 */
+	const uint32_t SP = ~P3 & ~P2 & P1 & ~P0;             /* 2 */
 	const uint32_t NL = ~P3 & ~P2 & P1 & P0;              /* 3 */
-	const uint32_t WO = ~P3 & P2 & ~P1 & ~P0 & ALL;      /* 4 */
+	const uint32_t WO = ~P3 & P2 & ~P1 & ~P0;             /* 4 */
 	const uint32_t N = ~P3 & P2 & ~P1 & P0;               /* 5 */
-	const uint32_t L = (P3 | (P2 & P1)) & ALL;            /* 6 .. 14 */
+	const uint32_t L = P3 | (P2 & P1);                    /* 6 .. 14 */
 	const uint32_t S1 = (~P3 & P2 & P1 & P0) | (P3 & ~P2 & ~(P1 & P0)); /* 7 .. 10: s t m d */
 	const uint32_t RV = (P3 & ~P2 & P1 & P0) | (P3 & P2 & ~P1 & ~P0);   /* 11, 12: r v */
 	const uint32_t LL = P3 & P2 & ~P1 & P0;               /* 13 */
 	const uint32_t LE = P3 & P2 & P1 & ~P0;               /* 14 */
-	const uint32_t Ostart = O_ & ~((O_ | SP) << 1);
+	if ((SP | NL | WO | N | S1 | RV | LL | LE) & HB) return false; /* multi-byte whitespace / digit / contraction letter */
+	const uint32_t LEAD = ~CONT;
+	const uint32_t Ostart = O_ & LEAD & ~((O_ | SP) << 1);
+	const uint32_t OstartAll = jtk_spread_up(Ostart, CONT & O_); /* ... on every byte of that character */
 	const uint32_t APs = AP & Ostart;
 	const uint32_t CE = (L << 1) & (((S1 << 1) & (APs << 2)) | ((((LE << 1) & (RV << 2)) | ((LL << 1) & (LL << 2))) & (APs << 3)));
 	uint32_t B;
 	if (c.T->pattern_kind == JTK_PAT_CL100K) {
 		const uint32_t Wn = SP | WO, W = Wn | NL;
-		const uint32_t BL = L & ((N << 1) | (NL << 1) | ((O_ << 1) & ~(Ostart << 1)) | CE);
+		const uint32_t BL = L & ((N << 1) | (NL << 1) | ((O_ << 1) & ~(OstartAll << 1)) | CE);
 		const uint32_t BNL = NL & ((L | N) << 1);
 		uint32_t BW = Wn & (~(W << 1) | (~W >> 1));
-		const uint32_t cand = Wn & (NL << 1) & ~BW & 0xFFFF0u; /* after an NL, followed by whitespace: needs the two run scans */
+		const uint32_t cand = Wn & (NL << 1) & ~BW & 0xFFFF00u; /* after an NL, followed by whitespace: needs the two run scans */
 		if (cand) {
 			/* does a \r\n come before the whitespace run ends?  unknown when the run leaves the window */
-			const uint32_t hit = jtk_spread_down(NL, Wn), edge = jtk_spread_down(Wn & 0x800000u, Wn);
+			const uint32_t hit = jtk_spread_down(NL, Wn), edge = jtk_spread_down(Wn & 0x80000000u, Wn);
 			const uint32_t nla = hit >> 1;
 			if (cand & (edge >> 1) & ~nla) return false;
 			BW |= cand & ~nla;
@@ -515,7 +520,7 @@ JTK_HD bool jtk_boundary_fast(const jtk_tile_ctx &c, int chunk, uint32_t *out) {
 		}
 		/* \p{N}{1,3}: every third position of a digit run starts a piece */
 		uint32_t BN = 0;
-		if (N & 0xFFFF0u) {
+		if (N & 0xFFFF00u) {
 			uint32_t T0 = N & ~(N << 1);
 			if (N & 1u) { /* the run of window position 0 began earlier: its phase comes from a walk */
 				T0 &= ~1u;
@@ -541,7 +546,7 @@ JTK_HD bool jtk_boundary_fast(const jtk_tile_ctx &c, int chunk, uint32_t *out) {
 		const uint32_t BW = W & (~(W << 1) | (~W >> 1));
 		B = BL | Ostart | BN | BW;
 	}
-	*out = (B >> 4) & 0xFFFFu;
+	*out = ((B & LEAD) >> 8) & 0xFFFFu;
 	return true;
 }
 

@@ -17,12 +17,20 @@ ASCII_UNITS_A = ["'s", "'t", "'re", "'ve", "'m", "'ll", "'d", "'S", "'LL", "x", 
 ASCII_UNITS_B = ["\n", "\n", " ", " ", " ", "\t", "!", "a", "1", "12345678", "\r\n", "          "]
 
 
-def random_docs(rng, ndocs, ascii_only=False):
+# non-ASCII letters, combining marks, multi-byte punctuation and emoji with ASCII whitespace / digits / apostrophes:
+# the multi-byte side of the bit-parallel split rules
+UTF8_ALPH = list("жяЖ中文あカ한नमけдоброеутро") + ["्", "ा", "ั", "ก", "é", "ß", "ñ", "—", "“", "。", "，", "🍕", "😀", "‍", "️"] + list(
+    "      \n\n\t''!?.,-0123abcsStTdD")
+
+
+def random_docs(rng, ndocs, ascii_only=False, utf8_letters=False):
     docs = []
     for _ in range(ndocs):
         n = rng.choice([0, 1, 5, 40, 200, 700])
         mode = rng.random()
-        if ascii_only:
+        if utf8_letters:
+            s = "".join(rng.choice(UTF8_ALPH) for _ in range(rng.randint(0, n)))
+        elif ascii_only:
             # stresses the bit-parallel fast path: contractions, digit runs, whitespace / newline runs
             k = rng.randint(0, n)
             if mode < 0.5:
@@ -50,8 +58,8 @@ def test_tile_emulator_matches_oracle(name, oracles):
     e = emu.EmuEncoding(name, pat, 0x100, ranks, special)
     o = oracles[name]
     rng = random.Random(7)
-    for it in range(3000):
-        docs = random_docs(rng, rng.randint(1, 4), ascii_only=(it % 2 == 1))
+    for it in range(4500):
+        docs = random_docs(rng, rng.randint(1, 4), ascii_only=(it % 3 == 1), utf8_letters=(it % 3 == 2))
         blob = b"".join(docs)
         off = np.zeros(len(docs) + 1, dtype=np.int64)
         off[1:] = np.cumsum([len(x) for x in docs])

@@ -110,6 +110,7 @@ struct jtk_tables {
 	/* whole-piece lookup, keys of 25..max_token_len bytes: slot = {hash lo, hash hi, rank, token index}, verified against tok_bytes */
 	const jtk_slot *tab_b;
 	uint32_t mask_b;
+	const uint32_t *long_filter; /* 65 536-bit filter over (first eight bytes, length) of the keys of table B: most long pieces skip the byte-wise hash */
 	const uint8_t *tok_bytes;   /* concatenated token bytes, by token index */
 	const uint32_t *tok_off;    /* ntokens + 1 */
 	/* merge loop (GptBytePairEncoding.java:200-300) re-keyed on (id left, id right) -> rank of the concatenation */

@@ -157,22 +157,51 @@ JTK_HD bool jtk_classify_fast(jtk_tile_ctx &c, int chunk) {
 	return true;
 }
 
+/* Character whose lead byte is at region index r (UTF-8 decoding without loops; the staging buffer is padded, so the three
+ * bytes after r are always readable).  dstart: document-start bits of region indices r + 1 .. r + 3 (bit 0 = r + 1).
+ * Same result as jtk_decode_char. */
+JTK_HD int jtk_decode_char_fast(const jtk_tables &T, const uint8_t *sb, int r, uint32_t dstart, int *len) {
+	const uint32_t b0 = sb[r];
+	*len = 1;
+	if (b0 < 0xC0 || b0 >= 0xF8) return JTK_C_O; /* stray continuation byte or invalid lead (ASCII is handled by the caller) */
+	const uint32_t b1 = sb[r + 1], b2 = sb[r + 2], b3 = sb[r + 3];
+	const int n = b0 < 0xE0 ? 2 : b0 < 0xF0 ? 3 : 4;
+	const bool ok = (b1 & 0xC0) == 0x80 && (n < 3 || (b2 & 0xC0) == 0x80) && (n < 4 || (b3 & 0xC0) == 0x80) && (dstart & ((1u << (n - 1)) - 1u)) == 0;
+	if (!ok) return JTK_C_O;
+	const uint32_t cp = n == 2 ? ((b0 & 0x1F) << 6) | (b1 & 0x3F)
+	                  : n == 3 ? ((b0 & 0x0F) << 12) | ((b1 & 0x3F) << 6) | (b2 & 0x3F)
+	                           : ((b0 & 0x07) << 18) | ((b1 & 0x3F) << 12) | ((b2 & 0x3F) << 6) | (b3 & 0x3F);
+	*len = n;
+	return jtk_cp_class(T, cp);
+}
+
 /* General classification of the 16 bytes of chunk `chunk` (region indices 16*chunk ..) into c.cls: UTF-8 decoding. */
 JTK_HD void jtk_classify_generic(jtk_tile_ctx &c, int chunk) {
 	const jtk_tables &T = *c.T;
 	const int r0 = chunk * 16;
-	jtk_region_start is_start{&c};
+	/* document-start bits of region indices r0 - 3 .. r0 + 28 (bit 3 = r0), one 64-bit extract */
+	uint32_t dwin;
+	{
+		const int lo = r0 - 3;
+		if (lo < 0) {
+			dwin = c.dmask[0] << 3;
+		} else {
+			const int wi = lo >> 5, sh = lo & 31;
+			dwin = c.dmask[wi] >> sh;
+			if (sh) dwin |= c.dmask[wi + 1] << (32 - sh);
+		}
+	}
 	int cur = JTK_C_O, rem = 0;
 	/* a character may have started in the previous chunk */
-	if ((c.sb[r0] & 0xC0) == 0x80 && !jtk_docstart(c, r0)) {
+	if ((c.sb[r0] & 0xC0) == 0x80 && !((dwin >> 3) & 1u)) {
 		for (int k = 1; k <= 3 && r0 - k >= c.rs; k++) {
-			uint8_t b = c.sb[r0 - k];
+			const uint8_t b = c.sb[r0 - k];
 			if ((b & 0xC0) == 0x80) {
-				if (jtk_docstart(c, r0 - k)) break;
+				if ((dwin >> (3 - k)) & 1u) break;
 				continue;
 			}
 			int len;
-			int cl = jtk_decode_char(T, c.sb, r0 - k, JTK_REGION + 16, is_start, &len);
+			const int cl = jtk_decode_char_fast(T, c.sb, r0 - k, dwin >> (4 - k), &len);
 			if (len > k) {
 				cur = cl;
 				rem = len - k;
@@ -180,25 +209,29 @@ JTK_HD void jtk_classify_generic(jtk_tile_ctx &c, int chunk) {
 			break;
 		}
 	}
-	uint8_t out[16];
+	uint32_t out[4] = {0, 0, 0, 0};
 	for (int i = 0; i < 16; i++) {
 		const int r = r0 + i;
 		const uint8_t b = c.sb[r];
+		uint32_t v;
 		if (rem > 0) { /* inside a validated character */
-			out[i] = (uint8_t) (cur | JTK_CONT);
+			v = (uint32_t) (cur | JTK_CONT);
 			rem--;
-			continue;
-		}
-		if (b < 0x80) {
-			out[i] = T.ascii_cls[b];
+		} else if (b < 0x80) {
+			v = c.ascii_lut[b];
 		} else {
 			int len;
-			cur = jtk_decode_char(T, c.sb, r, JTK_REGION + 16, is_start, &len);
+			cur = jtk_decode_char_fast(T, c.sb, r, dwin >> (4 + i), &len);
 			rem = len - 1;
-			out[i] = (uint8_t) cur;
+			v = (uint32_t) cur;
 		}
+		out[i >> 2] |= v << (8 * (i & 3));
 	}
-	for (int i = 0; i < 16; i++) c.cls[r0 + i] = out[i];
+	uint32_t *o = reinterpret_cast<uint32_t *>(c.cls + r0);
+	o[0] = out[0];
+	o[1] = out[1];
+	o[2] = out[2];
+	o[3] = out[3];
 }
 
 JTK_HD void jtk_classify_chunk(jtk_tile_ctx &c, int chunk) {
@@ -688,6 +721,15 @@ JTK_HD void jtk_lookup_pair2(const jtk_tables &T, int32_t l1, int32_t r1, int32_
 	*o2 = jtk_pair_resolve(T, b2, c0, c1, l2, r2);
 }
 
+/* keys of 25..max_token_len bytes: filter on (first eight bytes, length) first, the byte-wise hash only for survivors */
+JTK_HD int32_t jtk_lookup_long(const jtk_tables &T, const uint8_t *p, int n) {
+	uint32_t k[6];
+	jtk_build_key(p, 8, k);
+	const uint32_t f = jtk_hash3(k[0], k[1], (uint32_t) n) & 0xFFFFu;
+	if (!((T.long_filter[f >> 5] >> (f & 31)) & 1u)) return JTK_RANK_MAX;
+	return jtk_lookup_b(T, p, (uint32_t) n);
+}
+
 /* Whole-piece lookup of the n bytes at p (n >= 1): rank or JTK_RANK_MAX. */
 JTK_HD int32_t jtk_lookup_piece(const jtk_tables &T, const uint8_t *p, int n) {
 	if (n == 1) {
@@ -700,7 +742,7 @@ JTK_HD int32_t jtk_lookup_piece(const jtk_tables &T, const uint8_t *p, int n) {
 		return jtk_lookup_a(T, k, (uint32_t) n, jtk_hash6(k, (uint32_t) n));
 	}
 	if (n > T.max_token_len) return JTK_RANK_MAX;
-	return jtk_lookup_b(T, p, (uint32_t) n);
+	return jtk_lookup_long(T, p, n);
 }
 
 /* ---------------------------------------------------------------------------------------------

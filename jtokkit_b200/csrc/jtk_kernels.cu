@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(JTK_NT, 2) jtk_split_lookup_kernel(const __gri
 							h = jtk_hash6(key, (uint32_t) n);
 							out = jtk_lookup_a(T, key, (uint32_t) n, h);
 						} else {
-							out = n > T.max_token_len ? JTK_RANK_MAX : jtk_lookup_b(T, p, (uint32_t) n);
+							out = n > T.max_token_len ? JTK_RANK_MAX : jtk_lookup_long(T, p, n);
 						}
 						if (out != JTK_RANK_MAX) {
 							hits++;
@@ -715,9 +715,12 @@ __global__ void __launch_bounds__(1024, 1) jtk_tile_scan_kernel(const jtk_encode
  * kernel 4: ids to their final position (one CTA per tile) + document token offsets
  * ------------------------------------------------------------------------------------------- */
 constexpr int GNT = 256;
+constexpr int GATHER_SMEM = (int) sizeof(int32_t) * RECN + (int) sizeof(uint16_t) * (RECN + 8);
 
 __global__ void __launch_bounds__(GNT) jtk_gather_kernel(const __grid_constant__ jtk_encode_args a) {
-	__shared__ uint32_t s_prefix[RECN + 1]; /* tokens before each piece of the tile */
+	extern __shared__ __align__(16) uint8_t gsm[];
+	int32_t *s_tok = reinterpret_cast<int32_t *>(gsm);                            /* the tile's tokens in order, staged for coalesced stores */
+	uint16_t *s_prefix = reinterpret_cast<uint16_t *>(gsm + sizeof(int32_t) * RECN); /* tokens before each piece of the tile */
 	__shared__ int s_w[GNT / 32];
 	const int tid = threadIdx.x;
 	const long long tile = a.tile_begin + blockIdx.x;
@@ -754,16 +757,16 @@ __global__ void __launch_bounds__(GNT) jtk_gather_kernel(const __grid_constant__
 		for (int j = 0; j < IPT; j++) {
 			const int q = qb + j;
 			if (q < P) {
-				s_prefix[q] = (uint32_t) excl;
+				s_prefix[q] = (uint16_t) excl;
 				if (rec_is_id(r[j])) {
-					if (write_ids) a.ids[base + excl] = r[j];
+					s_tok[excl] = r[j];
 				} else {
 					const uint32_t pl = rec_payload(r[j]);
 					const int s = (int) ((pl >> 11) & 0x1FFFu);
 					if (pl & REC_LONG) {
 						a.long_list[stok[s]].insert_at = base + excl;
 					} else if (write_ids) {
-						for (int k = 0; k < cnt[j]; k++) a.ids[base + excl + k] = stok[s + k];
+						for (int k = 0; k < cnt[j]; k++) s_tok[excl + k] = stok[s + k];
 					}
 				}
 				excl += cnt[j];
@@ -771,8 +774,12 @@ __global__ void __launch_bounds__(GNT) jtk_gather_kernel(const __grid_constant__
 		}
 		carry += round_total;
 	}
-	if (tid == 0) s_prefix[P] = (uint32_t) carry;
+	if (tid == 0) s_prefix[P] = (uint16_t) carry;
 	__syncthreads();
+	if (write_ids) {
+		int32_t *dst = a.ids + base;
+		for (int k = tid; k < carry; k += GNT) dst[k] = s_tok[k];
+	}
 	if (a.tok_off) {
 		for (int64_t d = a.tile_first_doc[tile] + tid; d <= a.ndocs; d += GNT) {
 			const int64_t g = a.doc_off[d];
@@ -1116,7 +1123,9 @@ __global__ void jtk_long_fix_offsets_kernel(const jtk_long_piece *list, const in
  * launch wrappers
  * ============================================================================================= */
 cudaError_t jtk_encode_kernel_setup() {
-	return cudaFuncSetAttribute(jtk_split_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JTK_SMEM_BYTES);
+	cudaError_t e = cudaFuncSetAttribute(jtk_split_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JTK_SMEM_BYTES);
+	if (e != cudaSuccess) return e;
+	return cudaFuncSetAttribute(jtk_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GATHER_SMEM);
 }
 
 cudaError_t jtk_launch_tile_first_doc(const int64_t *doc_off, int64_t ndocs, int64_t ntiles, int32_t *out, cudaStream_t st) {
@@ -1170,7 +1179,7 @@ cudaError_t jtk_launch_sub_batch(const jtk_encode_args &a, int num_sms, cudaEven
 	cfg.blockDim = dim3(GNTM);
 	cudaLaunchKernelEx(&cfg, jtk_merge_medium_kernel, a);
 	jtk_tile_scan_kernel<<<1, 1024, 0, st>>>(a);
-	jtk_gather_kernel<<<(unsigned) nt, GNT, 0, st>>>(a);
+	jtk_gather_kernel<<<(unsigned) nt, GNT, GATHER_SMEM, st>>>(a);
 	return cudaGetLastError();
 }
 

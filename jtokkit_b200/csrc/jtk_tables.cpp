@@ -261,6 +261,7 @@ int jtk_build_host_tables(const jtk_params *p, jtk_host_tables *t, std::string *
 	/* table B: hashed long keys, w = token index + 1 (0 = empty) */
 	t->mask_b = pow2_at_least((uint64_t) (n_b / 0.8) + 1) - 1;
 	t->tab_b.assign(2 * (size_t) (t->mask_b + 1), jtk_slot{0, 0, 0, 0});
+	t->long_filter.assign(2048, 0);
 	for (int64_t k = 0; k < ntok; k++) {
 		uint32_t len = t->tok_off[(size_t) k + 1] - t->tok_off[(size_t) k];
 		const uint8_t *kb = t->tok_bytes.data() + t->tok_off[(size_t) k];
@@ -282,6 +283,12 @@ int jtk_build_host_tables(const jtk_params *p, jtk_host_tables *t, std::string *
 			uint64_t h = jtk_hash_bytes_init();
 			for (uint32_t i = 0; i < len; i++) h = jtk_hash_bytes_step(h, kb[i]);
 			h = jtk_hash_bytes_final(h, len);
+			{
+				uint32_t w[6];
+				pack_inline_key(kb, 8, w);
+				const uint32_t f = jtk_hash3(w[0], w[1], len) & 0xFFFFu;
+				t->long_filter[f >> 5] |= 1u << (f & 31);
+			}
 			jtk_slot s{(uint32_t) h, (uint32_t) (h >> 32), (uint32_t) t->tok_rank[(size_t) k], (uint32_t) k + 1};
 			int pr = bucket_insert(t->tab_b, t->mask_b, (uint32_t) h, s, [](const jtk_slot &x) { return x.w == 0; });
 			t->max_probe_b = std::max(t->max_probe_b, pr);
@@ -390,6 +397,7 @@ jtk_tables jtk_host_view(const jtk_host_tables &h) {
 	v.mask_a = h.mask_a;
 	v.tab_b = h.tab_b.data();
 	v.mask_b = h.mask_b;
+	v.long_filter = h.long_filter.data();
 	v.tok_bytes = h.tok_bytes.data();
 	v.tok_off = h.tok_off.data();
 	v.byte_id = h.byte_id.data();

@@ -26,6 +26,7 @@ struct jtk_host_tables {
 	uint32_t mask_a = 0;
 	std::vector<jtk_slot> tab_b;
 	uint32_t mask_b = 0;
+	std::vector<uint32_t> long_filter;
 	std::vector<uint8_t> tok_bytes;
 	std::vector<uint32_t> tok_off;
 	std::vector<int32_t> tok_rank; /* by token index (host only) */

@@ -557,8 +557,12 @@ static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspa
 	CUDA_TRY(cudaMemsetAsync(w->hdr, 0, sizeof(jtk_batch_header), st));
 	CUDA_TRY(jtk_launch_tile_first_doc(d_doc_off, ndocs, ntiles, w->tile_first_doc, st));
 	const bool time_kernel = (flags & JTK_TIME_KERNEL) && sync_and_long;
+	/* sub-batches: a small first one (16 MiB) so that the piece memo is warm early, then full-size ones */
 	const int64_t sub = w->sub_tiles;
-	const int64_t nsub = (ntiles + sub - 1) / sub;
+	std::vector<int64_t> cuts(1, 0);
+	if (memo && ntiles > 4 * 2048) cuts.push_back(2048);
+	while (cuts.back() < ntiles) cuts.push_back(std::min<int64_t>(ntiles, cuts.back() + sub));
+	const int64_t nsub = (int64_t) cuts.size() - 1;
 	if (time_kernel)
 		while ((int64_t) w->kev.size() < 2 * nsub) {
 			cudaEvent_t ev;
@@ -566,8 +570,8 @@ static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspa
 			w->kev.push_back(ev);
 		}
 	for (int64_t i = 0; i < nsub; i++) {
-		a.tile_begin = i * sub;
-		a.tile_end = std::min<int64_t>(ntiles, (i + 1) * sub);
+		a.tile_begin = cuts[(size_t) i];
+		a.tile_end = cuts[(size_t) i + 1];
 		CUDA_TRY(jtk_launch_sub_batch(a, ds->num_sms, time_kernel ? w->kev[(size_t) (2 * i)] : nullptr, time_kernel ? w->kev[(size_t) (2 * i + 1)] : nullptr, st));
 	}
 	CUDA_TRY(jtk_launch_finalize(a, st));

@@ -84,9 +84,30 @@ def dist_setup(n_gpus):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return rank, world, local
+
+
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this process (and thus its pinned host buffers, first touch) to the CPUs NVML reports as local to the GPU:
+    with several ranks per box the host<->device copies of the e2e leg otherwise cross the socket interconnect.
+    Returns the previous affinity so that the CPU baseline can use every core again."""
+    try:
+        import pynvml
+        before = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= before
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return before
+    except Exception:
+        return None
 
 
 def reduce_over_ranks(stats, world):
@@ -158,6 +179,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the encode path has no CPU fallback")
     torch.cuda.set_device(local)
+    all_cpus = bind_to_gpu_numa_node(local)
     dev = torch.device("cuda", local)
     jt.EncodingFactory.devices = [local]
     enc = jt.EncodingFactory.cl100k_base()
@@ -250,6 +272,8 @@ def run_ours(args):
     cpu = None
     parity = None
     if world == 1 and not args.no_cpu_baseline:
+        if all_cpus:
+            os.sched_setaffinity(0, all_cpus)
         threads = os.cpu_count() or 1
         probe = cpu_port_throughput(h_in_np, h_off_np, 8 << 20, threads)
         sample_bytes = int(min(nbytes, max(16 << 20, probe[1] / probe[3] * 12.0)))
@@ -283,7 +307,7 @@ def run_ours(args):
         "clocks": clocks,
         "host_cores": os.cpu_count(),
     }
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
 
 
 def main():
@@ -300,6 +324,12 @@ def main():
         run_reference(args)
     else:
         run_ours(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
 
 
 if __name__ == "__main__":

@@ -226,7 +226,7 @@ __device__ int merge_group(const jtk_tables &T, const uint8_t *p, int n, int32_t
 /* ---------------------------------------------------------------------------------------------
  * kernel 1: split + whole-piece lookup
  * ------------------------------------------------------------------------------------------- */
-__global__ void __launch_bounds__(JTK_NT, 2) jtk_split_lookup_kernel(const __grid_constant__ jtk_encode_args a) {
+__global__ void __launch_bounds__(JTK_NT, 4) jtk_split_lookup_kernel(const __grid_constant__ jtk_encode_args a) {
 	extern __shared__ __align__(16) uint8_t smem[];
 	uint8_t *sb = smem;
 	uint8_t *cls = sb + (JTK_REGION + 16);
@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(SNT) jtk_short_scatter_kernel(const __grid_con
 
 /* NSLOT = 16 / 32 / 64: pieces of 2..16 / 17..32 / 33..64 bytes; NSLOT * NTHREADS is constant (32 KiB of scratch) */
 template <int NSLOT, int NTHREADS>
-__global__ void __launch_bounds__(NTHREADS) jtk_merge_short_kernel(const __grid_constant__ jtk_encode_args a) {
+__global__ void __launch_bounds__(NTHREADS, 7) jtk_merge_short_kernel(const __grid_constant__ jtk_encode_args a) {
 	__shared__ int32_t s_scr[2 * NSLOT * NTHREADS]; /* tok / rk, slot k of thread t at k * NTHREADS + t (bank = thread) */
 	const jtk_tables &T = a.T;
 	const int tid = threadIdx.x, lane = tid & 31;
@@ -1138,7 +1138,7 @@ cudaError_t jtk_launch_tile_first_doc(const int64_t *doc_off, int64_t ndocs, int
 cudaError_t jtk_launch_sub_batch(const jtk_encode_args &a, int num_sms, cudaEvent_t k0, cudaEvent_t k1, cudaStream_t st) {
 	const int64_t nt = a.tile_end - a.tile_begin;
 	if (nt <= 0) return cudaSuccess;
-	int64_t grid = (int64_t) num_sms * 2;
+	int64_t grid = (int64_t) num_sms * 4;
 	if (grid > nt) grid = nt;
 	/* the table-probing kernels run with the hot tables pinned in L2 (persisting hits, streaming misses) */
 	cudaLaunchAttribute attr[1];

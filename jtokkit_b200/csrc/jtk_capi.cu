@@ -39,7 +39,7 @@ struct jtk_workspace {
 	/* sized for ntiles_cap tiles / long_cap long pieces */
 	int64_t ntiles_cap = 0, long_cap = 0;
 	int32_t *tile_first_doc = nullptr;
-	int32_t *tile_count = nullptr, *npieces = nullptr, *nslow = nullptr;
+	int32_t *tile_count = nullptr, *npieces = nullptr, *nslow = nullptr, *tile_slow_used = nullptr;
 	int64_t *tile_base = nullptr;
 	/* per sub-batch: piece records, merged-token staging, unresolved-piece lists */
 	int64_t sub_tiles = 0;
@@ -282,6 +282,7 @@ static void free_workspace(jtk_workspace *w) {
 	cudaFree(w->tile_count);
 	cudaFree(w->npieces);
 	cudaFree(w->nslow);
+	cudaFree(w->tile_slow_used);
 	cudaFree(w->tile_base);
 	cudaFree(w->rec);
 	cudaFree(w->slowtok);
@@ -396,9 +397,10 @@ static int ensure_ws_tiles(jtk_workspace *w, int64_t ntiles, int64_t long_cap) {
 		cudaFree(w->tile_count);
 		cudaFree(w->npieces);
 		cudaFree(w->nslow);
+		cudaFree(w->tile_slow_used);
 		cudaFree(w->tile_base);
 		cudaFree(w->tile_first_b);
-		w->tile_first_doc = w->tile_count = w->npieces = w->nslow = nullptr;
+		w->tile_first_doc = w->tile_count = w->npieces = w->nslow = w->tile_slow_used = nullptr;
 		w->tile_base = nullptr;
 		w->tile_first_b = nullptr;
 		w->ntiles_cap = 0;
@@ -407,6 +409,7 @@ static int ensure_ws_tiles(jtk_workspace *w, int64_t ntiles, int64_t long_cap) {
 		CUDA_TRY(cudaMalloc(&w->tile_count, sizeof(int32_t) * cap));
 		CUDA_TRY(cudaMalloc(&w->npieces, sizeof(int32_t) * cap));
 		CUDA_TRY(cudaMalloc(&w->nslow, sizeof(int32_t) * cap));
+		CUDA_TRY(cudaMalloc(&w->tile_slow_used, sizeof(int32_t) * cap));
 		CUDA_TRY(cudaMalloc(&w->tile_base, sizeof(int64_t) * (cap + 1)));
 		CUDA_TRY(cudaMalloc(&w->tile_first_b, sizeof(int64_t) * cap));
 		w->ntiles_cap = cap;
@@ -447,6 +450,7 @@ static void fill_args(jtk_encode_args &a, const jtk_device_state *ds, const jtk_
 	a.tile_first_doc = w->tile_first_doc;
 	a.npieces = w->npieces;
 	a.nslow = w->nslow;
+	a.tile_slow_used = w->tile_slow_used;
 	a.tile_count = w->tile_count;
 	a.tile_base = w->tile_base;
 	a.tile_first_b = w->tile_first_b;

@@ -42,13 +42,13 @@ static_assert(TC % NT == 0, "threads per CTA must divide the chunks per tile");
 
 /* piece records: a token id, or (id space is limited to >= JTK_REC_MIN_ID at registration) a payload */
 constexpr int32_t REC_BASE = (int32_t) 0x80000000;
-constexpr uint32_t REC_LONG = 1u << 24;
+constexpr uint32_t REC_LONG = 1u << 28; /* payload = REC_LONG | index into long_list; else (offset << 11) | (count - 1) */
 __device__ __forceinline__ bool rec_is_id(int32_t r) { return r >= JTK_REC_MIN_ID; }
 __device__ __forceinline__ int32_t rec_make(int s, int m) { return REC_BASE + (int32_t) (((uint32_t) s << 11) | (uint32_t) (m - 1)); }
 __device__ __forceinline__ uint32_t rec_payload(int32_t r) { return (uint32_t) (r - REC_BASE); }
 
 /* indices into the small shared "misc" array */
-enum { M_TILE = 0, M_NSLOW, M_RS, M_CARRY, M_HITS, M_NDEFER, M_WSUM = 16, M_HIST = 48 /* .. M_HIST + JTK_SHORT_PIECE */, M_WORDS = 128 };
+enum { M_TILE = 0, M_NSLOW, M_RS, M_CARRY, M_HITS, M_NDEFER, M_SLOWTOK, M_WSUM = 16, M_HIST = 48 /* .. M_HIST + JTK_SHORT_PIECE */, M_WORDS = 128 };
 static_assert(M_HIST + JTK_SHORT_PIECE + 1 <= M_WORDS, "misc too small");
 
 /* first set bit in [from, limit] of a bit array, or -1 */
@@ -266,6 +266,7 @@ __global__ void __launch_bounds__(JTK_NT, 4) jtk_split_lookup_kernel(const __gri
 			misc[M_NSLOW] = 0;
 			misc[M_HITS] = 0;
 			misc[M_NDEFER] = 0;
+			misc[M_SLOWTOK] = 0;
 		}
 		if (tid <= JTK_SHORT_PIECE) misc[M_HIST + tid] = 0;
 		__syncthreads();
@@ -407,8 +408,7 @@ __global__ void __launch_bounds__(JTK_NT, 4) jtk_split_lookup_kernel(const __gri
 						lp.flags = 0;
 						a.long_list[idx] = lp;
 					}
-					a.slowtok[lt * (long long) RECN + s] = (int32_t) idx;
-					out = REC_BASE + (int32_t) (REC_LONG | ((uint32_t) s << 11));
+					out = REC_BASE + (int32_t) (REC_LONG | (idx & 0x0FFFFFFFu));
 				} else {
 					const int n = e - r;
 					const uint8_t *p = sb + r;
@@ -440,13 +440,14 @@ __global__ void __launch_bounds__(JTK_NT, 4) jtk_split_lookup_kernel(const __gri
 								if (q1.x == ((a.memo_epoch << 8) | 2u) && (q1.y & 0xFFu) == (uint32_t) n && q0.x == key[0] && q0.y == key[1] && q0.z == key[2] &&
 								    q0.w == key[3]) {
 									const int cnt = (int) (q1.y >> 8);
-									int32_t *stok = a.slowtok + lt * (long long) RECN + s;
+									const int off = (int) atomicAdd(&misc[M_SLOWTOK], (uint32_t) cnt); /* dense area of the tile's slowtok slice */
+									int32_t *stok = a.slowtok + lt * (long long) RECN + off;
 									if (!(a.flags & JTK_COUNT_ONLY)) {
 										stok[0] = (int32_t) q1.z;
 										if (cnt > 1) stok[1] = (int32_t) q1.w;
 										for (int k = 2; k < cnt; k++) stok[k] = me->tok[k];
 									}
-									out = rec_make(s, cnt);
+									out = rec_make(off, cnt);
 									hits += cnt;
 									memo_hit = true;
 								}
@@ -484,6 +485,7 @@ __global__ void __launch_bounds__(JTK_NT, 4) jtk_split_lookup_kernel(const __gri
 		if (tid == 0) {
 			a.nslow[tile] = (int32_t) misc[M_NSLOW];
 			a.tile_count[tile] = (int32_t) misc[M_HITS];
+			a.tile_slow_used[tile] = (int32_t) misc[M_SLOWTOK];
 		}
 		if (tid <= JTK_SHORT_PIECE && misc[M_HIST + tid]) atomicAdd(&a.hdr->short_cnt[tid], misc[M_HIST + tid]);
 	}
@@ -561,11 +563,12 @@ __global__ void __launch_bounds__(NTHREADS, 7) jtk_merge_short_kernel(const __gr
 			bool unk = false;
 			const int cnt = NSLOT <= 32 ? jtk_merge_short_t<uint32_t>(T, a.bytes + tb + s, n, tk, rk, NTHREADS, &unk)
 			                            : jtk_merge_short_t<uint64_t>(T, a.bytes + tb + s, n, tk, rk, NTHREADS, &unk);
+			const int off = atomicAdd(&a.tile_slow_used[a.tile_begin + lt], cnt); /* dense area of the tile's slowtok slice */
 			if (write_tok) {
-				int32_t *stok = a.slowtok + lt * (long long) RECN + s;
+				int32_t *stok = a.slowtok + lt * (long long) RECN + off;
 				for (int k = 0; k < cnt; k++) stok[k] = tk[k * NTHREADS];
 			}
-			rec[q] = rec_make(s, cnt);
+			rec[q] = rec_make(off, cnt);
 			atomicAdd(&a.tile_count[a.tile_begin + lt], cnt);
 			if (unk) flag_doc(a, tb + s, JTK_DOC_UNKNOWN_BYTES);
 			if (NSLOT == 16 && a.memo && !unk && cnt <= JTK_MEMO_MAX_TOKENS) { /* remember the result for later occurrences in this call */
@@ -622,13 +625,16 @@ __global__ void __launch_bounds__(GNTM) jtk_merge_medium_kernel(const __grid_con
 			bool unk = false;
 			const int cnt = merge_group<3>(T, a.bytes + tb + s, n, tk, rk, &unk);
 			__syncwarp(gmask);
+			int off = 0;
+			if (gl == 0) off = atomicAdd(&a.tile_slow_used[a.tile_begin + lt], cnt);
+			off = __shfl_sync(gmask, off, g * 8);
 			if (write_tok) {
-				int32_t *stok = a.slowtok + lt * (long long) RECN + s;
+				int32_t *stok = a.slowtok + lt * (long long) RECN + off;
 				for (int k = gl; k < cnt; k += 8) stok[k] = tk[k];
 			}
 			__syncwarp(gmask);
 			if (gl == 0) {
-				rec[q] = rec_make(s, cnt);
+				rec[q] = rec_make(off, cnt);
 				atomicAdd(&a.tile_count[a.tile_begin + lt], cnt);
 				if (unk) flag_doc(a, tb + s, JTK_DOC_UNKNOWN_BYTES);
 			}
@@ -653,13 +659,16 @@ __global__ void __launch_bounds__(GNTM) jtk_merge_medium_kernel(const __grid_con
 			bool unk = false;
 			const int cnt = merge_group<5>(T, a.bytes + tb + s, n, wtok, wrk, &unk);
 			__syncwarp();
+			int off = 0;
+			if (lane == 0) off = atomicAdd(&a.tile_slow_used[a.tile_begin + lt], cnt);
+			off = __shfl_sync(0xFFFFFFFFu, off, 0);
 			if (write_tok) {
-				int32_t *stok = a.slowtok + lt * (long long) RECN + s;
+				int32_t *stok = a.slowtok + lt * (long long) RECN + off;
 				for (int k = lane; k < cnt; k += 32) stok[k] = wtok[k];
 			}
 			__syncwarp();
 			if (lane == 0) {
-				rec[q] = rec_make(s, cnt);
+				rec[q] = rec_make(off, cnt);
 				atomicAdd(&a.tile_count[a.tile_begin + lt], cnt);
 				if (unk) flag_doc(a, tb + s, JTK_DOC_UNKNOWN_BYTES);
 			}
@@ -762,11 +771,11 @@ __global__ void __launch_bounds__(GNT) jtk_gather_kernel(const __grid_constant__
 					s_tok[excl] = r[j];
 				} else {
 					const uint32_t pl = rec_payload(r[j]);
-					const int s = (int) ((pl >> 11) & 0x1FFFu);
 					if (pl & REC_LONG) {
-						a.long_list[stok[s]].insert_at = base + excl;
+						a.long_list[pl & 0x0FFFFFFFu].insert_at = base + excl;
 					} else if (write_ids) {
-						for (int k = 0; k < cnt[j]; k++) s_tok[excl + k] = stok[s + k];
+						const int off = (int) ((pl >> 11) & 0x3FFFu); /* dense area of the tile's slowtok slice */
+						for (int k = 0; k < cnt[j]; k++) s_tok[excl + k] = stok[off + k];
 					}
 				}
 				excl += cnt[j];

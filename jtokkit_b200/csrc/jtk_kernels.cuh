@@ -58,11 +58,12 @@ struct jtk_encode_args {
 	int32_t *npieces;      /* pieces that start in the tile */
 	int32_t *nslow;        /* of those, pieces the whole-piece lookup did not resolve */
 	int32_t *tile_count;   /* tokens produced by the tile */
+	int32_t *tile_slow_used; /* tokens in the dense front part of the tile's slowtok slice */
 	int64_t *tile_base;    /* ntiles + 1: exclusive scan of tile_count */
 	int64_t *tile_first_b; /* first piece start in the tile (global position) or -1 */
 	/* per tile of the sub-batch (index tile - tile_begin) */
 	int32_t *rec;          /* JTK_RECN per tile: one record per piece, in order */
-	int32_t *slowtok;      /* JTK_RECN per tile: tokens of merged pieces at the piece's tile-local byte position */
+	int32_t *slowtok;      /* JTK_RECN per tile: tokens of merged / memoised pieces, densely packed from the front (records hold the offset) */
 	uint16_t *slowq;       /* JTK_QCAP per tile: piece indices of the unresolved short pieces (<= JTK_SHORT_PIECE bytes) */
 	uint32_t *shortlist;   /* JTK_QCAP per tile (one list for the sub-batch): unresolved short pieces sorted by length */
 	uint32_t *med8;        /* JTK_MED8_PER_TILE per tile: (tile index << 14 | piece index) of unresolved pieces of 33..256 bytes */

@@ -266,7 +266,7 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "tile_kernel_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            traffic = json.load(f).get("dram_bytes_per_step")  # ncu --set full capture, all launches of the kernel in one step
 
     # ---- CPU baseline on a bounded sample of the same corpus (rank 0, N=1 only) + parity of that sample
     cpu = None

@@ -1,0 +1,13 @@
+#!/bin/bash
+# Run under gpurun on a B200: the bench, then the ncu launch list and one `--set full` capture of the dominant kernel for
+# the very same command (B200_PROFILING.md recipe).  Outputs land in gpurun_out/; tools/summarise_profiles.py turns them into
+# the tracked files under profiles/.
+set -u
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r1.json 2> gpurun_out/bench_r1.err; echo "bench rc=$?"
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r1_reference.json 2> gpurun_out/bench_r1_reference.err; echo "reference rc=$?"
+$CMD > gpurun_out/r1_plain.log 2>&1 || { echo "plain run failed"; exit 1; }
+# launches of the two timed steps (skip: 3 warm-up steps x launches per step; the bench prints launches per step)
+LPS=$(python -c "import json;print(json.load(open('gpurun_out/bench_r1.json'))['roofline']['launches_per_step'])")
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:jtk_ -s $((3 * LPS)) -c $((2 * LPS)) --csv --log-file gpurun_out/r1_launches.csv $CMD > gpurun_out/r1_ncu1.log 2>&1; echo "ncu list rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:jtk_split_lookup -s 28 -c 2 -o gpurun_out/r1_split_lookup $CMD > gpurun_out/r1_ncu2.log 2>&1; echo "ncu full rc=$?"

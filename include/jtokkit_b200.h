@@ -33,6 +33,7 @@ extern "C" {
 #define JTK_DOC_HAS_SPECIAL 1   /* text.contains(specialToken): UnsupportedOperationException, GptBytePairEncoding.java:52-56 */
 #define JTK_DOC_UNKNOWN_BYTES 2 /* a final part is not in the vocabulary: IllegalArgumentException, TokenEncoder.java:64-71 */
 #define JTK_DOC_UNKNOWN_ID 4    /* decode: IllegalArgumentException("Unknown token for decoding"), GptBytePairEncoding.java:313 */
+#define JTK_DOC_PATTERN_STACK 8 /* general split pattern only: the backtracking stack overflowed (java.util.regex: StackOverflowError); the document has no ids */
 
 /* ---- encode flags ---------------------------------------------------------------------------- */
 #define JTK_ENCODE_ORDINARY 0u /* encodeOrdinary: GptBytePairEncoding.java:61-64,71-103 */

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("JTK_LIB", os.path.join(HERE, "libjtokkit_b200.so"))  # JTK_LIB: development override for A/B builds
 
 JTK_OK, JTK_E_ARG, JTK_E_CUDA, JTK_E_PATTERN_UNSUPPORTED, JTK_E_NOMEM, JTK_E_CAPACITY = 0, -1, -2, -3, -4, -5
-DOC_OK, DOC_HAS_SPECIAL, DOC_UNKNOWN_BYTES, DOC_UNKNOWN_ID = 0, 1, 2, 4
+DOC_OK, DOC_HAS_SPECIAL, DOC_UNKNOWN_BYTES, DOC_UNKNOWN_ID, DOC_PATTERN_STACK = 0, 1, 2, 4, 8
 ENCODE_ORDINARY, CHECK_SPECIAL, COUNT_ONLY, TIME_KERNEL = 0, 1, 2, 0x100
 RE_CASE_INSENSITIVE, RE_UNICODE_CASE, RE_UNICODE_CHARACTER_CLASS = 0x02, 0x40, 0x100
 

@@ -364,6 +364,9 @@ class Encoding:
             raise NotImplementedError("Encoding special tokens is not supported yet.")  # UnsupportedOperationException
         if status.size and (status & _capi.DOC_UNKNOWN_BYTES).any():
             raise ValueError("Unknown token for encoding")  # IllegalArgumentException, TokenEncoder.java:67
+        if status.size and (status & _capi.DOC_PATTERN_STACK).any():
+            # general split patterns only: java.util.regex would die with StackOverflowError on such a text
+            raise RecursionError("split pattern exhausted the device backtracking stack")
 
     # ------------------------------------------------------------------ api/Encoding.java
     def encode(self, text, max_tokens=None):

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "jtk_kernels.cuh"
+#include "jtk_regex.h"
 #include "jtk_tables.h"
 
 /* ------------------------------------------------------------------ error plumbing */
@@ -38,6 +39,10 @@ extern "C" const char *jtk_version(void) {
 struct jtk_workspace {
 	/* sized for ntiles_cap tiles / long_cap long pieces */
 	int64_t ntiles_cap = 0, long_cap = 0;
+	/* general split patterns: start + gap bit arrays (2 * rx_words_cap words) and the backtrack stacks */
+	uint32_t *rx_bits = nullptr;
+	int64_t rx_words_cap = 0;
+	void *rx_stacks = nullptr;
 	int32_t *tile_first_doc = nullptr;
 	int32_t *tile_count = nullptr, *npieces = nullptr, *nslow = nullptr, *tile_slow_used = nullptr;
 	int64_t *tile_base = nullptr;
@@ -148,6 +153,7 @@ static int init_device(jtk_encoding *e, int device) {
 	const size_t hot_bytes = ar.total;
 	const size_t o_tokb = ar.add(h.tok_bytes), o_toko = ar.add(h.tok_off), o_spb = ar.add(h.special_bytes), o_spo = ar.add(h.special_off);
 	const size_t o_deck = ar.add(h.dec_keys), o_decb = ar.add(h.dec_bytes), o_deco = ar.add(h.dec_off);
+	const size_t o_rxi = ar.add(h.rx_inst), o_rxs = ar.add(h.rx_sets), o_rxr = ar.add(h.rx_ranges);
 	uint8_t *base = nullptr;
 	CUDA_TRY(cudaMalloc(&base, ar.total));
 	ds->allocs.push_back(base);
@@ -169,6 +175,10 @@ static int init_device(jtk_encoding *e, int device) {
 	T.dec_keys = reinterpret_cast<const uint32_t *>(base + o_deck);
 	T.dec_bytes = base + o_decb;
 	T.dec_off = reinterpret_cast<const uint32_t *>(base + o_deco);
+	T.rx_inst = base + o_rxi;
+	T.rx_sets = base + o_rxs;
+	T.rx_ranges = reinterpret_cast<const uint32_t *>(base + o_rxr);
+	T.rx_ninst = h.rx_ninst;
 	T.mask_a = h.mask_a;
 	T.mask_b = h.mask_b;
 	T.mask_p = h.mask_p;
@@ -293,6 +303,8 @@ static void free_workspace(jtk_workspace *w) {
 	for (cudaEvent_t ev : w->kev) cudaEventDestroy(ev);
 	cudaFree(w->tile_first_b);
 	cudaFree(w->long_list);
+	cudaFree(w->rx_bits);
+	cudaFree(w->rx_stacks);
 	cudaFree(w->hdr);
 	cudaFreeHost(w->hdr_host);
 	cudaFree(w->d_in);
@@ -560,6 +572,26 @@ static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspa
 	}
 	CUDA_TRY(cudaMemsetAsync(w->hdr, 0, sizeof(jtk_batch_header), st));
 	CUDA_TRY(jtk_launch_tile_first_doc(d_doc_off, ndocs, ntiles, w->tile_first_doc, st));
+	int general_launches = 0;
+	if (ds->T.pattern_kind == JTK_PAT_GENERAL && ntiles > 0) {
+		/* general pattern: piece / gap bits per document first (jtk_general_split_kernel), the tile kernels read them */
+		const int64_t words = (ntiles * (int64_t) JTK_TILE + JTK_REGION) / 32 + 2;
+		if (words > w->rx_words_cap) {
+			cudaFree(w->rx_bits);
+			w->rx_bits = nullptr;
+			w->rx_words_cap = 0;
+			CUDA_TRY(cudaMalloc(&w->rx_bits, sizeof(uint32_t) * 2 * (size_t) (words + words / 4)));
+			w->rx_words_cap = words + words / 4;
+		}
+		if (!w->rx_stacks) CUDA_TRY(cudaMalloc(&w->rx_stacks, sizeof(jtk_rx_frame) * (size_t) JTK_RX_STACK * JTK_RX_THREADS));
+		CUDA_TRY(cudaMemsetAsync(w->rx_bits, 0, sizeof(uint32_t) * 2 * (size_t) words, st));
+		a.rx_start = w->rx_bits;
+		a.rx_skip = w->rx_bits + words;
+		a.rx_words = words;
+		a.rx_stacks = w->rx_stacks;
+		CUDA_TRY(jtk_launch_general_split(a, st));
+		general_launches = 1;
+	}
 	const bool time_kernel = (flags & JTK_TIME_KERNEL) && sync_and_long;
 	/* sub-batches: a small first one (16 MiB) so that the piece memo is warm early, then full-size ones */
 	const int64_t sub = w->sub_tiles;
@@ -579,7 +611,7 @@ static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspa
 		CUDA_TRY(jtk_launch_sub_batch(a, ds->num_sms, time_kernel ? w->kev[(size_t) (2 * i)] : nullptr, time_kernel ? w->kev[(size_t) (2 * i + 1)] : nullptr, st));
 	}
 	CUDA_TRY(jtk_launch_finalize(a, st));
-	info->gpu_launches = (ntiles > 0 ? 1 : 0) + 9 * nsub + 1;
+	info->gpu_launches = (ntiles > 0 ? 1 : 0) + general_launches + 9 * nsub + 1;
 	CUDA_TRY(cudaMemcpyAsync(w->hdr_host, w->hdr, sizeof(jtk_batch_header), cudaMemcpyDeviceToHost, st));
 	if (!sync_and_long) return JTK_OK;
 	CUDA_TRY(cudaStreamSynchronize(st));

@@ -49,7 +49,8 @@ JTK_HD bool jtk_is_other(int c) { return c <= JTK_C_AP; }
 /* ---- split rule kinds ("compiled pattern") ---------------------------------------------------- */
 enum {
 	JTK_PAT_X50K = 1,  /* r50k_base / p50k_base / p50k_edit, EncodingFactory.java:63,77,91 */
-	JTK_PAT_CL100K = 2 /* cl100k_base, EncodingFactory.java:105 */
+	JTK_PAT_CL100K = 2, /* cl100k_base, EncodingFactory.java:105 */
+	JTK_PAT_GENERAL = 3 /* any other pattern: backtracking program (jtk_regex.h), one thread per document */
 };
 
 #define JTK_RANK_MAX 0x7fffffff                  /* Integer.MAX_VALUE sentinel, GptBytePairEncoding.java:208 */
@@ -130,6 +131,11 @@ struct jtk_tables {
 	uint32_t mask_d;
 	const uint8_t *dec_bytes;    /* ordinary tokens followed by special-token strings */
 	const uint32_t *dec_off;
+	/* JTK_PAT_GENERAL only: the compiled split program (jtk_regex.h: jtk_rx_inst / jtk_rx_set / code point ranges) */
+	const void *rx_inst;
+	const void *rx_sets;
+	const uint32_t *rx_ranges;
+	int32_t rx_ninst;
 };
 
 /* ---- hashing (identical on host and device) ---------------------------------------------------- */

@@ -24,6 +24,7 @@
 #include <cstring>
 
 #include "jtk_device.cuh"
+#include "jtk_regex.h"
 
 #ifndef JTK_DEFER_SLOW
 #define JTK_DEFER_SLOW 0 /* 1: process chunks that miss the ASCII fast paths in a dense second pass (measured slower: it serialises the slow chunks behind a barrier) */
@@ -43,6 +44,7 @@ static_assert(TC % NT == 0, "threads per CTA must divide the chunks per tile");
 /* piece records: a token id, or (id space is limited to >= JTK_REC_MIN_ID at registration) a payload */
 constexpr int32_t REC_BASE = (int32_t) 0x80000000;
 constexpr uint32_t REC_LONG = 1u << 28; /* payload = REC_LONG | index into long_list; else (offset << 11) | (count - 1) */
+constexpr uint32_t REC_SKIP = 1u << 29; /* general patterns: a gap between matches, no tokens */
 __device__ __forceinline__ bool rec_is_id(int32_t r) { return r >= JTK_REC_MIN_ID; }
 __device__ __forceinline__ int32_t rec_make(int s, int m) { return REC_BASE + (int32_t) (((uint32_t) s << 11) | (uint32_t) (m - 1)); }
 __device__ __forceinline__ uint32_t rec_payload(int32_t r) { return (uint32_t) (r - REC_BASE); }
@@ -226,6 +228,7 @@ __device__ int merge_group(const jtk_tables &T, const uint8_t *p, int n, int32_t
 /* ---------------------------------------------------------------------------------------------
  * kernel 1: split + whole-piece lookup
  * ------------------------------------------------------------------------------------------- */
+template <bool GENERAL>
 __global__ void __launch_bounds__(JTK_NT, 4) jtk_split_lookup_kernel(const __grid_constant__ jtk_encode_args a) {
 	extern __shared__ __align__(16) uint8_t smem[];
 	uint8_t *sb = smem;
@@ -279,13 +282,25 @@ __global__ void __launch_bounds__(JTK_NT, 4) jtk_split_lookup_kernel(const __gri
 		c.carry_n = 0;
 
 		/* ---- P1: stage bytes (16-byte loads), clear masks, mark document starts ---- */
+		const int64_t first_doc = a.tile_first_doc[tile];
+		if (GENERAL) {
+			/* general pattern: the piece bits were computed per document by jtk_general_split_kernel; dmask holds the gap bits */
+			const int64_t w0 = c.g0 / 32; /* g0 is a multiple of 32 (negative for the first tile) */
+			for (int w = tid; w < JTK_MASK_WORDS; w += NT) {
+				const int64_t gw = w0 + w;
+				const bool in = gw >= 0 && gw < a.rx_words;
+				bmask[w] = in ? a.rx_start[gw] : 0u;
+				dmask[w] = in ? a.rx_skip[gw] : 0u;
+			}
+			for (int ch = tid; ch <= JTK_REGION_CHUNKS; ch += NT) jtk_load_chunk(c, ch);
+			__syncthreads();
+		} else {
 		for (int w = tid; w < JTK_MASK_WORDS; w += NT) {
 			bmask[w] = 0;
 			dmask[w] = 0;
 		}
 		for (int ch = tid; ch <= JTK_REGION_CHUNKS; ch += NT) jtk_load_chunk(c, ch);
 		__syncthreads();
-		const int64_t first_doc = a.tile_first_doc[tile];
 		jtk_mark_docstarts(c, first_doc, tid, NT);
 		__syncthreads();
 		if (tid == 0) misc[M_RS] = (uint32_t) jtk_region_first(c);
@@ -325,6 +340,7 @@ __global__ void __launch_bounds__(JTK_NT, 4) jtk_split_lookup_kernel(const __gri
 #else
 		for (int ch = BH / 16 + tid; ch < JTK_REGION_CHUNKS; ch += NT) reinterpret_cast<uint16_t *>(bmask)[ch] = (uint16_t) jtk_boundary_chunk(c, ch);
 #endif
+		} /* !GENERAL */
 		if (check_special) {
 			for (int ch = tid; ch < TC; ch += NT) {
 				const int r0 = BH + ch * 16;
@@ -361,8 +377,10 @@ __global__ void __launch_bounds__(JTK_NT, 4) jtk_split_lookup_kernel(const __gri
 			else if (gbase + 16 > a.total) m &= (1u << (int) (a.total - gbase)) - 1u;
 			bits[j] = m;
 			mycount += __popc(m);
-			if (a.piece_flags)
-				for (int i = 0; i < 16 && gbase + i < a.total; i++) a.piece_flags[gbase + i] = (m >> i) & 1u;
+			if (a.piece_flags) {
+				const uint32_t real = GENERAL ? m & ~(uint32_t) reinterpret_cast<const uint16_t *>(dmask)[BH / 16 + ch] : m; /* gaps are not pieces */
+				for (int i = 0; i < 16 && gbase + i < a.total; i++) a.piece_flags[gbase + i] = (real >> i) & 1u;
+			}
 		}
 		int npieces;
 		int base = block_exclusive_scan<NT>(mycount, reinterpret_cast<int *>(misc + M_WSUM), &npieces);
@@ -394,7 +412,9 @@ __global__ void __launch_bounds__(JTK_NT, 4) jtk_split_lookup_kernel(const __gri
 				int e = (q + 1 < npieces) ? (int) plist[q + 1] : next_bit(bmask, r + 1, r + JTK_LONG_PIECE);
 				if (e >= 0 && e - r > JTK_LONG_PIECE) e = -1;
 				int32_t out;
-				if (e < 0) { /* longer than JTK_LONG_PIECE: deferred to the long-piece kernels */
+				if (GENERAL && ((dmask[r >> 5] >> (r & 31)) & 1u)) {
+					out = REC_BASE + (int32_t) REC_SKIP;
+				} else if (e < 0) { /* longer than JTK_LONG_PIECE: deferred to the long-piece kernels */
 					const unsigned idx = atomicAdd(&a.hdr->n_long, 1u);
 					if ((int64_t) idx < a.long_cap) {
 						jtk_long_piece lp;
@@ -488,6 +508,28 @@ __global__ void __launch_bounds__(JTK_NT, 4) jtk_split_lookup_kernel(const __gri
 			a.tile_slow_used[tile] = (int32_t) misc[M_SLOWTOK];
 		}
 		if (tid <= JTK_SHORT_PIECE && misc[M_HIST + tid]) atomicAdd(&a.hdr->short_cnt[tid], misc[M_HIST + tid]);
+	}
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * kernel 0 (general patterns only): Matcher.find() over every document with the compiled backtracking program
+ * (jtk_regex.h).  Regex search is sequential within a document, so the unit of parallelism is the document: a thread
+ * takes documents from a ticket counter and ORs their piece / gap bits into the two global bit arrays.
+ * ------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(128) jtk_general_split_kernel(const __grid_constant__ jtk_encode_args a) {
+	const jtk_rx_program P = jtk_rx_program_of(a.T);
+	jtk_rx_frame *st = static_cast<jtk_rx_frame *>(a.rx_stacks) + (size_t) (blockIdx.x * blockDim.x + threadIdx.x) * JTK_RX_STACK;
+	if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(a.rx_start + (a.total >> 5), 1u << (a.total & 31)); /* the end of the input ends the last piece */
+	for (;;) {
+		const int64_t d = (int64_t) atomicAdd(&a.hdr->rx_ticket, 1u);
+		if (d >= a.ndocs) break;
+		const int64_t lo = a.doc_off[d], n = a.doc_off[d + 1];
+		bool overflow = false;
+		atomicOr(a.rx_start + (lo >> 5), 1u << (lo & 31));
+		jtk_rx_split_document(
+		    P, a.T, a.bytes, lo, n, st, JTK_RX_STACK, [&](int64_t g) { atomicOr(a.rx_start + (g >> 5), 1u << (g & 31)); },
+		    [&](int64_t g) { atomicOr(a.rx_skip + (g >> 5), 1u << (g & 31)); }, &overflow);
+		if (overflow && a.doc_status) atomicOr(a.doc_status + d, JTK_DOC_PATTERN_STACK);
 	}
 }
 
@@ -756,7 +798,7 @@ __global__ void __launch_bounds__(GNT) jtk_gather_kernel(const __grid_constant__
 			if (q < P) {
 				r[j] = rec[q];
 				if (rec_is_id(r[j])) cnt[j] = 1;
-				else if (!(rec_payload(r[j]) & REC_LONG)) cnt[j] = (int) (rec_payload(r[j]) & 0x7FFu) + 1;
+				else if (!(rec_payload(r[j]) & (REC_LONG | REC_SKIP))) cnt[j] = (int) (rec_payload(r[j]) & 0x7FFu) + 1;
 			}
 			mine += cnt[j];
 		}
@@ -773,7 +815,7 @@ __global__ void __launch_bounds__(GNT) jtk_gather_kernel(const __grid_constant__
 					const uint32_t pl = rec_payload(r[j]);
 					if (pl & REC_LONG) {
 						a.long_list[pl & 0x0FFFFFFFu].insert_at = base + excl;
-					} else if (write_ids) {
+					} else if (write_ids && !(pl & REC_SKIP)) {
 						const int off = (int) ((pl >> 11) & 0x3FFFu); /* dense area of the tile's slowtok slice */
 						for (int k = 0; k < cnt[j]; k++) s_tok[excl + k] = stok[off + k];
 					}
@@ -1132,7 +1174,9 @@ __global__ void jtk_long_fix_offsets_kernel(const jtk_long_piece *list, const in
  * launch wrappers
  * ============================================================================================= */
 cudaError_t jtk_encode_kernel_setup() {
-	cudaError_t e = cudaFuncSetAttribute(jtk_split_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JTK_SMEM_BYTES);
+	cudaError_t e = cudaFuncSetAttribute(jtk_split_lookup_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, JTK_SMEM_BYTES);
+	if (e != cudaSuccess) return e;
+	e = cudaFuncSetAttribute(jtk_split_lookup_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, JTK_SMEM_BYTES);
 	if (e != cudaSuccess) return e;
 	return cudaFuncSetAttribute(jtk_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GATHER_SMEM);
 }
@@ -1170,7 +1214,8 @@ cudaError_t jtk_launch_sub_batch(const jtk_encode_args &a, int num_sms, cudaEven
 	cfg.gridDim = dim3((unsigned) grid);
 	cfg.blockDim = dim3(JTK_NT);
 	cfg.dynamicSmemBytes = JTK_SMEM_BYTES;
-	cudaLaunchKernelEx(&cfg, jtk_split_lookup_kernel, a);
+	if (a.T.pattern_kind == JTK_PAT_GENERAL) cudaLaunchKernelEx(&cfg, jtk_split_lookup_kernel<true>, a);
+	else cudaLaunchKernelEx(&cfg, jtk_split_lookup_kernel<false>, a);
 	if (k1) cudaEventRecord(k1, st);
 	cfg.dynamicSmemBytes = 0;
 	jtk_short_offsets_kernel<<<1, 32, 0, st>>>(a);
@@ -1189,6 +1234,14 @@ cudaError_t jtk_launch_sub_batch(const jtk_encode_args &a, int num_sms, cudaEven
 	cudaLaunchKernelEx(&cfg, jtk_merge_medium_kernel, a);
 	jtk_tile_scan_kernel<<<1, 1024, 0, st>>>(a);
 	jtk_gather_kernel<<<(unsigned) nt, GNT, GATHER_SMEM, st>>>(a);
+	return cudaGetLastError();
+}
+
+cudaError_t jtk_launch_general_split(const jtk_encode_args &a, cudaStream_t st) {
+	int64_t blocks = (a.ndocs + 127) / 128;
+	if (blocks > JTK_RX_THREADS / 128) blocks = JTK_RX_THREADS / 128;
+	if (blocks < 1) blocks = 1;
+	jtk_general_split_kernel<<<(unsigned) blocks, 128, 0, st>>>(a);
 	return cudaGetLastError();
 }
 

@@ -34,7 +34,7 @@ struct jtk_batch_header {
 	unsigned int short_base[JTK_SHORT_PIECE + 2]; /* exclusive scan of short_cnt */
 	unsigned int short_cur[JTK_SHORT_PIECE + 2];  /* scatter cursors */
 	unsigned int short_next[4];                   /* work counters of the three jtk_merge_short_kernel launches */
-	unsigned int pad;
+	unsigned int rx_ticket; /* document counter of jtk_general_split_kernel */
 };
 
 #define JTK_RECN (JTK_TILE + JTK_FWD_HALO) /* per-tile slots of rec / slowtok: pieces + unresolved pieces <= JTK_RECN */
@@ -79,6 +79,11 @@ struct jtk_encode_args {
 	uint8_t *piece_flags;  /* debug: one byte per input byte, 1 where a piece starts (nullable) */
 	jtk_memo_entry *memo;  /* per-call piece memo (nullable) */
 	uint32_t memo_mask, memo_epoch;
+	/* JTK_PAT_GENERAL only: one bit per input byte (word g / 32, bit g % 32), written by jtk_general_split_kernel:
+	 * piece starts, and which of those pieces are gaps (text the pattern did not match: no tokens) */
+	uint32_t *rx_start, *rx_skip;
+	int64_t rx_words;
+	void *rx_stacks;       /* JTK_RX_THREADS backtrack stacks of JTK_RX_STACK frames */
 	/* host side only: L2 access-policy window over the hot tables (0 bytes = none) */
 	const void *l2_base;
 	size_t l2_bytes;
@@ -90,6 +95,9 @@ cudaError_t jtk_launch_tile_first_doc(const int64_t *doc_off, int64_t ndocs, int
 /* the four kernels of one sub-batch; k0/k1 (nullable) bracket the split+lookup kernel */
 cudaError_t jtk_launch_sub_batch(const jtk_encode_args &a, int num_sms, cudaEvent_t k0, cudaEvent_t k1, cudaStream_t st);
 cudaError_t jtk_launch_finalize(const jtk_encode_args &a, cudaStream_t st);
+/* JTK_PAT_GENERAL: runs the split program over every document (one thread per document) before the sub-batches; rx_start / rx_skip must be zeroed */
+#define JTK_RX_THREADS (148 * 128)
+cudaError_t jtk_launch_general_split(const jtk_encode_args &a, cudaStream_t st);
 cudaError_t jtk_encode_kernel_setup();
 
 /* long-piece path */

@@ -1,0 +1,612 @@
+/* Compiler for general split patterns: java.util.regex subset -> jtk_rx_inst program (see jtk_regex.h). */
+#include "jtk_regex_compile.h"
+
+#include <algorithm>
+#include <cstring>
+#include <memory>
+
+namespace {
+
+enum { N_SET, N_CAT, N_ALT, N_REP, N_LOOK, N_EMPTY, N_BOL, N_EOL };
+
+struct node {
+	int type = N_EMPTY;
+	int set = -1;                          /* N_SET */
+	std::vector<std::unique_ptr<node>> kids; /* N_CAT, N_ALT */
+	std::unique_ptr<node> sub;             /* N_REP, N_LOOK */
+	int min = 0, max = 0, mode = 0;        /* N_REP */
+	bool neg = false;                      /* N_LOOK */
+};
+
+struct set_builder {
+	bool neg = false, dot = false;
+	std::vector<std::pair<uint32_t, uint32_t>> ranges;
+	uint32_t flags = 0;
+	bool ci = false;
+};
+
+struct parser {
+	std::vector<uint32_t> p;
+	size_t i = 0;
+	int flags;
+	std::string err;
+	jtk_rx_compiled *out;
+	int look_depth = 0, max_look_depth = 0;
+
+	bool failed() const { return !err.empty(); }
+	void fail(const std::string &m) {
+		if (err.empty()) err = m + " (at pattern index " + std::to_string(i) + ")";
+	}
+	int peek() const { return i < p.size() ? (int) p[i] : -1; }
+	bool eat(int c) {
+		if (peek() == c) {
+			i++;
+			return true;
+		}
+		return false;
+	}
+
+	int finish_set(set_builder &b) {
+		/* case-insensitive: close the ranges under ASCII case folding (+ U+017F / U+212A with UNICODE_CASE) */
+		const bool ucase = (flags & (JTK_RE_UNICODE_CASE | JTK_RE_UNICODE_CHARACTER_CLASS)) != 0;
+		if (b.ci) {
+			std::vector<std::pair<uint32_t, uint32_t>> extra;
+			for (auto &r : b.ranges) {
+				for (uint32_t c = std::max<uint32_t>(r.first, 'a'); c <= std::min<uint32_t>(r.second, 'z'); c++) extra.emplace_back(c - 32, c - 32);
+				for (uint32_t c = std::max<uint32_t>(r.first, 'A'); c <= std::min<uint32_t>(r.second, 'Z'); c++) extra.emplace_back(c + 32, c + 32);
+				if (ucase) {
+					if ((r.first <= 's' && 's' <= r.second) || (r.first <= 'S' && 'S' <= r.second)) extra.emplace_back(0x17F, 0x17F);
+					if ((r.first <= 'k' && 'k' <= r.second) || (r.first <= 'K' && 'K' <= r.second)) extra.emplace_back(0x212A, 0x212A);
+					if (r.first <= 0x17F && 0x17F <= r.second) {
+						extra.emplace_back('s', 's');
+						extra.emplace_back('S', 'S');
+					}
+					if (r.first <= 0x212A && 0x212A <= r.second) {
+						extra.emplace_back('k', 'k');
+						extra.emplace_back('K', 'K');
+					}
+				}
+				if (ucase && r.second >= 0x80 && !(r.first == r.second && (r.first == 0x17F || r.first == 0x212A))) {
+					fail("UNICODE_CASE matching of non-ASCII characters is not supported");
+					return 0;
+				}
+			}
+			b.ranges.insert(b.ranges.end(), extra.begin(), extra.end());
+		}
+		std::sort(b.ranges.begin(), b.ranges.end());
+		std::vector<std::pair<uint32_t, uint32_t>> merged;
+		for (auto &r : b.ranges) {
+			if (!merged.empty() && r.first <= merged.back().second + 1) merged.back().second = std::max(merged.back().second, r.second);
+			else merged.push_back(r);
+		}
+		jtk_rx_set s;
+		memset(&s, 0, sizeof(s));
+		s.flags = b.flags | (b.neg ? JTK_RX_NEG : 0) | (b.dot ? JTK_RX_DOT : 0);
+		const bool ucc = (flags & JTK_RE_UNICODE_CHARACTER_CLASS) != 0;
+		for (uint32_t c = 0; c < 128; c++) {
+			bool in = false;
+			for (auto &r : merged)
+				if (c >= r.first && c <= r.second) in = true;
+			const bool isl = (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z');
+			const bool isn = c >= '0' && c <= '9';
+			const bool iss = c == ' ' || (c >= 9 && c <= 13);
+			(void) ucc;
+			in = in || ((s.flags & JTK_RX_HAS_L) && isl) || ((s.flags & JTK_RX_HAS_N) && isn) || ((s.flags & JTK_RX_HAS_S) && iss) ||
+			     ((s.flags & JTK_RX_HAS_NOT_L) && !isl) || ((s.flags & JTK_RX_HAS_NOT_N) && !isn) || ((s.flags & JTK_RX_HAS_NOT_S) && !iss);
+			if (in) s.ascii[c >> 5] |= 1u << (c & 31);
+		}
+		s.range_begin = (int32_t) (out->ranges.size() / 2);
+		for (auto &r : merged)
+			if (r.second >= 128) {
+				out->ranges.push_back(std::max<uint32_t>(r.first, 128));
+				out->ranges.push_back(r.second);
+				s.range_count++;
+			}
+		out->sets.push_back(s);
+		return (int) out->sets.size() - 1;
+	}
+
+	static int hexval(int c) {
+		if (c >= '0' && c <= '9') return c - '0';
+		if (c >= 'a' && c <= 'f') return c - 'a' + 10;
+		if (c >= 'A' && c <= 'F') return c - 'A' + 10;
+		return -1;
+	}
+
+	/* after a backslash: adds to the set or returns a literal (>= 0) */
+	int escape(set_builder &b) {
+		int c = peek();
+		if (c < 0) {
+			fail("dangling backslash");
+			return -1;
+		}
+		i++;
+		const bool ucc = (flags & JTK_RE_UNICODE_CHARACTER_CLASS) != 0;
+		switch (c) {
+		case 'r': return '\r';
+		case 'n': return '\n';
+		case 't': return '\t';
+		case 'f': return '\f';
+		case 'a': return 7;
+		case 'e': return 27;
+		case 's': /* [ \t\n\x0B\f\r], or White_Space under UNICODE_CHARACTER_CLASS */
+			if (ucc) b.flags |= JTK_RX_HAS_S;
+			else {
+				b.ranges.emplace_back(9, 13);
+				b.ranges.emplace_back(' ', ' ');
+			}
+			return -1;
+		case 'S':
+			if (ucc) b.flags |= JTK_RX_HAS_NOT_S;
+			else {
+				b.ranges.emplace_back(0, 8);
+				b.ranges.emplace_back(14, 31);
+				b.ranges.emplace_back(33, 0x10FFFF);
+			}
+			return -1;
+		case 'd':
+			if (ucc) fail("\\d under UNICODE_CHARACTER_CLASS is not supported");
+			b.ranges.emplace_back('0', '9');
+			return -1;
+		case 'w':
+			if (ucc) fail("\\w under UNICODE_CHARACTER_CLASS is not supported");
+			b.ranges.emplace_back('0', '9');
+			b.ranges.emplace_back('a', 'z');
+			b.ranges.emplace_back('A', 'Z');
+			b.ranges.emplace_back('_', '_');
+			return -1;
+		case 'D':
+		case 'W': fail("\\D and \\W are not supported"); return -1;
+		case 'x': {
+			int v = 0;
+			if (eat('{')) {
+				int k = 0;
+				while (hexval(peek()) >= 0) {
+					v = v * 16 + hexval(peek());
+					i++;
+					k++;
+				}
+				if (!k || !eat('}') || v > 0x10FFFF) fail("bad \\x{...} escape");
+			} else {
+				for (int k = 0; k < 2; k++) {
+					if (hexval(peek()) < 0) {
+						fail("bad \\xhh escape");
+						return -1;
+					}
+					v = v * 16 + hexval(peek());
+					i++;
+				}
+			}
+			return v;
+		}
+		case 'u': {
+			int v = 0;
+			for (int k = 0; k < 4; k++) {
+				if (hexval(peek()) < 0) {
+					fail("bad \\uhhhh escape");
+					return -1;
+				}
+				v = v * 16 + hexval(peek());
+				i++;
+			}
+			return v;
+		}
+		case 'p':
+		case 'P': {
+			bool neg = c == 'P';
+			std::string name;
+			if (eat('{')) {
+				if (eat('^')) neg = !neg;
+				while (peek() >= 0 && peek() != '}') name.push_back((char) p[i++]);
+				if (!eat('}')) fail("unterminated \\p{...}");
+			} else if (peek() >= 0) {
+				name.push_back((char) p[i++]);
+			}
+			if (name == "L" || name == "IsL" || name == "gc=L" || name == "general_category=L") b.flags |= neg ? JTK_RX_HAS_NOT_L : JTK_RX_HAS_L;
+			else if (name == "N" || name == "IsN" || name == "gc=N" || name == "general_category=N") b.flags |= neg ? JTK_RX_HAS_NOT_N : JTK_RX_HAS_N;
+			else fail("unsupported \\p{...} property (only L and N are supported)");
+			return -1;
+		}
+		default:
+			if ((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || (c >= '0' && c <= '9')) {
+				fail("unsupported escape sequence");
+				return -1;
+			}
+			return c;
+		}
+	}
+
+	std::unique_ptr<node> set_node(set_builder &b) {
+		auto nd = std::make_unique<node>();
+		nd->type = N_SET;
+		nd->set = finish_set(b);
+		return nd;
+	}
+
+	std::unique_ptr<node> parse_class(bool ci) {
+		set_builder b;
+		b.ci = ci;
+		if (eat('^')) b.neg = true;
+		bool first = true;
+		for (;;) {
+			int c = peek();
+			if (c < 0) {
+				fail("unterminated character class");
+				break;
+			}
+			if (c == ']' && !first) {
+				i++;
+				break;
+			}
+			first = false;
+			if (c == '[') {
+				fail("nested character classes are not supported");
+				break;
+			}
+			if (c == '&' && i + 1 < p.size() && p[i + 1] == '&') {
+				fail("class intersection is not supported");
+				break;
+			}
+			i++;
+			int lit = c;
+			if (c == '\\') {
+				lit = escape(b);
+				if (failed()) break;
+				if (lit < 0) continue;
+			}
+			if (peek() == '-' && i + 1 < p.size() && p[i + 1] != ']') {
+				i++;
+				int hi = peek();
+				i++;
+				if (hi == '\\') {
+					set_builder tmp;
+					hi = escape(tmp);
+					if (hi < 0) fail("bad range end in character class");
+				}
+				if (hi < lit) fail("illegal character range");
+				if (failed()) break;
+				b.ranges.emplace_back((uint32_t) lit, (uint32_t) hi);
+			} else {
+				b.ranges.emplace_back((uint32_t) lit, (uint32_t) lit);
+			}
+		}
+		return set_node(b);
+	}
+
+	std::unique_ptr<node> parse_atom(bool &ci) {
+		int c = peek();
+		if (c == '(') {
+			i++;
+			bool sub_ci = ci;
+			if (eat('?')) {
+				if (eat(':')) {
+				} else if (peek() == '!' || peek() == '=') {
+					const bool neg = peek() == '!';
+					i++;
+					auto lk = std::make_unique<node>();
+					lk->type = N_LOOK;
+					lk->neg = neg;
+					look_depth++;
+					max_look_depth = std::max(max_look_depth, look_depth);
+					lk->sub = parse_alt(sub_ci);
+					look_depth--;
+					if (!eat(')')) fail("missing ) after look-ahead");
+					return lk;
+				} else if (peek() == '<') {
+					fail("look-behind / named groups are not supported");
+					return std::make_unique<node>();
+				} else {
+					bool on = true, seen = false;
+					while (peek() >= 0 && peek() != ')' && peek() != ':') {
+						int f = peek();
+						i++;
+						seen = true;
+						if (f == '-') on = false;
+						else if (f == 'i') sub_ci = on;
+						else if (f == 'u') flags |= on ? JTK_RE_UNICODE_CASE : 0;
+						else {
+							fail("unsupported inline flag");
+							return std::make_unique<node>();
+						}
+					}
+					if (!seen) {
+						fail("bad group syntax");
+						return std::make_unique<node>();
+					}
+					if (eat(')')) {
+						ci = sub_ci;
+						return std::make_unique<node>();
+					}
+					if (!eat(':')) {
+						fail("bad inline flag group");
+						return std::make_unique<node>();
+					}
+				}
+			}
+			auto g = parse_alt(sub_ci);
+			if (!eat(')')) fail("missing )");
+			return g;
+		}
+		if (c == '[') {
+			i++;
+			return parse_class(ci);
+		}
+		if (c == '.') {
+			i++;
+			set_builder b;
+			b.dot = true;
+			return set_node(b);
+		}
+		if (c == '^') {
+			i++;
+			auto nd = std::make_unique<node>();
+			nd->type = N_BOL;
+			return nd;
+		}
+		if (c == '$') {
+			i++;
+			auto nd = std::make_unique<node>();
+			nd->type = N_EOL;
+			return nd;
+		}
+		if (c == '\\') {
+			i++;
+			int nc = peek();
+			if (nc == 'b' || nc == 'B' || nc == 'A' || nc == 'z' || nc == 'Z' || nc == 'G' || nc == 'R' || nc == 'X' || nc == 'Q' || nc == 'h' || nc == 'H' || nc == 'v' ||
+			    nc == 'V' || nc == 'k' || (nc >= '1' && nc <= '9')) {
+				fail("unsupported escape (boundary / back-reference / quoting)");
+				return std::make_unique<node>();
+			}
+			set_builder b;
+			b.ci = ci;
+			int lit = escape(b);
+			if (lit >= 0) b.ranges.emplace_back((uint32_t) lit, (uint32_t) lit);
+			return set_node(b);
+		}
+		if (c == '*' || c == '+' || c == '?') {
+			fail("dangling quantifier");
+			return std::make_unique<node>();
+		}
+		i++;
+		set_builder b;
+		b.ci = ci;
+		b.ranges.emplace_back((uint32_t) c, (uint32_t) c);
+		return set_node(b);
+	}
+
+	std::unique_ptr<node> parse_quantified(bool &ci) {
+		auto atom = parse_atom(ci);
+		for (;;) {
+			int c = peek(), mn, mx;
+			if (c == '*') {
+				mn = 0;
+				mx = -1;
+				i++;
+			} else if (c == '+') {
+				mn = 1;
+				mx = -1;
+				i++;
+			} else if (c == '?') {
+				mn = 0;
+				mx = 1;
+				i++;
+			} else if (c == '{') {
+				i++;
+				int a = 0, k = 0;
+				while (peek() >= '0' && peek() <= '9') {
+					a = a * 10 + (peek() - '0');
+					i++;
+					k++;
+				}
+				mn = mx = a;
+				if (eat(',')) {
+					mx = -1;
+					int b = 0, kb = 0;
+					while (peek() >= '0' && peek() <= '9') {
+						b = b * 10 + (peek() - '0');
+						i++;
+						kb++;
+					}
+					if (kb) mx = b;
+				}
+				if (!k || !eat('}') || (mx >= 0 && mx < mn)) {
+					fail("bad {n,m} quantifier");
+					return atom;
+				}
+			} else {
+				return atom;
+			}
+			if (atom->type != N_SET && atom->type != N_CAT && atom->type != N_ALT && atom->type != N_REP) {
+				fail("quantifier on a zero-width construct is not supported");
+				return atom;
+			}
+			auto rep = std::make_unique<node>();
+			rep->type = N_REP;
+			rep->min = mn;
+			rep->max = mx;
+			rep->mode = eat('?') ? 1 : eat('+') ? 2 : 0;
+			rep->sub = std::move(atom);
+			atom = std::move(rep);
+		}
+	}
+
+	std::unique_ptr<node> parse_cat(bool ci) {
+		auto cat = std::make_unique<node>();
+		cat->type = N_CAT;
+		while (!failed()) {
+			int c = peek();
+			if (c < 0 || c == '|' || c == ')') break;
+			cat->kids.push_back(parse_quantified(ci));
+		}
+		return cat;
+	}
+
+	std::unique_ptr<node> parse_alt(bool ci) {
+		auto first = parse_cat(ci);
+		if (peek() != '|') return first;
+		auto alt = std::make_unique<node>();
+		alt->type = N_ALT;
+		alt->kids.push_back(std::move(first));
+		while (!failed() && eat('|')) alt->kids.push_back(parse_cat(ci));
+		return alt;
+	}
+
+	/* can the node match the empty string? */
+	static bool nullable(const node *nd) {
+		switch (nd->type) {
+		case N_SET: return false;
+		case N_CAT:
+			for (auto &k : nd->kids)
+				if (!nullable(k.get())) return false;
+			return true;
+		case N_ALT:
+			for (auto &k : nd->kids)
+				if (nullable(k.get())) return true;
+			return false;
+		case N_REP: return nd->min == 0 || nullable(nd->sub.get());
+		default: return true;
+		}
+	}
+
+	void emit(const node *nd) {
+		auto &code = out->inst;
+		switch (nd->type) {
+		case N_EMPTY: break;
+		case N_SET: code.push_back({JTK_RX_SET, nd->set, 0, 0, 0}); break;
+		case N_BOL: code.push_back({JTK_RX_BOL, 0, 0, 0, 0}); break;
+		case N_EOL: code.push_back({JTK_RX_EOL, 0, 0, 0, 0}); break;
+		case N_CAT:
+			for (auto &k : nd->kids) emit(k.get());
+			break;
+		case N_ALT: {
+			std::vector<size_t> jumps;
+			for (size_t b = 0; b < nd->kids.size(); b++) {
+				size_t split = 0;
+				const bool last = b + 1 == nd->kids.size();
+				if (!last) {
+					split = code.size();
+					code.push_back({JTK_RX_SPLIT, 0, 0, 0, 0});
+				}
+				if (!last) code[split].a = (int32_t) code.size();
+				emit(nd->kids[b].get());
+				if (!last) {
+					jumps.push_back(code.size());
+					code.push_back({JTK_RX_JMP, 0, 0, 0, 0});
+					code[split].b = (int32_t) code.size();
+				}
+			}
+			for (size_t j : jumps) code[j].a = (int32_t) code.size();
+			break;
+		}
+		case N_LOOK: {
+			/* LOOK jumps over the inlined sub-program */
+			const size_t look = code.size();
+			code.push_back({JTK_RX_LOOK, nd->neg ? 1 : 0, 0, 0, 0});
+			const size_t jmp = code.size();
+			code.push_back({JTK_RX_JMP, 0, 0, 0, 0});
+			code[look].b = (int32_t) code.size();
+			emit(nd->sub.get());
+			code.push_back({JTK_RX_MATCH, 0, 0, 0, 0});
+			code[jmp].a = (int32_t) code.size();
+			/* LOOK continues at pc + 1 = the JMP, which skips the sub-program */
+			break;
+		}
+		case N_REP: {
+			const node *sub = nd->sub.get();
+			if (sub->type == N_SET) {
+				code.push_back({JTK_RX_REP, sub->set, nd->min, nd->max, nd->mode});
+				break;
+			}
+			if (nullable(sub)) {
+				fail("a loop over a sub-expression that can match the empty string is not supported");
+				break;
+			}
+			if (nd->mode == 2) {
+				fail("possessive quantifiers on groups are not supported");
+				break;
+			}
+			if (nd->min > 16 || nd->max > 16) {
+				fail("counted loops beyond 16 are not supported");
+				break;
+			}
+			for (int k = 0; k < nd->min; k++) emit(sub);
+			if (nd->max < 0) { /* X* : L: SPLIT(body, out) body: X JMP L out: */
+				const size_t l = code.size();
+				code.push_back({JTK_RX_SPLIT, 0, 0, 0, 0});
+				const size_t body = code.size();
+				emit(sub);
+				code.push_back({JTK_RX_JMP, (int32_t) l, 0, 0, 0});
+				const size_t outp = code.size();
+				code[l].a = nd->mode == 1 ? (int32_t) outp : (int32_t) body;
+				code[l].b = nd->mode == 1 ? (int32_t) body : (int32_t) outp;
+			} else {
+				/* optional copies, nested so that each further copy is only tried after the previous one */
+				std::vector<size_t> splits;
+				for (int k = nd->min; k < nd->max; k++) {
+					splits.push_back(code.size());
+					code.push_back({JTK_RX_SPLIT, 0, 0, 0, 0});
+					const size_t body = code.size();
+					code[splits.back()].a = (int32_t) body;
+					emit(sub);
+				}
+				for (size_t sidx : splits) {
+					if (nd->mode == 1) {
+						code[sidx].b = code[sidx].a;
+						code[sidx].a = (int32_t) code.size();
+					} else {
+						code[sidx].b = (int32_t) code.size();
+					}
+				}
+			}
+			break;
+		}
+		}
+	}
+};
+
+} /* namespace */
+
+int jtk_rx_compile(const char *pattern, int flags, jtk_rx_compiled *out, std::string *err) {
+	parser ps;
+	ps.flags = flags;
+	ps.out = out;
+	out->inst.clear();
+	out->sets.clear();
+	out->ranges.clear();
+	for (size_t i = 0, n = strlen(pattern); i < n;) {
+		const unsigned char b = (unsigned char) pattern[i];
+		uint32_t cp;
+		int len;
+		if (b < 0x80) {
+			cp = b;
+			len = 1;
+		} else if ((b & 0xE0) == 0xC0) {
+			cp = b & 0x1F;
+			len = 2;
+		} else if ((b & 0xF0) == 0xE0) {
+			cp = b & 0x0F;
+			len = 3;
+		} else {
+			cp = b & 0x07;
+			len = 4;
+		}
+		for (int k = 1; k < len && i + (size_t) k < n; k++) cp = (cp << 6) | ((unsigned char) pattern[i + (size_t) k] & 0x3F);
+		ps.p.push_back(cp);
+		i += (size_t) len;
+	}
+	bool ci = (flags & JTK_RE_CASE_INSENSITIVE) != 0;
+	auto root = ps.parse_alt(ci);
+	if (!ps.failed() && ps.i < ps.p.size()) ps.fail("unmatched )");
+	if (!ps.failed() && ps.max_look_depth > 2) ps.fail("look-ahead nested more than twice is not supported");
+	if (!ps.failed()) {
+		out->nullable = parser::nullable(root.get());
+		ps.emit(root.get());
+		out->inst.push_back({JTK_RX_MATCH, 0, 0, 0, 0});
+	}
+	if (ps.failed()) {
+		*err = ps.err;
+		return JTK_E_PATTERN_UNSUPPORTED;
+	}
+	if (out->ranges.empty()) out->ranges.push_back(0);
+	return JTK_OK;
+}

@@ -1,5 +1,6 @@
 /* Host-side table construction; see jtk_tables.h. */
 #include "jtk_tables.h"
+#include "jtk_regex_compile.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -199,15 +200,33 @@ int jtk_build_host_tables(const jtk_params *p, jtk_host_tables *t, std::string *
 	/* ---- the split pattern: recognised patterns are compiled to a class table + rule kind ---- */
 	if (!strcmp(p->pattern, X50K_PATTERN)) t->pattern_kind = JTK_PAT_X50K;
 	else if (!strcmp(p->pattern, CL100K_PATTERN)) t->pattern_kind = JTK_PAT_CL100K;
-	else {
-		*err = std::string("split pattern is not supported by the device pattern compiler: ") + p->pattern;
-		return JTK_E_PATTERN_UNSUPPORTED;
+	else t->pattern_kind = JTK_PAT_GENERAL;
+	if (p->pattern_flags & JTK_RE_CASE_INSENSITIVE)
+		t->pattern_kind = JTK_PAT_GENERAL; /* the rule kinds restate the patterns as EncodingFactory compiles them (case-sensitive) */
+	if (t->pattern_kind == JTK_PAT_GENERAL) {
+		/* any other pattern: compiled to a backtracking program (jtk_regex.h); constructs outside the subset fail here */
+		jtk_rx_compiled prog;
+		std::string rerr;
+		int rc = jtk_rx_compile(p->pattern, p->pattern_flags, &prog, &rerr);
+		if (rc != JTK_OK) {
+			*err = std::string("split pattern is not supported by the device pattern compiler: ") + rerr + ": " + p->pattern;
+			return rc;
+		}
+		if (prog.nullable)
+			for (int64_t i = 0; i < p->vocab_size; i++)
+				if (p->vocab_off[i + 1] == p->vocab_off[i]) {
+					*err = "a pattern that can match the empty string together with an empty vocabulary key is not supported";
+					return JTK_E_PATTERN_UNSUPPORTED;
+				}
+		t->rx_inst.resize(prog.inst.size() * sizeof(jtk_rx_inst));
+		memcpy(t->rx_inst.data(), prog.inst.data(), t->rx_inst.size());
+		t->rx_sets.resize(prog.sets.size() * sizeof(jtk_rx_set));
+		if (!prog.sets.empty()) memcpy(t->rx_sets.data(), prog.sets.data(), t->rx_sets.size());
+		t->rx_ranges = prog.ranges;
+		t->rx_ninst = (int32_t) prog.inst.size();
 	}
-	if (p->pattern_flags & JTK_RE_CASE_INSENSITIVE) {
-		*err = "Pattern.CASE_INSENSITIVE on a predefined split pattern is not supported";
-		return JTK_E_PATTERN_UNSUPPORTED;
-	}
-	build_class_tables(t, p->pattern_flags);
+	/* the general program reads the class table for \p{L}, \p{N} and the Unicode \s only: always White_Space there */
+	build_class_tables(t, t->pattern_kind == JTK_PAT_GENERAL ? (p->pattern_flags | JTK_RE_UNICODE_CHARACTER_CLASS) : p->pattern_flags);
 
 	/* ---- vocabulary: Map.put semantics (a later duplicate key replaces the value), TokenEncoder.java:41-44 ---- */
 	std::unordered_map<std::string, int32_t> index_of; /* key bytes -> token index */
@@ -413,5 +432,9 @@ jtk_tables jtk_host_view(const jtk_host_tables &h) {
 	v.mask_d = h.mask_d;
 	v.dec_bytes = h.dec_bytes.data();
 	v.dec_off = h.dec_off.data();
+	v.rx_inst = h.rx_inst.data();
+	v.rx_sets = h.rx_sets.data();
+	v.rx_ranges = h.rx_ranges.data();
+	v.rx_ninst = h.rx_ninst;
 	return v;
 }

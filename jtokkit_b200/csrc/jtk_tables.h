@@ -44,6 +44,10 @@ struct jtk_host_tables {
 	uint32_t mask_d = 0;
 	std::vector<uint8_t> dec_bytes;
 	std::vector<uint32_t> dec_off;
+	/* JTK_PAT_GENERAL: the compiled split program (raw jtk_rx_inst / jtk_rx_set arrays, 16-byte aligned by the vector) */
+	std::vector<uint8_t> rx_inst, rx_sets;
+	std::vector<uint32_t> rx_ranges;
+	int32_t rx_ninst = 0;
 	/* statistics (reported by DESIGN.md / tests) */
 	int64_t n_tokens = 0, n_pairs = 0;
 	int32_t max_probe_a = 0, max_probe_b = 0, max_probe_p = 0;

@@ -43,6 +43,9 @@ def lib():
         L.emu_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_stats.argtypes = [C.c_void_p, C.c_void_p]
         L.emu_tile.restype = C.c_int
+        L.emu_general_split.restype = C.c_int
+        L.emu_general_split.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
+        L.emu_pattern_kind.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -74,3 +77,17 @@ class EmuEncoding:
         if n < 0:
             raise AssertionError("tile halo view disagrees with owner tile: %d" % n)
         return pf[:utf8.size], (ids[:n] if want_ids else None), tok_off, status[:nd]
+
+    def pattern_kind(self):
+        return lib().emu_pattern_kind(self._h)
+
+    def general_split(self, utf8, doc_off, stack_cap=1024):
+        """(start flags, skip flags) per byte from the general-pattern program; raises on backtrack-stack overflow."""
+        utf8 = np.ascontiguousarray(utf8, dtype=np.uint8)
+        doc_off = np.ascontiguousarray(doc_off, dtype=np.int64)
+        start = np.zeros(max(1, utf8.size), dtype=np.uint8)
+        skip = np.zeros(max(1, utf8.size), dtype=np.uint8)
+        rc = lib().emu_general_split(self._h, _p(utf8), _p(doc_off), doc_off.size - 1, _p(start), _p(skip), stack_cap)
+        if rc != 0:
+            raise OverflowError("general split: rc %d" % rc)
+        return start[:utf8.size], skip[:utf8.size]

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../jtokkit_b200/csrc/jtk_device.cuh"
+#include "../../jtokkit_b200/csrc/jtk_regex.h"
 #include "../../jtokkit_b200/csrc/jtk_tables.h"
 
 struct emu_encoding {
@@ -170,3 +171,19 @@ int64_t emu_run(const emu_encoding *e, const uint8_t *bytes, int64_t total, cons
 	return out_pos;
 }
 }
+
+/* General split patterns: runs the backtracking program (jtk_regex.h) over every document the way jtk_general_split_kernel
+ * does.  start[g] = 1 at piece starts, skip[g] = 1 where the piece starting at g is a gap.  Returns 0, 1 on stack overflow, -1 if
+ * the encoding has no general program. */
+extern "C" int emu_general_split(const emu_encoding *e, const uint8_t *bytes, const int64_t *doc_off, int64_t ndocs, uint8_t *start, uint8_t *skip, int stack_cap) {
+	if (e->view.pattern_kind != JTK_PAT_GENERAL) return -1;
+	const jtk_rx_program P = jtk_rx_program_of(e->view);
+	bool overflow = false;
+	std::vector<jtk_rx_frame> st((size_t) stack_cap);
+	for (int64_t d = 0; d < ndocs && !overflow; d++)
+		jtk_rx_split_document(P, e->view, bytes, doc_off[d], doc_off[d + 1], st.data(), stack_cap, [&](int64_t g) { start[g] = 1; }, [&](int64_t g) { skip[g] = 1; }, &overflow);
+	return overflow ? 1 : 0;
+}
+
+extern "C" int emu_pattern_kind(const emu_encoding *e) { return e->view.pattern_kind; }
+

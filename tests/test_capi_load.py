@@ -52,11 +52,12 @@ def test_registration_fails_loudly_without_a_gpu():
 
 
 def test_unsupported_pattern_is_rejected_at_registration():
-    """Patterns outside the device pattern compiler fail at registration (they never run on the CPU instead)."""
+    """Patterns outside the device pattern compiler's subset fail at registration (they never run on the CPU instead)."""
     import jtokkit_b200 as jt
-    params = jt.GptBytePairEncodingParams("custom", jt.Pattern.compile(r"\w+|\s+"), {b"a": 0}, {})
-    with pytest.raises(ValueError):
-        jt.EncodingFactory.from_parameters(params)
+    for pat in [r"(?<=a)b", r"\bword\b", r"(a)\1", r"(?:a*)*", r"[a-z&&[^b]]", r"\p{Lu}+", r"a{2,1}", r"(", r"x{17}y(?:ab){20}"]:
+        params = jt.GptBytePairEncodingParams("custom", jt.Pattern.compile(pat), {b"a": 0}, {})
+        with pytest.raises(ValueError):
+            jt.EncodingFactory.from_parameters(params)
 
 
 def test_product_does_not_import_the_oracle():

@@ -85,3 +85,74 @@ def test_table_statistics():
         st = e.stats()
         assert st[0] == ntok and st[1] == npairs
         assert st[2] <= 40 and st[4] <= 16  # longest probe sequences (piece table slots / pair table buckets)
+
+
+# General split patterns: the device's backtracking program (jtk_regex.h + the compiler in jtk_regex.cpp)
+# against the oracle's independently written matcher.  Flags: 0x02 CASE_INSENSITIVE, 0x40 UNICODE_CASE, 0x100 UNICODE_CHARACTER_CLASS.
+GENERAL_PATTERNS = [
+    ("test", 0), (r"\w+|\s+", 0), (r"[a-z]+|[0-9]{1,3}| ?[^a-z0-9 ]+", 0), (r"(?i:'s|'t|'re)|\p{L}+|\p{N}{1,3}|\s+(?!\S)|\s+|.", 0x100),
+    (r"a*b|c", 0), (r"\s*[a-z]+?\d|[a-z]+", 0), (r"(?:ab|a)(?:bc|c)?|.", 0),
+    (r"[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]+[\r\n]*|\s*[\r\n]+|\s+(?!\S)|\s+", 0x100),
+    (r"(?i)hello|the |[a-z]+", 0), (r"(?i)s+|k+", 0x42), (r"\p{L}++|\d*+x|\S", 0), (r"(?:[a-c]|de){2,3}|\S+?(?= )|\s", 0), (r"x*", 0),
+    (r"^\w+|\w+$|\s", 0), (r"'(?:[sdmt]|ll|ve|re)| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+", 0),
+    (r"'s|'t|'re|'ve|'m|'ll|'d| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+", 0x102),
+    (r"(?:\p{L}\p{N}?)+| (?! )|[^ ]", 0x100), (r"[一-鿿]+|\x41{2}|\x{1F355}|[a-zé-ü]+|\S", 0),
+]
+
+
+def expected_piece_bits(o, docs, off, nbytes):
+    """Piece-start and gap bits per byte from the oracle's Matcher.find() restatement (empty matches produce nothing)."""
+    start, skip = np.zeros(nbytes, np.uint8), np.zeros(nbytes, np.uint8)
+    for d, doc in enumerate(docs):
+        prev = 0
+        for (a, b) in o.split(doc):
+            if b == a:
+                continue
+            if a > prev:
+                start[off[d] + prev] = skip[off[d] + prev] = 1
+            start[off[d] + a] = 1
+            prev = b
+        if prev < len(doc):
+            start[off[d] + prev] = skip[off[d] + prev] = 1
+    return start, skip
+
+
+@pytest.mark.parametrize("index", range(len(GENERAL_PATTERNS)))
+def test_general_pattern_program_matches_oracle_matcher(index):
+    import emu
+    from oracle import jo
+    jo.build()
+    pat, flags = GENERAL_PATTERNS[index]
+    e = emu.EmuEncoding("g", pat, flags, {b"a": 0}, {})
+    assert e.pattern_kind() == 3
+    o = jo.OracleEncoding("g", pat, flags, {b"a": 0}, {})
+    rng = random.Random(100 + index)
+    for it in range(150):
+        docs = random_docs(rng, rng.randint(1, 4), ascii_only=(it % 3 == 1), utf8_letters=(it % 3 == 2))
+        blob = b"".join(docs)
+        off = np.zeros(len(docs) + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(x) for x in docs])
+        start, skip = e.general_split(np.frombuffer(blob, dtype=np.uint8), off)
+        exp_start, exp_skip = expected_piece_bits(o, docs, off, len(blob))
+        assert np.array_equal(start, exp_start) and np.array_equal(skip, exp_skip), (pat, docs)
+
+
+def test_general_pattern_stack_overflow_is_reported():
+    """A group loop keeps one frame per iteration: a long run exhausts a small stack and the call says so instead of mis-splitting."""
+    import emu
+    e = emu.EmuEncoding("g", r"(?:a|b)+c|.", 0, {b"a": 0}, {})
+    text = np.frombuffer(b"ab" * 400, dtype=np.uint8)
+    off = np.array([0, text.size], dtype=np.int64)
+    with pytest.raises(OverflowError):
+        e.general_split(text, off, stack_cap=64)
+    e.general_split(text, off, stack_cap=4096)
+
+
+def test_predefined_patterns_do_not_take_the_general_path():
+    import emu
+    from oracle import jo
+    for name in ["cl100k_base", "r50k_base"]:
+        pat, fname, special = jo.BUILTIN[name]
+        assert emu.EmuEncoding(name, pat, 0x100, {b"a": 0}, {}).pattern_kind() in (1, 2)
+    pat = jo.BUILTIN["cl100k_base"][0]
+    assert emu.EmuEncoding("ci", pat, 0x102, {b"a": 0}, {}).pattern_kind() == 3  # CASE_INSENSITIVE: general program

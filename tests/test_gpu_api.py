@@ -53,9 +53,16 @@ def test_registry_registration(registry):
     with pytest.raises(ValueError):  # every byte is unknown: IllegalArgumentException from TokenEncoder.encode
         registry.get_encoding("empty_maps").encode("a")
     assert registry.get_encoding("empty_maps").encode("") == []
-    # an arbitrary pattern is outside the device pattern compiler: registration fails, nothing falls back to the CPU
+    # BaseEncodingRegistryTest.java:110-125: an arbitrary pattern with two empty maps registers (general pattern program)
+    registry.register_gpt_byte_pair_encoding(jt.GptBytePairEncodingParams("test", jt.Pattern.compile("test"), {}, {}))
+    enc = registry.get_encoding("test")
+    assert enc.get_name() == "test"
+    assert enc.encode("nothing matches here") == [] and enc.encode("") == []
+    with pytest.raises(ValueError):  # "test" matches, but no byte of it is in the (empty) vocabulary
+        enc.encode("a test")
+    # constructs outside the compiler's subset fail at registration, nothing falls back to the CPU
     with pytest.raises(ValueError):
-        registry.register_gpt_byte_pair_encoding(jt.GptBytePairEncodingParams("test", jt.Pattern.compile("test"), {}, {}))
+        registry.register_gpt_byte_pair_encoding(jt.GptBytePairEncodingParams("lookbehind", jt.Pattern.compile("(?<=a)b"), {}, {}))
 
 
 def test_default_registry_is_eager():

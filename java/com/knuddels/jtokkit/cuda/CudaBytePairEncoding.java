@@ -151,6 +151,8 @@ public final class CudaBytePairEncoding implements Encoding, AutoCloseable {
 		// the reference's exception types and messages (GptBytePairEncoding.java:54, TokenEncoder.java:67)
 		if ((status & JtkNative.DOC_HAS_SPECIAL) != 0) throw new UnsupportedOperationException("Encoding special tokens is not supported yet.");
 		if ((status & JtkNative.DOC_UNKNOWN_BYTES) != 0) throw new IllegalArgumentException("Unknown token for encoding");
+		// general split patterns only: java.util.regex dies the same way on texts that recurse too deep
+		if ((status & JtkNative.DOC_PATTERN_STACK) != 0) throw new StackOverflowError("split pattern exhausted the device backtracking stack");
 	}
 
 	private List<Integer> encodeOne(final String text, final boolean ordinary) {

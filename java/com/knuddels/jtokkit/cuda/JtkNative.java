@@ -48,7 +48,7 @@ final class JtkNative {
 
 	static final int JTK_OK = 0, JTK_E_PATTERN_UNSUPPORTED = -3;
 	static final int CHECK_SPECIAL = 1, COUNT_ONLY = 2;
-	static final int DOC_HAS_SPECIAL = 1, DOC_UNKNOWN_BYTES = 2, DOC_UNKNOWN_ID = 4;
+	static final int DOC_HAS_SPECIAL = 1, DOC_UNKNOWN_BYTES = 2, DOC_UNKNOWN_ID = 4, DOC_PATTERN_STACK = 8;
 
 	static String lastError() throws Throwable {
 		return ((MemorySegment) LAST_ERROR.invokeExact()).reinterpret(4096).getString(0);

@@ -138,6 +138,31 @@ def cpu_port_throughput(utf8_np, doc_off_np, sample_bytes, threads):
     return total / dt, nb, int(total), dt, ids, counts, nd
 
 
+def cpu_tiktoken_throughput(utf8_np, doc_off_np, sample_bytes, threads):
+    """SURVEY.md §8d CPU baseline (2): tiktoken's encode_ordinary_batch exactly as the reference's own benchmark/bench.py:28 calls
+    it, built from the reference's regex string and vocabulary file.  Context only (it is the upstream JTokkit mirrors, not
+    JTokkit); None when tiktoken is not importable."""
+    try:
+        import tiktoken
+        from tiktoken.load import load_tiktoken_bpe
+    except ImportError:
+        return None
+    import numpy as np
+    import jtokkit_b200 as jt
+    params = jt.EncodingFactory.predefined_params(jt.EncodingType.CL100K_BASE)
+    path = os.path.join(os.path.dirname(os.path.abspath(jt.__file__)), "data", "cl100k_base.tiktoken")
+    enc = tiktoken.Encoding("cl100k_jtokkit", pat_str=params.get_pattern().pattern(), mergeable_ranks=load_tiktoken_bpe(path), special_tokens={})
+    nd = max(1, int(np.searchsorted(doc_off_np, sample_bytes, side="right")) - 1)
+    raw = utf8_np[:int(doc_off_np[nd])].tobytes()
+    docs = [raw[int(doc_off_np[d]):int(doc_off_np[d + 1])].decode("utf-8") for d in range(nd)]
+    t0 = time.perf_counter()
+    out = enc.encode_ordinary_batch(docs, num_threads=threads)
+    dt = time.perf_counter() - t0
+    ntok = sum(len(x) for x in out)
+    return {"value": ntok / dt, "unit": "tokens/s", "cores": threads, "kind": "tiktoken %s encode_ordinary_batch" % tiktoken.__version__,
+            "sample": "first %d bytes / %d documents (%d tokens) of the same corpus, %.1f s, %.3f GB/s input" % (len(raw), nd, ntok, dt, len(raw) / dt / 1e9)}
+
+
 def run_reference(args):
     """--impl reference: the reference's own algorithm on the host cores (oracle port: no JVM in this image)."""
     import numpy as np
@@ -271,6 +296,7 @@ def run_ours(args):
     # ---- CPU baseline on a bounded sample of the same corpus (rank 0, N=1 only) + parity of that sample
     cpu = None
     parity = None
+    tk = None
     if world == 1 and not args.no_cpu_baseline:
         if all_cpus:
             os.sched_setaffinity(0, all_cpus)
@@ -286,6 +312,7 @@ def run_ours(args):
             ok = ok and bool(np.array_equal(o_ids[h_off_np[d]:h_off_np[d] + c], r.ids[r.token_offsets[d]:r.token_offsets[d] + c]))
         parity = "bit-exact vs oracle on the CPU-baseline sample (%d documents: all counts, every %dth document's ids)" % (nd, max(1, nd // 512)) \
             if ok else "MISMATCH vs oracle"
+        tk = cpu_tiktoken_throughput(h_in_np, h_off_np, 64 << 20, threads)
 
     out = {
         "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -303,6 +330,7 @@ def run_ours(args):
                      "frac_whole_step": algo_bytes / (dev_ms / args.steps * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": int(algo_bytes), "peak_source": peak_src,
                      "frac_of_nominal_8000": achieved / 8000.0},
         "cpu_baseline": cpu,
+        "cpu_tiktoken": tk,
         "parity": parity,
         "clocks": clocks,
         "host_cores": os.cpu_count(),

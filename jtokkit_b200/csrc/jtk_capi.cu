@@ -43,6 +43,9 @@ struct jtk_workspace {
 	uint32_t *rx_bits = nullptr;
 	int64_t rx_words_cap = 0;
 	void *rx_stacks = nullptr;
+	/* side streams for the merge kernels (JTK_SIDE_STREAMS=0 keeps everything on one stream) */
+	jtk_side_streams side;
+	bool side_ok = false;
 	int32_t *tile_first_doc = nullptr;
 	int32_t *tile_count = nullptr, *npieces = nullptr, *nslow = nullptr, *tile_slow_used = nullptr;
 	int64_t *tile_base = nullptr;
@@ -312,6 +315,13 @@ static void free_workspace(jtk_workspace *w) {
 	cudaFree(w->d_ids);
 	cudaFree(w->d_tok_off);
 	cudaFree(w->d_status);
+	if (w->side_ok) {
+		for (int i = 0; i < 3; i++) {
+			cudaStreamDestroy(w->side.s[i]);
+			cudaEventDestroy(w->side.join[i]);
+		}
+		cudaEventDestroy(w->side.fork);
+	}
 	if (w->stream) cudaStreamDestroy(w->stream);
 	delete w;
 }
@@ -359,6 +369,14 @@ static int64_t sub_batch_tiles() {
 	return v;
 }
 
+static bool side_streams_enabled() {
+	static const bool v = [] {
+		const char *env = getenv("JTK_SIDE_STREAMS");
+		return !(env && env[0] == '0');
+	}();
+	return v;
+}
+
 static bool memo_enabled() {
 	static const bool v = [] {
 		const char *env = getenv("JTK_MEMO");
@@ -400,6 +418,14 @@ static void release_memo(jtk_device_state *ds, jtk_memo_buf *m) {
 }
 
 static int ensure_ws_tiles(jtk_workspace *w, int64_t ntiles, int64_t long_cap) {
+	if (!w->side_ok && side_streams_enabled()) {
+		for (int i = 0; i < 3; i++) {
+			CUDA_TRY(cudaStreamCreateWithFlags(&w->side.s[i], cudaStreamNonBlocking));
+			CUDA_TRY(cudaEventCreateWithFlags(&w->side.join[i], cudaEventDisableTiming));
+		}
+		CUDA_TRY(cudaEventCreateWithFlags(&w->side.fork, cudaEventDisableTiming));
+		w->side_ok = true;
+	}
 	if (!w->hdr) {
 		CUDA_TRY(cudaMalloc(&w->hdr, sizeof(jtk_batch_header)));
 		CUDA_TRY(cudaHostAlloc(&w->hdr_host, sizeof(jtk_batch_header), cudaHostAllocDefault));
@@ -608,7 +634,7 @@ static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspa
 	for (int64_t i = 0; i < nsub; i++) {
 		a.tile_begin = cuts[(size_t) i];
 		a.tile_end = cuts[(size_t) i + 1];
-		CUDA_TRY(jtk_launch_sub_batch(a, ds->num_sms, time_kernel ? w->kev[(size_t) (2 * i)] : nullptr, time_kernel ? w->kev[(size_t) (2 * i + 1)] : nullptr, st));
+		CUDA_TRY(jtk_launch_sub_batch(a, ds->num_sms, time_kernel ? w->kev[(size_t) (2 * i)] : nullptr, time_kernel ? w->kev[(size_t) (2 * i + 1)] : nullptr, st, w->side_ok ? &w->side : nullptr));
 	}
 	CUDA_TRY(jtk_launch_finalize(a, st));
 	info->gpu_launches = (ntiles > 0 ? 1 : 0) + general_launches + 9 * nsub + 1;

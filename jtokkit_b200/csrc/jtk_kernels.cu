@@ -1188,7 +1188,7 @@ cudaError_t jtk_launch_tile_first_doc(const int64_t *doc_off, int64_t ndocs, int
 }
 
 /* the four kernels of one sub-batch [a.tile_begin, a.tile_end) */
-cudaError_t jtk_launch_sub_batch(const jtk_encode_args &a, int num_sms, cudaEvent_t k0, cudaEvent_t k1, cudaStream_t st) {
+cudaError_t jtk_launch_sub_batch(const jtk_encode_args &a, int num_sms, cudaEvent_t k0, cudaEvent_t k1, cudaStream_t st, const jtk_side_streams *side) {
 	const int64_t nt = a.tile_end - a.tile_begin;
 	if (nt <= 0) return cudaSuccess;
 	int64_t grid = (int64_t) num_sms * 4;
@@ -1220,18 +1220,29 @@ cudaError_t jtk_launch_sub_batch(const jtk_encode_args &a, int num_sms, cudaEven
 	cfg.dynamicSmemBytes = 0;
 	jtk_short_offsets_kernel<<<1, 32, 0, st>>>(a);
 	jtk_short_scatter_kernel<<<(unsigned) nt, SNT, 0, st>>>(a);
-	cfg.gridDim = dim3((unsigned) (num_sms * 6));
-	cfg.blockDim = dim3(256);
-	cudaLaunchKernelEx(&cfg, jtk_merge_short_kernel<16, 256>, a);
-	cfg.gridDim = dim3((unsigned) (num_sms * 6));
-	cfg.blockDim = dim3(128);
-	cudaLaunchKernelEx(&cfg, jtk_merge_short_kernel<32, 128>, a);
-	cfg.gridDim = dim3((unsigned) (num_sms * 6));
-	cfg.blockDim = dim3(64);
-	cudaLaunchKernelEx(&cfg, jtk_merge_short_kernel<64, 64>, a);
+	/* the four merge kernels are independent of each other (own lists, own pieces): longest chains first, side by side */
+	if (side) {
+		cudaEventRecord(side->fork, st);
+		for (int i = 0; i < 3; i++) cudaStreamWaitEvent(side->s[i], side->fork, 0);
+	}
 	cfg.gridDim = dim3((unsigned) (num_sms * 6));
 	cfg.blockDim = dim3(GNTM);
+	cfg.stream = side ? side->s[0] : st;
 	cudaLaunchKernelEx(&cfg, jtk_merge_medium_kernel, a);
+	cfg.blockDim = dim3(64);
+	cfg.stream = side ? side->s[1] : st;
+	cudaLaunchKernelEx(&cfg, jtk_merge_short_kernel<64, 64>, a);
+	cfg.blockDim = dim3(128);
+	cfg.stream = side ? side->s[2] : st;
+	cudaLaunchKernelEx(&cfg, jtk_merge_short_kernel<32, 128>, a);
+	cfg.blockDim = dim3(256);
+	cfg.stream = st;
+	cudaLaunchKernelEx(&cfg, jtk_merge_short_kernel<16, 256>, a);
+	if (side)
+		for (int i = 0; i < 3; i++) {
+			cudaEventRecord(side->join[i], side->s[i]);
+			cudaStreamWaitEvent(st, side->join[i], 0);
+		}
 	jtk_tile_scan_kernel<<<1, 1024, 0, st>>>(a);
 	jtk_gather_kernel<<<(unsigned) nt, GNT, GATHER_SMEM, st>>>(a);
 	return cudaGetLastError();

@@ -92,8 +92,14 @@ struct jtk_encode_args {
 #define JTK_SMEM_BYTES (2 * (JTK_REGION + 16) + 2 * 4 * (((JTK_REGION + 32) / 32 + 1)) + 2 * JTK_RECN + 4 * (JTK_TILE / 16) + 512 + 128)
 
 cudaError_t jtk_launch_tile_first_doc(const int64_t *doc_off, int64_t ndocs, int64_t ntiles, int32_t *out, cudaStream_t st);
-/* the four kernels of one sub-batch; k0/k1 (nullable) bracket the split+lookup kernel */
-cudaError_t jtk_launch_sub_batch(const jtk_encode_args &a, int num_sms, cudaEvent_t k0, cudaEvent_t k1, cudaStream_t st);
+/* Side streams on which the merge kernels of a sub-batch run next to each other: each of them alone leaves most of the GPU
+ * idle (few pieces, long dependent chains), together they fill it.  nullptr = everything on the caller's stream. */
+struct jtk_side_streams {
+	cudaStream_t s[3];
+	cudaEvent_t fork, join[3];
+};
+/* the kernels of one sub-batch; k0/k1 (nullable) bracket the split+lookup kernel */
+cudaError_t jtk_launch_sub_batch(const jtk_encode_args &a, int num_sms, cudaEvent_t k0, cudaEvent_t k1, cudaStream_t st, const jtk_side_streams *side);
 cudaError_t jtk_launch_finalize(const jtk_encode_args &a, cudaStream_t st);
 /* JTK_PAT_GENERAL: runs the split program over every document (one thread per document) before the sub-batches; rx_start / rx_skip must be zeroed */
 #define JTK_RX_THREADS (148 * 128)

@@ -49,11 +49,19 @@ struct jtk_workspace {
 	int32_t *tile_first_doc = nullptr;
 	int32_t *tile_count = nullptr, *npieces = nullptr, *nslow = nullptr, *tile_slow_used = nullptr;
 	int64_t *tile_base = nullptr;
-	/* per sub-batch: piece records, merged-token staging, unresolved-piece lists */
+	/* per sub-batch: piece records, merged-token staging, unresolved-piece lists.  Two lanes: the split+lookup kernel of sub-batch
+	 * k + 1 runs on the caller's stream while the merge / gather kernels of sub-batch k run on post_stream (JTK_PIPELINE=0: one lane) */
 	int64_t sub_tiles = 0;
-	int32_t *rec = nullptr, *slowtok = nullptr;
-	uint16_t *slowq = nullptr;
-	uint32_t *med8 = nullptr, *med32 = nullptr, *shortlist = nullptr;
+	struct lane_t {
+		int32_t *rec = nullptr, *slowtok = nullptr;
+		uint16_t *slowq = nullptr;
+		uint32_t *med8 = nullptr, *med32 = nullptr, *shortlist = nullptr;
+		jtk_sub_header *sub = nullptr;
+		cudaEvent_t split_done = nullptr, post_done = nullptr;
+	} lane[2];
+	int nlanes = 0;
+	cudaStream_t post_stream = nullptr;
+	cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
 	std::vector<cudaEvent_t> kev; /* event pairs around the split+lookup kernel of every sub-batch (JTK_TIME_KERNEL) */
 	int64_t *tile_first_b = nullptr;
 	jtk_long_piece *long_list = nullptr;
@@ -297,12 +305,20 @@ static void free_workspace(jtk_workspace *w) {
 	cudaFree(w->nslow);
 	cudaFree(w->tile_slow_used);
 	cudaFree(w->tile_base);
-	cudaFree(w->rec);
-	cudaFree(w->slowtok);
-	cudaFree(w->slowq);
-	cudaFree(w->med8);
-	cudaFree(w->med32);
-	cudaFree(w->shortlist);
+	for (auto &ln : w->lane) {
+		cudaFree(ln.rec);
+		cudaFree(ln.slowtok);
+		cudaFree(ln.slowq);
+		cudaFree(ln.med8);
+		cudaFree(ln.med32);
+		cudaFree(ln.shortlist);
+		cudaFree(ln.sub);
+		if (ln.split_done) cudaEventDestroy(ln.split_done);
+		if (ln.post_done) cudaEventDestroy(ln.post_done);
+	}
+	if (w->post_stream) cudaStreamDestroy(w->post_stream);
+	if (w->ev_begin) cudaEventDestroy(w->ev_begin);
+	if (w->ev_end) cudaEventDestroy(w->ev_end);
 	for (cudaEvent_t ev : w->kev) cudaEventDestroy(ev);
 	cudaFree(w->tile_first_b);
 	cudaFree(w->long_list);
@@ -377,6 +393,23 @@ static bool side_streams_enabled() {
 	return v;
 }
 
+static bool pipeline_enabled() {
+	static const bool v = [] {
+		const char *env = getenv("JTK_PIPELINE"); /* measured: no gain on B200 (profiles/r1_history.md), so off unless asked for */
+		return env && env[0] == '1';
+	}();
+	return v;
+}
+
+/* CTAs per SM of the split+lookup kernel; 0 = one CTA per tile (lets the other lane's kernels in as CTAs retire) */
+static int split_ctas_per_sm() {
+	static const int v = [] {
+		const char *env = getenv("JTK_SPLIT_CTAS");
+		return env ? atoi(env) : (pipeline_enabled() ? 0 : 4);
+	}();
+	return v;
+}
+
 static bool memo_enabled() {
 	static const bool v = [] {
 		const char *env = getenv("JTK_MEMO");
@@ -418,13 +451,29 @@ static void release_memo(jtk_device_state *ds, jtk_memo_buf *m) {
 }
 
 static int ensure_ws_tiles(jtk_workspace *w, int64_t ntiles, int64_t long_cap) {
+	int prio_lo = 0, prio_hi = 0;
+	CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi)); /* numerically lower = higher priority */
 	if (!w->side_ok && side_streams_enabled()) {
 		for (int i = 0; i < 3; i++) {
-			CUDA_TRY(cudaStreamCreateWithFlags(&w->side.s[i], cudaStreamNonBlocking));
+			CUDA_TRY(cudaStreamCreateWithPriority(&w->side.s[i], cudaStreamNonBlocking, prio_hi));
 			CUDA_TRY(cudaEventCreateWithFlags(&w->side.join[i], cudaEventDisableTiming));
 		}
 		CUDA_TRY(cudaEventCreateWithFlags(&w->side.fork, cudaEventDisableTiming));
 		w->side_ok = true;
+	}
+	if (w->nlanes == 0) {
+		w->nlanes = pipeline_enabled() ? 2 : 1;
+		for (int l = 0; l < w->nlanes; l++) {
+			CUDA_TRY(cudaMalloc(&w->lane[l].sub, sizeof(jtk_sub_header)));
+			CUDA_TRY(cudaMemset(w->lane[l].sub, 0, sizeof(jtk_sub_header)));
+			CUDA_TRY(cudaEventCreateWithFlags(&w->lane[l].split_done, cudaEventDisableTiming));
+			CUDA_TRY(cudaEventCreateWithFlags(&w->lane[l].post_done, cudaEventDisableTiming));
+		}
+		if (w->nlanes > 1) {
+			CUDA_TRY(cudaStreamCreateWithPriority(&w->post_stream, cudaStreamNonBlocking, prio_hi));
+			CUDA_TRY(cudaEventCreateWithFlags(&w->ev_begin, cudaEventDisableTiming));
+			CUDA_TRY(cudaEventCreateWithFlags(&w->ev_end, cudaEventDisableTiming));
+		}
 	}
 	if (!w->hdr) {
 		CUDA_TRY(cudaMalloc(&w->hdr, sizeof(jtk_batch_header)));
@@ -454,22 +503,25 @@ static int ensure_ws_tiles(jtk_workspace *w, int64_t ntiles, int64_t long_cap) {
 	}
 	const int64_t sub = std::min<int64_t>(std::max<int64_t>(ntiles, 1), sub_batch_tiles());
 	if (sub > w->sub_tiles) {
-		cudaFree(w->rec);
-		cudaFree(w->slowtok);
-		cudaFree(w->slowq);
-		cudaFree(w->med8);
-		cudaFree(w->med32);
-		cudaFree(w->shortlist);
-		w->rec = w->slowtok = nullptr;
-		w->slowq = nullptr;
-		w->med8 = w->med32 = w->shortlist = nullptr;
 		w->sub_tiles = 0;
-		CUDA_TRY(cudaMalloc(&w->rec, sizeof(int32_t) * (size_t) sub * JTK_RECN));
-		CUDA_TRY(cudaMalloc(&w->slowtok, sizeof(int32_t) * (size_t) sub * JTK_RECN));
-		CUDA_TRY(cudaMalloc(&w->slowq, sizeof(uint16_t) * (size_t) sub * JTK_QCAP));
-		CUDA_TRY(cudaMalloc(&w->med8, sizeof(uint32_t) * (size_t) sub * JTK_MED8_PER_TILE));
-		CUDA_TRY(cudaMalloc(&w->med32, sizeof(uint32_t) * (size_t) sub * JTK_MED32_PER_TILE));
-		CUDA_TRY(cudaMalloc(&w->shortlist, sizeof(uint32_t) * (size_t) sub * JTK_QCAP));
+		for (int l = 0; l < w->nlanes; l++) {
+			jtk_workspace::lane_t &ln = w->lane[l];
+			cudaFree(ln.rec);
+			cudaFree(ln.slowtok);
+			cudaFree(ln.slowq);
+			cudaFree(ln.med8);
+			cudaFree(ln.med32);
+			cudaFree(ln.shortlist);
+			ln.rec = ln.slowtok = nullptr;
+			ln.slowq = nullptr;
+			ln.med8 = ln.med32 = ln.shortlist = nullptr;
+			CUDA_TRY(cudaMalloc(&ln.rec, sizeof(int32_t) * (size_t) sub * JTK_RECN));
+			CUDA_TRY(cudaMalloc(&ln.slowtok, sizeof(int32_t) * (size_t) sub * JTK_RECN));
+			CUDA_TRY(cudaMalloc(&ln.slowq, sizeof(uint16_t) * (size_t) sub * JTK_QCAP));
+			CUDA_TRY(cudaMalloc(&ln.med8, sizeof(uint32_t) * (size_t) sub * JTK_MED8_PER_TILE));
+			CUDA_TRY(cudaMalloc(&ln.med32, sizeof(uint32_t) * (size_t) sub * JTK_MED32_PER_TILE));
+			CUDA_TRY(cudaMalloc(&ln.shortlist, sizeof(uint32_t) * (size_t) sub * JTK_QCAP));
+		}
 		w->sub_tiles = sub;
 	}
 	if (long_cap > w->long_cap) {
@@ -483,6 +535,17 @@ static int ensure_ws_tiles(jtk_workspace *w, int64_t ntiles, int64_t long_cap) {
 	return JTK_OK;
 }
 
+static void set_lane(jtk_encode_args &a, const jtk_workspace *w, int l) {
+	const jtk_workspace::lane_t &ln = w->lane[l];
+	a.rec = ln.rec;
+	a.slowtok = ln.slowtok;
+	a.slowq = ln.slowq;
+	a.med8 = ln.med8;
+	a.med32 = ln.med32;
+	a.shortlist = ln.shortlist;
+	a.sub = ln.sub;
+}
+
 static void fill_args(jtk_encode_args &a, const jtk_device_state *ds, const jtk_workspace *w) {
 	a.T = ds->T;
 	a.tile_first_doc = w->tile_first_doc;
@@ -492,12 +555,7 @@ static void fill_args(jtk_encode_args &a, const jtk_device_state *ds, const jtk_
 	a.tile_count = w->tile_count;
 	a.tile_base = w->tile_base;
 	a.tile_first_b = w->tile_first_b;
-	a.rec = w->rec;
-	a.slowtok = w->slowtok;
-	a.slowq = w->slowq;
-	a.med8 = w->med8;
-	a.med32 = w->med32;
-	a.shortlist = w->shortlist;
+	set_lane(a, w, 0);
 	a.hdr = w->hdr;
 	a.long_list = w->long_list;
 	a.long_cap = w->long_cap;
@@ -597,6 +655,7 @@ static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspa
 		a.memo_epoch = memo->epoch;
 	}
 	CUDA_TRY(cudaMemsetAsync(w->hdr, 0, sizeof(jtk_batch_header), st));
+	for (int l = 0; l < w->nlanes; l++) CUDA_TRY(cudaMemsetAsync(w->lane[l].sub, 0, sizeof(jtk_sub_header), st));
 	CUDA_TRY(jtk_launch_tile_first_doc(d_doc_off, ndocs, ntiles, w->tile_first_doc, st));
 	int general_launches = 0;
 	if (ds->T.pattern_kind == JTK_PAT_GENERAL && ntiles > 0) {
@@ -622,7 +681,7 @@ static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspa
 	/* sub-batches: a small first one (16 MiB) so that the piece memo is warm early, then full-size ones */
 	const int64_t sub = w->sub_tiles;
 	std::vector<int64_t> cuts(1, 0);
-	if (memo && ntiles > 4 * 2048) cuts.push_back(2048);
+	if (memo && ntiles > 4 * JTK_FIRST_SUB_TILES) cuts.push_back(JTK_FIRST_SUB_TILES);
 	while (cuts.back() < ntiles) cuts.push_back(std::min<int64_t>(ntiles, cuts.back() + sub));
 	const int64_t nsub = (int64_t) cuts.size() - 1;
 	if (time_kernel)
@@ -631,10 +690,33 @@ static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspa
 			CUDA_TRY(cudaEventCreate(&ev));
 			w->kev.push_back(ev);
 		}
+	/* Two sub-batches in flight: split+lookup of sub-batch i on the caller's stream, everything after it on post_stream with
+	 * the other lane of buffers; the split of sub-batch i + 2 waits for the lane to be free again. */
+	const bool piped = w->nlanes > 1 && nsub > 1;
+	const jtk_side_streams *side = w->side_ok ? &w->side : nullptr;
+	if (piped) {
+		CUDA_TRY(cudaEventRecord(w->ev_begin, st));
+		CUDA_TRY(cudaStreamWaitEvent(w->post_stream, w->ev_begin, 0));
+	}
 	for (int64_t i = 0; i < nsub; i++) {
+		const int l = piped ? (int) (i & 1) : 0;
+		set_lane(a, w, l);
 		a.tile_begin = cuts[(size_t) i];
 		a.tile_end = cuts[(size_t) i + 1];
-		CUDA_TRY(jtk_launch_sub_batch(a, ds->num_sms, time_kernel ? w->kev[(size_t) (2 * i)] : nullptr, time_kernel ? w->kev[(size_t) (2 * i + 1)] : nullptr, st, w->side_ok ? &w->side : nullptr));
+		if (piped && i >= 2) CUDA_TRY(cudaStreamWaitEvent(st, w->lane[l].post_done, 0));
+		CUDA_TRY(jtk_launch_split(a, ds->num_sms, split_ctas_per_sm(), time_kernel ? w->kev[(size_t) (2 * i)] : nullptr, time_kernel ? w->kev[(size_t) (2 * i + 1)] : nullptr, st));
+		if (piped) {
+			CUDA_TRY(cudaEventRecord(w->lane[l].split_done, st));
+			CUDA_TRY(cudaStreamWaitEvent(w->post_stream, w->lane[l].split_done, 0));
+			CUDA_TRY(jtk_launch_post(a, ds->num_sms, w->post_stream, side));
+			CUDA_TRY(cudaEventRecord(w->lane[l].post_done, w->post_stream));
+		} else {
+			CUDA_TRY(jtk_launch_post(a, ds->num_sms, st, side));
+		}
+	}
+	if (piped) {
+		CUDA_TRY(cudaEventRecord(w->ev_end, w->post_stream));
+		CUDA_TRY(cudaStreamWaitEvent(st, w->ev_end, 0));
 	}
 	CUDA_TRY(jtk_launch_finalize(a, st));
 	info->gpu_launches = (ntiles > 0 ? 1 : 0) + general_launches + 9 * nsub + 1;

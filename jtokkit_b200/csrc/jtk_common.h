@@ -61,7 +61,11 @@ enum {
 #ifndef JTK_TILE
 #define JTK_TILE 8192       /* bytes owned by one tile */
 #endif
-#define JTK_NT (JTK_TILE / 16) /* threads per CTA: 16 bytes each */
+#ifndef JTK_NT
+/* threads per CTA of the split+lookup kernel: one per 16-byte chunk of the tile (measured: 608 threads = one per chunk of the
+ * whole region, 3 CTAs per SM, saves the second round over the halo chunks but loses more through the lower occupancy) */
+#define JTK_NT (JTK_TILE / 16)
+#endif
 #ifndef JTK_BACK_HALO
 #define JTK_BACK_HALO 64    /* context bytes before the tile */
 #endif

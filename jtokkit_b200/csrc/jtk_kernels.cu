@@ -38,8 +38,8 @@ constexpr int RECN = JTK_RECN;
 constexpr int QCAP = JTK_QCAP;
 constexpr int BH = JTK_BACK_HALO;
 constexpr int TC = JTK_TILE / 16;  /* 16-byte chunks per tile */
-constexpr int CPT = TC / NT;       /* chunks per thread in the piece-listing step */
-static_assert(TC % NT == 0, "threads per CTA must divide the chunks per tile");
+constexpr int CPT = 1;             /* chunks per thread in the piece-listing step (threads >= TC have none) */
+static_assert(TC <= NT && NT % 32 == 0 && NT <= 1024, "one thread per tile chunk at least");
 
 /* piece records: a token id, or (id space is limited to >= JTK_REC_MIN_ID at registration) a payload */
 constexpr int32_t REC_BASE = (int32_t) 0x80000000;
@@ -229,7 +229,7 @@ __device__ int merge_group(const jtk_tables &T, const uint8_t *p, int n, int32_t
  * kernel 1: split + whole-piece lookup
  * ------------------------------------------------------------------------------------------- */
 template <bool GENERAL>
-__global__ void __launch_bounds__(JTK_NT, 4) jtk_split_lookup_kernel(const __grid_constant__ jtk_encode_args a) {
+__global__ void __launch_bounds__(JTK_NT, 2048 / JTK_NT) jtk_split_lookup_kernel(const __grid_constant__ jtk_encode_args a) {
 	extern __shared__ __align__(16) uint8_t smem[];
 	uint8_t *sb = smem;
 	uint8_t *cls = sb + (JTK_REGION + 16);
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(JTK_NT, 4) jtk_split_lookup_kernel(const __gri
 		/* ---- P0: take a tile ---- */
 		__syncthreads();
 		if (tid == 0) {
-			misc[M_TILE] = atomicAdd(&a.hdr->ticket, 1u);
+			misc[M_TILE] = atomicAdd(&a.sub->ticket, 1u);
 			misc[M_NSLOW] = 0;
 			misc[M_HITS] = 0;
 			misc[M_NDEFER] = 0;
@@ -372,12 +372,12 @@ __global__ void __launch_bounds__(JTK_NT, 4) jtk_split_lookup_kernel(const __gri
 		for (int j = 0; j < CPT; j++) {
 			const int ch = tid * CPT + j;
 			const int64_t gbase = tb + ch * 16;
-			uint32_t m = reinterpret_cast<const uint16_t *>(bmask)[BH / 16 + ch];
+			uint32_t m = ch < TC ? reinterpret_cast<const uint16_t *>(bmask)[BH / 16 + ch] : 0u;
 			if (gbase >= a.total) m = 0;
 			else if (gbase + 16 > a.total) m &= (1u << (int) (a.total - gbase)) - 1u;
 			bits[j] = m;
 			mycount += __popc(m);
-			if (a.piece_flags) {
+			if (a.piece_flags && ch < TC) {
 				const uint32_t real = GENERAL ? m & ~(uint32_t) reinterpret_cast<const uint16_t *>(dmask)[BH / 16 + ch] : m; /* gaps are not pieces */
 				for (int i = 0; i < 16 && gbase + i < a.total; i++) a.piece_flags[gbase + i] = (real >> i) & 1u;
 			}
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(JTK_NT, 4) jtk_split_lookup_kernel(const __gri
 		int base = block_exclusive_scan<NT>(mycount, reinterpret_cast<int *>(misc + M_WSUM), &npieces);
 		for (int j = 0; j < CPT; j++) {
 			const int ch = tid * CPT + j;
-			chunk_pref[ch] = (uint32_t) base;
+			if (ch < TC) chunk_pref[ch] = (uint32_t) base;
 			for (uint32_t m = bits[j]; m;) {
 				const int i = __ffs((int) m) - 1;
 				m &= m - 1;
@@ -456,16 +456,26 @@ __global__ void __launch_bounds__(JTK_NT, 4) jtk_split_lookup_kernel(const __gri
 							bool memo_hit = false;
 							if (n <= JTK_MEMO_MAX_PIECE && a.memo) { /* has this call merged the same piece before? */
 								const jtk_memo_entry *me = a.memo + ((h * 0x9E3779B1u) >> 8 & a.memo_mask);
-								const uint4 q0 = *reinterpret_cast<const uint4 *>(me), q1 = *(reinterpret_cast<const uint4 *>(me) + 1);
-								if (q1.x == ((a.memo_epoch << 8) | 2u) && (q1.y & 0xFFu) == (uint32_t) n && q0.x == key[0] && q0.y == key[1] && q0.z == key[2] &&
-								    q0.w == key[3]) {
+								/* The merge kernel of the previous sub-batch may be filling entries while this kernel reads them: an entry is
+								 * written once per epoch and published by its meta word (data, fence, meta), so whatever is read after
+								 * meta was seen valid is final.  L2 loads: this SM's L1 may hold an older copy of the line. */
+								const uint4 *mp = reinterpret_cast<const uint4 *>(me);
+								uint4 q1 = __ldcg(mp + 1);
+								uint4 q0 = make_uint4(0, 0, 0, 0);
+								bool cand = q1.x == ((a.memo_epoch << 8) | 2u) && (q1.y & 0xFFu) == (uint32_t) n;
+								if (cand) {
+									__threadfence();
+									q0 = __ldcg(mp);
+									q1 = __ldcg(mp + 1);
+								}
+								if (cand && q0.x == key[0] && q0.y == key[1] && q0.z == key[2] && q0.w == key[3]) {
 									const int cnt = (int) (q1.y >> 8);
 									const int off = (int) atomicAdd(&misc[M_SLOWTOK], (uint32_t) cnt); /* dense area of the tile's slowtok slice */
 									int32_t *stok = a.slowtok + lt * (long long) RECN + off;
 									if (!(a.flags & JTK_COUNT_ONLY)) {
 										stok[0] = (int32_t) q1.z;
 										if (cnt > 1) stok[1] = (int32_t) q1.w;
-										for (int k = 2; k < cnt; k++) stok[k] = me->tok[k];
+										for (int k = 2; k < cnt; k++) stok[k] = __ldcg(&me->tok[k]);
 									}
 									out = rec_make(off, cnt);
 									hits += cnt;
@@ -476,8 +486,8 @@ __global__ void __launch_bounds__(JTK_NT, 4) jtk_split_lookup_kernel(const __gri
 							} else if (n <= JTK_SHORT_PIECE) {
 								a.slowq[lt * (long long) QCAP + atomicAdd(&misc[M_NSLOW], 1u)] = (uint16_t) q;
 								atomicAdd(&misc[M_HIST + n], 1u);
-							} else if (n <= JTK_GROUP8_PIECE) a.med8[atomicAdd(&a.hdr->n_med8, 1u)] = ((uint32_t) lt << 14) | (uint32_t) q;
-							else a.med32[atomicAdd(&a.hdr->n_med32, 1u)] = ((uint32_t) lt << 14) | (uint32_t) q;
+							} else if (n <= JTK_GROUP8_PIECE) a.med8[atomicAdd(&a.sub->n_med8, 1u)] = ((uint32_t) lt << 14) | (uint32_t) q;
+							else a.med32[atomicAdd(&a.sub->n_med32, 1u)] = ((uint32_t) lt << 14) | (uint32_t) q;
 						}
 					}
 				}
@@ -507,7 +517,7 @@ __global__ void __launch_bounds__(JTK_NT, 4) jtk_split_lookup_kernel(const __gri
 			a.tile_count[tile] = (int32_t) misc[M_HITS];
 			a.tile_slow_used[tile] = (int32_t) misc[M_SLOWTOK];
 		}
-		if (tid <= JTK_SHORT_PIECE && misc[M_HIST + tid]) atomicAdd(&a.hdr->short_cnt[tid], misc[M_HIST + tid]);
+		if (tid <= JTK_SHORT_PIECE && misc[M_HIST + tid]) atomicAdd(&a.sub->short_cnt[tid], misc[M_HIST + tid]);
 	}
 }
 
@@ -544,14 +554,14 @@ __global__ void jtk_short_offsets_kernel(const jtk_encode_args a) {
 	if (threadIdx.x != 0) return;
 	unsigned run = 0;
 	for (int n = 0; n <= JTK_SHORT_PIECE; n++) {
-		a.hdr->short_base[n] = run;
-		a.hdr->short_cur[n] = run;
-		run += a.hdr->short_cnt[n];
+		a.sub->short_base[n] = run;
+		a.sub->short_cur[n] = run;
+		run += a.sub->short_cnt[n];
 	}
-	a.hdr->short_base[JTK_SHORT_PIECE + 1] = run;
-	a.hdr->short_next[0] = 0;
-	a.hdr->short_next[1] = a.hdr->short_base[17];
-	a.hdr->short_next[2] = a.hdr->short_base[33];
+	a.sub->short_base[JTK_SHORT_PIECE + 1] = run;
+	a.sub->short_next[0] = 0;
+	a.sub->short_next[1] = a.sub->short_base[17];
+	a.sub->short_next[2] = a.sub->short_base[33];
 }
 
 constexpr int SNT = 128;
@@ -570,7 +580,7 @@ __global__ void __launch_bounds__(SNT) jtk_short_scatter_kernel(const __grid_con
 	__syncthreads();
 	for (int k = tid; k < S; k += SNT) atomicAdd(&s_hist[(rec_payload(rec[sq[k]]) & 0x7FFu) + 1], 1u);
 	__syncthreads();
-	if (tid <= JTK_SHORT_PIECE) s_cur[tid] = s_hist[tid] ? atomicAdd(&a.hdr->short_cur[tid], s_hist[tid]) : 0u; /* reserve a range per length */
+	if (tid <= JTK_SHORT_PIECE) s_cur[tid] = s_hist[tid] ? atomicAdd(&a.sub->short_cur[tid], s_hist[tid]) : 0u; /* reserve a range per length */
 	__syncthreads();
 	for (int k = tid; k < S; k += SNT) {
 		const int q = sq[k];
@@ -586,8 +596,8 @@ __global__ void __launch_bounds__(NTHREADS, 7) jtk_merge_short_kernel(const __gr
 	const jtk_tables &T = a.T;
 	const int tid = threadIdx.x, lane = tid & 31;
 	const bool write_tok = !(a.flags & JTK_COUNT_ONLY);
-	const unsigned end = a.hdr->short_base[NSLOT + 1];
-	unsigned *cursor = &a.hdr->short_next[NSLOT == 16 ? 0 : NSLOT == 32 ? 1 : 2];
+	const unsigned end = a.sub->short_base[NSLOT + 1];
+	unsigned *cursor = &a.sub->short_next[NSLOT == 16 ? 0 : NSLOT == 32 ? 1 : 2];
 	int32_t *tk = s_scr + tid, *rk = s_scr + NSLOT * NTHREADS + tid;
 	for (;;) {
 		unsigned idx = 0;
@@ -648,13 +658,13 @@ __global__ void __launch_bounds__(GNTM) jtk_merge_medium_kernel(const __grid_con
 	int32_t *wtok = s_scr + warp * 2 * JTK_LONG_PIECE, *wrk = wtok + JTK_LONG_PIECE;
 	/* 8-lane groups */
 	{
-		const unsigned n8 = a.hdr->n_med8;
+		const unsigned n8 = a.sub->n_med8;
 		const int g = lane >> 3, gl = lane & 7;
 		const unsigned gmask = 0xFFu << (g * 8);
 		int32_t *tk = wtok + g * JTK_GROUP8_PIECE, *rk = wrk + g * JTK_GROUP8_PIECE;
 		for (;;) {
 			unsigned idx = 0;
-			if (gl == 0) idx = atomicAdd(&a.hdr->cursor8, 1u);
+			if (gl == 0) idx = atomicAdd(&a.sub->cursor8, 1u);
 			idx = __shfl_sync(gmask, idx, g * 8);
 			if (idx >= n8) break;
 			const uint32_t e = a.med8[idx];
@@ -685,10 +695,10 @@ __global__ void __launch_bounds__(GNTM) jtk_merge_medium_kernel(const __grid_con
 	__syncwarp();
 	/* whole warps */
 	{
-		const unsigned n32 = a.hdr->n_med32;
+		const unsigned n32 = a.sub->n_med32;
 		for (;;) {
 			unsigned idx = 0;
-			if (lane == 0) idx = atomicAdd(&a.hdr->cursor32, 1u);
+			if (lane == 0) idx = atomicAdd(&a.sub->cursor32, 1u);
 			idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
 			if (idx >= n32) break;
 			const uint32_t e = a.med32[idx];
@@ -755,9 +765,9 @@ __global__ void __launch_bounds__(1024, 1) jtk_tile_scan_kernel(const jtk_encode
 	if (tid == 0) {
 		a.tile_base[a.tile_end] = s_carry;
 		a.hdr->total_tokens = (unsigned long long) s_carry;
-		a.hdr->ticket = 0; /* the next sub-batch starts its tickets and medium-piece lists at zero */
-		a.hdr->n_med8 = a.hdr->n_med32 = a.hdr->cursor8 = a.hdr->cursor32 = 0;
-		for (int n = 0; n <= JTK_SHORT_PIECE; n++) a.hdr->short_cnt[n] = 0;
+		a.sub->ticket = 0; /* the next sub-batch starts its tickets and medium-piece lists at zero */
+		a.sub->n_med8 = a.sub->n_med32 = a.sub->cursor8 = a.sub->cursor32 = 0;
+		for (int n = 0; n <= JTK_SHORT_PIECE; n++) a.sub->short_cnt[n] = 0;
 		if (!(a.flags & JTK_COUNT_ONLY) && a.ids && s_carry > a.ids_cap) a.hdr->overflow = 1;
 	}
 }
@@ -766,12 +776,18 @@ __global__ void __launch_bounds__(1024, 1) jtk_tile_scan_kernel(const jtk_encode
  * kernel 4: ids to their final position (one CTA per tile) + document token offsets
  * ------------------------------------------------------------------------------------------- */
 constexpr int GNT = 256;
-constexpr int GATHER_SMEM = (int) sizeof(int32_t) * RECN + (int) sizeof(uint16_t) * (RECN + 8);
+constexpr int GIPT = 8;     /* consecutive pieces per thread and round: one block scan per 2048 pieces */
+constexpr int GCAP = 4096;  /* tokens staged in shared memory at a time for coalesced stores */
 
-__global__ void __launch_bounds__(GNT) jtk_gather_kernel(const __grid_constant__ jtk_encode_args a) {
-	extern __shared__ __align__(16) uint8_t gsm[];
-	int32_t *s_tok = reinterpret_cast<int32_t *>(gsm);                            /* the tile's tokens in order, staged for coalesced stores */
-	uint16_t *s_prefix = reinterpret_cast<uint16_t *>(gsm + sizeof(int32_t) * RECN); /* tokens before each piece of the tile */
+__device__ __forceinline__ int rec_count(int32_t r) {
+	if (rec_is_id(r)) return 1;
+	const uint32_t pl = rec_payload(r);
+	return (pl & (REC_LONG | REC_SKIP)) ? 0 : (int) (pl & 0x7FFu) + 1;
+}
+
+__global__ void __launch_bounds__(GNT, 8) jtk_gather_kernel(const __grid_constant__ jtk_encode_args a) {
+	__shared__ __align__(16) int32_t s_tok[GCAP];          /* the round's tokens in order */
+	__shared__ uint16_t s_gpref[RECN / GIPT + 2];            /* tokens of the tile before each group of GIPT pieces */
 	__shared__ int s_w[GNT / 32];
 	const int tid = threadIdx.x;
 	const long long tile = a.tile_begin + blockIdx.x;
@@ -783,60 +799,74 @@ __global__ void __launch_bounds__(GNT) jtk_gather_kernel(const __grid_constant__
 	const int32_t *rec = a.rec + lt * (long long) RECN;
 	const int32_t *stok = a.slowtok + lt * (long long) RECN;
 	const bool write_ids = !(a.flags & JTK_COUNT_ONLY) && a.ids != nullptr && !a.hdr->overflow;
+	int32_t *dst = a.ids + base;
 	int carry = 0;
-	constexpr int IPT = 8; /* consecutive pieces per thread and round: one block scan per 2048 pieces */
-	for (int q0 = 0; q0 < P; q0 += GNT * IPT) {
-		const int qb = q0 + tid * IPT;
-		int32_t r[IPT];
-		int cnt[IPT];
+	for (int q0 = 0; q0 < P; q0 += GNT * GIPT) {
+		const int qb = q0 + tid * GIPT;
+		int32_t r[GIPT];
+		int cnt[GIPT];
+		if (qb + GIPT <= P) { /* the tile's slice of rec is 16-byte aligned and qb a multiple of 8 */
+			const int4 v0 = *reinterpret_cast<const int4 *>(rec + qb), v1 = *reinterpret_cast<const int4 *>(rec + qb + 4);
+			r[0] = v0.x, r[1] = v0.y, r[2] = v0.z, r[3] = v0.w, r[4] = v1.x, r[5] = v1.y, r[6] = v1.z, r[7] = v1.w;
+		} else {
+#pragma unroll
+			for (int j = 0; j < GIPT; j++) r[j] = qb + j < P ? rec[qb + j] : (int32_t) (REC_BASE + (int32_t) REC_SKIP);
+		}
 		int mine = 0;
 #pragma unroll
-		for (int j = 0; j < IPT; j++) {
-			const int q = qb + j;
-			r[j] = 0;
-			cnt[j] = 0;
-			if (q < P) {
-				r[j] = rec[q];
-				if (rec_is_id(r[j])) cnt[j] = 1;
-				else if (!(rec_payload(r[j]) & (REC_LONG | REC_SKIP))) cnt[j] = (int) (rec_payload(r[j]) & 0x7FFu) + 1;
-			}
+		for (int j = 0; j < GIPT; j++) {
+			cnt[j] = rec_count(r[j]);
 			mine += cnt[j];
 		}
 		int round_total;
 		int excl = carry + block_exclusive_scan<GNT>(mine, s_w, &round_total);
+		if (qb < P) s_gpref[qb / GIPT] = (uint16_t) excl;
 #pragma unroll
-		for (int j = 0; j < IPT; j++) {
-			const int q = qb + j;
-			if (q < P) {
-				s_prefix[q] = (uint16_t) excl;
-				if (rec_is_id(r[j])) {
-					s_tok[excl] = r[j];
-				} else {
-					const uint32_t pl = rec_payload(r[j]);
-					if (pl & REC_LONG) {
-						a.long_list[pl & 0x0FFFFFFFu].insert_at = base + excl;
-					} else if (write_ids && !(pl & REC_SKIP)) {
-						const int off = (int) ((pl >> 11) & 0x3FFFu); /* dense area of the tile's slowtok slice */
-						for (int k = 0; k < cnt[j]; k++) s_tok[excl + k] = stok[off + k];
+		for (int j = 0; j < GIPT; j++)
+			if (qb + j < P && !rec_is_id(r[j]) && (rec_payload(r[j]) & REC_LONG)) {
+				int before = excl - carry;
+				for (int i = 0; i < j; i++) before += cnt[i];
+				a.long_list[rec_payload(r[j]) & 0x0FFFFFFFu].insert_at = base + carry + before;
+			}
+		if (write_ids) {
+			/* stage the round's tokens in windows of GCAP (one window unless the tile is unusually token-dense), store coalesced */
+			for (int w0 = 0; w0 < round_total; w0 += GCAP) {
+				int pos = excl - carry - w0; /* window-relative position of this thread's first token */
+#pragma unroll
+				for (int j = 0; j < GIPT; j++) {
+					if (cnt[j] && pos + cnt[j] > 0 && pos < GCAP) {
+						if (rec_is_id(r[j])) {
+							s_tok[pos] = r[j];
+						} else {
+							const int off = (int) ((rec_payload(r[j]) >> 11) & 0x3FFFu); /* dense area of the tile's slowtok slice */
+							for (int k = 0; k < cnt[j]; k++)
+								if (pos + k >= 0 && pos + k < GCAP) s_tok[pos + k] = stok[off + k];
+						}
 					}
+					pos += cnt[j];
 				}
-				excl += cnt[j];
+				__syncthreads();
+				const int nw = min(GCAP, round_total - w0);
+				for (int k = tid; k < nw; k += GNT) dst[carry + w0 + k] = s_tok[k];
+				if (w0 + GCAP < round_total) __syncthreads();
 			}
 		}
 		carry += round_total;
-	}
-	if (tid == 0) s_prefix[P] = (uint16_t) carry;
-	__syncthreads();
-	if (write_ids) {
-		int32_t *dst = a.ids + base;
-		for (int k = tid; k < carry; k += GNT) dst[k] = s_tok[k];
+		__syncthreads(); /* s_tok / s_w are reused by the next round */
 	}
 	if (a.tok_off) {
+		__syncthreads();
 		for (int64_t d = a.tile_first_doc[tile] + tid; d <= a.ndocs; d += GNT) {
 			const int64_t g = a.doc_off[d];
 			if (g >= tb + JTK_TILE) break;
 			if (g < tb) continue;
-			a.tok_off[d] = base + s_prefix[a.tok_off[d]];
+			const int pi = (int) a.tok_off[d]; /* tile-local index of the document's first piece (jtk_split_lookup_kernel) */
+			int before = carry;
+			if (pi < P) {
+				before = s_gpref[pi / GIPT];
+				for (int q = pi - pi % GIPT; q < pi; q++) before += rec_count(rec[q]);
+			}
+			a.tok_off[d] = base + before;
 		}
 	}
 }
@@ -1178,7 +1208,7 @@ cudaError_t jtk_encode_kernel_setup() {
 	if (e != cudaSuccess) return e;
 	e = cudaFuncSetAttribute(jtk_split_lookup_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, JTK_SMEM_BYTES);
 	if (e != cudaSuccess) return e;
-	return cudaFuncSetAttribute(jtk_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GATHER_SMEM);
+	return cudaSuccess;
 }
 
 cudaError_t jtk_launch_tile_first_doc(const int64_t *doc_off, int64_t ndocs, int64_t ntiles, int32_t *out, cudaStream_t st) {
@@ -1187,37 +1217,50 @@ cudaError_t jtk_launch_tile_first_doc(const int64_t *doc_off, int64_t ndocs, int
 	return cudaGetLastError();
 }
 
-/* the four kernels of one sub-batch [a.tile_begin, a.tile_end) */
-cudaError_t jtk_launch_sub_batch(const jtk_encode_args &a, int num_sms, cudaEvent_t k0, cudaEvent_t k1, cudaStream_t st, const jtk_side_streams *side) {
+static unsigned l2_window_attr(const jtk_encode_args &a, cudaLaunchAttribute *attr) {
+	/* the table-probing kernels run with the hot tables pinned in L2 (persisting hits, streaming misses) */
+	if (a.l2_bytes == 0) return 0;
+	attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+	attr[0].val.accessPolicyWindow.base_ptr = const_cast<void *>(a.l2_base);
+	attr[0].val.accessPolicyWindow.num_bytes = a.l2_bytes;
+	attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+	attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+	attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+	return 1;
+}
+
+/* split + whole-piece lookup of the sub-batch [a.tile_begin, a.tile_end).  ctas_per_sm > 0: persistent CTAs taking tiles by
+ * ticket; 0: one CTA per tile, so that kernels of the previous sub-batch (higher-priority streams) get SM slots as CTAs retire. */
+cudaError_t jtk_launch_split(const jtk_encode_args &a, int num_sms, int ctas_per_sm, cudaEvent_t k0, cudaEvent_t k1, cudaStream_t st) {
 	const int64_t nt = a.tile_end - a.tile_begin;
 	if (nt <= 0) return cudaSuccess;
-	int64_t grid = (int64_t) num_sms * 4;
+	int64_t grid = ctas_per_sm > 0 ? (int64_t) num_sms * (2048 / JTK_NT) : nt;
 	if (grid > nt) grid = nt;
-	/* the table-probing kernels run with the hot tables pinned in L2 (persisting hits, streaming misses) */
 	cudaLaunchAttribute attr[1];
-	unsigned nattr = 0;
-	if (a.l2_bytes > 0) {
-		attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-		attr[0].val.accessPolicyWindow.base_ptr = const_cast<void *>(a.l2_base);
-		attr[0].val.accessPolicyWindow.num_bytes = a.l2_bytes;
-		attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
-		attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-		attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-		nattr = 1;
-	}
 	cudaLaunchConfig_t cfg;
 	memset(&cfg, 0, sizeof(cfg));
 	cfg.stream = st;
 	cfg.attrs = attr;
-	cfg.numAttrs = nattr;
-	if (k0) cudaEventRecord(k0, st);
+	cfg.numAttrs = l2_window_attr(a, attr);
 	cfg.gridDim = dim3((unsigned) grid);
 	cfg.blockDim = dim3(JTK_NT);
 	cfg.dynamicSmemBytes = JTK_SMEM_BYTES;
+	if (k0) cudaEventRecord(k0, st);
 	if (a.T.pattern_kind == JTK_PAT_GENERAL) cudaLaunchKernelEx(&cfg, jtk_split_lookup_kernel<true>, a);
 	else cudaLaunchKernelEx(&cfg, jtk_split_lookup_kernel<false>, a);
 	if (k1) cudaEventRecord(k1, st);
-	cfg.dynamicSmemBytes = 0;
+	return cudaGetLastError();
+}
+
+/* everything after it: sort the unresolved short pieces by length, merge, scan, gather */
+cudaError_t jtk_launch_post(const jtk_encode_args &a, int num_sms, cudaStream_t st, const jtk_side_streams *side) {
+	const int64_t nt = a.tile_end - a.tile_begin;
+	if (nt <= 0) return cudaSuccess;
+	cudaLaunchAttribute attr[1];
+	cudaLaunchConfig_t cfg;
+	memset(&cfg, 0, sizeof(cfg));
+	cfg.attrs = attr;
+	cfg.numAttrs = l2_window_attr(a, attr);
 	jtk_short_offsets_kernel<<<1, 32, 0, st>>>(a);
 	jtk_short_scatter_kernel<<<(unsigned) nt, SNT, 0, st>>>(a);
 	/* the four merge kernels are independent of each other (own lists, own pieces): longest chains first, side by side */
@@ -1244,7 +1287,7 @@ cudaError_t jtk_launch_sub_batch(const jtk_encode_args &a, int num_sms, cudaEven
 			cudaStreamWaitEvent(st, side->join[i], 0);
 		}
 	jtk_tile_scan_kernel<<<1, 1024, 0, st>>>(a);
-	jtk_gather_kernel<<<(unsigned) nt, GNT, GATHER_SMEM, st>>>(a);
+	jtk_gather_kernel<<<(unsigned) nt, GNT, 0, st>>>(a);
 	return cudaGetLastError();
 }
 

@@ -25,16 +25,23 @@ struct jtk_batch_header {
 	unsigned long long total_tokens;
 	unsigned int n_long;
 	unsigned int overflow;   /* ids capacity exceeded */
-	unsigned int ticket;     /* tile ticket counter */
 	unsigned int long_next;  /* work counter of the long-piece kernel */
 	unsigned int violations; /* long-piece rounds that had to fall back to one-merge-at-a-time */
-	unsigned int n_med8, n_med32;   /* medium pieces of the current sub-batch (33..256 bytes / 257..JTK_LONG_PIECE bytes) */
+	unsigned int rx_ticket;  /* document counter of jtk_general_split_kernel */
+	unsigned int pad;
+};
+
+/* Counters of one sub-batch.  Two sub-batches are in flight at a time (the split+lookup kernel of one runs while the merge /
+ * gather kernels of the previous one finish), so there are two of these and two sets of per-sub-batch buffers ("lanes"). */
+struct jtk_sub_header {
+	unsigned int ticket;     /* tile ticket counter */
+	unsigned int n_med8, n_med32;   /* medium pieces of the sub-batch (65..256 bytes / 257..JTK_LONG_PIECE bytes) */
 	unsigned int cursor8, cursor32; /* work counters of jtk_merge_medium_kernel */
 	unsigned int short_cnt[JTK_SHORT_PIECE + 2];  /* unresolved short pieces of the sub-batch by length */
 	unsigned int short_base[JTK_SHORT_PIECE + 2]; /* exclusive scan of short_cnt */
 	unsigned int short_cur[JTK_SHORT_PIECE + 2];  /* scatter cursors */
 	unsigned int short_next[4];                   /* work counters of the three jtk_merge_short_kernel launches */
-	unsigned int rx_ticket; /* document counter of jtk_general_split_kernel */
+	unsigned int pad;
 };
 
 #define JTK_RECN (JTK_TILE + JTK_FWD_HALO) /* per-tile slots of rec / slowtok: pieces + unresolved pieces <= JTK_RECN */
@@ -43,7 +50,8 @@ struct jtk_batch_header {
 #define JTK_GROUP8_PIECE 256                /* up to this length a medium piece is merged by 8 lanes, above by a warp */
 #define JTK_MED8_PER_TILE (JTK_RECN / (JTK_SHORT_PIECE + 1) + 1)
 #define JTK_MED32_PER_TILE (JTK_RECN / (JTK_GROUP8_PIECE + 1) + 1)
-#define JTK_DEFAULT_SUB_TILES 16384        /* tiles per sub-batch: 128 MiB of input (measured: larger sub-batches win over L2 locality) */
+#define JTK_DEFAULT_SUB_TILES ((128 << 20) / JTK_TILE) /* tiles per sub-batch: 128 MiB of input (measured: larger sub-batches win over L2 locality) */
+#define JTK_FIRST_SUB_TILES ((16 << 20) / JTK_TILE)    /* a small first sub-batch warms the piece memo */
 
 struct jtk_encode_args {
 	jtk_tables T;
@@ -69,6 +77,7 @@ struct jtk_encode_args {
 	uint32_t *med8;        /* JTK_MED8_PER_TILE per tile: (tile index << 14 | piece index) of unresolved pieces of 33..256 bytes */
 	uint32_t *med32;       /* JTK_MED32_PER_TILE per tile: same for 257..JTK_LONG_PIECE bytes */
 	jtk_batch_header *hdr;
+	jtk_sub_header *sub;   /* the lane's counters */
 	int32_t *ids;
 	int64_t ids_cap;
 	int64_t *tok_off;
@@ -98,8 +107,10 @@ struct jtk_side_streams {
 	cudaStream_t s[3];
 	cudaEvent_t fork, join[3];
 };
-/* the kernels of one sub-batch; k0/k1 (nullable) bracket the split+lookup kernel */
-cudaError_t jtk_launch_sub_batch(const jtk_encode_args &a, int num_sms, cudaEvent_t k0, cudaEvent_t k1, cudaStream_t st, const jtk_side_streams *side);
+/* the kernels of one sub-batch in two parts, so that the second part of sub-batch k can run (on its own stream, other lane of
+ * buffers) next to the first part of sub-batch k + 1; k0/k1 (nullable) bracket the split+lookup kernel */
+cudaError_t jtk_launch_split(const jtk_encode_args &a, int num_sms, int ctas_per_sm, cudaEvent_t k0, cudaEvent_t k1, cudaStream_t st);
+cudaError_t jtk_launch_post(const jtk_encode_args &a, int num_sms, cudaStream_t st, const jtk_side_streams *side);
 cudaError_t jtk_launch_finalize(const jtk_encode_args &a, cudaStream_t st);
 /* JTK_PAT_GENERAL: runs the split program over every document (one thread per document) before the sub-batches; rx_start / rx_skip must be zeroed */
 #define JTK_RX_THREADS (148 * 128)

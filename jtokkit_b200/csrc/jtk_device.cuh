@@ -209,29 +209,42 @@ JTK_HD void jtk_classify_generic(jtk_tile_ctx &c, int chunk) {
 			break;
 		}
 	}
-	uint32_t out[4] = {0, 0, 0, 0};
-	for (int i = 0; i < 16; i++) {
+	/* One iteration per CHARACTER (not per byte): the lanes of a warp stay together on multi-byte text instead of taking
+	 * turns in the decode branch.  A character's class bytes (lead: class, continuation bytes: class | JTK_CONT) are OR-ed
+	 * into a 128-bit accumulator at its byte offset; what sticks out beyond byte 15 belongs to the next chunk, which
+	 * recomputes it with the look-back above. */
+	uint64_t lo = 0, hi = 0;
+	int i = 0;
+	if (rem > 0) { /* continuation bytes of a character that started in the previous chunk */
+		const uint32_t pat = ((uint32_t) (cur | JTK_CONT) * 0x010101u) & ((1u << (8 * rem)) - 1u);
+		lo = pat;
+		i = rem;
+	}
+	while (i < 16) {
 		const int r = r0 + i;
-		const uint8_t b = c.sb[r];
-		uint32_t v;
-		if (rem > 0) { /* inside a validated character */
-			v = (uint32_t) (cur | JTK_CONT);
-			rem--;
-		} else if (b < 0x80) {
-			v = c.ascii_lut[b];
+		const uint32_t b = c.sb[r];
+		uint32_t pat;
+		int len = 1;
+		if (b < 0x80) {
+			pat = c.ascii_lut[b];
 		} else {
-			int len;
-			cur = jtk_decode_char_fast(T, c.sb, r, dwin >> (4 + i), &len);
-			rem = len - 1;
-			v = (uint32_t) cur;
+			const uint32_t k = (uint32_t) jtk_decode_char_fast(T, c.sb, r, dwin >> (4 + i), &len);
+			pat = (k * 0x01010101u) | 0x80808000u;
+			if (len < 4) pat &= (1u << (8 * len)) - 1u;
 		}
-		out[i >> 2] |= v << (8 * (i & 3));
+		if (i < 8) {
+			lo |= (uint64_t) pat << (8 * i);
+			if (i > 4) hi |= (uint64_t) pat >> (8 * (8 - i));
+		} else {
+			hi |= (uint64_t) pat << (8 * (i - 8));
+		}
+		i += len;
 	}
 	uint32_t *o = reinterpret_cast<uint32_t *>(c.cls + r0);
-	o[0] = out[0];
-	o[1] = out[1];
-	o[2] = out[2];
-	o[3] = out[3];
+	o[0] = (uint32_t) lo;
+	o[1] = (uint32_t) (lo >> 32);
+	o[2] = (uint32_t) hi;
+	o[3] = (uint32_t) (hi >> 32);
 }
 
 JTK_HD void jtk_classify_chunk(jtk_tile_ctx &c, int chunk) {

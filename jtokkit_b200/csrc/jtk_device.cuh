@@ -175,6 +175,9 @@ JTK_HD int jtk_decode_char_fast(const jtk_tables &T, const uint8_t *sb, int r, u
 	return jtk_cp_class(T, cp);
 }
 
+/* bit b of each of the four bytes of w -> 4 mask bits */
+JTK_HD uint32_t jtk_plane4(uint32_t w, int b) { return (((w >> b) & 0x01010101u) * 0x01020408u) >> 24; }
+
 /* General classification of the 16 bytes of chunk `chunk` (region indices 16*chunk ..) into c.cls: UTF-8 decoding. */
 JTK_HD void jtk_classify_generic(jtk_tile_ctx &c, int chunk) {
 	const jtk_tables &T = *c.T;
@@ -209,42 +212,44 @@ JTK_HD void jtk_classify_generic(jtk_tile_ctx &c, int chunk) {
 			break;
 		}
 	}
-	/* One iteration per CHARACTER (not per byte): the lanes of a warp stay together on multi-byte text instead of taking
-	 * turns in the decode branch.  A character's class bytes (lead: class, continuation bytes: class | JTK_CONT) are OR-ed
-	 * into a 128-bit accumulator at its byte offset; what sticks out beyond byte 15 belongs to the next chunk, which
-	 * recomputes it with the look-back above. */
-	uint64_t lo = 0, hi = 0;
-	int i = 0;
-	if (rem > 0) { /* continuation bytes of a character that started in the previous chunk */
-		const uint32_t pat = ((uint32_t) (cur | JTK_CONT) * 0x010101u) & ((1u << (8 * rem)) - 1u);
-		lo = pat;
-		i = rem;
+	/* ASCII bytes: four table reads per word like the fast path (non-ASCII bytes are masked to class 0 = "other", which is
+	 * also what stray continuation bytes and invalid leads are).  Then one iteration per multi-byte CHARACTER: its class
+	 * bytes (lead: class, continuation bytes: class | JTK_CONT) are OR-ed into the 128-bit result at its byte offset; what
+	 * sticks out beyond byte 15 belongs to the next chunk, which recomputes it with the look-back above. */
+	const uint32_t *w = reinterpret_cast<const uint32_t *>(c.sb + r0);
+	const uint8_t *lut = c.ascii_lut;
+	uint32_t o[4], leads = 0;
+	for (int k = 0; k < 4; k++) {
+		const uint32_t x = w[k], a7 = x & 0x7F7F7F7Fu;
+		const uint32_t v = lut[a7 & 0xFF] | (lut[(a7 >> 8) & 0xFF] << 8) | (lut[(a7 >> 16) & 0xFF] << 16) | ((uint32_t) lut[a7 >> 24] << 24);
+		o[k] = v & ~(((x & 0x80808080u) >> 7) * 0xFFu);
+		leads |= jtk_plane4(x & (x << 1), 7) << (4 * k); /* bytes >= 0xC0 */
 	}
-	while (i < 16) {
-		const int r = r0 + i;
-		const uint32_t b = c.sb[r];
-		uint32_t pat;
-		int len = 1;
-		if (b < 0x80) {
-			pat = c.ascii_lut[b];
-		} else {
-			const uint32_t k = (uint32_t) jtk_decode_char_fast(T, c.sb, r, dwin >> (4 + i), &len);
-			pat = (k * 0x01010101u) | 0x80808000u;
-			if (len < 4) pat &= (1u << (8 * len)) - 1u;
-		}
+	uint64_t lo = o[0] | ((uint64_t) o[1] << 32), hi = o[2] | ((uint64_t) o[3] << 32);
+	if (rem > 0) lo |= ((uint32_t) (cur | JTK_CONT) * 0x010101u) & ((1u << (8 * rem)) - 1u); /* a character that started in the previous chunk */
+	for (uint32_t m = leads; m; m &= m - 1) {
+#if defined(__CUDA_ARCH__)
+		const int i = __ffs((int) m) - 1;
+#else
+		const int i = __builtin_ctz(m);
+#endif
+		int len;
+		const uint32_t k = (uint32_t) jtk_decode_char_fast(T, c.sb, r0 + i, dwin >> (4 + i), &len);
+		if (len == 1) continue; /* invalid: stays "other" */
+		uint32_t pat = (k * 0x01010101u) | 0x80808000u;
+		if (len < 4) pat &= (1u << (8 * len)) - 1u;
 		if (i < 8) {
 			lo |= (uint64_t) pat << (8 * i);
 			if (i > 4) hi |= (uint64_t) pat >> (8 * (8 - i));
 		} else {
 			hi |= (uint64_t) pat << (8 * (i - 8));
 		}
-		i += len;
 	}
-	uint32_t *o = reinterpret_cast<uint32_t *>(c.cls + r0);
-	o[0] = (uint32_t) lo;
-	o[1] = (uint32_t) (lo >> 32);
-	o[2] = (uint32_t) hi;
-	o[3] = (uint32_t) (hi >> 32);
+	uint32_t *out = reinterpret_cast<uint32_t *>(c.cls + r0);
+	out[0] = (uint32_t) lo;
+	out[1] = (uint32_t) (lo >> 32);
+	out[2] = (uint32_t) hi;
+	out[3] = (uint32_t) (hi >> 32);
 }
 
 JTK_HD void jtk_classify_chunk(jtk_tile_ctx &c, int chunk) {
@@ -472,8 +477,6 @@ JTK_HD bool jtk_is_piece_start(const jtk_tile_ctx &c, int r, int cur, int *nrun)
  * The formulas are the rules of jtk_is_piece_start written as boolean algebra; the emulator test
  * (tests/test_emu_cpu.py) fuzzes both paths against the oracle.
  * ------------------------------------------------------------------------------------------- */
-/* bit b of each of the four bytes of w -> 4 mask bits */
-JTK_HD uint32_t jtk_plane4(uint32_t w, int b) { return (((w >> b) & 0x01010101u) * 0x01020408u) >> 24; }
 
 /* spread `seed` forward (towards higher positions) through runs of `run`: result has every position reachable from a
  * seed bit by stepping +1 while staying inside run */

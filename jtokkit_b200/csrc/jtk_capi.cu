@@ -649,7 +649,7 @@ static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspa
 	a.doc_status = d_doc_status;
 	a.flags = flags;
 	a.piece_flags = d_piece_flags;
-	if (memo) {
+	if (memo && w->nlanes == 1) { /* the two-lane pipeline would read the memo while the other lane's merge kernel fills it */
 		a.memo = memo->p;
 		a.memo_mask = JTK_MEMO_ENTRIES - 1;
 		a.memo_epoch = memo->epoch;
@@ -681,7 +681,7 @@ static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspa
 	/* sub-batches: a small first one (16 MiB) so that the piece memo is warm early, then full-size ones */
 	const int64_t sub = w->sub_tiles;
 	std::vector<int64_t> cuts(1, 0);
-	if (memo && ntiles > 4 * JTK_FIRST_SUB_TILES) cuts.push_back(JTK_FIRST_SUB_TILES);
+	if (a.memo && ntiles > 4 * JTK_FIRST_SUB_TILES) cuts.push_back(JTK_FIRST_SUB_TILES);
 	while (cuts.back() < ntiles) cuts.push_back(std::min<int64_t>(ntiles, cuts.back() + sub));
 	const int64_t nsub = (int64_t) cuts.size() - 1;
 	if (time_kernel)

@@ -456,18 +456,11 @@ __global__ void __launch_bounds__(JTK_NT, 2048 / JTK_NT) jtk_split_lookup_kernel
 							bool memo_hit = false;
 							if (n <= JTK_MEMO_MAX_PIECE && a.memo) { /* has this call merged the same piece before? */
 								const jtk_memo_entry *me = a.memo + ((h * 0x9E3779B1u) >> 8 & a.memo_mask);
-								/* The merge kernel of the previous sub-batch may be filling entries while this kernel reads them: an entry is
-								 * written once per epoch and published by its meta word (data, fence, meta), so whatever is read after
-								 * meta was seen valid is final.  L2 loads: this SM's L1 may hold an older copy of the line. */
+								/* entries are written by the merge kernel of EARLIER sub-batches of this call (stream ordered, never while this
+								 * kernel runs: the two-lane pipeline runs without a memo) */
 								const uint4 *mp = reinterpret_cast<const uint4 *>(me);
-								uint4 q1 = __ldcg(mp + 1);
-								uint4 q0 = make_uint4(0, 0, 0, 0);
-								bool cand = q1.x == ((a.memo_epoch << 8) | 2u) && (q1.y & 0xFFu) == (uint32_t) n;
-								if (cand) {
-									__threadfence();
-									q0 = __ldcg(mp);
-									q1 = __ldcg(mp + 1);
-								}
+								const uint4 q0 = mp[0], q1 = mp[1];
+								const bool cand = q1.x == ((a.memo_epoch << 8) | 2u) && (q1.y & 0xFFu) == (uint32_t) n;
 								if (cand && q0.x == key[0] && q0.y == key[1] && q0.z == key[2] && q0.w == key[3]) {
 									const int cnt = (int) (q1.y >> 8);
 									const int off = (int) atomicAdd(&misc[M_SLOWTOK], (uint32_t) cnt); /* dense area of the tile's slowtok slice */
@@ -475,7 +468,7 @@ __global__ void __launch_bounds__(JTK_NT, 2048 / JTK_NT) jtk_split_lookup_kernel
 									if (!(a.flags & JTK_COUNT_ONLY)) {
 										stok[0] = (int32_t) q1.z;
 										if (cnt > 1) stok[1] = (int32_t) q1.w;
-										for (int k = 2; k < cnt; k++) stok[k] = __ldcg(&me->tok[k]);
+										for (int k = 2; k < cnt; k++) stok[k] = me->tok[k];
 									}
 									out = rec_make(off, cnt);
 									hits += cnt;

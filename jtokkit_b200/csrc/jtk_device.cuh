@@ -136,6 +136,13 @@ JTK_HD int jtk_decode_char(const jtk_tables &T, const uint8_t *s, int64_t p, int
 	return jtk_cp_class(T, cp);
 }
 
+/* read-only global load (non-coherent path on the device: lets the compiler batch independent loads) */
+#if defined(__CUDA_ARCH__)
+#define JTK_LDG(ptr) __ldg(ptr)
+#else
+#define JTK_LDG(ptr) (*(ptr))
+#endif
+
 struct jtk_region_start {
 	const jtk_tile_ctx *c;
 	JTK_HD bool operator()(int64_t r) const { return jtk_docstart(*c, (int) r); }
@@ -737,6 +744,20 @@ JTK_HD void jtk_lookup_pair2(const jtk_tables &T, int32_t l1, int32_t r1, int32_
 	*o2 = jtk_pair_resolve(T, b2, c0, c1, l2, r2);
 }
 
+/* Up to four rank probes with all slot loads in flight together; probe i is skipped (JTK_RANK_MAX) when bit i of `valid` is clear. */
+JTK_HD void jtk_lookup_pair4(const jtk_tables &T, const int32_t *l, const int32_t *r, uint32_t valid, int32_t *out) {
+	uint32_t b[4];
+	jtk_slot s[8];
+	for (int i = 0; i < 4; i++) {
+		b[i] = jtk_hash_pair(l[i], r[i]) & T.mask_p;
+		if ((valid >> i) & 1u) {
+			s[2 * i] = T.pair[2 * b[i]];
+			s[2 * i + 1] = T.pair[2 * b[i] + 1];
+		}
+	}
+	for (int i = 0; i < 4; i++) out[i] = ((valid >> i) & 1u) ? jtk_pair_resolve(T, b[i], s[2 * i], s[2 * i + 1], l[i], r[i]) : JTK_RANK_MAX;
+}
+
 /* keys of 25..max_token_len bytes: filter on (first eight bytes, length) first, the byte-wise hash only for survivors */
 JTK_HD int32_t jtk_lookup_long(const jtk_tables &T, const uint8_t *p, int n) {
 	uint32_t k[6];
@@ -795,16 +816,23 @@ JTK_HD int jtk_merge_short_t(const jtk_tables &T, const uint8_t *p, int n, int32
 	}
 	MaskT alive = (n >= BITS) ? ~(MaskT) 0 : ((ONE << n) - ONE);
 	for (;;) {
-		/* leftmost strict minimum (:232-240) */
-		int32_t mr = JTK_RANK_MAX;
-		int mi = -1;
+		/* leftmost strict minimum (:232-240), and the leftmost minimum over the other positions: the candidate for the NEXT
+		 * iteration of the reference loop, merged in the same round trip to the pair table when that is provably what the
+		 * sequential loop would do */
+		int32_t mr = JTK_RANK_MAX, mr2 = JTK_RANK_MAX;
+		int mi = -1, mi2 = -1;
 		for (MaskT m = alive; m;) {
 			const int k = ctz(m);
 			m &= m - 1;
 			const int32_t r = rk[k * stride];
 			if (r < mr) {
+				mr2 = mr;
+				mi2 = mi;
 				mr = r;
 				mi = k;
+			} else if (r < mr2) {
+				mr2 = r;
+				mi2 = k;
 			}
 		}
 		if (mi < 0) break; /* :247,260-262 */
@@ -812,20 +840,57 @@ JTK_HD int jtk_merge_short_t(const jtk_tables &T, const uint8_t *p, int n, int32
 		const int nx = ctz(above);
 		const MaskT above2 = above & (above - 1);
 		const MaskT below = alive & ((ONE << mi) - ONE);
+		const int pv = below ? top(below) : -1;
 		tok[mi * stride] = mr; /* rank == id of the merged token */
 		alive &= ~(ONE << nx);
 		rk[nx * stride] = JTK_RANK_MAX;
-		if (above2 && below) { /* both neighbours exist: issue the two probes together (:254-257) */
-			const int pv = top(below);
-			int32_t r_right, r_left;
-			jtk_lookup_pair2(T, mr, tok[ctz(above2) * stride], tok[pv * stride], mr, &r_right, &r_left);
-			rk[mi * stride] = r_right;
-			rk[pv * stride] = r_left;
-		} else {
-			rk[mi * stride] = above2 ? jtk_lookup_pair(T, mr, tok[ctz(above2) * stride]) : JTK_RANK_MAX; /* :254 */
-			if (below) {
-				const int pv = top(below);
-				rk[pv * stride] = jtk_lookup_pair(T, tok[pv * stride], mr); /* :255-257 */
+		/* The second merge is what the reference does next iff its pair is untouched by the first merge (not a neighbour of
+		 * it) and neither of the two ranks the first merge recomputes comes before it in (rank, position) order.  The id of
+		 * a merged token is the rank just found, so all four probes can be issued before any of them returns. */
+		const bool spec = mi2 >= 0 && mi2 != nx && mi2 != pv;
+		int nx2 = -1, nn2 = -1, pv2 = -1;
+		if (spec) {
+			const MaskT aboveB = alive & ~(((ONE << mi2) << 1) - ONE);
+			nx2 = ctz(aboveB);
+			const MaskT above2B = aboveB & (aboveB - 1);
+			const MaskT belowB = alive & ((ONE << mi2) - ONE);
+			if (above2B) nn2 = ctz(above2B);
+			if (belowB) pv2 = top(belowB);
+		}
+		int32_t pl[4], pr[4], res[4];
+		uint32_t valid = 0;
+		pl[0] = mr, pr[0] = 0;
+		if (above2) { /* :254 */
+			pr[0] = tok[ctz(above2) * stride];
+			valid |= 1u;
+		}
+		pl[1] = 0, pr[1] = mr;
+		if (pv >= 0) { /* :255-257 */
+			pl[1] = tok[pv * stride];
+			valid |= 2u;
+		}
+		pl[2] = mr2, pr[2] = 0;
+		if (nn2 >= 0) {
+			pr[2] = tok[nn2 * stride];
+			valid |= 4u;
+		}
+		pl[3] = 0, pr[3] = mr2;
+		if (pv2 >= 0) {
+			pl[3] = tok[pv2 * stride];
+			valid |= 8u;
+		}
+		jtk_lookup_pair4(T, pl, pr, valid, res);
+		rk[mi * stride] = res[0];
+		if (pv >= 0) rk[pv * stride] = res[1];
+		if (spec) {
+			const bool left_first = pv >= 0 && (res[1] < mr2 || (res[1] == mr2 && pv < mi2));
+			const bool right_first = res[0] < mr2 || (res[0] == mr2 && mi < mi2);
+			if (!left_first && !right_first) {
+				tok[mi2 * stride] = mr2;
+				alive &= ~(ONE << nx2);
+				rk[nx2 * stride] = JTK_RANK_MAX;
+				rk[mi2 * stride] = res[2];
+				if (pv2 >= 0) rk[pv2 * stride] = res[3];
 			}
 		}
 	}

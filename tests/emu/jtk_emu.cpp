@@ -186,4 +186,3 @@ extern "C" int emu_general_split(const emu_encoding *e, const uint8_t *bytes, co
 }
 
 extern "C" int emu_pattern_kind(const emu_encoding *e) { return e->view.pattern_kind; }
-

@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(SNT) jtk_short_scatter_kernel(const __grid_con
 
 /* NSLOT = 16 / 32 / 64: pieces of 2..16 / 17..32 / 33..64 bytes; NSLOT * NTHREADS is constant (32 KiB of scratch) */
 template <int NSLOT, int NTHREADS>
-__global__ void __launch_bounds__(NTHREADS, NTHREADS >= 256 ? 5 : 7) jtk_merge_short_kernel(const __grid_constant__ jtk_encode_args a) {
+__global__ void __launch_bounds__(NTHREADS, NTHREADS >= 256 ? 4 : 7) jtk_merge_short_kernel(const __grid_constant__ jtk_encode_args a) {
 	__shared__ int32_t s_scr[2 * NSLOT * NTHREADS]; /* tok / rk, slot k of thread t at k * NTHREADS + t (bank = thread) */
 	const jtk_tables &T = a.T;
 	const int tid = threadIdx.x, lane = tid & 31;

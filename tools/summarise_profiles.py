@@ -8,7 +8,7 @@ shutil.copy(os.path.join(G, "r1_launches.csv"), os.path.join(P, "r1_launches.csv
 table = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "launch_table.py"), os.path.join(G, "r1_launches.csv")], capture_output=True, text=True).stdout
 open(os.path.join(P, "r1_launches_summary.txt"), "w").write(
     "ncu --metrics gpu__time_duration.sum --clock-control none -k regex:jtk_ (two timed steps of: python bench.py --steps 2 --warmup 3 --no-cpu-baseline)\n"
-    "per-launch times are cold-cache and serialised: compare shares, not absolutes\n\n" + table)
+    "per-launch times are cold-cache and serialised (in production the four merge kernels of a sub-batch overlap on forked streams): compare shares, not absolutes\n\n" + table)
 raw = subprocess.run(["ncu", "-i", os.path.join(G, "r1_split_lookup.ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 h, units = rows[0], rows[1]
@@ -39,6 +39,25 @@ open(os.path.join(P, "r1_split_lookup_source_hotspots.txt"), "w").write("per-fun
 per_launch = sum(traffic) / len(traffic)
 json.dump({"kernel": "jtk_split_lookup_kernel", "dram_bytes_per_launch": per_launch, "launch": "one 128 MiB sub-batch (16384 tiles)",
            "dram_bytes_per_step": per_launch * 8, "source": "profiles/r1_split_lookup_ncu_full.txt"}, open(os.path.join(P, "tile_kernel_traffic.json"), "w"), indent=1)
+mg = os.path.join(G, "r1_merge_gather.ncu-rep")
+if os.path.exists(mg):
+    raw = subprocess.run(["ncu", "-i", mg, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    h, units = rows[0], rows[1]
+    out = ["JTK_SIDE_STREAMS=0 ncu --set full --clock-control none -k regex:jtk_merge_short|jtk_merge_medium|jtk_gather -s 140 -c 5 python bench.py --steps 2 --warmup 3 --no-cpu-baseline",
+           "(one full-size sub-batch; in production the four merge kernels run side by side on forked streams)", ""]
+    for r in rows[2:]:
+        m, u = dict(zip(h, r)), dict(zip(h, units))
+        out.append(m.get("Kernel Name", "?"))
+        for k in keys[1:]:
+            if k in m:
+                out.append("  %-70s %s %s" % (k, m[k], u.get(k, "")))
+        st = [(k, float(v.replace(",", ""))) for k, v in m.items() if "issue_stalled" in k and k.endswith("per_issue_active.ratio") and v]
+        out.append("  stall reasons (warps stalled per issue-active cycle): " + ", ".join("%s %.2f" % (k.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), v) for k, v in sorted(st, key=lambda kv: -kv[1])[:5]))
+    open(os.path.join(P, "r1_merge_gather_ncu_full.txt"), "w").write("\n".join(out) + "\n")
+for f in ("r1_pcie.txt", "r1_per_language.txt"):
+    if os.path.exists(os.path.join(G, f)):
+        shutil.copy(os.path.join(G, f), os.path.join(P, f))
 for f in ("bench_r1.json", "bench_r1_reference.json"):
     if os.path.exists(os.path.join(G, f)):
         shutil.copy(os.path.join(G, f), os.path.join(P, f))

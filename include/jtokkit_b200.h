@@ -94,6 +94,13 @@ int jtk_encoding_num_devices(const jtk_encoding *enc);
  */
 int jtk_encode_batch(jtk_encoding *enc, const uint8_t *utf8, const int64_t *doc_off, int64_t ndocs, uint32_t flags, jtk_result **out);
 
+/* Special-token ENCODING: every occurrence of a registered special token becomes its id, the text between occurrences is
+ * encoded like encodeOrdinary.  NOT in the reference (README.md:46 lists it as not started; GptBytePairEncoding.java:52-56
+ * throws instead) - behind its own entry point for that reason; semantics of the upstream the reference mirrors, tiktoken's
+ * encode(text, allowed_special="all"): leftmost-first, non-overlapping, the longest token where several start at the same
+ * position.  Same result object as jtk_encode_batch; first device of the encoding only. */
+int jtk_encode_batch_special(jtk_encoding *enc, const uint8_t *utf8, const int64_t *doc_off, int64_t ndocs, uint32_t flags, jtk_result **out);
+
 int64_t jtk_result_num_docs(const jtk_result *r);
 int64_t jtk_result_num_tokens(const jtk_result *r);
 const int32_t *jtk_result_ids(const jtk_result *r);           /* num_tokens ids, NULL for JTK_COUNT_ONLY */

@@ -285,14 +285,16 @@ class Encoding:
         blob, off = pack_documents(texts)
         return self.encode_packed(blob, off, ordinary=ordinary, count_only=count_only)
 
-    def encode_packed(self, utf8, doc_off, ordinary=False, count_only=False, copy=True):
+    def encode_packed(self, utf8, doc_off, ordinary=False, count_only=False, copy=True, with_special_tokens=False):
         """HOST arrays in, HOST arrays out; host<->device copies happen inside the C call.
-        copy=False returns views into the library's pinned result buffers (valid until BatchResult.close())."""
+        copy=False returns views into the library's pinned result buffers (valid until BatchResult.close()).
+        with_special_tokens: special tokens in the text become their ids (jtk_encode_batch_special; not in the reference)."""
         utf8 = np.ascontiguousarray(utf8, dtype=np.uint8)
         doc_off = np.ascontiguousarray(doc_off, dtype=np.int64)
-        flags = (0 if ordinary else _capi.CHECK_SPECIAL) | (_capi.COUNT_ONLY if count_only else 0)
+        flags = (0 if ordinary or with_special_tokens else _capi.CHECK_SPECIAL) | (_capi.COUNT_ONLY if count_only else 0)
         r = C.c_void_p()
-        _capi.check(_capi.lib().jtk_encode_batch(self._h, _ptr(utf8), _ptr(doc_off), doc_off.size - 1, flags, C.byref(r)))
+        call = _capi.lib().jtk_encode_batch_special if with_special_tokens else _capi.lib().jtk_encode_batch
+        _capi.check(call(self._h, _ptr(utf8), _ptr(doc_off), doc_off.size - 1, flags, C.byref(r)))
         L = _capi.lib()
         nd, nt = L.jtk_result_num_docs(r), L.jtk_result_num_tokens(r)
         ids = None
@@ -325,6 +327,22 @@ class Encoding:
 
     def encode_ordinary_batch(self, texts):
         return self.encode_batch(texts, ordinary=True)
+
+    # Special-token ENCODING is not part of the reference (README.md:46 "not started"; Encoding.encode throws
+    # UnsupportedOperationException instead), hence the methods of their own.  Semantics: tiktoken's
+    # encode(text, allowed_special="all") - every occurrence of a registered special token becomes its id.
+    def encode_with_special_tokens_batch(self, texts):
+        blob, off = pack_documents(texts)
+        return self.encode_packed(blob, off, with_special_tokens=True)
+
+    def encode_with_special_tokens(self, text):
+        if text is None:
+            return []
+        res = self.encode_with_special_tokens_batch([text])
+        self._raise_for_status(res.doc_status)
+        return res.tokens(0)
+
+    encodeWithSpecialTokens = encode_with_special_tokens
 
     def count_tokens_batch(self, texts, ordinary=False):
         res = self.encode_batch(texts, ordinary=ordinary, count_only=True)

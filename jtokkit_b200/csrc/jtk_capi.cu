@@ -164,7 +164,7 @@ static int init_device(jtk_encoding *e, int device) {
 	const size_t hot_bytes = ar.total;
 	const size_t o_tokb = ar.add(h.tok_bytes), o_toko = ar.add(h.tok_off), o_spb = ar.add(h.special_bytes), o_spo = ar.add(h.special_off);
 	const size_t o_deck = ar.add(h.dec_keys), o_decb = ar.add(h.dec_bytes), o_deco = ar.add(h.dec_off);
-	const size_t o_rxi = ar.add(h.rx_inst), o_rxs = ar.add(h.rx_sets), o_rxr = ar.add(h.rx_ranges);
+	const size_t o_rxi = ar.add(h.rx_inst), o_rxs = ar.add(h.rx_sets), o_rxr = ar.add(h.rx_ranges), o_spi = ar.add(h.special_ids);
 	uint8_t *base = nullptr;
 	CUDA_TRY(cudaMalloc(&base, ar.total));
 	ds->allocs.push_back(base);
@@ -183,6 +183,7 @@ static int init_device(jtk_encoding *e, int device) {
 	T.tok_off = reinterpret_cast<const uint32_t *>(base + o_toko);
 	T.special_bytes = base + o_spb;
 	T.special_off = reinterpret_cast<const uint32_t *>(base + o_spo);
+	T.special_ids = reinterpret_cast<const int32_t *>(base + o_spi);
 	T.dec_keys = reinterpret_cast<const uint32_t *>(base + o_deck);
 	T.dec_bytes = base + o_decb;
 	T.dec_off = reinterpret_cast<const uint32_t *>(base + o_deco);
@@ -1224,6 +1225,133 @@ extern "C" void jtk_result_free(jtk_result *r) {
 /* ------------------------------------------------------------------ decode */
 /* Runs the decode kernels on the encoding's first device.  On success *h_bytes (pinned) holds the bytes,
  * h_id_off (optional, nids + 1) the byte offset of every token, r->byte_off / status / bad_ids per document. */
+/* ------------------------------------------------------------------ special-token encoding
+ * Not in the reference (README.md:46 "not started"; encodeInternal throws, GptBytePairEncoding.java:52-56): semantics of
+ * tiktoken's encode(text, allowed_special="all").  One device, whole batch resident (a convenience path, not the pipelined
+ * hot path): find the occurrences per document, encode the segments between them as documents of their own with the
+ * ordinary kernels, replace each special segment by the token's id. */
+extern "C" int jtk_encode_batch_special(jtk_encoding *e, const uint8_t *utf8, const int64_t *doc_off, int64_t ndocs, uint32_t flags, jtk_result **out) {
+	if (!e || !doc_off || !out || ndocs < 0) return set_error(JTK_E_ARG, "null argument");
+	*out = nullptr;
+	if (doc_off[0] != 0) return set_error(JTK_E_ARG, "doc_off[0] must be 0");
+	for (int64_t d = 0; d < ndocs; d++)
+		if (doc_off[d + 1] < doc_off[d]) return set_error(JTK_E_ARG, "doc_off is not monotone");
+	const int64_t total = doc_off[ndocs];
+	if (total > 0 && !utf8) return set_error(JTK_E_ARG, "utf8 is null");
+	jtk_device_state *ds = e->devs[0];
+	CUDA_TRY(cudaSetDevice(ds->device));
+	jtk_workspace *w = acquire_ws(ds);
+	jtk_result *r = new jtk_result();
+	r->enc = e;
+	r->ndocs = ndocs;
+	cudaStream_t st = nullptr;
+	std::vector<void *> dev; /* device buffers of this call */
+	auto dalloc = [&](size_t bytes) -> void * {
+		void *p = nullptr;
+		if (cudaMalloc(&p, std::max<size_t>(bytes, 16)) != cudaSuccess) {
+			cudaGetLastError();
+			return nullptr;
+		}
+		dev.push_back(p);
+		return p;
+	};
+	int rc = JTK_OK;
+	do {
+		cudaError_t ce;
+#define STRY(expr)                                                                              \
+	if ((ce = (expr)) != cudaSuccess) {                                                         \
+		rc = set_error(JTK_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(ce));        \
+		break;                                                                                  \
+	}
+#define SALLOC(var, type, count)                                           \
+	type *var = static_cast<type *>(dalloc(sizeof(type) * (size_t) (count))); \
+	if (!var) {                                                            \
+		rc = set_error(JTK_E_NOMEM, "device allocation failed");          \
+		break;                                                             \
+	}
+		STRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+		SALLOC(d_in, uint8_t, total + 64);
+		SALLOC(d_doc, int64_t, ndocs + 1);
+		SALLOC(d_base, int64_t, ndocs + 1);
+		SALLOC(d_sums, int64_t, jtk_scan_blocks(ndocs + 1) + 1);
+		SALLOC(d_total, int64_t, 1);
+		STRY(cudaMemsetAsync(d_in + total, 0, 64, st));
+		if (total > 0) STRY(cudaMemcpyAsync(d_in, utf8, (size_t) total, cudaMemcpyHostToDevice, st));
+		STRY(cudaMemcpyAsync(d_doc, doc_off, sizeof(int64_t) * (size_t) (ndocs + 1), cudaMemcpyHostToDevice, st));
+		jtk_special_args a;
+		memset(&a, 0, sizeof(a));
+		a.T = ds->T;
+		a.bytes = d_in;
+		a.total = total;
+		a.doc_off = d_doc;
+		a.ndocs = ndocs;
+		a.match_base = d_base;
+		STRY(jtk_launch_special_count(a, st));
+		STRY(jtk_launch_exclusive_scan(d_base, ndocs + 1, d_sums, d_total, st));
+		int64_t nmatch = 0;
+		STRY(cudaMemcpyAsync(&nmatch, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+		STRY(cudaStreamSynchronize(st));
+		const int64_t nseg = ndocs + 2 * nmatch;
+		a.nseg = nseg;
+		SALLOC(d_seg_off, int64_t, nseg + 1);
+		SALLOC(d_seg_special, int32_t, nseg + 1);
+		SALLOC(d_seg_ids, int32_t, total + 16);
+		SALLOC(d_seg_tok, int64_t, nseg + 1);
+		SALLOC(d_seg_st, int32_t, nseg + 1);
+		SALLOC(d_shift, int64_t, nseg + 1);
+		SALLOC(d_sums2, int64_t, jtk_scan_blocks(nseg + 1) + 1);
+		a.seg_off = d_seg_off;
+		a.seg_special = d_seg_special;
+		STRY(jtk_launch_special_fill(a, st));
+		STRY(cudaMemsetAsync(d_seg_st, 0, sizeof(int32_t) * (size_t) (nseg + 1), st));
+		jtk_device_info info;
+		memset(&info, 0, sizeof(info));
+		jtk_memo_buf *memo = acquire_memo(ds);
+		rc = encode_device_impl(e, ds, w, d_in, total, d_seg_off, nseg, flags & ~(uint32_t) (JTK_CHECK_SPECIAL | JTK_COUNT_ONLY | JTK_TIME_KERNEL), d_seg_ids, total + 16,
+		                        d_seg_tok, d_seg_st, nullptr, st, &info, true, memo);
+		release_memo(ds, memo);
+		if (rc != JTK_OK) break;
+		const int64_t nseg_tok = info.num_tokens;
+		a.seg_ids = d_seg_ids;
+		a.seg_tok_off = d_seg_tok;
+		a.seg_status = d_seg_st;
+		a.shift = d_shift;
+		STRY(jtk_launch_special_shift(a, st));
+		STRY(jtk_launch_exclusive_scan(d_shift, nseg + 1, d_sums2, d_total, st));
+		int64_t shift_total = 0;
+		STRY(cudaMemcpyAsync(&shift_total, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+		STRY(cudaStreamSynchronize(st));
+		const int64_t ntok = nseg_tok + shift_total;
+		SALLOC(d_ids, int32_t, ntok + 1);
+		SALLOC(d_tok, int64_t, ndocs + 1);
+		SALLOC(d_st, int32_t, ndocs + 1);
+		a.ids = d_ids;
+		a.tok_off = d_tok;
+		a.doc_status = d_st;
+		STRY(jtk_launch_special_gather(a, nseg_tok, st));
+		if ((rc = pinned_get(e, sizeof(int32_t) * std::max<int64_t>(ntok, 1), &r->ids)) != JTK_OK) break;
+		if ((rc = pinned_get(e, sizeof(int64_t) * (ndocs + 1), &r->tok_off)) != JTK_OK) break;
+		if ((rc = pinned_get(e, sizeof(int32_t) * (ndocs + 1), &r->status)) != JTK_OK) break;
+		if (ntok > 0) STRY(cudaMemcpyAsync(r->ids.p, d_ids, sizeof(int32_t) * (size_t) ntok, cudaMemcpyDeviceToHost, st));
+		STRY(cudaMemcpyAsync(r->tok_off.p, d_tok, sizeof(int64_t) * (size_t) (ndocs + 1), cudaMemcpyDeviceToHost, st));
+		if (ndocs > 0) STRY(cudaMemcpyAsync(r->status.p, d_st, sizeof(int32_t) * (size_t) ndocs, cudaMemcpyDeviceToHost, st));
+		STRY(cudaStreamSynchronize(st));
+		r->ntokens = ntok;
+		r->launches = info.gpu_launches + 10;
+#undef STRY
+#undef SALLOC
+	} while (0);
+	for (void *p : dev) cudaFree(p);
+	if (st) cudaStreamDestroy(st);
+	release_ws(ds, w);
+	if (rc != JTK_OK) {
+		jtk_result_free(r);
+		return rc;
+	}
+	*out = r;
+	return JTK_OK;
+}
+
 static int decode_impl(jtk_encoding *e, const int32_t *ids, const int64_t *tok_off, int64_t ndocs, jtk_result *r, std::vector<int64_t> *h_id_off) {
 	jtk_device_state *ds = e->devs[0];
 	CUDA_TRY(cudaSetDevice(ds->device));

@@ -128,6 +128,7 @@ struct jtk_tables {
 	int32_t special_has_empty;  /* "".contains: every document is flagged */
 	const uint8_t *special_bytes;
 	const uint32_t *special_off; /* nspecial + 1 */
+	const int32_t *special_ids;  /* nspecial (special-token encoding, jtk_encode_batch_special) */
 	uint32_t special_first[8];   /* bitmap of first bytes */
 	uint32_t special_first_single; /* that byte when exactly one non-zero first byte occurs, else 0 */
 	/* decode (GptBytePairEncoding.java:136-151,302-314): id -> token index, open addressing {id, token index + 1} */

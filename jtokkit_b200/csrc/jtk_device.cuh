@@ -658,6 +658,25 @@ JTK_HD bool jtk_special_at(const jtk_tables &T, const uint8_t *gbytes, int64_t g
 	return false;
 }
 
+/* The longest special token that starts at global position g and ends at or before hi: its index and *len, or -1.
+ * (Special-token ENCODING, jtk_encode_batch_special: not in the reference, semantics of tiktoken's allowed_special="all".) */
+JTK_HD int jtk_special_match(const jtk_tables &T, const uint8_t *gbytes, int64_t g, int64_t hi, int *len) {
+	int best = -1;
+	uint32_t best_len = 0;
+	for (int s = 0; s < T.nspecial; s++) {
+		const uint32_t a = T.special_off[s], n = T.special_off[s + 1] - a;
+		if (n <= best_len || g + n > hi) continue;
+		uint32_t i = 0;
+		while (i < n && gbytes[g + i] == T.special_bytes[a + i]) i++;
+		if (i == n) {
+			best = s;
+			best_len = n;
+		}
+	}
+	*len = (int) best_len;
+	return best;
+}
+
 /* ---------------------------------------------------------------------------------------------
  * table lookups
  * ------------------------------------------------------------------------------------------- */

@@ -1475,6 +1475,109 @@ __global__ void jtk_decode_gather_kernel(const jtk_decode_args a, const int32_t 
 
 } /* namespace */
 
+/* ---------------------------------------------------------------------------------------------
+ * special-token encoding (see jtk_special_args)
+ * ------------------------------------------------------------------------------------------- */
+/* One thread per document walks its bytes (leftmost-first, non-overlapping matches are inherently sequential; candidates
+ * are found eight bytes at a time when all special tokens start with the same byte).  FILL = false: count; true: write the segments. */
+template <bool FILL>
+__global__ void jtk_special_scan_kernel(const jtk_special_args a) {
+	const jtk_tables &T = a.T;
+	for (int64_t d = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; d < a.ndocs; d += (int64_t) gridDim.x * blockDim.x) {
+		const int64_t lo = a.doc_off[d], hi = a.doc_off[d + 1];
+		int64_t seg = 0, cnt = 0;
+		if (FILL) {
+			seg = d + 2 * a.match_base[d];
+			a.seg_off[seg] = lo;
+			a.seg_special[seg] = 0;
+		}
+		const uint64_t pat = (uint64_t) T.special_first_single * 0x0101010101010101ull;
+		for (int64_t i = lo; i < hi;) {
+			if (T.special_first_single && (i & 7) == 0 && i + 8 <= hi) { /* SWAR "has byte": skip eight bytes without a candidate */
+				const uint64_t x = *reinterpret_cast<const uint64_t *>(a.bytes + i) ^ pat;
+				if (!((x - 0x0101010101010101ull) & ~x & 0x8080808080808080ull)) {
+					i += 8;
+					continue;
+				}
+			}
+			const uint8_t b = a.bytes[i];
+			int len = 0;
+			if (((T.special_first[b >> 5] >> (b & 31)) & 1u) && jtk_special_match(T, a.bytes, i, hi, &len) >= 0) {
+				if (FILL) {
+					const int idx = jtk_special_match(T, a.bytes, i, hi, &len);
+					a.seg_off[seg + 1] = i;
+					a.seg_special[seg + 1] = idx + 1;
+					a.seg_off[seg + 2] = i + len;
+					a.seg_special[seg + 2] = 0;
+					seg += 2;
+				}
+				cnt++;
+				i += len;
+			} else {
+				i++;
+			}
+		}
+		if (!FILL) a.match_base[d] = cnt;
+	}
+	if (FILL && blockIdx.x == 0 && threadIdx.x == 0) a.seg_off[a.nseg] = a.total;
+	if (!FILL && blockIdx.x == 0 && threadIdx.x == 0) a.match_base[a.ndocs] = 0;
+}
+
+__global__ void jtk_special_shift_kernel(const jtk_special_args a) {
+	for (int64_t s = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; s <= a.nseg; s += (int64_t) gridDim.x * blockDim.x)
+		a.shift[s] = (s < a.nseg && a.seg_special[s]) ? 1 - (a.seg_tok_off[s + 1] - a.seg_tok_off[s]) : 0;
+}
+
+__global__ void jtk_special_gather_kernel(const jtk_special_args a, int64_t ntok) {
+	const int64_t stride = (int64_t) gridDim.x * blockDim.x, t0 = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+	/* tokens of text segments move by the shift of their segment */
+	for (int64_t t = t0; t < ntok; t += stride) {
+		int64_t lo = 0, hi = a.nseg - 1; /* last segment with seg_tok_off[s] <= t */
+		while (lo < hi) {
+			const int64_t mid = (lo + hi + 1) >> 1;
+			if (a.seg_tok_off[mid] <= t) lo = mid;
+			else hi = mid - 1;
+		}
+		if (!a.seg_special[lo]) a.ids[t + a.shift[lo]] = a.seg_ids[t];
+	}
+	/* a special segment becomes the token's id */
+	for (int64_t s = t0; s < a.nseg; s += stride)
+		if (a.seg_special[s]) a.ids[a.seg_tok_off[s] + a.shift[s]] = a.T.special_ids[a.seg_special[s] - 1];
+	/* documents: token offsets and the status bits of their text segments */
+	for (int64_t d = t0; d <= a.ndocs; d += stride) {
+		const int64_t s0 = d + 2 * a.match_base[d];
+		a.tok_off[d] = a.seg_tok_off[s0] + a.shift[s0];
+		if (d < a.ndocs) {
+			const int64_t s1 = d + 1 + 2 * a.match_base[d + 1];
+			int32_t st = 0;
+			for (int64_t s = s0; s < s1; s += 2) st |= a.seg_status[s];
+			a.doc_status[d] = st;
+		}
+	}
+}
+
+cudaError_t jtk_launch_special_count(const jtk_special_args &a, cudaStream_t st) {
+	const unsigned grid = (unsigned) std::min<int64_t>((a.ndocs + 127) / 128 + 1, 148 * 16);
+	jtk_special_scan_kernel<false><<<grid, 128, 0, st>>>(a);
+	return cudaGetLastError();
+}
+cudaError_t jtk_launch_special_fill(const jtk_special_args &a, cudaStream_t st) {
+	const unsigned grid = (unsigned) std::min<int64_t>((a.ndocs + 127) / 128 + 1, 148 * 16);
+	jtk_special_scan_kernel<true><<<grid, 128, 0, st>>>(a);
+	return cudaGetLastError();
+}
+cudaError_t jtk_launch_special_shift(const jtk_special_args &a, cudaStream_t st) {
+	const unsigned grid = (unsigned) std::min<int64_t>((a.nseg + 256) / 256 + 1, 148 * 16);
+	jtk_special_shift_kernel<<<grid, 256, 0, st>>>(a);
+	return cudaGetLastError();
+}
+cudaError_t jtk_launch_special_gather(const jtk_special_args &a, int64_t ntok, cudaStream_t st) {
+	const int64_t work = std::max<int64_t>(ntok, a.nseg + 1);
+	const unsigned grid = (unsigned) std::min<int64_t>((work + 255) / 256 + 1, 148 * 16);
+	jtk_special_gather_kernel<<<grid, 256, 0, st>>>(a, ntok);
+	return cudaGetLastError();
+}
+
 int64_t jtk_scan_blocks(int64_t n) { return (n + SCAN_NT * SCAN_ITEMS - 1) / (SCAN_NT * SCAN_ITEMS); }
 
 /* id_byte_off has nids + 1 entries; entry nids must be zero on entry and receives the total. */
@@ -1489,6 +1592,14 @@ cudaError_t jtk_launch_decode_lengths(const jtk_decode_args &a, int32_t *tok_ind
 	jtk_scan_block_kernel<<<(unsigned) nb, SCAN_NT, 0, st>>>(a.id_byte_off, n, block_sums);
 	jtk_scan_sums_kernel<<<1, 1024, 0, st>>>(block_sums, nb, total);
 	jtk_scan_add_kernel<<<(unsigned) nb, SCAN_NT, 0, st>>>(a.id_byte_off, n, block_sums);
+	return cudaGetLastError();
+}
+
+cudaError_t jtk_launch_exclusive_scan(int64_t *data, int64_t n, int64_t *block_sums, int64_t *total, cudaStream_t st) {
+	const int64_t nb = jtk_scan_blocks(n);
+	jtk_scan_block_kernel<<<(unsigned) nb, SCAN_NT, 0, st>>>(data, n, block_sums);
+	jtk_scan_sums_kernel<<<1, 1024, 0, st>>>(block_sums, nb, total);
+	jtk_scan_add_kernel<<<(unsigned) nb, SCAN_NT, 0, st>>>(data, n, block_sums);
 	return cudaGetLastError();
 }
 

@@ -127,6 +127,36 @@ cudaError_t jtk_launch_long_insert(const jtk_long_piece *list, const int64_t *cu
 cudaError_t jtk_launch_long_fix_offsets(const jtk_long_piece *list, const int64_t *cum, unsigned int n_long, const int64_t *doc_off, int64_t ndocs,
                                         int64_t *tok_off, cudaStream_t st);
 
+/* Special-token ENCODING (not in the reference: README.md:46; semantics of tiktoken's allowed_special="all").  Every
+ * occurrence of a special token cuts its document into segments: text, token, text, ...  The segments are encoded as
+ * documents of their own by the ordinary pipeline (the text of a special token yields throw-away tokens), then a gather
+ * replaces each special segment by the token's id. */
+struct jtk_special_args {
+	jtk_tables T;
+	const uint8_t *bytes;
+	int64_t total;
+	const int64_t *doc_off;
+	int64_t ndocs;
+	int64_t *match_base;    /* ndocs + 1: matches per document, then their exclusive scan */
+	int64_t nseg;           /* ndocs + 2 * matches */
+	int64_t *seg_off;       /* nseg + 1: the segments as document offsets */
+	int32_t *seg_special;   /* nseg: special-token index + 1, 0 for text */
+	/* after the ordinary encode of the segments */
+	const int32_t *seg_ids;     /* tokens of all segments */
+	const int64_t *seg_tok_off; /* nseg + 1 */
+	const int32_t *seg_status;  /* nseg */
+	int64_t *shift;         /* nseg + 1: per segment (1 - its token count) for special segments, 0 for text; then the exclusive scan */
+	int32_t *ids;           /* final tokens */
+	int64_t *tok_off;       /* ndocs + 1 */
+	int32_t *doc_status;    /* ndocs */
+};
+cudaError_t jtk_launch_special_count(const jtk_special_args &a, cudaStream_t st);
+cudaError_t jtk_launch_special_fill(const jtk_special_args &a, cudaStream_t st);
+cudaError_t jtk_launch_special_shift(const jtk_special_args &a, cudaStream_t st);
+cudaError_t jtk_launch_special_gather(const jtk_special_args &a, int64_t nseg_tokens, cudaStream_t st);
+/* in-place exclusive scan of data[0..n) (int64); *total (device) receives the sum; block_sums: jtk_scan_blocks(n) scratch */
+cudaError_t jtk_launch_exclusive_scan(int64_t *data, int64_t n, int64_t *block_sums, int64_t *total, cudaStream_t st);
+
 /* decode path */
 struct jtk_decode_args {
 	jtk_tables T;

@@ -427,6 +427,7 @@ jtk_tables jtk_host_view(const jtk_host_tables &h) {
 	v.special_has_empty = h.special_has_empty;
 	v.special_bytes = h.special_bytes.data();
 	v.special_off = h.special_off.data();
+	v.special_ids = h.special_ids.data();
 	memcpy(v.special_first, h.special_first, sizeof(v.special_first));
 	v.dec_keys = h.dec_keys.data();
 	v.mask_d = h.mask_d;

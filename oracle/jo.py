@@ -49,6 +49,8 @@ def _lib():
     lib.jo_split.argtypes = [vp, vp, C.c_int64, vp, vp, C.c_int64]
     lib.jo_encode.restype = C.c_int64
     lib.jo_encode.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_int, vp, C.c_int64]
+    lib.jo_encode_with_special.restype = C.c_int64
+    lib.jo_encode_with_special.argtypes = [vp, vp, C.c_int64, C.c_int, vp, C.c_int64]
     lib.jo_encode_max.restype = C.c_int64
     lib.jo_encode_max.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_int, vp, C.c_int64, C.POINTER(C.c_int)]
     lib.jo_contains_special.restype = C.c_int
@@ -148,6 +150,15 @@ class OracleEncoding:
         n = lib().jo_encode(self._h, _p(b), b.size, check_special, merge, _p(out), out.size)
         if n == E_SPECIAL:
             raise NotImplementedError("Encoding special tokens is not supported yet.")
+        if n < 0:
+            raise ValueError("oracle encode failed: %d" % n)
+        return out[:n].tolist()
+
+    def encode_with_special(self, text, merge=MERGE_AUTO):
+        """tiktoken's encode(text, allowed_special="all"): special tokens in the text become their ids (not in the reference)."""
+        b = self._bytes(text)
+        out = np.empty(b.size + 1, dtype=np.int32)
+        n = lib().jo_encode_with_special(self._h, _p(b), b.size, merge, _p(out), out.size)
         if n < 0:
             raise ValueError("oracle encode failed: %d" % n)
         return out[:n].tolist()

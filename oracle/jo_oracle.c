@@ -526,6 +526,40 @@ static int64_t encode_core(const jo_encoding *e, const uint8_t *text, int64_t n,
 	return status < 0 ? status : cnt;
 }
 
+/* Special-token ENCODING.  The reference does not implement it (README.md:46 "not started"; encodeInternal throws, :52-56), so
+ * this restates the upstream the reference mirrors - tiktoken's encode(text, allowed_special="all") - with the reference's
+ * pieces: the text is cut at every occurrence of a special token (leftmost first, non-overlapping; the longest token when
+ * several start at the same position), the stretches between them are encoded like encodeOrdinary each on its own, and every
+ * occurrence contributes the special token's id.  Empty special tokens never match. */
+int64_t jo_encode_with_special(const jo_encoding *e, const uint8_t *text, int64_t n, int merge_algo, int32_t *out, int64_t cap) {
+	int64_t cnt = 0, seg = 0, i = 0;
+	while (i <= n) {
+		int64_t best = -1, best_len = 0;
+		if (i < n)
+			for (int64_t s = 0; s < e->spec.nkeys; s++) {
+				const uint8_t *p = e->spec.bytes + e->spec.off[s];
+				int64_t len = e->spec.off[s + 1] - e->spec.off[s];
+				if (len > best_len && i + len <= n && memcmp(text + i, p, (size_t) len) == 0) {
+					best = s;
+					best_len = len;
+				}
+			}
+		if (best < 0 && i < n) {
+			i++;
+			continue;
+		}
+		int64_t m = encode_core(e, text + seg, i - seg, 0, 0, merge_algo, out + cnt, cap - cnt);
+		if (m < 0) return m;
+		cnt += m;
+		if (best < 0) break;
+		if (cnt >= cap) return JO_E_CAPACITY;
+		out[cnt++] = e->spec.rank[best];
+		i += best_len;
+		seg = i;
+	}
+	return cnt;
+}
+
 int64_t jo_encode(const jo_encoding *e, const uint8_t *text, int64_t n, int check_special, int merge_algo, int32_t *out, int64_t cap) {
 	if (check_special && jo_contains_special(e, text, n)) return JO_E_SPECIAL;
 	return encode_core(e, text, n, 0, 0, merge_algo, out, cap);

@@ -51,6 +51,9 @@ int64_t jo_encode_max(const jo_encoding *enc, const uint8_t *text, int64_t n, in
 /* text.contains(specialToken) for any special token (:52-56). */
 int jo_contains_special(const jo_encoding *enc, const uint8_t *text, int64_t n);
 
+/* special-token encoding as tiktoken's encode(text, allowed_special="all") (the reference has none, README.md:46) */
+int64_t jo_encode_with_special(const jo_encoding *enc, const uint8_t *text, int64_t n, int merge_algo, int32_t *out, int64_t cap);
+
 /* decodeBytes (:136-151).  Returns byte count or JO_E_UNKNOWN_ID (bad id in *bad_id). */
 int64_t jo_decode_bytes(const jo_encoding *enc, const int32_t *ids, int64_t n, uint8_t *out, int64_t cap, int32_t *bad_id);
 

@@ -151,3 +151,26 @@ def test_max_tokens_variants_match_oracle(gpu_encodings, oracles):
             assert (ro.get_tokens(), ro.is_truncated()) == orc.encode_max(t, m, ordinary=True)
     r = enc.encode(None, 5)
     assert r.get_tokens() == [] and not r.is_truncated()
+
+
+def test_special_token_encoding_matches_tiktoken_semantics(gpu_encodings, oracles):
+    """special-token ENCODING (absent from the reference, README.md:46) behind its own method, against the
+    oracle's restatement of tiktoken's encode(text, allowed_special="all") (itself checked against tiktoken in test_oracle.py)."""
+    import random
+    rng = random.Random(11)
+    for name in ["cl100k_base", "p50k_edit", "r50k_base"]:
+        g, o = gpu_encodings[name], oracles[name]
+        from oracle import jo
+        special = list(jo.BUILTIN[name][2].keys())
+        units = special + ["hello", " world", " ", "\n", "<|", "|>", "<|endoftext", "endoftext|>", "<", "12345", "'s", "中文", "<|fim_", "  ", "x" * 300]
+        texts = ["".join(rng.choice(units) for _ in range(rng.randint(0, 14))) for _ in range(400)]
+        texts += ["", special[0], special[0] * 3, "a" + special[0], special[0] + "b", "tail <|endoftext|>", "x" * 9000 + special[0] + "y" * 9000]
+        res = g.encode_with_special_tokens_batch(texts)
+        assert not res.doc_status.any()
+        for t, ids in zip(texts, res.to_lists()):
+            assert ids == o.encode_with_special(t), (name, t[:80])
+        assert g.encode_with_special_tokens("hello <|endoftext|> world") == o.encode_with_special("hello <|endoftext|> world")
+        # the reference behaviour of encode() is unchanged
+        with pytest.raises(NotImplementedError):
+            g.encode("hello <|endoftext|> world")
+    assert gpu_encodings["cl100k_base"].encode_with_special_tokens("<|endoftext|>") == [100257]

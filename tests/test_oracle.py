@@ -92,6 +92,23 @@ def test_differential_vs_tiktoken_and_regex(name, oracles):
         assert o.split(s) == [(cum[m.start()], cum[m.end()]) for m in rx.finditer(s)], s
 
 
+@pytest.mark.parametrize("name", ["cl100k_base", "r50k_base"])
+def test_special_token_encoding_vs_tiktoken(name, oracles):
+    """jo_encode_with_special (used to check jtk_encode_batch_special; the reference has no special-token encoding) restates
+    tiktoken's encode(text, allowed_special="all")."""
+    tiktoken = pytest.importorskip("tiktoken")
+    from tiktoken.load import load_tiktoken_bpe
+    from oracle import jo
+    pat, fname, special = jo.BUILTIN[name]
+    tk = tiktoken.Encoding(name, pat_str=pat, mergeable_ranks=load_tiktoken_bpe(os.path.join(jo.DATA, fname)), special_tokens=special)
+    o = oracles[name]
+    rng = random.Random(3)
+    units = list(special.keys()) + ["hello", " world", " ", "\n", "<|", "|>", "<|endoftext", "endoftext|>", "<", "12345", "'s", "中文", "<|fim_", "  "]
+    for _ in range(2000):
+        s = "".join(rng.choice(units) for _ in range(rng.randint(0, 12)))
+        assert o.encode_with_special(s) == tk.encode(s, allowed_special="all"), s
+
+
 def test_custom_patterns_follow_java_regex_semantics(oracles):
     """registerGptBytePairEncoding accepts arbitrary patterns (BaseEncodingRegistryTest.java:110-125): the oracle's matcher
     skips unmatched characters, advances past empty matches and honours ordered alternation."""

@@ -109,6 +109,11 @@ public final class CudaBytePairEncoding implements Encoding, AutoCloseable {
 	}
 
 	public Batch encodeBatch(final List<String> texts, final boolean ordinary, final boolean countOnly) {
+		return encodeBatch(texts, ordinary, countOnly, false);
+	}
+
+	/** withSpecialTokens: tiktoken's allowed_special="all" (jtk_encode_batch_special); the reference has no such mode. */
+	public Batch encodeBatch(final List<String> texts, final boolean ordinary, final boolean countOnly, final boolean withSpecialTokens) {
 		try (Arena arena = Arena.ofConfined()) {
 			// String.getBytes(UTF_8), exactly as ImmutableByteArray.from (ImmutableByteArray.java:16-19): lone surrogates become '?'.
 			// Never GetStringUTFChars / modified UTF-8.
@@ -127,8 +132,9 @@ public final class CudaBytePairEncoding implements Encoding, AutoCloseable {
 			}
 			off.setAtIndex(JAVA_LONG, utf8.length, pos);
 			final MemorySegment out = arena.allocate(ADDRESS);
-			final int flags = (ordinary ? 0 : JtkNative.CHECK_SPECIAL) | (countOnly ? JtkNative.COUNT_ONLY : 0);
-			final int rc = (int) JtkNative.ENCODE_BATCH.invokeExact(handle, bytes, off, (long) utf8.length, flags, out);
+			final int flags = (ordinary || withSpecialTokens ? 0 : JtkNative.CHECK_SPECIAL) | (countOnly ? JtkNative.COUNT_ONLY : 0);
+			final int rc = withSpecialTokens ? (int) JtkNative.ENCODE_BATCH_SPECIAL.invokeExact(handle, bytes, off, (long) utf8.length, flags, out)
+			                                 : (int) JtkNative.ENCODE_BATCH.invokeExact(handle, bytes, off, (long) utf8.length, flags, out);
 			if (rc != JtkNative.JTK_OK) throw new IllegalStateException(JtkNative.lastError());
 			final MemorySegment r = out.get(ADDRESS, 0);
 			try {
@@ -172,6 +178,16 @@ public final class CudaBytePairEncoding implements Encoding, AutoCloseable {
 	@Override
 	public List<Integer> encodeOrdinary(final String text) {
 		return encodeOne(text, true);
+	}
+
+	/** New method (not part of api/Encoding.java): every registered special token in the text becomes its id. */
+	public List<Integer> encodeWithSpecialTokens(final String text) {
+		if (text == null) return Collections.emptyList();
+		final Batch b = encodeBatch(Collections.singletonList(text), true, false, true);
+		raise(b.docStatus[0]);
+		final List<Integer> out = new ArrayList<>(b.ids.length);
+		for (final int id : b.ids) out.add(id);
+		return out;
 	}
 
 	/** encode(text, maxTokens): full device encode, clip, then the reference's back-off loop verbatim (:90-100) with the JVM's own decoder. */

@@ -30,6 +30,8 @@ final class JtkNative {
 	static final MethodHandle ENCODING_DESTROY = fn("jtk_encoding_destroy", FunctionDescriptor.ofVoid(ADDRESS));
 	/** int jtk_encode_batch(jtk_encoding*, const uint8_t* utf8, const int64_t* doc_off, int64_t ndocs, uint32_t flags, jtk_result** out) */
 	static final MethodHandle ENCODE_BATCH = fn("jtk_encode_batch", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, JAVA_INT, ADDRESS));
+	/** int jtk_encode_batch_special(...): same signature; special tokens in the text become their ids (not in the reference) */
+	static final MethodHandle ENCODE_BATCH_SPECIAL = fn("jtk_encode_batch_special", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, JAVA_INT, ADDRESS));
 	static final MethodHandle RESULT_NUM_TOKENS = fn("jtk_result_num_tokens", FunctionDescriptor.of(JAVA_LONG, ADDRESS));
 	static final MethodHandle RESULT_IDS = fn("jtk_result_ids", FunctionDescriptor.of(ADDRESS, ADDRESS));
 	static final MethodHandle RESULT_TOKEN_OFFSETS = fn("jtk_result_token_offsets", FunctionDescriptor.of(ADDRESS, ADDRESS));

@@ -1,6 +1,8 @@
 #!/usr/bin/env python3
 """PCIe copy rates of the box (pinned host memory): H2D alone, D2H alone, both at once.  Context for bench.py's e2e number."""
-import torch, time
+import sys, torch, time
+if len(sys.argv) > 1:
+    torch.cuda.set_device(int(sys.argv[1]))
 n = 1 << 30
 h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
 h_out = torch.empty(n, dtype=torch.uint8).pin_memory()

@@ -391,7 +391,7 @@ static int64_t sub_batch_tiles() {
 	static const int64_t v = [] {
 		const char *env = getenv("JTK_SUB_TILES");
 		long n = env ? atol(env) : 0;
-		return (int64_t) (n >= 64 ? n : JTK_DEFAULT_SUB_TILES);
+		return (int64_t) (n >= 64 ? std::min<long>(n, 1l << 18) : JTK_DEFAULT_SUB_TILES); /* list entries carry the tile index in 18 bits */
 	}();
 	return v;
 }
@@ -692,8 +692,15 @@ static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspa
 	/* sub-batches: a small first one (16 MiB) so that the piece memo is warm early, then full-size ones */
 	const int64_t sub = w->sub_tiles;
 	std::vector<int64_t> cuts(1, 0);
-	if (a.memo && ntiles > 4 * JTK_FIRST_SUB_TILES) cuts.push_back(JTK_FIRST_SUB_TILES);
-	while (cuts.back() < ntiles) cuts.push_back(std::min<int64_t>(ntiles, cuts.back() + sub));
+	{
+		/* with a memo the sub-batches grow geometrically (16 MiB, 64 MiB, 256 MiB, ...): pieces merged in one sub-batch are memo
+		 * hits in all later ones, so the early ones are kept short; the later ones are long to amortise launches and tails */
+		int64_t step = (a.memo && ntiles > 4 * JTK_FIRST_SUB_TILES) ? JTK_FIRST_SUB_TILES : sub;
+		while (cuts.back() < ntiles) {
+			cuts.push_back(std::min<int64_t>(ntiles, cuts.back() + std::min<int64_t>(step, sub)));
+			step *= 4;
+		}
+	}
 	const int64_t nsub = (int64_t) cuts.size() - 1;
 	if (time_kernel)
 		while ((int64_t) w->kev.size() < 2 * nsub) {

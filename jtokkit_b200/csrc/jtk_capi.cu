@@ -69,8 +69,6 @@ struct jtk_workspace {
 	jtk_batch_header *hdr_host = nullptr; /* pinned */
 	/* buffers of the host-buffer path */
 	int64_t in_cap = 0, docs_cap = 0;
-	uint8_t *d_in = nullptr;
-	int64_t *d_doc_off = nullptr;
 	int32_t *d_ids = nullptr;
 	int64_t *d_tok_off = nullptr;
 	int32_t *d_status = nullptr;
@@ -104,6 +102,16 @@ struct jtk_device_state {
 	std::mutex mu;
 	std::vector<jtk_workspace *> free_ws;
 	std::vector<jtk_memo_buf *> free_memo;
+	std::vector<struct jtk_in_buf *> free_in;
+};
+
+/* Device-side input buffer of the host-buffer path (one chunk of documents + their offsets).  The copy-in runs on a ring of
+ * these, several chunks ahead of the kernels, so that it finishes early and leaves the PCIe link to the copy-out. */
+struct jtk_in_buf {
+	uint8_t *d_in = nullptr;
+	int64_t cap = 0;
+	int64_t *d_doc = nullptr;
+	int64_t doc_cap = 0;
 };
 
 struct jtk_pinned_buf {
@@ -337,8 +345,6 @@ static void free_workspace(jtk_workspace *w) {
 	cudaFree(w->rx_stacks);
 	cudaFree(w->hdr);
 	cudaFreeHost(w->hdr_host);
-	cudaFree(w->d_in);
-	cudaFree(w->d_doc_off);
 	cudaFree(w->d_ids);
 	cudaFree(w->d_tok_off);
 	cudaFree(w->d_status);
@@ -357,6 +363,11 @@ extern "C" void jtk_encoding_destroy(jtk_encoding *e) {
 	if (!e) return;
 	for (jtk_device_state *ds : e->devs) {
 		cudaSetDevice(ds->device);
+		for (jtk_in_buf *b : ds->free_in) {
+			cudaFree(b->d_in);
+			cudaFree(b->d_doc);
+			delete b;
+		}
 		for (jtk_workspace *w : ds->free_ws) free_workspace(w);
 		for (jtk_memo_buf *m : ds->free_memo) {
 			cudaFree(m->p);
@@ -869,28 +880,21 @@ struct shard_job {
 	std::string err;
 };
 
+/* output-side buffers of a workspace for a chunk of nbytes / ndocs (ids: at most one token per byte) */
 static int ensure_ws_io(jtk_workspace *w, int64_t nbytes, int64_t ndocs, bool want_ids) {
 	if (nbytes > w->in_cap) {
-		cudaFree(w->d_in);
 		cudaFree(w->d_ids);
-		w->d_in = nullptr;
 		w->d_ids = nullptr;
-		w->in_cap = 0;
-		int64_t cap = nbytes + nbytes / 8 + 4096;
-		CUDA_TRY(cudaMalloc(&w->d_in, (size_t) cap + 64));
-		w->in_cap = cap;
+		w->in_cap = nbytes + nbytes / 8 + 4096;
 	}
 	if (want_ids && !w->d_ids) CUDA_TRY(cudaMalloc(&w->d_ids, sizeof(int32_t) * (size_t) (w->in_cap + 16)));
 	if (ndocs > w->docs_cap) {
-		cudaFree(w->d_doc_off);
 		cudaFree(w->d_tok_off);
 		cudaFree(w->d_status);
-		w->d_doc_off = nullptr;
 		w->d_tok_off = nullptr;
 		w->d_status = nullptr;
 		w->docs_cap = 0;
 		int64_t cap = ndocs + ndocs / 8 + 1024;
-		CUDA_TRY(cudaMalloc(&w->d_doc_off, sizeof(int64_t) * (size_t) (cap + 1)));
 		CUDA_TRY(cudaMalloc(&w->d_tok_off, sizeof(int64_t) * (size_t) (cap + 1)));
 		CUDA_TRY(cudaMalloc(&w->d_status, sizeof(int32_t) * (size_t) (cap + 1)));
 		w->docs_cap = cap;
@@ -898,9 +902,30 @@ static int ensure_ws_io(jtk_workspace *w, int64_t nbytes, int64_t ndocs, bool wa
 	return JTK_OK;
 }
 
+static int ensure_in_buf(jtk_in_buf *b, int64_t nbytes, int64_t ndocs) {
+	if (nbytes > b->cap) {
+		cudaFree(b->d_in);
+		b->d_in = nullptr;
+		b->cap = 0;
+		const int64_t cap = nbytes + nbytes / 8 + 4096;
+		CUDA_TRY(cudaMalloc(&b->d_in, (size_t) cap + 64));
+		b->cap = cap;
+	}
+	if (ndocs > b->doc_cap) {
+		cudaFree(b->d_doc);
+		b->d_doc = nullptr;
+		b->doc_cap = 0;
+		const int64_t cap = ndocs + ndocs / 8 + 1024;
+		CUDA_TRY(cudaMalloc(&b->d_doc, sizeof(int64_t) * (size_t) (cap + 1)));
+		b->doc_cap = cap;
+	}
+	return JTK_OK;
+}
+
 /* One shard = one device.  Chunks of whole documents run through a three-stage pipeline on three streams
- * (copy-in, compute, copy-out) over three workspaces: while chunk k is encoded, chunk k+1 is copied in and the ids
- * of chunk k-1 are copied out, so PCIe in both directions and the SMs are busy at the same time. */
+ * (copy-in, compute, copy-out) over NS workspaces: while chunk k is encoded, later chunks are copied in and the ids of
+ * earlier chunks are copied out, so PCIe in both directions and the SMs are busy at the same time.  Stages are ordered by
+ * events between the streams; the host only waits where it has to read a result (token counts, staged offsets). */
 static void run_shard(shard_job *job) {
 	jtk_encoding *e = job->e;
 	jtk_device_state *ds = job->ds;
@@ -911,15 +936,24 @@ static void run_shard(shard_job *job) {
 	if (cudaSetDevice(ds->device) != cudaSuccess) return fail(set_error(JTK_E_CUDA, "cudaSetDevice failed"));
 	const int64_t *off = job->doc_off;
 	const bool want_ids = !(job->flags & JTK_COUNT_ONLY);
-	/* chunk boundaries */
+	/* chunk boundaries: whole documents, chunk sizes ramp up from 8 MiB to chunk_bytes and back down towards the end of the
+	 * shard, so that the exposed head (first copy-in + first compute) and tail (last compute + last copy-out) of the
+	 * copy-in / compute / copy-out pipeline are short while the steady state moves large chunks */
 	std::vector<int64_t> cb;
 	cb.push_back(job->d_begin);
-	while (cb.back() < job->d_end) {
-		int64_t d = cb.back();
-		const int64_t lim = off[d] + e->chunk_bytes;
-		int64_t hi = std::upper_bound(off + d + 1, off + job->d_end + 1, lim) - off - 1; /* last doc end <= lim */
-		if (hi <= d) hi = d + 1;                                                             /* a single oversized document */
-		cb.push_back(hi);
+	{
+		const int64_t small = std::min<int64_t>(e->chunk_bytes, 8ll << 20), end_byte = off[job->d_end];
+		int64_t ramp = small;
+		while (cb.back() < job->d_end) {
+			int64_t d = cb.back();
+			const int64_t remaining = end_byte - off[d];
+			const int64_t want = std::max<int64_t>(small, std::min<int64_t>(std::min<int64_t>(ramp, e->chunk_bytes), remaining / 2));
+			const int64_t lim = off[d] + want;
+			int64_t hi = std::upper_bound(off + d + 1, off + job->d_end + 1, lim) - off - 1; /* last doc end <= lim */
+			if (hi <= d) hi = d + 1;                                                             /* a single oversized document */
+			cb.push_back(hi);
+			ramp *= 2;
+		}
 	}
 	const size_t nchunks = cb.size() - 1;
 	const int64_t shard_bytes = off[job->d_end] - off[job->d_begin];
@@ -929,11 +963,24 @@ static void run_shard(shard_job *job) {
 		if (rc != JTK_OK) return fail(rc);
 	}
 	constexpr int NS = 3;
+	/* JTK_TRACE=1: per-chunk begin / end times of the three stages on stderr (development aid) */
+	static const bool trace = getenv("JTK_TRACE") != nullptr;
+	std::vector<cudaEvent_t> tr;
+	cudaEvent_t tr0 = nullptr;
+	auto mark = [&](cudaStream_t st) {
+		if (!trace) return;
+		cudaEvent_t ev;
+		cudaEventCreate(&ev);
+		cudaEventRecord(ev, st);
+		tr.push_back(ev);
+	};
 	jtk_memo_buf *memo = acquire_memo(ds); /* shared by all chunks of this call on this device */
+	constexpr int NR = 8; /* input ring: the copy-in may run this many chunks ahead of the kernels */
 	jtk_workspace *ws[NS];
-	cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
-	cudaEvent_t ev_in[NS], ev_k0[NS], ev_k1[NS], ev_out[NS];
-	jtk_pinned_buf stage_off[NS], stage_doc[NS];
+	jtk_in_buf *ring[NR];
+	cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr, s_meta = nullptr;
+	cudaEvent_t ev_in[NR], ev_free[NR], ev_k0[NS], ev_k1[NS], ev_out[NS], ev_meta[NS];
+	jtk_pinned_buf stage_off[NS], stage_doc[NR];
 	jtk_device_info infos[NS];
 	int64_t out_chunk[NS]; /* chunk whose copy-out is in flight on the slot, -1 = none */
 	int64_t out_base[NS];
@@ -941,16 +988,30 @@ static void run_shard(shard_job *job) {
 	int rc = JTK_OK;
 	for (int i = 0; i < NS; i++) {
 		ws[i] = acquire_ws(ds);
-		ev_in[i] = ev_k0[i] = ev_k1[i] = ev_out[i] = nullptr;
+		ev_k0[i] = ev_k1[i] = ev_out[i] = ev_meta[i] = nullptr;
 		out_chunk[i] = -1;
 		out_base[i] = 0;
 	}
+	for (int i = 0; i < NR; i++) {
+		ev_in[i] = ev_free[i] = nullptr;
+		ring[i] = nullptr;
+		std::lock_guard<std::mutex> lk(ds->mu);
+		if (!ds->free_in.empty()) {
+			ring[i] = ds->free_in.back();
+			ds->free_in.pop_back();
+		} else {
+			ring[i] = new jtk_in_buf();
+		}
+	}
 	if (cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking) != cudaSuccess ||
-	    cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking) != cudaSuccess)
+	    cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&s_meta, cudaStreamNonBlocking) != cudaSuccess)
 		rc = set_error(JTK_E_CUDA, "cudaStreamCreate failed");
 	for (int i = 0; i < NS && rc == JTK_OK; i++)
-		if (cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&ev_k0[i]) != cudaSuccess ||
-		    cudaEventCreate(&ev_k1[i]) != cudaSuccess || cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming) != cudaSuccess)
+		if (cudaEventCreate(&ev_k0[i]) != cudaSuccess || cudaEventCreate(&ev_k1[i]) != cudaSuccess ||
+		    cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ev_meta[i], cudaEventDisableTiming) != cudaSuccess)
+			rc = set_error(JTK_E_CUDA, "cudaEventCreate failed");
+	for (int i = 0; i < NR && rc == JTK_OK; i++)
+		if (cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming) != cudaSuccess)
 			rc = set_error(JTK_E_CUDA, "cudaEventCreate failed");
 
 	/* the copy-out of a slot has landed: rebase its token offsets / statuses into the shard's arrays */
@@ -987,9 +1048,9 @@ static void run_shard(shard_job *job) {
 			jtk_encode_args a;
 			memset(&a, 0, sizeof(a));
 			fill_args(a, ds, w);
-			a.bytes = w->d_in;
+			a.bytes = ring[k % NR]->d_in;
 			a.total = cbytes;
-			a.doc_off = w->d_doc_off;
+			a.doc_off = ring[k % NR]->d_doc;
 			a.ndocs = nd;
 			a.ntiles = (cbytes + JTK_TILE - 1) / JTK_TILE;
 			a.ids = want_ids ? w->d_ids : nullptr;
@@ -1011,6 +1072,7 @@ static void run_shard(shard_job *job) {
 			cudaEventDestroy(l1);
 			if (r2 != JTK_OK) return r2;
 		}
+		CUDA_TRY(cudaEventRecord(ev_free[k % NR], s_comp)); /* the chunk's input buffer may be overwritten from here on */
 		job->launches += info.gpu_launches;
 		const int64_t ntok = info.num_tokens;
 		if (want_ids) {
@@ -1030,7 +1092,13 @@ static void run_shard(shard_job *job) {
 				pinned_put(e, job->ids);
 				job->ids = bigger;
 			}
+			mark(s_out);
 			CUDA_TRY(cudaMemcpyAsync(static_cast<int32_t *>(job->ids.p) + job->ntokens, w->d_ids, sizeof(int32_t) * (size_t) ntok, cudaMemcpyDeviceToHost, s_out));
+			mark(s_out);
+		}
+		{
+			int r2 = retire(slot); /* the slot's previous copy-out must have been consumed before its staging buffer is reused */
+			if (r2 != JTK_OK) return r2;
 		}
 		jtk_pinned_buf &so = stage_off[slot];
 		const int64_t need = (int64_t) sizeof(int64_t) * (nd + 1) + (int64_t) sizeof(int32_t) * (nd + 1);
@@ -1041,8 +1109,11 @@ static void run_shard(shard_job *job) {
 		}
 		int64_t *h_tok = static_cast<int64_t *>(so.p);
 		int32_t *h_st = reinterpret_cast<int32_t *>(h_tok + nd + 1);
-		CUDA_TRY(cudaMemcpyAsync(h_tok, w->d_tok_off, sizeof(int64_t) * (size_t) (nd + 1), cudaMemcpyDeviceToHost, s_out));
-		if (nd > 0) CUDA_TRY(cudaMemcpyAsync(h_st, w->d_status, sizeof(int32_t) * (size_t) nd, cudaMemcpyDeviceToHost, s_out));
+		/* the small per-document arrays go on their own stream so that the id copies stay back to back on s_out */
+		CUDA_TRY(cudaMemcpyAsync(h_tok, w->d_tok_off, sizeof(int64_t) * (size_t) (nd + 1), cudaMemcpyDeviceToHost, s_meta));
+		if (nd > 0) CUDA_TRY(cudaMemcpyAsync(h_st, w->d_status, sizeof(int32_t) * (size_t) nd, cudaMemcpyDeviceToHost, s_meta));
+		CUDA_TRY(cudaEventRecord(ev_meta[slot], s_meta));
+		CUDA_TRY(cudaStreamWaitEvent(s_out, ev_meta[slot], 0));
 		CUDA_TRY(cudaEventRecord(ev_out[slot], s_out));
 		out_chunk[slot] = (int64_t) k;
 		out_base[slot] = job->ntokens;
@@ -1058,35 +1129,69 @@ static void run_shard(shard_job *job) {
 		return JTK_OK;
 	};
 
+	/* Stream-side ordering, the host does not wait for copies.  The copy-in of chunk j overwrites ring buffer j % NR, free once
+	 * chunk j - NR has been encoded (ev_free, recorded by copy_out); the kernels of chunk k reuse the slot's id / offset
+	 * buffers, free once the copy-out of chunk k - NS has landed (ev_out).  Copy-ins are queued as far ahead as the ring
+	 * allows, so the copy-in finishes early and leaves the PCIe link to the copy-out (measured, profiles/r1_pcie*.txt:
+	 * ~46 GB/s per direction while both are busy, ~56 GB/s alone). */
+	auto issue_in = [&](size_t j) -> int {
+		const int64_t d0 = cb[j], d1 = cb[j + 1], nd = d1 - d0;
+		const int64_t b0 = off[d0], cbytes = off[d1] - b0;
+		jtk_in_buf *in = ring[j % NR];
+		if (j >= (size_t) NR) {
+			if (cbytes <= in->cap && nd <= in->doc_cap) CUDA_TRY(cudaStreamWaitEvent(s_in, ev_free[j % NR], 0));
+			else CUDA_TRY(cudaEventSynchronize(ev_free[j % NR])); /* about to be reallocated */
+		}
+		int r2 = ensure_in_buf(in, cbytes, nd);
+		if (r2 != JTK_OK) return r2;
+		/* chunk-relative document offsets (the kernels require doc_off[0] == 0), staged in pinned memory */
+		jtk_pinned_buf &sd = stage_doc[j % NR];
+		if (sd.cap < (int64_t) sizeof(int64_t) * (nd + 1)) {
+			pinned_put(e, sd);
+			r2 = pinned_get(e, (int64_t) sizeof(int64_t) * (nd + 1) * 5 / 4, &sd);
+			if (r2 != JTK_OK) return r2;
+		}
+		int64_t *rebase = static_cast<int64_t *>(sd.p);
+		for (int64_t i = 0; i <= nd; i++) rebase[i] = off[d0 + i] - b0;
+		if (trace && !tr0) {
+			cudaEventCreate(&tr0);
+			cudaEventRecord(tr0, s_in);
+		}
+		mark(s_in);
+		CUDA_TRY(cudaMemcpyAsync(in->d_doc, rebase, sizeof(int64_t) * (size_t) (nd + 1), cudaMemcpyHostToDevice, s_in));
+		if (cbytes > 0) CUDA_TRY(cudaMemcpyAsync(in->d_in, job->utf8 + b0, (size_t) cbytes, cudaMemcpyHostToDevice, s_in));
+		mark(s_in);
+		CUDA_TRY(cudaEventRecord(ev_in[j % NR], s_in));
+		return JTK_OK;
+	};
+	size_t next_in = 0;
 	for (size_t k = 0; k < nchunks && rc == JTK_OK; k++) {
 		const int slot = (int) (k % NS);
 		jtk_workspace *w = ws[slot];
 		const int64_t d0 = cb[k], d1 = cb[k + 1], nd = d1 - d0;
-		const int64_t b0 = off[d0], cbytes = off[d1] - b0;
-		rc = retire(slot); /* the slot's previous copy-out must have landed before its buffers are reused */
+		const int64_t cbytes = off[d1] - off[d0];
+		/* ev_free of chunk j - NR is recorded by copy_out(j - NR); at this point copy_out has been called for the chunks up to k - 2 */
+		while (rc == JTK_OK && next_in < nchunks && (next_in < (size_t) NR || next_in + 2 <= k + (size_t) NR)) rc = issue_in(next_in++);
 		if (rc != JTK_OK) break;
+		jtk_in_buf *in = ring[k % NR];
+		if (k >= (size_t) NS) {
+			if (cbytes <= w->in_cap && nd <= w->docs_cap) {
+				cudaStreamWaitEvent(s_comp, ev_out[slot], 0);
+			} else {
+				rc = retire(slot); /* the slot's buffers are about to be reallocated: its copy-out must have landed */
+				if (rc != JTK_OK) break;
+			}
+		}
 		rc = ensure_ws_io(w, cbytes, nd, want_ids);
 		if (rc != JTK_OK) break;
-		/* chunk-relative document offsets (the kernels require doc_off[0] == 0), staged in pinned memory */
-		jtk_pinned_buf &sd = stage_doc[slot];
-		if (sd.cap < (int64_t) sizeof(int64_t) * (nd + 1)) {
-			pinned_put(e, sd);
-			rc = pinned_get(e, (int64_t) sizeof(int64_t) * (nd + 1) * 5 / 4, &sd);
-			if (rc != JTK_OK) break;
-		}
-		int64_t *rebase = static_cast<int64_t *>(sd.p);
-		for (int64_t i = 0; i <= nd; i++) rebase[i] = off[d0 + i] - b0;
-		cudaError_t ce = cudaMemcpyAsync(w->d_doc_off, rebase, sizeof(int64_t) * (size_t) (nd + 1), cudaMemcpyHostToDevice, s_in);
-		if (ce == cudaSuccess && cbytes > 0) ce = cudaMemcpyAsync(w->d_in, job->utf8 + b0, (size_t) cbytes, cudaMemcpyHostToDevice, s_in);
-		if (ce == cudaSuccess && nd > 0) ce = cudaMemsetAsync(w->d_status, 0, sizeof(int32_t) * (size_t) nd, s_in);
-		if (ce == cudaSuccess) ce = cudaEventRecord(ev_in[slot], s_in);
-		if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s_comp, ev_in[slot], 0);
+		cudaError_t ce = cudaStreamWaitEvent(s_comp, ev_in[k % NR], 0);
+		if (ce == cudaSuccess && nd > 0) ce = cudaMemsetAsync(w->d_status, 0, sizeof(int32_t) * (size_t) nd, s_comp); /* after the slot's previous copy-out */
 		if (ce != cudaSuccess) {
-			rc = set_error(JTK_E_CUDA, std::string("H2D: ") + cudaGetErrorString(ce));
+			rc = set_error(JTK_E_CUDA, std::string("chunk set-up: ") + cudaGetErrorString(ce));
 			break;
 		}
 		cudaEventRecord(ev_k0[slot], s_comp);
-		rc = encode_device_impl(e, ds, w, w->d_in, cbytes, w->d_doc_off, nd, job->flags, want_ids ? w->d_ids : nullptr, w->in_cap, w->d_tok_off, w->d_status,
+		rc = encode_device_impl(e, ds, w, in->d_in, cbytes, in->d_doc, nd, job->flags, want_ids ? w->d_ids : nullptr, w->in_cap, w->d_tok_off, w->d_status,
 		                        nullptr, s_comp, &infos[slot], false, memo);
 		cudaEventRecord(ev_k1[slot], s_comp);
 		if (rc != JTK_OK) break;
@@ -1098,18 +1203,41 @@ static void run_shard(shard_job *job) {
 	if (s_in) cudaStreamSynchronize(s_in);
 	if (s_comp) cudaStreamSynchronize(s_comp);
 	if (s_out) cudaStreamSynchronize(s_out);
+	if (s_meta) cudaStreamSynchronize(s_meta);
+	if (trace && tr0) {
+		/* marks come in pairs: per chunk one copy-in pair (in loop order) and, when ids are wanted, one copy-out pair */
+		std::string line = "jtk trace (ms since first copy-in):";
+		for (size_t i = 0; i + 1 < tr.size(); i += 2) {
+			float t0 = 0, t1 = 0;
+			cudaEventElapsedTime(&t0, tr0, tr[i]);
+			cudaEventElapsedTime(&t1, tr0, tr[i + 1]);
+			char buf[64];
+			snprintf(buf, sizeof(buf), " [%.2f %.2f]", t0, t1);
+			line += buf;
+		}
+		fprintf(stderr, "%s\n", line.c_str());
+		for (cudaEvent_t ev : tr) cudaEventDestroy(ev);
+		cudaEventDestroy(tr0);
+	}
 	for (int i = 0; i < NS; i++) {
-		if (ev_in[i]) cudaEventDestroy(ev_in[i]);
 		if (ev_k0[i]) cudaEventDestroy(ev_k0[i]);
 		if (ev_k1[i]) cudaEventDestroy(ev_k1[i]);
 		if (ev_out[i]) cudaEventDestroy(ev_out[i]);
+		if (ev_meta[i]) cudaEventDestroy(ev_meta[i]);
 		release_ws(ds, ws[i]);
 		pinned_put(e, stage_off[i]);
+	}
+	for (int i = 0; i < NR; i++) {
+		if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+		if (ev_free[i]) cudaEventDestroy(ev_free[i]);
 		pinned_put(e, stage_doc[i]);
+		std::lock_guard<std::mutex> lk(ds->mu);
+		ds->free_in.push_back(ring[i]);
 	}
 	if (s_in) cudaStreamDestroy(s_in);
 	if (s_comp) cudaStreamDestroy(s_comp);
 	if (s_out) cudaStreamDestroy(s_out);
+	if (s_meta) cudaStreamDestroy(s_meta);
 	release_memo(ds, memo);
 	if (rc != JTK_OK) fail(rc);
 }

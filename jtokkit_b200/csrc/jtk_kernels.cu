@@ -1272,7 +1272,8 @@ cudaError_t jtk_launch_post(const jtk_encode_args &a, int num_sms, cudaStream_t 
 		cudaEventRecord(side->fork, st);
 		for (int i = 0; i < 3; i++) cudaStreamWaitEvent(side->s[i], side->fork, 0);
 	}
-	cfg.gridDim = dim3((unsigned) (num_sms * 6));
+	static const int merge_grid = getenv("JTK_MERGE_GRID") ? atoi(getenv("JTK_MERGE_GRID")) : 6; /* persistent CTAs per SM of each merge kernel */
+	cfg.gridDim = dim3((unsigned) (num_sms * merge_grid));
 	cfg.blockDim = dim3(GNTM);
 	cfg.stream = side ? side->s[0] : st;
 	cudaLaunchKernelEx(&cfg, jtk_merge_medium_kernel, a);

@@ -31,21 +31,22 @@ for r in rows[2:]:
         out.append("    %-40s %.3f" % (k.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), v))
     traffic.append(sum(float(m[k].replace(",", "")) * scale.get(u[k], 1) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum")))
 open(os.path.join(P, "r1_split_lookup_ncu_full.txt"), "w").write(
-    "ncu --set full --clock-control none --import-source on -k regex:jtk_split_lookup -s 28 -c 2 python bench.py --steps 2 --warmup 3 --no-cpu-baseline\n"
-    "(selected raw metrics; a launch covers one 128 MiB sub-batch = 16384 tiles of the 1 GiB multilingual corpus)\n\n" + "\n".join(out) + "\n")
-summ = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), os.path.join(G, "r1_split_lookup.ncu-rep"), "134217728"], capture_output=True, text=True).stdout
+    "ncu --set full --clock-control none --import-source on -k regex:jtk_split_lookup -s 17 -c 1 python bench.py --steps 2 --warmup 3 --no-cpu-baseline\n"
+    "(selected raw metrics; the launch covers the 256 MiB sub-batch = 32768 tiles of the first timed step over the 1 GiB multilingual corpus;\n"
+    " a step runs five sub-batches of 16, 64, 256, 512 and 176 MiB)\n\n" + "\n".join(out) + "\n")
+summ = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), os.path.join(G, "r1_split_lookup.ncu-rep"), "268435456"], capture_output=True, text=True).stdout
 open(os.path.join(P, "r1_split_lookup_source_hotspots.txt"), "w").write("per-function / per-line shares from the ncu source page (first captured launch)\n\n" + summ)
-# the dominant kernel launches once per sub-batch; scale to a whole step (1 GiB = 8 sub-batches of 128 MiB, the first split 16 + 112 MiB)
+# the dominant kernel launches once per sub-batch; the captured launch covers 256 MiB of the step's 1 GiB: scale by 4
 per_launch = sum(traffic) / len(traffic)
-json.dump({"kernel": "jtk_split_lookup_kernel", "dram_bytes_per_launch": per_launch, "launch": "one 128 MiB sub-batch (16384 tiles)",
-           "dram_bytes_per_step": per_launch * 8, "source": "profiles/r1_split_lookup_ncu_full.txt"}, open(os.path.join(P, "tile_kernel_traffic.json"), "w"), indent=1)
+json.dump({"kernel": "jtk_split_lookup_kernel", "dram_bytes_per_launch": per_launch, "launch": "the 256 MiB sub-batch (32768 tiles) of a step",
+           "dram_bytes_per_step": per_launch * 4, "source": "profiles/r1_split_lookup_ncu_full.txt"}, open(os.path.join(P, "tile_kernel_traffic.json"), "w"), indent=1)
 mg = os.path.join(G, "r1_merge_gather.ncu-rep")
 if os.path.exists(mg):
     raw = subprocess.run(["ncu", "-i", mg, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     h, units = rows[0], rows[1]
-    out = ["JTK_SIDE_STREAMS=0 ncu --set full --clock-control none -k regex:jtk_merge_short|jtk_merge_medium|jtk_gather -s 140 -c 5 python bench.py --steps 2 --warmup 3 --no-cpu-baseline",
-           "(one full-size sub-batch; in production the four merge kernels run side by side on forked streams)", ""]
+    out = ["JTK_SIDE_STREAMS=0 ncu --set full --clock-control none -k regex:jtk_merge_short|jtk_merge_medium|jtk_gather -s 85 -c 5 python bench.py --steps 2 --warmup 3 --no-cpu-baseline",
+           "(the 256 MiB sub-batch of the first timed step; in production the four merge kernels run side by side on forked streams)", ""]
     for r in rows[2:]:
         m, u = dict(zip(h, r)), dict(zip(h, units))
         out.append(m.get("Kernel Name", "?"))

@@ -832,16 +832,23 @@ __global__ void __launch_bounds__(GNT, 8) jtk_gather_kernel(const __grid_constan
 						if (rec_is_id(r[j])) {
 							s_tok[pos] = r[j];
 						} else {
-							const int off = (int) ((rec_payload(r[j]) >> 11) & 0x3FFFu); /* dense area of the tile's slowtok slice */
+							/* merged / memoised piece: only note WHERE its tokens are (REC_BASE + index into the tile's slowtok slice);
+							 * the loads happen in the coalesced copy loop below, all in flight together, instead of one dependent
+							 * load per iteration of this divergent loop */
+							const int off = (int) ((rec_payload(r[j]) >> 11) & 0x3FFFu);
 							for (int k = 0; k < cnt[j]; k++)
-								if (pos + k >= 0 && pos + k < GCAP) s_tok[pos + k] = stok[off + k];
+								if (pos + k >= 0 && pos + k < GCAP) s_tok[pos + k] = REC_BASE + (off + k);
 						}
 					}
 					pos += cnt[j];
 				}
 				__syncthreads();
 				const int nw = min(GCAP, round_total - w0);
-				for (int k = tid; k < nw; k += GNT) dst[carry + w0 + k] = s_tok[k];
+				for (int k = tid; k < nw; k += GNT) {
+					int32_t v = s_tok[k];
+					if (!rec_is_id(v)) v = stok[v - REC_BASE];
+					dst[carry + w0 + k] = v;
+				}
 				if (w0 + GCAP < round_total) __syncthreads();
 			}
 		}

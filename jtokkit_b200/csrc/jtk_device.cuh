@@ -840,18 +840,20 @@ JTK_HD int jtk_merge_short_t(const jtk_tables &T, const uint8_t *p, int n, int32
 		 * sequential loop would do */
 		int32_t mr = JTK_RANK_MAX, mr2 = JTK_RANK_MAX;
 		int mi = -1, mi2 = -1;
-		for (MaskT m = alive; m;) {
-			const int k = ctz(m);
-			m &= m - 1;
-			const int32_t r = rk[k * stride];
-			if (r < mr) {
-				mr2 = mr;
-				mi2 = mi;
-				mr = r;
-				mi = k;
-			} else if (r < mr2) {
-				mr2 = r;
-				mi2 = k;
+		for (int half = 0; half < BITS / 32; half++) { /* 32 bits at a time: find-first-set on 64 bits is several instructions */
+			for (uint32_t m = (uint32_t) (alive >> (half ? BITS - 32 : 0)); m;) {
+				const int k = 32 * half + jtk_ctz(m);
+				m &= m - 1;
+				const int32_t r = rk[k * stride];
+				if (r < mr) {
+					mr2 = mr;
+					mi2 = mi;
+					mr = r;
+					mi = k;
+				} else if (r < mr2) {
+					mr2 = r;
+					mi2 = k;
+				}
 			}
 		}
 		if (mi < 0) break; /* :247,260-262 */

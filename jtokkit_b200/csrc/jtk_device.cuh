@@ -315,6 +315,15 @@ JTK_HD int jtk_global_count_n_before(const jtk_tile_ctx &c, int64_t g) {
 	int64_t lo = jtk_doc_floor(c, g);
 	int k = 0;
 	while (g > lo) {
+		if ((g & 7) == 0 && g - 8 >= lo) {
+			/* eight ASCII digits at once (a run of a million digits would otherwise be walked byte by byte from every tile) */
+			const uint64_t t = *reinterpret_cast<const uint64_t *>(c.gbytes + g - 8) ^ 0x3030303030303030ull;
+			if ((((t + 0x7676767676767676ull) | t) & 0x8080808080808080ull) == 0) {
+				k = (k + 8) % 3;
+				g -= 8;
+				continue;
+			}
+		}
 		int64_t lead;
 		if (jtk_global_char_before(c, g, lo, &lead) != JTK_C_N) break;
 		k = (k + 1) % 3;

@@ -599,8 +599,8 @@ static int run_long_pieces(jtk_device_state *ds, jtk_workspace *w, jtk_encode_ar
 		if (lp.end - lp.start > 0x7ffffff0ll) return set_error(JTK_E_ARG, "a single piece exceeds 2 GiB");
 	}
 	int32_t *scr = nullptr;
-	CUDA_TRY(cudaMalloc(&scr, sizeof(int32_t) * 4 * (size_t) parts));
-	int32_t *scr_tok = scr, *scr_rk = scr + parts, *scr_nxt = scr + 2 * parts, *scr_prv = scr + 3 * parts;
+	CUDA_TRY(cudaMalloc(&scr, sizeof(int32_t) * JTK_LONG_SCRATCH_ARRAYS * (size_t) parts));
+	int32_t *scr_tok = scr;
 	int rc = JTK_OK;
 	int64_t *d_cum = nullptr;
 	int32_t *ids2 = nullptr;
@@ -612,7 +612,7 @@ static int run_long_pieces(jtk_device_state *ds, jtk_workspace *w, jtk_encode_ar
 		break;                                                                                  \
 	}
 		LTRY(cudaMemcpyAsync(a.long_list, list.data(), sizeof(jtk_long_piece) * n_long, cudaMemcpyHostToDevice, st));
-		LTRY(jtk_launch_long_merge(a, n_long, scr_tok, scr_rk, scr_nxt, scr_prv, ds->num_sms, st));
+		LTRY(jtk_launch_long_merge(a, n_long, scr, parts, ds->num_sms, st));
 		LTRY(cudaMemcpyAsync(list.data(), a.long_list, sizeof(jtk_long_piece) * n_long, cudaMemcpyDeviceToHost, st));
 		LTRY(cudaMemcpyAsync(w->hdr_host, a.hdr, sizeof(jtk_batch_header), cudaMemcpyDeviceToHost, st));
 		LTRY(cudaStreamSynchronize(st));

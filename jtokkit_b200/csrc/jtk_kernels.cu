@@ -932,13 +932,20 @@ struct long_scan_state {
 	int reset; /* 1 when a live unflagged part occurs in the span */
 };
 
-__global__ void __launch_bounds__(LNT, 1)
-    jtk_long_merge_kernel(const jtk_encode_args a, unsigned int n_long, int32_t *scr_tok, int32_t *scr_rk, int32_t *scr_nxt, int32_t *scr_prv) {
+/* Scratch of the long-piece kernel: eight int32 arrays of `stride` elements (one slot per input byte of all long pieces). */
+struct jtk_long_scratch {
+	int32_t *base;
+	int64_t stride;
+};
+
+enum { LST_NONE = 0, LST_UNK = 1, LST_SEL = 2, LST_REJ = 3 }; /* per-part status of the round; bit 2: the pair to the left is selected too */
+
+__global__ void __launch_bounds__(LNT, 1) jtk_long_merge_kernel(const jtk_encode_args a, unsigned int n_long, const jtk_long_scratch scr) {
 	__shared__ int32_t s_red[LNT / 32];
 	__shared__ int s_scan_run[LNT / 32];
 	__shared__ int s_scan_reset[LNT / 32];
 	__shared__ int32_t s_min;
-	__shared__ int s_flag, s_piece, s_carry_run, s_first;
+	__shared__ int s_flag, s_piece, s_carry_run, s_first, s_m, s_unk;
 	const jtk_tables &T = a.T;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	for (;;) {
@@ -951,7 +958,8 @@ __global__ void __launch_bounds__(LNT, 1)
 		const int64_t n64 = lp.end - lp.start;
 		const int n = (int) n64;
 		const uint8_t *p = a.bytes + lp.start;
-		int32_t *tok = scr_tok + lp.scratch, *rk = scr_rk + lp.scratch, *nxt = scr_nxt + lp.scratch, *prv = scr_prv + lp.scratch;
+		int32_t *tok = scr.base + lp.scratch, *rk = tok + scr.stride, *nxt = rk + scr.stride, *prv = nxt + scr.stride, *st = prv + scr.stride,
+		        *aux0 = st + scr.stride, *aux1 = aux0 + scr.stride, *cand = aux1 + scr.stride;
 		bool strict = false;
 	restart:
 		for (int k = tid; k < n; k += LNT) {
@@ -959,10 +967,19 @@ __global__ void __launch_bounds__(LNT, 1)
 			rk[k] = (k + 1 < n) ? T.bytepair[((uint32_t) p[k] << 8) | p[k + 1]] : JTK_RANK_MAX;
 			nxt[k] = k + 1;
 			prv[k] = k - 1;
+			st[k] = LST_NONE;
 		}
 		__syncthreads();
+		/* Rounds.  A round merges, in one go, the pairs the reference loop would merge next: every pair whose rank is at most
+		 * T = (current minimum) + window and that survives the (rank, position) priority among adjacent candidates.  That is
+		 * exactly the sequential order as long as no pair CREATED by these merges - the final ones and the transient one
+		 * between two merges that are one part apart - ranks at or below T; this is checked before anything is changed.
+		 * On a failed check the round is redone with window 0 (only the minimum rank: adjacent candidates then form runs of
+		 * equal rank, resolved by a parity scan), and if that fails too (a vocabulary in which a concatenation ranks below
+		 * its parts) the piece restarts in strict mode: one merge per round, the reference loop verbatim. */
+		int wcur = 0, cool = 0, cool_len = 2; /* window; rounds to stay at window 0 after a failed windowed round (doubles per failure) */
+		bool force_exact = false;
 		for (;;) {
-			/* global minimum rank (and, in strict mode, its leftmost position) */
 			int32_t mr = JTK_RANK_MAX;
 			for (int k = tid; k < n; k += LNT) mr = min(mr, rk[k]);
 			mr = __reduce_min_sync(0xFFFFFFFFu, mr);
@@ -976,6 +993,7 @@ __global__ void __launch_bounds__(LNT, 1)
 					s_flag = 0;
 					s_carry_run = 0;
 					s_first = 0x7fffffff;
+					s_m = 0;
 				}
 			}
 			__syncthreads();
@@ -1005,124 +1023,211 @@ __global__ void __launch_bounds__(LNT, 1)
 				__syncthreads();
 				continue;
 			}
-			/* selection: in list order, a flagged part (rk == mr) is selected iff an even number of flagged parts
-			 * directly precede it.  Blocked scan over positions, LNT * 8 positions per step, removed parts are
-			 * transparent.  Selected parts get rk = -mark (SEL) so that the merge pass can find them. */
-			for (int base = 0; base < n; base += LNT * 8) {
-				const int k0 = base + tid * 8;
-				int run = 0, reset = 0; /* summary of this thread's 8 positions */
-				int loc_run[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-				/* removed parts are marked by nxt[k] = -1 and are transparent */
-				for (int i = 0; i < 8; i++) {
-					const int k = k0 + i;
-					if (k >= n || nxt[k] < 0) continue;
-					loc_run[i] = 0;
-					if (rk[k] == mr) {
-						loc_run[i] = run; /* flagged parts directly before it inside this thread's span */
-						run++;
-					} else {
-						run = 0;
-						reset = 1;
+			const int win = (force_exact || cool > 0) ? 0 : wcur;
+			const int32_t thr = (win > 0 && mr < JTK_RANK_MAX - 2 - win) ? mr + win : mr;
+			const bool windowed = thr > mr;
+			/* candidates: parts whose pair ranks at most thr (removed parts and the last part have rk = JTK_RANK_MAX) */
+			for (int k = tid; k < n; k += LNT)
+				if (rk[k] <= thr) {
+					cand[atomicAdd(&s_m, 1)] = k;
+					st[k] = LST_UNK;
+				}
+			__syncthreads();
+			const int m = s_m;
+			bool failed = false, chains = false;
+			if (windowed) {
+				/* priority among adjacent candidates: a candidate is selected iff no adjacent candidate with a smaller (rank, position)
+				 * key is selected.  Relaxation; chains of decreasing keys are short unless the ranks are equal (window 0 handles those). */
+				for (int it = 0;; it++) {
+					if (tid == 0) s_unk = 0;
+					__syncthreads();
+					int undecided = 0;
+					for (int i = tid; i < m; i += LNT) {
+						const int k = cand[i];
+						if (st[k] != LST_UNK) continue;
+						const int32_t r = rk[k];
+						const int l = prv[k], rt = nxt[k];
+						const int sl = l >= 0 ? (st[l] & 3) : LST_NONE, sr = rt < n ? (st[rt] & 3) : LST_NONE;
+						const bool lsm = sl != LST_NONE && rk[l] <= r; /* left neighbour: smaller position, so smaller key on equal ranks */
+						const bool rsm = sr != LST_NONE && rk[rt] < r;
+						if ((lsm && sl == LST_SEL) || (rsm && sr == LST_SEL)) st[k] = LST_REJ;
+						else if ((!lsm || sl == LST_REJ) && (!rsm || sr == LST_REJ)) st[k] = LST_SEL;
+						else undecided++;
+					}
+					undecided = __reduce_add_sync(0xFFFFFFFFu, undecided);
+					if (lane == 0 && undecided) atomicAdd(&s_unk, undecided);
+					__syncthreads();
+					const int unk = s_unk;
+					__syncthreads();
+					if (!unk) break;
+					/* chains of decreasing keys shrink geometrically; a long run of equal ranks (repeated text) loses one part per
+					 * iteration: leave those to window 0, which resolves them with a scan */
+					if (it >= 40 || (it >= 6 && unk > m / 2)) {
+						failed = chains = true;
+						break;
 					}
 				}
-				/* exclusive scan of (run, reset) across threads */
-				int xr = run, xs = reset;
-				for (int o = 1; o < 32; o <<= 1) {
-					int yr = __shfl_up_sync(0xFFFFFFFFu, xr, o), ys = __shfl_up_sync(0xFFFFFFFFu, xs, o);
-					if (lane >= o) {
-						if (!xs) xr += yr;
-						xs |= ys;
-					}
-				}
-				if (lane == 31) {
-					s_scan_run[warp] = xr;
-					s_scan_reset[warp] = xs;
-				}
-				__syncthreads();
-				if (warp == 0) {
-					int vr = s_scan_run[lane], vs = s_scan_reset[lane];
-					for (int o = 1; o < 32; o <<= 1) {
-						int yr = __shfl_up_sync(0xFFFFFFFFu, vr, o), ys = __shfl_up_sync(0xFFFFFFFFu, vs, o);
-						if (lane >= o) {
-							if (!vs) vr += yr;
-							vs |= ys;
+			} else {
+				/* window 0: in list order, a flagged part (rk == mr) is selected iff an even number of flagged parts directly precede
+				 * it.  Blocked scan over positions, LNT * 8 positions per step, removed parts are transparent. */
+				for (int base = 0; base < n; base += LNT * 8) {
+					const int k0 = base + tid * 8;
+					int run = 0, reset = 0; /* summary of this thread's 8 positions */
+					int loc_run[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+					for (int i = 0; i < 8; i++) {
+						const int k = k0 + i;
+						if (k >= n || nxt[k] < 0) continue;
+						loc_run[i] = 0;
+						if (rk[k] == mr) {
+							loc_run[i] = run; /* flagged parts directly before it inside this thread's span */
+							run++;
+						} else {
+							run = 0;
+							reset = 1;
 						}
 					}
-					s_scan_run[lane] = vr;
-					s_scan_reset[lane] = vs;
+					/* scan of (run, reset) across threads */
+					int xr = run, xs = reset;
+					for (int o = 1; o < 32; o <<= 1) {
+						int yr = __shfl_up_sync(0xFFFFFFFFu, xr, o), ys = __shfl_up_sync(0xFFFFFFFFu, xs, o);
+						if (lane >= o) {
+							if (!xs) xr += yr;
+							xs |= ys;
+						}
+					}
+					if (lane == 31) {
+						s_scan_run[warp] = xr;
+						s_scan_reset[warp] = xs;
+					}
+					__syncthreads();
+					if (warp == 0) {
+						int vr = s_scan_run[lane], vs = s_scan_reset[lane];
+						for (int o = 1; o < 32; o <<= 1) {
+							int yr = __shfl_up_sync(0xFFFFFFFFu, vr, o), ys = __shfl_up_sync(0xFFFFFFFFu, vs, o);
+							if (lane >= o) {
+								if (!vs) vr += yr;
+								vs |= ys;
+							}
+						}
+						s_scan_run[lane] = vr;
+						s_scan_reset[lane] = vs;
+					}
+					__syncthreads();
+					/* exclusive prefix for this thread: carry (block) . warps before . lanes before */
+					int pr = s_carry_run;
+					if (warp > 0) {
+						if (s_scan_reset[warp - 1]) pr = s_scan_run[warp - 1];
+						else pr += s_scan_run[warp - 1];
+					}
+					{
+						int er = __shfl_up_sync(0xFFFFFFFFu, xr, 1), es = __shfl_up_sync(0xFFFFFFFFu, xs, 1);
+						if (lane > 0) {
+							if (es) pr = er;
+							else pr += er;
+						}
+					}
+					bool seen_reset = false;
+					for (int i = 0; i < 8; i++) {
+						const int k = k0 + i;
+						if (k >= n || nxt[k] < 0) continue;
+						if (rk[k] == mr) {
+							const int before = seen_reset ? loc_run[i] : loc_run[i] + pr;
+							st[k] = (before & 1) == 0 ? LST_SEL : LST_REJ;
+						} else {
+							seen_reset = true;
+						}
+					}
+					__syncthreads();
+					if (tid == LNT - 1) {
+						/* carry for the next step: inclusive result of the last thread */
+						int cr = s_scan_run[LNT / 32 - 1];
+						int cs = s_scan_reset[LNT / 32 - 1];
+						s_carry_run = cs ? cr : s_carry_run + cr;
+					}
+					__syncthreads();
+				}
+			}
+			/* check, without changing anything: the ranks of the pairs these merges create */
+			if (!failed) {
+				for (int i = tid; i < m; i += LNT) {
+					const int k = cand[i];
+					if ((st[k] & 3) != LST_SEL) continue;
+					const int32_t mk = rk[k]; /* rank of the pair == id of the merged token */
+					const int j = nxt[k], nn = nxt[j], pv = prv[k];
+					int32_t r1 = JTK_RANK_MAX, r0 = JTK_RANK_MAX;
+					bool bad = false;
+					if (nn < n) {
+						int32_t right = tok[nn];
+						if ((st[nn] & 3) == LST_SEL) { /* the next pair merges too: between the two merges the pair (merged, its first part) exists */
+							if (jtk_lookup_pair(T, mk, right) <= thr) bad = true;
+							right = rk[nn];
+						}
+						r1 = jtk_lookup_pair(T, mk, right);
+						if (r1 <= thr) bad = true;
+					}
+					if (pv >= 0) {
+						const int ppv = prv[pv];
+						int32_t left = tok[pv];
+						if (ppv >= 0 && (st[ppv] & 3) == LST_SEL) { /* pv is the second part of a selected pair */
+							if (jtk_lookup_pair(T, left, mk) <= thr) bad = true;
+							left = rk[ppv];
+							st[k] = LST_SEL | 4;
+						}
+						r0 = jtk_lookup_pair(T, left, mk);
+						if (r0 <= thr) bad = true;
+					}
+					aux0[k] = r0;
+					aux1[k] = r1;
+					if (bad) s_flag = 1;
 				}
 				__syncthreads();
-				/* exclusive prefix for this thread: carry (block) . warps before . lanes before */
-				int pr = s_carry_run, ps = 0;
-				if (warp > 0) {
-					if (s_scan_reset[warp - 1]) {
-						pr = s_scan_run[warp - 1];
-						ps = 1;
-					} else pr += s_scan_run[warp - 1];
-				}
-				{
-					int er = __shfl_up_sync(0xFFFFFFFFu, xr, 1), es = __shfl_up_sync(0xFFFFFFFFu, xs, 1);
-					if (lane > 0) {
-						if (es) {
-							pr = er;
-							ps = 1;
-						} else pr += er;
+				failed = s_flag != 0;
+			}
+			if (!failed) {
+				/* apply */
+				for (int i = tid; i < m; i += LNT) {
+					const int k = cand[i];
+					const int s0 = st[k];
+					if ((s0 & 3) != LST_SEL) continue;
+					const int j = nxt[k], nn = nxt[j];
+					tok[k] = rk[k];
+					rk[j] = DEAD;
+					nxt[j] = -1;
+					nxt[k] = nn;
+					if (nn < n) prv[nn] = k;
+					rk[k] = aux1[k];
+					if (!(s0 & 4)) { /* otherwise the pair to the left was selected: its own new rank covers this one */
+						const int pv = prv[k];
+						if (pv >= 0) rk[pv] = aux0[k];
 					}
 				}
-				(void) ps;
-				/* mark selections */
-				bool seen_reset = false;
-				for (int i = 0; i < 8; i++) {
-					const int k = k0 + i;
-					if (k >= n || nxt[k] < 0) continue;
-					if (rk[k] == mr) {
-						const int before = seen_reset ? loc_run[i] : loc_run[i] + pr;
-						if ((before & 1) == 0) rk[k] = JTK_RANK_MAX - 1; /* SEL marker (never a real rank: ranks < MAX-1 enforced at registration) */
-					} else {
-						seen_reset = true;
+			}
+			__syncthreads();
+			for (int i = tid; i < m; i += LNT) st[cand[i]] = LST_NONE;
+			__syncthreads();
+			if (failed) {
+				if (windowed) { /* redo the round with the minimum rank only, and stay there for a while */
+					wcur >>= 2;
+					force_exact = true;
+					if (chains) { /* repeated text: windows will keep failing for a while */
+						cool_len = min(cool_len * 2, 1 << 20);
+						cool = cool_len;
 					}
+					continue;
 				}
-				__syncthreads();
-				if (tid == LNT - 1) {
-					/* carry for the next step: inclusive result of the last thread */
-					int cr = s_scan_run[LNT / 32 - 1];
-					int cs = s_scan_reset[LNT / 32 - 1];
-					s_carry_run = cs ? cr : s_carry_run + cr;
-				}
-				__syncthreads();
-			}
-			/* merge every selected pair */
-			for (int k = tid; k < n; k += LNT) {
-				if (rk[k] != JTK_RANK_MAX - 1) continue;
-				const int j = nxt[k];
-				const int nn = nxt[j];
-				tok[k] = mr;
-				rk[j] = DEAD;
-				nxt[j] = -1;
-				nxt[k] = nn;
-				if (nn < n) prv[nn] = k;
-			}
-			__syncthreads();
-			/* recompute the ranks around every merged part (:254-257) */
-			for (int k = tid; k < n; k += LNT) {
-				if (rk[k] != JTK_RANK_MAX - 1) continue;
-				const int nn = nxt[k];
-				const int32_t r1 = nn < n ? jtk_lookup_pair(T, mr, tok[nn]) : JTK_RANK_MAX;
-				/* the right neighbour may itself be a merged part; both sides then compute the same value */
-				int32_t r0 = JTK_RANK_MAX;
-				const int pv = prv[k];
-				if (pv >= 0) r0 = jtk_lookup_pair(T, tok[pv], mr);
-				if (r1 < mr || r0 < mr) s_flag = 1; /* a new pair outranks the round: not equal to the sequential order */
-				rk[k] = r1;
-				if (pv >= 0 && rk[pv] != JTK_RANK_MAX - 1) rk[pv] = r0;
-			}
-			__syncthreads();
-			if (s_flag) {
 				strict = true;
 				if (tid == 0) atomicAdd(&a.hdr->violations, 1u);
 				__syncthreads();
 				goto restart;
 			}
+			if (windowed) {
+				wcur = min(wcur * 2, 1 << 24);
+				cool_len = 2;
+			} else if (cool > 0) {
+				cool--;
+			}
+			if (wcur < 16) wcur = 16;
+			force_exact = false;
 		}
 		/* compact the surviving parts: out[0..count) = tokens in order (written over tok[] front via rk[] as temp) */
 		__syncthreads();
@@ -1321,10 +1426,12 @@ cudaError_t jtk_launch_long_bounds(const jtk_encode_args &a, unsigned int n_long
 	return cudaGetLastError();
 }
 
-cudaError_t jtk_launch_long_merge(const jtk_encode_args &a, unsigned int n_long, int32_t *scr_tok, int32_t *scr_rk, int32_t *scr_nxt, int32_t *scr_prv,
-                                  int num_sms, cudaStream_t st) {
+cudaError_t jtk_launch_long_merge(const jtk_encode_args &a, unsigned int n_long, int32_t *scratch, int64_t stride, int num_sms, cudaStream_t st) {
 	unsigned grid = n_long < (unsigned) num_sms ? n_long : (unsigned) num_sms;
-	jtk_long_merge_kernel<<<grid, LNT, 0, st>>>(a, n_long, scr_tok, scr_rk, scr_nxt, scr_prv);
+	jtk_long_scratch scr;
+	scr.base = scratch;
+	scr.stride = stride;
+	jtk_long_merge_kernel<<<grid, LNT, 0, st>>>(a, n_long, scr);
 	return cudaGetLastError();
 }
 

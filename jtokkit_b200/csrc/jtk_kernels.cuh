@@ -119,8 +119,9 @@ cudaError_t jtk_encode_kernel_setup();
 
 /* long-piece path */
 cudaError_t jtk_launch_long_bounds(const jtk_encode_args &a, unsigned int n_long, cudaStream_t st);
-cudaError_t jtk_launch_long_merge(const jtk_encode_args &a, unsigned int n_long, int32_t *scr_tok, int32_t *scr_rk, int32_t *scr_nxt, int32_t *scr_prv,
-                                  int num_sms, cudaStream_t st);
+/* scratch: JTK_LONG_SCRATCH_ARRAYS int32 arrays of `stride` elements each (stride >= total bytes of the long pieces); the first array holds the tokens afterwards */
+#define JTK_LONG_SCRATCH_ARRAYS 8
+cudaError_t jtk_launch_long_merge(const jtk_encode_args &a, unsigned int n_long, int32_t *scratch, int64_t stride, int num_sms, cudaStream_t st);
 /* list: device copy sorted by start with scratch offsets filled; cum[i] = tokens of long pieces 0..i-1 (n_long + 1 entries) */
 cudaError_t jtk_launch_long_insert(const jtk_long_piece *list, const int64_t *cum, unsigned int n_long, const int32_t *scr_tok, const int32_t *ids_in,
                                    int32_t *ids_out, int64_t total_in, cudaStream_t st);

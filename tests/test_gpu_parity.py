@@ -118,3 +118,50 @@ def test_golden_max_tokens(name, gpu_encodings):
         assert r.get_tokens() == ten, inp
         assert r.is_truncated() == (len(full) > len(ten)), inp
         assert inp.startswith(enc.decode(r.get_tokens()))
+
+
+def test_long_piece_rounds_fuzz_custom_vocabularies():
+    """The long-piece kernel merges many pairs per round (every candidate up to a rank window that survives the (rank, position)
+    priority) and checks the created pairs before changing anything.  Small alphabets, random vocabularies - including ones
+    in which a concatenation ranks BELOW its parts, where the reference order differs from any naive parallel order - and
+    pieces of 1.1 - 40 KiB, against the oracle's literal loop."""
+    import random
+    import jtokkit_b200 as jt
+    from oracle import jo
+    rng = random.Random(2024)
+    pat = r"\S+|\s+"
+    for trial in range(10):
+        alphabet = [bytes([c]) for c in b"abcdeXY"[:rng.randint(2, 7)]]
+        vocab = {b" ": 1000}
+        for b in alphabet:
+            vocab[b] = len(vocab)
+        tokens = list(alphabet)
+        for _ in range(rng.randint(3, 60)):
+            a, b = rng.choice(tokens), rng.choice(tokens)
+            if len(a + b) <= 12 and a + b not in vocab:
+                vocab[a + b] = len(vocab)
+                tokens.append(a + b)
+        ranks = dict(vocab)
+        if trial % 2 == 1:  # shuffle the ranks: no longer a valid merge order (longer tokens may rank below their parts)
+            keys = [k for k in ranks if k != b" "]
+            ids = [ranks[k] for k in keys]
+            rng.shuffle(ids)
+            ranks.update(zip(keys, ids))
+        g = jt.EncodingFactory.from_parameters(jt.GptBytePairEncodingParams("long_fuzz_%d" % trial, jt.Pattern.compile(pat), ranks, {}))
+        o = jo.OracleEncoding("long_fuzz_%d" % trial, pat, 0, ranks, {})
+        docs = []
+        for _ in range(6):
+            n = rng.choice([1100, 2500, 9000, 40000])
+            mode = rng.random()
+            if mode < 0.4:
+                s = b"".join(rng.choice(alphabet) for _ in range(n))
+            elif mode < 0.7:
+                unit = b"".join(rng.choice(alphabet) for _ in range(rng.randint(1, 5)))
+                s = unit * (n // len(unit))
+            else:
+                s = b"".join(rng.choice(tokens) for _ in range(n // 3))
+            docs.append(s + b" " + s[: n // 3])
+        res = g.encode_ordinary_batch([d.decode() for d in docs])
+        assert not res.doc_status.any()
+        for d, ids in zip(docs, res.to_lists()):
+            assert ids == o.encode_ordinary(d, jo.MERGE_LITERAL if len(d) < 12000 else jo.MERGE_AUTO), (trial, len(d))

@@ -18,12 +18,12 @@ docs = synth.config5_adversarial(n=1 << 20)
 names = ["a x 2^20", "random [a-z]", "spaces", "'!' x 2^20", "'ab' x 2^19", "random CJK", "newlines", "digits"]
 for name, doc in zip(names, docs):
     blob, o = jt.pack_documents([doc] * 8)
-    t0 = time.perf_counter()
-    res = enc.encode_packed(blob, o, ordinary=True)
-    dt = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    res = enc.encode_packed(blob, o, ordinary=True)
-    dt = time.perf_counter() - t0
+    times = []
+    for _ in range(4):
+        t0 = time.perf_counter()
+        res = enc.encode_packed(blob, o, ordinary=True)
+        times.append(time.perf_counter() - t0)
+    dt = min(times[1:])
     first = res.tokens(0)
     ok = all(res.tokens(i) == first for i in range(1, 8)) and enc.decode_bytes(first) == doc
     print("config 4 %-14s 8 x 1 MiB: %8.1f ms host-to-host, %8d tokens per document, round trip %s" % (name, dt * 1e3, len(first), "ok" if ok else "FAILED"), flush=True)

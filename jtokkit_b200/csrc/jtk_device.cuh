@@ -522,41 +522,31 @@ JTK_HD uint32_t jtk_spread_down(uint32_t seed, uint32_t run) {
 	return f;
 }
 
-JTK_HD bool jtk_boundary_fast(const jtk_tile_ctx &c, int chunk, uint32_t *out) {
-	const int r0 = chunk * 16;
-	const int ws = r0 - 8; /* window start */
-	if (ws < c.rs || c.g0 + r0 + 24 > c.total) return false;
-	{ /* document starts in [ws, ws + 32] */
-		const int wi = ws >> 5, sh = ws & 31;
-		uint32_t d = c.dmask[wi] >> sh;
-		if (sh) d |= c.dmask[wi + 1] << (32 - sh);
-		if (d | (c.dmask[(ws + 32) >> 5] >> ((ws + 32) & 31) & 1u)) return false;
-	}
-	const uint32_t *bw = reinterpret_cast<const uint32_t *>(c.sb + ws);
-	const uint32_t *cw = reinterpret_cast<const uint32_t *>(c.cls + ws);
-	uint32_t P0 = 0, P1 = 0, P2 = 0, P3 = 0, CONT = 0, HB = 0;
-	for (int k = 0; k < 8; k++) {
-		const uint32_t w = cw[k];
-		P0 |= jtk_plane4(w, 0) << (4 * k);
-		P1 |= jtk_plane4(w, 1) << (4 * k);
-		P2 |= jtk_plane4(w, 2) << (4 * k);
-		P3 |= jtk_plane4(w, 3) << (4 * k);
-		CONT |= jtk_plane4(w, 7) << (4 * k);
-		HB |= jtk_plane4(bw[k], 7) << (4 * k);
-	}
+struct jtk_planes {
+	uint32_t P0, P1, P2, P3, CONT, HB; /* bit planes of the class codes, continuation-byte flags and high bits of the 32 window bytes */
+};
+
+/* The split rules as boolean algebra over the window positions in `valid` (a contiguous range of bits): positions outside
+ * `valid` do not exist, exactly as if the text began at the lowest valid position and ended after the highest one.
+ * starts_doc: the lowest valid position is a document start (otherwise the text continues before the window);
+ * top_is_end: the text ends after the highest valid position (otherwise it continues beyond the window).
+ * Returns false when a rule needs context from outside the window (the caller falls back to the per-position rules). */
+JTK_HD bool jtk_boundary_eval(const jtk_tile_ctx &c, int ws, const jtk_planes &pl, uint32_t valid, bool starts_doc, bool top_is_end, uint32_t *Bout) {
+	const uint32_t P0 = pl.P0, P1 = pl.P1, P2 = pl.P2, P3 = pl.P3, CONT = pl.CONT & valid;
 	/* class masks from the four bit planes of the class code (jtk_common.h) */
-	const uint32_t O_ = ~P3 & ~P2 & ~P1;                  /* 0, 1 */
-	const uint32_t AP = O_ & P0;                          /* 1 */
-	const uint32_t SP = ~P3 & ~P2 & P1 & ~P0;             /* 2 */
-	const uint32_t NL = ~P3 & ~P2 & P1 & P0;              /* 3 */
-	const uint32_t WO = ~P3 & P2 & ~P1 & ~P0;             /* 4 */
-	const uint32_t N = ~P3 & P2 & ~P1 & P0;               /* 5 */
-	const uint32_t L = P3 | (P2 & P1);                    /* 6 .. 14 */
-	const uint32_t S1 = (~P3 & P2 & P1 & P0) | (P3 & ~P2 & ~(P1 & P0)); /* 7 .. 10: s t m d */
-	const uint32_t RV = (P3 & ~P2 & P1 & P0) | (P3 & P2 & ~P1 & ~P0);   /* 11, 12: r v */
-	const uint32_t LL = P3 & P2 & ~P1 & P0;               /* 13 */
-	const uint32_t LE = P3 & P2 & P1 & ~P0;               /* 14 */
-	if ((SP | NL | WO | N | S1 | RV | LL | LE) & HB) return false; /* multi-byte whitespace / digit / contraction letter */
+	const uint32_t O_ = ~P3 & ~P2 & ~P1 & valid;                  /* 0, 1 */
+	const uint32_t AP = O_ & P0;                                  /* 1 */
+	const uint32_t SP = ~P3 & ~P2 & P1 & ~P0 & valid;             /* 2 */
+	const uint32_t NL = ~P3 & ~P2 & P1 & P0 & valid;              /* 3 */
+	const uint32_t WO = ~P3 & P2 & ~P1 & ~P0 & valid;             /* 4 */
+	const uint32_t N = ~P3 & P2 & ~P1 & P0 & valid;               /* 5 */
+	const uint32_t L = (P3 | (P2 & P1)) & valid;                  /* 6 .. 14 */
+	const uint32_t S1 = ((~P3 & P2 & P1 & P0) | (P3 & ~P2 & ~(P1 & P0))) & valid; /* 7 .. 10: s t m d */
+	const uint32_t RV = ((P3 & ~P2 & P1 & P0) | (P3 & P2 & ~P1 & ~P0)) & valid;   /* 11, 12: r v */
+	const uint32_t LL = P3 & P2 & ~P1 & P0 & valid;               /* 13 */
+	const uint32_t LE = P3 & P2 & P1 & ~P0 & valid;               /* 14 */
+	if ((SP | NL | WO | N | S1 | RV | LL | LE) & pl.HB) return false; /* multi-byte whitespace / digit / contraction letter */
+	const uint32_t low = starts_doc ? 0u : (valid & 1u); /* window position 0 exists and has text before it */
 	const uint32_t LEAD = ~CONT;
 	const uint32_t Ostart = O_ & LEAD & ~((O_ | SP) << 1);
 	const uint32_t OstartAll = jtk_spread_up(Ostart, CONT & O_); /* ... on every byte of that character */
@@ -567,18 +557,18 @@ JTK_HD bool jtk_boundary_fast(const jtk_tile_ctx &c, int chunk, uint32_t *out) {
 		const uint32_t Wn = SP | WO, W = Wn | NL;
 		const uint32_t BL = L & ((N << 1) | (NL << 1) | ((O_ << 1) & ~(OstartAll << 1)) | CE);
 		const uint32_t BNL = NL & ((L | N) << 1);
-		uint32_t BW = Wn & (~(W << 1) | (~W >> 1));
+		uint32_t BW = Wn & (~(W << 1) | ((~W & valid) >> 1)); /* start of a run, or its last character when a non-whitespace character follows */
 		const uint32_t cand = Wn & (NL << 1) & ~BW & 0xFFFF00u; /* after an NL, followed by whitespace: needs the two run scans */
 		if (cand) {
 			/* does a \r\n come before the whitespace run ends?  unknown when the run leaves the window */
-			const uint32_t hit = jtk_spread_down(NL, Wn), edge = jtk_spread_down(Wn & 0x80000000u, Wn);
+			const uint32_t hit = jtk_spread_down(NL, Wn), edge = top_is_end ? 0u : jtk_spread_down(Wn & 0x80000000u, Wn);
 			const uint32_t nla = hit >> 1;
 			if (cand & (edge >> 1) & ~nla) return false;
 			BW |= cand & ~nla;
 			const uint32_t cand2 = cand & nla;
 			if (cand2) {
 				/* are the NLs before it the tail of an "other" piece?  unknown when the NL run reaches the window start */
-				const uint32_t tail = jtk_spread_up(O_, NL) & NL, open = jtk_spread_up(NL & 1u, NL);
+				const uint32_t tail = jtk_spread_up(O_, NL) & NL, open = jtk_spread_up(NL & low, NL);
 				if (cand2 & (open << 1)) return false;
 				BW |= cand2 & (tail << 1);
 			}
@@ -587,7 +577,7 @@ JTK_HD bool jtk_boundary_fast(const jtk_tile_ctx &c, int chunk, uint32_t *out) {
 		uint32_t BN = 0;
 		if (N & 0xFFFF00u) {
 			uint32_t T0 = N & ~(N << 1);
-			if (N & 1u) { /* the run of window position 0 began earlier: its phase comes from a walk */
+			if (N & low) { /* the run of window position 0 began earlier: its phase comes from a walk */
 				T0 &= ~1u;
 				const int k = jtk_count_n_before(c, ws);
 				const int o = (3 - k) % 3;
@@ -608,10 +598,58 @@ JTK_HD bool jtk_boundary_fast(const jtk_tile_ctx &c, int chunk, uint32_t *out) {
 		const uint32_t CS = APs & ((S1 >> 1) | ((RV >> 1) & (LE >> 2)) | ((LL >> 1) & (LL >> 2)));
 		const uint32_t BL = L & (CE | ~((L | SP | CS) << 1));
 		const uint32_t BN = N & ~((N | SP) << 1);
-		const uint32_t BW = W & (~(W << 1) | (~W >> 1));
+		const uint32_t BW = W & (~(W << 1) | ((~W & valid) >> 1));
 		B = BL | Ostart | BN | BW;
 	}
-	*out = ((B & LEAD) >> 8) & 0xFFFFu;
+	*Bout = B & LEAD & valid;
+	return true;
+}
+
+JTK_HD bool jtk_boundary_fast(const jtk_tile_ctx &c, int chunk, uint32_t *out) {
+	const int r0 = chunk * 16;
+	const int ws = r0 - 8; /* window start */
+	if (ws < c.rs || c.g0 + r0 + 24 > c.total) return false;
+	/* document starts at window positions 0 .. 31 (D) and right after the window (Dtop) */
+	uint32_t D;
+	{
+		const int wi = ws >> 5, sh = ws & 31;
+		D = c.dmask[wi] >> sh;
+		if (sh) D |= c.dmask[wi + 1] << (32 - sh);
+	}
+	const uint32_t Dtop = (c.dmask[(ws + 32) >> 5] >> ((ws + 32) & 31)) & 1u;
+	const uint32_t *bw = reinterpret_cast<const uint32_t *>(c.sb + ws);
+	const uint32_t *cw = reinterpret_cast<const uint32_t *>(c.cls + ws);
+	jtk_planes pl = {0, 0, 0, 0, 0, 0};
+	for (int k = 0; k < 8; k++) {
+		const uint32_t w = cw[k];
+		pl.P0 |= jtk_plane4(w, 0) << (4 * k);
+		pl.P1 |= jtk_plane4(w, 1) << (4 * k);
+		pl.P2 |= jtk_plane4(w, 2) << (4 * k);
+		pl.P3 |= jtk_plane4(w, 3) << (4 * k);
+		pl.CONT |= jtk_plane4(w, 7) << (4 * k);
+		pl.HB |= jtk_plane4(bw[k], 7) << (4 * k);
+	}
+	uint32_t B;
+	if ((D | Dtop) == 0) {
+		if (!jtk_boundary_eval(c, ws, pl, 0xFFFFFFFFu, false, false, &B)) return false;
+	} else {
+		/* one document start in or right after the window: the rules are evaluated once for the text that ends before it and once
+		 * for the text that starts at it (short documents otherwise send every eighth chunk through the per-position rules) */
+		if ((D & (D - 1)) || (D && Dtop)) return false;
+		const int d = D ? jtk_ctz(D) : 32;
+		B = 0;
+		if (d > 0) {
+			uint32_t Bl;
+			if (!jtk_boundary_eval(c, ws, pl, d >= 32 ? 0xFFFFFFFFu : ((1u << d) - 1u), false, true, &Bl)) return false;
+			B |= Bl;
+		}
+		if (d < 32) {
+			uint32_t Br;
+			if (!jtk_boundary_eval(c, ws, pl, ~((1u << d) - 1u), true, false, &Br)) return false;
+			B |= Br | (1u << d);
+		}
+	}
+	*out = (B >> 8) & 0xFFFFu;
 	return true;
 }
 

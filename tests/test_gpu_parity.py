@@ -1,4 +1,5 @@
 """First GPU parity tests: golden vectors, fuzz against the oracle, split flags, tile edges, long pieces."""
+import os
 import random
 
 import numpy as np
@@ -130,7 +131,7 @@ def test_long_piece_rounds_fuzz_custom_vocabularies():
     from oracle import jo
     rng = random.Random(2024)
     pat = r"\S+|\s+"
-    for trial in range(10):
+    for trial in range(int(os.environ.get("JTK_TEST_TRIALS", "10"))):
         alphabet = [bytes([c]) for c in b"abcdeXY"[:rng.randint(2, 7)]]
         vocab = {b" ": 1000}
         for b in alphabet:

@@ -81,6 +81,7 @@ int jtk_encoding_create(const jtk_params *params, const int *devices, int ndev, 
  * file in the reference's resource format ("<base64> <rank>\n"). */
 int jtk_encoding_create_builtin(const char *name, const char *tiktoken_path, const int *devices, int ndev, jtk_encoding **out);
 
+/* Every jtk_result of the encoding must have been freed before (a result's pinned buffers return to the encoding's pool). */
 void jtk_encoding_destroy(jtk_encoding *enc);
 const char *jtk_encoding_name(const jtk_encoding *enc); /* Encoding.getName(), api/Encoding.java:189 */
 int jtk_encoding_num_devices(const jtk_encoding *enc);

@@ -176,6 +176,39 @@ class GptBytePairEncodingParams:
 
 
 # ----------------------------------------------------------------------------- batch result
+class _ResultOwner:
+    """Owns a C jtk_result: its pinned buffers go back to the library's pool when the last array viewing them is gone
+    (or earlier, on BatchResult.close())."""
+
+    def __init__(self, handle, encoding):
+        self.handle = handle
+        self.encoding = encoding  # the result's buffers go back to the encoding's pool: keep it alive until then
+
+    def free(self):
+        if self.handle is not None:
+            h, self.handle = self.handle, None
+            _capi.lib().jtk_result_free(h)
+            self.encoding = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class _PinnedView:
+    """Array-interface window onto one buffer of a jtk_result; numpy keeps it (and through it the owner) as the array's base."""
+
+    def __init__(self, owner, ptr, n, typestr):
+        self.owner = owner
+        self.__array_interface__ = {"data": (ptr or 0, False), "shape": (n,), "typestr": typestr, "version": 3}
+
+
+def _view(owner, ptr, n, typestr, dtype):
+    return np.asarray(_PinnedView(owner, ptr, n, typestr)) if n and ptr else np.zeros(0, dtype=dtype)
+
+
 class BatchResult:
     """Result of Encoding.encode_batch: primitive arrays, no boxing (ids int32, token offsets int64, per-document status)."""
 
@@ -185,20 +218,15 @@ class BatchResult:
         self.doc_status = doc_status
         self.device_ms = device_ms
         self.gpu_launches = gpu_launches
-        self._handle = None  # C result kept alive for zero-copy views (encode_packed(copy=False))
+        self._owner = None  # zero-copy results: the C result the arrays are views of
 
     def close(self):
-        """Returns the pinned result buffers to the library (only needed for copy=False results)."""
-        if self._handle is not None:
-            h, self._handle = self._handle, None
+        """Returns the pinned result buffers to the library right away (zero-copy results only; the arrays must not be used
+        afterwards).  Without it they go back when the last array viewing them is garbage collected."""
+        if self._owner is not None:
+            o, self._owner = self._owner, None
             self.ids = self.token_offsets = self.doc_status = None
-            _capi.lib().jtk_result_free(h)
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
+            o.free()
 
     def __len__(self):
         return self.token_offsets.size - 1
@@ -285,9 +313,12 @@ class Encoding:
         blob, off = pack_documents(texts)
         return self.encode_packed(blob, off, ordinary=ordinary, count_only=count_only)
 
-    def encode_packed(self, utf8, doc_off, ordinary=False, count_only=False, copy=True, with_special_tokens=False):
+    def encode_packed(self, utf8, doc_off, ordinary=False, count_only=False, copy=False, with_special_tokens=False):
         """HOST arrays in, HOST arrays out; host<->device copies happen inside the C call.
-        copy=False returns views into the library's pinned result buffers (valid until BatchResult.close()).
+        The result arrays are views into the library's pinned result buffers (no copy: copying 400 MB of ids costs more than
+        encoding them); the buffers return to the library's pool when the arrays are garbage collected or on
+        BatchResult.close().  copy=True returns independent numpy arrays instead.  Pass pinned input (torch pin_memory,
+        jtk_host_alloc) for full PCIe speed: pageable memory is copied in at ~8 GB/s by the driver.
         with_special_tokens: special tokens in the text become their ids (jtk_encode_batch_special; not in the reference)."""
         utf8 = np.ascontiguousarray(utf8, dtype=np.uint8)
         doc_off = np.ascontiguousarray(doc_off, dtype=np.int64)
@@ -297,18 +328,18 @@ class Encoding:
         _capi.check(call(self._h, _ptr(utf8), _ptr(doc_off), doc_off.size - 1, flags, C.byref(r)))
         L = _capi.lib()
         nd, nt = L.jtk_result_num_docs(r), L.jtk_result_num_tokens(r)
-        ids = None
-        if not count_only:
-            ids = np.ctypeslib.as_array(C.cast(L.jtk_result_ids(r), C.POINTER(C.c_int32)), shape=(max(nt, 1),))[:nt]
-        tok_off = np.ctypeslib.as_array(C.cast(L.jtk_result_token_offsets(r), C.POINTER(C.c_int64)), shape=(nd + 1,))
-        status = np.ctypeslib.as_array(C.cast(L.jtk_result_doc_status(r), C.POINTER(C.c_int32)), shape=(max(nd, 1),))[:nd]
+        owner = _ResultOwner(r, self)
+        ids = None if count_only else _view(owner, L.jtk_result_ids(r), nt, "<i4", np.int32)
+        tok_off = _view(owner, L.jtk_result_token_offsets(r), nd + 1, "<i8", np.int64)
+        status = _view(owner, L.jtk_result_doc_status(r), nd, "<i4", np.int32)
         res = BatchResult(ids, tok_off, status, L.jtk_result_device_ms(r), L.jtk_result_gpu_launches(r))
         if copy:
             res.ids = None if ids is None else ids.copy()
             res.token_offsets, res.doc_status = tok_off.copy(), status.copy()
-            L.jtk_result_free(r)
+            del ids, tok_off, status
+            owner.free()
         else:
-            res._handle = r
+            res._owner = owner
         return res
 
     def encode_device(self, d_utf8, d_doc_off, d_ids, d_tok_off, d_status, ordinary=False, count_only=False, time_kernel=False, device=None):

@@ -1,0 +1,25 @@
+#!/usr/bin/env python3
+"""Throughput of the general split-pattern path (one thread per document runs the backtracking program) next to the
+rule-based path of the predefined pattern, same vocabulary and text (development probe)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import jtokkit_b200 as jt
+from jtokkit_b200 import synth
+
+p = jt.EncodingFactory.predefined_params(jt.EncodingType.CL100K_BASE)
+size = (int(sys.argv[1]) if len(sys.argv) > 1 else 64) << 20
+data, off = synth.config3_multilingual(torch.device("cpu"), total=size, seed=11)
+d, o = data.numpy(), off.numpy()
+variants = [("predefined cl100k pattern (class tables + bit-parallel rules)", p.get_pattern().pattern(), 0x100),
+            ("same pattern with CASE_INSENSITIVE (general program)", p.get_pattern().pattern(), 0x102),
+            (r"general: \w+|\s+|[^\w\s]+", r"\w+|\s+|[^\w\s]+", 0)]
+base = None
+for label, pat, flags in variants:
+    enc = jt.EncodingFactory.from_parameters(jt.GptBytePairEncodingParams("probe", jt.Pattern.compile(pat, flags), p.encoder, p.special_tokens_encoder))
+    enc.encode_packed(d, o, ordinary=True)
+    t0 = time.perf_counter()
+    res = enc.encode_packed(d, o, ordinary=True)
+    dt = time.perf_counter() - t0
+    print("%-70s %6.1f ms host-to-host for %d MiB / %d documents (%.2f GB/s), %d tokens, flagged documents %d" %
+          (label, dt * 1e3, size >> 20, o.size - 1, d.size / dt / 1e9, res.ids.size, int((res.doc_status != 0).sum())), flush=True)

@@ -75,7 +75,9 @@ enum {
 #define JTK_FWD_HALO (JTK_LONG_PIECE + 16) /* a piece starting in the tile ends inside the halo or is long */
 #define JTK_REGION (JTK_BACK_HALO + JTK_TILE + JTK_FWD_HALO)
 #define JTK_REGION_CHUNKS (JTK_REGION / 16)
+#ifndef JTK_SHORT_PIECE
 #define JTK_SHORT_PIECE 64  /* thread-per-piece merge up to this length, lane groups above */
+#endif
 
 /* 16-byte table slots */
 struct jtk_slot {

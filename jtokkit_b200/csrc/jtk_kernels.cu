@@ -554,8 +554,8 @@ __global__ void jtk_short_offsets_kernel(const jtk_encode_args a) {
 	}
 	a.sub->short_base[JTK_SHORT_PIECE + 1] = run;
 	a.sub->short_next[0] = 0;
-	a.sub->short_next[1] = a.sub->short_base[17];
-	a.sub->short_next[2] = a.sub->short_base[33];
+	a.sub->short_next[1] = a.sub->short_base[JTK_SHORT_PIECE < 17 ? JTK_SHORT_PIECE + 1 : 17];
+	a.sub->short_next[2] = a.sub->short_base[JTK_SHORT_PIECE < 33 ? JTK_SHORT_PIECE + 1 : 33];
 }
 
 constexpr int SNT = 128;
@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(NTHREADS, NTHREADS >= 256 ? 4 : 7) jtk_merge_s
 	const jtk_tables &T = a.T;
 	const int tid = threadIdx.x, lane = tid & 31;
 	const bool write_tok = !(a.flags & JTK_COUNT_ONLY);
-	const unsigned end = a.sub->short_base[NSLOT + 1];
+	const unsigned end = a.sub->short_base[(NSLOT < JTK_SHORT_PIECE ? NSLOT : JTK_SHORT_PIECE) + 1];
 	unsigned *cursor = &a.sub->short_next[NSLOT == 16 ? 0 : NSLOT == 32 ? 1 : 2];
 	int32_t *tk = s_scr + tid, *rk = s_scr + NSLOT * NTHREADS + tid;
 	for (;;) {

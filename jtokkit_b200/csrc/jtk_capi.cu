@@ -42,6 +42,8 @@ struct jtk_workspace {
 	/* general split patterns: start + gap bit arrays (2 * rx_words_cap words) and the backtrack stacks */
 	uint32_t *rx_bits = nullptr;
 	int64_t rx_words_cap = 0;
+	int64_t *rx_rec = nullptr; /* per-slice / per-document records of the sliced matcher */
+	int64_t rx_rec_cap = 0;
 	void *rx_stacks = nullptr;
 	/* side streams for the merge kernels (JTK_SIDE_STREAMS=0 keeps everything on one stream) */
 	jtk_side_streams side;
@@ -342,6 +344,7 @@ static void free_workspace(jtk_workspace *w) {
 	cudaFree(w->tile_first_b);
 	cudaFree(w->long_list);
 	cudaFree(w->rx_bits);
+	cudaFree(w->rx_rec);
 	cudaFree(w->rx_stacks);
 	cudaFree(w->hdr);
 	cudaFreeHost(w->hdr_host);
@@ -683,21 +686,32 @@ static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspa
 	if (ds->T.pattern_kind == JTK_PAT_GENERAL && ntiles > 0) {
 		/* general pattern: piece / gap bits per document first (jtk_general_split_kernel), the tile kernels read them */
 		const int64_t words = (ntiles * (int64_t) JTK_TILE + JTK_REGION) / 32 + 2;
+		const int64_t slices = (nbytes + JTK_RX_SLICE - 1) / JTK_RX_SLICE, recs = 4 * slices + ndocs + 1;
 		if (words > w->rx_words_cap) {
 			cudaFree(w->rx_bits);
 			w->rx_bits = nullptr;
 			w->rx_words_cap = 0;
-			CUDA_TRY(cudaMalloc(&w->rx_bits, sizeof(uint32_t) * 2 * (size_t) (words + words / 4)));
+			CUDA_TRY(cudaMalloc(&w->rx_bits, sizeof(uint32_t) * 5 * (size_t) (words + words / 4)));
 			w->rx_words_cap = words + words / 4;
 		}
+		if (recs > w->rx_rec_cap) {
+			cudaFree(w->rx_rec);
+			w->rx_rec = nullptr;
+			w->rx_rec_cap = 0;
+			CUDA_TRY(cudaMalloc(&w->rx_rec, sizeof(int64_t) * (size_t) (recs + recs / 4)));
+			w->rx_rec_cap = recs + recs / 4;
+		}
 		if (!w->rx_stacks) CUDA_TRY(cudaMalloc(&w->rx_stacks, sizeof(jtk_rx_frame) * (size_t) JTK_RX_STACK * JTK_RX_THREADS));
-		CUDA_TRY(cudaMemsetAsync(w->rx_bits, 0, sizeof(uint32_t) * 2 * (size_t) words, st));
+		CUDA_TRY(cudaMemsetAsync(w->rx_bits, 0, sizeof(uint32_t) * 5 * (size_t) words, st));
 		a.rx_start = w->rx_bits;
 		a.rx_skip = w->rx_bits + words;
+		a.rx_spec = w->rx_bits + 2 * words;
 		a.rx_words = words;
+		a.rx_rec = w->rx_rec;
+		a.rx_slices = slices;
 		a.rx_stacks = w->rx_stacks;
 		CUDA_TRY(jtk_launch_general_split(a, st));
-		general_launches = 1;
+		general_launches = 3;
 	}
 	const bool time_kernel = (flags & JTK_TIME_KERNEL) && sync_and_long;
 	/* sub-batches: a small first one (16 MiB) so that the piece memo is warm early, then full-size ones */

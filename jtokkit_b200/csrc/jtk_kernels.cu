@@ -516,25 +516,60 @@ __global__ void __launch_bounds__(JTK_NT, 2048 / JTK_NT) jtk_split_lookup_kernel
 }
 
 /* ---------------------------------------------------------------------------------------------
- * kernel 0 (general patterns only): Matcher.find() over every document with the compiled backtracking program
- * (jtk_regex.h).  Regex search is sequential within a document, so the unit of parallelism is the document: a thread
- * takes documents from a ticket counter and ORs their piece / gap bits into the two global bit arrays.
+ * kernels 0 (general patterns only): Matcher.find() over every document with the compiled backtracking program, in the
+ * sliced form described in jtk_regex.h: every 512-byte slice is matched speculatively from its first byte (threads take
+ * slices by ticket), one thread per document then follows the true chain from slice to slice, re-matching only until it
+ * meets the speculative trail, and a last pass turns match start / end bits into piece-start and gap bits.
  * ------------------------------------------------------------------------------------------- */
-__global__ void __launch_bounds__(128) jtk_general_split_kernel(const __grid_constant__ jtk_encode_args a) {
+__device__ __forceinline__ jtk_rx_split_buffers rx_buffers(const jtk_encode_args &a) {
+	jtk_rx_split_buffers B;
+	B.ms = a.rx_start;
+	B.me = a.rx_skip;
+	B.s_ms = a.rx_spec;
+	B.s_me = a.rx_spec + a.rx_words;
+	B.s_from = a.rx_spec + 2 * a.rx_words;
+	B.exit_slice = a.rx_rec;
+	B.last_ms = a.rx_rec + a.rx_slices;
+	B.last_me = a.rx_rec + 2 * a.rx_slices;
+	B.join = a.rx_rec + 3 * a.rx_slices;
+	B.exit_doc = a.rx_rec + 4 * a.rx_slices;
+	B.nwords = a.rx_words;
+	B.nslices = a.rx_slices;
+	return B;
+}
+
+struct rx_atomic_or {
+	__device__ void operator()(uint32_t *w, uint32_t m) const { atomicOr(w, m); }
+};
+
+__global__ void __launch_bounds__(128) jtk_general_slice_kernel(const __grid_constant__ jtk_encode_args a) {
 	const jtk_rx_program P = jtk_rx_program_of(a.T);
-	jtk_rx_frame *st = static_cast<jtk_rx_frame *>(a.rx_stacks) + (size_t) (blockIdx.x * blockDim.x + threadIdx.x) * JTK_RX_STACK;
-	if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(a.rx_start + (a.total >> 5), 1u << (a.total & 31)); /* the end of the input ends the last piece */
+	const jtk_rx_split_buffers B = rx_buffers(a);
+	/* eight times the threads of the per-document pass on the same stack memory: what overflows a small stack is redone there */
+	jtk_rx_frame *st = static_cast<jtk_rx_frame *>(a.rx_stacks) + (size_t) (blockIdx.x * blockDim.x + threadIdx.x) * JTK_RX_STACK_SMALL;
 	for (;;) {
-		const int64_t d = (int64_t) atomicAdd(&a.hdr->rx_ticket, 1u);
-		if (d >= a.ndocs) break;
-		const int64_t lo = a.doc_off[d], n = a.doc_off[d + 1];
-		bool overflow = false;
-		atomicOr(a.rx_start + (lo >> 5), 1u << (lo & 31));
-		jtk_rx_split_document(
-		    P, a.T, a.bytes, lo, n, st, JTK_RX_STACK, [&](int64_t g) { atomicOr(a.rx_start + (g >> 5), 1u << (g & 31)); },
-		    [&](int64_t g) { atomicOr(a.rx_skip + (g >> 5), 1u << (g & 31)); }, &overflow);
-		if (overflow && a.doc_status) atomicOr(a.doc_status + d, JTK_DOC_PATTERN_STACK);
+		const int64_t slice = (int64_t) atomicAdd(&a.hdr->rx_ticket, 1u);
+		if (slice >= a.rx_slices) break;
+		int64_t bad = -1;
+		jtk_rx_slice_pass(P, a.T, a.bytes, a.total, a.doc_off, a.ndocs, slice, B, st, JTK_RX_STACK_SMALL, &bad, rx_atomic_or());
 	}
+}
+
+__global__ void __launch_bounds__(128) jtk_general_stitch_kernel(const __grid_constant__ jtk_encode_args a) {
+	const jtk_rx_program P = jtk_rx_program_of(a.T);
+	const jtk_rx_split_buffers B = rx_buffers(a);
+	jtk_rx_frame *st = static_cast<jtk_rx_frame *>(a.rx_stacks) + (size_t) (blockIdx.x * blockDim.x + threadIdx.x) * JTK_RX_STACK;
+	for (;;) {
+		const int64_t d = (int64_t) atomicAdd(&a.hdr->rx_ticket2, 1u);
+		if (d >= a.ndocs) break;
+		if (a.doc_off[d + 1] == a.doc_off[d]) continue;
+		if (!jtk_rx_stitch_doc(P, a.T, a.bytes, a.total, a.doc_off, d, B, st, JTK_RX_STACK, rx_atomic_or()) && a.doc_status) atomicOr(a.doc_status + d, JTK_DOC_PATTERN_STACK);
+	}
+}
+
+__global__ void jtk_general_finish_kernel(const jtk_encode_args a) {
+	const jtk_rx_split_buffers B = rx_buffers(a);
+	for (int64_t w = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; w < a.rx_words; w += (int64_t) gridDim.x * blockDim.x) jtk_rx_finish_word(B, w, a.total);
 }
 
 /* ---------------------------------------------------------------------------------------------
@@ -1409,10 +1444,17 @@ cudaError_t jtk_launch_post(const jtk_encode_args &a, int num_sms, cudaStream_t 
 }
 
 cudaError_t jtk_launch_general_split(const jtk_encode_args &a, cudaStream_t st) {
-	int64_t blocks = (a.ndocs + 127) / 128;
+	int64_t blocks = (a.rx_slices + 127) / 128;
+	if (blocks > JTK_RX_THREADS / 128 * (JTK_RX_STACK / JTK_RX_STACK_SMALL)) blocks = JTK_RX_THREADS / 128 * (JTK_RX_STACK / JTK_RX_STACK_SMALL);
+	if (blocks < 1) blocks = 1;
+	jtk_general_slice_kernel<<<(unsigned) blocks, 128, 0, st>>>(a);
+	blocks = (a.ndocs + 127) / 128;
 	if (blocks > JTK_RX_THREADS / 128) blocks = JTK_RX_THREADS / 128;
 	if (blocks < 1) blocks = 1;
-	jtk_general_split_kernel<<<(unsigned) blocks, 128, 0, st>>>(a);
+	jtk_general_stitch_kernel<<<(unsigned) blocks, 128, 0, st>>>(a);
+	blocks = (a.rx_words + 255) / 256;
+	if (blocks > 148 * 16) blocks = 148 * 16;
+	jtk_general_finish_kernel<<<(unsigned) blocks, 256, 0, st>>>(a);
 	return cudaGetLastError();
 }
 

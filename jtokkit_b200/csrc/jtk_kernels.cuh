@@ -27,8 +27,8 @@ struct jtk_batch_header {
 	unsigned int overflow;   /* ids capacity exceeded */
 	unsigned int long_next;  /* work counter of the long-piece kernel */
 	unsigned int violations; /* long-piece rounds that had to fall back to one-merge-at-a-time */
-	unsigned int rx_ticket;  /* document counter of jtk_general_split_kernel */
-	unsigned int pad;
+	unsigned int rx_ticket;  /* slice counter of jtk_general_slice_kernel */
+	unsigned int rx_ticket2; /* document counter of jtk_general_stitch_kernel */
 };
 
 /* Counters of one sub-batch.  Two sub-batches are in flight at a time (the split+lookup kernel of one runs while the merge /
@@ -93,6 +93,9 @@ struct jtk_encode_args {
 	uint32_t *rx_start, *rx_skip;
 	int64_t rx_words;
 	void *rx_stacks;       /* JTK_RX_THREADS backtrack stacks of JTK_RX_STACK frames */
+	uint32_t *rx_spec;     /* three more bit arrays of rx_words words: speculative match starts / ends / resume positions per slice */
+	int64_t *rx_rec;       /* 4 * rx_slices + ndocs + 1 int64: per-slice exit / crossing match / join position, per-document exit */
+	int64_t rx_slices;
 	/* host side only: L2 access-policy window over the hot tables (0 bytes = none) */
 	const void *l2_base;
 	size_t l2_bytes;
@@ -112,7 +115,8 @@ struct jtk_side_streams {
 cudaError_t jtk_launch_split(const jtk_encode_args &a, int num_sms, int ctas_per_sm, cudaEvent_t k0, cudaEvent_t k1, cudaStream_t st);
 cudaError_t jtk_launch_post(const jtk_encode_args &a, int num_sms, cudaStream_t st, const jtk_side_streams *side);
 cudaError_t jtk_launch_finalize(const jtk_encode_args &a, cudaStream_t st);
-/* JTK_PAT_GENERAL: runs the split program over every document (one thread per document) before the sub-batches; rx_start / rx_skip must be zeroed */
+/* JTK_PAT_GENERAL: Matcher.find() over every document before the sub-batches, in three passes (speculative per slice, stitch per
+ * document, finish per word: jtk_regex.h); rx_start / rx_skip / rx_spec must be zeroed */
 #define JTK_RX_THREADS (148 * 128)
 cudaError_t jtk_launch_general_split(const jtk_encode_args &a, cudaStream_t st);
 cudaError_t jtk_encode_kernel_setup();

@@ -51,7 +51,8 @@ struct jtk_rx_set {
 #define JTK_RX_HAS_NOT_N 32u
 #define JTK_RX_HAS_NOT_S 64u
 #define JTK_RX_DOT 128u
-#define JTK_RX_STACK 1024 /* backtrack frames per thread on the device (global memory, 16 KiB); a document that needs more is flagged JTK_DOC_PATTERN_STACK */
+#define JTK_RX_STACK 1024 /* backtrack frames per thread of the per-document pass (global memory, 16 KiB); a document that needs more is flagged JTK_DOC_PATTERN_STACK */
+#define JTK_RX_STACK_SMALL 128 /* frames per thread of the per-slice pass (eight times as many threads share the same memory); what overflows here is redone by the per-document pass */
 
 struct jtk_rx_program {
 	const jtk_rx_inst *inst;
@@ -332,31 +333,202 @@ JTK_HD void jtk_rx_find_all(const jtk_rx_program &P, const jtk_tables &T, const 
 	}
 }
 
-/* One document -> piece bits.  set_start(g) marks a piece start at global byte g, set_skip(g) marks the piece that starts
- * at g as a gap (text no alternative matched: Matcher.find() skips it, it produces no tokens).  Empty matches produce
- * nothing either (bytePairMerge of an empty piece is an empty list, GptBytePairEncoding.java:205-209; a vocabulary with
- * an empty key is rejected at registration when the pattern can match the empty string). */
-template <typename SetStart, typename SetSkip>
-JTK_HD void jtk_rx_split_document(const jtk_rx_program &P, const jtk_tables &T, const uint8_t *s, int64_t lo, int64_t n, jtk_rx_frame *st, int cap, SetStart set_start,
-                                  SetSkip set_skip, bool *overflow) {
-	int64_t prev_end = lo;
-	jtk_rx_find_all(
-	    P, T, s, lo, n, st, cap,
-	    [&](int64_t ms, int64_t me) {
-		    if (me == ms) return;
-		    if (ms > prev_end) {
-			    set_start(prev_end);
-			    set_skip(prev_end);
-		    }
-		    set_start(ms);
-		    prev_end = me;
-	    },
-	    overflow);
-	if (*overflow) return;
-	if (prev_end < n) {
-		set_start(prev_end);
-		set_skip(prev_end);
+/* ---------------------------------------------------------------------------------------------
+ * Parallel form of Matcher.find() over long documents.
+ *
+ * What find() does next depends only on the position `from` at which it resumes (the end of the previous match, one
+ * character further after an empty match): two runs that reach the same `from` are identical from there on.  So the byte
+ * array is cut into slices of JTK_RX_SLICE bytes and every slice is matched SPECULATIVELY from its first byte, recording
+ * the `from` positions it passes.  A cheap sequential pass per document then follows the true chain from the document
+ * start: inside a slice it re-matches only until it lands on a position the speculative run has passed too, accepts the
+ * rest of that slice's result and jumps to the slice's exit.  Runs started inside a piece re-align with the true sequence
+ * within a few matches (the next whitespace, typically), so almost all matching happens in the parallel pass.
+ *
+ * Bits: ms / me = starts / ends of non-empty matches.  A document start counts as a match end.  Piece starts are then
+ * ms | me, and a piece that starts at an end without a start is a gap (text no alternative matched: no tokens).
+ * Empty matches produce nothing (bytePairMerge of an empty piece is an empty list, GptBytePairEncoding.java:205-209; a
+ * vocabulary with an empty key is rejected at registration when the pattern can match the empty string).
+ * ------------------------------------------------------------------------------------------- */
+#ifndef JTK_RX_SLICE
+#define JTK_RX_SLICE 512
+#endif
+#define JTK_RX_SPEC_LIMIT (8 * JTK_RX_SLICE) /* a speculative search that finds nothing this far beyond its slice gives up */
+#define JTK_RX_NO_EXIT (-2)                  /* slice record: the speculative run gave up */
+
+struct jtk_rx_split_buffers {
+	uint32_t *ms, *me;             /* final bits (after jtk_rx_finish_word: piece starts / gap flags) */
+	uint32_t *s_ms, *s_me, *s_from; /* speculative bits per slice */
+	int64_t *exit_slice;           /* `from` with which the speculative run left the slice (>= slice end), or JTK_RX_NO_EXIT */
+	int64_t *last_ms, *last_me;    /* the match that crosses the slice end (its bits lie outside the slice), or -1 */
+	int64_t *join;                 /* first position of the slice from which the speculative bits are valid (none: >= slice end) */
+	int64_t *exit_doc;             /* per document: `from` with which the run from the document start left its first slice */
+	int64_t nwords, nslices;
+};
+
+enum { JTK_RX_FOUND = 0, JTK_RX_NONE = 1, JTK_RX_GAVE_UP = 2 };
+
+/* next match at or after `from` (search positions beyond `limit` are not tried) */
+JTK_HD int jtk_rx_find_next(const jtk_rx_program &P, const jtk_tables &T, const uint8_t *s, int64_t lo, int64_t n, int64_t from, int64_t limit, int64_t *ms, int64_t *me,
+                            jtk_rx_frame *st, int cap, bool *overflow) {
+	for (int64_t stp = from; stp <= n;) {
+		if (stp > limit) return JTK_RX_GAVE_UP;
+		const int64_t r = jtk_rx_run<0>(P, T, s, lo, n, stp, 0, st, cap, overflow);
+		if (*overflow) return JTK_RX_NONE;
+		if (r >= 0) {
+			*ms = stp;
+			*me = r;
+			return JTK_RX_FOUND;
+		}
+		if (stp >= n) break;
+		int len;
+		jtk_rx_decode(s, stp, n, &len);
+		stp += len;
 	}
+	return JTK_RX_NONE;
+}
+
+JTK_HD bool jtk_rx_bit(const uint32_t *b, int64_t g) { return (b[g >> 5] >> (g & 31)) & 1u; }
+
+/* Follows the chain from `from` inside the document [lo, hi) until it leaves [.., end_run).  Match bits go to ms / me through
+ * `bor` (matches that end inside the run only; the one that crosses end_run is returned in *cross_ms / *cross_me).  from_bits
+ * (nullable): every `from` passed is recorded.  stop_bits (nullable): the run stops as soon as it lands on a recorded `from`
+ * of another run and returns it with *joined = true.  Returns the `from` at which it stopped (>= end_run, hi when nothing
+ * matches any more) or JTK_RX_NO_EXIT when a search gave up (limit >= 0: bytes a search may go beyond end_run).  On a
+ * backtrack-stack overflow *overflow is set and the `from` whose search overflowed is returned (everything before it is done). */
+template <typename Or>
+JTK_HD int64_t jtk_rx_chain(const jtk_rx_program &P, const jtk_tables &T, const uint8_t *s, int64_t lo, int64_t hi, int64_t from, int64_t end_run, int64_t limit,
+                            uint32_t *ms_bits, uint32_t *me_bits, uint32_t *from_bits, const uint32_t *stop_bits, int64_t *cross_ms, int64_t *cross_me, bool *joined,
+                            jtk_rx_frame *st, int cap, bool *overflow, Or bor) {
+	*cross_ms = *cross_me = -1;
+	*joined = false;
+	bool first = true;
+	while (from < end_run) {
+		if (stop_bits && !first && jtk_rx_bit(stop_bits, from)) {
+			*joined = true;
+			return from;
+		}
+		first = false;
+		if (from_bits) bor(from_bits + (from >> 5), 1u << (from & 31));
+		int64_t ms, me;
+		const int r = jtk_rx_find_next(P, T, s, lo, hi, from, limit < 0 ? hi : end_run + limit, &ms, &me, st, cap, overflow);
+		if (*overflow) return from;
+		if (r == JTK_RX_GAVE_UP) return JTK_RX_NO_EXIT;
+		if (r == JTK_RX_NONE) return hi;
+		if (me > ms) {
+			if (me >= end_run) { /* its end bit lies outside this run's range: the caller places it */
+				*cross_ms = ms;
+				*cross_me = me;
+				return me;
+			}
+			bor(ms_bits + (ms >> 5), 1u << (ms & 31));
+			bor(me_bits + (me >> 5), 1u << (me & 31));
+			from = me;
+		} else { /* empty match: nothing to emit, the search moves on by one character */
+			if (ms >= hi) return hi;
+			int len;
+			jtk_rx_decode(s, ms, hi, &len);
+			from = ms + len;
+		}
+	}
+	return from;
+}
+
+/* Pass 1, one call per slice: the speculative run from the slice start (when the slice starts inside a document) and the true
+ * runs of the documents that start inside the slice.  A run that overflows the (small) backtrack stack is left to pass 2. */
+template <typename Or>
+JTK_HD bool jtk_rx_slice_pass(const jtk_rx_program &P, const jtk_tables &T, const uint8_t *s, int64_t total, const int64_t *doc_off, int64_t ndocs, int64_t slice,
+                              const jtk_rx_split_buffers &B, jtk_rx_frame *st, int cap, int64_t *bad_doc, Or bor) {
+	const int64_t s0 = slice * JTK_RX_SLICE, s1 = s0 + JTK_RX_SLICE < total ? s0 + JTK_RX_SLICE : total;
+	/* d = last document that starts at or before s0 */
+	int64_t a = 0, b = ndocs - 1;
+	while (a < b) {
+		const int64_t mid = (a + b + 1) >> 1;
+		if (doc_off[mid] <= s0) a = mid;
+		else b = mid - 1;
+	}
+	int64_t d = a;
+	bool overflow = false, joined;
+	int64_t cms, cme;
+	B.exit_slice[slice] = JTK_RX_NO_EXIT;
+	B.last_ms[slice] = B.last_me[slice] = -1;
+	B.join[slice] = s1;
+	if (ndocs > 0 && doc_off[d] < s0 && doc_off[d + 1] > s0) { /* the slice starts inside document d */
+		const int64_t lo = doc_off[d], hi = doc_off[d + 1], end_run = hi < s1 ? hi : s1;
+		const int64_t e = jtk_rx_chain(P, T, s, lo, hi, s0, end_run, JTK_RX_SPEC_LIMIT, B.s_ms, B.s_me, B.s_from, nullptr, &cms, &cme, &joined, st, cap, &overflow, bor);
+		if (overflow) { /* only the true chain may condemn a document: this slice is simply matched again by pass 2 */
+			overflow = false;
+		} else {
+			B.exit_slice[slice] = e;
+			B.last_ms[slice] = cms;
+			B.last_me[slice] = cme;
+		}
+	}
+	/* documents that start inside the slice: the true chain from their start (a document start counts as a match end) */
+	while (d < ndocs && doc_off[d] < s0) d++;
+	for (; d < ndocs && doc_off[d] < s1; d++) {
+		const int64_t lo = doc_off[d], hi = doc_off[d + 1], end_run = hi < s1 ? hi : s1;
+		bor(B.me + (lo >> 5), 1u << (lo & 31));
+		const int64_t e = jtk_rx_chain(P, T, s, lo, hi, lo, end_run, -1, B.ms, B.me, nullptr, nullptr, &cms, &cme, &joined, st, cap, &overflow, bor);
+		overflow = false; /* (small stack) pass 2 resumes at e with the large one: everything before e is done */
+		if (cms >= 0) {
+			bor(B.ms + (cms >> 5), 1u << (cms & 31));
+			bor(B.me + (cme >> 5), 1u << (cme & 31));
+		}
+		B.exit_doc[d] = e;
+	}
+	return true;
+}
+
+/* Pass 2, one call per document: follows the true chain through the slices after the document's first one. */
+template <typename Or>
+JTK_HD bool jtk_rx_stitch_doc(const jtk_rx_program &P, const jtk_tables &T, const uint8_t *s, int64_t total, const int64_t *doc_off, int64_t d,
+                              const jtk_rx_split_buffers &B, jtk_rx_frame *st, int cap, Or bor) {
+	const int64_t lo = doc_off[d], hi = doc_off[d + 1];
+	int64_t cur = B.exit_doc[d];
+	bool overflow = false, joined;
+	int64_t cms, cme;
+	while (cur < hi) {
+		const int64_t slice = cur / JTK_RX_SLICE, s0 = slice * JTK_RX_SLICE, s1 = s0 + JTK_RX_SLICE < total ? s0 + JTK_RX_SLICE : total;
+		const int64_t end_run = hi < s1 ? hi : s1;
+		const bool usable = B.exit_slice[slice] != JTK_RX_NO_EXIT && s0 > lo; /* the slice's speculative run belongs to this document and completed */
+		if (!(usable && jtk_rx_bit(B.s_from, cur))) {
+			/* match from the true position until the speculative run's trail is hit (or the slice ends) */
+			const int64_t e = jtk_rx_chain(P, T, s, lo, hi, cur, end_run, -1, B.ms, B.me, nullptr, usable ? B.s_from : nullptr, &cms, &cme, &joined, st, cap, &overflow, bor);
+			if (overflow) return false;
+			if (!joined) {
+				if (cms >= 0) {
+					bor(B.ms + (cms >> 5), 1u << (cms & 31));
+					bor(B.me + (cme >> 5), 1u << (cme & 31));
+				}
+				cur = e;
+				continue;
+			}
+			cur = e;
+		}
+		/* from `cur` on the slice's speculative result is the true one */
+		B.join[slice] = cur;
+		if (B.last_ms[slice] >= 0) {
+			bor(B.ms + (B.last_ms[slice] >> 5), 1u << (B.last_ms[slice] & 31));
+			bor(B.me + (B.last_me[slice] >> 5), 1u << (B.last_me[slice] & 31));
+		}
+		cur = B.exit_slice[slice];
+	}
+	return true;
+}
+
+/* Pass 3, one call per 32-bit word: accepted speculative bits join the final ones; then ms / me become piece starts / gap flags. */
+JTK_HD void jtk_rx_finish_word(const jtk_rx_split_buffers &B, int64_t w, int64_t total) {
+	const int64_t slice = (w * 32) / JTK_RX_SLICE;
+	uint32_t ms = B.ms[w], me = B.me[w];
+	if (slice < B.nslices) {
+		const int64_t j = B.join[slice] - w * 32; /* speculative bits at word positions >= j are valid */
+		const uint32_t mask = j <= 0 ? 0xFFFFFFFFu : j >= 32 ? 0u : (0xFFFFFFFFu << j);
+		ms |= B.s_ms[w] & mask;
+		me |= B.s_me[w] & mask;
+	}
+	if ((total >> 5) == w) me |= 1u << (total & 31); /* the end of the input ends the last piece */
+	B.ms[w] = ms | me;
+	B.me[w] = me & ~ms;
 }
 
 #endif /* JTK_REGEX_H */

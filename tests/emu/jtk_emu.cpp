@@ -172,17 +172,44 @@ int64_t emu_run(const emu_encoding *e, const uint8_t *bytes, int64_t total, cons
 }
 }
 
-/* General split patterns: runs the backtracking program (jtk_regex.h) over every document the way jtk_general_split_kernel
- * does.  start[g] = 1 at piece starts, skip[g] = 1 where the piece starting at g is a gap.  Returns 0, 1 on stack overflow, -1 if
- * the encoding has no general program. */
+/* General split patterns: runs the three passes of the sliced Matcher.find() (jtk_regex.h) the way the kernels do, with
+ * JTK_RX_SLICE-byte slices (tests/emu/Makefile makes them tiny).  start[g] = 1 at piece starts, skip[g] = 1 where the piece
+ * starting at g is a gap.  Returns 0, 1 on stack overflow, -1 if the encoding has no general program. */
 extern "C" int emu_general_split(const emu_encoding *e, const uint8_t *bytes, const int64_t *doc_off, int64_t ndocs, uint8_t *start, uint8_t *skip, int stack_cap) {
 	if (e->view.pattern_kind != JTK_PAT_GENERAL) return -1;
 	const jtk_rx_program P = jtk_rx_program_of(e->view);
-	bool overflow = false;
+	const int64_t total = doc_off[ndocs];
+	const int64_t nslices = (total + JTK_RX_SLICE - 1) / JTK_RX_SLICE, nwords = total / 32 + 2;
+	std::vector<uint32_t> bits((size_t) (5 * nwords), 0);
+	std::vector<int64_t> rec((size_t) (4 * nslices + ndocs + 1), 0);
+	jtk_rx_split_buffers B;
+	B.ms = bits.data();
+	B.me = B.ms + nwords;
+	B.s_ms = B.me + nwords;
+	B.s_me = B.s_ms + nwords;
+	B.s_from = B.s_me + nwords;
+	B.exit_slice = rec.data();
+	B.last_ms = B.exit_slice + nslices;
+	B.last_me = B.last_ms + nslices;
+	B.join = B.last_me + nslices;
+	B.exit_doc = B.join + nslices;
+	B.nwords = nwords;
+	B.nslices = nslices;
 	std::vector<jtk_rx_frame> st((size_t) stack_cap);
-	for (int64_t d = 0; d < ndocs && !overflow; d++)
-		jtk_rx_split_document(P, e->view, bytes, doc_off[d], doc_off[d + 1], st.data(), stack_cap, [&](int64_t g) { start[g] = 1; }, [&](int64_t g) { skip[g] = 1; }, &overflow);
-	return overflow ? 1 : 0;
+	auto bor = [](uint32_t *w, uint32_t m) { *w |= m; };
+	int64_t bad = -1;
+	for (int64_t s = 0; s < nslices; s++)
+		jtk_rx_slice_pass(P, e->view, bytes, total, doc_off, ndocs, s, B, st.data(), stack_cap < 10 ? stack_cap : 10, &bad, bor); /* tiny stack: overflows are left to pass 2, as on the device */
+	for (int64_t d = 0; d < ndocs; d++) {
+		if (doc_off[d + 1] == doc_off[d]) continue;
+		if (!jtk_rx_stitch_doc(P, e->view, bytes, total, doc_off, d, B, st.data(), stack_cap, bor)) return 1;
+	}
+	for (int64_t w = 0; w < nwords; w++) jtk_rx_finish_word(B, w, total);
+	for (int64_t g = 0; g < total; g++) {
+		start[g] = (B.ms[g >> 5] >> (g & 31)) & 1u;
+		skip[g] = (B.me[g >> 5] >> (g & 31)) & 1u;
+	}
+	return 0;
 }
 
 extern "C" int emu_pattern_kind(const emu_encoding *e) { return e->view.pattern_kind; }

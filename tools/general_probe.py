@@ -14,7 +14,9 @@ d, o = data.numpy(), off.numpy()
 variants = [("predefined cl100k pattern (class tables + bit-parallel rules)", p.get_pattern().pattern(), 0x100),
             ("same pattern with CASE_INSENSITIVE (general program)", p.get_pattern().pattern(), 0x102),
             (r"general: \w+|\s+|[^\w\s]+", r"\w+|\s+|[^\w\s]+", 0)]
-base = None
+from tools.gpu_probe import run
+dev = torch.device("cuda", 0)
+d_dev, o_dev = data.to(dev), off.to(dev)
 for label, pat, flags in variants:
     enc = jt.EncodingFactory.from_parameters(jt.GptBytePairEncodingParams("probe", jt.Pattern.compile(pat, flags), p.encoder, p.special_tokens_encoder))
     enc.encode_packed(d, o, ordinary=True)
@@ -23,3 +25,5 @@ for label, pat, flags in variants:
     dt = time.perf_counter() - t0
     print("%-70s %6.1f ms host-to-host for %d MiB / %d documents (%.2f GB/s), %d tokens, flagged documents %d" %
           (label, dt * 1e3, size >> 20, o.size - 1, d.size / dt / 1e9, res.ids.size, int((res.doc_status != 0).sum())), flush=True)
+    res.close()
+    run(enc, d_dev, o_dev, "  device-resident", steps=3)

@@ -684,7 +684,7 @@ static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspa
 	CUDA_TRY(jtk_launch_tile_first_doc(d_doc_off, ndocs, ntiles, w->tile_first_doc, st));
 	int general_launches = 0;
 	if (ds->T.pattern_kind == JTK_PAT_GENERAL && ntiles > 0) {
-		/* general pattern: piece / gap bits per document first (jtk_general_split_kernel), the tile kernels read them */
+		/* general pattern: piece / gap bits first (jtk_general_slice / stitch / finish kernels), the tile kernels read them */
 		const int64_t words = (ntiles * (int64_t) JTK_TILE + JTK_REGION) / 32 + 2;
 		const int64_t slices = (nbytes + JTK_RX_SLICE - 1) / JTK_RX_SLICE, recs = 4 * slices + ndocs + 1;
 		if (words > w->rx_words_cap) {

@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(JTK_NT, 2048 / JTK_NT) jtk_split_lookup_kernel
 		/* ---- P1: stage bytes (16-byte loads), clear masks, mark document starts ---- */
 		const int64_t first_doc = a.tile_first_doc[tile];
 		if (GENERAL) {
-			/* general pattern: the piece bits were computed per document by jtk_general_split_kernel; dmask holds the gap bits */
+			/* general pattern: the piece bits were computed by the jtk_general_* kernels; dmask holds the gap bits */
 			const int64_t w0 = c.g0 / 32; /* g0 is a multiple of 32 (negative for the first tile) */
 			for (int w = tid; w < JTK_MASK_WORDS; w += NT) {
 				const int64_t gw = w0 + w;

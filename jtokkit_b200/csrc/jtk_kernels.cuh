@@ -88,7 +88,7 @@ struct jtk_encode_args {
 	uint8_t *piece_flags;  /* debug: one byte per input byte, 1 where a piece starts (nullable) */
 	jtk_memo_entry *memo;  /* per-call piece memo (nullable) */
 	uint32_t memo_mask, memo_epoch;
-	/* JTK_PAT_GENERAL only: one bit per input byte (word g / 32, bit g % 32), written by jtk_general_split_kernel:
+	/* JTK_PAT_GENERAL only: one bit per input byte (word g / 32, bit g % 32), written by the jtk_general_* kernels:
 	 * piece starts, and which of those pieces are gaps (text the pattern did not match: no tokens) */
 	uint32_t *rx_start, *rx_skip;
 	int64_t rx_words;

@@ -1,6 +1,6 @@
 /*
  * General split patterns: a java.util.regex subset compiled at registration into a small backtracking program that the
- * GPU runs with one thread per document (jtk_general_split_kernel).  This is what makes
+ * GPU runs per 512-byte slice and stitches per document (jtk_general_slice / stitch / finish kernels, see below).  This is what makes
  * EncodingRegistry.registerGptBytePairEncoding (AbstractEncodingRegistry.java:63-66) accept patterns other than the two
  * predefined ones, e.g. Pattern.compile("test") in BaseEncodingRegistryTest.java:110-125.  The predefined patterns never
  * take this path (they compile to class tables + bit-parallel rules, jtk_device.cuh); it is the slow, general one.

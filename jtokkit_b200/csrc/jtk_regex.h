@@ -141,10 +141,11 @@ struct jtk_rx_frame {
 
 /* Runs the program from instruction `pc0` at byte position `start` of the document s[lo..n).  Returns the end of the match
  * or -1; *overflow is set when the backtrack stack st[0..cap) was too small (the caller flags the document).  DEPTH: look-ahead
- * nesting; a look-ahead runs on the unused rest of the same stack. */
+ * nesting; a look-ahead runs on the unused rest of the same stack.  *hit_end is set when the end of the text n was observed (a
+ * speculative run over a truncated view of the document cannot be trusted then). */
 template <int DEPTH>
 JTK_HD int64_t jtk_rx_run(const jtk_rx_program &P, const jtk_tables &T, const uint8_t *s, int64_t lo, int64_t n, int64_t start, int pc0, jtk_rx_frame *st, int cap,
-                          bool *overflow) {
+                          bool *overflow, bool *hit_end) {
 	int sp = 0;
 	int pc = pc0;
 	int64_t pos = start;
@@ -155,9 +156,11 @@ JTK_HD int64_t jtk_rx_run(const jtk_rx_program &P, const jtk_tables &T, const ui
 		case JTK_RX_MATCH: return pos;
 		case JTK_RX_SET: {
 			if (pos >= n) {
+				*hit_end = true;
 				fail = true;
 				break;
 			}
+			if (pos + 4 > n) *hit_end = true;
 			int len;
 			const uint32_t cp = jtk_rx_decode(s, pos, n, &len);
 			if (!jtk_rx_in_set(P, T, in.a, cp)) fail = true;
@@ -178,6 +181,7 @@ JTK_HD int64_t jtk_rx_run(const jtk_rx_program &P, const jtk_tables &T, const ui
 					q += len;
 					count++;
 				}
+				if (q + 4 > n) *hit_end = true;
 				if (count < in.b) {
 					fail = true;
 					break;
@@ -201,6 +205,7 @@ JTK_HD int64_t jtk_rx_run(const jtk_rx_program &P, const jtk_tables &T, const ui
 				q += len;
 				count++;
 			}
+			if (q + 4 > n) *hit_end = true; /* (within a character of the end: the last character may have been decoded differently) */
 			if (count < in.b) {
 				fail = true;
 				break;
@@ -236,6 +241,7 @@ JTK_HD int64_t jtk_rx_run(const jtk_rx_program &P, const jtk_tables &T, const ui
 			else pc++;
 			break;
 		case JTK_RX_EOL: { /* Java '$' without MULTILINE: at the end, or before a final line terminator */
+			if (pos + 4 > n) *hit_end = true;
 			bool ok = pos == n;
 			if (!ok && pos < n) {
 				int len;
@@ -250,7 +256,7 @@ JTK_HD int64_t jtk_rx_run(const jtk_rx_program &P, const jtk_tables &T, const ui
 		}
 		case JTK_RX_LOOK: {
 			int64_t r = -1;
-			if (DEPTH < 2) r = jtk_rx_run<(DEPTH < 2 ? DEPTH + 1 : 2)>(P, T, s, lo, n, pos, in.b, st + sp, cap - sp, overflow); /* look-ahead nests at most twice (checked at compile time of the pattern) */
+			if (DEPTH < 2) r = jtk_rx_run<(DEPTH < 2 ? DEPTH + 1 : 2)>(P, T, s, lo, n, pos, in.b, st + sp, cap - sp, overflow, hit_end); /* look-ahead nests at most twice (checked at compile time of the pattern) */
 			else *overflow = true;
 			if ((r >= 0) == (in.a != 0)) fail = true;
 			else pc++;
@@ -282,6 +288,7 @@ JTK_HD int64_t jtk_rx_run(const jtk_rx_program &P, const jtk_tables &T, const ui
 				sp--;
 			} else { /* lazy run: take one more character */
 				bool took = false;
+				if (f.pos + 4 > n) *hit_end = true;
 				if ((rep.c < 0 || f.count < rep.c) && f.pos < n) {
 					int len;
 					const uint32_t cp = jtk_rx_decode(s, f.pos, n, &len);
@@ -314,7 +321,8 @@ JTK_HD void jtk_rx_find_all(const jtk_rx_program &P, const jtk_tables &T, const 
 		}
 		int64_t ms = -1, me = -1;
 		for (int64_t stp = from; stp <= n;) {
-			const int64_t r = jtk_rx_run<0>(P, T, s, lo, n, stp, 0, st, cap, overflow);
+			bool hit_end = false;
+			const int64_t r = jtk_rx_run<0>(P, T, s, lo, n, stp, 0, st, cap, overflow, &hit_end);
 			if (*overflow) return;
 			if (r >= 0) {
 				ms = stp;
@@ -352,7 +360,7 @@ JTK_HD void jtk_rx_find_all(const jtk_rx_program &P, const jtk_tables &T, const 
 #ifndef JTK_RX_SLICE
 #define JTK_RX_SLICE 512
 #endif
-#define JTK_RX_SPEC_LIMIT (8 * JTK_RX_SLICE) /* a speculative search that finds nothing this far beyond its slice gives up */
+#define JTK_RX_SPEC_LIMIT (8 * JTK_RX_SLICE) /* a speculative run sees this much of the document beyond its slice; it gives up when the matcher reaches the end of that view */
 #define JTK_RX_NO_EXIT (-2)                  /* slice record: the speculative run gave up */
 
 struct jtk_rx_split_buffers {
@@ -367,24 +375,26 @@ struct jtk_rx_split_buffers {
 
 enum { JTK_RX_FOUND = 0, JTK_RX_NONE = 1, JTK_RX_GAVE_UP = 2 };
 
-/* next match at or after `from` (search positions beyond `limit` are not tried) */
-JTK_HD int jtk_rx_find_next(const jtk_rx_program &P, const jtk_tables &T, const uint8_t *s, int64_t lo, int64_t n, int64_t from, int64_t limit, int64_t *ms, int64_t *me,
+/* next match at or after `from`.  `view` <= n is the end of the text as this search may see it: when it is short of n and the
+ * matcher gets to see it, the search gives up (with the whole text the outcome might differ). */
+JTK_HD int jtk_rx_find_next(const jtk_rx_program &P, const jtk_tables &T, const uint8_t *s, int64_t lo, int64_t n, int64_t from, int64_t view, int64_t *ms, int64_t *me,
                             jtk_rx_frame *st, int cap, bool *overflow) {
-	for (int64_t stp = from; stp <= n;) {
-		if (stp > limit) return JTK_RX_GAVE_UP;
-		const int64_t r = jtk_rx_run<0>(P, T, s, lo, n, stp, 0, st, cap, overflow);
+	bool hit_end = false;
+	for (int64_t stp = from; stp <= view;) {
+		const int64_t r = jtk_rx_run<0>(P, T, s, lo, view, stp, 0, st, cap, overflow, &hit_end);
 		if (*overflow) return JTK_RX_NONE;
+		if (hit_end && view < n) return JTK_RX_GAVE_UP;
 		if (r >= 0) {
 			*ms = stp;
 			*me = r;
 			return JTK_RX_FOUND;
 		}
-		if (stp >= n) break;
+		if (stp >= view) break;
 		int len;
-		jtk_rx_decode(s, stp, n, &len);
+		jtk_rx_decode(s, stp, view, &len);
 		stp += len;
 	}
-	return JTK_RX_NONE;
+	return view < n ? JTK_RX_GAVE_UP : JTK_RX_NONE;
 }
 
 JTK_HD bool jtk_rx_bit(const uint32_t *b, int64_t g) { return (b[g >> 5] >> (g & 31)) & 1u; }
@@ -393,7 +403,7 @@ JTK_HD bool jtk_rx_bit(const uint32_t *b, int64_t g) { return (b[g >> 5] >> (g &
  * `bor` (matches that end inside the run only; the one that crosses end_run is returned in *cross_ms / *cross_me).  from_bits
  * (nullable): every `from` passed is recorded.  stop_bits (nullable): the run stops as soon as it lands on a recorded `from`
  * of another run and returns it with *joined = true.  Returns the `from` at which it stopped (>= end_run, hi when nothing
- * matches any more) or JTK_RX_NO_EXIT when a search gave up (limit >= 0: bytes a search may go beyond end_run).  On a
+ * matches any more) or JTK_RX_NO_EXIT when a search gave up (limit >= 0: bytes of the document beyond end_run that a search may see).  On a
  * backtrack-stack overflow *overflow is set and the `from` whose search overflowed is returned (everything before it is done). */
 template <typename Or>
 JTK_HD int64_t jtk_rx_chain(const jtk_rx_program &P, const jtk_tables &T, const uint8_t *s, int64_t lo, int64_t hi, int64_t from, int64_t end_run, int64_t limit,
@@ -410,7 +420,8 @@ JTK_HD int64_t jtk_rx_chain(const jtk_rx_program &P, const jtk_tables &T, const 
 		first = false;
 		if (from_bits) bor(from_bits + (from >> 5), 1u << (from & 31));
 		int64_t ms, me;
-		const int r = jtk_rx_find_next(P, T, s, lo, hi, from, limit < 0 ? hi : end_run + limit, &ms, &me, st, cap, overflow);
+		const int64_t view = (limit < 0 || end_run + limit > hi) ? hi : end_run + limit;
+		const int r = jtk_rx_find_next(P, T, s, lo, hi, from, view, &ms, &me, st, cap, overflow);
 		if (*overflow) return from;
 		if (r == JTK_RX_GAVE_UP) return JTK_RX_NO_EXIT;
 		if (r == JTK_RX_NONE) return hi;

@@ -27,3 +27,16 @@ for label, pat, flags in variants:
           (label, dt * 1e3, size >> 20, o.size - 1, d.size / dt / 1e9, res.ids.size, int((res.doc_status != 0).sum())), flush=True)
     res.close()
     run(enc, d_dev, o_dev, "  device-resident", steps=3)
+
+# adversarial for the sliced matcher: one match (or one gap) per 1 MiB document
+enc = jt.EncodingFactory.from_parameters(jt.GptBytePairEncodingParams("probe_long", jt.Pattern.compile(r"[a-z]+|\d{1,3}"), p.encoder, p.special_tokens_encoder))
+for name, doc in (("one 1 MiB match per document", b"a" * (1 << 20)), ("one 1 MiB gap per document", b"!" * (1 << 20))):
+    blob, o2 = jt.pack_documents([doc] * 8)
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        res = enc.encode_packed(blob, o2, ordinary=True)
+        ts.append(time.perf_counter() - t0)
+        n = res.ids.size
+        res.close()
+    print("%-40s 8 x 1 MiB: %.1f ms host-to-host, %d tokens" % (name, min(ts[1:]) * 1e3, n), flush=True)

@@ -211,6 +211,7 @@ static int init_device(jtk_encoding *e, int device) {
 	T.rx_sets = base + o_rxs;
 	T.rx_ranges = reinterpret_cast<const uint32_t *>(base + o_rxr);
 	T.rx_ninst = h.rx_ninst;
+	memcpy(T.rx_first, h.rx_first, sizeof(T.rx_first));
 	T.mask_a = h.mask_a;
 	T.mask_b = h.mask_b;
 	T.mask_p = h.mask_p;

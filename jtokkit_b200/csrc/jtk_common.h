@@ -143,6 +143,7 @@ struct jtk_tables {
 	const void *rx_sets;
 	const uint32_t *rx_ranges;
 	int32_t rx_ninst;
+	uint32_t rx_first[8]; /* bytes with which a match can begin (all ones when the pattern can match the empty string) */
 };
 
 /* ---- hashing (identical on host and device) ---------------------------------------------------- */

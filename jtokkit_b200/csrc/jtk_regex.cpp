@@ -608,5 +608,41 @@ int jtk_rx_compile(const char *pattern, int flags, jtk_rx_compiled *out, std::st
 		return JTK_E_PATTERN_UNSUPPORTED;
 	}
 	if (out->ranges.empty()) out->ranges.push_back(0);
+	/* first bytes: walk the program from its entry over everything that consumes no character */
+	memset(out->first, 0, sizeof(out->first));
+	{
+		bool any = out->nullable;
+		std::vector<char> seen(out->inst.size(), 0);
+		std::vector<int> todo(1, 0);
+		while (!todo.empty() && !any) {
+			const int pc = todo.back();
+			todo.pop_back();
+			if (pc < 0 || pc >= (int) out->inst.size() || seen[(size_t) pc]) continue;
+			seen[(size_t) pc] = 1;
+			const jtk_rx_inst &in = out->inst[(size_t) pc];
+			switch (in.op) {
+			case JTK_RX_SET:
+			case JTK_RX_REP: {
+				const jtk_rx_set &st = out->sets[(size_t) in.a];
+				for (int w = 0; w < 4; w++) /* the bitmap holds the un-negated ASCII members; `.` ignores it */
+					out->first[w] |= (st.flags & JTK_RX_DOT) ? ~0u : (st.flags & JTK_RX_NEG) ? ~st.ascii[w] : st.ascii[w];
+				if (st.range_count > 0 || (st.flags & ~0u)) /* can hold non-ASCII characters (ranges, classes, negation, dot): any byte >= 0x80 */
+					for (int w = 4; w < 8; w++) out->first[w] = ~0u;
+				if (in.op == JTK_RX_REP && in.b == 0) todo.push_back(pc + 1); /* may take nothing */
+				break;
+			}
+			case JTK_RX_SPLIT:
+				todo.push_back(in.a);
+				todo.push_back(in.b);
+				break;
+			case JTK_RX_JMP: todo.push_back(in.a); break;
+			case JTK_RX_LOOK: /* zero width: the sub-program does not consume, matching goes on at pc + 1 */
+			case JTK_RX_BOL:
+			case JTK_RX_EOL: todo.push_back(pc + 1); break;
+			default: any = true; /* MATCH reached without consuming: the pattern can match the empty string */
+			}
+		}
+		if (any) memset(out->first, 0xFF, sizeof(out->first));
+	}
 	return JTK_OK;
 }

@@ -59,10 +59,12 @@ struct jtk_rx_program {
 	int32_t ninst;
 	const jtk_rx_set *sets;
 	const uint32_t *ranges;
+	const uint32_t *first; /* 256-bit map of the bytes a match can begin with */
 };
 
 JTK_HD jtk_rx_program jtk_rx_program_of(const jtk_tables &T) {
 	jtk_rx_program P;
+	P.first = T.rx_first;
 	P.inst = static_cast<const jtk_rx_inst *>(T.rx_inst);
 	P.ninst = T.rx_ninst;
 	P.sets = static_cast<const jtk_rx_set *>(T.rx_sets);
@@ -381,6 +383,14 @@ JTK_HD int jtk_rx_find_next(const jtk_rx_program &P, const jtk_tables &T, const 
                             jtk_rx_frame *st, int cap, bool *overflow) {
 	bool hit_end = false;
 	for (int64_t stp = from; stp <= view;) {
+		/* positions whose first byte cannot begin a match are stepped over character by character without running the program */
+		while (stp < view && !((P.first[s[stp] >> 5] >> (s[stp] & 31)) & 1u)) {
+			int len;
+			jtk_rx_decode(s, stp, view, &len);
+			stp += len;
+			if (stp + 4 > view) hit_end = true; /* the last character of a truncated view may have been cut */
+		}
+		if (hit_end && view < n) return JTK_RX_GAVE_UP;
 		const int64_t r = jtk_rx_run<0>(P, T, s, lo, view, stp, 0, st, cap, overflow, &hit_end);
 		if (*overflow) return JTK_RX_NONE;
 		if (hit_end && view < n) return JTK_RX_GAVE_UP;

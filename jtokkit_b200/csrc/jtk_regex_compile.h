@@ -13,6 +13,7 @@ struct jtk_rx_compiled {
 	std::vector<jtk_rx_set> sets;
 	std::vector<uint32_t> ranges;
 	bool nullable = false; /* the pattern can match the empty string */
+	uint32_t first[8];     /* bytes with which a match can begin (every byte when nullable): lets the search skip the others */
 };
 
 /* pattern: UTF-8 java.util.regex source; flags: Pattern flag bits.  Returns JTK_OK or JTK_E_PATTERN_UNSUPPORTED with *err. */

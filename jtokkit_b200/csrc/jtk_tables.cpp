@@ -228,6 +228,7 @@ int jtk_build_host_tables(const jtk_params *p, jtk_host_tables *t, std::string *
 		if (!prog.sets.empty()) memcpy(t->rx_sets.data(), prog.sets.data(), t->rx_sets.size());
 		t->rx_ranges = prog.ranges;
 		t->rx_ninst = (int32_t) prog.inst.size();
+		memcpy(t->rx_first, prog.first, sizeof(t->rx_first));
 	}
 	/* the general program reads the class table for \p{L}, \p{N} and the Unicode \s only: always White_Space there */
 	build_class_tables(t, t->pattern_kind == JTK_PAT_GENERAL ? (p->pattern_flags | JTK_RE_UNICODE_CHARACTER_CLASS) : p->pattern_flags);
@@ -441,5 +442,6 @@ jtk_tables jtk_host_view(const jtk_host_tables &h) {
 	v.rx_sets = h.rx_sets.data();
 	v.rx_ranges = h.rx_ranges.data();
 	v.rx_ninst = h.rx_ninst;
+	memcpy(v.rx_first, h.rx_first, sizeof(v.rx_first));
 	return v;
 }

@@ -48,6 +48,7 @@ struct jtk_host_tables {
 	std::vector<uint8_t> rx_inst, rx_sets;
 	std::vector<uint32_t> rx_ranges;
 	int32_t rx_ninst = 0;
+	uint32_t rx_first[8] = {~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u};
 	/* statistics (reported by DESIGN.md / tests) */
 	int64_t n_tokens = 0, n_pairs = 0;
 	int32_t max_probe_a = 0, max_probe_b = 0, max_probe_p = 0;

@@ -20,6 +20,8 @@ struct jtk_tile_ctx {
 	uint8_t *cls;    /* JTK_REGION + 16 class bytes */
 	uint32_t *bmask; /* piece-start bits, (JTK_REGION + 32) / 32 + 1 words */
 	uint32_t *dmask; /* document-start bits, same size; the end of the input counts as a document start */
+	uint32_t *planes; /* per 16-byte chunk three words: bit planes 0 / 1, 2 / 3 of the class codes and continuation flag / byte high bit,
+	                   * sixteen positions each (written with the classes, read by the bit-parallel split rules) */
 	int32_t *tok;    /* JTK_TILE + JTK_FWD_HALO token staging, indexed by r - JTK_BACK_HALO */
 	int32_t *rk;     /* same size: pair ranks during merging, then per-piece token counts */
 	/* geometry */
@@ -148,6 +150,24 @@ struct jtk_region_start {
 	JTK_HD bool operator()(int64_t r) const { return jtk_docstart(*c, (int) r); }
 };
 
+/* bit b of each of the four bytes of w -> 4 mask bits */
+JTK_HD uint32_t jtk_plane4(uint32_t w, int b) { return (((w >> b) & 0x01010101u) * 0x01020408u) >> 24; }
+
+/* the chunk's bit planes from its four class words and four byte words (see jtk_tile_ctx::planes) */
+JTK_HD void jtk_store_planes(jtk_tile_ctx &c, int chunk, const uint32_t *cw, const uint32_t *bw) {
+	uint32_t p01 = 0, p23 = 0, pch = 0;
+	for (int k = 0; k < 4; k++) {
+		const uint32_t w = cw[k];
+		p01 |= (jtk_plane4(w, 0) | (jtk_plane4(w, 1) << 16)) << (4 * k);
+		p23 |= (jtk_plane4(w, 2) | (jtk_plane4(w, 3) << 16)) << (4 * k);
+		pch |= (jtk_plane4(w, 7) | (jtk_plane4(bw[k], 7) << 16)) << (4 * k);
+	}
+	uint32_t *o = c.planes + 3 * chunk;
+	o[0] = p01;
+	o[1] = p23;
+	o[2] = pch;
+}
+
 /* Fast classification of chunk `chunk`: sixteen ASCII bytes are sixteen table reads (a character cannot straddle into an
  * ASCII chunk).  Returns false when the chunk holds a non-ASCII byte. */
 JTK_HD bool jtk_classify_fast(jtk_tile_ctx &c, int chunk) {
@@ -157,10 +177,16 @@ JTK_HD bool jtk_classify_fast(jtk_tile_ctx &c, int chunk) {
 	if (((w0 | w1 | w2 | w3) & 0x80808080u) != 0) return false;
 	uint32_t *o = reinterpret_cast<uint32_t *>(c.cls + r0);
 	const uint8_t *lut = c.ascii_lut;
-	o[0] = lut[w0 & 0xFF] | (lut[(w0 >> 8) & 0xFF] << 8) | (lut[(w0 >> 16) & 0xFF] << 16) | ((uint32_t) lut[w0 >> 24] << 24);
-	o[1] = lut[w1 & 0xFF] | (lut[(w1 >> 8) & 0xFF] << 8) | (lut[(w1 >> 16) & 0xFF] << 16) | ((uint32_t) lut[w1 >> 24] << 24);
-	o[2] = lut[w2 & 0xFF] | (lut[(w2 >> 8) & 0xFF] << 8) | (lut[(w2 >> 16) & 0xFF] << 16) | ((uint32_t) lut[w2 >> 24] << 24);
-	o[3] = lut[w3 & 0xFF] | (lut[(w3 >> 8) & 0xFF] << 8) | (lut[(w3 >> 16) & 0xFF] << 16) | ((uint32_t) lut[w3 >> 24] << 24);
+	uint32_t v[4];
+	v[0] = lut[w0 & 0xFF] | (lut[(w0 >> 8) & 0xFF] << 8) | (lut[(w0 >> 16) & 0xFF] << 16) | ((uint32_t) lut[w0 >> 24] << 24);
+	v[1] = lut[w1 & 0xFF] | (lut[(w1 >> 8) & 0xFF] << 8) | (lut[(w1 >> 16) & 0xFF] << 16) | ((uint32_t) lut[w1 >> 24] << 24);
+	v[2] = lut[w2 & 0xFF] | (lut[(w2 >> 8) & 0xFF] << 8) | (lut[(w2 >> 16) & 0xFF] << 16) | ((uint32_t) lut[w2 >> 24] << 24);
+	v[3] = lut[w3 & 0xFF] | (lut[(w3 >> 8) & 0xFF] << 8) | (lut[(w3 >> 16) & 0xFF] << 16) | ((uint32_t) lut[w3 >> 24] << 24);
+	o[0] = v[0];
+	o[1] = v[1];
+	o[2] = v[2];
+	o[3] = v[3];
+	jtk_store_planes(c, chunk, v, w);
 	return true;
 }
 
@@ -181,9 +207,6 @@ JTK_HD int jtk_decode_char_fast(const jtk_tables &T, const uint8_t *sb, int r, u
 	*len = n;
 	return jtk_cp_class(T, cp);
 }
-
-/* bit b of each of the four bytes of w -> 4 mask bits */
-JTK_HD uint32_t jtk_plane4(uint32_t w, int b) { return (((w >> b) & 0x01010101u) * 0x01020408u) >> 24; }
 
 /* General classification of the 16 bytes of chunk `chunk` (region indices 16*chunk ..) into c.cls: UTF-8 decoding. */
 JTK_HD void jtk_classify_generic(jtk_tile_ctx &c, int chunk) {
@@ -253,10 +276,12 @@ JTK_HD void jtk_classify_generic(jtk_tile_ctx &c, int chunk) {
 		}
 	}
 	uint32_t *out = reinterpret_cast<uint32_t *>(c.cls + r0);
-	out[0] = (uint32_t) lo;
-	out[1] = (uint32_t) (lo >> 32);
-	out[2] = (uint32_t) hi;
-	out[3] = (uint32_t) (hi >> 32);
+	const uint32_t v[4] = {(uint32_t) lo, (uint32_t) (lo >> 32), (uint32_t) hi, (uint32_t) (hi >> 32)};
+	out[0] = v[0];
+	out[1] = v[1];
+	out[2] = v[2];
+	out[3] = v[3];
+	jtk_store_planes(c, chunk, v, w);
 }
 
 JTK_HD void jtk_classify_chunk(jtk_tile_ctx &c, int chunk) {
@@ -617,17 +642,21 @@ JTK_HD bool jtk_boundary_fast(const jtk_tile_ctx &c, int chunk, uint32_t *out) {
 		if (sh) D |= c.dmask[wi + 1] << (32 - sh);
 	}
 	const uint32_t Dtop = (c.dmask[(ws + 32) >> 5] >> ((ws + 32) & 31)) & 1u;
-	const uint32_t *bw = reinterpret_cast<const uint32_t *>(c.sb + ws);
-	const uint32_t *cw = reinterpret_cast<const uint32_t *>(c.cls + ws);
-	jtk_planes pl = {0, 0, 0, 0, 0, 0};
-	for (int k = 0; k < 8; k++) {
-		const uint32_t w = cw[k];
-		pl.P0 |= jtk_plane4(w, 0) << (4 * k);
-		pl.P1 |= jtk_plane4(w, 1) << (4 * k);
-		pl.P2 |= jtk_plane4(w, 2) << (4 * k);
-		pl.P3 |= jtk_plane4(w, 3) << (4 * k);
-		pl.CONT |= jtk_plane4(w, 7) << (4 * k);
-		pl.HB |= jtk_plane4(bw[k], 7) << (4 * k);
+	/* the window [ws, ws + 32) = last eight positions of the previous chunk, this chunk, first eight of the next one */
+	jtk_planes pl;
+	{
+		const uint32_t *pp = c.planes + 3 * (chunk - 1);
+		const uint32_t a0 = pp[0], a1 = pp[1], a2 = pp[2], b0 = pp[3], b1 = pp[4], b2 = pp[5], c0 = pp[6], c1 = pp[7], c2 = pp[8];
+#define JTK_WIN_LO(a, b, c) ((((a) >> 8) & 0xFFu) | (((b) & 0xFFFFu) << 8) | (((c) & 0xFFu) << 24))
+#define JTK_WIN_HI(a, b, c) ((((a) >> 24) & 0xFFu) | (((b) >> 16) << 8) | ((((c) >> 16) & 0xFFu) << 24))
+		pl.P0 = JTK_WIN_LO(a0, b0, c0);
+		pl.P1 = JTK_WIN_HI(a0, b0, c0);
+		pl.P2 = JTK_WIN_LO(a1, b1, c1);
+		pl.P3 = JTK_WIN_HI(a1, b1, c1);
+		pl.CONT = JTK_WIN_LO(a2, b2, c2);
+		pl.HB = JTK_WIN_HI(a2, b2, c2);
+#undef JTK_WIN_LO
+#undef JTK_WIN_HI
 	}
 	uint32_t B;
 	if ((D | Dtop) == 0) {

@@ -240,6 +240,7 @@ __global__ void __launch_bounds__(JTK_NT, 2048 / JTK_NT) jtk_split_lookup_kernel
 	uint32_t *chunk_pref = reinterpret_cast<uint32_t *>(plist + RECN);      /* pieces before each 16-byte chunk */
 	uint32_t *misc = chunk_pref + TC;
 	uint8_t *s_ascii = reinterpret_cast<uint8_t *>(misc + M_WORDS); /* ASCII class table, 128 bytes */
+	uint32_t *planes = reinterpret_cast<uint32_t *>(s_ascii + 128); /* three words of bit planes per chunk (jtk_tile_ctx::planes) */
 
 	const int tid = threadIdx.x;
 	const int lane = tid & 31;
@@ -251,6 +252,7 @@ __global__ void __launch_bounds__(JTK_NT, 2048 / JTK_NT) jtk_split_lookup_kernel
 	c.cls = cls;
 	c.bmask = bmask;
 	c.dmask = dmask;
+	c.planes = planes;
 	c.tok = nullptr;
 	c.rk = nullptr;
 	c.total = a.total;

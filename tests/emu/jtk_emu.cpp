@@ -52,14 +52,15 @@ void emu_stats(const emu_encoding *e, int64_t *out) {
 
 struct emu_tile_state {
 	std::vector<uint8_t> sb, cls;
-	std::vector<uint32_t> bmask, dmask;
+	std::vector<uint32_t> bmask, dmask, planes;
 	std::vector<int32_t> tok, rk;
 	jtk_tile_ctx c;
-	emu_tile_state() : sb(JTK_REGION + 16), cls(JTK_REGION + 16), bmask(JTK_MASK_WORDS), dmask(JTK_MASK_WORDS), tok(JTK_TILE + JTK_FWD_HALO), rk(JTK_TILE + JTK_FWD_HALO) {
+	emu_tile_state() : sb(JTK_REGION + 16), cls(JTK_REGION + 16), bmask(JTK_MASK_WORDS), dmask(JTK_MASK_WORDS), planes(3 * (JTK_REGION_CHUNKS + 2)), tok(JTK_TILE + JTK_FWD_HALO), rk(JTK_TILE + JTK_FWD_HALO) {
 		c.sb = sb.data();
 		c.cls = cls.data();
 		c.bmask = bmask.data();
 		c.dmask = dmask.data();
+		c.planes = planes.data();
 		c.tok = tok.data();
 		c.rk = rk.data();
 	}

@@ -873,8 +873,10 @@ __global__ void __launch_bounds__(GNT, 8) jtk_gather_kernel(const __grid_constan
 							 * the loads happen in the coalesced copy loop below, all in flight together, instead of one dependent
 							 * load per iteration of this divergent loop */
 							const int off = (int) ((rec_payload(r[j]) >> 11) & 0x3FFFu);
-							for (int k = 0; k < cnt[j]; k++)
-								if (pos + k >= 0 && pos + k < GCAP) s_tok[pos + k] = REC_BASE + (off + k);
+							const int k0 = pos < 0 ? -pos : 0, k1 = min(cnt[j], GCAP - pos); /* the part of the piece inside the window */
+							int32_t *o = s_tok + pos;
+							const int32_t src = REC_BASE + off;
+							for (int k = k0; k < k1; k++) o[k] = src + k;
 						}
 					}
 					pos += cnt[j];

@@ -854,7 +854,7 @@ __global__ void __launch_bounds__(GNT, 8) jtk_gather_kernel(const __grid_constan
 		if (qb < P) s_gpref[qb / GIPT] = (uint16_t) excl;
 #pragma unroll
 		for (int j = 0; j < GIPT; j++)
-			if (qb + j < P && !rec_is_id(r[j]) && (rec_payload(r[j]) & REC_LONG)) {
+			if (!cnt[j] && qb + j < P && !rec_is_id(r[j]) && (rec_payload(r[j]) & REC_LONG)) { /* (no tokens here: rare, tested first) */
 				int before = excl - carry;
 				for (int i = 0; i < j; i++) before += cnt[i];
 				a.long_list[rec_payload(r[j]) & 0x0FFFFFFFu].insert_at = base + carry + before;
@@ -883,10 +883,16 @@ __global__ void __launch_bounds__(GNT, 8) jtk_gather_kernel(const __grid_constan
 				}
 				__syncthreads();
 				const int nw = min(GCAP, round_total - w0);
-				for (int k = tid; k < nw; k += GNT) {
-					int32_t v = s_tok[k];
-					if (!rec_is_id(v)) v = stok[v - REC_BASE];
-					dst[carry + w0 + k] = v;
+				for (int k = tid; k < nw; k += 4 * GNT) { /* four tokens per thread and step: the dependent loads of merged tokens overlap */
+					int32_t v[4];
+#pragma unroll
+					for (int i = 0; i < 4; i++) v[i] = k + i * GNT < nw ? s_tok[k + i * GNT] : 0;
+#pragma unroll
+					for (int i = 0; i < 4; i++)
+						if (!rec_is_id(v[i])) v[i] = stok[v[i] - REC_BASE];
+#pragma unroll
+					for (int i = 0; i < 4; i++)
+						if (k + i * GNT < nw) dst[carry + w0 + k + i * GNT] = v[i];
 				}
 				if (w0 + GCAP < round_total) __syncthreads();
 			}

@@ -863,6 +863,19 @@ __global__ void __launch_bounds__(GNT, 8) jtk_gather_kernel(const __grid_constan
 			/* stage the round's tokens in windows of GCAP (one window unless the tile is unusually token-dense), store coalesced */
 			for (int w0 = 0; w0 < round_total; w0 += GCAP) {
 				int pos = excl - carry - w0; /* window-relative position of this thread's first token */
+				if (round_total <= GCAP) { /* the usual case, one window: nothing to clip */
+#pragma unroll
+					for (int j = 0; j < GIPT; j++) {
+						if (rec_is_id(r[j])) {
+							s_tok[pos] = r[j];
+						} else if (cnt[j]) {
+							int32_t *o = s_tok + pos;
+							const int32_t src = REC_BASE + (int) ((rec_payload(r[j]) >> 11) & 0x3FFFu);
+							for (int k = 0; k < cnt[j]; k++) o[k] = src + k;
+						}
+						pos += cnt[j];
+					}
+				} else
 #pragma unroll
 				for (int j = 0; j < GIPT; j++) {
 					if (cnt[j] && pos + cnt[j] > 0 && pos < GCAP) {

@@ -292,9 +292,29 @@ class Encoding:
         rc = _capi.lib().jtk_encoding_create(C.byref(p), _ptr(devs), 0 if devs is None else devs.size, C.byref(h))
         if rc == _capi.JTK_E_PATTERN_UNSUPPORTED:
             raise ValueError("unsupported split pattern (no CPU fallback): " + _capi.last_error())
+        if rc == _capi.JTK_E_ARG:
+            raise ValueError("invalid encoding parameters: " + _capi.last_error())
         _capi.check(rc)
         self._h = h
         self.devices = list(devices) if devices else [0]
+
+    @classmethod
+    def from_tiktoken_file(cls, name, tiktoken_path, devices=None):
+        """A predefined encoding created entirely by the C ABI (jtk_encoding_create_builtin): the library parses the
+        .tiktoken file (EncodingFactory.loadMergeableRanks, EncodingFactory.java:139-164) and supplies the predefined pattern and
+        special tokens for `name` - the path a non-JVM, non-Python caller uses."""
+        self = cls.__new__(cls)
+        self._name = name
+        self._special = dict(_PREDEFINED[EncodingType.from_name(name)][2]) if EncodingType.from_name(name) else {}
+        devs = np.array(devices, dtype=np.int32) if devices else None
+        h = C.c_void_p()
+        rc = _capi.lib().jtk_encoding_create_builtin(name.encode("utf-8"), os.fsencode(tiktoken_path), _ptr(devs), 0 if devs is None else devs.size, C.byref(h))
+        if rc == _capi.JTK_E_ARG:
+            raise ValueError("invalid encoding parameters: " + _capi.last_error())
+        _capi.check(rc)
+        self._h = h
+        self.devices = list(devices) if devices else [0]
+        return self
 
     def close(self):
         if getattr(self, "_h", None):
@@ -322,6 +342,11 @@ class Encoding:
         with_special_tokens: special tokens in the text become their ids (jtk_encode_batch_special; not in the reference)."""
         utf8 = np.ascontiguousarray(utf8, dtype=np.uint8)
         doc_off = np.ascontiguousarray(doc_off, dtype=np.int64)
+        # the C ABI takes plain pointers: it cannot know the length of the byte buffer, so the bounds are checked here
+        if doc_off.ndim != 1 or doc_off.size < 1 or utf8.ndim != 1:
+            raise ValueError("doc_off must be a 1-D array of ndocs + 1 offsets and utf8 a 1-D byte array")
+        if int(doc_off[0]) != 0 or int(doc_off[-1]) > utf8.size or (doc_off.size > 1 and bool((np.diff(doc_off) < 0).any())):
+            raise ValueError("doc_off must start at 0, be non-decreasing and end at or before len(utf8)")
         flags = (0 if ordinary or with_special_tokens else _capi.CHECK_SPECIAL) | (_capi.COUNT_ONLY if count_only else 0)
         r = C.c_void_p()
         call = _capi.lib().jtk_encode_batch_special if with_special_tokens else _capi.lib().jtk_encode_batch
@@ -348,6 +373,8 @@ class Encoding:
         tile_kernel_ms)."""
         import torch
         dev = d_utf8.device.index if device is None else device
+        if d_doc_off.numel() < 1 or d_tok_off.numel() < d_doc_off.numel() or (d_status is not None and d_status.numel() < d_doc_off.numel() - 1):
+            raise ValueError("d_doc_off needs ndocs + 1 entries, d_tok_off at least as many, d_status at least ndocs")
         flags = (0 if ordinary else _capi.CHECK_SPECIAL) | (_capi.COUNT_ONLY if count_only else 0) | (_capi.TIME_KERNEL if time_kernel else 0)
         info = _capi.JtkDeviceInfo()
         _capi.check(_capi.lib().jtk_encode_batch_device(

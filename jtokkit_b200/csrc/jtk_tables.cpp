@@ -263,6 +263,24 @@ int jtk_build_host_tables(const jtk_params *p, jtk_host_tables *t, std::string *
 	}
 	const int64_t ntok = (int64_t) t->tok_rank.size();
 	t->n_tokens = ntok;
+	{
+		/* The device merge loop identifies a part by its token id (pair table keyed on (id left, id right), the id of a merged part is
+		 * the rank just found), so two different byte sequences must not share an id.  The reference looks ranks up by bytes
+		 * (GptBytePairEncoding.getRank :285-300) and tolerates such a vocabulary, but cannot decode it unambiguously either
+		 * (TokenEncoder.java:41-44: the last key put for a value wins); none of the predefined vocabularies has one. */
+		std::unordered_map<int32_t, int64_t> first_with_rank;
+		first_with_rank.reserve((size_t) ntok * 2);
+		for (int64_t k = 0; k < ntok; k++) {
+			auto ins = first_with_rank.emplace(t->tok_rank[(size_t) k], k);
+			if (!ins.second) {
+				char buf[160];
+				snprintf(buf, sizeof(buf), "token id %d is assigned to two different byte sequences (vocabulary entries %lld and %lld): ids must be unique per byte sequence",
+				         (int) t->tok_rank[(size_t) k], (long long) ins.first->second, (long long) k);
+				*err = buf;
+				return JTK_E_ARG;
+			}
+		}
+	}
 	if (t->tok_bytes.empty()) t->tok_bytes.push_back(0);
 
 	t->byte_id.resize(256);

@@ -69,3 +69,40 @@ def test_product_does_not_import_the_oracle():
                 for line in open(os.path.join(dirpath, f), errors="replace"):
                     if "oracle" in line.lower():
                         assert not any(tok in line for tok in loaders), (f, line)
+
+
+def test_duplicate_ids_are_rejected_at_registration():
+    """Two different byte sequences sharing one id: the device merge loop identifies parts by id, so registration refuses the
+    vocabulary (JTK_E_ARG -> ValueError) instead of merging pairs the reference would not (the check runs before any
+    device is touched, so it is testable without a GPU).  The same key twice is Map.put semantics and stays legal."""
+    import jtokkit_b200 as jt
+    pat = jt.Pattern.compile(jt.api.CL100K_PATTERN, jt.Pattern.UNICODE_CHARACTER_CLASS)
+    vocab = {b"a": 0, b"b": 1, b"c": 2, b"d": 3, b"e": 4, b"ab": 5, b"cd": 5, b"abe": 6}
+    with pytest.raises(ValueError) as ei:
+        jt.EncodingFactory.from_parameters(jt.GptBytePairEncodingParams("dup", pat, vocab, {}))
+    assert "two different byte sequences" in str(ei.value)
+    # a single-byte id colliding with a multi-byte id is the same defect
+    with pytest.raises(ValueError):
+        jt.EncodingFactory.from_parameters(jt.GptBytePairEncodingParams("dup2", pat, {b"a": 0, b"b": 1, b"ab": 1}, {}))
+
+
+def test_c_abi_builtin_loader_argument_errors():
+    """jtk_encoding_create_builtin (EncodingFactory.java:139-164 for non-JVM callers): unknown names and unreadable files are
+    argument errors with the reference's message shape; a good file gets as far as the device check."""
+    import torch
+    import jtokkit_b200 as jt
+    from jtokkit_b200 import _capi
+    good = os.path.join(ROOT, "jtokkit_b200", "data", "cl100k_base.tiktoken")
+    with pytest.raises(ValueError) as ei:
+        jt.Encoding.from_tiktoken_file("no_such_base", good)
+    assert "unknown predefined encoding" in str(ei.value)
+    with pytest.raises(ValueError) as ei:
+        jt.Encoding.from_tiktoken_file("cl100k_base", os.path.join(ROOT, "does", "not", "exist.tiktoken"))
+    assert "Could not find" in str(ei.value)
+    bad = os.path.join(ROOT, "tests", "golden", "cl100k_base_encodings.csv")  # not a .tiktoken file
+    with pytest.raises(ValueError):
+        jt.Encoding.from_tiktoken_file("cl100k_base", bad)
+    if not torch.cuda.is_available():
+        with pytest.raises(_capi.JtkError) as ei:
+            jt.Encoding.from_tiktoken_file("cl100k_base", good)
+        assert ei.value.code == _capi.JTK_E_CUDA  # parsed fine, then: no device, no CPU fallback

@@ -174,3 +174,44 @@ def test_special_token_encoding_matches_tiktoken_semantics(gpu_encodings, oracle
         with pytest.raises(NotImplementedError):
             g.encode("hello <|endoftext|> world")
     assert gpu_encodings["cl100k_base"].encode_with_special_tokens("<|endoftext|>") == [100257]
+
+
+def test_c_abi_builtin_loader_matches_python_loader(gpu_encodings, oracles):
+    """jtk_encoding_create_builtin parses each vendored .tiktoken file itself (EncodingFactory.loadMergeableRanks,
+    EncodingFactory.java:139-164) and must give the same encoding as the handle built from the Python-side loader:
+    same ids on golden inputs + fuzz text, same special-token guard, same decode."""
+    import os
+    import random
+    import jtokkit_b200 as jt
+    from conftest import load_golden
+    rng = random.Random(5)
+    files = {"r50k_base": "r50k_base.tiktoken", "p50k_base": "p50k_base.tiktoken", "p50k_edit": "p50k_base.tiktoken", "cl100k_base": "cl100k_base.tiktoken"}
+    units = ["hello", " world", "'s", "'LL", " ", "  ", "\n", "\r\n", "1234567", "日本語", "é", "\U0001F355", "!!!", " x", "\t", "don't", "ſ"]
+    for name, fname in files.items():
+        enc = jt.Encoding.from_tiktoken_file(name, os.path.join(jt.api.DATA_DIR, fname))
+        assert enc.get_name() == name
+        texts = [row[0] for row in load_golden(name)[::3]] + ["".join(rng.choice(units) for _ in range(rng.randint(0, 40))) for _ in range(300)]
+        got = enc.encode_ordinary_batch(texts)
+        ref = gpu_encodings[name].encode_ordinary_batch(texts)
+        assert np.array_equal(got.ids, ref.ids) and np.array_equal(got.token_offsets, ref.token_offsets)
+        assert got.tokens(5) == oracles[name].encode_ordinary(texts[5])
+        # predefined special tokens come from the library's own table (EncodingFactory.java:24-53)
+        with pytest.raises(NotImplementedError):
+            enc.encode("a <|endoftext|> b")
+        assert enc.decode(ref.tokens(7)) == texts[7]
+        if name in ("p50k_edit", "cl100k_base"):
+            with pytest.raises(NotImplementedError):
+                enc.encode("<|fim_middle|>")
+        else:
+            assert enc.encode("<|fim_middle|>") == gpu_encodings[name].encode("<|fim_middle|>")
+        enc.close()
+
+
+def test_encode_packed_rejects_inconsistent_offsets(gpu_encodings):
+    """The C ABI takes plain pointers; the Python mirror checks the offsets against the buffer before the call."""
+    enc = gpu_encodings["cl100k_base"]
+    data = np.frombuffer(b"hello world", dtype=np.uint8)
+    for off in ([0, 12], [1, 11], [0, 8, 4, 11], []):
+        with pytest.raises(ValueError):
+            enc.encode_packed(data, np.array(off, dtype=np.int64))
+    assert enc.encode_packed(data, np.array([0, 5, 11], dtype=np.int64)).to_lists() == [[15339], [1917]]

@@ -1,5 +1,6 @@
-"""GPU parity on the BASELINE.json configurations (sizes reduced to what the oracle finishes in seconds; the full 1 GiB
-comparison runs inside bench.py on its CPU-baseline sample) plus size-independent properties at larger sizes."""
+"""GPU parity on the BASELINE.json configurations at their full sizes where the oracle finishes in seconds (config 2: 64 MiB,
+config 4: over a million strings, config 5: all eight classes at 1 MiB; config 3 at 128 MiB here, its complete 1 GiB corpus is
+compared inside bench.py) plus size-independent properties at larger sizes."""
 import os
 
 import numpy as np
@@ -19,16 +20,18 @@ def compare_with_oracle(enc, orc, data_np, off_np, ordinary, threads=None):
 
 @pytest.mark.parametrize("name", ["r50k_base", "p50k_base"])
 def test_config2_english_encode_ordinary(name, gpu_encodings, oracles):
-    """configs[1]: r50k_base / p50k_base encodeOrdinary on synthetic English (16 MiB here), bit-exact."""
+    """configs[1] at full size: r50k_base / p50k_base encodeOrdinary on 64 MiB of synthetic English in 1 024 documents, bit-exact."""
     from jtokkit_b200 import synth
-    data, off = synth.config2_english_64mib("cuda", total=16 << 20)
+    data, off = synth.config2_english_64mib("cuda", total=64 << 20)
+    assert data.numel() >= (64 << 20) - 65536 and off.numel() - 1 >= 1000
     compare_with_oracle(gpu_encodings[name], oracles[name], data.cpu().numpy(), off.cpu().numpy(), ordinary=True)
 
 
 def test_config3_multilingual_encode(gpu_encodings, oracles):
-    """configs[2]: cl100k_base encode of the multilingual corpus (32 MiB here), bit-exact incl. document token offsets."""
+    """configs[2]: cl100k_base encode of the multilingual corpus (128 MiB here, the first eighth of the bench corpus), bit-exact
+    incl. document token offsets."""
     from jtokkit_b200 import synth
-    data, off = synth.config3_multilingual("cuda", total=32 << 20)
+    data, off = synth.config3_multilingual("cuda", total=128 << 20)
     res = compare_with_oracle(gpu_encodings["cl100k_base"], oracles["cl100k_base"], data.cpu().numpy(), off.cpu().numpy(), ordinary=False)
     # round trip on the device decode path: decode(encode(x)) == x for the whole batch
     enc = gpu_encodings["cl100k_base"]
@@ -40,10 +43,12 @@ def test_config3_multilingual_encode(gpu_encodings, oracles):
 
 
 def test_config4_count_tokens_short_strings(gpu_encodings, oracles):
-    """configs[3]: countTokens-only on short chat-length strings (8 MiB, ~30k strings here)."""
+    """configs[3]: countTokens-only on short chat-length strings: 288 MiB = more than a million strings (a tenth of the
+    10 M of BASELINE.json; every string's count is compared)."""
     from jtokkit_b200 import synth
-    data, off = synth.config4_chat("cuda", total=8 << 20)
+    data, off = synth.config4_chat("cuda", total=288 << 20)
     d, o = data.cpu().numpy(), off.cpu().numpy()
+    assert o.size - 1 >= 1_000_000
     res = gpu_encodings["cl100k_base"].encode_packed(d, o, count_only=True)
     _, _, counts = oracles["cl100k_base"].encode_batch_compact(d, o, os.cpu_count() or 1, check_special=True)
     assert res.ids is None
@@ -52,13 +57,12 @@ def test_config4_count_tokens_short_strings(gpu_encodings, oracles):
 
 @pytest.mark.parametrize("name", ["cl100k_base", "r50k_base"])
 def test_config5_adversarial_long_pieces(name, gpu_encodings, oracles):
-    """configs[4]: whitespace-free / repeated-byte documents stressing the merge loop (64 KiB per class here, 1 MiB for two
-    classes); expected ids from the oracle's exact heap merge (the literal O(n^2) loop is checked against it in test_oracle)."""
+    """configs[4] at full size: all eight classes of whitespace-free / repeated-byte 1 MiB documents (plus the 64 KiB versions);
+    expected ids from the oracle's exact heap merge (the literal O(n^2) loop is checked against it in test_oracle)."""
     from jtokkit_b200 import synth
     from oracle import jo
-    docs = synth.config5_adversarial(n=1 << 16)
-    big = synth.config5_adversarial(n=1 << 20)
-    docs += [big[0], big[1][: 1 << 18], big[7][: 1 << 18]]
+    docs = synth.config5_adversarial(n=1 << 16) + synth.config5_adversarial(n=1 << 20)
+    assert len(docs) == 16 and all(len(x.encode("utf-8") if isinstance(x, str) else x) >= (1 << 20) - 3 for x in docs[8:])
     enc, orc = gpu_encodings[name], oracles[name]
     res = enc.encode_ordinary_batch(docs)
     for d, doc in enumerate(docs):

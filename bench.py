@@ -10,8 +10,12 @@ independent, there is no data-path collective).
   value    : whole-job tokens/s, corpus resident in HBM, CUDA-event timed on the launching stream, max over ranks
   e2e      : same metric through the host-buffer C-ABI call (jtk_encode_batch) from pinned host memory, H2D + D2H inside
   roofline : algorithmic bytes of the tile kernel / its CUDA-event duration vs the measured HBM copy peak
+  strong   : ONE 1 GiB corpus (rank 0's) encoded through jtk_encode_batch on a handle that spans all N GPUs of the box
+             (in-library sharding: byte-balanced document chunks, chunk c on device c % N, no collective), host buffers in,
+             host result out, checked id by id against the single-device result; the other ranks wait on a host-side barrier
   cpu_baseline : the oracle's C restatement of the reference algorithm ("port"; this image has no JVM, so JTokkit itself
-             cannot run) on all host cores over a bounded sample of the same corpus
+             cannot run) on all host cores over the same corpus (all of it unless the host is too slow for ~30 s), which
+             doubles as the parity check: a mismatch makes the bench exit non-zero
 """
 import argparse
 import json
@@ -25,7 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 DEFAULT_BYTES = 1 << 30
-REFERENCE_SAMPLE_BYTES = 128 << 20
+REFERENCE_SAMPLE_BYTES = DEFAULT_BYTES  # the reference arm times the same 1 GiB corpus as the CUDA arm (~3 s per step on 16 cores)
 METRIC = "cl100k_base encode tokens/s (1 GiB synthetic multilingual corpus per GPU)"
 
 
@@ -163,6 +167,15 @@ def cpu_tiktoken_throughput(utf8_np, doc_off_np, sample_bytes, threads):
             "sample": "first %d bytes / %d documents (%d tokens) of the same corpus, %.1f s, %.3f GB/s input" % (len(raw), nd, ntok, dt, len(raw) / dt / 1e9)}
 
 
+WORKLOAD = "cl100k_base encode (special-token guard on), 1 GiB synthetic multilingual corpus per GPU, documents log-uniform 1-64 KiB"
+
+
+def workload_config(nbytes, ndocs, ntok):
+    """The same dictionary in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "bytes_per_gpu": int(nbytes), "docs_per_gpu": int(ndocs), "tokens_per_gpu": int(ntok),
+            "l2": "input (1 GiB) and output (~1.5 GiB) are far larger than the 126 MB L2; no flush needed"}
+
+
 def run_reference(args):
     """--impl reference: the reference's own algorithm on the host cores (oracle port: no JVM in this image)."""
     import numpy as np
@@ -172,21 +185,21 @@ def run_reference(args):
         return
     from jtokkit_b200 import synth
     dev = "cuda" if torch.cuda.is_available() else "cpu"
-    data, doc_off = synth.config3_multilingual(dev, total=REFERENCE_SAMPLE_BYTES)
+    data, doc_off = synth.config3_multilingual(dev, total=args.bytes)
     utf8, off = data.cpu().numpy(), doc_off.cpu().numpy()
     threads = os.cpu_count() or 1
     times, tokens, nbytes = [], 0, 0
     for step in range(args.warmup + args.steps):
-        tps, nbytes, tokens, dt, _, _, _ = cpu_port_throughput(utf8, off, REFERENCE_SAMPLE_BYTES, threads)
+        tps, nbytes, tokens, dt, _, _, _ = cpu_port_throughput(utf8, off, int(utf8.size), threads)
         if step >= args.warmup:
             times.append(dt)
     dt = sum(times) / len(times)
     value = tokens / dt
-    sample = "first %d bytes (%d tokens) of the 1 GiB synthetic multilingual corpus per step" % (nbytes, tokens)
+    sample = "the whole corpus of the CUDA arm's rank 0 per step: %d bytes, %d documents, %d tokens" % (nbytes, off.size - 1, tokens)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": "cl100k_base encode, 1 GiB synthetic multilingual corpus (documents 1-64 KiB)", "sample_bytes": nbytes},
+        "config": workload_config(nbytes, off.size - 1, tokens),
         "input_gb_per_s": nbytes / dt / 1e9,
         "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -199,7 +212,7 @@ def run_ours(args):
     import numpy as np
     import torch
     import jtokkit_b200 as jt
-    from jtokkit_b200 import synth
+    from jtokkit_b200 import sharding, synth
     rank, world, local = dist_setup(args.gpus)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the encode path has no CPU fallback")
@@ -208,6 +221,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     jt.EncodingFactory.devices = [local]
     enc = jt.EncodingFactory.cl100k_base()
+    # ranks that only wait (strong-scaling leg) must wait on the HOST: an NCCL barrier would spin on their GPU
+    host_group = torch.distributed.new_group(backend="gloo") if world > 1 else None
 
     # ---- workload: one 1 GiB corpus per GPU (different seed per rank)
     data, doc_off = synth.config3_multilingual(dev, total=args.bytes, seed=3003 + rank)
@@ -275,8 +290,48 @@ def run_ours(args):
     stats = torch.tensor([dev_ms, e2e_s, float(ntok), float(nbytes), float(launches), float(ndocs), float(sum(kernel_ms) / len(kernel_ms))],
                          dtype=torch.float64, device=dev)
     mx, sm = reduce_over_ranks(stats, world)
+
+    # ---- strong scaling: ONE corpus (rank 0's) through ONE handle that spans all N GPUs (jtk_encode_batch shards it in the library)
+    strong = None
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier(group=host_group)  # every rank's GPU is idle from here on
+    if rank == 0:
+        if all_cpus:
+            os.sched_setaffinity(0, all_cpus)
+        enc_all = enc if world == 1 else jt.Encoding(jt.EncodingFactory.predefined_params(jt.EncodingType.CL100K_BASE), devices=list(range(world)))
+        rs = None
+        for _ in range(2):
+            rs = enc_all.encode_packed(h_in_np, h_off_np, copy=False)
+            rs.close()
+        rs = None
+        kernel_ms_strong = 0.0
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            if rs is not None:
+                rs.close()
+            rs = enc_all.encode_packed(h_in_np, h_off_np, copy=False)
+            kernel_ms_strong += rs.device_ms
+        strong_s = (time.perf_counter() - t0) / args.steps
+        same = bool(np.array_equal(rs.ids, r.ids)) and bool(np.array_equal(rs.token_offsets, r.token_offsets)) and not rs.doc_status.any()
+        plan = sharding.plan_chunks(h_off_np, world)
+        strong = {"n_gpus": world, "api": "jtk_encode_batch on one handle over %d devices (in-library chunk sharding, no collective)" % world,
+                  "corpus": "rank 0's 1 GiB corpus (%d bytes, %d documents)" % (nbytes, ndocs), "chunks": int(plan.size - 1),
+                  "ms_per_step": strong_s * 1e3, "value": ntok / strong_s, "unit": "tokens/s", "input_gb_per_s": nbytes / strong_s / 1e9,
+                  "kernel_ms_per_step_max_over_devices": kernel_ms_strong / args.steps,
+                  "single_gpu_ms_per_step": e2e_s / args.steps * 1e3, "speedup_vs_single_gpu": e2e_s / args.steps / strong_s,
+                  "h2d_bytes_per_step": int(nbytes + 8 * (ndocs + 1)), "d2h_bytes_per_step": int(4 * ntok + 12 * (ndocs + 1)),
+                  "parity": "ids, token offsets and statuses identical to the single-device result" if same else "MISMATCH vs single device"}
+        rs.close()
+        if world > 1:
+            enc_all.close()
+    if world > 1:
+        torch.distributed.barrier(group=host_group)
     if rank != 0:
         return
+    if strong and strong["parity"].startswith("MISMATCH"):
+        print(json.dumps({"error": "multi-device result differs from the single-device result", "strong": strong}), flush=True)
+        raise SystemExit(3)
     dev_ms_max, e2e_s_max = float(mx[0]), float(mx[1])
     tokens_all, bytes_all, launches_all, ndocs_all = float(sm[2]), float(sm[3]), int(sm[4]), float(sm[5])
     value = tokens_all * args.steps / (dev_ms_max * 1e-3)
@@ -302,24 +357,28 @@ def run_ours(args):
             os.sched_setaffinity(0, all_cpus)
         threads = os.cpu_count() or 1
         probe = cpu_port_throughput(h_in_np, h_off_np, 8 << 20, threads)
-        sample_bytes = int(min(nbytes, max(16 << 20, probe[1] / probe[3] * 12.0)))
+        # the whole corpus when the host gets through it in ~30 s (16 cores: ~3 s), else a prefix of it
+        sample_bytes = int(min(nbytes, max(16 << 20, probe[1] / probe[3] * 30.0)))
         tps, sb, st, dt, o_ids, o_counts, nd = cpu_port_throughput(h_in_np, h_off_np, sample_bytes, threads)
+        whole = nd == ndocs
         cpu = {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
-               "sample": "first %d bytes / %d documents (%d tokens) of the same corpus, %.1f s, %.3f GB/s input" % (sb, nd, st, dt, sb / dt / 1e9)}
+               "sample": "%s: %d bytes / %d documents (%d tokens), %.1f s, %.3f GB/s input" %
+                         ("the whole corpus" if whole else "a prefix of the same corpus", sb, nd, st, dt, sb / dt / 1e9)}
         ok = bool(np.array_equal(o_counts[:nd], np.diff(r.token_offsets[:nd + 1])))
-        for d in range(0, nd, max(1, nd // 512)):
+        for d in range(nd):  # every document of the sample, id by id
+            if not ok:
+                break
             c = int(o_counts[d])
-            ok = ok and bool(np.array_equal(o_ids[h_off_np[d]:h_off_np[d] + c], r.ids[r.token_offsets[d]:r.token_offsets[d] + c]))
-        parity = "bit-exact vs oracle on the CPU-baseline sample (%d documents: all counts, every %dth document's ids)" % (nd, max(1, nd // 512)) \
+            ok = bool(np.array_equal(o_ids[h_off_np[d]:h_off_np[d] + c], r.ids[r.token_offsets[d]:r.token_offsets[d] + c]))
+        parity = "bit-exact vs oracle: counts and ids of %s (%d of %d documents, %d tokens)" % ("every document" if whole else "a prefix", nd, ndocs, st) \
             if ok else "MISMATCH vs oracle"
+        del o_ids
         tk = cpu_tiktoken_throughput(h_in_np, h_off_np, 64 << 20, threads)
 
     out = {
         "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": "cl100k_base encode (special-token guard on), 1 GiB synthetic multilingual corpus per GPU, documents log-uniform 1-64 KiB",
-                   "bytes_per_gpu": nbytes, "docs_per_gpu": ndocs, "tokens_per_gpu": ntok, "long_pieces": nlong,
-                   "l2": "input (1 GiB) and output (~1.5 GiB) are far larger than the 126 MB L2; no flush needed"},
+        "config": workload_config(nbytes, ndocs, ntok), "long_pieces": nlong,
         "input_gb_per_s": bytes_all * args.steps / (dev_ms_max * 1e-3) / 1e9,
         "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": int(nbytes + 8 * (ndocs + 1)),
                 "d2h_bytes_per_step": int(4 * ntok + 12 * (ndocs + 1)), "input_gb_per_s": bytes_all * args.steps / e2e_s_max / 1e9,
@@ -329,6 +388,7 @@ def run_ours(args):
                      "kernel": "jtk_split_lookup_kernel", "kernel_ms": kms, "launches_per_step": int(launches // args.steps),
                      "frac_whole_step": algo_bytes / (dev_ms / args.steps * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": int(algo_bytes), "peak_source": peak_src,
                      "frac_of_nominal_8000": achieved / 8000.0},
+        "strong": strong,
         "cpu_baseline": cpu,
         "cpu_tiktoken": tk,
         "parity": parity,
@@ -336,6 +396,8 @@ def run_ours(args):
         "host_cores": os.cpu_count(),
     }
     print(json.dumps(out), flush=True)
+    if parity is not None and parity.startswith("MISMATCH"):
+        raise SystemExit(3)  # a fast result that differs from the reference algorithm is not a result
 
 
 def main():

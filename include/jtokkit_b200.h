@@ -89,11 +89,21 @@ int jtk_encoding_num_devices(const jtk_encoding *enc);
 /*
  * The new batch entry point (the shape of the JMH harness' encodeAll(Encoding, List<String>),
  * benchmark/.../AbstractBenchmark.java:37).  Documents are the UTF-8 bytes utf8[doc_off[d] .. doc_off[d+1]),
- * doc_off[0] == 0.  HOST buffers; host<->device copies happen inside the call, documents are sharded over the
- * encoding's devices by byte-balanced contiguous ranges.  Replaces Encoding.encode / encodeOrdinary /
- * countTokens / countTokensOrdinary (api/Encoding.java:29,80,127,147) for a whole batch.
+ * doc_off[0] == 0.  HOST buffers; host<->device copies happen inside the call.  The batch is cut into byte-balanced
+ * contiguous document ranges ("chunks", jtk_plan_chunks); chunk c runs on device c % ndev on that device's own streams
+ * (like one task per document on the thread pool of AbstractMultiThreadedBenchmark.java:34-45, with a range of documents as
+ * the task and a GPU as the worker).  No collective: a chunk's token count is published when its kernels have run, the
+ * prefix over earlier chunks is its position in the one pinned result buffer, and its ids are copied there directly.
+ * Replaces Encoding.encode / encodeOrdinary / countTokens / countTokensOrdinary (api/Encoding.java:29,80,127,147) for a
+ * whole batch.
  */
 int jtk_encode_batch(jtk_encoding *enc, const uint8_t *utf8, const int64_t *doc_off, int64_t ndocs, uint32_t flags, jtk_result **out);
+
+/* The chunk plan jtk_encode_batch uses for `ndev` devices (pure host function, no device needed): cuts[0 .. n] with
+ * cuts[0] == 0 and cuts[n] == ndocs; chunk c = documents [cuts[c], cuts[c + 1]) runs on device c % ndev.  chunk_bytes <= 0
+ * selects the library default (64 MiB, JTK_CHUNK_MB).  Returns n, or the required capacity (> cuts_capacity - 1) without
+ * writing when `cuts` is too small, or JTK_E_ARG. */
+int64_t jtk_plan_chunks(const int64_t *doc_off, int64_t ndocs, int ndev, int64_t chunk_bytes, int64_t *cuts, int64_t cuts_capacity);
 
 /* Special-token ENCODING: every occurrence of a registered special token becomes its id, the text between occurrences is
  * encoded like encodeOrdinary.  NOT in the reference (README.md:46 lists it as not started; GptBytePairEncoding.java:52-56
@@ -124,7 +134,7 @@ typedef struct jtk_device_info {
 	int64_t num_long_pieces; /* pieces longer than the in-tile limit, handled by the long-piece kernels */
 	int64_t gpu_launches;
 	int32_t reserved;
-	float tile_kernel_ms; /* duration of the dominant kernel (jtk_encode_tiles_kernel) when JTK_TIME_KERNEL is set, else 0 */
+	float tile_kernel_ms; /* duration of the dominant kernel (jtk_split_lookup_kernel, summed over the sub-batches) when JTK_TIME_KERNEL is set, else 0 */
 } jtk_device_info;
 
 int jtk_encode_batch_device(jtk_encoding *enc, int device, const uint8_t *d_utf8, int64_t nbytes, const int64_t *d_doc_off, int64_t ndocs,
@@ -153,6 +163,11 @@ const int32_t *jtk_result_bad_ids(const jtk_result *r);      /* ndocs */
  * GptBytePairEncoding.java:42-45,66-69,79,90-100,110-119) for one text: full device encode, clip to
  * maxTokens, then the reference's back-off to a token prefix that decodes to a prefix of the text.
  * *ids is malloc'ed by the library (free with jtk_free); returns JTK_OK and *doc_status.
+ * Known divergence: the reference stops its find() loop once maxTokens tokens exist (:79), so text AFTER that point is never
+ * looked at; this call encodes the whole text, so *doc_status also reports JTK_DOC_UNKNOWN_BYTES (custom vocabularies
+ * without all 256 bytes) or JTK_DOC_PATTERN_STACK (general patterns) that stem from the unread tail, where the reference
+ * would return normally.  The predefined encodings cannot produce either status.  The returned ids are always the
+ * reference's.
  */
 int jtk_encode_max_tokens(jtk_encoding *enc, const uint8_t *utf8, int64_t nbytes, int32_t max_tokens, uint32_t flags, int32_t **ids,
                           int64_t *num_ids, int32_t *truncated, int32_t *doc_status);

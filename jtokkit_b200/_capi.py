@@ -35,6 +35,7 @@ SIGNATURES = {
     "jtk_encoding_name": (C.c_char_p, [vp]),
     "jtk_encoding_num_devices": (C.c_int, [vp]),
     "jtk_encode_batch": (C.c_int, [vp, vp, vp, i64, u32, C.POINTER(vp)]),
+    "jtk_plan_chunks": (i64, [vp, i64, C.c_int, i64, vp, i64]),
     "jtk_encode_batch_special": (C.c_int, [vp, vp, vp, i64, u32, C.POINTER(vp)]),
     "jtk_result_num_docs": (i64, [vp]),
     "jtk_result_num_tokens": (i64, [vp]),

@@ -5,6 +5,7 @@
  */
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -875,25 +876,68 @@ extern "C" void jtk_host_free(void *p) {
 }
 extern "C" void jtk_free(void *p) { free(p); }
 
-/* ------------------------------------------------------------------ the host-buffer batch */
-struct shard_job {
-	jtk_encoding *e;
-	jtk_device_state *ds;
-	const uint8_t *utf8;
-	const int64_t *doc_off;
-	int64_t d_begin, d_end; /* documents [d_begin, d_end) */
-	uint32_t flags;
-	/* outputs */
-	std::vector<int64_t> chunk_doc_begin, chunk_tokens;
-	jtk_pinned_buf ids;      /* this shard's ids */
-	int64_t ntokens = 0;
-	int64_t *tok_off_out;    /* points into the result's tok_off: entries d_begin .. d_end (shard-local, rebased later) */
-	int32_t *status_out;
+/* ------------------------------------------------------------------ the host-buffer batch
+ * One batch = one global list of CHUNKS (contiguous ranges of whole documents, byte balanced).  Chunk c runs on device c % G:
+ * every device takes every G-th chunk, so all devices walk through the batch side by side (the reference's
+ * AbstractMultiThreadedBenchmark.java:34-45 hands one document per task to a thread pool; here a task is a chunk of documents
+ * and a worker is a GPU).  There is no data-path collective and no host-side concatenation of ids: the token count of a
+ * chunk is published as soon as its kernels have run, the exclusive prefix over the chunks before it is the chunk's position
+ * in the ONE pinned result buffer, and the chunk's device-to-host copy lands there directly. */
+struct batch_ctx {
+	jtk_encoding *e = nullptr;
+	const uint8_t *utf8 = nullptr;
+	const int64_t *doc_off = nullptr;
+	uint32_t flags = 0;
+	int G = 1;
+	std::vector<int64_t> cb; /* chunk c = documents [cb[c], cb[c + 1]) */
+	/* result arrays (pinned) */
+	int32_t *ids = nullptr;
+	int64_t ids_cap = 0; /* tokens */
+	int64_t *tok_off = nullptr;
+	int32_t *status = nullptr;
+	/* token counts and result positions of the chunks */
+	std::mutex mu;
+	std::condition_variable cv;
+	std::vector<int64_t> ntok;  /* -1 = not known yet */
+	std::vector<int64_t> base;  /* nchunks + 1; valid up to index known */
+	size_t known = 0;           /* base[0 .. known] are final */
+	bool failed = false;
+	/* chunks that did not fit the result buffer (its size is an estimate): kept in buffers of their own, merged at the end */
+	std::vector<jtk_pinned_buf> spill;
+};
+
+struct device_job {
+	batch_ctx *B = nullptr;
+	jtk_device_state *ds = nullptr;
+	int g = 0;
 	double device_ms = 0;
 	int64_t launches = 0;
 	int rc = JTK_OK;
 	std::string err;
 };
+
+static void publish_chunk(batch_ctx *B, size_t c, int64_t ntok) {
+	std::lock_guard<std::mutex> lk(B->mu);
+	B->ntok[c] = ntok;
+	while (B->known < B->ntok.size() && B->ntok[B->known] >= 0) {
+		B->base[B->known + 1] = B->base[B->known] + B->ntok[B->known];
+		B->known++;
+	}
+	B->cv.notify_all();
+}
+static void fail_batch(batch_ctx *B) {
+	std::lock_guard<std::mutex> lk(B->mu);
+	B->failed = true;
+	B->cv.notify_all();
+}
+/* position of chunk c in the result: waits until every earlier chunk (on whichever device) has published its token count */
+static bool wait_base(batch_ctx *B, size_t c, int64_t *base) {
+	std::unique_lock<std::mutex> lk(B->mu);
+	B->cv.wait(lk, [&] { return B->failed || B->known >= c; });
+	if (B->known < c) return false;
+	*base = B->base[c];
+	return true;
+}
 
 /* output-side buffers of a workspace for a chunk of nbytes / ndocs (ids: at most one token per byte) */
 static int ensure_ws_io(jtk_workspace *w, int64_t nbytes, int64_t ndocs, bool want_ids) {
@@ -937,46 +981,68 @@ static int ensure_in_buf(jtk_in_buf *b, int64_t nbytes, int64_t ndocs) {
 	return JTK_OK;
 }
 
-/* One shard = one device.  Chunks of whole documents run through a three-stage pipeline on three streams
- * (copy-in, compute, copy-out) over NS workspaces: while chunk k is encoded, later chunks are copied in and the ids of
- * earlier chunks are copied out, so PCIe in both directions and the SMs are busy at the same time.  Stages are ordered by
- * events between the streams; the host only waits where it has to read a result (token counts, staged offsets). */
-static void run_shard(shard_job *job) {
-	jtk_encoding *e = job->e;
+/* Chunk boundaries of a batch for G devices: whole documents; the chunk size ramps up from 8 MiB to chunk_bytes wave by wave
+ * (a wave = one chunk per device) and back down towards the end of the batch, so that the exposed head (first copy-in + first
+ * compute) and tail (last compute + last copy-out) of each device's copy-in / compute / copy-out pipeline are short while the
+ * steady state moves large chunks. */
+static void plan_chunks(const int64_t *off, int64_t ndocs, int G, int64_t chunk_bytes, std::vector<int64_t> *cb) {
+	cb->assign(1, 0);
+	const int64_t small = std::min<int64_t>(chunk_bytes, 8ll << 20), end_byte = off[ndocs];
+	int64_t ramp = small, want = small;
+	while (cb->back() < ndocs) {
+		const int64_t d = cb->back();
+		if ((cb->size() - 1) % (size_t) G == 0) { /* a new wave: one size for all its chunks */
+			const int64_t remaining = end_byte - off[d];
+			want = std::max<int64_t>(small, std::min<int64_t>(std::min<int64_t>(ramp, chunk_bytes), remaining / (2 * (int64_t) G)));
+			ramp = std::min<int64_t>(ramp * 2, chunk_bytes);
+		}
+		const int64_t lim = off[d] + want;
+		int64_t hi = std::upper_bound(off + d + 1, off + ndocs + 1, lim) - off - 1; /* last doc end <= lim */
+		if (hi <= d) hi = d + 1;                                                     /* a single oversized document */
+		cb->push_back(hi);
+	}
+}
+
+extern "C" int64_t jtk_plan_chunks(const int64_t *doc_off, int64_t ndocs, int ndev, int64_t chunk_bytes, int64_t *cuts, int64_t cuts_capacity) {
+	if (!doc_off || ndocs < 0 || ndev < 1 || doc_off[0] != 0) return set_error(JTK_E_ARG, "jtk_plan_chunks: bad argument");
+	for (int64_t d = 0; d < ndocs; d++)
+		if (doc_off[d + 1] < doc_off[d]) return set_error(JTK_E_ARG, "doc_off is not monotone");
+	if (chunk_bytes <= 0) {
+		chunk_bytes = 64ll << 20;
+		if (const char *env = getenv("JTK_CHUNK_MB")) {
+			long mb = atol(env);
+			if (mb >= 1) chunk_bytes = (int64_t) mb << 20;
+		}
+	}
+	std::vector<int64_t> cb;
+	plan_chunks(doc_off, ndocs, ndev, chunk_bytes, &cb);
+	const int64_t n = (int64_t) cb.size() - 1;
+	if (cuts && cuts_capacity >= n + 1) memcpy(cuts, cb.data(), sizeof(int64_t) * cb.size());
+	return n;
+}
+
+/* One worker = one device.  Its chunks run through a three-stage pipeline on three streams (copy-in, compute, copy-out) over
+ * NS workspaces: while chunk k is encoded, later chunks are copied in and the ids of earlier chunks are copied out, so PCIe
+ * in both directions and the SMs are busy at the same time.  Stages are ordered by events between the streams; the host only
+ * waits where it has to read a result (token counts, staged offsets). */
+static void run_device(device_job *job) {
+	batch_ctx *B = job->B;
+	jtk_encoding *e = B->e;
 	jtk_device_state *ds = job->ds;
 	auto fail = [&](int rc) {
 		job->rc = rc;
 		job->err = g_last_error;
+		fail_batch(B);
 	};
 	if (cudaSetDevice(ds->device) != cudaSuccess) return fail(set_error(JTK_E_CUDA, "cudaSetDevice failed"));
-	const int64_t *off = job->doc_off;
-	const bool want_ids = !(job->flags & JTK_COUNT_ONLY);
-	/* chunk boundaries: whole documents, chunk sizes ramp up from 8 MiB to chunk_bytes and back down towards the end of the
-	 * shard, so that the exposed head (first copy-in + first compute) and tail (last compute + last copy-out) of the
-	 * copy-in / compute / copy-out pipeline are short while the steady state moves large chunks */
-	std::vector<int64_t> cb;
-	cb.push_back(job->d_begin);
-	{
-		const int64_t small = std::min<int64_t>(e->chunk_bytes, 8ll << 20), end_byte = off[job->d_end];
-		int64_t ramp = small;
-		while (cb.back() < job->d_end) {
-			int64_t d = cb.back();
-			const int64_t remaining = end_byte - off[d];
-			const int64_t want = std::max<int64_t>(small, std::min<int64_t>(std::min<int64_t>(ramp, e->chunk_bytes), remaining / 2));
-			const int64_t lim = off[d] + want;
-			int64_t hi = std::upper_bound(off + d + 1, off + job->d_end + 1, lim) - off - 1; /* last doc end <= lim */
-			if (hi <= d) hi = d + 1;                                                             /* a single oversized document */
-			cb.push_back(hi);
-			ramp *= 2;
-		}
-	}
-	const size_t nchunks = cb.size() - 1;
-	const int64_t shard_bytes = off[job->d_end] - off[job->d_begin];
-	if (want_ids) {
-		/* sized from the densest batch seen so far; the buffer grows if a shard needs more */
-		int rc = pinned_get(e, sizeof(int32_t) * (shard_bytes / 1024 * e->tokens_per_kib.load() + 4096), &job->ids);
-		if (rc != JTK_OK) return fail(rc);
-	}
+	const int64_t *off = B->doc_off;
+	const bool want_ids = !(B->flags & JTK_COUNT_ONLY);
+	/* this device's chunks: local index k <-> global chunk g + k * G */
+	const size_t nglobal = B->cb.size() - 1;
+	const size_t nchunks = nglobal > (size_t) job->g ? (nglobal - (size_t) job->g + (size_t) B->G - 1) / (size_t) B->G : 0;
+	if (nchunks == 0) return;
+	auto gc = [&](size_t k) { return (size_t) job->g + k * (size_t) B->G; };
+	const std::vector<int64_t> &cb = B->cb;
 	constexpr int NS = 3;
 	/* JTK_TRACE=1: per-chunk begin / end times of the three stages on stderr (development aid) */
 	static const bool trace = getenv("JTK_TRACE") != nullptr;
@@ -997,7 +1063,7 @@ static void run_shard(shard_job *job) {
 	cudaEvent_t ev_in[NR], ev_free[NR], ev_k0[NS], ev_k1[NS], ev_out[NS], ev_meta[NS];
 	jtk_pinned_buf stage_off[NS], stage_doc[NR];
 	jtk_device_info infos[NS];
-	int64_t out_chunk[NS]; /* chunk whose copy-out is in flight on the slot, -1 = none */
+	int64_t out_chunk[NS]; /* local chunk whose copy-out is in flight on the slot, -1 = none */
 	int64_t out_base[NS];
 	memset(infos, 0, sizeof(infos));
 	int rc = JTK_OK;
@@ -1029,27 +1095,29 @@ static void run_shard(shard_job *job) {
 		if (cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming) != cudaSuccess)
 			rc = set_error(JTK_E_CUDA, "cudaEventCreate failed");
 
-	/* the copy-out of a slot has landed: rebase its token offsets / statuses into the shard's arrays */
+	/* the copy-out of a slot has landed: rebase its token offsets / statuses into the result's arrays */
 	auto retire = [&](int slot) -> int {
 		if (out_chunk[slot] < 0) return JTK_OK;
 		CUDA_TRY(cudaEventSynchronize(ev_out[slot]));
-		const size_t k = (size_t) out_chunk[slot];
-		const int64_t d0 = cb[k], nd = cb[k + 1] - d0;
+		const size_t c = gc((size_t) out_chunk[slot]);
+		const int64_t d0 = cb[c], nd = cb[c + 1] - d0;
 		const int64_t *h_tok = static_cast<const int64_t *>(stage_off[slot].p);
 		const int32_t *h_st = reinterpret_cast<const int32_t *>(h_tok + nd + 1);
 		const int64_t base = out_base[slot];
 		for (int64_t i = 0; i < nd; i++) {
-			job->tok_off_out[d0 - job->d_begin + i] = h_tok[i] + base;
-			job->status_out[d0 - job->d_begin + i] = h_st[i];
+			B->tok_off[d0 + i] = h_tok[i] + base;
+			B->status[d0 + i] = h_st[i];
 		}
 		out_chunk[slot] = -1;
 		return JTK_OK;
 	};
-	/* chunk k has been encoded on its slot: read the totals, run the long-piece path if needed, start the copy-out */
+	/* local chunk k has been encoded on its slot: read the totals, run the long-piece path if needed, publish the token count,
+	 * wait for the chunk's position in the result, start the copy-out */
 	auto copy_out = [&](size_t k) -> int {
 		const int slot = (int) (k % NS);
+		const size_t c = gc(k);
 		jtk_workspace *w = ws[slot];
-		const int64_t d0 = cb[k], d1 = cb[k + 1], nd = d1 - d0;
+		const int64_t d0 = cb[c], d1 = cb[c + 1], nd = d1 - d0;
 		const int64_t cbytes = off[d1] - off[d0];
 		CUDA_TRY(cudaEventSynchronize(ev_k1[slot]));
 		float ms = 0;
@@ -1072,7 +1140,7 @@ static void run_shard(shard_job *job) {
 			a.ids_cap = w->in_cap;
 			a.tok_off = w->d_tok_off;
 			a.doc_status = w->d_status;
-			a.flags = job->flags;
+			a.flags = B->flags;
 			cudaEvent_t l0, l1;
 			cudaEventCreate(&l0);
 			cudaEventCreate(&l1);
@@ -1090,25 +1158,31 @@ static void run_shard(shard_job *job) {
 		CUDA_TRY(cudaEventRecord(ev_free[k % NR], s_comp)); /* the chunk's input buffer may be overwritten from here on */
 		job->launches += info.gpu_launches;
 		const int64_t ntok = info.num_tokens;
-		if (want_ids) {
-			if ((job->ntokens + ntok) * (int64_t) sizeof(int32_t) > job->ids.cap) {
-				/* rare: the shard is denser than anything seen before; finish the copies in flight, then move to a bigger buffer */
-				for (int i = 0; i < NS; i++) {
-					int r2 = retire(i);
-					if (r2 != JTK_OK) return r2;
-				}
-				CUDA_TRY(cudaStreamSynchronize(s_out));
-				jtk_pinned_buf bigger;
-				const int64_t done_bytes = std::max<int64_t>(off[d1] - off[job->d_begin], 1);
-				const int64_t projected = (job->ntokens + ntok) * shard_bytes / done_bytes; /* tokens if the rest is as dense */
-				int r2 = pinned_get(e, sizeof(int32_t) * (projected + projected / 8 + 4096), &bigger);
+		publish_chunk(B, c, ntok);
+		{
+			const int64_t per_kib = ntok * 1024 / std::max<int64_t>(cbytes, 1024) + 8;
+			int64_t cur = e->tokens_per_kib.load();
+			while (per_kib > cur && !e->tokens_per_kib.compare_exchange_weak(cur, per_kib)) {
+			}
+		}
+		int64_t base = 0;
+		if (!wait_base(B, c, &base)) return set_error(JTK_E_CUDA, "another device of the batch failed");
+		if (want_ids && ntok > 0) {
+			int32_t *dst = B->ids + base;
+			if (base + ntok > B->ids_cap) {
+				/* rare: the batch is denser than anything seen before and the result buffer (sized from the densest chunk so far) is
+				 * too small; this chunk and all later ones go to buffers of their own and are merged when the batch is done */
+				jtk_pinned_buf sp;
+				int r2 = pinned_get(e, sizeof(int32_t) * ntok, &sp);
 				if (r2 != JTK_OK) return r2;
-				memcpy(bigger.p, job->ids.p, (size_t) job->ntokens * 4);
-				pinned_put(e, job->ids);
-				job->ids = bigger;
+				{
+					std::lock_guard<std::mutex> lk(B->mu);
+					B->spill[c] = sp;
+				}
+				dst = static_cast<int32_t *>(sp.p);
 			}
 			mark(s_out);
-			CUDA_TRY(cudaMemcpyAsync(static_cast<int32_t *>(job->ids.p) + job->ntokens, w->d_ids, sizeof(int32_t) * (size_t) ntok, cudaMemcpyDeviceToHost, s_out));
+			CUDA_TRY(cudaMemcpyAsync(dst, w->d_ids, sizeof(int32_t) * (size_t) ntok, cudaMemcpyDeviceToHost, s_out));
 			mark(s_out);
 		}
 		{
@@ -1131,16 +1205,7 @@ static void run_shard(shard_job *job) {
 		CUDA_TRY(cudaStreamWaitEvent(s_out, ev_meta[slot], 0));
 		CUDA_TRY(cudaEventRecord(ev_out[slot], s_out));
 		out_chunk[slot] = (int64_t) k;
-		out_base[slot] = job->ntokens;
-		job->ntokens += ntok;
-		{
-			const int64_t per_kib = ntok * 1024 / std::max<int64_t>(cbytes, 1024) + 8;
-			int64_t cur = e->tokens_per_kib.load();
-			while (per_kib > cur && !e->tokens_per_kib.compare_exchange_weak(cur, per_kib)) {
-			}
-		}
-		job->tok_off_out[d1 - job->d_begin] = job->ntokens;
-		job->chunk_tokens.push_back(ntok);
+		out_base[slot] = base;
 		return JTK_OK;
 	};
 
@@ -1150,7 +1215,8 @@ static void run_shard(shard_job *job) {
 	 * allows, so the copy-in finishes early and leaves the PCIe link to the copy-out (measured, profiles/r1_pcie*.txt:
 	 * ~46 GB/s per direction while both are busy, ~56 GB/s alone). */
 	auto issue_in = [&](size_t j) -> int {
-		const int64_t d0 = cb[j], d1 = cb[j + 1], nd = d1 - d0;
+		const size_t c = gc(j);
+		const int64_t d0 = cb[c], d1 = cb[c + 1], nd = d1 - d0;
 		const int64_t b0 = off[d0], cbytes = off[d1] - b0;
 		jtk_in_buf *in = ring[j % NR];
 		if (j >= (size_t) NR) {
@@ -1174,7 +1240,7 @@ static void run_shard(shard_job *job) {
 		}
 		mark(s_in);
 		CUDA_TRY(cudaMemcpyAsync(in->d_doc, rebase, sizeof(int64_t) * (size_t) (nd + 1), cudaMemcpyHostToDevice, s_in));
-		if (cbytes > 0) CUDA_TRY(cudaMemcpyAsync(in->d_in, job->utf8 + b0, (size_t) cbytes, cudaMemcpyHostToDevice, s_in));
+		if (cbytes > 0) CUDA_TRY(cudaMemcpyAsync(in->d_in, B->utf8 + b0, (size_t) cbytes, cudaMemcpyHostToDevice, s_in));
 		mark(s_in);
 		CUDA_TRY(cudaEventRecord(ev_in[j % NR], s_in));
 		return JTK_OK;
@@ -1182,8 +1248,9 @@ static void run_shard(shard_job *job) {
 	size_t next_in = 0;
 	for (size_t k = 0; k < nchunks && rc == JTK_OK; k++) {
 		const int slot = (int) (k % NS);
+		const size_t c = gc(k);
 		jtk_workspace *w = ws[slot];
-		const int64_t d0 = cb[k], d1 = cb[k + 1], nd = d1 - d0;
+		const int64_t d0 = cb[c], d1 = cb[c + 1], nd = d1 - d0;
 		const int64_t cbytes = off[d1] - off[d0];
 		/* ev_free of chunk j - NR is recorded by copy_out(j - NR); at this point copy_out has been called for the chunks up to k - 2 */
 		while (rc == JTK_OK && next_in < nchunks && (next_in < (size_t) NR || next_in + 2 <= k + (size_t) NR)) rc = issue_in(next_in++);
@@ -1206,22 +1273,23 @@ static void run_shard(shard_job *job) {
 			break;
 		}
 		cudaEventRecord(ev_k0[slot], s_comp);
-		rc = encode_device_impl(e, ds, w, in->d_in, cbytes, in->d_doc, nd, job->flags, want_ids ? w->d_ids : nullptr, w->in_cap, w->d_tok_off, w->d_status,
+		rc = encode_device_impl(e, ds, w, in->d_in, cbytes, in->d_doc, nd, B->flags, want_ids ? w->d_ids : nullptr, w->in_cap, w->d_tok_off, w->d_status,
 		                        nullptr, s_comp, &infos[slot], false, memo);
 		cudaEventRecord(ev_k1[slot], s_comp);
 		if (rc != JTK_OK) break;
 		if (k >= 1) rc = copy_out(k - 1);
 	}
-	if (rc == JTK_OK && nchunks >= 1) rc = copy_out(nchunks - 1);
+	if (rc == JTK_OK) rc = copy_out(nchunks - 1);
 	for (int i = 0; i < NS && rc == JTK_OK; i++) rc = retire(i);
-	if (nchunks == 0) job->tok_off_out[0] = 0;
 	if (s_in) cudaStreamSynchronize(s_in);
 	if (s_comp) cudaStreamSynchronize(s_comp);
 	if (s_out) cudaStreamSynchronize(s_out);
 	if (s_meta) cudaStreamSynchronize(s_meta);
 	if (trace && tr0) {
 		/* marks come in pairs: per chunk one copy-in pair (in loop order) and, when ids are wanted, one copy-out pair */
-		std::string line = "jtk trace (ms since first copy-in):";
+		char head[64];
+		snprintf(head, sizeof(head), "jtk trace device %d (ms since first copy-in):", ds->device);
+		std::string line = head;
 		for (size_t i = 0; i + 1 < tr.size(); i += 2) {
 			float t0 = 0, t1 = 0;
 			cudaEventElapsedTime(&t0, tr0, tr[i]);
@@ -1265,99 +1333,88 @@ extern "C" int jtk_encode_batch(jtk_encoding *e, const uint8_t *utf8, const int6
 		if (doc_off[d + 1] < doc_off[d]) return set_error(JTK_E_ARG, "doc_off is not monotone");
 	const int64_t total = doc_off[ndocs];
 	if (total > 0 && !utf8) return set_error(JTK_E_ARG, "utf8 is null");
+	const bool want_ids = !(flags & JTK_COUNT_ONLY);
 	jtk_result *r = new jtk_result();
 	r->enc = e;
 	r->ndocs = ndocs;
 	int rc = pinned_get(e, sizeof(int64_t) * (ndocs + 1), &r->tok_off);
 	if (rc == JTK_OK) rc = pinned_get(e, sizeof(int32_t) * (ndocs + 1), &r->status);
+	/* the ids of all chunks land in one buffer, sized from the densest chunk seen so far (chunks that do not fit are kept aside) */
+	if (rc == JTK_OK && want_ids) rc = pinned_get(e, sizeof(int32_t) * (total / 1024 * e->tokens_per_kib.load() + 4096), &r->ids);
 	if (rc != JTK_OK) {
 		jtk_result_free(r);
 		return rc;
 	}
-	/* byte-balanced contiguous document ranges, one per device */
-	const int G = (int) e->devs.size();
-	std::vector<shard_job> jobs((size_t) G);
-	std::vector<int64_t> cut((size_t) G + 1, 0);
-	for (int g = 1; g < G; g++) {
-		const int64_t target = total / G * g;
-		cut[(size_t) g] = std::max<int64_t>(cut[(size_t) g - 1], std::lower_bound(doc_off, doc_off + ndocs + 1, target) - doc_off);
-		if (cut[(size_t) g] > ndocs) cut[(size_t) g] = ndocs;
+	batch_ctx B;
+	B.e = e;
+	B.utf8 = utf8;
+	B.doc_off = doc_off;
+	B.flags = flags;
+	B.G = (int) e->devs.size();
+	plan_chunks(doc_off, ndocs, B.G, e->chunk_bytes, &B.cb);
+	const size_t nchunks = B.cb.size() - 1;
+	B.ids = static_cast<int32_t *>(r->ids.p);
+	B.ids_cap = want_ids ? r->ids.cap / (int64_t) sizeof(int32_t) : 0;
+	B.tok_off = static_cast<int64_t *>(r->tok_off.p);
+	B.status = static_cast<int32_t *>(r->status.p);
+	B.ntok.assign(nchunks, -1);
+	B.base.assign(nchunks + 1, 0);
+	B.spill.assign(nchunks, jtk_pinned_buf());
+	std::vector<device_job> jobs((size_t) B.G);
+	for (int g = 0; g < B.G; g++) {
+		jobs[(size_t) g].B = &B;
+		jobs[(size_t) g].ds = e->devs[(size_t) g];
+		jobs[(size_t) g].g = g;
 	}
-	cut[(size_t) G] = ndocs;
-	std::vector<std::vector<int64_t>> shard_off((size_t) G);
-	std::vector<std::vector<int32_t>> shard_st((size_t) G);
-	for (int g = 0; g < G; g++) {
-		shard_job &j = jobs[(size_t) g];
-		j.e = e;
-		j.ds = e->devs[(size_t) g];
-		j.utf8 = utf8;
-		j.doc_off = doc_off;
-		j.d_begin = cut[(size_t) g];
-		j.d_end = cut[(size_t) g + 1];
-		j.flags = flags;
-		shard_off[(size_t) g].assign((size_t) (j.d_end - j.d_begin) + 1, 0);
-		shard_st[(size_t) g].assign((size_t) (j.d_end - j.d_begin) + 1, 0);
-		j.tok_off_out = shard_off[(size_t) g].data();
-		j.status_out = shard_st[(size_t) g].data();
-	}
-	if (G == 1) {
-		run_shard(&jobs[0]);
+	if (B.G == 1 || nchunks <= 1) {
+		run_device(&jobs[0]);
 	} else {
 		std::vector<std::thread> th;
-		for (int g = 0; g < G; g++) th.emplace_back(run_shard, &jobs[(size_t) g]);
+		for (int g = 0; g < B.G; g++) th.emplace_back(run_device, &jobs[(size_t) g]);
 		for (auto &t : th) t.join();
 	}
-	for (int g = 0; g < G; g++)
+	auto drop_spill = [&] {
+		for (jtk_pinned_buf &sp : B.spill) pinned_put(e, sp);
+	};
+	for (int g = 0; g < B.G; g++)
 		if (jobs[(size_t) g].rc != JTK_OK) {
 			rc = jobs[(size_t) g].rc;
 			std::string msg = jobs[(size_t) g].err;
-			for (int k = 0; k < G; k++) pinned_put(e, jobs[(size_t) k].ids);
+			drop_spill();
 			jtk_result_free(r);
 			return set_error(rc, msg);
 		}
-	/* the host only concatenates per-device arrays and rebases token offsets */
-	int64_t total_tokens = 0;
-	for (int g = 0; g < G; g++) total_tokens += jobs[(size_t) g].ntokens;
+	const int64_t total_tokens = B.base[nchunks];
 	r->ntokens = total_tokens;
-	int64_t *tok_off = static_cast<int64_t *>(r->tok_off.p);
-	int32_t *status = static_cast<int32_t *>(r->status.p);
-	int64_t base = 0;
-	for (int g = 0; g < G; g++) {
-		shard_job &j = jobs[(size_t) g];
-		const int64_t nd = j.d_end - j.d_begin;
-		for (int64_t i = 0; i < nd; i++) {
-			tok_off[j.d_begin + i] = j.tok_off_out[i] + base;
-			status[j.d_begin + i] = j.status_out[i];
-		}
-		base += j.ntokens;
-		r->device_ms = std::max(r->device_ms, j.device_ms);
-		r->launches += j.launches;
+	B.tok_off[ndocs] = total_tokens;
+	for (int g = 0; g < B.G; g++) {
+		r->device_ms = std::max(r->device_ms, jobs[(size_t) g].device_ms);
+		r->launches += jobs[(size_t) g].launches;
 	}
-	tok_off[ndocs] = total_tokens;
 	if ((flags & JTK_CHECK_SPECIAL) && e->host.special_has_empty) /* "".contains(...) is true for every text */
-		for (int64_t d = 0; d < ndocs; d++) status[d] |= JTK_DOC_HAS_SPECIAL;
-	if (!(flags & JTK_COUNT_ONLY)) {
-		if (G == 1) {
-			r->ids = jobs[0].ids;
-			jobs[0].ids.p = nullptr;
-		} else {
-			rc = pinned_get(e, sizeof(int32_t) * std::max<int64_t>(total_tokens, 1), &r->ids);
-			if (rc != JTK_OK) {
-				for (int k = 0; k < G; k++) pinned_put(e, jobs[(size_t) k].ids);
-				jtk_result_free(r);
-				return rc;
-			}
-			int64_t pos = 0;
-			for (int g = 0; g < G; g++) {
-				memcpy(static_cast<int32_t *>(r->ids.p) + pos, jobs[(size_t) g].ids.p, sizeof(int32_t) * (size_t) jobs[(size_t) g].ntokens);
-				pos += jobs[(size_t) g].ntokens;
-				pinned_put(e, jobs[(size_t) g].ids);
-			}
+		for (int64_t d = 0; d < ndocs; d++) B.status[d] |= JTK_DOC_HAS_SPECIAL;
+	if (want_ids && total_tokens > B.ids_cap) {
+		/* the size estimate was too low: one buffer of the right size, the part that did land plus the chunks kept aside */
+		jtk_pinned_buf full;
+		rc = pinned_get(e, sizeof(int32_t) * total_tokens, &full);
+		if (rc != JTK_OK) {
+			drop_spill();
+			jtk_result_free(r);
+			return rc;
 		}
+		int32_t *dst = static_cast<int32_t *>(full.p);
+		for (size_t c = 0; c < nchunks; c++) {
+			const int32_t *src = B.spill[c].p ? static_cast<const int32_t *>(B.spill[c].p) : B.ids + B.base[c];
+			memcpy(dst + B.base[c], src, sizeof(int32_t) * (size_t) B.ntok[c]);
+		}
+		pinned_put(e, r->ids);
+		r->ids = full;
 	}
+	drop_spill();
 	*out = r;
 	return JTK_OK;
 }
+
 
 extern "C" int64_t jtk_result_num_docs(const jtk_result *r) { return r ? r->ndocs : 0; }
 extern "C" int64_t jtk_result_num_tokens(const jtk_result *r) { return r ? r->ntokens : 0; }

@@ -65,3 +65,32 @@ def test_byte_balanced_cuts_edge_cases():
     assert sharding.byte_balanced_cuts(np.array([0], dtype=np.int64), 4).tolist() == [0, 0, 0, 0, 0]  # empty batch
     even = np.arange(0, 801, 100, dtype=np.int64)
     assert sharding.byte_balanced_cuts(even, 4).tolist() == [0, 2, 4, 6, 8]
+
+
+def test_chunk_plan_of_the_in_library_multi_gpu_batch():
+    """jtk_plan_chunks (pure host function of the C ABI): the plan jtk_encode_batch runs for G devices - contiguous, complete,
+    whole documents, chunk c on device c % G, devices byte balanced, a single device reduces to one ramped chunk list."""
+    from jtokkit_b200 import sharding
+    rng = np.random.default_rng(3)
+    lens = np.exp(rng.uniform(np.log(1024), np.log(65536), size=70000)).astype(np.int64)  # ~1 GiB of 1-64 KiB documents
+    off = np.zeros(lens.size + 1, dtype=np.int64)
+    off[1:] = np.cumsum(lens)
+    total = int(off[-1])
+    for G in (1, 2, 4, 8):
+        cuts = sharding.plan_chunks(off, G)
+        assert cuts[0] == 0 and cuts[-1] == lens.size and np.all(np.diff(cuts) > 0)
+        per_dev = np.zeros(G, dtype=np.int64)
+        sizes = off[cuts[1:]] - off[cuts[:-1]]
+        for c, sz in enumerate(sizes):
+            per_dev[sharding.device_of_chunk(c, G)] += sz
+        assert per_dev.sum() == total
+        assert per_dev.max() - per_dev.min() <= 0.03 * total / G + (8 << 20), (G, per_dev)
+        assert sizes.max() <= (64 << 20) + 65536 and sizes[0] <= (8 << 20) + 65536  # ramp from 8 MiB up to the 64 MiB default
+    # small chunk size, ragged documents, empty documents, an oversized document, an empty batch
+    off2 = np.array([0, 0, 10, 10, 5_000_000, 5_000_001, 5_000_001], dtype=np.int64)
+    cuts = sharding.plan_chunks(off2, 3, chunk_bytes=1 << 20)
+    assert cuts[0] == 0 and cuts[-1] == 6 and np.all(np.diff(cuts) > 0)
+    assert sharding.plan_chunks(np.array([0], dtype=np.int64), 4).tolist() == [0]
+    import pytest
+    with pytest.raises(ValueError):
+        sharding.plan_chunks(np.array([0, 5, 3], dtype=np.int64), 2)

@@ -117,3 +117,24 @@ def test_device_resident_call_and_properties_at_size():
     sample = list(range(0, offn.size - 1, 1999))
     back = enc.decode_bytes_batch([host.tokens(d) for d in sample])
     assert back == [raw[offn[d]:offn[d + 1]] for d in sample]
+
+
+def test_result_buffer_estimate_too_small_is_recovered(oracles):
+    """The one pinned result buffer of a batch is sized from the densest chunk seen so far (440 tokens per KiB on a fresh handle);
+    a batch with one token per byte overruns it: the chunks that do not fit are kept aside and merged at the end.  Same ids."""
+    import jtokkit_b200 as jt
+    doc = ("1 2 3 4 5 6 7 8 9 0 " * 3277)[:65536]
+    docs = [doc] * 64  # 4 MiB, ~4 M tokens
+    os.environ["JTK_CHUNK_MB"] = "1"
+    try:
+        enc = jt.EncodingFactory.cl100k_base()
+    finally:
+        del os.environ["JTK_CHUNK_MB"]
+    res = enc.encode_batch(docs)
+    exp = oracles["cl100k_base"].encode(doc)
+    assert len(exp) == 65536
+    assert res.ids.size == 64 * 65536 and np.array_equal(res.token_offsets, np.arange(65) * 65536)
+    for d in (0, 15, 16, 17, 40, 63):
+        assert res.tokens(d) == exp
+    again = enc.encode_batch(docs)  # the estimate has adapted: the direct path
+    assert np.array_equal(again.ids, res.ids)

@@ -27,6 +27,7 @@ import numpy as np
 from . import _capi
 
 DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+_LIVE_LOCK = threading.Lock()  # guards the per-encoding count of results that still own pinned buffers of the encoding
 
 
 # ----------------------------------------------------------------------------- enums (static tables of the reference)
@@ -188,7 +189,9 @@ class _ResultOwner:
         if self.handle is not None:
             h, self.handle = self.handle, None
             _capi.lib().jtk_result_free(h)
-            self.encoding = None
+            enc, self.encoding = self.encoding, None
+            if enc is not None:
+                enc._result_released()
 
     def __del__(self):
         try:
@@ -317,9 +320,25 @@ class Encoding:
         return self
 
     def close(self):
-        if getattr(self, "_h", None):
-            _capi.lib().jtk_encoding_destroy(self._h)
-            self._h = None
+        """Destroys the C handle.  Results that still view the encoding's pinned buffers keep it alive: the handle is destroyed
+        when the last of them has been released (jtk_encoding_destroy requires every jtk_result to be freed first)."""
+        with _LIVE_LOCK:
+            self._closing = True
+            if getattr(self, "_live", 0) > 0:
+                return
+            h, self._h = getattr(self, "_h", None), None
+        if h:
+            _capi.lib().jtk_encoding_destroy(h)
+
+    def _result_released(self):
+        with _LIVE_LOCK:
+            self._live = getattr(self, "_live", 0) - 1
+            destroy = getattr(self, "_closing", False) and self._live <= 0
+            h = getattr(self, "_h", None) if destroy else None
+            if destroy:
+                self._h = None
+        if h:
+            _capi.lib().jtk_encoding_destroy(h)
 
     def __del__(self):
         try:
@@ -353,6 +372,8 @@ class Encoding:
         _capi.check(call(self._h, _ptr(utf8), _ptr(doc_off), doc_off.size - 1, flags, C.byref(r)))
         L = _capi.lib()
         nd, nt = L.jtk_result_num_docs(r), L.jtk_result_num_tokens(r)
+        with _LIVE_LOCK:
+            self._live = getattr(self, "_live", 0) + 1
         owner = _ResultOwner(r, self)
         ids = None if count_only else _view(owner, L.jtk_result_ids(r), nt, "<i4", np.int32)
         tok_off = _view(owner, L.jtk_result_token_offsets(r), nd + 1, "<i8", np.int64)

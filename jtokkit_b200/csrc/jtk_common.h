@@ -57,14 +57,11 @@ enum {
 #define JTK_PSEUDO_BASE ((int32_t) 0x80000000)   /* id of a single byte that is not in the vocabulary: PSEUDO_BASE + byte */
 #define JTK_INLINE_KEY_MAX 24                    /* piece table A stores keys of up to 24 bytes inline */
 
-/* ---- tile geometry (overridable so that the host-side emulator in tests/ can use tiny tiles) ---------- */
+/* ---- tile geometry (overridable so that the host-side emulator in tests/ can use tiny tiles) ----------
+ * The region a CTA stages = back halo + tile + forward halo.  With the default numbers it is 511 chunks of 16 bytes plus one
+ * pad chunk = 512: one chunk per thread of a 512-thread CTA in the classification and split steps, no partial second round. */
 #ifndef JTK_TILE
-#define JTK_TILE 8192       /* bytes owned by one tile */
-#endif
-#ifndef JTK_NT
-/* threads per CTA of the split+lookup kernel: one per 16-byte chunk of the tile (measured: 608 threads = one per chunk of the
- * whole region, 3 CTAs per SM, saves the second round over the halo chunks but loses more through the lower occupancy) */
-#define JTK_NT (JTK_TILE / 16)
+#define JTK_TILE 7072       /* bytes owned by one tile (a multiple of 32) */
 #endif
 #ifndef JTK_BACK_HALO
 #define JTK_BACK_HALO 64    /* context bytes before the tile */
@@ -75,6 +72,10 @@ enum {
 #define JTK_FWD_HALO (JTK_LONG_PIECE + 16) /* a piece starting in the tile ends inside the halo or is long */
 #define JTK_REGION (JTK_BACK_HALO + JTK_TILE + JTK_FWD_HALO)
 #define JTK_REGION_CHUNKS (JTK_REGION / 16)
+#ifndef JTK_NT
+/* threads per CTA of the split+lookup kernel: one per 16-byte chunk of the region incl. the pad chunk, rounded up to warps */
+#define JTK_NT ((JTK_REGION_CHUNKS + 1 + 31) / 32 * 32)
+#endif
 #ifndef JTK_SHORT_PIECE
 #define JTK_SHORT_PIECE 64  /* thread-per-piece merge up to this length, lane groups above */
 #endif
@@ -83,11 +84,13 @@ enum {
 struct jtk_slot {
 	uint32_t x, y, z, w;
 };
-/* 32-byte slot of piece table A: 24 key bytes (zero padded), key length, rank; one slot per 32-byte sector */
+/* 32-byte slot of piece table A: 24 key bytes (zero padded), key length, rank; one slot per 32-byte sector.  The first 16 bytes
+ * hold everything a key of up to eight bytes needs (90 % of the pieces of English text): one 16-byte load, three compares. */
 struct alignas(16) jtk_slot_a {
-	uint32_t k[6];
-	uint32_t len; /* 0 = empty */
+	uint32_t k01[2]; /* key bytes 0..7 */
+	uint32_t len;    /* 0 = empty */
 	uint32_t rank;
+	uint32_t k25[4]; /* key bytes 8..23 */
 };
 
 /* Per-call piece memo (direct mapped): the tokens bytePairMerge produced for a short piece, so that later occurrences of
@@ -111,6 +114,10 @@ struct jtk_tables {
 	const uint8_t *ascii_cls;   /* 128 */
 	const uint16_t *cp_stage1;  /* 0x1100 */
 	const uint8_t *cp_stage2;   /* nblocks * 256 */
+	/* the same classes in the forms the tile kernel reads (jtk_classify_chunk) */
+	const uint32_t *lut_sp;     /* 256: class bits 0..3 of an ASCII byte in bits 0, 8, 16, 24; zero for bytes >= 0x80 */
+	const uint8_t *cls2;        /* 2048: class of the code points below U+0800 (everything a two-byte sequence can encode) */
+	const uint8_t *bmp_nib;     /* 32768: class of the code points below U+10000, two per byte (low nibble = even code point) */
 	/* whole-piece lookup (GptBytePairEncoding.java:81-83), keys <= 24 bytes inline */
 	const jtk_slot_a *tab_a;
 	uint32_t mask_a;            /* slot count - 1 (linear probing) */

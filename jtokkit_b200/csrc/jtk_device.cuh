@@ -16,12 +16,12 @@
 
 struct jtk_tile_ctx {
 	/* region arrays (shared memory on the device); region index r <-> global byte g0 + r */
-	uint8_t *sb;     /* JTK_REGION + 16 input bytes (zero padded) */
-	uint8_t *cls;    /* JTK_REGION + 16 class bytes */
+	uint8_t *sb;     /* JTK_REGION + 32 input bytes (zero padded) */
 	uint32_t *bmask; /* piece-start bits, (JTK_REGION + 32) / 32 + 1 words */
 	uint32_t *dmask; /* document-start bits, same size; the end of the input counts as a document start */
-	uint32_t *planes; /* per 16-byte chunk three words: bit planes 0 / 1, 2 / 3 of the class codes and continuation flag / byte high bit,
-	                   * sixteen positions each (written with the classes, read by the bit-parallel split rules) */
+	uint32_t *planes; /* per 16-byte chunk four words: bit planes 0 | 1 << 16 and 2 | 3 << 16 of the class codes, continuation-byte flags |
+	                   * byte high bits << 16 (sixteen positions each), one spare.  This is the ONLY product of the classification
+	                   * step: the bit-parallel split rules read the planes directly, the per-position rules through jtk_clsb */
 	int32_t *tok;    /* JTK_TILE + JTK_FWD_HALO token staging, indexed by r - JTK_BACK_HALO */
 	int32_t *rk;     /* same size: pair ranks during merging, then per-piece token counts */
 	/* geometry */
@@ -34,13 +34,21 @@ struct jtk_tile_ctx {
 	const int64_t *doc_off;
 	int64_t ndocs;
 	const jtk_tables *T;
-	const uint8_t *ascii_lut; /* T->ascii_cls or a shared-memory copy of it */
+	const uint32_t *lut_sp; /* T->lut_sp or a shared-memory copy of it */
+	const uint8_t *cls2;    /* T->cls2 or a shared-memory copy of it */
 };
 
 #define JTK_MASK_WORDS ((JTK_REGION + 32) / 32 + 1)
 
 JTK_HD bool jtk_docstart(const jtk_tile_ctx &c, int r) { return (c.dmask[r >> 5] >> (r & 31)) & 1u; }
-JTK_HD int jtk_cls(const jtk_tile_ctx &c, int r) { return c.cls[r] & JTK_CLS_MASK; }
+/* class code | JTK_CONT of region index r, read back from the chunk's bit planes */
+JTK_HD int jtk_clsb(const jtk_tile_ctx &c, int r) {
+	const uint32_t *o = c.planes + 4 * (r >> 4);
+	const int b = r & 15;
+	const uint32_t p01 = o[0] >> b, p23 = o[1] >> b, pc = o[2] >> b;
+	return (int) ((p01 & 1u) | ((p01 >> 15) & 2u) | ((p23 & 1u) << 2) | ((p23 >> 13) & 8u) | ((pc & 1u) << 7));
+}
+JTK_HD int jtk_cls(const jtk_tile_ctx &c, int r) { return jtk_clsb(c, r) & JTK_CLS_MASK; }
 
 #if defined(__CUDA_ARCH__)
 #define JTK_SMEM_OR(p, v) atomicOr((p), (v))
@@ -145,147 +153,112 @@ JTK_HD int jtk_decode_char(const jtk_tables &T, const uint8_t *s, int64_t p, int
 #define JTK_LDG(ptr) (*(ptr))
 #endif
 
-struct jtk_region_start {
-	const jtk_tile_ctx *c;
-	JTK_HD bool operator()(int64_t r) const { return jtk_docstart(*c, (int) r); }
-};
-
 /* bit b of each of the four bytes of w -> 4 mask bits */
 JTK_HD uint32_t jtk_plane4(uint32_t w, int b) { return (((w >> b) & 0x01010101u) * 0x01020408u) >> 24; }
 
-/* the chunk's bit planes from its four class words and four byte words (see jtk_tile_ctx::planes) */
-JTK_HD void jtk_store_planes(jtk_tile_ctx &c, int chunk, const uint32_t *cw, const uint32_t *bw) {
-	uint32_t p01 = 0, p23 = 0, pch = 0;
-	for (int k = 0; k < 4; k++) {
-		const uint32_t w = cw[k];
-		p01 |= (jtk_plane4(w, 0) | (jtk_plane4(w, 1) << 16)) << (4 * k);
-		p23 |= (jtk_plane4(w, 2) | (jtk_plane4(w, 3) << 16)) << (4 * k);
-		pch |= (jtk_plane4(w, 7) | (jtk_plane4(bw[k], 7) << 16)) << (4 * k);
-	}
-	uint32_t *o = c.planes + 3 * chunk;
-	o[0] = p01;
-	o[1] = p23;
-	o[2] = pch;
+/* result byte i = byte number (nibble i of sel) of the eight bytes {x, y} (the PRMT instruction on the device) */
+JTK_HD uint32_t jtk_byte_perm(uint32_t x, uint32_t y, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+	return __byte_perm(x, y, sel);
+#else
+	const uint64_t v = x | ((uint64_t) y << 32);
+	uint32_t r = 0;
+	for (int i = 0; i < 4; i++) r |= (uint32_t) ((v >> (8 * ((sel >> (4 * i)) & 7u))) & 0xFFu) << (8 * i);
+	return r;
+#endif
 }
 
-/* Fast classification of chunk `chunk`: sixteen ASCII bytes are sixteen table reads (a character cannot straddle into an
- * ASCII chunk).  Returns false when the chunk holds a non-ASCII byte. */
-JTK_HD bool jtk_classify_fast(jtk_tile_ctx &c, int chunk) {
+/* the 32-bit word that starts at byte address p (p + 3 readable, any alignment): two aligned loads and a funnel shift */
+JTK_HD uint32_t jtk_load_u32(const uint8_t *p) {
+	const uint32_t *aw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t) 3);
+	const int sh = (int) (reinterpret_cast<uintptr_t>(p) & 3) * 8;
+#if defined(__CUDA_ARCH__)
+	return __funnelshift_r(aw[0], aw[1], sh);
+#else
+	return sh ? (aw[0] >> sh) | (aw[1] << (32 - sh)) : aw[0];
+#endif
+}
+
+/* Classification of the 16 bytes of chunk `chunk` (region indices 16 * chunk ..) into the chunk's bit planes.
+ * Pass 1, every chunk: per byte one read of the 256-entry table lut_sp (the four class bits of an ASCII byte spread over the four
+ * bytes of a word, zero for bytes >= 0x80) accumulated with a shift by the byte's position - two accumulators of eight
+ * positions, two byte permutes turn them into the plane words.  Pass 2, chunks with non-ASCII bytes only: one loop iteration
+ * per multi-byte CHARACTER whose lead byte lies in the chunk or in the three bytes before it (a character may straddle the
+ * chunk boundary; the previous chunk's thread clips it, this one adds the rest): UTF-8 decoding from one unaligned word,
+ * class from a flat table (two-byte characters: 2 KiB table in shared memory; three-byte: 32 KiB nibble table; four-byte:
+ * the two-level table), planes updated with one multiply-add per plane word.  A lead byte whose continuation bytes are
+ * missing (or cut off by a document start) is a one-byte "other" character, as is a stray continuation byte (input from
+ * String.getBytes(UTF_8) never contains either). */
+JTK_HD void jtk_classify_chunk(jtk_tile_ctx &c, int chunk) {
 	const int r0 = chunk * 16;
 	const uint32_t *w = reinterpret_cast<const uint32_t *>(c.sb + r0);
 	const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
-	if (((w0 | w1 | w2 | w3) & 0x80808080u) != 0) return false;
-	uint32_t *o = reinterpret_cast<uint32_t *>(c.cls + r0);
-	const uint8_t *lut = c.ascii_lut;
-	uint32_t v[4];
-	v[0] = lut[w0 & 0xFF] | (lut[(w0 >> 8) & 0xFF] << 8) | (lut[(w0 >> 16) & 0xFF] << 16) | ((uint32_t) lut[w0 >> 24] << 24);
-	v[1] = lut[w1 & 0xFF] | (lut[(w1 >> 8) & 0xFF] << 8) | (lut[(w1 >> 16) & 0xFF] << 16) | ((uint32_t) lut[w1 >> 24] << 24);
-	v[2] = lut[w2 & 0xFF] | (lut[(w2 >> 8) & 0xFF] << 8) | (lut[(w2 >> 16) & 0xFF] << 16) | ((uint32_t) lut[w2 >> 24] << 24);
-	v[3] = lut[w3 & 0xFF] | (lut[(w3 >> 8) & 0xFF] << 8) | (lut[(w3 >> 16) & 0xFF] << 16) | ((uint32_t) lut[w3 >> 24] << 24);
-	o[0] = v[0];
-	o[1] = v[1];
-	o[2] = v[2];
-	o[3] = v[3];
-	jtk_store_planes(c, chunk, v, w);
-	return true;
-}
-
-/* Character whose lead byte is at region index r (UTF-8 decoding without loops; the staging buffer is padded, so the three
- * bytes after r are always readable).  dstart: document-start bits of region indices r + 1 .. r + 3 (bit 0 = r + 1).
- * Same result as jtk_decode_char. */
-JTK_HD int jtk_decode_char_fast(const jtk_tables &T, const uint8_t *sb, int r, uint32_t dstart, int *len) {
-	const uint32_t b0 = sb[r];
-	*len = 1;
-	if (b0 < 0xC0 || b0 >= 0xF8) return JTK_C_O; /* stray continuation byte or invalid lead (ASCII is handled by the caller) */
-	const uint32_t b1 = sb[r + 1], b2 = sb[r + 2], b3 = sb[r + 3];
-	const int n = b0 < 0xE0 ? 2 : b0 < 0xF0 ? 3 : 4;
-	const bool ok = (b1 & 0xC0) == 0x80 && (n < 3 || (b2 & 0xC0) == 0x80) && (n < 4 || (b3 & 0xC0) == 0x80) && (dstart & ((1u << (n - 1)) - 1u)) == 0;
-	if (!ok) return JTK_C_O;
-	const uint32_t cp = n == 2 ? ((b0 & 0x1F) << 6) | (b1 & 0x3F)
-	                  : n == 3 ? ((b0 & 0x0F) << 12) | ((b1 & 0x3F) << 6) | (b2 & 0x3F)
-	                           : ((b0 & 0x07) << 18) | ((b1 & 0x3F) << 12) | ((b2 & 0x3F) << 6) | (b3 & 0x3F);
-	*len = n;
-	return jtk_cp_class(T, cp);
-}
-
-/* General classification of the 16 bytes of chunk `chunk` (region indices 16*chunk ..) into c.cls: UTF-8 decoding. */
-JTK_HD void jtk_classify_generic(jtk_tile_ctx &c, int chunk) {
-	const jtk_tables &T = *c.T;
-	const int r0 = chunk * 16;
-	/* document-start bits of region indices r0 - 3 .. r0 + 28 (bit 3 = r0), one 64-bit extract */
-	uint32_t dwin;
-	{
-		const int lo = r0 - 3;
-		if (lo < 0) {
-			dwin = c.dmask[0] << 3;
-		} else {
-			const int wi = lo >> 5, sh = lo & 31;
-			dwin = c.dmask[wi] >> sh;
-			if (sh) dwin |= c.dmask[wi + 1] << (32 - sh);
-		}
-	}
-	int cur = JTK_C_O, rem = 0;
-	/* a character may have started in the previous chunk */
-	if ((c.sb[r0] & 0xC0) == 0x80 && !((dwin >> 3) & 1u)) {
-		for (int k = 1; k <= 3 && r0 - k >= c.rs; k++) {
-			const uint8_t b = c.sb[r0 - k];
-			if ((b & 0xC0) == 0x80) {
-				if ((dwin >> (3 - k)) & 1u) break;
-				continue;
+	const uint32_t *lut = c.lut_sp;
+#define JTK_SP(x, k) lut[((x) >> (8 * (k))) & 0xFFu]
+	const uint32_t lo = JTK_SP(w0, 0) + (JTK_SP(w0, 1) << 1) + (JTK_SP(w0, 2) << 2) + (JTK_SP(w0, 3) << 3) + (JTK_SP(w1, 0) << 4) + (JTK_SP(w1, 1) << 5) +
+	                    (JTK_SP(w1, 2) << 6) + (JTK_SP(w1, 3) << 7);
+	const uint32_t hi = JTK_SP(w2, 0) + (JTK_SP(w2, 1) << 1) + (JTK_SP(w2, 2) << 2) + (JTK_SP(w2, 3) << 3) + (JTK_SP(w3, 0) << 4) + (JTK_SP(w3, 1) << 5) +
+	                    (JTK_SP(w3, 2) << 6) + (JTK_SP(w3, 3) << 7);
+#undef JTK_SP
+	uint32_t p01 = jtk_byte_perm(lo, hi, 0x5140u), p23 = jtk_byte_perm(lo, hi, 0x7362u), pch = 0;
+	if (((w0 | w1 | w2 | w3) & 0x80808080u) != 0) {
+		const jtk_tables &T = *c.T;
+		const uint32_t HB = jtk_plane4(w0, 7) | (jtk_plane4(w1, 7) << 4) | (jtk_plane4(w2, 7) << 8) | (jtk_plane4(w3, 7) << 12);
+		/* lead bytes (>= 0xC0) of the window [r0 - 3, r0 + 16): bit j <-> region index r0 - 3 + j */
+		uint32_t L = (jtk_plane4(w0 & (w0 << 1), 7) | (jtk_plane4(w1 & (w1 << 1), 7) << 4) | (jtk_plane4(w2 & (w2 << 1), 7) << 8) | (jtk_plane4(w3 & (w3 << 1), 7) << 12)) << 3;
+		/* document-start bits of region indices r0 - 3 .. r0 + 28 (bit 3 = r0) */
+		uint32_t dwin;
+		{
+			const int lo3 = r0 - 3;
+			if (lo3 < 0) {
+				dwin = c.dmask[0] << 3;
+			} else {
+				const int wi = lo3 >> 5, sh = lo3 & 31;
+				dwin = c.dmask[wi] >> sh;
+				if (sh) dwin |= c.dmask[wi + 1] << (32 - sh);
 			}
-			int len;
-			const int cl = jtk_decode_char_fast(T, c.sb, r0 - k, dwin >> (4 - k), &len);
-			if (len > k) {
-				cur = cl;
-				rem = len - k;
-			}
-			break;
 		}
+		if (chunk > 0 && (w0 & 0xC0u) == 0x80u && !((dwin >> 3) & 1u)) {
+			/* the chunk begins inside a character: its lead byte is the closest lead byte among the three bytes before the chunk */
+			const uint32_t wp = w[-1];
+			const uint32_t lp = jtk_plane4(wp & (wp << 1), 7) >> 1;
+			if (lp) L |= 1u << (31 - jtk_clz(lp));
+		}
+		uint32_t cont = 0;
+		for (uint32_t m = L; m; m &= m - 1) {
+			const int j = jtk_ctz(m);
+			const uint32_t x = jtk_load_u32(c.sb + r0 - 3 + j);
+			const uint32_t b0 = x & 0xFFu;
+			if (b0 >= 0xF8u) continue; /* invalid lead: stays a one-byte "other" character */
+			const int n = b0 < 0xE0u ? 2 : b0 < 0xF0u ? 3 : 4;
+			if (j + n <= 3) continue;  /* a character of the previous chunk that ends before this one */
+			const uint32_t cm = (0x00C0C0C0u >> (8 * (4 - n))) << 8;
+			if ((x & cm) != (cm & 0x80808080u) || ((dwin >> (j + 1)) & ((1u << (n - 1)) - 1u)) != 0) continue;
+			uint32_t k;
+			if (n == 2) {
+				k = c.cls2[((x & 0x1Fu) << 6) | ((x >> 8) & 0x3Fu)];
+			} else if (n == 3) {
+				const uint32_t cp = ((x & 0x0Fu) << 12) | ((x >> 2) & 0xFC0u) | ((x >> 16) & 0x3Fu);
+				k = (JTK_LDG(T.bmp_nib + (cp >> 1)) >> ((cp & 1u) * 4)) & 0xFu;
+			} else {
+				k = (uint32_t) jtk_cp_class(T, ((x & 0x07u) << 18) | ((x << 4) & 0x3F000u) | ((x >> 10) & 0xFC0u) | ((x >> 24) & 0x3Fu));
+			}
+			const uint32_t mm = ((((1u << n) - 1u) << j) >> 3) & 0xFFFFu; /* the character's bytes inside this chunk */
+			p01 += ((k & 1u) | ((k & 2u) << 15)) * mm;
+			p23 += (((k >> 2) & 1u) | ((k & 8u) << 13)) * mm;
+			cont |= mm & ~((1u << j) >> 3);
+		}
+		pch = cont | (HB << 16);
 	}
-	/* ASCII bytes: four table reads per word like the fast path (non-ASCII bytes are masked to class 0 = "other", which is
-	 * also what stray continuation bytes and invalid leads are).  Then one iteration per multi-byte CHARACTER: its class
-	 * bytes (lead: class, continuation bytes: class | JTK_CONT) are OR-ed into the 128-bit result at its byte offset; what
-	 * sticks out beyond byte 15 belongs to the next chunk, which recomputes it with the look-back above. */
-	const uint32_t *w = reinterpret_cast<const uint32_t *>(c.sb + r0);
-	const uint8_t *lut = c.ascii_lut;
-	uint32_t o[4], leads = 0;
-	for (int k = 0; k < 4; k++) {
-		const uint32_t x = w[k], a7 = x & 0x7F7F7F7Fu;
-		const uint32_t v = lut[a7 & 0xFF] | (lut[(a7 >> 8) & 0xFF] << 8) | (lut[(a7 >> 16) & 0xFF] << 16) | ((uint32_t) lut[a7 >> 24] << 24);
-		o[k] = v & ~(((x & 0x80808080u) >> 7) * 0xFFu);
-		leads |= jtk_plane4(x & (x << 1), 7) << (4 * k); /* bytes >= 0xC0 */
-	}
-	uint64_t lo = o[0] | ((uint64_t) o[1] << 32), hi = o[2] | ((uint64_t) o[3] << 32);
-	if (rem > 0) lo |= ((uint32_t) (cur | JTK_CONT) * 0x010101u) & ((1u << (8 * rem)) - 1u); /* a character that started in the previous chunk */
-	for (uint32_t m = leads; m; m &= m - 1) {
+	uint32_t *o = c.planes + 4 * chunk;
 #if defined(__CUDA_ARCH__)
-		const int i = __ffs((int) m) - 1;
+	*reinterpret_cast<uint4 *>(o) = make_uint4(p01, p23, pch, 0u);
 #else
-		const int i = __builtin_ctz(m);
+	o[0] = p01;
+	o[1] = p23;
+	o[2] = pch;
+	o[3] = 0;
 #endif
-		int len;
-		const uint32_t k = (uint32_t) jtk_decode_char_fast(T, c.sb, r0 + i, dwin >> (4 + i), &len);
-		if (len == 1) continue; /* invalid: stays "other" */
-		uint32_t pat = (k * 0x01010101u) | 0x80808000u;
-		if (len < 4) pat &= (1u << (8 * len)) - 1u;
-		if (i < 8) {
-			lo |= (uint64_t) pat << (8 * i);
-			if (i > 4) hi |= (uint64_t) pat >> (8 * (8 - i));
-		} else {
-			hi |= (uint64_t) pat << (8 * (i - 8));
-		}
-	}
-	uint32_t *out = reinterpret_cast<uint32_t *>(c.cls + r0);
-	const uint32_t v[4] = {(uint32_t) lo, (uint32_t) (lo >> 32), (uint32_t) hi, (uint32_t) (hi >> 32)};
-	out[0] = v[0];
-	out[1] = v[1];
-	out[2] = v[2];
-	out[3] = v[3];
-	jtk_store_planes(c, chunk, v, w);
-}
-
-JTK_HD void jtk_classify_chunk(jtk_tile_ctx &c, int chunk) {
-	if (!jtk_classify_fast(c, chunk)) jtk_classify_generic(c, chunk);
 }
 
 /* ---------------------------------------------------------------------------------------------
@@ -363,12 +336,12 @@ JTK_HD int jtk_global_count_n_before(const jtk_tile_ctx &c, int64_t g) {
 /* lead index of the character that ends right before region index r (r > c.rs, no document start at r) */
 JTK_HD int jtk_prev_lead(const jtk_tile_ctx &c, int r) {
 	int p = r - 1;
-	while (p > c.rs && (c.cls[p] & JTK_CONT)) p--;
+	while (p > c.rs && (jtk_clsb(c, p) & JTK_CONT)) p--;
 	return p;
 }
 JTK_HD int jtk_char_len(const jtk_tile_ctx &c, int r) {
 	int len = 1;
-	while (len < 4 && (c.cls[r + len] & JTK_CONT)) len++;
+	while (len < 4 && (jtk_clsb(c, r + len) & JTK_CONT)) len++;
 	return len;
 }
 
@@ -645,8 +618,13 @@ JTK_HD bool jtk_boundary_fast(const jtk_tile_ctx &c, int chunk, uint32_t *out) {
 	/* the window [ws, ws + 32) = last eight positions of the previous chunk, this chunk, first eight of the next one */
 	jtk_planes pl;
 	{
-		const uint32_t *pp = c.planes + 3 * (chunk - 1);
-		const uint32_t a0 = pp[0], a1 = pp[1], a2 = pp[2], b0 = pp[3], b1 = pp[4], b2 = pp[5], c0 = pp[6], c1 = pp[7], c2 = pp[8];
+		const uint32_t *pp = c.planes + 4 * (chunk - 1);
+#if defined(__CUDA_ARCH__)
+		const uint4 qa = *reinterpret_cast<const uint4 *>(pp), qb = *reinterpret_cast<const uint4 *>(pp + 4), qc = *reinterpret_cast<const uint4 *>(pp + 8);
+		const uint32_t a0 = qa.x, a1 = qa.y, a2 = qa.z, b0 = qb.x, b1 = qb.y, b2 = qb.z, c0 = qc.x, c1 = qc.y, c2 = qc.z;
+#else
+		const uint32_t a0 = pp[0], a1 = pp[1], a2 = pp[2], b0 = pp[4], b1 = pp[5], b2 = pp[6], c0 = pp[8], c1 = pp[9], c2 = pp[10];
+#endif
 #define JTK_WIN_LO(a, b, c) ((((a) >> 8) & 0xFFu) | (((b) & 0xFFFFu) << 8) | (((c) & 0xFFu) << 24))
 #define JTK_WIN_HI(a, b, c) ((((a) >> 24) & 0xFFu) | (((b) >> 16) << 8) | ((((c) >> 16) & 0xFFu) << 24))
 		pl.P0 = JTK_WIN_LO(a0, b0, c0);
@@ -694,11 +672,11 @@ JTK_HD uint32_t jtk_boundary_generic(const jtk_tile_ctx &c, int chunk) {
 			bits |= 1u << i;
 			nrun = 0;
 			if (c.g0 + r >= c.total) break;
-			if (jtk_cls(c, r) == JTK_C_N && !(c.cls[r] & JTK_CONT)) nrun = 1;
+			if (jtk_clsb(c, r) == JTK_C_N) nrun = 1; /* class N on a lead byte */
 			continue;
 		}
 		if (c.g0 + r >= c.total) break;
-		const int cb = c.cls[r];
+		const int cb = jtk_clsb(c, r);
 		if (cb & JTK_CONT) continue;
 		const int cur = cb & JTK_CLS_MASK;
 		if (jtk_is_piece_start(c, r, cur, &nrun)) bits |= 1u << i;
@@ -762,7 +740,27 @@ JTK_HD int32_t jtk_lookup_a(const jtk_tables &T, const uint32_t *k, uint32_t len
 	for (;;) {
 		const jtk_slot_a s = T.tab_a[b]; /* 32 bytes, one sector: two 16-byte loads */
 		if (s.len == 0) return JTK_RANK_MAX;
-		if (s.len == len && s.k[0] == k[0] && s.k[1] == k[1] && s.k[2] == k[2] && s.k[3] == k[3] && s.k[4] == k[4] && s.k[5] == k[5]) return (int32_t) s.rank;
+		if (s.len == len && s.k01[0] == k[0] && s.k01[1] == k[1] && s.k25[0] == k[2] && s.k25[1] == k[3] && s.k25[2] == k[4] && s.k25[3] == k[5]) return (int32_t) s.rank;
+		b = (b + 1) & T.mask_a;
+	}
+}
+
+/* whole-piece lookup for keys of 1..8 bytes (k0, k1 zero padded): the first half of a slot holds everything */
+JTK_HD uint32_t jtk_hash6_short(uint32_t k0, uint32_t k1, uint32_t len) {
+	const uint32_t k[6] = {k0, k1, 0u, 0u, 0u, 0u}; /* the four zero words fold into constants */
+	return jtk_hash6(k, len);
+}
+JTK_HD int32_t jtk_lookup_a8(const jtk_tables &T, uint32_t k0, uint32_t k1, uint32_t len, uint32_t h) {
+	uint32_t b = h & T.mask_a;
+	for (;;) {
+#if defined(__CUDA_ARCH__)
+		const uint4 s = JTK_LDG(reinterpret_cast<const uint4 *>(T.tab_a + b));
+		const uint32_t s0 = s.x, s1 = s.y, sl = s.z, sr = s.w;
+#else
+		const uint32_t s0 = T.tab_a[b].k01[0], s1 = T.tab_a[b].k01[1], sl = T.tab_a[b].len, sr = T.tab_a[b].rank;
+#endif
+		if (sl == 0) return JTK_RANK_MAX;
+		if (sl == len && s0 == k0 && s1 == k1) return (int32_t) sr;
 		b = (b + 1) & T.mask_a;
 	}
 }

@@ -27,10 +27,6 @@
 #include "jtk_device.cuh"
 #include "jtk_regex.h"
 
-#ifndef JTK_DEFER_SLOW
-#define JTK_DEFER_SLOW 0 /* 1: process chunks that miss the ASCII fast paths in a dense second pass (measured slower: it serialises the slow chunks behind a barrier) */
-#endif
-
 namespace {
 
 constexpr int NT = JTK_NT;
@@ -39,7 +35,6 @@ constexpr int RECN = JTK_RECN;
 constexpr int QCAP = JTK_QCAP;
 constexpr int BH = JTK_BACK_HALO;
 constexpr int TC = JTK_TILE / 16;  /* 16-byte chunks per tile */
-constexpr int CPT = 1;             /* chunks per thread in the piece-listing step (threads >= TC have none) */
 static_assert(TC <= NT && NT % 32 == 0 && NT <= 1024, "one thread per tile chunk at least");
 
 /* piece records: a token id, or (id space is limited to >= JTK_REC_MIN_ID at registration) a payload */
@@ -50,9 +45,7 @@ __device__ __forceinline__ bool rec_is_id(int32_t r) { return r >= JTK_REC_MIN_I
 __device__ __forceinline__ int32_t rec_make(int s, int m) { return REC_BASE + (int32_t) (((uint32_t) s << 11) | (uint32_t) (m - 1)); }
 __device__ __forceinline__ uint32_t rec_payload(int32_t r) { return (uint32_t) (r - REC_BASE); }
 
-/* indices into the small shared "misc" array */
-enum { M_TILE = 0, M_NSLOW, M_RS, M_CARRY, M_HITS, M_NDEFER, M_SLOWTOK, M_WSUM = 16, M_HIST = 48 /* .. M_HIST + JTK_SHORT_PIECE */, M_WORDS = 128 };
-static_assert(M_HIST + JTK_SHORT_PIECE + 1 <= M_WORDS, "misc too small");
+
 
 /* first set bit in [from, limit] of a bit array, or -1 */
 __device__ __forceinline__ int next_bit(const uint32_t *bm, int from, int limit) {
@@ -228,31 +221,240 @@ __device__ int merge_group(const jtk_tables &T, const uint8_t *p, int n, int32_t
 
 /* ---------------------------------------------------------------------------------------------
  * kernel 1: split + whole-piece lookup
+ *
+ * Persistent CTAs of JTK_NT threads take tiles by ticket.  The region of a tile (back halo + tile + forward halo, 8 192 bytes)
+ * is staged by ONE bulk asynchronous copy (cp.async.bulk global -> shared, completion on an mbarrier); the region of the
+ * NEXT tile is requested before the current one is processed (two staging buffers), so the copy runs under the compute and
+ * no thread spends instructions on staging.  Per tile:
+ *   P1  mark document starts (bit mask), wait for the bytes
+ *   P2  one 16-byte chunk per thread: code point classes -> bit planes (jtk_classify_chunk); special-token first-byte test
+ *   P3  one chunk per thread: split rules over the planes -> piece-start bits
+ *   P4a piece starts listed in order (popcount + block scan)
+ *   P4b one piece per thread: pieces of up to 8 bytes probe the first half of their table slot (one 16-byte load); longer
+ *       pieces, misses and everything unusual go to a short deferred list, which a second, dense pass resolves (full-key
+ *       probe, long keys, memo, queues for the merge kernels): the rare paths no longer run inside every warp.
  * ------------------------------------------------------------------------------------------- */
+constexpr int SB_BYTES = JTK_REGION + 32;                 /* one staging buffer: region + pad chunk + 16 zero bytes */
+constexpr int COPY_BYTES = JTK_REGION + 16;               /* what the bulk copy covers in the interior of the input */
+constexpr int PLANE_BYTES = 16 * (JTK_REGION_CHUNKS + 2); /* four plane words per chunk */
+constexpr int PLIST_BYTES = ((2 * JTK_TILE > PLANE_BYTES ? 2 * JTK_TILE : PLANE_BYTES) + 15) / 16 * 16; /* plist reuses the planes' memory after P3 */
+constexpr int DEFCAP = 2048;                              /* deferred pieces per tile held in shared memory (more are resolved in place) */
+static_assert(SB_BYTES % 16 == 0 && COPY_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+static_assert(JTK_REGION_CHUNKS + 1 <= NT, "one thread per region chunk");
+
+/* indices into the small shared "misc" array */
+enum { M_NSLOW = 0, M_HITS, M_SLOWTOK, M_NDEF, M_CARRY, M_TICKET /* 2 */, M_WSUM = 16, M_HIST = 48 /* .. M_HIST + JTK_SHORT_PIECE */, M_WORDS = 128 };
+static_assert(M_HIST + JTK_SHORT_PIECE + 1 <= M_WORDS, "misc too small");
+
+constexpr int SPLIT_SMEM_BYTES = 2 * SB_BYTES + PLIST_BYTES + 2 * 4 * JTK_MASK_WORDS + 4 * ((TC + 3) / 4 * 4) + 4 * M_WORDS + 1024 + 2048 + 2 * DEFCAP + 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "WAIT_LOOP:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	    "@p bra WAIT_DONE;\n"
+	    "bra WAIT_LOOP;\n"
+	    "WAIT_DONE:\n"
+	    "}\n" ::"r"(smem_u32(bar)),
+	    "r"(parity)
+	    : "memory");
+}
+/* one bulk asynchronous copy global -> shared; src, dst and bytes are multiples of 16; completion is counted on `bar` */
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+	             "r"(smem_u32(bar))
+	             : "memory");
+}
+
+/* the part of tile `tile`'s region that consists of whole 16-byte chunks inside the input: [*lo, *hi) in region bytes */
+__device__ __forceinline__ void region_copy_range(int64_t tile, int64_t total, int *lo, int *hi) {
+	const int64_t g0 = tile * (int64_t) JTK_TILE - BH;
+	*lo = g0 < 0 ? (int) -g0 : 0;
+	const int64_t avail = (total & ~(int64_t) 15) - g0; /* end of the last whole chunk of the input, in region bytes */
+	*hi = avail >= COPY_BYTES ? COPY_BYTES : (avail > *lo ? (int) avail : *lo);
+}
+
+/* dynamic shared memory of the split+lookup kernel: fixed offsets, so that every device function can address it */
+extern __shared__ __align__(128) uint8_t jtk_dyn_smem[];
+constexpr int OFF_SB = 0;                                  /* two staging buffers */
+constexpr int OFF_PLANES = OFF_SB + 2 * SB_BYTES;          /* planes, later the piece list */
+constexpr int OFF_BMASK = OFF_PLANES + PLIST_BYTES;
+constexpr int OFF_DMASK = OFF_BMASK + 4 * JTK_MASK_WORDS;
+constexpr int OFF_CPREF = OFF_DMASK + 4 * JTK_MASK_WORDS;  /* pieces before each 16-byte chunk of the tile */
+constexpr int OFF_MISC = OFF_CPREF + 4 * ((TC + 3) / 4 * 4);
+constexpr int OFF_LUT = OFF_MISC + 4 * M_WORDS;
+constexpr int OFF_CLS2 = OFF_LUT + 1024;
+constexpr int OFF_DEF = OFF_CLS2 + 2048;
+constexpr int OFF_MBAR = OFF_DEF + 2 * DEFCAP;
+static_assert(OFF_MBAR + 16 == SPLIT_SMEM_BYTES && OFF_MBAR % 8 == 0 && OFF_PLANES % 16 == 0 && OFF_BMASK % 16 == 0, "shared memory layout");
+struct split_smem {
+	__device__ __forceinline__ uint8_t *sb(int i) const { return jtk_dyn_smem + OFF_SB + i * SB_BYTES; }
+	__device__ __forceinline__ uint32_t *planes() const { return reinterpret_cast<uint32_t *>(jtk_dyn_smem + OFF_PLANES); }
+	__device__ __forceinline__ uint16_t *plist() const { return reinterpret_cast<uint16_t *>(jtk_dyn_smem + OFF_PLANES); }
+	__device__ __forceinline__ uint32_t *bmask() const { return reinterpret_cast<uint32_t *>(jtk_dyn_smem + OFF_BMASK); }
+	__device__ __forceinline__ uint32_t *dmask() const { return reinterpret_cast<uint32_t *>(jtk_dyn_smem + OFF_DMASK); }
+	__device__ __forceinline__ uint32_t *chunk_pref() const { return reinterpret_cast<uint32_t *>(jtk_dyn_smem + OFF_CPREF); }
+	__device__ __forceinline__ uint32_t *misc() const { return reinterpret_cast<uint32_t *>(jtk_dyn_smem + OFF_MISC); }
+	__device__ __forceinline__ uint32_t *lut_sp() const { return reinterpret_cast<uint32_t *>(jtk_dyn_smem + OFF_LUT); }
+	__device__ __forceinline__ uint8_t *cls2() const { return jtk_dyn_smem + OFF_CLS2; }
+	__device__ __forceinline__ uint16_t *deflist() const { return reinterpret_cast<uint16_t *>(jtk_dyn_smem + OFF_DEF); }
+	__device__ __forceinline__ uint64_t *mbar() const { return reinterpret_cast<uint64_t *>(jtk_dyn_smem + OFF_MBAR); }
+};
+
+/* The unusual pieces of a tile (pass 2 of P4b): longer than eight bytes, not a token as a whole, longer than the in-tile limit. */
+template <bool GENERAL>
+__device__ __noinline__ int split_slow_piece(const jtk_encode_args &a, const uint8_t *sb, int q, int npieces, long long lt, int64_t tb) {
+	const jtk_tables &T = a.T;
+	const split_smem S;
+	int hits = 0;
+	const int r = S.plist()[q];
+	const int s = r - BH;
+	int e = (q + 1 < npieces) ? (int) S.plist()[q + 1] : next_bit(S.bmask(), r + 1, r + JTK_LONG_PIECE);
+	if (e >= 0 && e - r > JTK_LONG_PIECE) e = -1;
+	int32_t out;
+	if (e < 0) { /* longer than JTK_LONG_PIECE: deferred to the long-piece kernels */
+		const unsigned idx = atomicAdd(&a.hdr->n_long, 1u);
+		if ((int64_t) idx < a.long_cap) {
+			jtk_long_piece lp;
+			lp.start = tb + s;
+			const int e2 = next_bit(S.bmask(), r + 1, JTK_REGION - 1);
+			lp.end = e2 < 0 ? -1 : (tb - BH) + e2;
+			lp.insert_at = 0; /* set by the gather kernel */
+			lp.count = 0;
+			lp.scratch = 0;
+			lp.doc = 0;
+			lp.flags = 0;
+			a.long_list[idx] = lp;
+		}
+		out = REC_BASE + (int32_t) (REC_LONG | (idx & 0x0FFFFFFFu));
+	} else {
+		const int n = e - r;
+		const uint8_t *p = sb + r;
+		uint32_t key[6] = {0, 0, 0, 0, 0, 0};
+		uint32_t h = 0;
+		if (n <= JTK_INLINE_KEY_MAX) { /* (pieces of up to eight bytes come here after a miss of the short probe, or as the tile's last piece) */
+			jtk_build_key(p, n, key);
+			h = jtk_hash6(key, (uint32_t) n);
+			out = jtk_lookup_a(T, key, (uint32_t) n, h);
+			if (out != JTK_RANK_MAX) {
+				hits++;
+			} else if (n == 1) { /* a byte that is not in the vocabulary (TokenEncoder.java:64-71) */
+				flag_doc(a, tb + s, JTK_DOC_UNKNOWN_BYTES);
+				out = JTK_REC_MIN_ID; /* the document is in error; keep the record a plain id */
+				hits++;
+			}
+		} else {
+			out = n > T.max_token_len ? JTK_RANK_MAX : jtk_lookup_long(T, p, n);
+			if (out != JTK_RANK_MAX) hits++;
+		}
+		if (out == JTK_RANK_MAX) {
+			out = rec_make(s, n);
+			bool memo_hit = false;
+			if (n <= JTK_MEMO_MAX_PIECE && n >= 2 && a.memo) { /* has this call merged the same piece before? */
+				const jtk_memo_entry *me = a.memo + ((h * 0x9E3779B1u) >> 8 & a.memo_mask);
+				/* entries are written by the merge kernel of EARLIER sub-batches of this call (stream ordered, never while this
+				 * kernel runs: the two-lane pipeline runs without a memo) */
+				const uint4 *mp = reinterpret_cast<const uint4 *>(me);
+				const uint4 q0 = mp[0], q1 = mp[1];
+				const bool cand = q1.x == ((a.memo_epoch << 8) | 2u) && (q1.y & 0xFFu) == (uint32_t) n;
+				if (cand && q0.x == key[0] && q0.y == key[1] && q0.z == key[2] && q0.w == key[3]) {
+					const int cnt = (int) (q1.y >> 8);
+					const int off = (int) atomicAdd(&S.misc()[M_SLOWTOK], (uint32_t) cnt); /* dense area of the tile's slowtok slice */
+					int32_t *stok = a.slowtok + lt * (long long) RECN + off;
+					if (!(a.flags & JTK_COUNT_ONLY)) {
+						stok[0] = (int32_t) q1.z;
+						if (cnt > 1) stok[1] = (int32_t) q1.w;
+						for (int k = 2; k < cnt; k++) stok[k] = me->tok[k];
+					}
+					out = rec_make(off, cnt);
+					hits += cnt;
+					memo_hit = true;
+				}
+			}
+			if (memo_hit) {
+			} else if (n <= JTK_SHORT_PIECE) {
+				a.slowq[lt * (long long) QCAP + atomicAdd(&S.misc()[M_NSLOW], 1u)] = (uint16_t) q;
+				atomicAdd(&S.misc()[M_HIST + n], 1u);
+			} else if (n <= JTK_GROUP8_PIECE) a.med8[atomicAdd(&a.sub->n_med8, 1u)] = ((uint32_t) lt << 14) | (uint32_t) q;
+			else a.med32[atomicAdd(&a.sub->n_med32, 1u)] = ((uint32_t) lt << 14) | (uint32_t) q;
+		}
+	}
+	(a.rec + lt * (long long) RECN)[q] = out;
+	return hits;
+}
+
 template <bool GENERAL>
 __global__ void __launch_bounds__(JTK_NT, 2048 / JTK_NT) jtk_split_lookup_kernel(const __grid_constant__ jtk_encode_args a) {
-	extern __shared__ __align__(16) uint8_t smem[];
-	uint8_t *sb = smem;
-	uint8_t *cls = sb + (JTK_REGION + 16);
-	uint32_t *bmask = reinterpret_cast<uint32_t *>(cls + (JTK_REGION + 16));
-	uint32_t *dmask = bmask + JTK_MASK_WORDS;
-	uint16_t *plist = reinterpret_cast<uint16_t *>(dmask + JTK_MASK_WORDS); /* region index of every piece start, in order */
-	uint32_t *chunk_pref = reinterpret_cast<uint32_t *>(plist + RECN);      /* pieces before each 16-byte chunk */
-	uint32_t *misc = chunk_pref + TC;
-	uint8_t *s_ascii = reinterpret_cast<uint8_t *>(misc + M_WORDS); /* ASCII class table, 128 bytes */
-	uint32_t *planes = reinterpret_cast<uint32_t *>(s_ascii + 128); /* three words of bit planes per chunk (jtk_tile_ctx::planes) */
+	const split_smem L;
+	struct {
+		uint8_t *sb[2];
+		uint32_t *planes, *bmask, *dmask, *chunk_pref, *lut_sp;
+		uint16_t *plist, *deflist;
+		uint8_t *cls2;
+		uint64_t *mbar;
+	} S;
+	S.sb[0] = L.sb(0);
+	S.sb[1] = L.sb(1);
+	S.planes = L.planes();
+	S.plist = L.plist(); /* region index of every piece start, in order (written after the planes' last use) */
+	S.bmask = L.bmask();
+	S.dmask = L.dmask();
+	S.chunk_pref = L.chunk_pref();
+	S.lut_sp = L.lut_sp();
+	S.cls2 = L.cls2();
+	S.deflist = L.deflist();
+	S.mbar = L.mbar();
+	uint32_t *const misc = L.misc();
 
 	const int tid = threadIdx.x;
-	const int lane = tid & 31;
+	const int lane = tid & 31, warp = tid >> 5;
 	const jtk_tables &T = a.T;
-	if (tid < 128) s_ascii[tid] = T.ascii_cls[tid];
+
+	/* ---- once per CTA: tables, zeroed masks and pads, barriers, the first two tickets ---- */
+	for (int i = tid; i < 256; i += NT) S.lut_sp[i] = T.lut_sp[i];
+	for (int i = tid; i < 512; i += NT) reinterpret_cast<uint32_t *>(S.cls2)[i] = reinterpret_cast<const uint32_t *>(T.cls2)[i];
+	for (int w = tid; w < 2 * JTK_MASK_WORDS; w += NT) S.bmask[w] = 0; /* bmask and dmask */
+	if (tid < M_WORDS) misc[tid] = 0;
+	if (tid < 8) { /* the 16 bytes after what the copies cover stay zero for good */
+		reinterpret_cast<uint32_t *>(S.sb[tid >> 2] + COPY_BYTES)[tid & 3] = 0;
+	}
+	if (tid == 0) {
+		mbar_init(&S.mbar[0], 1);
+		mbar_init(&S.mbar[1], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	const int64_t ntiles_sub = a.tile_end - a.tile_begin;
+	auto issue = [&](int64_t lt_next, int buf) { /* one thread: request the region of sub-batch tile lt_next into staging buffer buf */
+		int lo, hi;
+		region_copy_range(a.tile_begin + lt_next, a.total, &lo, &hi);
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* the buffer was last touched by ordinary loads / stores */
+		mbar_expect_tx(&S.mbar[buf], (uint32_t) (hi - lo));
+		if (hi > lo) bulk_load(S.sb[buf] + lo, a.bytes + ((a.tile_begin + lt_next) * (int64_t) JTK_TILE - BH) + lo, (uint32_t) (hi - lo), &S.mbar[buf]);
+	};
+	if (tid == 0) {
+		const unsigned t0 = atomicAdd(&a.sub->ticket, 1u);
+		if ((int64_t) t0 < ntiles_sub) issue((int64_t) t0, 0);
+		misc[M_TICKET] = t0;
+		misc[M_TICKET + 1] = atomicAdd(&a.sub->ticket, 1u);
+	}
+	__syncthreads();
+	int64_t cur = misc[M_TICKET], nxt = misc[M_TICKET + 1];
+	__syncthreads(); /* the ticket slots are rewritten inside the loop */
 
 	jtk_tile_ctx c;
-	c.sb = sb;
-	c.cls = cls;
-	c.bmask = bmask;
-	c.dmask = dmask;
-	c.planes = planes;
+	c.bmask = S.bmask;
+	c.dmask = S.dmask;
+	c.planes = S.planes;
 	c.tok = nullptr;
 	c.rk = nullptr;
 	c.total = a.total;
@@ -260,31 +462,26 @@ __global__ void __launch_bounds__(JTK_NT, 2048 / JTK_NT) jtk_split_lookup_kernel
 	c.doc_off = a.doc_off;
 	c.ndocs = a.ndocs;
 	c.T = &T;
-	c.ascii_lut = s_ascii;
+	c.lut_sp = S.lut_sp;
+	c.cls2 = S.cls2;
 	/* the special-token guard only has to look at bytes that can start a special token */
 	const bool check_special = (a.flags & JTK_CHECK_SPECIAL) && T.nspecial > 0;
 
-	for (;;) {
-		/* ---- P0: take a tile ---- */
-		__syncthreads();
-		if (tid == 0) {
-			misc[M_TILE] = atomicAdd(&a.sub->ticket, 1u);
-			misc[M_NSLOW] = 0;
-			misc[M_HITS] = 0;
-			misc[M_NDEFER] = 0;
-			misc[M_SLOWTOK] = 0;
-		}
-		if (tid <= JTK_SHORT_PIECE) misc[M_HIST + tid] = 0;
-		__syncthreads();
-		const long long tile = a.tile_begin + (long long) misc[M_TILE];
-		if (tile >= a.tile_end) break;
-		const long long lt = tile - a.tile_begin; /* index into the per-sub-batch buffers */
+	for (int it = 0; cur < ntiles_sub; it++) {
+		const int buf = it & 1;
+		const long long lt = cur; /* index into the per-sub-batch buffers */
+		const long long tile = a.tile_begin + lt;
 		const int64_t tb = tile * (int64_t) JTK_TILE;
+		uint8_t *const sb = S.sb[buf];
+		c.sb = sb;
 		c.g0 = tb - BH;
 		c.rs = 0;
 		c.carry_n = 0;
+		/* ---- P0: request the next tile's bytes (its buffer was released by the barrier that ended the previous tile), take a ticket ---- */
+		if (tid == 0 && nxt < ntiles_sub) issue(nxt, buf ^ 1);
+		if (tid == NT - 32) misc[M_TICKET + buf] = atomicAdd(&a.sub->ticket, 1u);
 
-		/* ---- P1: stage bytes (16-byte loads), clear masks, mark document starts ---- */
+		/* ---- P1: document starts; the bytes the bulk copy does not cover (start / end of the input); wait for the copy ---- */
 		const int64_t first_doc = a.tile_first_doc[tile];
 		if (GENERAL) {
 			/* general pattern: the piece bits were computed by the jtk_general_* kernels; dmask holds the gap bits */
@@ -292,71 +489,46 @@ __global__ void __launch_bounds__(JTK_NT, 2048 / JTK_NT) jtk_split_lookup_kernel
 			for (int w = tid; w < JTK_MASK_WORDS; w += NT) {
 				const int64_t gw = w0 + w;
 				const bool in = gw >= 0 && gw < a.rx_words;
-				bmask[w] = in ? a.rx_start[gw] : 0u;
-				dmask[w] = in ? a.rx_skip[gw] : 0u;
+				S.bmask[w] = in ? a.rx_start[gw] : 0u;
+				S.dmask[w] = in ? a.rx_skip[gw] : 0u;
 			}
-			for (int ch = tid; ch <= JTK_REGION_CHUNKS; ch += NT) jtk_load_chunk(c, ch);
-			__syncthreads();
 		} else {
-		for (int w = tid; w < JTK_MASK_WORDS; w += NT) {
-			bmask[w] = 0;
-			dmask[w] = 0;
+			jtk_mark_docstarts(c, first_doc, tid, NT);
 		}
-		for (int ch = tid; ch <= JTK_REGION_CHUNKS; ch += NT) jtk_load_chunk(c, ch);
-		__syncthreads();
-		jtk_mark_docstarts(c, first_doc, tid, NT);
-		__syncthreads();
-		if (tid == 0) misc[M_RS] = (uint32_t) jtk_region_first(c);
-		__syncthreads();
-		c.rs = (int) misc[M_RS];
-
-		/* ---- P2: code point classes.  Chunks the ASCII fast path cannot take are collected and then processed densely,
-		 * one per thread, so that a single non-ASCII chunk does not drag its whole warp through the slow path ---- */
-#if JTK_DEFER_SLOW
-		for (int ch = tid; ch <= JTK_REGION_CHUNKS; ch += NT)
-			if (!jtk_classify_fast(c, ch)) plist[atomicAdd(&misc[M_NDEFER], 1u)] = (uint16_t) ch;
-		__syncthreads();
-		for (int i = tid; i < (int) misc[M_NDEFER]; i += NT) jtk_classify_generic(c, plist[i]);
-#else
-		for (int ch = tid; ch <= JTK_REGION_CHUNKS; ch += NT) jtk_classify_chunk(c, ch);
-#endif
-		__syncthreads();
-		if (tid == 0) {
-			misc[M_CARRY] = (uint32_t) jtk_region_carry_n(c);
-			misc[M_NDEFER] = 0;
-		}
-		__syncthreads();
-		c.carry_n = (int) misc[M_CARRY];
-
-		/* ---- P3: split rules -> piece-start bits (same two-step scheme); special-token guard ---- */
-#if JTK_DEFER_SLOW
-		for (int ch = BH / 16 + tid; ch < JTK_REGION_CHUNKS; ch += NT) {
-			uint32_t bits;
-			if (jtk_boundary_fast(c, ch, &bits)) reinterpret_cast<uint16_t *>(bmask)[ch] = (uint16_t) bits;
-			else plist[atomicAdd(&misc[M_NDEFER], 1u)] = (uint16_t) ch;
-		}
-		__syncthreads();
-		for (int i = tid; i < (int) misc[M_NDEFER]; i += NT) {
-			const int ch = plist[i];
-			reinterpret_cast<uint16_t *>(bmask)[ch] = (uint16_t) jtk_boundary_generic(c, ch);
-		}
-#else
-		for (int ch = BH / 16 + tid; ch < JTK_REGION_CHUNKS; ch += NT) reinterpret_cast<uint16_t *>(bmask)[ch] = (uint16_t) jtk_boundary_chunk(c, ch);
-#endif
-		} /* !GENERAL */
-		if (check_special) {
-			for (int ch = tid; ch < TC; ch += NT) {
-				const int r0 = BH + ch * 16;
-				if (T.special_first_single) { /* one candidate first byte (built-ins: '<'): SWAR "has byte" test on the 16 bytes */
-					const uint32_t *w = reinterpret_cast<const uint32_t *>(sb + r0);
-					const uint32_t pat = T.special_first_single * 0x01010101u;
-					uint32_t any = 0;
+		{
+			int lo, hi;
+			region_copy_range(tile, a.total, &lo, &hi);
+			if (lo > 0 || hi < COPY_BYTES) { /* first / last tiles only */
+				for (int i = tid; i < COPY_BYTES / 4; i += NT) {
+					const int r = 4 * i;
+					if (r >= lo && r < hi) continue;
+					uint32_t v = 0;
 					for (int k = 0; k < 4; k++) {
-						const uint32_t x = w[k] ^ pat;
-						any |= (x - 0x01010101u) & ~x & 0x80808080u;
+						const int64_t g = c.g0 + r + k;
+						if (g >= 0 && g < a.total) v |= (uint32_t) a.bytes[g] << (8 * k);
 					}
-					if (!any) continue;
+					reinterpret_cast<uint32_t *>(sb)[i] = v;
 				}
+			}
+		}
+		mbar_wait(&S.mbar[buf], (uint32_t) (it >> 1) & 1u);
+		__syncthreads();
+
+		if (!GENERAL) {
+			c.rs = jtk_region_first(c);
+			/* ---- P2: code point classes -> bit planes, one chunk per thread ---- */
+			if (tid <= JTK_REGION_CHUNKS) jtk_classify_chunk(c, tid);
+		}
+		if (check_special && tid >= BH / 16 && tid < BH / 16 + TC) {
+			const int r0 = tid * 16;
+			bool look = true;
+			if (T.special_first_single) { /* one candidate first byte (built-ins: '<'): SWAR "has byte" test on the 16 bytes */
+				const uint4 w = *reinterpret_cast<const uint4 *>(sb + r0);
+				const uint32_t pat = T.special_first_single * 0x01010101u;
+				const uint32_t x0 = w.x ^ pat, x1 = w.y ^ pat, x2 = w.z ^ pat, x3 = w.w ^ pat;
+				look = ((((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1) | ((x2 - 0x01010101u) & ~x2) | ((x3 - 0x01010101u) & ~x3)) & 0x80808080u) != 0;
+			}
+			if (look)
 				for (int i = 0; i < 16; i++) {
 					const int64_t g = c.g0 + r0 + i;
 					if (g >= a.total) break;
@@ -365,133 +537,133 @@ __global__ void __launch_bounds__(JTK_NT, 2048 / JTK_NT) jtk_split_lookup_kernel
 						if (jtk_special_at(T, a.bytes, g, jtk_doc_ceil(c, g))) flag_doc(a, g, JTK_DOC_HAS_SPECIAL);
 					}
 				}
+		}
+		if (!GENERAL) {
+			__syncthreads();
+			/* \p{N} carry into the region: needed only when the region starts inside a digit run (the same answer in every thread) */
+			if (T.pattern_kind == JTK_PAT_CL100K && !jtk_docstart(c, c.rs) && c.g0 + c.rs > 0 && jtk_clsb(c, c.rs) == JTK_C_N) {
+				if (tid == 0) misc[M_CARRY] = (uint32_t) jtk_global_count_n_before(c, c.g0 + c.rs);
+				__syncthreads();
+				c.carry_n = (int) misc[M_CARRY];
+			}
+			/* ---- P3: split rules -> piece-start bits ---- */
+			{
+				const int ch = BH / 16 + tid;
+				if (ch < JTK_REGION_CHUNKS) reinterpret_cast<uint16_t *>(S.bmask)[ch] = (uint16_t) jtk_boundary_chunk(c, ch);
 			}
 		}
 		__syncthreads();
 
-		/* ---- P4a: list the piece starts of the tile in order (thread owns CPT consecutive chunks) ---- */
-		uint32_t bits[CPT];
-		int mycount = 0;
-		for (int j = 0; j < CPT; j++) {
-			const int ch = tid * CPT + j;
+		/* ---- P4a: list the piece starts of the tile in order (thread owns one chunk) ---- */
+		uint32_t bits;
+		int mycount;
+		{
+			const int ch = tid;
 			const int64_t gbase = tb + ch * 16;
-			uint32_t m = ch < TC ? reinterpret_cast<const uint16_t *>(bmask)[BH / 16 + ch] : 0u;
+			uint32_t m = ch < TC ? reinterpret_cast<const uint16_t *>(S.bmask)[BH / 16 + ch] : 0u;
 			if (gbase >= a.total) m = 0;
 			else if (gbase + 16 > a.total) m &= (1u << (int) (a.total - gbase)) - 1u;
-			bits[j] = m;
-			mycount += __popc(m);
+			bits = m;
+			mycount = __popc(m);
 			if (a.piece_flags && ch < TC) {
-				const uint32_t real = GENERAL ? m & ~(uint32_t) reinterpret_cast<const uint16_t *>(dmask)[BH / 16 + ch] : m; /* gaps are not pieces */
+				const uint32_t real = GENERAL ? m & ~(uint32_t) reinterpret_cast<const uint16_t *>(S.dmask)[BH / 16 + ch] : m; /* gaps are not pieces */
 				for (int i = 0; i < 16 && gbase + i < a.total; i++) a.piece_flags[gbase + i] = (real >> i) & 1u;
 			}
 		}
-		int npieces;
-		int base = block_exclusive_scan<NT>(mycount, reinterpret_cast<int *>(misc + M_WSUM), &npieces);
-		for (int j = 0; j < CPT; j++) {
-			const int ch = tid * CPT + j;
-			if (ch < TC) chunk_pref[ch] = (uint32_t) base;
-			for (uint32_t m = bits[j]; m;) {
-				const int i = __ffs((int) m) - 1;
-				m &= m - 1;
-				plist[base++] = (uint16_t) (BH + ch * 16 + i);
+		int npieces, base;
+		{
+			/* block-wide exclusive scan with one barrier: warp scan, warp totals to shared memory, every warp scans the totals itself */
+			int x = mycount;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const int y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+				if (lane >= o) x += y;
 			}
+			if (lane == 31) misc[M_WSUM + warp] = (uint32_t) x;
+			__syncthreads();
+			int ws = lane < NWARPS ? (int) misc[M_WSUM + lane] : 0;
+#pragma unroll
+			for (int o = 1; o < NWARPS; o <<= 1) {
+				const int y = __shfl_up_sync(0xFFFFFFFFu, ws, o);
+				if (lane >= o) ws += y;
+			}
+			npieces = __shfl_sync(0xFFFFFFFFu, ws, NWARPS - 1);
+			const int before = __shfl_sync(0xFFFFFFFFu, ws, warp > 0 ? warp - 1 : 0);
+			base = x - mycount + (warp > 0 ? before : 0);
+		}
+		/* the planes are no longer needed: their memory becomes the piece list; the document-start bits are cleared for the next tile */
+		if (!GENERAL)
+			for (int w = tid; w < JTK_MASK_WORDS; w += NT) S.dmask[w] = 0;
+		if (tid < TC) S.chunk_pref[tid] = (uint32_t) base;
+		for (uint32_t m = bits; m;) {
+			const int i = __ffs((int) m) - 1;
+			m &= m - 1;
+			S.plist[base++] = (uint16_t) (BH + tid * 16 + i);
 		}
 		if (tid == 0) {
 			/* first piece start of the tile (the end of the input counts), for the long-piece bounds kernel */
-			const int fb = next_bit(bmask, BH, BH + JTK_TILE - 1);
+			const int fb = next_bit(S.bmask, BH, BH + JTK_TILE - 1);
 			a.tile_first_b[tile] = fb < 0 ? -1 : c.g0 + fb;
 			a.npieces[tile] = npieces;
 		}
 		__syncthreads();
 
-		/* ---- P4b: one piece per thread: whole-piece lookup (GptBytePairEncoding.java:81-83) ---- */
+		/* ---- P4b pass 1: one piece per thread; keys of up to eight bytes probe the first half of their slot
+		 * (whole-piece fast path, GptBytePairEncoding.java:81-83), everything else is deferred ---- */
 		int32_t *rec = a.rec + lt * (long long) RECN;
 		int hits = 0;
 		for (int q0 = 0; q0 < npieces; q0 += NT) {
 			const int q = q0 + tid;
+			bool defer = false;
 			if (q < npieces) {
-				const int r = plist[q];
-				const int s = r - BH;
-				int e = (q + 1 < npieces) ? (int) plist[q + 1] : next_bit(bmask, r + 1, r + JTK_LONG_PIECE);
-				if (e >= 0 && e - r > JTK_LONG_PIECE) e = -1;
-				int32_t out;
-				if (GENERAL && ((dmask[r >> 5] >> (r & 31)) & 1u)) {
-					out = REC_BASE + (int32_t) REC_SKIP;
-				} else if (e < 0) { /* longer than JTK_LONG_PIECE: deferred to the long-piece kernels */
-					const unsigned idx = atomicAdd(&a.hdr->n_long, 1u);
-					if ((int64_t) idx < a.long_cap) {
-						jtk_long_piece lp;
-						lp.start = tb + s;
-						const int e2 = next_bit(bmask, r + 1, JTK_REGION - 1);
-						lp.end = e2 < 0 ? -1 : c.g0 + e2;
-						lp.insert_at = 0; /* set by the gather kernel */
-						lp.count = 0;
-						lp.scratch = 0;
-						lp.doc = 0;
-						lp.flags = 0;
-						a.long_list[idx] = lp;
+				const int r = S.plist[q];
+				const int e = (q + 1 < npieces) ? (int) S.plist[q + 1] : -1; /* the tile's last piece ends in the halo: deferred */
+				const int n = e - r;
+				if (GENERAL && ((S.dmask[r >> 5] >> (r & 31)) & 1u)) {
+					rec[q] = REC_BASE + (int32_t) REC_SKIP;
+				} else if ((unsigned) (n - 1) < 8u) {
+					const uint32_t *aw = reinterpret_cast<const uint32_t *>(sb + (r & ~3));
+					const int sh = (r & 3) * 8;
+					const uint32_t a0 = aw[0], a1 = aw[1], a2 = aw[2];
+					uint32_t k0 = __funnelshift_r(a0, a1, sh), k1 = __funnelshift_r(a1, a2, sh);
+					const uint32_t keep = 0xFFFFFFFFu >> ((32 - 8 * n) & 31); /* n = 4 or 8: all four bytes */
+					if (n <= 4) {
+						k0 &= keep;
+						k1 = 0;
+					} else {
+						k1 &= keep;
 					}
-					out = REC_BASE + (int32_t) (REC_LONG | (idx & 0x0FFFFFFFu));
-				} else {
-					const int n = e - r;
-					const uint8_t *p = sb + r;
-					if (n == 1) {
-						out = T.byte_id[p[0]];
-						if (out < JTK_PSEUDO_BASE + 256) {
-							flag_doc(a, tb + s, JTK_DOC_UNKNOWN_BYTES);
-							out = JTK_REC_MIN_ID; /* the document is in error; keep the record a plain id */
-						}
+					const int32_t out = jtk_lookup_a8(T, k0, k1, (uint32_t) n, jtk_hash6_short(k0, k1, (uint32_t) n));
+					if (out != JTK_RANK_MAX) {
+						rec[q] = out;
 						hits++;
 					} else {
-						uint32_t key[6];
-						uint32_t h = 0;
-						if (n <= JTK_INLINE_KEY_MAX) {
-							jtk_build_key(p, n, key);
-							h = jtk_hash6(key, (uint32_t) n);
-							out = jtk_lookup_a(T, key, (uint32_t) n, h);
-						} else {
-							out = n > T.max_token_len ? JTK_RANK_MAX : jtk_lookup_long(T, p, n);
-						}
-						if (out != JTK_RANK_MAX) {
-							hits++;
-						} else {
-							out = rec_make(s, n);
-							bool memo_hit = false;
-							if (n <= JTK_MEMO_MAX_PIECE && a.memo) { /* has this call merged the same piece before? */
-								const jtk_memo_entry *me = a.memo + ((h * 0x9E3779B1u) >> 8 & a.memo_mask);
-								/* entries are written by the merge kernel of EARLIER sub-batches of this call (stream ordered, never while this
-								 * kernel runs: the two-lane pipeline runs without a memo) */
-								const uint4 *mp = reinterpret_cast<const uint4 *>(me);
-								const uint4 q0 = mp[0], q1 = mp[1];
-								const bool cand = q1.x == ((a.memo_epoch << 8) | 2u) && (q1.y & 0xFFu) == (uint32_t) n;
-								if (cand && q0.x == key[0] && q0.y == key[1] && q0.z == key[2] && q0.w == key[3]) {
-									const int cnt = (int) (q1.y >> 8);
-									const int off = (int) atomicAdd(&misc[M_SLOWTOK], (uint32_t) cnt); /* dense area of the tile's slowtok slice */
-									int32_t *stok = a.slowtok + lt * (long long) RECN + off;
-									if (!(a.flags & JTK_COUNT_ONLY)) {
-										stok[0] = (int32_t) q1.z;
-										if (cnt > 1) stok[1] = (int32_t) q1.w;
-										for (int k = 2; k < cnt; k++) stok[k] = me->tok[k];
-									}
-									out = rec_make(off, cnt);
-									hits += cnt;
-									memo_hit = true;
-								}
-							}
-							if (memo_hit) {
-							} else if (n <= JTK_SHORT_PIECE) {
-								a.slowq[lt * (long long) QCAP + atomicAdd(&misc[M_NSLOW], 1u)] = (uint16_t) q;
-								atomicAdd(&misc[M_HIST + n], 1u);
-							} else if (n <= JTK_GROUP8_PIECE) a.med8[atomicAdd(&a.sub->n_med8, 1u)] = ((uint32_t) lt << 14) | (uint32_t) q;
-							else a.med32[atomicAdd(&a.sub->n_med32, 1u)] = ((uint32_t) lt << 14) | (uint32_t) q;
-						}
+						defer = true;
 					}
+				} else {
+					defer = true;
 				}
-				rec[q] = out;
+			}
+			/* warp-aggregated append to the deferred list */
+			const unsigned dm = __ballot_sync(0xFFFFFFFFu, defer);
+			if (dm) {
+				unsigned slot = 0;
+				if (lane == 0) slot = atomicAdd(&misc[M_NDEF], (unsigned) __popc(dm));
+				slot = __shfl_sync(0xFFFFFFFFu, slot, 0) + __popc(dm & ((1u << lane) - 1u));
+				if (defer) {
+					if (slot < (unsigned) DEFCAP) S.deflist[slot] = (uint16_t) q;
+					else hits += split_slow_piece<GENERAL>(a, sb, q, npieces, lt, tb); /* list full: resolve in place */
+				}
 			}
 		}
+		__syncthreads();
+		/* ---- P4b pass 2: the deferred pieces, densely ---- */
+		{
+			const int ndef = min((int) misc[M_NDEF], DEFCAP);
+			for (int i = tid; i < ndef; i += NT) hits += split_slow_piece<GENERAL>(a, sb, S.deflist[i], npieces, lt, tb);
+		}
 		hits = __reduce_add_sync(0xFFFFFFFFu, hits);
-		if (lane == 0) atomicAdd(&misc[M_HITS], (uint32_t) hits);
+		if (lane == 0 && hits) atomicAdd(&misc[M_HITS], (uint32_t) hits);
 		/* tile-local piece index of the documents that start in this tile (the end of the input included);
 		 * jtk_gather_kernel turns it into a token offset */
 		if (a.tok_off) {
@@ -501,19 +673,29 @@ __global__ void __launch_bounds__(JTK_NT, 2048 / JTK_NT) jtk_split_lookup_kernel
 				if (g < tb) continue;
 				const int s = (int) (g - tb);
 				const int ch = s >> 4;
-				uint32_t m = reinterpret_cast<const uint16_t *>(bmask)[BH / 16 + ch] & ((1u << (s & 15)) - 1u);
+				uint32_t m = reinterpret_cast<const uint16_t *>(S.bmask)[BH / 16 + ch] & ((1u << (s & 15)) - 1u);
 				const int64_t gbase = tb + ch * 16;
 				if (gbase + 16 > a.total) m &= (1u << (int) (a.total - gbase)) - 1u;
-				a.tok_off[d] = (int64_t) chunk_pref[ch] + __popc(m);
+				a.tok_off[d] = (int64_t) S.chunk_pref[ch] + __popc(m);
 			}
 		}
 		__syncthreads();
-		if (tid == 0) {
+		/* ---- the tile's counters go out, the next tile begins (its ticket was taken at the top) ---- */
+		if (tid <= JTK_SHORT_PIECE && misc[M_HIST + tid]) {
+			atomicAdd(&a.sub->short_cnt[tid], misc[M_HIST + tid]);
+			misc[M_HIST + tid] = 0;
+		}
+		if (tid == NT - 1) {
 			a.nslow[tile] = (int32_t) misc[M_NSLOW];
 			a.tile_count[tile] = (int32_t) misc[M_HITS];
 			a.tile_slow_used[tile] = (int32_t) misc[M_SLOWTOK];
+			misc[M_NSLOW] = 0;
+			misc[M_HITS] = 0;
+			misc[M_SLOWTOK] = 0;
+			misc[M_NDEF] = 0;
 		}
-		if (tid <= JTK_SHORT_PIECE && misc[M_HIST + tid]) atomicAdd(&a.sub->short_cnt[tid], misc[M_HIST + tid]);
+		cur = nxt;
+		nxt = misc[M_TICKET + buf];
 	}
 }
 
@@ -1368,9 +1550,9 @@ __global__ void jtk_long_fix_offsets_kernel(const jtk_long_piece *list, const in
  * launch wrappers
  * ============================================================================================= */
 cudaError_t jtk_encode_kernel_setup() {
-	cudaError_t e = cudaFuncSetAttribute(jtk_split_lookup_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, JTK_SMEM_BYTES);
+	cudaError_t e = cudaFuncSetAttribute(jtk_split_lookup_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLIT_SMEM_BYTES);
 	if (e != cudaSuccess) return e;
-	e = cudaFuncSetAttribute(jtk_split_lookup_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, JTK_SMEM_BYTES);
+	e = cudaFuncSetAttribute(jtk_split_lookup_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPLIT_SMEM_BYTES);
 	if (e != cudaSuccess) return e;
 	/* merge kernels: 75 % shared-memory carve-out = five CTAs of the 16-slot kernel per SM and ~85 KB of L1 for the pair table
 	 * (measured: mixed corpus 8.12 -> 7.65 ms per 512 MiB against the default carve-out; 50 % and 25 % are slower) */
@@ -1418,7 +1600,7 @@ cudaError_t jtk_launch_split(const jtk_encode_args &a, int num_sms, int ctas_per
 	cfg.numAttrs = l2_window_attr(a, attr);
 	cfg.gridDim = dim3((unsigned) grid);
 	cfg.blockDim = dim3(JTK_NT);
-	cfg.dynamicSmemBytes = JTK_SMEM_BYTES;
+	cfg.dynamicSmemBytes = SPLIT_SMEM_BYTES;
 	if (k0) cudaEventRecord(k0, st);
 	if (a.T.pattern_kind == JTK_PAT_GENERAL) cudaLaunchKernelEx(&cfg, jtk_split_lookup_kernel<true>, a);
 	else cudaLaunchKernelEx(&cfg, jtk_split_lookup_kernel<false>, a);

@@ -101,7 +101,6 @@ struct jtk_encode_args {
 	size_t l2_bytes;
 };
 
-#define JTK_SMEM_BYTES (2 * (JTK_REGION + 16) + 2 * 4 * (((JTK_REGION + 32) / 32 + 1)) + 2 * JTK_RECN + 4 * (JTK_TILE / 16) + 512 + 128 + 12 * (JTK_REGION_CHUNKS + 2))
 
 cudaError_t jtk_launch_tile_first_doc(const int64_t *doc_off, int64_t ndocs, int64_t ntiles, int32_t *out, cudaStream_t st);
 /* Side streams on which the merge kernels of a sub-batch run next to each other: each of them alone leaves most of the GPU

@@ -156,6 +156,16 @@ static void build_class_tables(jtk_host_tables *t, int flags) {
 		}
 		t->cp_stage1[b] = it->second;
 	}
+	/* flat forms for the tile kernel */
+	t->lut_sp.assign(256, 0);
+	for (uint32_t b = 0; b < 128; b++) {
+		const uint32_t k = t->ascii_cls[b];
+		t->lut_sp[b] = (k & 1u) | (((k >> 1) & 1u) << 8) | (((k >> 2) & 1u) << 16) | (((k >> 3) & 1u) << 24);
+	}
+	t->cls2.resize(2048);
+	for (uint32_t cp = 0; cp < 2048; cp++) t->cls2[cp] = classify_cp(cp, t->pattern_kind, flags);
+	t->bmp_nib.assign(32768, 0);
+	for (uint32_t cp = 0; cp < 65536; cp++) t->bmp_nib[cp >> 1] |= (uint8_t) (classify_cp(cp, t->pattern_kind, flags) << ((cp & 1u) * 4));
 }
 
 /* ------------------------------------------------------------------ hash tables */
@@ -299,7 +309,7 @@ int jtk_build_host_tables(const jtk_params *p, jtk_host_tables *t, std::string *
 
 	/* table A: inline keys, one 32-byte slot per probe, load <= 0.5 */
 	t->mask_a = pow2_at_least((uint64_t) (n_a / JTK_TABLE_A_LOAD) + 1) - 1;
-	t->tab_a.assign((size_t) t->mask_a + 1, jtk_slot_a{{0, 0, 0, 0, 0, 0}, 0, 0});
+	t->tab_a.assign((size_t) t->mask_a + 1, jtk_slot_a{{0, 0}, 0, 0, {0, 0, 0, 0}});
 	/* table B: hashed long keys, w = token index + 1 (0 = empty) */
 	t->mask_b = pow2_at_least((uint64_t) (n_b / 0.8) + 1) - 1;
 	t->tab_b.assign(2 * (size_t) (t->mask_b + 1), jtk_slot{0, 0, 0, 0});
@@ -310,10 +320,13 @@ int jtk_build_host_tables(const jtk_params *p, jtk_host_tables *t, std::string *
 		if (len == 0) continue; /* an empty key can only match an empty piece, which emits nothing on this path */
 		if (len <= JTK_INLINE_KEY_MAX) {
 			jtk_slot_a s;
-			pack_inline_key(kb, (int) len, s.k);
+			uint32_t kw[6];
+			pack_inline_key(kb, (int) len, kw);
+			s.k01[0] = kw[0], s.k01[1] = kw[1];
+			s.k25[0] = kw[2], s.k25[1] = kw[3], s.k25[2] = kw[4], s.k25[3] = kw[5];
 			s.len = len;
 			s.rank = (uint32_t) t->tok_rank[(size_t) k];
-			uint32_t b = jtk_hash6(s.k, len) & t->mask_a;
+			uint32_t b = jtk_hash6(kw, len) & t->mask_a;
 			int pr = 1;
 			while (t->tab_a[b].len != 0) {
 				b = (b + 1) & t->mask_a;
@@ -435,6 +448,9 @@ jtk_tables jtk_host_view(const jtk_host_tables &h) {
 	v.ascii_cls = h.ascii_cls.data();
 	v.cp_stage1 = h.cp_stage1.data();
 	v.cp_stage2 = h.cp_stage2.data();
+	v.lut_sp = h.lut_sp.data();
+	v.cls2 = h.cls2.data();
+	v.bmp_nib = h.bmp_nib.data();
 	v.tab_a = h.tab_a.data();
 	v.mask_a = h.mask_a;
 	v.tab_b = h.tab_b.data();

@@ -22,6 +22,8 @@ struct jtk_host_tables {
 	std::vector<uint8_t> ascii_cls;
 	std::vector<uint16_t> cp_stage1;
 	std::vector<uint8_t> cp_stage2;
+	std::vector<uint32_t> lut_sp;
+	std::vector<uint8_t> cls2, bmp_nib;
 	std::vector<jtk_slot_a> tab_a;
 	uint32_t mask_a = 0;
 	std::vector<jtk_slot> tab_b;

@@ -51,13 +51,12 @@ void emu_stats(const emu_encoding *e, int64_t *out) {
 }
 
 struct emu_tile_state {
-	std::vector<uint8_t> sb, cls;
+	std::vector<uint32_t> sbw; /* word aligned staging buffer */
 	std::vector<uint32_t> bmask, dmask, planes;
 	std::vector<int32_t> tok, rk;
 	jtk_tile_ctx c;
-	emu_tile_state() : sb(JTK_REGION + 16), cls(JTK_REGION + 16), bmask(JTK_MASK_WORDS), dmask(JTK_MASK_WORDS), planes(3 * (JTK_REGION_CHUNKS + 2)), tok(JTK_TILE + JTK_FWD_HALO), rk(JTK_TILE + JTK_FWD_HALO) {
-		c.sb = sb.data();
-		c.cls = cls.data();
+	emu_tile_state() : sbw((JTK_REGION + 32) / 4 + 1), bmask(JTK_MASK_WORDS), dmask(JTK_MASK_WORDS), planes(4 * (JTK_REGION_CHUNKS + 2)), tok(JTK_TILE + JTK_FWD_HALO), rk(JTK_TILE + JTK_FWD_HALO) {
+		c.sb = reinterpret_cast<uint8_t *>(sbw.data());
 		c.bmask = bmask.data();
 		c.dmask = dmask.data();
 		c.planes = planes.data();
@@ -102,7 +101,8 @@ int64_t emu_run(const emu_encoding *e, const uint8_t *bytes, int64_t total, cons
 	t.c.doc_off = doc_off;
 	t.c.ndocs = ndocs;
 	t.c.T = &e->view;
-	t.c.ascii_lut = e->view.ascii_cls;
+	t.c.lut_sp = e->view.lut_sp;
+	t.c.cls2 = e->view.cls2;
 	int64_t halo_mismatch = 0;
 	for (int64_t tile = 0; tile < ntiles; tile++) {
 		t.run(tile);

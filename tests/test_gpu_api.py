@@ -204,7 +204,8 @@ def test_c_abi_builtin_loader_matches_python_loader(gpu_encodings, oracles):
                 enc.encode("<|fim_middle|>")
         else:
             assert enc.encode("<|fim_middle|>") == gpu_encodings[name].encode("<|fim_middle|>")
-        enc.close()
+        enc.close()  # deferred until `got` (a view of the encoding's pinned buffers) has been released
+        got.close()
 
 
 def test_encode_packed_rejects_inconsistent_offsets(gpu_encodings):

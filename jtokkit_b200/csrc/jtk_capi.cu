@@ -84,12 +84,12 @@ struct jtk_memo_buf {
 	uint32_t epoch = 0;
 };
 /* entries of the per-call piece memo (64 bytes each): 2^20 = 64 MiB by default (measured on the mixed corpus: 2^18 7.62 ms,
- * 2^19 7.36, 2^20 7.32, 2^21 7.19 per 512 MiB; without a memo 9.51), JTK_MEMO_LOG2 overrides (16..24) */
+ * 2^19 7.36, 2^20 7.32, 2^21 7.19 per 512 MiB; without a memo 9.51), JTK_MEMO_LOG2 overrides (16..22) */
 static uint32_t memo_entries() {
 	static const uint32_t v = [] {
 		const char *env = getenv("JTK_MEMO_LOG2");
 		const int l = env ? atoi(env) : 20;
-		return 1u << (l < 16 ? 16 : l > 24 ? 24 : l);
+		return 1u << (l < 16 ? 16 : l > 22 ? 22 : l); /* a piece record holds the entry index in 22 bits */
 	}();
 	return v;
 }

@@ -785,6 +785,25 @@ JTK_HD void jtk_build_key(const uint8_t *p, int n, uint32_t *k) {
 	}
 }
 
+/* the first four zero-padded key words of the n <= 16 bytes at p (five aligned loads) */
+JTK_HD void jtk_build_key4(const uint8_t *p, int n, uint32_t *k) {
+	const uint32_t *aw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t) 3);
+	const int sh = (int) (reinterpret_cast<uintptr_t>(p) & 3) * 8;
+	uint32_t a[5];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+	for (int i = 0; i < 5; i++) a[i] = aw[i];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+	for (int i = 0; i < 4; i++) {
+		const uint32_t w = sh ? (a[i] >> sh) | (a[i + 1] << (32 - sh)) : a[i];
+		const int rem = n - 4 * i;
+		k[i] = rem >= 4 ? w : rem <= 0 ? 0u : (w & ((1u << (8 * rem)) - 1u));
+	}
+}
+
 /* whole-piece lookup for keys of 25..max_token_len bytes, verified byte by byte */
 JTK_HD int32_t jtk_lookup_b(const jtk_tables &T, const uint8_t *p, uint32_t n) {
 	uint64_t h = jtk_hash_bytes_init();

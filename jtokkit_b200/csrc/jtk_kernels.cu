@@ -41,9 +41,11 @@ static_assert(TC <= NT && NT % 32 == 0 && NT <= 1024, "one thread per tile chunk
 constexpr int32_t REC_BASE = (int32_t) 0x80000000;
 constexpr uint32_t REC_LONG = 1u << 28; /* payload = REC_LONG | index into long_list; else (offset << 11) | (count - 1) */
 constexpr uint32_t REC_SKIP = 1u << 29; /* general patterns: a gap between matches, no tokens */
+constexpr uint32_t REC_MEMO = 1u << 27; /* payload = REC_MEMO | memo entry << 4 | (count - 1): the tokens are read from the memo entry itself */
 __device__ __forceinline__ bool rec_is_id(int32_t r) { return r >= JTK_REC_MIN_ID; }
 __device__ __forceinline__ int32_t rec_make(int s, int m) { return REC_BASE + (int32_t) (((uint32_t) s << 11) | (uint32_t) (m - 1)); }
 __device__ __forceinline__ uint32_t rec_payload(int32_t r) { return (uint32_t) (r - REC_BASE); }
+__device__ __forceinline__ int32_t rec_make_memo(uint32_t entry, int m) { return REC_BASE + (int32_t) (REC_MEMO | (entry << 4) | (uint32_t) (m - 1)); }
 
 
 
@@ -234,19 +236,24 @@ __device__ int merge_group(const jtk_tables &T, const uint8_t *p, int n, int32_t
  *       pieces, misses and everything unusual go to a short deferred list, which a second, dense pass resolves (full-key
  *       probe, long keys, memo, queues for the merge kernels): the rare paths no longer run inside every warp.
  * ------------------------------------------------------------------------------------------- */
+#ifndef JTK_SPLIT_CTAS
+#define JTK_SPLIT_CTAS (2048 / JTK_NT) /* resident CTAs per SM of the split+lookup kernel (register budget = 65536 / (JTK_NT * JTK_SPLIT_CTAS)) */
+#endif
 constexpr int SB_BYTES = JTK_REGION + 32;                 /* one staging buffer: region + pad chunk + 16 zero bytes */
 constexpr int COPY_BYTES = JTK_REGION + 16;               /* what the bulk copy covers in the interior of the input */
 constexpr int PLANE_BYTES = 16 * (JTK_REGION_CHUNKS + 2); /* four plane words per chunk */
 constexpr int PLIST_BYTES = ((2 * JTK_TILE > PLANE_BYTES ? 2 * JTK_TILE : PLANE_BYTES) + 15) / 16 * 16; /* plist reuses the planes' memory after P3 */
-constexpr int DEFCAP = 2048;                              /* deferred pieces per tile held in shared memory (more are resolved in place) */
+constexpr int DEFCAP = 2048;                              /* pieces of 9..24 bytes per tile held in shared memory for the full-key pass (more are resolved in place) */
+constexpr int ODDCAP = 512;                               /* unusual pieces per tile (longer keys, long pieces, the tile's last piece) */
+constexpr int MISSCAP = 1024;                             /* table misses per tile held in shared memory for the memo / queue pass (more are resolved in place) */
 static_assert(SB_BYTES % 16 == 0 && COPY_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
 static_assert(JTK_REGION_CHUNKS + 1 <= NT, "one thread per region chunk");
 
 /* indices into the small shared "misc" array */
-enum { M_NSLOW = 0, M_HITS, M_SLOWTOK, M_NDEF, M_CARRY, M_TICKET /* 2 */, M_WSUM = 16, M_HIST = 48 /* .. M_HIST + JTK_SHORT_PIECE */, M_WORDS = 128 };
+enum { M_NSLOW = 0, M_HITS, M_SLOWTOK, M_NDEF, M_CARRY, M_TICKET /* 2 */, M_NODD = 7, M_NMISS, M_WSUM = 16, M_HIST = 48 /* .. M_HIST + JTK_SHORT_PIECE */, M_WORDS = 128 };
 static_assert(M_HIST + JTK_SHORT_PIECE + 1 <= M_WORDS, "misc too small");
 
-constexpr int SPLIT_SMEM_BYTES = 2 * SB_BYTES + PLIST_BYTES + 2 * 4 * JTK_MASK_WORDS + 4 * ((TC + 3) / 4 * 4) + 4 * M_WORDS + 1024 + 2048 + 2 * DEFCAP + 16;
+constexpr int SPLIT_SMEM_BYTES = 2 * SB_BYTES + PLIST_BYTES + 2 * 4 * JTK_MASK_WORDS + 4 * ((TC + 3) / 4 * 4) + 4 * M_WORDS + 1024 + 2048 + 2 * DEFCAP + 2 * ODDCAP + 2 * MISSCAP + 16;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -294,7 +301,9 @@ constexpr int OFF_MISC = OFF_CPREF + 4 * ((TC + 3) / 4 * 4);
 constexpr int OFF_LUT = OFF_MISC + 4 * M_WORDS;
 constexpr int OFF_CLS2 = OFF_LUT + 1024;
 constexpr int OFF_DEF = OFF_CLS2 + 2048;
-constexpr int OFF_MBAR = OFF_DEF + 2 * DEFCAP;
+constexpr int OFF_ODD = OFF_DEF + 2 * DEFCAP;
+constexpr int OFF_MISS = OFF_ODD + 2 * ODDCAP;
+constexpr int OFF_MBAR = OFF_MISS + 2 * MISSCAP;
 static_assert(OFF_MBAR + 16 == SPLIT_SMEM_BYTES && OFF_MBAR % 8 == 0 && OFF_PLANES % 16 == 0 && OFF_BMASK % 16 == 0, "shared memory layout");
 struct split_smem {
 	__device__ __forceinline__ uint8_t *sb(int i) const { return jtk_dyn_smem + OFF_SB + i * SB_BYTES; }
@@ -307,20 +316,69 @@ struct split_smem {
 	__device__ __forceinline__ uint32_t *lut_sp() const { return reinterpret_cast<uint32_t *>(jtk_dyn_smem + OFF_LUT); }
 	__device__ __forceinline__ uint8_t *cls2() const { return jtk_dyn_smem + OFF_CLS2; }
 	__device__ __forceinline__ uint16_t *deflist() const { return reinterpret_cast<uint16_t *>(jtk_dyn_smem + OFF_DEF); }
+	__device__ __forceinline__ uint16_t *oddlist() const { return reinterpret_cast<uint16_t *>(jtk_dyn_smem + OFF_ODD); }
+	__device__ __forceinline__ uint16_t *misslist() const { return reinterpret_cast<uint16_t *>(jtk_dyn_smem + OFF_MISS); }
 	__device__ __forceinline__ uint64_t *mbar() const { return reinterpret_cast<uint64_t *>(jtk_dyn_smem + OFF_MBAR); }
 };
 
-/* The unusual pieces of a tile (pass 2 of P4b): longer than eight bytes, not a token as a whole, longer than the in-tile limit. */
+/* A piece of n bytes at region index r that is not a token as a whole (pass 3 of P4b): the memo of this call may hold its tokens,
+ * otherwise it is queued for the merge kernels.  Returns the tokens accounted for now (memo hit) and stores the piece's record. */
+__device__ __forceinline__ int split_resolve_miss(const jtk_encode_args &a, const uint8_t *sb, int q, int r, int n, long long lt) {
+	const split_smem S;
+	const int s = r - BH;
+	int32_t out = rec_make(s, n);
+	int hits = 0;
+	bool memo_hit = false;
+	if (n <= JTK_MEMO_MAX_PIECE && a.memo) { /* has this call merged the same piece before? */
+		uint32_t key[6];
+		jtk_build_key4(sb + r, n, key);
+		key[4] = key[5] = 0;
+		const uint32_t entry = (jtk_hash6(key, (uint32_t) n) * 0x9E3779B1u) >> 8 & a.memo_mask;
+		/* entries are written by the merge kernel of EARLIER sub-batches of this call (stream ordered, never while this kernel
+		 * runs: the two-lane pipeline runs without a memo) and never change afterwards: the record points at the entry and
+		 * the gather kernel reads the tokens from there */
+		const uint4 *mp = reinterpret_cast<const uint4 *>(a.memo + entry);
+		const uint4 q0 = mp[0];
+		const uint2 q1 = *reinterpret_cast<const uint2 *>(mp + 1);
+		if (q1.x == ((a.memo_epoch << 8) | 2u) && (q1.y & 0xFFu) == (uint32_t) n && q0.x == key[0] && q0.y == key[1] && q0.z == key[2] && q0.w == key[3]) {
+			const int cnt = (int) (q1.y >> 8);
+			out = rec_make_memo(entry, cnt);
+			hits = cnt;
+			memo_hit = true;
+		}
+	}
+	/* queue for the merge kernels (warp-aggregated slot in the tile's list of short pieces) */
+	const bool shortq = !memo_hit && n <= JTK_SHORT_PIECE;
+	const unsigned act = __activemask();
+	const unsigned sm = __ballot_sync(act, shortq);
+	if (sm) {
+		const int lane = threadIdx.x & 31, leader = __ffs((int) sm) - 1;
+		unsigned slot = 0;
+		if (lane == leader) slot = atomicAdd(&S.misc()[M_NSLOW], (unsigned) __popc(sm));
+		slot = __shfl_sync(act, slot, leader) + __popc(sm & ((1u << lane) - 1u));
+		if (shortq) {
+			a.slowq[lt * (long long) QCAP + slot] = (uint16_t) q;
+			atomicAdd(&S.misc()[M_HIST + n], 1u);
+		}
+	}
+	if (!memo_hit && n > JTK_SHORT_PIECE) {
+		if (n <= JTK_GROUP8_PIECE) a.med8[atomicAdd(&a.sub->n_med8, 1u)] = ((uint32_t) lt << 14) | (uint32_t) q;
+		else a.med32[atomicAdd(&a.sub->n_med32, 1u)] = ((uint32_t) lt << 14) | (uint32_t) q;
+	}
+	(a.rec + lt * (long long) RECN)[q] = out;
+	return hits;
+}
+
+/* The unusual pieces of a tile: keys longer than 24 bytes, pieces longer than the in-tile limit, the tile's last piece (whose end
+ * lies in the halo), and whatever did not fit the shared-memory lists.  Complete on its own: lookup, memo, queues. */
 template <bool GENERAL>
 __device__ __noinline__ int split_slow_piece(const jtk_encode_args &a, const uint8_t *sb, int q, int npieces, long long lt, int64_t tb) {
 	const jtk_tables &T = a.T;
 	const split_smem S;
-	int hits = 0;
 	const int r = S.plist()[q];
 	const int s = r - BH;
 	int e = (q + 1 < npieces) ? (int) S.plist()[q + 1] : next_bit(S.bmask(), r + 1, r + JTK_LONG_PIECE);
 	if (e >= 0 && e - r > JTK_LONG_PIECE) e = -1;
-	int32_t out;
 	if (e < 0) { /* longer than JTK_LONG_PIECE: deferred to the long-piece kernels */
 		const unsigned idx = atomicAdd(&a.hdr->n_long, 1u);
 		if ((int64_t) idx < a.long_cap) {
@@ -335,75 +393,39 @@ __device__ __noinline__ int split_slow_piece(const jtk_encode_args &a, const uin
 			lp.flags = 0;
 			a.long_list[idx] = lp;
 		}
-		out = REC_BASE + (int32_t) (REC_LONG | (idx & 0x0FFFFFFFu));
-	} else {
-		const int n = e - r;
-		const uint8_t *p = sb + r;
-		uint32_t key[6] = {0, 0, 0, 0, 0, 0};
-		uint32_t h = 0;
-		if (n <= JTK_INLINE_KEY_MAX) { /* (pieces of up to eight bytes come here after a miss of the short probe, or as the tile's last piece) */
-			jtk_build_key(p, n, key);
-			h = jtk_hash6(key, (uint32_t) n);
-			out = jtk_lookup_a(T, key, (uint32_t) n, h);
-			if (out != JTK_RANK_MAX) {
-				hits++;
-			} else if (n == 1) { /* a byte that is not in the vocabulary (TokenEncoder.java:64-71) */
-				flag_doc(a, tb + s, JTK_DOC_UNKNOWN_BYTES);
-				out = JTK_REC_MIN_ID; /* the document is in error; keep the record a plain id */
-				hits++;
-			}
-		} else {
-			out = n > T.max_token_len ? JTK_RANK_MAX : jtk_lookup_long(T, p, n);
-			if (out != JTK_RANK_MAX) hits++;
-		}
-		if (out == JTK_RANK_MAX) {
-			out = rec_make(s, n);
-			bool memo_hit = false;
-			if (n <= JTK_MEMO_MAX_PIECE && n >= 2 && a.memo) { /* has this call merged the same piece before? */
-				const jtk_memo_entry *me = a.memo + ((h * 0x9E3779B1u) >> 8 & a.memo_mask);
-				/* entries are written by the merge kernel of EARLIER sub-batches of this call (stream ordered, never while this
-				 * kernel runs: the two-lane pipeline runs without a memo) */
-				const uint4 *mp = reinterpret_cast<const uint4 *>(me);
-				const uint4 q0 = mp[0], q1 = mp[1];
-				const bool cand = q1.x == ((a.memo_epoch << 8) | 2u) && (q1.y & 0xFFu) == (uint32_t) n;
-				if (cand && q0.x == key[0] && q0.y == key[1] && q0.z == key[2] && q0.w == key[3]) {
-					const int cnt = (int) (q1.y >> 8);
-					const int off = (int) atomicAdd(&S.misc()[M_SLOWTOK], (uint32_t) cnt); /* dense area of the tile's slowtok slice */
-					int32_t *stok = a.slowtok + lt * (long long) RECN + off;
-					if (!(a.flags & JTK_COUNT_ONLY)) {
-						stok[0] = (int32_t) q1.z;
-						if (cnt > 1) stok[1] = (int32_t) q1.w;
-						for (int k = 2; k < cnt; k++) stok[k] = me->tok[k];
-					}
-					out = rec_make(off, cnt);
-					hits += cnt;
-					memo_hit = true;
-				}
-			}
-			if (memo_hit) {
-			} else if (n <= JTK_SHORT_PIECE) {
-				a.slowq[lt * (long long) QCAP + atomicAdd(&S.misc()[M_NSLOW], 1u)] = (uint16_t) q;
-				atomicAdd(&S.misc()[M_HIST + n], 1u);
-			} else if (n <= JTK_GROUP8_PIECE) a.med8[atomicAdd(&a.sub->n_med8, 1u)] = ((uint32_t) lt << 14) | (uint32_t) q;
-			else a.med32[atomicAdd(&a.sub->n_med32, 1u)] = ((uint32_t) lt << 14) | (uint32_t) q;
-		}
+		(a.rec + lt * (long long) RECN)[q] = REC_BASE + (int32_t) (REC_LONG | (idx & 0x0FFFFFFFu));
+		return 0;
 	}
+	const int n = e - r;
+	const uint8_t *p = sb + r;
+	int32_t out;
+	if (n <= JTK_INLINE_KEY_MAX) {
+		uint32_t key[6];
+		jtk_build_key(p, n, key);
+		out = jtk_lookup_a(T, key, (uint32_t) n, jtk_hash6(key, (uint32_t) n));
+		if (out == JTK_RANK_MAX && n == 1) { /* a byte that is not in the vocabulary (TokenEncoder.java:64-71) */
+			flag_doc(a, tb + s, JTK_DOC_UNKNOWN_BYTES);
+			out = JTK_REC_MIN_ID; /* the document is in error; keep the record a plain id */
+		}
+	} else {
+		out = n > T.max_token_len ? JTK_RANK_MAX : jtk_lookup_long(T, p, n);
+	}
+	if (out == JTK_RANK_MAX) return split_resolve_miss(a, sb, q, r, n, lt);
 	(a.rec + lt * (long long) RECN)[q] = out;
-	return hits;
+	return 1;
 }
 
 template <bool GENERAL>
-__global__ void __launch_bounds__(JTK_NT, 2048 / JTK_NT) jtk_split_lookup_kernel(const __grid_constant__ jtk_encode_args a) {
+__global__ void __launch_bounds__(JTK_NT, JTK_SPLIT_CTAS) jtk_split_lookup_kernel(const __grid_constant__ jtk_encode_args a) {
 	const split_smem L;
 	struct {
-		uint8_t *sb[2];
+		uint8_t *sb0;
 		uint32_t *planes, *bmask, *dmask, *chunk_pref, *lut_sp;
-		uint16_t *plist, *deflist;
+		uint16_t *plist, *deflist, *oddlist, *misslist;
 		uint8_t *cls2;
 		uint64_t *mbar;
 	} S;
-	S.sb[0] = L.sb(0);
-	S.sb[1] = L.sb(1);
+	S.sb0 = L.sb(0);
 	S.planes = L.planes();
 	S.plist = L.plist(); /* region index of every piece start, in order (written after the planes' last use) */
 	S.bmask = L.bmask();
@@ -412,6 +434,8 @@ __global__ void __launch_bounds__(JTK_NT, 2048 / JTK_NT) jtk_split_lookup_kernel
 	S.lut_sp = L.lut_sp();
 	S.cls2 = L.cls2();
 	S.deflist = L.deflist();
+	S.oddlist = L.oddlist();
+	S.misslist = L.misslist();
 	S.mbar = L.mbar();
 	uint32_t *const misc = L.misc();
 
@@ -425,7 +449,7 @@ __global__ void __launch_bounds__(JTK_NT, 2048 / JTK_NT) jtk_split_lookup_kernel
 	for (int w = tid; w < 2 * JTK_MASK_WORDS; w += NT) S.bmask[w] = 0; /* bmask and dmask */
 	if (tid < M_WORDS) misc[tid] = 0;
 	if (tid < 8) { /* the 16 bytes after what the copies cover stay zero for good */
-		reinterpret_cast<uint32_t *>(S.sb[tid >> 2] + COPY_BYTES)[tid & 3] = 0;
+		reinterpret_cast<uint32_t *>(S.sb0 + (tid >> 2) * SB_BYTES + COPY_BYTES)[tid & 3] = 0;
 	}
 	if (tid == 0) {
 		mbar_init(&S.mbar[0], 1);
@@ -439,7 +463,7 @@ __global__ void __launch_bounds__(JTK_NT, 2048 / JTK_NT) jtk_split_lookup_kernel
 		region_copy_range(a.tile_begin + lt_next, a.total, &lo, &hi);
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* the buffer was last touched by ordinary loads / stores */
 		mbar_expect_tx(&S.mbar[buf], (uint32_t) (hi - lo));
-		if (hi > lo) bulk_load(S.sb[buf] + lo, a.bytes + ((a.tile_begin + lt_next) * (int64_t) JTK_TILE - BH) + lo, (uint32_t) (hi - lo), &S.mbar[buf]);
+		if (hi > lo) bulk_load(S.sb0 + buf * SB_BYTES + lo, a.bytes + ((a.tile_begin + lt_next) * (int64_t) JTK_TILE - BH) + lo, (uint32_t) (hi - lo), &S.mbar[buf]);
 	};
 	if (tid == 0) {
 		const unsigned t0 = atomicAdd(&a.sub->ticket, 1u);
@@ -472,7 +496,7 @@ __global__ void __launch_bounds__(JTK_NT, 2048 / JTK_NT) jtk_split_lookup_kernel
 		const long long lt = cur; /* index into the per-sub-batch buffers */
 		const long long tile = a.tile_begin + lt;
 		const int64_t tb = tile * (int64_t) JTK_TILE;
-		uint8_t *const sb = S.sb[buf];
+		uint8_t *const sb = S.sb0 + buf * SB_BYTES;
 		c.sb = sb;
 		c.g0 = tb - BH;
 		c.rs = 0;
@@ -609,15 +633,15 @@ __global__ void __launch_bounds__(JTK_NT, 2048 / JTK_NT) jtk_split_lookup_kernel
 		__syncthreads();
 
 		/* ---- P4b pass 1: one piece per thread; keys of up to eight bytes probe the first half of their slot
-		 * (whole-piece fast path, GptBytePairEncoding.java:81-83), everything else is deferred ---- */
+		 * (whole-piece fast path, GptBytePairEncoding.java:81-83); longer keys, misses and unusual pieces go to three lists ---- */
 		int32_t *rec = a.rec + lt * (long long) RECN;
 		int hits = 0;
 		for (int q0 = 0; q0 < npieces; q0 += NT) {
 			const int q = q0 + tid;
-			bool defer = false;
+			int kind = 0; /* 1: key of 9..24 bytes, 2: unusual, 3: miss of the short probe */
 			if (q < npieces) {
 				const int r = S.plist[q];
-				const int e = (q + 1 < npieces) ? (int) S.plist[q + 1] : -1; /* the tile's last piece ends in the halo: deferred */
+				const int e = (q + 1 < npieces) ? (int) S.plist[q + 1] : -1; /* the tile's last piece ends in the halo: unusual */
 				const int n = e - r;
 				if (GENERAL && ((S.dmask[r >> 5] >> (r & 31)) & 1u)) {
 					rec[q] = REC_BASE + (int32_t) REC_SKIP;
@@ -638,29 +662,83 @@ __global__ void __launch_bounds__(JTK_NT, 2048 / JTK_NT) jtk_split_lookup_kernel
 						rec[q] = out;
 						hits++;
 					} else {
-						defer = true;
+						kind = n == 1 ? 2 : 3; /* (a single byte outside the vocabulary is an error of its document: unusual) */
 					}
 				} else {
-					defer = true;
+					kind = (unsigned) (n - 9) <= (unsigned) (JTK_INLINE_KEY_MAX - 9) ? 1 : 2;
 				}
 			}
-			/* warp-aggregated append to the deferred list */
-			const unsigned dm = __ballot_sync(0xFFFFFFFFu, defer);
-			if (dm) {
-				unsigned slot = 0;
-				if (lane == 0) slot = atomicAdd(&misc[M_NDEF], (unsigned) __popc(dm));
-				slot = __shfl_sync(0xFFFFFFFFu, slot, 0) + __popc(dm & ((1u << lane) - 1u));
-				if (defer) {
-					if (slot < (unsigned) DEFCAP) S.deflist[slot] = (uint16_t) q;
-					else hits += split_slow_piece<GENERAL>(a, sb, q, npieces, lt, tb); /* list full: resolve in place */
+			/* warp-aggregated appends */
+			const unsigned m1 = __ballot_sync(0xFFFFFFFFu, kind == 1), m2 = __ballot_sync(0xFFFFFFFFu, kind == 2), m3 = __ballot_sync(0xFFFFFFFFu, kind == 3);
+			if (m1 | m2 | m3) {
+				unsigned s1 = 0, s2 = 0, s3 = 0;
+				if (lane == 0) {
+					if (m1) s1 = atomicAdd(&misc[M_NDEF], (unsigned) __popc(m1));
+					if (m2) s2 = atomicAdd(&misc[M_NODD], (unsigned) __popc(m2));
+					if (m3) s3 = atomicAdd(&misc[M_NMISS], (unsigned) __popc(m3));
 				}
+				const unsigned below = (1u << lane) - 1u;
+				s1 = __shfl_sync(0xFFFFFFFFu, s1, 0) + __popc(m1 & below);
+				s2 = __shfl_sync(0xFFFFFFFFu, s2, 0) + __popc(m2 & below);
+				s3 = __shfl_sync(0xFFFFFFFFu, s3, 0) + __popc(m3 & below);
+				bool placed = true;
+				if (kind == 1) {
+					placed = s1 < (unsigned) DEFCAP;
+					if (placed) S.deflist[s1] = (uint16_t) q;
+				} else if (kind == 2) {
+					placed = s2 < (unsigned) ODDCAP;
+					if (placed) S.oddlist[s2] = (uint16_t) q;
+				} else if (kind == 3) {
+					placed = s3 < (unsigned) MISSCAP;
+					if (placed) S.misslist[s3] = (uint16_t) q;
+				}
+				if (!placed) hits += split_slow_piece<GENERAL>(a, sb, q, npieces, lt, tb); /* list full: resolve in place */
 			}
 		}
 		__syncthreads();
-		/* ---- P4b pass 2: the deferred pieces, densely ---- */
+		/* ---- P4b pass 2: keys of 9..24 bytes, densely: full-key probe ---- */
 		{
-			const int ndef = min((int) misc[M_NDEF], DEFCAP);
-			for (int i = tid; i < ndef; i += NT) hits += split_slow_piece<GENERAL>(a, sb, S.deflist[i], npieces, lt, tb);
+			const int nkeys = min((int) misc[M_NDEF], DEFCAP), nodd = min((int) misc[M_NODD], ODDCAP); /* (what did not fit was resolved in place) */
+			for (int i0 = 0; i0 < nkeys; i0 += NT) {
+				const int i = i0 + tid;
+				bool miss = false;
+				int q = 0;
+				if (i < nkeys) {
+					q = S.deflist[i];
+					const int r = S.plist[q], n = (int) S.plist[q + 1] - r;
+					uint32_t key[6];
+					jtk_build_key(sb + r, n, key);
+					const int32_t out = jtk_lookup_a(T, key, (uint32_t) n, jtk_hash6(key, (uint32_t) n));
+					if (out != JTK_RANK_MAX) {
+						rec[q] = out;
+						hits++;
+					} else {
+						miss = true;
+					}
+				}
+				const unsigned mm = __ballot_sync(0xFFFFFFFFu, miss);
+				if (mm) {
+					unsigned s3 = 0;
+					if (lane == 0) s3 = atomicAdd(&misc[M_NMISS], (unsigned) __popc(mm));
+					s3 = __shfl_sync(0xFFFFFFFFu, s3, 0) + __popc(mm & ((1u << lane) - 1u));
+					if (miss) {
+						if (s3 < (unsigned) MISSCAP) S.misslist[s3] = (uint16_t) q;
+						else hits += split_slow_piece<GENERAL>(a, sb, q, npieces, lt, tb);
+					}
+				}
+			}
+			/* the unusual pieces */
+			for (int i = tid; i < nodd; i += NT) hits += split_slow_piece<GENERAL>(a, sb, S.oddlist[i], npieces, lt, tb);
+		}
+		__syncthreads();
+		/* ---- P4b pass 3: the table misses, densely: memo of this call, else the merge kernels' queues ---- */
+		{
+			const int nmiss = min((int) misc[M_NMISS], MISSCAP);
+			for (int i = tid; i < nmiss; i += NT) {
+				const int q = S.misslist[i];
+				const int r = S.plist[q];
+				hits += split_resolve_miss(a, sb, q, r, (int) S.plist[q + 1] - r, lt);
+			}
 		}
 		hits = __reduce_add_sync(0xFFFFFFFFu, hits);
 		if (lane == 0 && hits) atomicAdd(&misc[M_HITS], (uint32_t) hits);
@@ -693,6 +771,8 @@ __global__ void __launch_bounds__(JTK_NT, 2048 / JTK_NT) jtk_split_lookup_kernel
 			misc[M_HITS] = 0;
 			misc[M_SLOWTOK] = 0;
 			misc[M_NDEF] = 0;
+			misc[M_NODD] = 0;
+			misc[M_NMISS] = 0;
 		}
 		cur = nxt;
 		nxt = misc[M_TICKET + buf];
@@ -995,7 +1075,13 @@ constexpr int GCAP = 4096;  /* tokens staged in shared memory at a time for coal
 __device__ __forceinline__ int rec_count(int32_t r) {
 	if (rec_is_id(r)) return 1;
 	const uint32_t pl = rec_payload(r);
-	return (pl & (REC_LONG | REC_SKIP)) ? 0 : (int) (pl & 0x7FFu) + 1;
+	if (pl & (REC_LONG | REC_SKIP)) return 0;
+	return (pl & REC_MEMO) ? (int) (pl & 15u) + 1 : (int) (pl & 0x7FFu) + 1;
+}
+/* where the tokens of a merged / memoised piece are: REC_BASE + index into the tile's slowtok slice, or REC_BASE + REC_MEMO + entry << 4 */
+__device__ __forceinline__ int32_t rec_token_source(int32_t r) {
+	const uint32_t pl = rec_payload(r);
+	return REC_BASE + (int32_t) ((pl & REC_MEMO) ? (pl & ~15u) : ((pl >> 11) & 0x3FFFu));
 }
 
 __global__ void __launch_bounds__(GNT, 8) jtk_gather_kernel(const __grid_constant__ jtk_encode_args a) {
@@ -1052,7 +1138,7 @@ __global__ void __launch_bounds__(GNT, 8) jtk_gather_kernel(const __grid_constan
 							s_tok[pos] = r[j];
 						} else if (cnt[j]) {
 							int32_t *o = s_tok + pos;
-							const int32_t src = REC_BASE + (int) ((rec_payload(r[j]) >> 11) & 0x3FFFu);
+							const int32_t src = rec_token_source(r[j]);
 							for (int k = 0; k < cnt[j]; k++) o[k] = src + k;
 						}
 						pos += cnt[j];
@@ -1067,10 +1153,9 @@ __global__ void __launch_bounds__(GNT, 8) jtk_gather_kernel(const __grid_constan
 							/* merged / memoised piece: only note WHERE its tokens are (REC_BASE + index into the tile's slowtok slice);
 							 * the loads happen in the coalesced copy loop below, all in flight together, instead of one dependent
 							 * load per iteration of this divergent loop */
-							const int off = (int) ((rec_payload(r[j]) >> 11) & 0x3FFFu);
 							const int k0 = pos < 0 ? -pos : 0, k1 = min(cnt[j], GCAP - pos); /* the part of the piece inside the window */
 							int32_t *o = s_tok + pos;
-							const int32_t src = REC_BASE + off;
+							const int32_t src = rec_token_source(r[j]);
 							for (int k = k0; k < k1; k++) o[k] = src + k;
 						}
 					}
@@ -1084,7 +1169,10 @@ __global__ void __launch_bounds__(GNT, 8) jtk_gather_kernel(const __grid_constan
 					for (int i = 0; i < 4; i++) v[i] = k + i * GNT < nw ? s_tok[k + i * GNT] : 0;
 #pragma unroll
 					for (int i = 0; i < 4; i++)
-						if (!rec_is_id(v[i])) v[i] = stok[v[i] - REC_BASE];
+						if (!rec_is_id(v[i])) {
+							const uint32_t pl = rec_payload(v[i]);
+							v[i] = (pl & REC_MEMO) ? a.memo[(pl & ~REC_MEMO) >> 4].tok[pl & 15u] : stok[pl];
+						}
 #pragma unroll
 					for (int i = 0; i < 4; i++)
 						if (k + i * GNT < nw) dst[carry + w0 + k + i * GNT] = v[i];
@@ -1590,7 +1678,7 @@ static unsigned l2_window_attr(const jtk_encode_args &a, cudaLaunchAttribute *at
 cudaError_t jtk_launch_split(const jtk_encode_args &a, int num_sms, int ctas_per_sm, cudaEvent_t k0, cudaEvent_t k1, cudaStream_t st) {
 	const int64_t nt = a.tile_end - a.tile_begin;
 	if (nt <= 0) return cudaSuccess;
-	int64_t grid = ctas_per_sm > 0 ? (int64_t) num_sms * (2048 / JTK_NT) : nt;
+	int64_t grid = ctas_per_sm > 0 ? (int64_t) num_sms * JTK_SPLIT_CTAS : nt;
 	if (grid > nt) grid = nt;
 	cudaLaunchAttribute attr[1];
 	cudaLaunchConfig_t cfg;

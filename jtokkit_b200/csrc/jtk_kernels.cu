@@ -243,14 +243,16 @@ constexpr int SB_BYTES = JTK_REGION + 32;                 /* one staging buffer:
 constexpr int COPY_BYTES = JTK_REGION + 16;               /* what the bulk copy covers in the interior of the input */
 constexpr int PLANE_BYTES = 16 * (JTK_REGION_CHUNKS + 2); /* four plane words per chunk */
 constexpr int PLIST_BYTES = ((2 * JTK_TILE > PLANE_BYTES ? 2 * JTK_TILE : PLANE_BYTES) + 15) / 16 * 16; /* plist reuses the planes' memory after P3 */
-constexpr int DEFCAP = 2048;                              /* pieces of 9..24 bytes per tile held in shared memory for the full-key pass (more are resolved in place) */
-constexpr int ODDCAP = 512;                               /* unusual pieces per tile (longer keys, long pieces, the tile's last piece) */
-constexpr int MISSCAP = 1024;                             /* table misses per tile held in shared memory for the memo / queue pass (more are resolved in place) */
+/* per-warp lists of the lookup step (what does not fit is resolved in place) */
+constexpr int WKEYS = 128; /* pieces of 9..24 bytes: full-key pass */
+constexpr int WODD = 64;   /* unusual pieces (longer keys, long pieces, the tile's last piece) */
+constexpr int WMISS = 96;  /* table misses: memo / queue pass */
+constexpr int DEFCAP = WKEYS * (JTK_NT / 32), ODDCAP = WODD * (JTK_NT / 32), MISSCAP = WMISS * (JTK_NT / 32);
 static_assert(SB_BYTES % 16 == 0 && COPY_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
 static_assert(JTK_REGION_CHUNKS + 1 <= NT, "one thread per region chunk");
 
 /* indices into the small shared "misc" array */
-enum { M_NSLOW = 0, M_HITS, M_SLOWTOK, M_NDEF, M_CARRY, M_TICKET /* 2 */, M_NODD = 7, M_NMISS, M_WSUM = 16, M_HIST = 48 /* .. M_HIST + JTK_SHORT_PIECE */, M_WORDS = 128 };
+enum { M_NSLOW = 0, M_HITS, M_SLOWTOK, M_CARRY = 4, M_TICKET /* 2 */, M_WSUM = 16, M_HIST = 48 /* .. M_HIST + JTK_SHORT_PIECE */, M_WORDS = 128 };
 static_assert(M_HIST + JTK_SHORT_PIECE + 1 <= M_WORDS, "misc too small");
 
 constexpr int SPLIT_SMEM_BYTES = 2 * SB_BYTES + PLIST_BYTES + 2 * 4 * JTK_MASK_WORDS + 4 * ((TC + 3) / 4 * 4) + 4 * M_WORDS + 1024 + 2048 + 2 * DEFCAP + 2 * ODDCAP + 2 * MISSCAP + 16;
@@ -632,10 +634,14 @@ __global__ void __launch_bounds__(JTK_NT, JTK_SPLIT_CTAS) jtk_split_lookup_kerne
 		}
 		__syncthreads();
 
-		/* ---- P4b pass 1: one piece per thread; keys of up to eight bytes probe the first half of their slot
-		 * (whole-piece fast path, GptBytePairEncoding.java:81-83); longer keys, misses and unusual pieces go to three lists ---- */
+		/* ---- P4b: one piece per thread and round.  Pass 1: keys of up to eight bytes probe the first half of their slot
+		 * (whole-piece fast path, GptBytePairEncoding.java:81-83).  Longer keys, misses and unusual pieces go to three short
+		 * lists PER WARP (counts live in registers: no atomics, no block barrier), which the warp then works off densely:
+		 * pass 2 = full-key probe of the 9..24-byte keys, pass 3 = memo of this call / queues of the merge kernels ---- */
 		int32_t *rec = a.rec + lt * (long long) RECN;
 		int hits = 0;
+		uint16_t *const wkeys = S.deflist + warp * WKEYS, *const wodd = S.oddlist + warp * WODD, *const wmiss = S.misslist + warp * WMISS;
+		int nkeys = 0, nodd = 0, nmiss = 0; /* warp-uniform */
 		for (int q0 = 0; q0 < npieces; q0 += NT) {
 			const int q = q0 + tid;
 			int kind = 0; /* 1: key of 9..24 bytes, 2: unusual, 3: miss of the short probe */
@@ -668,77 +674,68 @@ __global__ void __launch_bounds__(JTK_NT, JTK_SPLIT_CTAS) jtk_split_lookup_kerne
 					kind = (unsigned) (n - 9) <= (unsigned) (JTK_INLINE_KEY_MAX - 9) ? 1 : 2;
 				}
 			}
-			/* warp-aggregated appends */
-			const unsigned m1 = __ballot_sync(0xFFFFFFFFu, kind == 1), m2 = __ballot_sync(0xFFFFFFFFu, kind == 2), m3 = __ballot_sync(0xFFFFFFFFu, kind == 3);
-			if (m1 | m2 | m3) {
-				unsigned s1 = 0, s2 = 0, s3 = 0;
-				if (lane == 0) {
-					if (m1) s1 = atomicAdd(&misc[M_NDEF], (unsigned) __popc(m1));
-					if (m2) s2 = atomicAdd(&misc[M_NODD], (unsigned) __popc(m2));
-					if (m3) s3 = atomicAdd(&misc[M_NMISS], (unsigned) __popc(m3));
-				}
+			const unsigned any = __ballot_sync(0xFFFFFFFFu, kind != 0);
+			if (any) {
+				const unsigned m1 = __ballot_sync(0xFFFFFFFFu, kind == 1), m3 = __ballot_sync(0xFFFFFFFFu, kind == 3), m2 = any & ~(m1 | m3);
 				const unsigned below = (1u << lane) - 1u;
-				s1 = __shfl_sync(0xFFFFFFFFu, s1, 0) + __popc(m1 & below);
-				s2 = __shfl_sync(0xFFFFFFFFu, s2, 0) + __popc(m2 & below);
-				s3 = __shfl_sync(0xFFFFFFFFu, s3, 0) + __popc(m3 & below);
 				bool placed = true;
 				if (kind == 1) {
-					placed = s1 < (unsigned) DEFCAP;
-					if (placed) S.deflist[s1] = (uint16_t) q;
-				} else if (kind == 2) {
-					placed = s2 < (unsigned) ODDCAP;
-					if (placed) S.oddlist[s2] = (uint16_t) q;
+					const int sl = nkeys + __popc(m1 & below);
+					placed = sl < WKEYS;
+					if (placed) wkeys[sl] = (uint16_t) q;
 				} else if (kind == 3) {
-					placed = s3 < (unsigned) MISSCAP;
-					if (placed) S.misslist[s3] = (uint16_t) q;
+					const int sl = nmiss + __popc(m3 & below);
+					placed = sl < WMISS;
+					if (placed) wmiss[sl] = (uint16_t) q;
+				} else if (kind == 2) {
+					const int sl = nodd + __popc(m2 & below);
+					placed = sl < WODD;
+					if (placed) wodd[sl] = (uint16_t) q;
 				}
+				nkeys += __popc(m1);
+				nmiss += __popc(m3);
+				nodd += __popc(m2);
 				if (!placed) hits += split_slow_piece<GENERAL>(a, sb, q, npieces, lt, tb); /* list full: resolve in place */
 			}
 		}
-		__syncthreads();
-		/* ---- P4b pass 2: keys of 9..24 bytes, densely: full-key probe ---- */
-		{
-			const int nkeys = min((int) misc[M_NDEF], DEFCAP), nodd = min((int) misc[M_NODD], ODDCAP); /* (what did not fit was resolved in place) */
-			for (int i0 = 0; i0 < nkeys; i0 += NT) {
-				const int i = i0 + tid;
-				bool miss = false;
-				int q = 0;
-				if (i < nkeys) {
-					q = S.deflist[i];
-					const int r = S.plist[q], n = (int) S.plist[q + 1] - r;
-					uint32_t key[6];
-					jtk_build_key(sb + r, n, key);
-					const int32_t out = jtk_lookup_a(T, key, (uint32_t) n, jtk_hash6(key, (uint32_t) n));
-					if (out != JTK_RANK_MAX) {
-						rec[q] = out;
-						hits++;
-					} else {
-						miss = true;
-					}
-				}
-				const unsigned mm = __ballot_sync(0xFFFFFFFFu, miss);
-				if (mm) {
-					unsigned s3 = 0;
-					if (lane == 0) s3 = atomicAdd(&misc[M_NMISS], (unsigned) __popc(mm));
-					s3 = __shfl_sync(0xFFFFFFFFu, s3, 0) + __popc(mm & ((1u << lane) - 1u));
-					if (miss) {
-						if (s3 < (unsigned) MISSCAP) S.misslist[s3] = (uint16_t) q;
-						else hits += split_slow_piece<GENERAL>(a, sb, q, npieces, lt, tb);
-					}
+		__syncwarp();
+		/* pass 2: keys of 9..24 bytes: full-key probe */
+		nkeys = min(nkeys, WKEYS);
+		for (int i0 = 0; i0 < nkeys; i0 += 32) {
+			const int i = i0 + lane;
+			bool miss = false;
+			int q = 0;
+			if (i < nkeys) {
+				q = wkeys[i];
+				const int r = S.plist[q], n = (int) S.plist[q + 1] - r;
+				uint32_t key[6];
+				jtk_build_key(sb + r, n, key);
+				const int32_t out = jtk_lookup_a(T, key, (uint32_t) n, jtk_hash6(key, (uint32_t) n));
+				if (out != JTK_RANK_MAX) {
+					rec[q] = out;
+					hits++;
+				} else {
+					miss = true;
 				}
 			}
-			/* the unusual pieces */
-			for (int i = tid; i < nodd; i += NT) hits += split_slow_piece<GENERAL>(a, sb, S.oddlist[i], npieces, lt, tb);
+			const unsigned mm = __ballot_sync(0xFFFFFFFFu, miss);
+			if (miss) {
+				const int sl = nmiss + __popc(mm & ((1u << lane) - 1u));
+				if (sl < WMISS) wmiss[sl] = (uint16_t) q;
+				else hits += split_slow_piece<GENERAL>(a, sb, q, npieces, lt, tb);
+			}
+			nmiss += __popc(mm);
 		}
-		__syncthreads();
-		/* ---- P4b pass 3: the table misses, densely: memo of this call, else the merge kernels' queues ---- */
-		{
-			const int nmiss = min((int) misc[M_NMISS], MISSCAP);
-			for (int i = tid; i < nmiss; i += NT) {
-				const int q = S.misslist[i];
-				const int r = S.plist[q];
-				hits += split_resolve_miss(a, sb, q, r, (int) S.plist[q + 1] - r, lt);
-			}
+		/* the unusual pieces */
+		nodd = min(nodd, WODD);
+		for (int i = lane; i < nodd; i += 32) hits += split_slow_piece<GENERAL>(a, sb, wodd[i], npieces, lt, tb);
+		__syncwarp();
+		/* pass 3: the table misses: memo of this call, else the merge kernels' queues */
+		nmiss = min(nmiss, WMISS);
+		for (int i = lane; i < nmiss; i += 32) {
+			const int q = wmiss[i];
+			const int r = S.plist[q];
+			hits += split_resolve_miss(a, sb, q, r, (int) S.plist[q + 1] - r, lt);
 		}
 		hits = __reduce_add_sync(0xFFFFFFFFu, hits);
 		if (lane == 0 && hits) atomicAdd(&misc[M_HITS], (uint32_t) hits);
@@ -770,9 +767,6 @@ __global__ void __launch_bounds__(JTK_NT, JTK_SPLIT_CTAS) jtk_split_lookup_kerne
 			misc[M_NSLOW] = 0;
 			misc[M_HITS] = 0;
 			misc[M_SLOWTOK] = 0;
-			misc[M_NDEF] = 0;
-			misc[M_NODD] = 0;
-			misc[M_NMISS] = 0;
 		}
 		cur = nxt;
 		nxt = misc[M_TICKET + buf];

@@ -132,6 +132,8 @@ struct jtk_tables {
 	const int32_t *bytepair;    /* 65536: rank of the two-byte token b0 b1, or JTK_RANK_MAX */
 	const jtk_slot *pair;       /* slot = {id left, id right, rank, 1} ; empty slot has w == 0 */
 	uint32_t mask_p;
+	const uint32_t *bigram_bits; /* 65536 bits: bit (b0 << 8 | b1) is set when some token contains the bytes b0 b1 next to each other.  Where it is
+	                              * clear no merge can ever join the two bytes, so bytePairMerge runs independently on both sides (jtk_safe_cut) */
 	/* special-token guard (GptBytePairEncoding.java:52-56) */
 	int32_t nspecial;
 	int32_t special_has_empty;  /* "".contains: every document is flagged */

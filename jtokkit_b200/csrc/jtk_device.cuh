@@ -915,6 +915,15 @@ JTK_HD int jtk_clz64(uint64_t m) {
 #endif
 }
 
+/* May bytePairMerge be run separately on the bytes before and after a position whose neighbouring bytes are b0, b1?  Yes when no
+ * token contains b0 b1 next to each other: every part the loop ever forms is a token (or a single byte), so no part can span the
+ * position, the pair across it never has a rank, and a merge on one side only changes ranks on that side - the global leftmost-minimum
+ * order (GptBytePairEncoding.java:232-240) restricted to either side is that side's own order.  `bits` = jtk_tables::bigram_bits. */
+JTK_HD bool jtk_safe_cut(const uint32_t *bits, uint32_t b0, uint32_t b1) {
+	const uint32_t g = (b0 << 8) | b1;
+	return !((JTK_LDG(bits + (g >> 5)) >> (g & 31)) & 1u);
+}
+
 /* MaskT = uint32_t for pieces up to 32 bytes, uint64_t up to 64 bytes */
 template <typename MaskT>
 JTK_HD int jtk_merge_short_t(const jtk_tables &T, const uint8_t *p, int n, int32_t *tok, int32_t *rk, int stride, bool *unknown) {

@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "jtk_device.cuh"
 #include "jtk_regex.h"
@@ -342,7 +343,7 @@ __device__ __forceinline__ int split_resolve_miss(const jtk_encode_args &a, cons
 		const uint4 *mp = reinterpret_cast<const uint4 *>(a.memo + entry);
 		const uint4 q0 = mp[0];
 		const uint2 q1 = *reinterpret_cast<const uint2 *>(mp + 1);
-		if (q1.x == ((a.memo_epoch << 8) | 2u) && (q1.y & 0xFFu) == (uint32_t) n && q0.x == key[0] && q0.y == key[1] && q0.z == key[2] && q0.w == key[3]) {
+		if ((q1.x >> 8) == a.memo_epoch && (q1.x & 3u) == 2u && (q1.y & 0xFFu) == (uint32_t) n && q0.x == key[0] && q0.y == key[1] && q0.z == key[2] && q0.w == key[3]) {
 			const int cnt = (int) (q1.y >> 8);
 			out = rec_make_memo(entry, cnt);
 			hits = cnt;

@@ -297,6 +297,17 @@ int jtk_build_host_tables(const jtk_params *p, jtk_host_tables *t, std::string *
 	for (int b = 0; b < 256; b++) t->byte_id[(size_t) b] = JTK_PSEUDO_BASE + b;
 	t->bytepair.assign(65536, JTK_RANK_MAX);
 
+	/* byte bigrams that occur inside some token (see jtk_tables::bigram_bits) */
+	t->bigram_bits.assign(2048, 0);
+	for (int64_t k = 0; k < ntok; k++) {
+		const uint8_t *kb = t->tok_bytes.data() + t->tok_off[(size_t) k];
+		const uint32_t len = t->tok_off[(size_t) k + 1] - t->tok_off[(size_t) k];
+		for (uint32_t i = 0; i + 1 < len; i++) {
+			const uint32_t g = (uint32_t) kb[i] << 8 | kb[i + 1];
+			t->bigram_bits[g >> 5] |= 1u << (g & 31);
+		}
+	}
+
 	int64_t n_a = 0, n_b = 0;
 	for (int64_t k = 0; k < ntok; k++) {
 		uint32_t len = t->tok_off[(size_t) k + 1] - t->tok_off[(size_t) k];
@@ -462,6 +473,7 @@ jtk_tables jtk_host_view(const jtk_host_tables &h) {
 	v.bytepair = h.bytepair.data();
 	v.pair = h.pair.data();
 	v.mask_p = h.mask_p;
+	v.bigram_bits = h.bigram_bits.data();
 	v.nspecial = h.nspecial;
 	v.special_has_empty = h.special_has_empty;
 	v.special_bytes = h.special_bytes.data();

@@ -155,11 +155,18 @@ int64_t emu_run(const emu_encoding *e, const uint8_t *bytes, int64_t total, cons
 			if (whole != JTK_RANK_MAX) {
 				ids[out_pos++] = whole;
 			} else {
+				/* like the merge kernels: independently on the segments between safe cuts (jtk_safe_cut) */
 				std::vector<int32_t> t2((size_t) n), r2((size_t) n), nx((size_t) n + 1);
-				int cnt;
-				if (n <= JTK_SHORT_PIECE) cnt = jtk_merge_short(e->view, p, (int) n, t2.data(), r2.data(), 1, &unknown);
-				else cnt = jtk_merge_seq(e->view, p, (int) n, t2.data(), r2.data(), nx.data(), &unknown);
-				for (int k = 0; k < cnt; k++) ids[out_pos++] = t2[(size_t) k];
+				int64_t sa = 0;
+				for (int64_t i = 1; i <= n; i++) {
+					if (i < n && !jtk_safe_cut(e->view.bigram_bits, p[i - 1], p[i])) continue;
+					const int64_t len = i - sa;
+					int cnt;
+					if (len <= JTK_SHORT_PIECE) cnt = jtk_merge_short(e->view, p + sa, (int) len, t2.data(), r2.data(), 1, &unknown);
+					else cnt = jtk_merge_seq(e->view, p + sa, (int) len, t2.data(), r2.data(), nx.data(), &unknown);
+					for (int k = 0; k < cnt; k++) ids[out_pos++] = t2[(size_t) k];
+					sa = i;
+				}
 			}
 		}
 		if (unknown && status) {

@@ -156,3 +156,39 @@ def test_predefined_patterns_do_not_take_the_general_path():
         assert emu.EmuEncoding(name, pat, 0x100, {b"a": 0}, {}).pattern_kind() in (1, 2)
     pat = jo.BUILTIN["cl100k_base"][0]
     assert emu.EmuEncoding("ci", pat, 0x102, {b"a": 0}, {}).pattern_kind() == 3  # CASE_INSENSITIVE: general program
+
+
+def test_segmentwise_merge_is_exact_for_random_vocabularies():
+    """The merge kernels run bytePairMerge separately on the segments between positions whose byte bigram occurs in no token
+    (jtk_safe_cut).  Random vocabularies over small alphabets - sparse and dense bigram tables, concatenations that rank below their
+    parts, missing single bytes - against the oracle's literal loop, through the emulator's copy of that segment loop."""
+    import emu
+    from oracle import jo
+    rng = random.Random(99)
+    pat = jo.BUILTIN["cl100k_base"][0]
+    for trial in range(60):
+        alphabet = "abcdefgh"[:rng.randint(2, 8)]
+        vocab = {}
+        ids = list(range(1000))
+        rng.shuffle(ids)
+        for ch in alphabet:
+            if rng.random() < 0.95:
+                vocab[ch.encode()] = ids.pop()
+        for _ in range(rng.randint(1, 40)):
+            w = "".join(rng.choice(alphabet) for _ in range(rng.randint(2, 6))).encode()
+            if w not in vocab:
+                vocab[w] = ids.pop()
+        e = emu.EmuEncoding("rnd", pat, 0x100, vocab, {})
+        o = jo.OracleEncoding("rnd", pat, 0x100, vocab, {})
+        docs = ["".join(rng.choice(alphabet) for _ in range(rng.choice([1, 2, 3, 7, 20, 60, 150]))).encode() for _ in range(40)]
+        blob = b"".join(docs)
+        off = np.zeros(len(docs) + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(x) for x in docs])
+        pf, got, tok_off, status = e.run(np.frombuffer(blob, dtype=np.uint8), off)
+        for d, doc in enumerate(docs):
+            try:
+                exp = o.encode_ordinary(doc)
+            except ValueError:
+                assert status[d] & 2, (trial, doc)  # JTK_DOC_UNKNOWN_BYTES
+                continue
+            assert got[tok_off[d]:tok_off[d + 1]].tolist() == exp, (trial, vocab, doc)

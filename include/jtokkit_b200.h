@@ -154,6 +154,12 @@ int jtk_split_batch_device(jtk_encoding *enc, int device, const uint8_t *d_utf8,
  * stays on the JVM side.)
  */
 int jtk_decode_batch(jtk_encoding *enc, const int32_t *ids, const int64_t *tok_off, int64_t ndocs, jtk_result **out);
+/* Device-resident variant of the same: all pointers are device memory on `device`, d_ids 16-byte aligned; work is enqueued on
+ * `cuda_stream` and the call returns when the bytes are written.  d_out == NULL: size query (*total_bytes only).
+ * d_out too small: JTK_E_CAPACITY with *total_bytes set.  d_doc_status must be zeroed by the caller. */
+int jtk_decode_batch_device(jtk_encoding *enc, int device, const int32_t *d_ids, int64_t nids, const int64_t *d_tok_off, int64_t ndocs, uint8_t *d_out,
+                            int64_t out_capacity, int64_t *d_byte_off, int32_t *d_doc_status, int32_t *d_bad_ids, void *cuda_stream, int64_t *total_bytes,
+                            int64_t *gpu_launches);
 const uint8_t *jtk_result_bytes(const jtk_result *r);
 const int64_t *jtk_result_byte_offsets(const jtk_result *r); /* ndocs + 1 */
 const int32_t *jtk_result_bad_ids(const jtk_result *r);      /* ndocs */

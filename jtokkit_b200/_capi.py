@@ -48,6 +48,7 @@ SIGNATURES = {
     "jtk_encode_batch_device": (C.c_int, [vp, C.c_int, vp, i64, vp, i64, u32, vp, i64, vp, vp, vp, C.POINTER(JtkDeviceInfo)]),
     "jtk_split_batch_device": (C.c_int, [vp, C.c_int, vp, i64, vp, i64, vp, vp]),
     "jtk_decode_batch": (C.c_int, [vp, vp, vp, i64, C.POINTER(vp)]),
+    "jtk_decode_batch_device": (C.c_int, [vp, C.c_int, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, C.POINTER(i64), C.POINTER(i64)]),
     "jtk_result_bytes": (vp, [vp]),
     "jtk_result_byte_offsets": (vp, [vp]),
     "jtk_result_bad_ids": (vp, [vp]),

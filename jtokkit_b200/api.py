@@ -404,6 +404,24 @@ class Encoding:
             d_status.data_ptr() if d_status is not None else None, torch.cuda.current_stream(dev).cuda_stream, C.byref(info)))
         return info.num_tokens, info.num_long_pieces, info.gpu_launches, info.tile_kernel_ms
 
+    def decode_device(self, d_ids, d_tok_off, d_out, d_byte_off, d_status, d_bad_ids, device=None):
+        """Device-resident batch decodeBytes (jtk_decode_batch_device): torch CUDA tensors in and out (int32 ids, int64 token offsets
+        -> uint8 bytes, int64 byte offsets, int32 status / first unknown id per document), on torch's current stream.
+        d_out=None asks for the byte count only.  Returns (total_bytes, gpu_launches)."""
+        import torch
+        dev = d_ids.device.index if device is None else device
+        total, launches = C.c_int64(0), C.c_int64(0)
+        nd = d_tok_off.numel() - 1
+        if d_out is not None and (d_byte_off.numel() < nd + 1 or d_status.numel() < nd or d_bad_ids.numel() < nd):
+            raise ValueError("d_byte_off needs ndocs + 1 entries, d_status and d_bad_ids ndocs")
+        rc = _capi.lib().jtk_decode_batch_device(
+            self._h, dev, d_ids.data_ptr(), d_ids.numel(), d_tok_off.data_ptr(), nd, d_out.data_ptr() if d_out is not None else None,
+            d_out.numel() if d_out is not None else 0, d_byte_off.data_ptr() if d_out is not None else None,
+            d_status.data_ptr() if d_out is not None else None, d_bad_ids.data_ptr() if d_out is not None else None,
+            torch.cuda.current_stream(dev).cuda_stream, C.byref(total), C.byref(launches))
+        _capi.check(rc)
+        return total.value, launches.value
+
     def encode_ordinary_batch(self, texts):
         return self.encode_batch(texts, ordinary=True)
 

@@ -76,6 +76,11 @@ struct jtk_workspace {
 	int64_t *d_tok_off = nullptr;
 	int32_t *d_status = nullptr;
 	cudaStream_t stream = nullptr;
+	/* scratch of the decode path */
+	int64_t *dec_tile = nullptr, *dec_sums = nullptr, *dec_total = nullptr;
+	unsigned long long *dec_badpos = nullptr;
+	int64_t dec_tiles_cap = 0, dec_docs_cap = 0;
+	int64_t *dec_total_host = nullptr; /* pinned */
 };
 
 /* per-call piece memo buffer (see jtk_memo_entry); pooled per device, an epoch per buffer makes old entries invisible */
@@ -186,6 +191,7 @@ static int init_device(jtk_encoding *e, int device) {
 	const size_t hot_bytes = ar.total;
 	const size_t o_tokb = ar.add(h.tok_bytes), o_toko = ar.add(h.tok_off), o_spb = ar.add(h.special_bytes), o_spo = ar.add(h.special_off);
 	const size_t o_deck = ar.add(h.dec_keys), o_decb = ar.add(h.dec_bytes), o_deco = ar.add(h.dec_off);
+	const size_t o_decd = ar.add(h.dec_direct);
 	const size_t o_rxi = ar.add(h.rx_inst), o_rxs = ar.add(h.rx_sets), o_rxr = ar.add(h.rx_ranges), o_spi = ar.add(h.special_ids);
 	uint8_t *base = nullptr;
 	CUDA_TRY(cudaMalloc(&base, ar.total));
@@ -213,6 +219,8 @@ static int init_device(jtk_encoding *e, int device) {
 	T.dec_keys = reinterpret_cast<const uint32_t *>(base + o_deck);
 	T.dec_bytes = base + o_decb;
 	T.dec_off = reinterpret_cast<const uint32_t *>(base + o_deco);
+	T.dec_direct = h.dec_direct.empty() ? nullptr : reinterpret_cast<const uint2 *>(base + o_decd);
+	T.dec_direct_size = (uint32_t) (h.dec_direct.size() / 2);
 	T.rx_inst = base + o_rxi;
 	T.rx_sets = base + o_rxs;
 	T.rx_ranges = reinterpret_cast<const uint32_t *>(base + o_rxr);
@@ -358,6 +366,11 @@ static void free_workspace(jtk_workspace *w) {
 	cudaFree(w->d_ids);
 	cudaFree(w->d_tok_off);
 	cudaFree(w->d_status);
+	cudaFree(w->dec_tile);
+	cudaFree(w->dec_sums);
+	cudaFree(w->dec_total);
+	cudaFree(w->dec_badpos);
+	cudaFreeHost(w->dec_total_host);
 	if (w->side_ok) {
 		for (int i = 0; i < 3; i++) {
 			cudaStreamDestroy(w->side.s[i]);
@@ -1574,7 +1587,85 @@ extern "C" int jtk_encode_batch_special(jtk_encoding *e, const uint8_t *utf8, co
 	return JTK_OK;
 }
 
-static int decode_impl(jtk_encoding *e, const int32_t *ids, const int64_t *tok_off, int64_t ndocs, jtk_result *r, std::vector<int64_t> *h_id_off) {
+/* Decode of a device-resident batch: pass 1 (bytes per tile + scan), one synchronisation to learn the byte count, pass 2.
+ * d_out == nullptr: size query only (*total_bytes).  Scratch lives in the workspace. */
+static int decode_device_impl(jtk_device_state *ds, jtk_workspace *w, const int32_t *d_ids, int64_t nids, const int64_t *d_tok_off, int64_t ndocs, uint8_t *d_out,
+                              int64_t out_capacity, int64_t *d_byte_off, int32_t *d_doc_status, int32_t *d_bad_ids, cudaStream_t st, int64_t *total_bytes,
+                              int64_t *launches, bool counted = false) {
+	if ((reinterpret_cast<uintptr_t>(d_ids) & 15) != 0) return set_error(JTK_E_ARG, "d_ids must be 16-byte aligned");
+	const int64_t nt = jtk_decode_tiles(nids);
+	if (nt + 1 > w->dec_tiles_cap) {
+		cudaFree(w->dec_tile);
+		cudaFree(w->dec_sums);
+		w->dec_tile = w->dec_sums = nullptr;
+		w->dec_tiles_cap = 0;
+		const int64_t cap = nt + nt / 4 + 16;
+		CUDA_TRY(cudaMalloc(&w->dec_tile, sizeof(int64_t) * (size_t) cap));
+		CUDA_TRY(cudaMalloc(&w->dec_sums, sizeof(int64_t) * (size_t) (jtk_scan_blocks(cap) + 1)));
+		w->dec_tiles_cap = cap;
+	}
+	if (!w->dec_total) {
+		CUDA_TRY(cudaMalloc(&w->dec_total, sizeof(int64_t)));
+		CUDA_TRY(cudaHostAlloc(&w->dec_total_host, sizeof(int64_t), cudaHostAllocDefault));
+	}
+	if (ndocs + 1 > w->dec_docs_cap) {
+		cudaFree(w->dec_badpos);
+		w->dec_badpos = nullptr;
+		w->dec_docs_cap = 0;
+		const int64_t cap = ndocs + ndocs / 4 + 16;
+		CUDA_TRY(cudaMalloc(&w->dec_badpos, sizeof(unsigned long long) * (size_t) cap));
+		w->dec_docs_cap = cap;
+	}
+	jtk_decode_args a;
+	memset(&a, 0, sizeof(a));
+	a.T = ds->T;
+	a.ids = d_ids;
+	a.nids = nids;
+	a.tok_off = d_tok_off;
+	a.ndocs = ndocs;
+	a.tile_bytes = w->dec_tile;
+	a.bad_pos = w->dec_badpos;
+	a.out = d_out;
+	a.byte_off = d_byte_off;
+	a.doc_status = d_doc_status;
+	a.bad_ids = d_bad_ids;
+	if (!counted) { /* (counted: pass 1 of the same batch has just run on this workspace: the size query of the host-buffer path) */
+		CUDA_TRY(cudaMemsetAsync(w->dec_badpos, 0xFF, sizeof(unsigned long long) * (size_t) (ndocs + 1), st));
+		CUDA_TRY(jtk_launch_decode_count(a, w->dec_sums, w->dec_total, st));
+		CUDA_TRY(cudaMemcpyAsync(w->dec_total_host, w->dec_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+		*launches = (nt > 0 ? 1 : 0) + 3;
+	}
+	*total_bytes = *w->dec_total_host;
+	if (!d_out) return JTK_OK;
+	if (*total_bytes > out_capacity) return set_error(JTK_E_CAPACITY, "output buffer too small for the decoded bytes");
+	CUDA_TRY(jtk_launch_decode_write(a, st));
+	*launches += 1;
+	return JTK_OK;
+}
+
+extern "C" int jtk_decode_batch_device(jtk_encoding *e, int device, const int32_t *d_ids, int64_t nids, const int64_t *d_tok_off, int64_t ndocs, uint8_t *d_out,
+                                       int64_t out_capacity, int64_t *d_byte_off, int32_t *d_doc_status, int32_t *d_bad_ids, void *cuda_stream,
+                                       int64_t *total_bytes, int64_t *gpu_launches) {
+	if (!e || !d_tok_off || !total_bytes || nids < 0 || ndocs < 0 || (nids > 0 && !d_ids) || (d_out && (!d_byte_off || !d_doc_status || !d_bad_ids)))
+		return set_error(JTK_E_ARG, "null argument");
+	int di = device_index(e, device);
+	if (di < 0) return set_error(JTK_E_ARG, "device is not one of the encoding's devices");
+	jtk_device_state *ds = e->devs[(size_t) di];
+	CUDA_TRY(cudaSetDevice(device));
+	jtk_workspace *w = acquire_ws(ds);
+	int64_t launches = 0;
+	int rc = decode_device_impl(ds, w, d_ids, nids, d_tok_off, ndocs, d_out, out_capacity, d_byte_off, d_doc_status, d_bad_ids,
+	                            reinterpret_cast<cudaStream_t>(cuda_stream), total_bytes, &launches);
+	if (rc == JTK_OK && d_out) CUDA_TRY(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(cuda_stream)));
+	if (gpu_launches) *gpu_launches = launches;
+	release_ws(ds, w);
+	return rc;
+}
+
+/* Host-buffer decode on the encoding's first device.  On success r->bytes (pinned) holds the bytes, r->byte_off / status / bad_ids
+ * the per-document arrays. */
+static int decode_impl(jtk_encoding *e, const int32_t *ids, const int64_t *tok_off, int64_t ndocs, jtk_result *r) {
 	jtk_device_state *ds = e->devs[0];
 	CUDA_TRY(cudaSetDevice(ds->device));
 	const int64_t nids = tok_off[ndocs];
@@ -1583,12 +1674,11 @@ static int decode_impl(jtk_encoding *e, const int32_t *ids, const int64_t *tok_o
 		if (tok_off[d + 1] < tok_off[d]) return set_error(JTK_E_ARG, "tok_off is not monotone");
 	cudaStream_t st;
 	CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-	int32_t *d_ids = nullptr, *d_idx = nullptr, *d_status = nullptr, *d_bad = nullptr;
-	int64_t *d_tok_off = nullptr, *d_id_off = nullptr, *d_sums = nullptr, *d_total = nullptr, *d_byte_off = nullptr;
-	unsigned long long *d_badpos = nullptr;
+	jtk_workspace *w = acquire_ws(ds);
+	int32_t *d_ids = nullptr, *d_status = nullptr, *d_bad = nullptr;
+	int64_t *d_tok_off = nullptr, *d_byte_off = nullptr;
 	uint8_t *d_out = nullptr;
 	int rc = JTK_OK;
-	const int64_t nb = jtk_scan_blocks(nids + 1);
 	do {
 		cudaError_t ce;
 #define DTRY(expr)                                                                       \
@@ -1596,41 +1686,20 @@ static int decode_impl(jtk_encoding *e, const int32_t *ids, const int64_t *tok_o
 		rc = set_error(JTK_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(ce)); \
 		break;                                                                           \
 	}
-		DTRY(cudaMalloc(&d_ids, sizeof(int32_t) * (size_t) std::max<int64_t>(nids, 1)));
-		DTRY(cudaMalloc(&d_idx, sizeof(int32_t) * (size_t) std::max<int64_t>(nids, 1)));
+		DTRY(cudaMalloc(&d_ids, sizeof(int32_t) * (size_t) std::max<int64_t>(nids, 4)));
 		DTRY(cudaMalloc(&d_tok_off, sizeof(int64_t) * (size_t) (ndocs + 1)));
-		DTRY(cudaMalloc(&d_id_off, sizeof(int64_t) * (size_t) (nids + 1)));
-		DTRY(cudaMalloc(&d_sums, sizeof(int64_t) * (size_t) (nb + 1)));
-		DTRY(cudaMalloc(&d_total, sizeof(int64_t)));
 		DTRY(cudaMalloc(&d_byte_off, sizeof(int64_t) * (size_t) (ndocs + 1)));
 		DTRY(cudaMalloc(&d_status, sizeof(int32_t) * (size_t) (ndocs + 1)));
 		DTRY(cudaMalloc(&d_bad, sizeof(int32_t) * (size_t) (ndocs + 1)));
-		DTRY(cudaMalloc(&d_badpos, sizeof(unsigned long long) * (size_t) (ndocs + 1)));
 		if (nids > 0) DTRY(cudaMemcpyAsync(d_ids, ids, sizeof(int32_t) * (size_t) nids, cudaMemcpyHostToDevice, st));
 		DTRY(cudaMemcpyAsync(d_tok_off, tok_off, sizeof(int64_t) * (size_t) (ndocs + 1), cudaMemcpyHostToDevice, st));
-		DTRY(cudaMemsetAsync(d_badpos, 0xFF, sizeof(unsigned long long) * (size_t) (ndocs + 1), st));
 		DTRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t) * (size_t) (ndocs + 1), st));
-		DTRY(cudaMemsetAsync(d_id_off + nids, 0, sizeof(int64_t), st));
-		jtk_decode_args a;
-		memset(&a, 0, sizeof(a));
-		a.T = ds->T;
-		a.ids = d_ids;
-		a.nids = nids;
-		a.tok_off = d_tok_off;
-		a.ndocs = ndocs;
-		a.id_byte_off = d_id_off;
-		a.byte_off = d_byte_off;
-		a.doc_status = d_status;
-		a.bad_ids = d_bad;
-		DTRY(jtk_launch_decode_lengths(a, d_idx, d_badpos, d_sums, d_total, st));
-		int64_t total = 0;
-		DTRY(cudaMemcpyAsync(&total, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-		DTRY(cudaStreamSynchronize(st));
-		DTRY(cudaMalloc(&d_out, (size_t) std::max<int64_t>(total, 1)));
-		a.out = d_out;
-		DTRY(jtk_launch_decode_gather(a, d_idx, d_badpos, st));
+		int64_t total = 0, launches = 0;
+		if ((rc = decode_device_impl(ds, w, d_ids, nids, d_tok_off, ndocs, nullptr, 0, nullptr, nullptr, nullptr, st, &total, &launches)) != JTK_OK) break;
+		DTRY(cudaMalloc(&d_out, (size_t) std::max<int64_t>(total, 1) + 16));
+		if ((rc = decode_device_impl(ds, w, d_ids, nids, d_tok_off, ndocs, d_out, total, d_byte_off, d_status, d_bad, st, &total, &launches, true)) != JTK_OK) break;
 		r->nbytes = total;
-		r->launches = (nids > 0 ? 1 : 0) + 4;
+		r->launches = launches;
 		if ((rc = pinned_get(e, total, &r->bytes)) != JTK_OK) break;
 		if ((rc = pinned_get(e, sizeof(int64_t) * (ndocs + 1), &r->byte_off)) != JTK_OK) break;
 		if ((rc = pinned_get(e, sizeof(int32_t) * (ndocs + 1), &r->status)) != JTK_OK) break;
@@ -1639,25 +1708,17 @@ static int decode_impl(jtk_encoding *e, const int32_t *ids, const int64_t *tok_o
 		DTRY(cudaMemcpyAsync(r->byte_off.p, d_byte_off, sizeof(int64_t) * (size_t) (ndocs + 1), cudaMemcpyDeviceToHost, st));
 		DTRY(cudaMemcpyAsync(r->status.p, d_status, sizeof(int32_t) * (size_t) (ndocs + 1), cudaMemcpyDeviceToHost, st));
 		DTRY(cudaMemcpyAsync(r->bad_ids.p, d_bad, sizeof(int32_t) * (size_t) (ndocs + 1), cudaMemcpyDeviceToHost, st));
-		if (h_id_off) {
-			h_id_off->resize((size_t) nids + 1);
-			DTRY(cudaMemcpyAsync(h_id_off->data(), d_id_off, sizeof(int64_t) * (size_t) (nids + 1), cudaMemcpyDeviceToHost, st));
-		}
 		DTRY(cudaStreamSynchronize(st));
 #undef DTRY
 	} while (0);
 	cudaFree(d_ids);
-	cudaFree(d_idx);
 	cudaFree(d_tok_off);
-	cudaFree(d_id_off);
-	cudaFree(d_sums);
-	cudaFree(d_total);
 	cudaFree(d_byte_off);
 	cudaFree(d_status);
 	cudaFree(d_bad);
-	cudaFree(d_badpos);
 	cudaFree(d_out);
 	cudaStreamDestroy(st);
+	release_ws(ds, w);
 	return rc;
 }
 
@@ -1669,7 +1730,7 @@ extern "C" int jtk_decode_batch(jtk_encoding *e, const int32_t *ids, const int64
 	r->enc = e;
 	r->ndocs = ndocs;
 	r->ntokens = tok_off[ndocs];
-	int rc = decode_impl(e, ids, tok_off, ndocs, r, nullptr);
+	int rc = decode_impl(e, ids, tok_off, ndocs, r);
 	if (rc != JTK_OK) {
 		std::string keep = g_last_error;
 		jtk_result_free(r);
@@ -1768,8 +1829,25 @@ extern "C" int jtk_encode_max_tokens(jtk_encoding *e, const uint8_t *utf8, int64
 	jtk_result dr;
 	dr.enc = e;
 	const int64_t tok_off[2] = {0, k};
-	std::vector<int64_t> id_off;
-	rc = decode_impl(e, tok.data(), tok_off, 1, &dr, &id_off);
+	rc = decode_impl(e, tok.data(), tok_off, 1, &dr);
+	/* byte offset of every token of the clipped prefix (lengths from the registration-time tables: the bytes themselves came from the device) */
+	std::vector<int64_t> id_off((size_t) k + 1, 0);
+	for (int64_t i = 0; i < k && rc == JTK_OK; i++) {
+		const jtk_host_tables &h = e->host;
+		int64_t len = -1;
+		uint32_t sl = jtk_hash_pair(tok[(size_t) i], 0) & h.mask_d;
+		for (;;) {
+			const uint32_t v = h.dec_keys[2 * sl + 1];
+			if (v == 0) break;
+			if (h.dec_keys[2 * sl] == (uint32_t) tok[(size_t) i]) {
+				len = (int64_t) h.dec_off[v] - h.dec_off[v - 1];
+				break;
+			}
+			sl = (sl + 1) & h.mask_d;
+		}
+		if (len < 0) rc = set_error(JTK_E_ARG, "internal: encode produced an id the decode table does not know");
+		id_off[(size_t) i + 1] = id_off[(size_t) i] + std::max<int64_t>(len, 0);
+	}
 	std::vector<uint8_t> dbytes;
 	if (rc == JTK_OK) dbytes.assign(static_cast<uint8_t *>(dr.bytes.p), static_cast<uint8_t *>(dr.bytes.p) + dr.nbytes);
 	pinned_put(e, dr.bytes);

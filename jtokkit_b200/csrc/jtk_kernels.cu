@@ -1787,34 +1787,75 @@ namespace {
 constexpr int SCAN_NT = 256;
 constexpr int SCAN_ITEMS = 16;
 
-__device__ __forceinline__ int decode_find(const jtk_tables &T, int32_t id) {
+/* token id -> (offset into dec_bytes, length); false for an id that neither map knows (GptBytePairEncoding.java:302-314) */
+__device__ __forceinline__ bool decode_entry(const jtk_tables &T, int32_t id, uint32_t *off, uint32_t *len) {
+	if (T.dec_direct) { /* ids are small non-negative numbers (all predefined encodings): one 8-byte read */
+		if ((uint32_t) id >= T.dec_direct_size) return false;
+		const uint2 e = __ldg(T.dec_direct + id);
+		*off = e.x;
+		*len = e.y;
+		return e.y != 0xFFFFFFFFu;
+	}
 	uint32_t s = jtk_hash_pair(id, 0) & T.mask_d;
 	for (;;) {
 		const uint32_t v = T.dec_keys[2 * s + 1];
-		if (v == 0) return -1;
-		if (T.dec_keys[2 * s] == (uint32_t) id) return (int) v - 1;
+		if (v == 0) return false;
+		if (T.dec_keys[2 * s] == (uint32_t) id) {
+			*off = T.dec_off[v - 1];
+			*len = T.dec_off[v] - *off;
+			return true;
+		}
 		s = (s + 1) & T.mask_d;
 	}
 }
 
-__global__ void jtk_decode_lengths_kernel(const jtk_decode_args a, int32_t *tok_index, unsigned long long *bad_pos) {
-	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-	for (int64_t j = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; j < a.nids; j += stride) {
-		const int idx = decode_find(a.T, a.ids[j]);
-		tok_index[j] = idx;
-		if (idx >= 0) {
-			a.id_byte_off[j] = a.T.dec_off[idx + 1] - a.T.dec_off[idx];
+constexpr int DNT = 256;           /* threads per CTA of the decode kernels */
+constexpr int DPT = 16;            /* consecutive tokens per thread */
+constexpr int DTILE = DNT * DPT;   /* tokens per tile */
+constexpr int DWIN = 24 * 1024;    /* bytes of a tile staged in shared memory at a time (a tile of typical text is ~11 KB) */
+
+/* pass 1: bytes per tile of DTILE tokens; unknown ids are reported per document (the smallest position) */
+__global__ void __launch_bounds__(DNT) jtk_decode_count_kernel(const __grid_constant__ jtk_decode_args a) {
+	__shared__ int s_w[DNT / 32];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int64_t t0 = (int64_t) blockIdx.x * DTILE + (int64_t) tid * DPT;
+	int32_t ids[DPT];
+	if (t0 + DPT <= a.nids) { /* tiles start at multiples of 4096 tokens: 16-byte aligned */
+#pragma unroll
+		for (int i = 0; i < DPT / 4; i++) {
+			const int4 v = __ldg(reinterpret_cast<const int4 *>(a.ids + t0) + i);
+			ids[4 * i] = v.x, ids[4 * i + 1] = v.y, ids[4 * i + 2] = v.z, ids[4 * i + 3] = v.w;
+		}
+	} else {
+#pragma unroll
+		for (int i = 0; i < DPT; i++) ids[i] = t0 + i < a.nids ? a.ids[t0 + i] : 0;
+	}
+	int sum = 0;
+#pragma unroll
+	for (int i = 0; i < DPT; i++) {
+		if (t0 + i >= a.nids) break;
+		uint32_t off, len;
+		if (decode_entry(a.T, ids[i], &off, &len)) {
+			sum += (int) len;
 		} else {
-			a.id_byte_off[j] = 0;
-			/* document of token j: last d with tok_off[d] <= j */
+			/* document of token j: the last d with tok_off[d] <= j */
+			const int64_t j = t0 + i;
 			int64_t lo = 0, hi = a.ndocs - 1;
 			while (lo < hi) {
-				int64_t mid = (lo + hi + 1) >> 1;
+				const int64_t mid = (lo + hi + 1) >> 1;
 				if (a.tok_off[mid] <= j) lo = mid;
 				else hi = mid - 1;
 			}
-			atomicMin(bad_pos + lo, (unsigned long long) j);
+			atomicMin(a.bad_pos + lo, (unsigned long long) j);
 		}
+	}
+	sum = __reduce_add_sync(0xFFFFFFFFu, sum);
+	if (lane == 0) s_w[warp] = sum;
+	__syncthreads();
+	if (tid == 0) {
+		int t = 0;
+		for (int w = 0; w < DNT / 32; w++) t += s_w[w];
+		a.tile_bytes[blockIdx.x] = t;
 	}
 }
 
@@ -1895,19 +1936,92 @@ __global__ void jtk_scan_add_kernel(int64_t *data, int64_t n, const int64_t *blo
 		if (base + i < n) data[base + i] += add;
 }
 
-__global__ void jtk_decode_gather_kernel(const jtk_decode_args a, const int32_t *tok_index, const unsigned long long *bad_pos) {
-	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-	for (int64_t j = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; j < a.nids; j += stride) {
-		const int idx = tok_index[j];
-		if (idx < 0) continue;
-		const uint32_t s = a.T.dec_off[idx], e = a.T.dec_off[idx + 1];
-		uint8_t *dst = a.out + a.id_byte_off[j];
-		for (uint32_t k = s; k < e; k++) dst[k - s] = a.T.dec_bytes[k];
+/* pass 2: one CTA per tile: per-token byte offsets by a block scan, token bytes copied into a shared-memory window that has the
+ * same 16-byte misalignment as its place in the output, then flushed with 16-byte stores; document byte offsets, statuses */
+__global__ void __launch_bounds__(DNT) jtk_decode_write_kernel(const __grid_constant__ jtk_decode_args a) {
+	__shared__ __align__(16) uint8_t s_out[DWIN + 32];
+	__shared__ int s_pref[DNT + 1];
+	__shared__ int s_w[DNT / 32];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int64_t tile0 = (int64_t) blockIdx.x * DTILE;
+	const int64_t t0 = tile0 + (int64_t) tid * DPT;
+	const int64_t base = a.tile_bytes[blockIdx.x]; /* exclusive scan of pass 1 */
+	uint32_t off[DPT], len[DPT];
+	int sum = 0;
+#pragma unroll
+	for (int i = 0; i < DPT; i++) {
+		off[i] = 0, len[i] = 0;
+		if (t0 + i < a.nids && !decode_entry(a.T, __ldg(a.ids + t0 + i), &off[i], &len[i])) len[i] = 0;
+		sum += (int) len[i];
 	}
-	for (int64_t d = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; d <= a.ndocs; d += stride) {
-		a.byte_off[d] = a.id_byte_off[a.tok_off[d]];
+	int x = sum;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const int y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+		if (lane >= o) x += y;
+	}
+	if (lane == 31) s_w[warp] = x;
+	__syncthreads();
+	int wpre = 0, total = 0;
+	for (int w = 0; w < DNT / 32; w++) {
+		if (w < warp) wpre += s_w[w];
+		total += s_w[w];
+	}
+	const int mine = wpre + x - sum; /* tile-relative byte offset of this thread's first token */
+	s_pref[tid] = mine;
+	if (tid == DNT - 1) s_pref[DNT] = total;
+	for (int w0 = 0; w0 < total; w0 += DWIN) {
+		const int mis = (int) ((base + w0) & 15);
+		const int wn = min(DWIN, total - w0); /* bytes of this window */
+		__syncthreads();
+		int pos = mine - w0;
+#pragma unroll
+		for (int i = 0; i < DPT; i++) {
+			const int l = (int) len[i];
+			if (l && pos + l > 0 && pos < wn) {
+				const uint8_t *src = a.T.dec_bytes + off[i];
+				const int k0 = pos < 0 ? -pos : 0, k1 = min(l, wn - pos);
+				for (int k = k0; k < k1; k++) s_out[mis + pos + k] = src[k];
+			}
+			pos += l;
+		}
+		__syncthreads();
+		/* flush: staging byte mis + k <-> output byte base + w0 + k; whole 16-byte groups with one store, the ragged ends bytewise */
+		uint8_t *const gout = a.out + (base + w0 - mis);
+		const int nchunk = (mis + wn + 15) >> 4;
+		for (int c = tid; c < nchunk; c += DNT) {
+			const int lo = c == 0 ? mis : 0, hi = min(16, mis + wn - 16 * c);
+			if (lo == 0 && hi == 16) {
+				*reinterpret_cast<uint4 *>(gout + 16 * c) = *reinterpret_cast<const uint4 *>(s_out + 16 * c);
+			} else {
+				for (int k = lo; k < hi; k++) gout[16 * c + k] = s_out[16 * c + k];
+			}
+		}
+	}
+	__syncthreads();
+	/* documents whose first token lies in this tile (the last tile also takes the documents that start at the very end) */
+	const bool last = blockIdx.x == gridDim.x - 1;
+	const int64_t tile_end = last ? a.nids + 1 : tile0 + DTILE;
+	int64_t lo = 0, hi = a.ndocs + 1; /* first d in [0, ndocs] with tok_off[d] >= tile0 */
+	while (lo < hi) {
+		const int64_t mid = (lo + hi) >> 1;
+		if (a.tok_off[mid] >= tile0) hi = mid;
+		else lo = mid + 1;
+	}
+	for (int64_t d = lo + tid; d <= a.ndocs; d += DNT) {
+		const int64_t j = a.tok_off[d];
+		if (j >= tile_end) break;
+		const int jl = (int) (j - tile0);
+		int before = jl >= DTILE ? total : s_pref[jl / DPT];
+		if (jl < DTILE)
+			for (int i = 0; i < jl % DPT; i++) {
+				uint32_t o2, l2;
+				const int64_t jj = tile0 + jl - jl % DPT + i;
+				if (jj < a.nids && decode_entry(a.T, a.ids[jj], &o2, &l2)) before += (int) l2;
+			}
+		a.byte_off[d] = base + before;
 		if (d < a.ndocs) {
-			const unsigned long long bp = bad_pos[d];
+			const unsigned long long bp = a.bad_pos[d];
 			if (bp != ~0ull) {
 				a.doc_status[d] |= JTK_DOC_UNKNOWN_ID;
 				a.bad_ids[d] = a.ids[bp];
@@ -2025,18 +2139,19 @@ cudaError_t jtk_launch_special_gather(const jtk_special_args &a, int64_t ntok, c
 
 int64_t jtk_scan_blocks(int64_t n) { return (n + SCAN_NT * SCAN_ITEMS - 1) / (SCAN_NT * SCAN_ITEMS); }
 
-/* id_byte_off has nids + 1 entries; entry nids must be zero on entry and receives the total. */
-cudaError_t jtk_launch_decode_lengths(const jtk_decode_args &a, int32_t *tok_index, unsigned long long *bad_pos, int64_t *block_sums, int64_t *total,
-                                      cudaStream_t st) {
-	if (a.nids > 0) {
-		unsigned grid = (unsigned) std::min<int64_t>((a.nids + 255) / 256, 148 * 16);
-		jtk_decode_lengths_kernel<<<grid, 256, 0, st>>>(a, tok_index, bad_pos);
-	}
-	const int64_t n = a.nids + 1;
+int64_t jtk_decode_tiles(int64_t nids) { return nids > 0 ? (nids + DTILE - 1) / DTILE : 0; }
+
+/* pass 1 + scan: a.tile_bytes (jtk_decode_tiles(nids) + 1 entries) ends up holding the exclusive scan of the bytes per tile, *total
+ * (device) the byte count.  a.bad_pos: ndocs entries preset to ~0; block_sums: jtk_scan_blocks(tiles + 1) scratch. */
+cudaError_t jtk_launch_decode_count(const jtk_decode_args &a, int64_t *block_sums, int64_t *total, cudaStream_t st) {
+	const int64_t nt = jtk_decode_tiles(a.nids);
+	if (nt > 0) jtk_decode_count_kernel<<<(unsigned) nt, DNT, 0, st>>>(a);
+	cudaMemsetAsync(a.tile_bytes + nt, 0, sizeof(int64_t), st);
+	const int64_t n = nt + 1;
 	const int64_t nb = jtk_scan_blocks(n);
-	jtk_scan_block_kernel<<<(unsigned) nb, SCAN_NT, 0, st>>>(a.id_byte_off, n, block_sums);
+	jtk_scan_block_kernel<<<(unsigned) nb, SCAN_NT, 0, st>>>(a.tile_bytes, n, block_sums);
 	jtk_scan_sums_kernel<<<1, 1024, 0, st>>>(block_sums, nb, total);
-	jtk_scan_add_kernel<<<(unsigned) nb, SCAN_NT, 0, st>>>(a.id_byte_off, n, block_sums);
+	jtk_scan_add_kernel<<<(unsigned) nb, SCAN_NT, 0, st>>>(a.tile_bytes, n, block_sums);
 	return cudaGetLastError();
 }
 
@@ -2048,9 +2163,9 @@ cudaError_t jtk_launch_exclusive_scan(int64_t *data, int64_t n, int64_t *block_s
 	return cudaGetLastError();
 }
 
-cudaError_t jtk_launch_decode_gather(const jtk_decode_args &a, const int32_t *tok_index, const unsigned long long *bad_pos, cudaStream_t st) {
-	const int64_t work = std::max<int64_t>(a.nids, a.ndocs + 1);
-	unsigned grid = (unsigned) std::min<int64_t>((work + 255) / 256, 148 * 16);
-	jtk_decode_gather_kernel<<<grid, 256, 0, st>>>(a, tok_index, bad_pos);
+/* pass 2; with no tokens at all one CTA still writes the document byte offsets */
+cudaError_t jtk_launch_decode_write(const jtk_decode_args &a, cudaStream_t st) {
+	const int64_t nt = jtk_decode_tiles(a.nids);
+	jtk_decode_write_kernel<<<(unsigned) (nt > 0 ? nt : 1), DNT, 0, st>>>(a);
 	return cudaGetLastError();
 }

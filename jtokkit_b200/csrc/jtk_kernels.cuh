@@ -161,24 +161,23 @@ cudaError_t jtk_launch_special_gather(const jtk_special_args &a, int64_t nseg_to
 /* in-place exclusive scan of data[0..n) (int64); *total (device) receives the sum; block_sums: jtk_scan_blocks(n) scratch */
 cudaError_t jtk_launch_exclusive_scan(int64_t *data, int64_t n, int64_t *block_sums, int64_t *total, cudaStream_t st);
 
-/* decode path */
+/* decode path: ids -> bytes (GptBytePairEncoding.decodeBytes / decodeToken, :136-151,302-314) in two passes over tiles of 4 096 tokens */
 struct jtk_decode_args {
 	jtk_tables T;
-	const int32_t *ids;
+	const int32_t *ids; /* 16-byte aligned */
 	int64_t nids;
 	const int64_t *tok_off;
 	int64_t ndocs;
-	int64_t *id_byte_off; /* nids + 1: exclusive scan of token byte lengths */
+	int64_t *tile_bytes;          /* jtk_decode_tiles(nids) + 1: bytes per tile, then their exclusive scan */
+	unsigned long long *bad_pos;  /* ndocs, preset to ~0: position of the first unknown id of a document */
 	uint8_t *out;
 	int64_t *byte_off; /* ndocs + 1 */
 	int32_t *doc_status;
 	int32_t *bad_ids;
 };
 int64_t jtk_scan_blocks(int64_t n);
-/* tok_index: nids scratch; bad_pos: ndocs entries preset to ~0; block_sums: jtk_scan_blocks(nids + 1) scratch;
- * total: device int64 receiving the byte count.  id_byte_off[nids] must be zero on entry. */
-cudaError_t jtk_launch_decode_lengths(const jtk_decode_args &a, int32_t *tok_index, unsigned long long *bad_pos, int64_t *block_sums, int64_t *total,
-                                      cudaStream_t st);
-cudaError_t jtk_launch_decode_gather(const jtk_decode_args &a, const int32_t *tok_index, const unsigned long long *bad_pos, cudaStream_t st);
+int64_t jtk_decode_tiles(int64_t nids);
+cudaError_t jtk_launch_decode_count(const jtk_decode_args &a, int64_t *block_sums, int64_t *total, cudaStream_t st);
+cudaError_t jtk_launch_decode_write(const jtk_decode_args &a, cudaStream_t st);
 
 #endif

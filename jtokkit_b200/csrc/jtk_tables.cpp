@@ -448,6 +448,30 @@ int jtk_build_host_tables(const jtk_params *p, jtk_host_tables *t, std::string *
 		for (auto &kv : last)
 			if (!ordinary.count(kv.first)) dec_put(kv.first, kv.second, true);
 	}
+	/* direct form of the same map for dense id spaces (every predefined encoding): id -> (offset, length) */
+	{
+		int64_t max_id = -1;
+		bool neg = false;
+		for (int64_t k = 0; k < ntok; k++) {
+			max_id = std::max<int64_t>(max_id, t->tok_rank[(size_t) k]);
+			neg |= t->tok_rank[(size_t) k] < 0;
+		}
+		for (int64_t i = 0; i < p->special_size; i++) {
+			max_id = std::max<int64_t>(max_id, t->special_ids[(size_t) i]);
+			neg |= t->special_ids[(size_t) i] < 0;
+		}
+		t->dec_direct.clear();
+		if (!neg && max_id >= 0 && max_id < (4 << 20)) {
+			t->dec_direct.assign(2 * (size_t) (max_id + 1), 0xFFFFFFFFu);
+			auto put = [&](int32_t id, int64_t index) {
+				t->dec_direct[2 * (size_t) id] = t->dec_off[(size_t) index];
+				t->dec_direct[2 * (size_t) id + 1] = t->dec_off[(size_t) index + 1] - t->dec_off[(size_t) index];
+			};
+			/* the same precedence as the hash form: among ordinary tokens the last key put for an id wins, special tokens only where no ordinary token has the id */
+			for (int64_t i = 0; i < p->special_size; i++) put(t->special_ids[(size_t) i], ndec_ord + i);
+			for (int64_t k = 0; k < ntok; k++) put(t->tok_rank[(size_t) k], k);
+		}
+	}
 	return JTK_OK;
 }
 
@@ -484,6 +508,8 @@ jtk_tables jtk_host_view(const jtk_host_tables &h) {
 	v.mask_d = h.mask_d;
 	v.dec_bytes = h.dec_bytes.data();
 	v.dec_off = h.dec_off.data();
+	v.dec_direct = h.dec_direct.empty() ? nullptr : reinterpret_cast<const uint2 *>(h.dec_direct.data());
+	v.dec_direct_size = (uint32_t) (h.dec_direct.size() / 2);
 	v.rx_inst = h.rx_inst.data();
 	v.rx_sets = h.rx_sets.data();
 	v.rx_ranges = h.rx_ranges.data();

@@ -216,3 +216,52 @@ def test_encode_packed_rejects_inconsistent_offsets(gpu_encodings):
         with pytest.raises(ValueError):
             enc.encode_packed(data, np.array(off, dtype=np.int64))
     assert enc.encode_packed(data, np.array([0, 5, 11], dtype=np.int64)).to_lists() == [[15339], [1917]]
+
+
+def test_device_resident_decode_round_trip_and_unknown_ids(gpu_encodings):
+    """jtk_decode_batch_device: decode(encode(x)) == x for a 64 MiB multilingual batch entirely on the device, byte
+    offsets per document, unknown ids reported per document with the first offending id (GptBytePairEncoding.java:313), empty
+    documents and the size query."""
+    import torch
+    from jtokkit_b200 import synth, _capi
+    enc = gpu_encodings["cl100k_base"]
+    data, off = synth.config3_multilingual("cuda", total=64 << 20, seed=21)
+    n, nd = data.numel(), off.numel() - 1
+    d_in = torch.zeros(n + 80, dtype=torch.uint8, device="cuda")
+    d_in[:n] = data
+    d_ids = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_tok = torch.empty(nd + 1, dtype=torch.int64, device="cuda")
+    d_st = torch.zeros(nd + 1, dtype=torch.int32, device="cuda")
+    ntok, _, _, _ = enc.encode_device(d_in[:n], off, d_ids, d_tok, d_st)
+    total, launches = enc.decode_device(d_ids[:ntok], d_tok, None, None, None, None)
+    assert total == n and launches > 0
+    d_out = torch.full((n + 64,), 0xEE, dtype=torch.uint8, device="cuda")
+    d_boff = torch.empty(nd + 1, dtype=torch.int64, device="cuda")
+    d_dst = torch.zeros(nd, dtype=torch.int32, device="cuda")
+    d_bad = torch.empty(nd, dtype=torch.int32, device="cuda")
+    total, _ = enc.decode_device(d_ids[:ntok], d_tok, d_out[:n], d_boff, d_dst, d_bad)
+    assert total == n and torch.equal(d_out[:n], data) and int(d_out[n:].min()) == 0xEE  # nothing written past the end
+    assert torch.equal(d_boff, off) and int(d_dst.max()) == 0
+    # capacity error
+    with pytest.raises(_capi.JtkError) as ei:
+        enc.decode_device(d_ids[:ntok], d_tok, d_out[:n - 1], d_boff, d_dst, d_bad)
+    assert ei.value.code == _capi.JTK_E_CAPACITY
+    # unknown ids: documents 3 and 5 get one each, document 5 two (the first one is reported); special tokens decode to their text
+    ids = d_ids[:ntok].clone()
+    tok = d_tok.cpu().numpy()
+    ids[int(tok[3]) + 2] = 100261
+    ids[int(tok[5]) + 1] = 2000000
+    ids[int(tok[5]) + 4] = -7
+    ids[int(tok[7])] = 100257
+    d_dst.zero_()
+    total2, _ = enc.decode_device(ids, d_tok, d_out, d_boff, d_dst, d_bad)
+    st, bad = d_dst.cpu().numpy(), d_bad.cpu().numpy()
+    assert st[3] == _capi.DOC_UNKNOWN_ID and bad[3] == 100261 and st[5] == _capi.DOC_UNKNOWN_ID and bad[5] == 2000000
+    assert st.sum() == 2 * _capi.DOC_UNKNOWN_ID
+    b7 = int(d_boff[7])
+    assert bytes(d_out[b7:b7 + 13].cpu().numpy()) == b"<|endoftext|>"
+    # empty batch, empty documents
+    z = torch.zeros(4, dtype=torch.int32, device="cuda")
+    t0 = torch.zeros(4, dtype=torch.int64, device="cuda")
+    total3, _ = enc.decode_device(z[:0], t0, d_out, d_boff, d_dst, d_bad)
+    assert total3 == 0 and int(d_boff[:4].abs().max()) == 0

@@ -263,6 +263,28 @@ def run_ours(args):
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     assert int(d_status.max().item()) == 0, "synthetic corpus must not trip the special-token guard"
 
+    # ---- decode: the step's 404 M ids back to bytes, device resident; must reproduce the corpus
+    d_dec = torch.empty(nbytes + 64, dtype=torch.uint8, device=dev)
+    d_boff = torch.empty(ndocs + 1, dtype=torch.int64, device=dev)
+    d_dst = torch.zeros(ndocs + 1, dtype=torch.int32, device=dev)
+    d_dbad = torch.empty(ndocs + 1, dtype=torch.int32, device=dev)
+    ids_view = d_ids[:ntok]
+    for _ in range(2):
+        enc.decode_device(ids_view, d_tok_off, d_dec[:nbytes], d_boff, d_dst, d_dbad)
+    torch.cuda.synchronize()
+    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    q0.record()
+    dec_launches = 0
+    for _ in range(args.steps):
+        dec_total, nl = enc.decode_device(ids_view, d_tok_off, d_dec[:nbytes], d_boff, d_dst, d_dbad)
+        dec_launches += nl
+    q1.record()
+    torch.cuda.synchronize()
+    dec_ms = q0.elapsed_time(q1) / args.steps
+    dec_ok = dec_total == nbytes and bool(torch.equal(d_dec[:nbytes], d_view)) and bool(torch.equal(d_boff, doc_off.to(dev))) and int(d_dst.max().item()) == 0
+    dec_algo = 4 * ntok + nbytes + 16 * (ndocs + 1)
+    del d_dec
+
     # ---- end to end through the host-buffer C-ABI call, pinned host input
     h_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
     h_in.copy_(d_view)
@@ -389,6 +411,10 @@ def run_ours(args):
                      "frac_whole_step": algo_bytes / (dev_ms / args.steps * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": int(algo_bytes), "peak_source": peak_src,
                      "frac_of_nominal_8000": achieved / 8000.0},
         "strong": strong,
+        "decode": {"api": "jtk_decode_batch_device (ids of the step, resident in HBM -> bytes)", "ms_per_step": dec_ms, "tokens_per_s": ntok / (dec_ms * 1e-3),
+                   "algorithmic_bytes": int(dec_algo), "achieved_gb_per_s": dec_algo / (dec_ms * 1e-3) / 1e9, "frac_of_hbm_peak": dec_algo / (dec_ms * 1e-3) / 1e9 / peak,
+                   "gpu_launches_per_step": int(dec_launches // args.steps),
+                   "parity": "decoded bytes and document offsets identical to the corpus" if dec_ok else "MISMATCH: decode(encode(x)) != x"},
         "cpu_baseline": cpu,
         "cpu_tiktoken": tk,
         "parity": parity,
@@ -396,7 +422,7 @@ def run_ours(args):
         "host_cores": os.cpu_count(),
     }
     print(json.dumps(out), flush=True)
-    if parity is not None and parity.startswith("MISMATCH"):
+    if (parity is not None and parity.startswith("MISMATCH")) or not dec_ok:
         raise SystemExit(3)  # a fast result that differs from the reference algorithm is not a result
 
 

@@ -4,14 +4,19 @@
 #include <algorithm>
 #include <cstring>
 #include <memory>
+#include <string>
+#include <vector>
+
+#include "unicode_ranges.inc"
 
 namespace {
 
-enum { N_SET, N_CAT, N_ALT, N_REP, N_LOOK, N_EMPTY, N_BOL, N_EOL };
+enum { N_SET, N_CAT, N_ALT, N_REP, N_LOOK, N_EMPTY, N_BOL, N_EOL, N_WORDB };
 
 struct node {
 	int type = N_EMPTY;
-	int set = -1;                          /* N_SET */
+	int set = -1;                          /* N_SET; N_WORDB: the word-character set */
+	int set2 = -1, set3 = -1;              /* N_WORDB: non-spacing marks, letters-or-digits */
 	std::vector<std::unique_ptr<node>> kids; /* N_CAT, N_ALT */
 	std::unique_ptr<node> sub;             /* N_REP, N_LOOK */
 	int min = 0, max = 0, mode = 0;        /* N_REP */
@@ -21,6 +26,7 @@ struct node {
 struct set_builder {
 	bool neg = false, dot = false;
 	std::vector<std::pair<uint32_t, uint32_t>> ranges;
+	std::vector<std::pair<uint32_t, uint32_t>> prop_ranges; /* from \\p{..} / \\d / \\w: Unicode properties, not subject to case folding */
 	uint32_t flags = 0;
 	bool ci = false;
 };
@@ -73,6 +79,7 @@ struct parser {
 			}
 			b.ranges.insert(b.ranges.end(), extra.begin(), extra.end());
 		}
+		b.ranges.insert(b.ranges.end(), b.prop_ranges.begin(), b.prop_ranges.end());
 		std::sort(b.ranges.begin(), b.ranges.end());
 		std::vector<std::pair<uint32_t, uint32_t>> merged;
 		for (auto &r : b.ranges) {
@@ -104,6 +111,70 @@ struct parser {
 			}
 		out->sets.push_back(s);
 		return (int) out->sets.size() - 1;
+	}
+
+	/* Unicode general categories (unicode_ranges.inc: JTK_UC_GC) as a bit mask over the category indices; 0 = unknown name */
+	static uint32_t gc_mask_of(const std::string &name) {
+		static const char *const names = JTK_UC_GC_NAMES;
+		if (name.size() == 2) {
+			for (int g = 0; g < 30; g++)
+				if (names[3 * g] == name[0] && names[3 * g + 1] == name[1]) return 1u << g;
+			if (name == "LC") return 7u; /* Lu Ll Lt */
+			return 0;
+		}
+		if (name.size() == 1) {
+			uint32_t m = 0;
+			for (int g = 0; g < 30; g++)
+				if (names[3 * g] == name[0]) m |= 1u << g;
+			return m;
+		}
+		return 0;
+	}
+	/* adds the code points whose category is in `mask` (or is not, for neg) */
+	static void add_gc(std::vector<std::pair<uint32_t, uint32_t>> &dst, uint32_t mask, bool neg) {
+		std::vector<std::pair<uint32_t, uint32_t>> in;
+		uint32_t next = 0; /* first code point not yet covered by a listed (assigned) range: the gaps are Cn */
+		const bool cn = (mask >> 29) & 1u;
+		for (int k = 0; k < JTK_UC_GC_COUNT; k++) {
+			const uint32_t lo = JTK_UC_GC[k][0], hi = JTK_UC_GC[k][1], g = JTK_UC_GC[k][2];
+			if (cn && lo > next) in.emplace_back(next, lo - 1);
+			if ((mask >> g) & 1u) in.emplace_back(lo, hi);
+			next = hi + 1;
+		}
+		if (cn && next <= 0x10FFFF) in.emplace_back(next, 0x10FFFF);
+		add_ranges(dst, in, neg);
+	}
+	/* dst += in, or its complement within [0, 0x10FFFF] (in: sorted, disjoint) */
+	static void add_ranges(std::vector<std::pair<uint32_t, uint32_t>> &dst, std::vector<std::pair<uint32_t, uint32_t>> in, bool neg) {
+		std::sort(in.begin(), in.end());
+		if (!neg) {
+			dst.insert(dst.end(), in.begin(), in.end());
+			return;
+		}
+		uint32_t next = 0;
+		for (auto &r : in) {
+			if (r.first > next) dst.emplace_back(next, r.first - 1);
+			next = std::max(next, r.second + 1);
+		}
+		if (next <= 0x10FFFF) dst.emplace_back(next, 0x10FFFF);
+	}
+	static std::vector<std::pair<uint32_t, uint32_t>> table_ranges(const uint32_t (*t)[2], int n) {
+		std::vector<std::pair<uint32_t, uint32_t>> v;
+		for (int k = 0; k < n; k++) v.emplace_back(t[k][0], t[k][1]);
+		return v;
+	}
+	/* \w under UNICODE_CHARACTER_CLASS: [\p{Alpha}\p{gc=Mn}\p{gc=Me}\p{gc=Mc}\p{Digit}\p{gc=Pc}\p{IsJoin_Control}] (java.util.regex.Pattern) */
+	static std::vector<std::pair<uint32_t, uint32_t>> unicode_word() {
+		std::vector<std::pair<uint32_t, uint32_t>> w = table_ranges(JTK_UC_ALPHA, JTK_UC_ALPHA_COUNT);
+		add_gc(w, (1u << 5) | (1u << 6) | (1u << 7) | (1u << 8) | (1u << 11), false); /* Mn Mc Me Nd Pc */
+		w.emplace_back(0x200C, 0x200D);
+		std::sort(w.begin(), w.end());
+		std::vector<std::pair<uint32_t, uint32_t>> m;
+		for (auto &r : w) {
+			if (!m.empty() && r.first <= m.back().second + 1) m.back().second = std::max(m.back().second, r.second);
+			else m.push_back(r);
+		}
+		return m;
 	}
 
 	static int hexval(int c) {
@@ -145,18 +216,21 @@ struct parser {
 			}
 			return -1;
 		case 'd':
-			if (ucc) fail("\\d under UNICODE_CHARACTER_CLASS is not supported");
-			b.ranges.emplace_back('0', '9');
+		case 'D': { /* [0-9], or \p{Nd} under UNICODE_CHARACTER_CLASS */
+			std::vector<std::pair<uint32_t, uint32_t>> in;
+			if (ucc) add_gc(in, 1u << 8, false);
+			else in.emplace_back('0', '9');
+			add_ranges(b.prop_ranges, in, c == 'D');
 			return -1;
+		}
 		case 'w':
-			if (ucc) fail("\\w under UNICODE_CHARACTER_CLASS is not supported");
-			b.ranges.emplace_back('0', '9');
-			b.ranges.emplace_back('a', 'z');
-			b.ranges.emplace_back('A', 'Z');
-			b.ranges.emplace_back('_', '_');
+		case 'W': { /* [a-zA-Z_0-9], or the Unicode word characters under UNICODE_CHARACTER_CLASS */
+			std::vector<std::pair<uint32_t, uint32_t>> in;
+			if (ucc) in = unicode_word();
+			else in = {{'0', '9'}, {'A', 'Z'}, {'_', '_'}, {'a', 'z'}};
+			add_ranges(b.prop_ranges, in, c == 'W');
 			return -1;
-		case 'D':
-		case 'W': fail("\\D and \\W are not supported"); return -1;
+		}
 		case 'x': {
 			int v = 0;
 			if (eat('{')) {
@@ -204,7 +278,27 @@ struct parser {
 			}
 			if (name == "L" || name == "IsL" || name == "gc=L" || name == "general_category=L") b.flags |= neg ? JTK_RX_HAS_NOT_L : JTK_RX_HAS_L;
 			else if (name == "N" || name == "IsN" || name == "gc=N" || name == "general_category=N") b.flags |= neg ? JTK_RX_HAS_NOT_N : JTK_RX_HAS_N;
-			else fail("unsupported \\p{...} property (only L and N are supported)");
+			else {
+				std::string nm = name;
+				for (const char *pre : {"Is", "gc=", "general_category="})
+					if (nm.rfind(pre, 0) == 0) {
+						nm = nm.substr(strlen(pre));
+						break;
+					}
+				const uint32_t mask = gc_mask_of(nm);
+				if (mask) add_gc(b.prop_ranges, mask, neg);
+				else if (nm == "Alphabetic" || (ucc && nm == "Alpha")) add_ranges(b.prop_ranges, table_ranges(JTK_UC_ALPHA, JTK_UC_ALPHA_COUNT), neg);
+				else if (nm == "Alpha") add_ranges(b.prop_ranges, {{'A', 'Z'}, {'a', 'z'}}, neg);
+				else if (nm == "White_Space" || nm == "WhiteSpace" || (ucc && nm == "Space")) add_ranges(b.prop_ranges, table_ranges(JTK_UC_WS, JTK_UC_WS_COUNT), neg);
+				else if (nm == "Space") add_ranges(b.prop_ranges, {{9, 13}, {' ', ' '}}, neg);
+				else if (nm == "Digit") {
+					std::vector<std::pair<uint32_t, uint32_t>> in;
+					if (ucc) add_gc(in, 1u << 8, false);
+					else in.emplace_back('0', '9');
+					add_ranges(b.prop_ranges, in, neg);
+				} else if (nm == "ASCII") add_ranges(b.prop_ranges, {{0, 127}}, neg);
+				else fail("unsupported \\p{...} property (general categories, Alphabetic, White_Space, Alpha, Digit, Space and ASCII are supported)");
+			}
 			return -1;
 		}
 		default:
@@ -352,7 +446,27 @@ struct parser {
 		if (c == '\\') {
 			i++;
 			int nc = peek();
-			if (nc == 'b' || nc == 'B' || nc == 'A' || nc == 'z' || nc == 'Z' || nc == 'G' || nc == 'R' || nc == 'X' || nc == 'Q' || nc == 'h' || nc == 'H' || nc == 'v' ||
+			if (nc == 'b' || nc == 'B') { /* word boundary (java.util.regex.Pattern.Bound) */
+				i++;
+				auto nd = std::make_unique<node>();
+				nd->type = N_WORDB;
+				nd->min = nc == 'B';
+				const bool ucc2 = (flags & JTK_RE_UNICODE_CHARACTER_CLASS) != 0;
+				set_builder w, mn, ld;
+				/* isWord: the Unicode word characters under UNICODE_CHARACTER_CLASS, else '_' or Character.isLetterOrDigit */
+				if (ucc2) w.prop_ranges = unicode_word();
+				else {
+					add_gc(w.prop_ranges, 0x1Fu | (1u << 8), false);
+					w.prop_ranges.emplace_back('_', '_');
+				}
+				add_gc(mn.prop_ranges, 1u << 5, false);           /* NON_SPACING_MARK */
+				add_gc(ld.prop_ranges, 0x1Fu | (1u << 8), false); /* Character.isLetterOrDigit: L* or Nd */
+				nd->set = finish_set(w);
+				nd->set2 = finish_set(mn);
+				nd->set3 = finish_set(ld);
+				return nd;
+			}
+			if (nc == 'A' || nc == 'z' || nc == 'Z' || nc == 'G' || nc == 'R' || nc == 'X' || nc == 'Q' || nc == 'h' || nc == 'H' || nc == 'v' ||
 			    nc == 'V' || nc == 'k' || (nc >= '1' && nc <= '9')) {
 				fail("unsupported escape (boundary / back-reference / quoting)");
 				return std::make_unique<node>();
@@ -475,6 +589,7 @@ struct parser {
 		case N_SET: code.push_back({JTK_RX_SET, nd->set, 0, 0, 0}); break;
 		case N_BOL: code.push_back({JTK_RX_BOL, 0, 0, 0, 0}); break;
 		case N_EOL: code.push_back({JTK_RX_EOL, 0, 0, 0, 0}); break;
+		case N_WORDB: code.push_back({JTK_RX_WORDB, nd->min, nd->set, nd->set2, nd->set3}); break;
 		case N_CAT:
 			for (auto &k : nd->kids) emit(k.get());
 			break;
@@ -638,7 +753,8 @@ int jtk_rx_compile(const char *pattern, int flags, jtk_rx_compiled *out, std::st
 			case JTK_RX_JMP: todo.push_back(in.a); break;
 			case JTK_RX_LOOK: /* zero width: the sub-program does not consume, matching goes on at pc + 1 */
 			case JTK_RX_BOL:
-			case JTK_RX_EOL: todo.push_back(pc + 1); break;
+			case JTK_RX_EOL:
+			case JTK_RX_WORDB: todo.push_back(pc + 1); break;
 			default: any = true; /* MATCH reached without consuming: the pattern can match the empty string */
 			}
 		}

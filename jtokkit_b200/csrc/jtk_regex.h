@@ -9,8 +9,11 @@
  * lazy / possessive quantifiers with backtracking, (?i) / (?i:...) with ASCII case folding (+ U+017F / U+212A under
  * UNICODE_CASE), positive / negative look-ahead, ^ $ ., Matcher.find() resumption (after an empty match the search
  * advances by one character), characters matched by no alternative are skipped.
+ * Unicode properties: every general category (\p{Lu}, \p{IsLu}, \p{gc=Lu}, one-letter groups, LC), Alphabetic, White_Space and
+ * the POSIX names Alpha / Digit / Space / ASCII; \d \D \w \W and \b \B in their ASCII and UNICODE_CHARACTER_CLASS meanings
+ * (tables of Unicode 15.0, unicode_ranges.inc; \b as java.util.regex.Pattern.Bound of JDK 11-18 defines it).
  * Not supported (registration fails with JTK_E_PATTERN_UNSUPPORTED, nothing falls back to the CPU): look-behind,
- * back-references, \b, named groups, class intersection, \d / \w under UNICODE_CHARACTER_CLASS, \p{..} other than L and N,
+ * back-references, named groups, class intersection / nested classes, script / block properties, \A \z \Z \G \R \X \Q..\E,
  * loops over sub-expressions that can match the empty string, counted loops beyond 16.
  */
 #ifndef JTK_REGEX_H
@@ -28,7 +31,8 @@ enum {
 	JTK_RX_LOOK,       /* a = 1 negative / 0 positive, b = pc of the sub-program (ends in MATCH); continues at pc + 1 */
 	JTK_RX_BOL,
 	JTK_RX_EOL,
-	JTK_RX_MATCH
+	JTK_RX_MATCH,
+	JTK_RX_WORDB       /* a = 1 for \\B; b, c, d = sets: word characters, non-spacing marks, letters-or-digits (java.util.regex.Pattern.Bound) */
 };
 
 struct jtk_rx_inst {
@@ -253,6 +257,30 @@ JTK_HD int64_t jtk_rx_run(const jtk_rx_program &P, const jtk_tables &T, const ui
 				if (cp == '\r' && pos + 2 == n && s[pos + 1] == '\n') ok = true;
 			}
 			if (!ok) fail = true;
+			else pc++;
+			break;
+		}
+		case JTK_RX_WORDB: {
+			/* Pattern.Bound.check: a character is a word character if isWord(ch), or if it is a non-spacing mark that follows a
+			 * letter or digit (possibly across other non-spacing marks) */
+			if (pos + 4 > n) *hit_end = true;
+			auto word_at = [&](int64_t at) { /* character starting at byte position `at` (lo <= at < n) */
+				int len;
+				const uint32_t cp = jtk_rx_decode(s, at, n, &len);
+				if (jtk_rx_in_set(P, T, in.b, cp)) return true;
+				if (!jtk_rx_in_set(P, T, in.c, cp)) return false;
+				int64_t q = at;
+				while (q > lo) { /* hasBaseCharacter: walk back over non-spacing marks */
+					q = jtk_rx_prev(s, q, lo);
+					const uint32_t c2 = jtk_rx_decode(s, q, n, &len);
+					if (jtk_rx_in_set(P, T, in.d, c2)) return true;
+					if (!jtk_rx_in_set(P, T, in.c, c2)) return false;
+				}
+				return false;
+			};
+			const bool left = pos > lo && word_at(jtk_rx_prev(s, pos, lo));
+			const bool right = pos < n && word_at(pos);
+			if ((left != right) == (in.a != 0)) fail = true;
 			else pc++;
 			break;
 		}

@@ -35,18 +35,43 @@ static inline uint8_t uc_get(uint32_t cp) {
 	if (!uc_flags) uc_init();
 	return cp < 0x110000 ? uc_flags[cp] : 0;
 }
+/* general category index per code point (order of JTK_UC_GC_NAMES; 29 = Cn) and the Alphabetic property, filled on first use */
+static uint8_t *uc_gc;
+static void uc_gc_init(void) {
+	uint8_t *t = (uint8_t *) malloc(0x110000);
+	memset(t, 29, 0x110000);
+	for (int k = 0; k < JTK_UC_GC_COUNT; k++)
+		for (uint32_t cp = JTK_UC_GC[k][0]; cp <= JTK_UC_GC[k][1]; cp++) t[cp] = (uint8_t) JTK_UC_GC[k][2];
+	for (int k = 0; k < JTK_UC_ALPHA_COUNT; k++)
+		for (uint32_t cp = JTK_UC_ALPHA[k][0]; cp <= JTK_UC_ALPHA[k][1]; cp++) t[cp] |= 0x80;
+	if (!__sync_bool_compare_and_swap(&uc_gc, NULL, t)) free(t);
+}
+static inline int uc_category(uint32_t cp) {
+	if (!uc_gc) uc_gc_init();
+	return cp < 0x110000 ? (uc_gc[cp] & 0x7F) : 29;
+}
+static inline int uc_alphabetic(uint32_t cp) {
+	if (!uc_gc) uc_gc_init();
+	return cp < 0x110000 ? (uc_gc[cp] >> 7) : 0;
+}
+/* \w under UNICODE_CHARACTER_CLASS: [\p{Alpha}\p{gc=Mn}\p{gc=Me}\p{gc=Mc}\p{Digit}\p{gc=Pc}\p{IsJoin_Control}] */
+static int uc_word(uint32_t cp) {
+	const int g = uc_category(cp);
+	return uc_alphabetic(cp) || g == 5 || g == 6 || g == 7 || g == 8 || g == 11 || cp == 0x200C || cp == 0x200D;
+}
 int jo_uc_is_letter(uint32_t cp) { return uc_get(cp) & 1; }
 int jo_uc_is_number(uint32_t cp) { return (uc_get(cp) >> 1) & 1; }
 int jo_uc_is_space(uint32_t cp) { return (uc_get(cp) >> 2) & 1; }
 
 /* ------------------------------------------------------------------ node tree */
-enum { N_SET, N_ANY, N_CAT, N_ALT, N_REP, N_LOOK, N_EMPTY, N_BOL, N_EOL };
-enum { C_L = 1, C_N, C_SPACE, C_DIGIT, C_WORD };
+enum { N_SET, N_ANY, N_CAT, N_ALT, N_REP, N_LOOK, N_EMPTY, N_BOL, N_EOL, N_WORDB };
+enum { C_L = 1, C_N, C_SPACE, C_DIGIT, C_WORD, C_GC /* mask of general categories */, C_ALPHA, C_ASCII };
 enum { Q_GREEDY, Q_LAZY, Q_POSSESSIVE };
 
 typedef struct cls_item {
 	int kind; /* C_* */
 	int neg;
+	uint32_t mask; /* C_GC */
 } cls_item;
 
 typedef struct node {
@@ -118,7 +143,23 @@ static void add_cls(node *nd, int kind, int neg) {
 	nd->cls = (cls_item *) realloc(nd->cls, sizeof(cls_item) * (size_t) (nd->ncls + 1));
 	nd->cls[nd->ncls].kind = kind;
 	nd->cls[nd->ncls].neg = neg;
+	nd->cls[nd->ncls].mask = 0;
 	nd->ncls++;
+}
+static void add_gc_cls(node *nd, uint32_t mask, int neg) {
+	add_cls(nd, C_GC, neg);
+	nd->cls[nd->ncls - 1].mask = mask;
+}
+/* mask of general categories for a one- or two-letter name (JTK_UC_GC_NAMES order), 0 = unknown */
+static uint32_t gc_mask_of(const char *name) {
+	static const char *const names = JTK_UC_GC_NAMES;
+	uint32_t m = 0;
+	if (!strcmp(name, "LC")) return 7u;
+	for (int g = 0; g < 30; g++) {
+		if (name[0] && name[1] && !name[2] && names[3 * g] == name[0] && names[3 * g + 1] == name[1]) m |= 1u << g;
+		if (name[0] && !name[1] && names[3 * g] == name[0]) m |= 1u << g;
+	}
+	return m;
 }
 
 static int peek(parser *ps) { return ps->i < ps->n ? (int) ps->p[ps->i] : -1; }
@@ -218,11 +259,7 @@ static int parse_escape(parser *ps, node *set, int *lit) {
 	case 'D':
 	case 'w':
 	case 'W':
-		if (ps->flags & JO_RE_UNICODE_CHARACTER_CLASS) {
-			fail(ps, "\\d and \\w under UNICODE_CHARACTER_CLASS are not supported");
-			return 0;
-		}
-		add_cls(set, (c == 'd' || c == 'D') ? C_DIGIT : C_WORD, c == 'D' || c == 'W');
+		add_cls(set, (c == 'd' || c == 'D') ? C_DIGIT : C_WORD, c == 'D' || c == 'W'); /* ASCII or Unicode meaning: cls_match */
 		return 1;
 	case 'p':
 	case 'P': {
@@ -243,8 +280,29 @@ static int parse_escape(parser *ps, node *set, int *lit) {
 		if (!strcmp(name, "L") || !strcmp(name, "IsL") || !strcmp(name, "gc=L") || !strcmp(name, "general_category=L")) add_cls(set, C_L, neg);
 		else if (!strcmp(name, "N") || !strcmp(name, "IsN") || !strcmp(name, "gc=N") || !strcmp(name, "general_category=N")) add_cls(set, C_N, neg);
 		else {
-			fail(ps, "unsupported \\p{...} property (only L and N are supported)");
-			return 0;
+			const char *nm = name;
+			if (!strncmp(nm, "Is", 2)) nm += 2;
+			else if (!strncmp(nm, "gc=", 3)) nm += 3;
+			else if (!strncmp(nm, "general_category=", 17)) nm += 17;
+			const uint32_t mask = gc_mask_of(nm);
+			const int ucc = (ps->flags & JO_RE_UNICODE_CHARACTER_CLASS) != 0;
+			if (mask) add_gc_cls(set, mask, neg);
+			else if (!strcmp(nm, "Alphabetic") || (ucc && !strcmp(nm, "Alpha"))) add_cls(set, C_ALPHA, neg);
+			else if (!strcmp(nm, "Alpha")) {
+				/* ASCII letters: as a nested item so that negation applies to the pair of ranges as a whole */
+				add_gc_cls(set, 3u, neg);
+				set->cls[set->ncls - 1].kind = C_ASCII; /* mask 3: letters */
+			} else if (!strcmp(nm, "White_Space") || !strcmp(nm, "WhiteSpace")) {
+				add_cls(set, C_SPACE, neg);
+				set->cls[set->ncls - 1].mask = 1; /* always the Unicode property */
+			} else if (!strcmp(nm, "Space")) add_cls(set, C_SPACE, neg);
+			else if (!strcmp(nm, "Digit")) add_cls(set, C_DIGIT, neg);
+			else if (!strcmp(nm, "ASCII")) {
+				add_cls(set, C_ASCII, neg);
+			} else {
+				fail(ps, "unsupported \\p{...} property");
+				return 0;
+			}
 		}
 		return 1;
 	}
@@ -388,7 +446,13 @@ static node *parse_atom(parser *ps, int *ci) {
 	if (c == '\\') {
 		ps->i++;
 		int nc = peek(ps);
-		if (nc == 'b' || nc == 'B' || nc == 'A' || nc == 'z' || nc == 'Z' || nc == 'G' || nc == 'R' || nc == 'X' || nc == 'Q' || nc == 'h' || nc == 'H' || nc == 'v' || nc == 'V' ||
+		if (nc == 'b' || nc == 'B') { /* word boundary */
+			ps->i++;
+			node *wb = new_node(ps, N_WORDB);
+			wb->look_neg = nc == 'B';
+			return wb;
+		}
+		if (nc == 'A' || nc == 'z' || nc == 'Z' || nc == 'G' || nc == 'R' || nc == 'X' || nc == 'Q' || nc == 'h' || nc == 'H' || nc == 'v' || nc == 'V' ||
 		    (nc >= '1' && nc <= '9') || nc == 'k') {
 			fail(ps, "unsupported escape (boundary / back-reference / quoting)");
 			return new_node(ps, N_EMPTY);
@@ -469,7 +533,7 @@ static node *parse_quantified(parser *ps, int *ci) {
 		rep->mode = Q_GREEDY;
 		if (eat(ps, '?')) rep->mode = Q_LAZY;
 		else if (eat(ps, '+')) rep->mode = Q_POSSESSIVE;
-		if (atom->type == N_LOOK || atom->type == N_EMPTY || atom->type == N_BOL || atom->type == N_EOL) {
+		if (atom->type == N_LOOK || atom->type == N_EMPTY || atom->type == N_BOL || atom->type == N_EOL || atom->type == N_WORDB) {
 			fail(ps, "quantifier on a zero-width construct is not supported");
 			return atom;
 		}
@@ -562,18 +626,24 @@ typedef struct mctx {
 	int64_t n;
 } mctx;
 
-static int cls_match(int kind, uint32_t cp, int ucc) {
-	switch (kind) {
+static int cls_match(const cls_item *it, uint32_t cp, int ucc) {
+	switch (it->kind) {
 	case C_L: return jo_uc_is_letter(cp);
 	case C_N: return jo_uc_is_number(cp);
 	case C_SPACE:
-		if (ucc) return jo_uc_is_space(cp);
+		if (ucc || it->mask) return jo_uc_is_space(cp);
 		return cp == ' ' || (cp >= 0x09 && cp <= 0x0D);
-	case C_DIGIT: /* \d and \w under UNICODE_CHARACTER_CLASS need Nd / Alphabetic tables the oracle does not
-	               * carry; such patterns are rejected in parse_escape, so only the ASCII meaning is left. */
+	case C_DIGIT: /* [0-9], or general category Nd under UNICODE_CHARACTER_CLASS */
+		if (ucc) return uc_category(cp) == 8;
 		return cp >= '0' && cp <= '9';
 	case C_WORD:
+		if (ucc) return uc_word(cp);
 		return (cp >= 'a' && cp <= 'z') || (cp >= 'A' && cp <= 'Z') || (cp >= '0' && cp <= '9') || cp == '_';
+	case C_GC: return (int) ((it->mask >> uc_category(cp)) & 1u);
+	case C_ALPHA: return uc_alphabetic(cp);
+	case C_ASCII:
+		if (it->mask == 3u) return (cp >= 'a' && cp <= 'z') || (cp >= 'A' && cp <= 'Z');
+		return cp < 128;
 	}
 	return 0;
 }
@@ -582,7 +652,7 @@ static int set_match_one(const node *nd, uint32_t cp, int ucc) {
 	for (int i = 0; i < nd->nranges; i++)
 		if (cp >= nd->ranges[i][0] && cp <= nd->ranges[i][1]) return 1;
 	for (int i = 0; i < nd->ncls; i++)
-		if (cls_match(nd->cls[i].kind, cp, ucc) != nd->cls[i].neg) return 1;
+		if (cls_match(&nd->cls[i], cp, ucc) != nd->cls[i].neg) return 1;
 	return 0;
 }
 
@@ -658,6 +728,7 @@ static void compute_first(const mctx *m, node *nd) {
 	case N_EMPTY:
 	case N_BOL:
 	case N_EOL:
+	case N_WORDB:
 		nd->nullable = 1;
 		break;
 	case N_LOOK:
@@ -764,6 +835,21 @@ static int64_t m_cat(const mctx *m, const node *cat, int idx, int64_t i, const k
 	return m_node(m, cat->kids[idx], i, &frames[0]);
 }
 
+/* Bound.isWord(ch) || (getType(ch) == NON_SPACING_MARK && hasBaseCharacter): the character at index i */
+static int word_char_at(const mctx *m, int64_t i) {
+	const int ucc = (m->re->flags & JO_RE_UNICODE_CHARACTER_CLASS) != 0;
+	const uint32_t cp = m->s[i];
+	const int g = uc_category(cp);
+	if (ucc ? uc_word(cp) : (cp == '_' || g <= 4 || g == 8)) return 1;
+	if (g != 5) return 0;
+	for (int64_t q = i - 1; q >= 0; q--) { /* hasBaseCharacter: back over non-spacing marks to a letter or digit */
+		const int g2 = uc_category(m->s[q]);
+		if (g2 <= 4 || g2 == 8) return 1;
+		if (g2 != 5) return 0;
+	}
+	return 0;
+}
+
 static int64_t m_node(const mctx *m, const node *nd, int64_t i, const kont *k) {
 	switch (nd->type) {
 	case N_EMPTY: return run_k(m, k, i);
@@ -777,6 +863,11 @@ static int64_t m_node(const mctx *m, const node *nd, int64_t i, const kont *k) {
 	case N_EOL: /* Java '$' without MULTILINE: at end, or before a final line terminator */
 		if (i == m->n || (i == m->n - 1 && is_line_term(m->s[i])) || (i == m->n - 2 && m->s[i] == '\r' && m->s[i + 1] == '\n')) return run_k(m, k, i);
 		return -1;
+	case N_WORDB: { /* java.util.regex.Pattern.Bound.check (JDK 11-18) */
+		const int left = i > 0 && word_char_at(m, i - 1), right = i < m->n && word_char_at(m, i);
+		if ((left != right) == (nd->look_neg != 0)) return -1;
+		return run_k(m, k, i);
+	}
 	case N_CAT: return m_cat(m, nd, 0, i, k);
 	case N_ALT:
 		for (int b = 0; b < nd->nkids; b++) {

@@ -54,10 +54,26 @@ def test_registration_fails_loudly_without_a_gpu():
 def test_unsupported_pattern_is_rejected_at_registration():
     """Patterns outside the device pattern compiler's subset fail at registration (they never run on the CPU instead)."""
     import jtokkit_b200 as jt
-    for pat in [r"(?<=a)b", r"\bword\b", r"(a)\1", r"(?:a*)*", r"[a-z&&[^b]]", r"\p{Lu}+", r"a{2,1}", r"(", r"x{17}y(?:ab){20}"]:
+    for pat in [r"(?<=a)b", r"(?<!a)b", r"(a)\1", r"(?<n>a)\k<n>", r"(?:a*)*", r"[a-z&&[^b]]", r"\p{IsLatin}+", r"\p{InGreek}", r"a{2,1}", r"(", r"x{17}y(?:ab){20}", r"\Ga", r"\X"]:
         params = jt.GptBytePairEncodingParams("custom", jt.Pattern.compile(pat), {b"a": 0}, {})
         with pytest.raises(ValueError):
             jt.EncodingFactory.from_parameters(params)
+
+
+def test_unicode_properties_and_word_boundaries_compile():
+    """What round 1 rejected and a JTokkit user can legally register (AbstractEncodingRegistry.java:63-66): general categories, \\w / \\d
+    under UNICODE_CHARACTER_CLASS (the factory's own flag, EncodingFactory.java:129), \\b.  Registration gets as far as the device."""
+    import torch
+    import jtokkit_b200 as jt
+    from jtokkit_b200 import _capi
+    for pat, flags in [(r"\p{Lu}+|\p{Ll}+|.", 0), (r"\w+|\d+|\s+", 0x100), (r"\bword\b|.", 0), (r"\b\w+\b|\W", 0x100), (r"[\p{IsAlphabetic}\p{Mn}]+|\P{L}", 0x100)]:
+        params = jt.GptBytePairEncodingParams("custom", jt.Pattern.compile(pat, flags), {b"a": 0}, {})
+        if torch.cuda.is_available():
+            jt.EncodingFactory.from_parameters(params).close()
+        else:
+            with pytest.raises(_capi.JtkError) as ei:
+                jt.EncodingFactory.from_parameters(params)
+            assert ei.value.code == _capi.JTK_E_CUDA  # the pattern compiled; only the device is missing
 
 
 def test_product_does_not_import_the_oracle():

@@ -97,6 +97,10 @@ GENERAL_PATTERNS = [
     (r"^\w+|\w+$|\s", 0), (r"'(?:[sdmt]|ll|ve|re)| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+", 0),
     (r"'s|'t|'re|'ve|'m|'ll|'d| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+", 0x102),
     (r"(?:\p{L}\p{N}?)+| (?! )|[^ ]", 0x100), (r"[一-鿿]+|\x41{2}|\x{1F355}|[a-zé-ü]+|\S", 0),
+    # Unicode properties and word boundaries (general categories, Alphabetic, \d \w \b with and without UNICODE_CHARACTER_CLASS)
+    (r"\p{Lu}\p{Ll}+|\p{Nd}+|\s+|.", 0x100), (r"\w+|\W+", 0x100), (r"\d+|\D", 0x100), (r"\p{Lu}+|\p{Ll}+|\P{L}", 0),
+    (r"[\p{Sc}\p{Sm}]+|\p{P}|\p{IsAlphabetic}+|\p{Z}+|.", 0x100), (r"\b\w+\b|\W", 0x100), (r"\B.|.", 0x100), (r"\bfoo\b|\w+|\W", 0),
+    (r"[^\W\d_]+|\d{1,3}|[\W_]", 0x100), (r"\p{gc=Mn}+|\p{IsLo}|\p{LC}+|\P{M}", 0),
 ]
 
 

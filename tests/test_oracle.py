@@ -159,3 +159,27 @@ def test_java_utf16_decoding_of_truncated_sequences():
     assert dec("🍕".encode()) == [0xD83C, 0xDF55]       # surrogate pair
     assert dec(b"\x80a") == [0xFFFD, 0x61]              # stray continuation byte
     assert dec(b"\xe2\x28\xa1") == [0xFFFD, 0x28, 0xFFFD]
+
+
+def test_oracle_unicode_properties_and_boundaries_against_the_regex_module():
+    """The oracle's restatement of \\p{..}, \\w, \\d and \\b (java.util.regex semantics, Unicode 15.0 tables) against the `regex` module on
+    stable code points.  \\b is compared under UNICODE_CHARACTER_CLASS only (without it Java asks Character.isLetterOrDigit, which
+    no Python engine mirrors) and without stray combining marks (Java's hasBaseCharacter rule differs from UTS #18 there)."""
+    import random
+    import regex
+    from oracle import jo
+    pats = [(r"\p{Lu}\p{Ll}+|\p{Nd}+|\s+|.", 0x100, True), (r"\w+|\W+", 0x100, True), (r"\d+|\D", 0x100, True), (r"\w+|[^\w\s]+|\s+", 0, False),
+            (r"\p{Lu}+|\p{Ll}+|\P{L}", 0, True), (r"[\p{Sc}\p{Sm}]+|\p{P}|\p{IsAlphabetic}+|\p{Z}+|.", 0x100, True), (r"\b\w+\b|\W", 0x100, True),
+            (r"\B.|.", 0x100, True), (r"[^\W\d_]+|\d{1,3}|[\W_]", 0x100, True), (r"\p{gc=Mn}+|\p{IsLo}|\p{LC}+|\P{M}", 0, True)]
+    alph = list("abcXYZ 019_-+$€£±.,;!?'\"()[]\n\t") + ["é", "ß", "Ж", "я", "中", "あ", "١", "२", "½", "Ⅷ", "ǅ", "ʰ", "　", " ", "—", "“", "𝐀", "🍕", "한", "é", "ा"]
+    rng = random.Random(5)
+    for pat, fl, unicode_mode in pats:
+        o = jo.OracleEncoding("t", pat, fl, {bytes([b]): b for b in range(256)}, {})
+        r = regex.compile(pat.replace(r"\p{IsAlphabetic}", r"\p{Alphabetic}").replace(r"\p{IsLo}", r"\p{Lo}"), regex.V0 | (regex.UNICODE if unicode_mode else regex.ASCII))
+        for _ in range(300):
+            t = "".join(rng.choice(alph) for _ in range(rng.randint(0, 30)))
+            boff = [0]
+            for ch in t:
+                boff.append(boff[-1] + len(ch.encode()))
+            exp = [(boff[m.start()], boff[m.end()]) for m in r.finditer(t) if m.end() > m.start()]
+            assert [(a, e) for a, e in o.split(t.encode()) if e > a] == exp, (pat, t)

@@ -32,9 +32,34 @@ public final class CudaBytePairEncoding implements Encoding, AutoCloseable {
 
 	private final String name;
 	private final MemorySegment handle;
+	private final boolean[] singleByteTokens = new boolean[256]; // which single bytes are tokens (for the exception text of TokenEncoder.java:67)
 
+	/** Devices from the system property jtokkit.cuda.devices ("0,1,2,3" or "all"; default: device 0). */
 	public CudaBytePairEncoding(final GptBytePairEncodingParams params) {
+		this(params, devicesFromProperty());
+	}
+
+	private static int[] devicesFromProperty() {
+		final String v = System.getProperty("jtokkit.cuda.devices", "0").trim();
+		if (v.equals("all")) {
+			final int n = Integer.getInteger("jtokkit.cuda.deviceCount", 8); // one box of B200s
+			final int[] all = new int[n];
+			for (int i = 0; i < n; i++) all[i] = i;
+			return all;
+		}
+		final String[] parts = v.split(",");
+		final int[] out = new int[parts.length];
+		for (int i = 0; i < parts.length; i++) out[i] = Integer.parseInt(parts[i].trim());
+		return out;
+	}
+
+	/**
+	 * @param devices CUDA devices the tables are replicated on; a batch is cut into byte-balanced document chunks and chunk c runs on
+	 *                devices[c % devices.length] inside jtk_encode_batch (AbstractMultiThreadedBenchmark.java:34-45 with GPUs as workers)
+	 */
+	public CudaBytePairEncoding(final GptBytePairEncodingParams params, final int[] devices) {
 		this.name = params.getName();
+		for (final byte[] k : params.getEncoder().keySet()) if (k.length == 1) singleByteTokens[k[0] & 0xFF] = true;
 		try (Arena arena = Arena.ofConfined()) {
 			final MemorySegment p = arena.allocate(PARAMS);
 			p.set(ADDRESS, 0, arena.allocateFrom(params.getName()));
@@ -84,7 +109,9 @@ public final class CudaBytePairEncoding implements Encoding, AutoCloseable {
 			p.set(ADDRESS, 72, si);
 			p.set(JAVA_LONG, 80, sp.size());
 			final MemorySegment out = arena.allocate(ADDRESS);
-			final int rc = (int) JtkNative.ENCODING_CREATE.invokeExact(p, MemorySegment.NULL, 0, out);
+			final MemorySegment devs = arena.allocate(JAVA_INT, Math.max(devices.length, 1));
+			for (int d = 0; d < devices.length; d++) devs.setAtIndex(JAVA_INT, d, devices[d]);
+			final int rc = (int) JtkNative.ENCODING_CREATE.invokeExact(p, devs, devices.length, out);
 			if (rc == JtkNative.JTK_E_PATTERN_UNSUPPORTED) throw new IllegalArgumentException("split pattern not supported on the device: " + JtkNative.lastError());
 			if (rc != JtkNative.JTK_OK) throw new IllegalStateException(JtkNative.lastError());
 			this.handle = out.get(ADDRESS, 0);
@@ -163,10 +190,23 @@ public final class CudaBytePairEncoding implements Encoding, AutoCloseable {
 		}
 	}
 
-	private static void raise(final int status) {
+	private void raise(final int status, final String text) {
 		// the reference's exception types and messages (GptBytePairEncoding.java:54, TokenEncoder.java:67)
 		if ((status & JtkNative.DOC_HAS_SPECIAL) != 0) throw new UnsupportedOperationException("Encoding special tokens is not supported yet.");
-		if ((status & JtkNative.DOC_UNKNOWN_BYTES) != 0) throw new IllegalArgumentException("Unknown token for encoding");
+		if ((status & JtkNative.DOC_UNKNOWN_BYTES) != 0) {
+			// TokenEncoder.java:67 appends the offending part (ImmutableByteArray.toString() = Arrays.toString of ONE byte: every part that is not
+			// a token is a single byte).  The device reports the document, not the part; when only one byte value without a single-byte token
+			// occurs in the text the part is known, otherwise the payload is left out rather than guessed.
+			int only = -1;
+			boolean unique = true;
+			if (text != null)
+				for (final byte b : text.getBytes(StandardCharsets.UTF_8))
+					if (!singleByteTokens[b & 0xFF]) {
+						if (only >= 0 && only != (b & 0xFF)) unique = false;
+						only = b & 0xFF;
+					}
+			throw new IllegalArgumentException(only >= 0 && unique ? "Unknown token for encoding: [" + (byte) only + "]" : "Unknown token for encoding");
+		}
 		// general split patterns only: java.util.regex dies the same way on texts that recurse too deep
 		if ((status & JtkNative.DOC_PATTERN_STACK) != 0) throw new StackOverflowError("split pattern exhausted the device backtracking stack");
 	}
@@ -174,7 +214,7 @@ public final class CudaBytePairEncoding implements Encoding, AutoCloseable {
 	private List<Integer> encodeOne(final String text, final boolean ordinary) {
 		if (text == null) return Collections.emptyList(); // GptBytePairEncoding.java:48-50,72-74
 		final Batch b = encodeBatch(Collections.singletonList(text), ordinary, false);
-		raise(b.docStatus[0]);
+		raise(b.docStatus[0], text);
 		final List<Integer> out = new ArrayList<>(b.ids.length);
 		for (final int id : b.ids) out.add(id);
 		return out;
@@ -194,7 +234,7 @@ public final class CudaBytePairEncoding implements Encoding, AutoCloseable {
 	public List<Integer> encodeWithSpecialTokens(final String text) {
 		if (text == null) return Collections.emptyList();
 		final Batch b = encodeBatch(Collections.singletonList(text), true, false, true);
-		raise(b.docStatus[0]);
+		raise(b.docStatus[0], text);
 		final List<Integer> out = new ArrayList<>(b.ids.length);
 		for (final int id : b.ids) out.add(id);
 		return out;
@@ -227,7 +267,7 @@ public final class CudaBytePairEncoding implements Encoding, AutoCloseable {
 	public int countTokens(final String text) {
 		if (text == null) return 0;
 		final Batch b = encodeBatch(Collections.singletonList(text), false, true);
-		raise(b.docStatus[0]);
+		raise(b.docStatus[0], text);
 		return (int) b.tokenOffsets[1];
 	}
 

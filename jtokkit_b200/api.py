@@ -285,6 +285,7 @@ class Encoding:
         self._name = params.get_name()
         self._special = dict(params.get_special_tokens_encoder())
         keys = [bytes(k) for k in params.get_encoder().keys()]
+        self._single = {k[0] for k in keys if len(k) == 1}
         kb, ko, kv = _flatten(keys, list(params.get_encoder().values()))
         sk = [k.encode("utf-8", "replace") for k in self._special.keys()]
         sb, so, sv = _flatten(sk, list(self._special.values()))
@@ -473,12 +474,18 @@ class Encoding:
                 raise ValueError("Unknown token for decoding: %d" % int(bad[d]))
         return [data[boff[d]:boff[d + 1]] for d in range(nd)]
 
-    @staticmethod
-    def _raise_for_status(status):
+    def _raise_for_status(self, status, text=None):
         if status.size and (status & _capi.DOC_HAS_SPECIAL).any():
             raise NotImplementedError("Encoding special tokens is not supported yet.")  # UnsupportedOperationException
         if status.size and (status & _capi.DOC_UNKNOWN_BYTES).any():
-            raise ValueError("Unknown token for encoding")  # IllegalArgumentException, TokenEncoder.java:67
+            # IllegalArgumentException, TokenEncoder.java:67: "Unknown token for encoding: " + Arrays.toString(part), the part being ONE byte
+            # (every part that is not a token is a single byte).  The device reports the document, not the part: the payload is given
+            # when only one byte value without a single-byte token occurs in the text (then it is that byte), else left out, never guessed.
+            absent = {b for b in _utf8(text)} - getattr(self, "_single", set(range(256))) if text is not None else set()
+            if len(absent) == 1:
+                b = absent.pop()
+                raise ValueError("Unknown token for encoding: [%d]" % (b - 256 if b > 127 else b))
+            raise ValueError("Unknown token for encoding")
         if status.size and (status & _capi.DOC_PATTERN_STACK).any():
             # general split patterns only: java.util.regex would die with StackOverflowError on such a text
             raise RecursionError("split pattern exhausted the device backtracking stack")
@@ -497,7 +504,7 @@ class Encoding:
             return [] if max_tokens is None else EncodingResult([], False)
         if max_tokens is None:
             res = self.encode_batch([text], ordinary=ordinary)
-            self._raise_for_status(res.doc_status)
+            self._raise_for_status(res.doc_status, text)
             return res.tokens(0)
         b = np.frombuffer(_utf8(text), dtype=np.uint8)
         ids, n, trunc, st = C.c_void_p(), C.c_int64(0), C.c_int32(0), C.c_int32(0)
@@ -505,7 +512,7 @@ class Encoding:
         _capi.check(_capi.lib().jtk_encode_max_tokens(self._h, _ptr(b), b.size, int(max_tokens), flags, C.byref(ids), C.byref(n), C.byref(trunc),
                                                       C.byref(st)))
         try:
-            self._raise_for_status(np.array([st.value], dtype=np.int32))
+            self._raise_for_status(np.array([st.value], dtype=np.int32), text)
             toks = np.ctypeslib.as_array(C.cast(ids, C.POINTER(C.c_int32)), shape=(max(n.value, 1),))[:n.value].tolist()
         finally:
             _capi.lib().jtk_free(ids)

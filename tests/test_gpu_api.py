@@ -115,10 +115,15 @@ def test_custom_vocabulary_unknown_bytes_and_duplicates(oracles):
     for text in ["ab", "abab a", "abc", "aab", " a ab", "xy", "xyz", "xyzxy"]:
         assert enc.encode(text) == orc.encode(text), text
     for text in ["abd", "q", "x"]:
-        with pytest.raises(ValueError):
+        with pytest.raises(ValueError) as ei:
             enc.encode(text)
+        # TokenEncoder.java:67: "Unknown token for encoding: " + Arrays.toString(one byte)
+        assert str(ei.value) == "Unknown token for encoding: [%d]" % ord(text[-1])
         with pytest.raises(ValueError):
             orc.encode(text)
+    with pytest.raises(ValueError) as ei:
+        enc.encode("dq")  # two different unknown bytes: the device reports the document, the payload is not guessed
+    assert str(ei.value) == "Unknown token for encoding"
     assert enc.decode([3, 100, 1]) == "ab<s>abc"  # special tokens decode to their string (GptBytePairEncoding.java:307-310)
     with pytest.raises(NotImplementedError):
         enc.encode("a<s>")

@@ -219,8 +219,8 @@ static int init_device(jtk_encoding *e, int device) {
 	T.dec_keys = reinterpret_cast<const uint32_t *>(base + o_deck);
 	T.dec_bytes = base + o_decb;
 	T.dec_off = reinterpret_cast<const uint32_t *>(base + o_deco);
-	T.dec_direct = h.dec_direct.empty() ? nullptr : reinterpret_cast<const uint2 *>(base + o_decd);
-	T.dec_direct_size = (uint32_t) (h.dec_direct.size() / 2);
+	T.dec_direct = h.dec_direct.empty() ? nullptr : reinterpret_cast<const uint4 *>(base + o_decd);
+	T.dec_direct_size = (uint32_t) (h.dec_direct.size() / 4);
 	T.rx_inst = base + o_rxi;
 	T.rx_sets = base + o_rxs;
 	T.rx_ranges = reinterpret_cast<const uint32_t *>(base + o_rxr);
@@ -1587,11 +1587,12 @@ extern "C" int jtk_encode_batch_special(jtk_encoding *e, const uint8_t *utf8, co
 	return JTK_OK;
 }
 
-/* Decode of a device-resident batch: pass 1 (bytes per tile + scan), one synchronisation to learn the byte count, pass 2.
- * d_out == nullptr: size query only (*total_bytes).  Scratch lives in the workspace. */
+/* Decode of a device-resident batch.  d_out == nullptr: size query (count pass + scan, *total_bytes).  Otherwise the single-pass
+ * kernel (ticketed tiles, decoupled look-back) writes the bytes; JTK_E_CAPACITY with *total_bytes set when they do not fit.
+ * Scratch lives in the workspace. */
 static int decode_device_impl(jtk_device_state *ds, jtk_workspace *w, const int32_t *d_ids, int64_t nids, const int64_t *d_tok_off, int64_t ndocs, uint8_t *d_out,
                               int64_t out_capacity, int64_t *d_byte_off, int32_t *d_doc_status, int32_t *d_bad_ids, cudaStream_t st, int64_t *total_bytes,
-                              int64_t *launches, bool counted = false) {
+                              int64_t *launches) {
 	if ((reinterpret_cast<uintptr_t>(d_ids) & 15) != 0) return set_error(JTK_E_ARG, "d_ids must be 16-byte aligned");
 	const int64_t nt = jtk_decode_tiles(nids);
 	if (nt + 1 > w->dec_tiles_cap) {
@@ -1600,13 +1601,13 @@ static int decode_device_impl(jtk_device_state *ds, jtk_workspace *w, const int3
 		w->dec_tile = w->dec_sums = nullptr;
 		w->dec_tiles_cap = 0;
 		const int64_t cap = nt + nt / 4 + 16;
-		CUDA_TRY(cudaMalloc(&w->dec_tile, sizeof(int64_t) * (size_t) cap));
+		CUDA_TRY(cudaMalloc(&w->dec_tile, sizeof(int64_t) * (size_t) (2 * cap))); /* tile states / byte counts, then the tiles' first documents */
 		CUDA_TRY(cudaMalloc(&w->dec_sums, sizeof(int64_t) * (size_t) (jtk_scan_blocks(cap) + 1)));
 		w->dec_tiles_cap = cap;
 	}
 	if (!w->dec_total) {
-		CUDA_TRY(cudaMalloc(&w->dec_total, sizeof(int64_t)));
-		CUDA_TRY(cudaHostAlloc(&w->dec_total_host, sizeof(int64_t), cudaHostAllocDefault));
+		CUDA_TRY(cudaMalloc(&w->dec_total, 4 * sizeof(int64_t))); /* byte count, ticket, overflow flag */
+		CUDA_TRY(cudaHostAlloc(&w->dec_total_host, 4 * sizeof(int64_t), cudaHostAllocDefault));
 	}
 	if (ndocs + 1 > w->dec_docs_cap) {
 		cudaFree(w->dec_badpos);
@@ -1624,23 +1625,35 @@ static int decode_device_impl(jtk_device_state *ds, jtk_workspace *w, const int3
 	a.tok_off = d_tok_off;
 	a.ndocs = ndocs;
 	a.tile_bytes = w->dec_tile;
+	a.ntiles = std::max<int64_t>(nt, 1);
+	a.tile_state = reinterpret_cast<unsigned long long *>(w->dec_tile);
+	a.tile_first_doc = w->dec_tile + w->dec_tiles_cap;
+	a.total_out = reinterpret_cast<long long *>(w->dec_total);
+	a.ticket = reinterpret_cast<unsigned int *>(w->dec_total + 1);
+	a.overflow = reinterpret_cast<unsigned int *>(w->dec_total + 2);
+	a.out_capacity = out_capacity;
 	a.bad_pos = w->dec_badpos;
 	a.out = d_out;
 	a.byte_off = d_byte_off;
 	a.doc_status = d_doc_status;
 	a.bad_ids = d_bad_ids;
-	if (!counted) { /* (counted: pass 1 of the same batch has just run on this workspace: the size query of the host-buffer path) */
-		CUDA_TRY(cudaMemsetAsync(w->dec_badpos, 0xFF, sizeof(unsigned long long) * (size_t) (ndocs + 1), st));
+	CUDA_TRY(cudaMemsetAsync(w->dec_badpos, 0xFF, sizeof(unsigned long long) * (size_t) (ndocs + 1), st));
+	if (!d_out) {
 		CUDA_TRY(jtk_launch_decode_count(a, w->dec_sums, w->dec_total, st));
 		CUDA_TRY(cudaMemcpyAsync(w->dec_total_host, w->dec_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
 		CUDA_TRY(cudaStreamSynchronize(st));
 		*launches = (nt > 0 ? 1 : 0) + 3;
+		*total_bytes = *w->dec_total_host;
+		return JTK_OK;
 	}
-	*total_bytes = *w->dec_total_host;
-	if (!d_out) return JTK_OK;
-	if (*total_bytes > out_capacity) return set_error(JTK_E_CAPACITY, "output buffer too small for the decoded bytes");
-	CUDA_TRY(jtk_launch_decode_write(a, st));
-	*launches += 1;
+	CUDA_TRY(cudaMemsetAsync(w->dec_tile, 0, sizeof(int64_t) * (size_t) a.ntiles, st));
+	CUDA_TRY(cudaMemsetAsync(w->dec_total, 0, 4 * sizeof(int64_t), st));
+	CUDA_TRY(jtk_launch_decode_fused(a, st));
+	CUDA_TRY(cudaMemcpyAsync(w->dec_total_host, w->dec_total, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	*launches = 2 + (ndocs > 0 ? 1 : 0);
+	*total_bytes = w->dec_total_host[0];
+	if (w->dec_total_host[2] != 0) return set_error(JTK_E_CAPACITY, "output buffer too small for the decoded bytes");
 	return JTK_OK;
 }
 
@@ -1657,7 +1670,6 @@ extern "C" int jtk_decode_batch_device(jtk_encoding *e, int device, const int32_
 	int64_t launches = 0;
 	int rc = decode_device_impl(ds, w, d_ids, nids, d_tok_off, ndocs, d_out, out_capacity, d_byte_off, d_doc_status, d_bad_ids,
 	                            reinterpret_cast<cudaStream_t>(cuda_stream), total_bytes, &launches);
-	if (rc == JTK_OK && d_out) CUDA_TRY(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(cuda_stream)));
 	if (gpu_launches) *gpu_launches = launches;
 	release_ws(ds, w);
 	return rc;
@@ -1697,9 +1709,10 @@ static int decode_impl(jtk_encoding *e, const int32_t *ids, const int64_t *tok_o
 		int64_t total = 0, launches = 0;
 		if ((rc = decode_device_impl(ds, w, d_ids, nids, d_tok_off, ndocs, nullptr, 0, nullptr, nullptr, nullptr, st, &total, &launches)) != JTK_OK) break;
 		DTRY(cudaMalloc(&d_out, (size_t) std::max<int64_t>(total, 1) + 16));
-		if ((rc = decode_device_impl(ds, w, d_ids, nids, d_tok_off, ndocs, d_out, total, d_byte_off, d_status, d_bad, st, &total, &launches, true)) != JTK_OK) break;
+		int64_t launches2 = 0;
+		if ((rc = decode_device_impl(ds, w, d_ids, nids, d_tok_off, ndocs, d_out, total, d_byte_off, d_status, d_bad, st, &total, &launches2)) != JTK_OK) break;
 		r->nbytes = total;
-		r->launches = launches;
+		r->launches = launches + launches2;
 		if ((rc = pinned_get(e, total, &r->bytes)) != JTK_OK) break;
 		if ((rc = pinned_get(e, sizeof(int64_t) * (ndocs + 1), &r->byte_off)) != JTK_OK) break;
 		if ((rc = pinned_get(e, sizeof(int32_t) * (ndocs + 1), &r->status)) != JTK_OK) break;

@@ -14,8 +14,8 @@
 #define JTK_HD __host__ __device__ __forceinline__
 #else
 #define JTK_HD inline
-struct uint2 { /* host builds without the CUDA headers (tests/emu) */
-	unsigned int x, y;
+struct uint4 { /* host builds without the CUDA headers (tests/emu) */
+	unsigned int x, y, z, w;
 };
 #endif
 
@@ -150,7 +150,7 @@ struct jtk_tables {
 	uint32_t mask_d;
 	const uint8_t *dec_bytes;    /* ordinary tokens followed by special-token strings */
 	const uint32_t *dec_off;
-	const uint2 *dec_direct;     /* id -> {offset into dec_bytes, length (0xFFFFFFFF = unknown id)} when all ids are small and non-negative, else null */
+	const uint4 *dec_direct;     /* id -> {offset into dec_bytes << 8 | length (0xFFFFFFFF = unknown id), first twelve bytes} when all ids are small and non-negative, else null */
 	uint32_t dec_direct_size;
 	/* JTK_PAT_GENERAL only: the compiled split program (jtk_regex.h: jtk_rx_inst / jtk_rx_set / code point ranges) */
 	const void *rx_inst;

@@ -1787,14 +1787,15 @@ namespace {
 constexpr int SCAN_NT = 256;
 constexpr int SCAN_ITEMS = 16;
 
-/* token id -> (offset into dec_bytes, length); false for an id that neither map knows (GptBytePairEncoding.java:302-314) */
-__device__ __forceinline__ bool decode_entry(const jtk_tables &T, int32_t id, uint32_t *off, uint32_t *len) {
-	if (T.dec_direct) { /* ids are small non-negative numbers (all predefined encodings): one 8-byte read */
+/* token id -> (offset into dec_bytes, length, first twelve bytes); false for an id that neither map knows (GptBytePairEncoding.java:302-314) */
+__device__ __forceinline__ bool decode_entry(const jtk_tables &T, int32_t id, uint32_t *off, uint32_t *len, uint32_t *b0, uint32_t *b1, uint32_t *b2) {
+	if (T.dec_direct) { /* ids are small non-negative numbers (all predefined encodings): one 16-byte read answers tokens of up to twelve bytes */
 		if ((uint32_t) id >= T.dec_direct_size) return false;
-		const uint2 e = __ldg(T.dec_direct + id);
-		*off = e.x;
-		*len = e.y;
-		return e.y != 0xFFFFFFFFu;
+		const uint4 e = __ldg(T.dec_direct + id);
+		*off = e.x >> 8;
+		*len = e.x & 0xFFu;
+		*b0 = e.y, *b1 = e.z, *b2 = e.w;
+		return e.x != 0xFFFFFFFFu;
 	}
 	uint32_t s = jtk_hash_pair(id, 0) & T.mask_d;
 	for (;;) {
@@ -1803,16 +1804,35 @@ __device__ __forceinline__ bool decode_entry(const jtk_tables &T, int32_t id, ui
 		if (T.dec_keys[2 * s] == (uint32_t) id) {
 			*off = T.dec_off[v - 1];
 			*len = T.dec_off[v] - *off;
+			uint32_t f[3] = {0, 0, 0};
+			for (uint32_t k = 0; k < 12 && k < *len; k++) f[k >> 2] |= (uint32_t) T.dec_bytes[*off + k] << (8 * (k & 3));
+			*b0 = f[0], *b1 = f[1], *b2 = f[2];
 			return true;
 		}
 		s = (s + 1) & T.mask_d;
 	}
 }
+__device__ __forceinline__ bool decode_len(const jtk_tables &T, int32_t id, uint32_t *len) {
+	if (T.dec_direct) {
+		if ((uint32_t) id >= T.dec_direct_size) return false;
+		const uint32_t x = __ldg(reinterpret_cast<const uint32_t *>(T.dec_direct + id));
+		*len = x & 0xFFu;
+		return x != 0xFFFFFFFFu;
+	}
+	uint32_t off, b0, b1, b2;
+	return decode_entry(T, id, &off, len, &b0, &b1, &b2);
+}
 
+#ifndef JTK_DECODE_CTAS
+#define JTK_DECODE_CTAS 4 /* resident CTAs per SM the single-pass decode kernel is compiled for (register budget) */
+#endif
 constexpr int DNT = 256;           /* threads per CTA of the decode kernels */
-constexpr int DPT = 16;            /* consecutive tokens per thread */
+#ifndef JTK_DECODE_DPT
+#define JTK_DECODE_DPT 8
+#endif
+constexpr int DPT = JTK_DECODE_DPT; /* consecutive tokens per thread */
 constexpr int DTILE = DNT * DPT;   /* tokens per tile */
-constexpr int DWIN = 24 * 1024;    /* bytes of a tile staged in shared memory at a time (a tile of typical text is ~11 KB) */
+constexpr int DWIN = 12 * 1024;    /* bytes of a tile staged in shared memory at a time (a tile of typical text is ~5.5 KB) */
 
 /* pass 1: bytes per tile of DTILE tokens; unknown ids are reported per document (the smallest position) */
 __global__ void __launch_bounds__(DNT) jtk_decode_count_kernel(const __grid_constant__ jtk_decode_args a) {
@@ -1834,8 +1854,8 @@ __global__ void __launch_bounds__(DNT) jtk_decode_count_kernel(const __grid_cons
 #pragma unroll
 	for (int i = 0; i < DPT; i++) {
 		if (t0 + i >= a.nids) break;
-		uint32_t off, len;
-		if (decode_entry(a.T, ids[i], &off, &len)) {
+		uint32_t len;
+		if (decode_len(a.T, ids[i], &len)) {
 			sum += (int) len;
 		} else {
 			/* document of token j: the last d with tok_off[d] <= j */
@@ -1936,23 +1956,56 @@ __global__ void jtk_scan_add_kernel(int64_t *data, int64_t n, const int64_t *blo
 		if (base + i < n) data[base + i] += add;
 }
 
-/* pass 2: one CTA per tile: per-token byte offsets by a block scan, token bytes copied into a shared-memory window that has the
- * same 16-byte misalignment as its place in the output, then flushed with 16-byte stores; document byte offsets, statuses */
-__global__ void __launch_bounds__(DNT) jtk_decode_write_kernel(const __grid_constant__ jtk_decode_args a) {
+/* Single pass: tiles of DTILE tokens are taken by ticket (so every predecessor of a tile has started), the tile's byte count is
+ * published, the exclusive prefix over all earlier tiles comes from a decoupled look-back over the published words (a warp
+ * inspects 32 predecessors at a time), then the token bytes are copied into a shared-memory window that has the same 16-byte
+ * misalignment as its place in the output and flushed with 16-byte stores.  Algorithmic bytes: 4 per token read, the bytes written.
+ * status word of a tile: bits 62..63 = 1 aggregate (bytes of the tile) / 2 inclusive prefix, bits 0..61 the value. */
+constexpr unsigned long long DST_AGG = 1ull << 62, DST_PREFIX = 2ull << 62, DST_MASK = (1ull << 62) - 1;
+
+__global__ void __launch_bounds__(DNT, JTK_DECODE_CTAS) jtk_decode_fused_kernel(const __grid_constant__ jtk_decode_args a) {
 	__shared__ __align__(16) uint8_t s_out[DWIN + 32];
 	__shared__ int s_pref[DNT + 1];
 	__shared__ int s_w[DNT / 32];
+	__shared__ long long s_base;
+	__shared__ unsigned s_tile;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int64_t tile0 = (int64_t) blockIdx.x * DTILE;
+	if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
+	__syncthreads();
+	const int64_t tile = s_tile;
+	const int64_t tile0 = tile * DTILE;
 	const int64_t t0 = tile0 + (int64_t) tid * DPT;
-	const int64_t base = a.tile_bytes[blockIdx.x]; /* exclusive scan of pass 1 */
-	uint32_t off[DPT], len[DPT];
+	int32_t ids[DPT];
+	if (t0 + DPT <= a.nids) {
+#pragma unroll
+		for (int i = 0; i < DPT / 4; i++) {
+			const int4 v = __ldg(reinterpret_cast<const int4 *>(a.ids + t0) + i);
+			ids[4 * i] = v.x, ids[4 * i + 1] = v.y, ids[4 * i + 2] = v.z, ids[4 * i + 3] = v.w;
+		}
+	} else {
+#pragma unroll
+		for (int i = 0; i < DPT; i++) ids[i] = t0 + i < a.nids ? a.ids[t0 + i] : 0;
+	}
+	uint8_t len[DPT]; /* (the bytes themselves are fetched when they are copied: the same table entries again, L1 hits) */
 	int sum = 0;
 #pragma unroll
 	for (int i = 0; i < DPT; i++) {
-		off[i] = 0, len[i] = 0;
-		if (t0 + i < a.nids && !decode_entry(a.T, __ldg(a.ids + t0 + i), &off[i], &len[i])) len[i] = 0;
-		sum += (int) len[i];
+		uint32_t l = 0;
+		if (t0 + i < a.nids && !decode_len(a.T, ids[i], &l)) {
+			l = 0;
+			/* unknown id: flag its document (the last d with tok_off[d] <= j) and remember the first one */
+			const int64_t j = t0 + i;
+			int64_t lo = 0, hi = a.ndocs - 1;
+			while (lo < hi) {
+				const int64_t mid = (lo + hi + 1) >> 1;
+				if (a.tok_off[mid] <= j) lo = mid;
+				else hi = mid - 1;
+			}
+			atomicMin(a.bad_pos + lo, (unsigned long long) j);
+			atomicOr(a.doc_status + lo, JTK_DOC_UNKNOWN_ID);
+		}
+		len[i] = (uint8_t) l;
+		sum += (int) l;
 	}
 	int x = sum;
 #pragma unroll
@@ -1963,6 +2016,7 @@ __global__ void __launch_bounds__(DNT) jtk_decode_write_kernel(const __grid_cons
 	if (lane == 31) s_w[warp] = x;
 	__syncthreads();
 	int wpre = 0, total = 0;
+#pragma unroll
 	for (int w = 0; w < DNT / 32; w++) {
 		if (w < warp) wpre += s_w[w];
 		total += s_w[w];
@@ -1970,18 +2024,80 @@ __global__ void __launch_bounds__(DNT) jtk_decode_write_kernel(const __grid_cons
 	const int mine = wpre + x - sum; /* tile-relative byte offset of this thread's first token */
 	s_pref[tid] = mine;
 	if (tid == DNT - 1) s_pref[DNT] = total;
-	for (int w0 = 0; w0 < total; w0 += DWIN) {
+	/* ---- publish the aggregate, look back for the exclusive prefix (warp 0) ---- */
+	if (warp == 0) {
+		volatile unsigned long long *st = a.tile_state;
+		if (lane == 0) {
+			st[tile] = (tile == 0 ? DST_PREFIX : DST_AGG) | (unsigned long long) total;
+			__threadfence();
+		}
+		long long excl = 0;
+		int64_t p = tile - 1; /* predecessor inspected by lane 0 of this round */
+		while (p >= 0) {
+			const int64_t mine_p = p - lane;
+			unsigned long long w = DST_PREFIX; /* lanes before the first tile contribute nothing */
+			if (mine_p >= 0) {
+				do {
+					w = st[mine_p];
+				} while ((w >> 62) == 0);
+			}
+			const unsigned pm = __ballot_sync(0xFFFFFFFFu, (w >> 62) == 2);
+			/* everything up to and including the nearest inclusive prefix counts */
+			const int stop = pm ? __ffs((int) pm) - 1 : 31;
+			long long v = lane <= stop && mine_p >= 0 ? (long long) (w & DST_MASK) : 0;
+#pragma unroll
+			for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+			excl += v;
+			if (pm) break;
+			p -= 32;
+		}
+		if (lane == 0) {
+			if (tile > 0) {
+				st[tile] = DST_PREFIX | (unsigned long long) (excl + total);
+				__threadfence();
+			}
+			s_base = excl;
+			if (tile == a.ntiles - 1) *a.total_out = excl + total;
+		}
+	}
+	__syncthreads();
+	const int64_t base = s_base;
+	const bool fits = base + total <= a.out_capacity;
+	if (!fits && tid == 0) *a.overflow = 1;
+	for (int w0 = 0; fits && w0 < total; w0 += DWIN) {
 		const int mis = (int) ((base + w0) & 15);
 		const int wn = min(DWIN, total - w0); /* bytes of this window */
-		__syncthreads();
+		if (w0) __syncthreads();
 		int pos = mine - w0;
 #pragma unroll
 		for (int i = 0; i < DPT; i++) {
 			const int l = (int) len[i];
 			if (l && pos + l > 0 && pos < wn) {
-				const uint8_t *src = a.T.dec_bytes + off[i];
-				const int k0 = pos < 0 ? -pos : 0, k1 = min(l, wn - pos);
-				for (int k = k0; k < k1; k++) s_out[mis + pos + k] = src[k];
+				uint32_t o2, l2, f0, f1, f2;
+				decode_entry(a.T, ids[i], &o2, &l2, &f0, &f1, &f2);
+				if (l <= 12 && pos >= 0 && pos + l <= wn) { /* the table entry holds the bytes: straight-line predicated byte stores */
+					uint8_t *d = s_out + mis + pos;
+					d[0] = (uint8_t) f0;
+					if (l > 1) d[1] = (uint8_t) (f0 >> 8);
+					if (l > 2) d[2] = (uint8_t) (f0 >> 16);
+					if (l > 3) d[3] = (uint8_t) (f0 >> 24);
+					if (l > 4) {
+						d[4] = (uint8_t) f1;
+						if (l > 5) d[5] = (uint8_t) (f1 >> 8);
+						if (l > 6) d[6] = (uint8_t) (f1 >> 16);
+						if (l > 7) d[7] = (uint8_t) (f1 >> 24);
+						if (l > 8) {
+							d[8] = (uint8_t) f2;
+							if (l > 9) d[9] = (uint8_t) (f2 >> 8);
+							if (l > 10) d[10] = (uint8_t) (f2 >> 16);
+							if (l > 11) d[11] = (uint8_t) (f2 >> 24);
+						}
+					}
+				} else {
+					const uint8_t *src = a.T.dec_bytes + o2;
+					const int k0 = pos < 0 ? -pos : 0, k1 = min(l, wn - pos);
+					for (int k = k0; k < k1; k++) s_out[mis + pos + k] = src[k];
+				}
 			}
 			pos += l;
 		}
@@ -1998,16 +2114,10 @@ __global__ void __launch_bounds__(DNT) jtk_decode_write_kernel(const __grid_cons
 			}
 		}
 	}
-	__syncthreads();
 	/* documents whose first token lies in this tile (the last tile also takes the documents that start at the very end) */
-	const bool last = blockIdx.x == gridDim.x - 1;
+	const bool last = tile == a.ntiles - 1;
 	const int64_t tile_end = last ? a.nids + 1 : tile0 + DTILE;
-	int64_t lo = 0, hi = a.ndocs + 1; /* first d in [0, ndocs] with tok_off[d] >= tile0 */
-	while (lo < hi) {
-		const int64_t mid = (lo + hi) >> 1;
-		if (a.tok_off[mid] >= tile0) hi = mid;
-		else lo = mid + 1;
-	}
+	const int64_t lo = a.tile_first_doc[tile]; /* first d in [0, ndocs] with tok_off[d] >= tile0 (jtk_decode_first_doc_kernel) */
 	for (int64_t d = lo + tid; d <= a.ndocs; d += DNT) {
 		const int64_t j = a.tok_off[d];
 		if (j >= tile_end) break;
@@ -2015,21 +2125,34 @@ __global__ void __launch_bounds__(DNT) jtk_decode_write_kernel(const __grid_cons
 		int before = jl >= DTILE ? total : s_pref[jl / DPT];
 		if (jl < DTILE)
 			for (int i = 0; i < jl % DPT; i++) {
-				uint32_t o2, l2;
+				uint32_t l2;
 				const int64_t jj = tile0 + jl - jl % DPT + i;
-				if (jj < a.nids && decode_entry(a.T, a.ids[jj], &o2, &l2)) before += (int) l2;
+				if (jj < a.nids && decode_len(a.T, a.ids[jj], &l2)) before += (int) l2;
 			}
 		a.byte_off[d] = base + before;
-		if (d < a.ndocs) {
-			const unsigned long long bp = a.bad_pos[d];
-			if (bp != ~0ull) {
-				a.doc_status[d] |= JTK_DOC_UNKNOWN_ID;
-				a.bad_ids[d] = a.ids[bp];
-			} else {
-				a.bad_ids[d] = 0;
-			}
-		}
 	}
+}
+
+/* first document whose first token is not before the tile (one thread per tile, before the main pass) */
+__global__ void jtk_decode_first_doc_kernel(const jtk_decode_args a) {
+	const int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+	if (t >= a.ntiles) return;
+	const int64_t tile0 = t * DTILE;
+	int64_t lo = 0, hi = a.ndocs + 1;
+	while (lo < hi) {
+		const int64_t mid = (lo + hi) >> 1;
+		if (a.tok_off[mid] >= tile0) hi = mid;
+		else lo = mid + 1;
+	}
+	a.tile_first_doc[t] = lo;
+}
+
+/* the first unknown id of every document (positions collected by the pass above) */
+__global__ void jtk_decode_bad_ids_kernel(const jtk_decode_args a) {
+	const int64_t d = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+	if (d >= a.ndocs) return;
+	const unsigned long long bp = a.bad_pos[d];
+	a.bad_ids[d] = bp != ~0ull ? a.ids[bp] : 0;
 }
 
 } /* namespace */
@@ -2163,9 +2286,10 @@ cudaError_t jtk_launch_exclusive_scan(int64_t *data, int64_t n, int64_t *block_s
 	return cudaGetLastError();
 }
 
-/* pass 2; with no tokens at all one CTA still writes the document byte offsets */
-cudaError_t jtk_launch_decode_write(const jtk_decode_args &a, cudaStream_t st) {
-	const int64_t nt = jtk_decode_tiles(a.nids);
-	jtk_decode_write_kernel<<<(unsigned) (nt > 0 ? nt : 1), DNT, 0, st>>>(a);
+/* the single-pass decode; a.ticket / a.tile_state (ntiles words) / a.overflow must be zero, a.bad_pos preset to ~0 */
+cudaError_t jtk_launch_decode_fused(const jtk_decode_args &a, cudaStream_t st) {
+	jtk_decode_first_doc_kernel<<<(unsigned) ((a.ntiles + 255) / 256), 256, 0, st>>>(a);
+	jtk_decode_fused_kernel<<<(unsigned) a.ntiles, DNT, 0, st>>>(a);
+	if (a.ndocs > 0) jtk_decode_bad_ids_kernel<<<(unsigned) ((a.ndocs + 255) / 256), 256, 0, st>>>(a);
 	return cudaGetLastError();
 }

@@ -168,7 +168,14 @@ struct jtk_decode_args {
 	int64_t nids;
 	const int64_t *tok_off;
 	int64_t ndocs;
-	int64_t *tile_bytes;          /* jtk_decode_tiles(nids) + 1: bytes per tile, then their exclusive scan */
+	int64_t *tile_bytes;          /* size query only: jtk_decode_tiles(nids) + 1: bytes per tile, then their exclusive scan */
+	int64_t ntiles;               /* max(jtk_decode_tiles(nids), 1) */
+	unsigned long long *tile_state; /* ntiles words, zeroed: published byte counts / prefixes of the single-pass kernel */
+	int64_t *tile_first_doc;      /* ntiles: scratch */
+	unsigned int *ticket;         /* zeroed */
+	unsigned int *overflow;       /* zeroed; set when the bytes do not fit out_capacity */
+	long long *total_out;         /* device: receives the byte count */
+	int64_t out_capacity;
 	unsigned long long *bad_pos;  /* ndocs, preset to ~0: position of the first unknown id of a document */
 	uint8_t *out;
 	int64_t *byte_off; /* ndocs + 1 */
@@ -178,6 +185,6 @@ struct jtk_decode_args {
 int64_t jtk_scan_blocks(int64_t n);
 int64_t jtk_decode_tiles(int64_t nids);
 cudaError_t jtk_launch_decode_count(const jtk_decode_args &a, int64_t *block_sums, int64_t *total, cudaStream_t st);
-cudaError_t jtk_launch_decode_write(const jtk_decode_args &a, cudaStream_t st);
+cudaError_t jtk_launch_decode_fused(const jtk_decode_args &a, cudaStream_t st);
 
 #endif

@@ -461,11 +461,16 @@ int jtk_build_host_tables(const jtk_params *p, jtk_host_tables *t, std::string *
 			neg |= t->special_ids[(size_t) i] < 0;
 		}
 		t->dec_direct.clear();
-		if (!neg && max_id >= 0 && max_id < (4 << 20)) {
-			t->dec_direct.assign(2 * (size_t) (max_id + 1), 0xFFFFFFFFu);
-			auto put = [&](int32_t id, int64_t index) {
-				t->dec_direct[2 * (size_t) id] = t->dec_off[(size_t) index];
-				t->dec_direct[2 * (size_t) id + 1] = t->dec_off[(size_t) index + 1] - t->dec_off[(size_t) index];
+		if (!neg && max_id >= 0 && max_id < (2 << 20) && t->dec_bytes.size() < (1u << 24) && t->max_token_len < 255) {
+			t->dec_direct.assign(4 * (size_t) (max_id + 1), 0xFFFFFFFFu);
+			auto put = [&](int32_t id, int64_t index) { /* {offset << 8 | length, first twelve bytes} */
+				const uint32_t o = t->dec_off[(size_t) index], l = t->dec_off[(size_t) index + 1] - o;
+				uint32_t f[3] = {0, 0, 0};
+				for (uint32_t k = 0; k < 12 && k < l; k++) f[k >> 2] |= (uint32_t) t->dec_bytes[o + k] << (8 * (k & 3));
+				t->dec_direct[4 * (size_t) id] = (o << 8) | l;
+				t->dec_direct[4 * (size_t) id + 1] = f[0];
+				t->dec_direct[4 * (size_t) id + 2] = f[1];
+				t->dec_direct[4 * (size_t) id + 3] = f[2];
 			};
 			/* the same precedence as the hash form: among ordinary tokens the last key put for an id wins, special tokens only where no ordinary token has the id */
 			for (int64_t i = 0; i < p->special_size; i++) put(t->special_ids[(size_t) i], ndec_ord + i);
@@ -508,8 +513,8 @@ jtk_tables jtk_host_view(const jtk_host_tables &h) {
 	v.mask_d = h.mask_d;
 	v.dec_bytes = h.dec_bytes.data();
 	v.dec_off = h.dec_off.data();
-	v.dec_direct = h.dec_direct.empty() ? nullptr : reinterpret_cast<const uint2 *>(h.dec_direct.data());
-	v.dec_direct_size = (uint32_t) (h.dec_direct.size() / 2);
+	v.dec_direct = h.dec_direct.empty() ? nullptr : reinterpret_cast<const uint4 *>(h.dec_direct.data());
+	v.dec_direct_size = (uint32_t) (h.dec_direct.size() / 4);
 	v.rx_inst = h.rx_inst.data();
 	v.rx_sets = h.rx_sets.data();
 	v.rx_ranges = h.rx_ranges.data();

@@ -47,7 +47,7 @@ struct jtk_host_tables {
 	uint32_t mask_d = 0;
 	std::vector<uint8_t> dec_bytes;
 	std::vector<uint32_t> dec_off;
-	std::vector<uint32_t> dec_direct; /* pairs (offset, length) by id, empty when the ids are not small non-negative numbers */
+	std::vector<uint32_t> dec_direct; /* quadruples (offset << 8 | length, first twelve bytes) by id, empty when the ids are not small non-negative numbers */
 	/* JTK_PAT_GENERAL: the compiled split program (raw jtk_rx_inst / jtk_rx_set arrays, 16-byte aligned by the vector) */
 	std::vector<uint8_t> rx_inst, rx_sets;
 	std::vector<uint32_t> rx_ranges;

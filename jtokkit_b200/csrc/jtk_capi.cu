@@ -37,6 +37,14 @@ extern "C" const char *jtk_version(void) {
 }
 
 /* ------------------------------------------------------------------ per-device state */
+struct jtk_pinned_buf {
+	void *p = nullptr;
+	int64_t cap = 0;
+};
+/* grow-only pinned staging buffer owned by a workspace / input buffer (never returned to the shared pool: a batch over eight devices
+ * uses ~90 of them per call, the pool keeps twelve) */
+static int pinned_grow(jtk_pinned_buf *b, int64_t bytes);
+
 struct jtk_workspace {
 	/* sized for ntiles_cap tiles / long_cap long pieces */
 	int64_t ntiles_cap = 0, long_cap = 0;
@@ -81,6 +89,7 @@ struct jtk_workspace {
 	unsigned long long *dec_badpos = nullptr;
 	int64_t dec_tiles_cap = 0, dec_docs_cap = 0;
 	int64_t *dec_total_host = nullptr; /* pinned */
+	jtk_pinned_buf h_stage; /* host-buffer path: the chunk's token offsets and statuses on their way to the result arrays */
 };
 
 /* per-call piece memo buffer (see jtk_memo_entry); pooled per device, an epoch per buffer makes old entries invisible */
@@ -120,11 +129,7 @@ struct jtk_in_buf {
 	int64_t cap = 0;
 	int64_t *d_doc = nullptr;
 	int64_t doc_cap = 0;
-};
-
-struct jtk_pinned_buf {
-	void *p = nullptr;
-	int64_t cap = 0;
+	jtk_pinned_buf h_doc; /* chunk-relative document offsets staged for the copy-in */
 };
 
 struct jtk_encoding {
@@ -371,6 +376,7 @@ static void free_workspace(jtk_workspace *w) {
 	cudaFree(w->dec_total);
 	cudaFree(w->dec_badpos);
 	cudaFreeHost(w->dec_total_host);
+	cudaFreeHost(w->h_stage.p);
 	if (w->side_ok) {
 		for (int i = 0; i < 3; i++) {
 			cudaStreamDestroy(w->side.s[i]);
@@ -389,6 +395,7 @@ extern "C" void jtk_encoding_destroy(jtk_encoding *e) {
 		for (jtk_in_buf *b : ds->free_in) {
 			cudaFree(b->d_in);
 			cudaFree(b->d_doc);
+			cudaFreeHost(b->h_doc.p);
 			delete b;
 		}
 		for (jtk_workspace *w : ds->free_ws) free_workspace(w);
@@ -881,6 +888,17 @@ static void pinned_put(jtk_encoding *e, jtk_pinned_buf &b) {
 	}
 }
 
+static int pinned_grow(jtk_pinned_buf *b, int64_t bytes) {
+	if (b->cap >= bytes) return JTK_OK;
+	if (b->p) cudaFreeHost(b->p);
+	b->p = nullptr;
+	b->cap = 0;
+	const int64_t cap = bytes + bytes / 4 + 4096;
+	CUDA_TRY(cudaHostAlloc(&b->p, (size_t) cap, cudaHostAllocPortable));
+	b->cap = cap;
+	return JTK_OK;
+}
+
 extern "C" void *jtk_host_alloc(int64_t nbytes) {
 	void *p = nullptr;
 	if (cudaHostAlloc(&p, (size_t) std::max<int64_t>(nbytes, 64), cudaHostAllocPortable) != cudaSuccess) {
@@ -1079,7 +1097,6 @@ static void run_device(device_job *job) {
 	jtk_in_buf *ring[NR];
 	cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr, s_meta = nullptr;
 	cudaEvent_t ev_in[NR], ev_free[NR], ev_k0[NS], ev_k1[NS], ev_out[NS], ev_meta[NS];
-	jtk_pinned_buf stage_off[NS], stage_doc[NR];
 	jtk_device_info infos[NS];
 	int64_t out_chunk[NS]; /* local chunk whose copy-out is in flight on the slot, -1 = none */
 	int64_t out_base[NS];
@@ -1119,7 +1136,7 @@ static void run_device(device_job *job) {
 		CUDA_TRY(cudaEventSynchronize(ev_out[slot]));
 		const size_t c = gc((size_t) out_chunk[slot]);
 		const int64_t d0 = cb[c], nd = cb[c + 1] - d0;
-		const int64_t *h_tok = static_cast<const int64_t *>(stage_off[slot].p);
+		const int64_t *h_tok = static_cast<const int64_t *>(ws[slot]->h_stage.p);
 		const int32_t *h_st = reinterpret_cast<const int32_t *>(h_tok + nd + 1);
 		const int64_t base = out_base[slot];
 		for (int64_t i = 0; i < nd; i++) {
@@ -1207,11 +1224,9 @@ static void run_device(device_job *job) {
 			int r2 = retire(slot); /* the slot's previous copy-out must have been consumed before its staging buffer is reused */
 			if (r2 != JTK_OK) return r2;
 		}
-		jtk_pinned_buf &so = stage_off[slot];
-		const int64_t need = (int64_t) sizeof(int64_t) * (nd + 1) + (int64_t) sizeof(int32_t) * (nd + 1);
-		if (so.cap < need) {
-			pinned_put(e, so);
-			int r2 = pinned_get(e, need + need / 4, &so);
+		jtk_pinned_buf &so = w->h_stage;
+		{
+			int r2 = pinned_grow(&so, (int64_t) sizeof(int64_t) * (nd + 1) + (int64_t) sizeof(int32_t) * (nd + 1));
 			if (r2 != JTK_OK) return r2;
 		}
 		int64_t *h_tok = static_cast<int64_t *>(so.p);
@@ -1244,12 +1259,10 @@ static void run_device(device_job *job) {
 		int r2 = ensure_in_buf(in, cbytes, nd);
 		if (r2 != JTK_OK) return r2;
 		/* chunk-relative document offsets (the kernels require doc_off[0] == 0), staged in pinned memory */
-		jtk_pinned_buf &sd = stage_doc[j % NR];
-		if (sd.cap < (int64_t) sizeof(int64_t) * (nd + 1)) {
-			pinned_put(e, sd);
-			r2 = pinned_get(e, (int64_t) sizeof(int64_t) * (nd + 1) * 5 / 4, &sd);
-			if (r2 != JTK_OK) return r2;
-		}
+		jtk_pinned_buf &sd = in->h_doc;
+		if (j >= (size_t) NR) CUDA_TRY(cudaEventSynchronize(ev_in[j % NR])); /* the copy-in of chunk j - NR has read the staging buffer (long ago) */
+		r2 = pinned_grow(&sd, (int64_t) sizeof(int64_t) * (nd + 1));
+		if (r2 != JTK_OK) return r2;
 		int64_t *rebase = static_cast<int64_t *>(sd.p);
 		for (int64_t i = 0; i <= nd; i++) rebase[i] = off[d0 + i] - b0;
 		if (trace && !tr0) {
@@ -1326,12 +1339,10 @@ static void run_device(device_job *job) {
 		if (ev_out[i]) cudaEventDestroy(ev_out[i]);
 		if (ev_meta[i]) cudaEventDestroy(ev_meta[i]);
 		release_ws(ds, ws[i]);
-		pinned_put(e, stage_off[i]);
 	}
 	for (int i = 0; i < NR; i++) {
 		if (ev_in[i]) cudaEventDestroy(ev_in[i]);
 		if (ev_free[i]) cudaEventDestroy(ev_free[i]);
-		pinned_put(e, stage_doc[i]);
 		std::lock_guard<std::mutex> lk(ds->mu);
 		ds->free_in.push_back(ring[i]);
 	}

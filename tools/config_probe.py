@@ -42,7 +42,7 @@ for _ in range(4):
     res.close()
 dt = min(times[1:])
 t0 = time.perf_counter()
-_, _, exp = orc.encode_batch(hn, on, threads, check_special=True)
+_, exp, _ = orc.encode_batch(hn, on, threads, check_special=True)
 t_or = time.perf_counter() - t0
 ok = bool(np.array_equal(counts, exp))
 print("  host to host %.1f ms = %.1f GB/s input, %.2f G tokens/s (kernel time max over devices %.1f ms); oracle port on %d cores %.1f s; every count identical: %s"

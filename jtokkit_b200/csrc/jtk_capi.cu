@@ -764,6 +764,15 @@ static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspa
 	 * the other lane of buffers; the split of sub-batch i + 2 waits for the lane to be free again. */
 	const bool piped = w->nlanes > 1 && nsub > 1;
 	const jtk_side_streams *side = w->side_ok ? &w->side : nullptr;
+	/* JTK_PHASE_TRACE=1 (development aid, device-resident call only): per sub-batch the time of split / scatter / merges / scan / gather on stderr */
+	static const bool phase_trace = getenv("JTK_PHASE_TRACE") != nullptr;
+	std::vector<cudaEvent_t> pm;
+	if (phase_trace && sync_and_long && !piped)
+		for (int64_t i = 0; i < 6 * nsub; i++) {
+			cudaEvent_t ev;
+			cudaEventCreate(&ev);
+			pm.push_back(ev);
+		}
 	if (piped) {
 		CUDA_TRY(cudaEventRecord(w->ev_begin, st));
 		CUDA_TRY(cudaStreamWaitEvent(w->post_stream, w->ev_begin, 0));
@@ -774,12 +783,16 @@ static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspa
 		a.tile_begin = cuts[(size_t) i];
 		a.tile_end = cuts[(size_t) i + 1];
 		if (piped && i >= 2) CUDA_TRY(cudaStreamWaitEvent(st, w->lane[l].post_done, 0));
+		if (!pm.empty()) cudaEventRecord(pm[(size_t) (6 * i)], st);
 		CUDA_TRY(jtk_launch_split(a, ds->num_sms, split_ctas_per_sm(), time_kernel ? w->kev[(size_t) (2 * i)] : nullptr, time_kernel ? w->kev[(size_t) (2 * i + 1)] : nullptr, st));
 		if (piped) {
 			CUDA_TRY(cudaEventRecord(w->lane[l].split_done, st));
 			CUDA_TRY(cudaStreamWaitEvent(w->post_stream, w->lane[l].split_done, 0));
 			CUDA_TRY(jtk_launch_post(a, ds->num_sms, w->post_stream, side));
 			CUDA_TRY(cudaEventRecord(w->lane[l].post_done, w->post_stream));
+		} else if (!pm.empty()) {
+			cudaEventRecord(pm[(size_t) (6 * i + 1)], st);
+			CUDA_TRY(jtk_launch_post(a, ds->num_sms, st, side, &pm[(size_t) (6 * i + 2)]));
 		} else {
 			CUDA_TRY(jtk_launch_post(a, ds->num_sms, st, side));
 		}
@@ -793,6 +806,24 @@ static int encode_device_impl(jtk_encoding *e, jtk_device_state *ds, jtk_workspa
 	CUDA_TRY(cudaMemcpyAsync(w->hdr_host, w->hdr, sizeof(jtk_batch_header), cudaMemcpyDeviceToHost, st));
 	if (!sync_and_long) return JTK_OK;
 	CUDA_TRY(cudaStreamSynchronize(st));
+	if (!pm.empty()) {
+		float tot[5] = {0, 0, 0, 0, 0};
+		for (int64_t i = 0; i < nsub; i++) {
+			std::string line = "jtk phases sub-batch " + std::to_string(i) + " (" + std::to_string(cuts[(size_t) i + 1] - cuts[(size_t) i]) + " tiles):";
+			static const char *const names[5] = {"split", "sort", "merge", "scan", "gather"};
+			for (int k = 0; k < 5; k++) {
+				float ms = 0;
+				cudaEventElapsedTime(&ms, pm[(size_t) (6 * i + k)], pm[(size_t) (6 * i + k + 1)]);
+				tot[k] += ms;
+				char buf[48];
+				snprintf(buf, sizeof(buf), " %s %.3f", names[k], ms);
+				line += buf;
+			}
+			fprintf(stderr, "%s\n", line.c_str());
+		}
+		fprintf(stderr, "jtk phases total: split %.3f sort %.3f merge %.3f scan %.3f gather %.3f ms\n", tot[0], tot[1], tot[2], tot[3], tot[4]);
+		for (cudaEvent_t ev : pm) cudaEventDestroy(ev);
+	}
 	if (time_kernel) {
 		info->tile_kernel_ms = 0;
 		for (int64_t i = 0; i < nsub; i++) {

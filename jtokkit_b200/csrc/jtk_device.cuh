@@ -697,6 +697,33 @@ JTK_HD uint32_t jtk_boundary_chunk(const jtk_tile_ctx &c, int chunk) {
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * safe cuts: positions inside a piece where bytePairMerge can be run separately on both sides (jtk_safe_cut below: the byte
+ * bigram around the position occurs in no token, so no merge ever crosses it and the piece as a whole cannot be a token
+ * either).  The split kernel lists such positions as additional piece starts: the unit of the merge kernels and of the memo
+ * becomes the SEGMENT - in scripts the vocabulary covers poorly a character or two instead of a run of letters.  Cuts are
+ * optional, so only chunks that contain a non-ASCII byte are examined (the 16-byte chunk grid is the same in every tile).
+ * ------------------------------------------------------------------------------------------- */
+JTK_HD bool jtk_safe_cut(const uint32_t *bits, uint32_t b0, uint32_t b1);
+/* cut bits of the 16 positions of chunk `chunk` (chunk >= 1); the caller masks document starts / the end of the input.  Only character
+ * boundaries next to a non-ASCII character are examined: a third of the positions in CJK text, almost none in English. */
+JTK_HD uint32_t jtk_cut_chunk(const jtk_tile_ctx &c, int chunk) {
+#ifdef JTK_NO_CUTS
+	return 0; /* development switch: no safe cuts at all (the pieces of the split pattern are the unit everywhere) */
+#endif
+	const uint32_t pch = c.planes[4 * chunk + 2];
+	if ((pch >> 16) == 0) return 0; /* all ASCII */
+	const uint8_t *p = c.sb + 16 * chunk;
+	uint32_t bits = 0;
+	/* candidates: character boundaries with a non-ASCII character on at least one side (ASCII runs are left to the split pattern) */
+	const uint32_t hb = pch >> 16, side = hb | (hb << 1) | (uint32_t) (p[-1] >> 7);
+	for (uint32_t m = side & ~pch & 0xFFFFu; m; m &= m - 1) {
+		const int i = jtk_ctz(m);
+		if (jtk_safe_cut(c.T->bigram_bits, p[i - 1], p[i])) bits |= 1u << i;
+	}
+	return bits;
+}
+
+/* ---------------------------------------------------------------------------------------------
  * special-token guard
  * ------------------------------------------------------------------------------------------- */
 /* Does any special token start at global position g (document ends at doc_hi)? */

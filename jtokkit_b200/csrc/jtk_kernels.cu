@@ -248,6 +248,8 @@ constexpr int PLIST_BYTES = ((2 * JTK_TILE > PLANE_BYTES ? 2 * JTK_TILE : PLANE_
 constexpr int WKEYS = 128; /* pieces of 9..24 bytes: full-key pass */
 constexpr int WODD = 64;   /* unusual pieces (longer keys, long pieces, the tile's last piece) */
 constexpr int WMISS = 96;  /* table misses: memo / queue pass */
+constexpr int PLIST_POS = 0x7FFF, PLIST_CUT = 0x8000; /* piece list entry: region index | "a safe cut, not a piece start of the split pattern" */
+static_assert(JTK_REGION + 32 <= PLIST_POS, "region indices must fit 15 bits");
 constexpr int DEFCAP = WKEYS * (JTK_NT / 32), ODDCAP = WODD * (JTK_NT / 32), MISSCAP = WMISS * (JTK_NT / 32);
 static_assert(SB_BYTES % 16 == 0 && COPY_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
 static_assert(JTK_REGION_CHUNKS + 1 <= NT, "one thread per region chunk");
@@ -256,7 +258,8 @@ static_assert(JTK_REGION_CHUNKS + 1 <= NT, "one thread per region chunk");
 enum { M_NSLOW = 0, M_HITS, M_SLOWTOK, M_CARRY = 4, M_TICKET /* 2 */, M_WSUM = 16, M_HIST = 48 /* .. M_HIST + JTK_SHORT_PIECE */, M_WORDS = 128 };
 static_assert(M_HIST + JTK_SHORT_PIECE + 1 <= M_WORDS, "misc too small");
 
-constexpr int SPLIT_SMEM_BYTES = 2 * SB_BYTES + PLIST_BYTES + 2 * 4 * JTK_MASK_WORDS + 4 * ((TC + 3) / 4 * 4) + 4 * M_WORDS + 1024 + 2048 + 2 * DEFCAP + 2 * ODDCAP + 2 * MISSCAP + 16;
+constexpr int MASK_BYTES = (4 * JTK_MASK_WORDS + 15) / 16 * 16; /* one bit mask over the region */
+constexpr int SPLIT_SMEM_BYTES = 2 * SB_BYTES + PLIST_BYTES + 3 * MASK_BYTES + 4 * ((TC + 3) / 4 * 4) + 4 * M_WORDS + 1024 + 2048 + 2 * DEFCAP + 2 * ODDCAP + 2 * MISSCAP + 16;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -298,8 +301,9 @@ extern __shared__ __align__(128) uint8_t jtk_dyn_smem[];
 constexpr int OFF_SB = 0;                                  /* two staging buffers */
 constexpr int OFF_PLANES = OFF_SB + 2 * SB_BYTES;          /* planes, later the piece list */
 constexpr int OFF_BMASK = OFF_PLANES + PLIST_BYTES;
-constexpr int OFF_DMASK = OFF_BMASK + 4 * JTK_MASK_WORDS;
-constexpr int OFF_CPREF = OFF_DMASK + 4 * JTK_MASK_WORDS;  /* pieces before each 16-byte chunk of the tile */
+constexpr int OFF_DMASK = OFF_BMASK + MASK_BYTES;
+constexpr int OFF_RMASK = OFF_DMASK + MASK_BYTES;  /* starts of the split pattern's pieces alone (bmask also has the safe cuts) */
+constexpr int OFF_CPREF = OFF_RMASK + MASK_BYTES;  /* pieces before each 16-byte chunk of the tile */
 constexpr int OFF_MISC = OFF_CPREF + 4 * ((TC + 3) / 4 * 4);
 constexpr int OFF_LUT = OFF_MISC + 4 * M_WORDS;
 constexpr int OFF_CLS2 = OFF_LUT + 1024;
@@ -314,6 +318,7 @@ struct split_smem {
 	__device__ __forceinline__ uint16_t *plist() const { return reinterpret_cast<uint16_t *>(jtk_dyn_smem + OFF_PLANES); }
 	__device__ __forceinline__ uint32_t *bmask() const { return reinterpret_cast<uint32_t *>(jtk_dyn_smem + OFF_BMASK); }
 	__device__ __forceinline__ uint32_t *dmask() const { return reinterpret_cast<uint32_t *>(jtk_dyn_smem + OFF_DMASK); }
+	__device__ __forceinline__ uint32_t *rmask() const { return reinterpret_cast<uint32_t *>(jtk_dyn_smem + OFF_RMASK); }
 	__device__ __forceinline__ uint32_t *chunk_pref() const { return reinterpret_cast<uint32_t *>(jtk_dyn_smem + OFF_CPREF); }
 	__device__ __forceinline__ uint32_t *misc() const { return reinterpret_cast<uint32_t *>(jtk_dyn_smem + OFF_MISC); }
 	__device__ __forceinline__ uint32_t *lut_sp() const { return reinterpret_cast<uint32_t *>(jtk_dyn_smem + OFF_LUT); }
@@ -378,9 +383,9 @@ template <bool GENERAL>
 __device__ __noinline__ int split_slow_piece(const jtk_encode_args &a, const uint8_t *sb, int q, int npieces, long long lt, int64_t tb) {
 	const jtk_tables &T = a.T;
 	const split_smem S;
-	const int r = S.plist()[q];
+	const int r = S.plist()[q] & PLIST_POS;
 	const int s = r - BH;
-	int e = (q + 1 < npieces) ? (int) S.plist()[q + 1] : next_bit(S.bmask(), r + 1, r + JTK_LONG_PIECE);
+	int e = (q + 1 < npieces) ? (int) (S.plist()[q + 1] & PLIST_POS) : next_bit(S.bmask(), r + 1, r + JTK_LONG_PIECE);
 	if (e >= 0 && e - r > JTK_LONG_PIECE) e = -1;
 	if (e < 0) { /* longer than JTK_LONG_PIECE: deferred to the long-piece kernels */
 		const unsigned idx = atomicAdd(&a.hdr->n_long, 1u);
@@ -402,7 +407,9 @@ __device__ __noinline__ int split_slow_piece(const jtk_encode_args &a, const uin
 	const int n = e - r;
 	const uint8_t *p = sb + r;
 	int32_t out;
-	if (n <= JTK_INLINE_KEY_MAX) {
+	if (!GENERAL && n != 1 && !(((S.rmask()[r >> 5] >> (r & 31)) & (S.rmask()[e >> 5] >> (e & 31))) & 1u)) {
+		out = JTK_RANK_MAX; /* a segment between safe cuts, not a piece of the split pattern: no whole-piece shortcut */
+	} else if (n <= JTK_INLINE_KEY_MAX) {
 		uint32_t key[6];
 		jtk_build_key(p, n, key);
 		out = jtk_lookup_a(T, key, (uint32_t) n, jtk_hash6(key, (uint32_t) n));
@@ -423,7 +430,7 @@ __global__ void __launch_bounds__(JTK_NT, JTK_SPLIT_CTAS) jtk_split_lookup_kerne
 	const split_smem L;
 	struct {
 		uint8_t *sb0;
-		uint32_t *planes, *bmask, *dmask, *chunk_pref, *lut_sp;
+		uint32_t *planes, *bmask, *dmask, *rmask, *chunk_pref, *lut_sp;
 		uint16_t *plist, *deflist, *oddlist, *misslist;
 		uint8_t *cls2;
 		uint64_t *mbar;
@@ -433,6 +440,7 @@ __global__ void __launch_bounds__(JTK_NT, JTK_SPLIT_CTAS) jtk_split_lookup_kerne
 	S.plist = L.plist(); /* region index of every piece start, in order (written after the planes' last use) */
 	S.bmask = L.bmask();
 	S.dmask = L.dmask();
+	S.rmask = L.rmask();
 	S.chunk_pref = L.chunk_pref();
 	S.lut_sp = L.lut_sp();
 	S.cls2 = L.cls2();
@@ -449,7 +457,7 @@ __global__ void __launch_bounds__(JTK_NT, JTK_SPLIT_CTAS) jtk_split_lookup_kerne
 	/* ---- once per CTA: tables, zeroed masks and pads, barriers, the first two tickets ---- */
 	for (int i = tid; i < 256; i += NT) S.lut_sp[i] = T.lut_sp[i];
 	for (int i = tid; i < 512; i += NT) reinterpret_cast<uint32_t *>(S.cls2)[i] = reinterpret_cast<const uint32_t *>(T.cls2)[i];
-	for (int w = tid; w < 2 * JTK_MASK_WORDS; w += NT) S.bmask[w] = 0; /* bmask and dmask */
+	for (int w = tid; w < 3 * MASK_BYTES / 4; w += NT) S.bmask[w] = 0; /* bmask, dmask and rmask */
 	if (tid < M_WORDS) misc[tid] = 0;
 	if (tid < 8) { /* the 16 bytes after what the copies cover stay zero for good */
 		reinterpret_cast<uint32_t *>(S.sb0 + (tid >> 2) * SB_BYTES + COPY_BYTES)[tid & 3] = 0;
@@ -565,6 +573,7 @@ __global__ void __launch_bounds__(JTK_NT, JTK_SPLIT_CTAS) jtk_split_lookup_kerne
 					}
 				}
 		}
+		uint32_t cutbits = 0;
 		if (!GENERAL) {
 			__syncthreads();
 			/* \p{N} carry into the region: needed only when the region starts inside a digit run (the same answer in every thread) */
@@ -576,10 +585,16 @@ __global__ void __launch_bounds__(JTK_NT, JTK_SPLIT_CTAS) jtk_split_lookup_kerne
 			/* ---- P3: split rules -> piece-start bits ---- */
 			{
 				const int ch = BH / 16 + tid;
-				if (ch < JTK_REGION_CHUNKS) reinterpret_cast<uint16_t *>(S.bmask)[ch] = (uint16_t) jtk_boundary_chunk(c, ch);
+				if (ch < JTK_REGION_CHUNKS) {
+					const uint32_t rb = jtk_boundary_chunk(c, ch);
+					cutbits = jtk_cut_chunk(c, ch) & ~rb;
+					reinterpret_cast<uint16_t *>(S.rmask)[ch] = (uint16_t) rb;
+					reinterpret_cast<uint16_t *>(S.bmask)[ch] = (uint16_t) (rb | cutbits);
+				}
 			}
 		}
-		__syncthreads();
+		/* (does the region have any safe cut?  if not - English text - every listed piece is a piece of the split pattern) */
+		const bool any_cuts = __syncthreads_or(cutbits != 0) != 0;
 
 		/* ---- P4a: list the piece starts of the tile in order (thread owns one chunk) ---- */
 		uint32_t bits;
@@ -593,7 +608,8 @@ __global__ void __launch_bounds__(JTK_NT, JTK_SPLIT_CTAS) jtk_split_lookup_kerne
 			bits = m;
 			mycount = __popc(m);
 			if (a.piece_flags && ch < TC) {
-				const uint32_t real = GENERAL ? m & ~(uint32_t) reinterpret_cast<const uint16_t *>(S.dmask)[BH / 16 + ch] : m; /* gaps are not pieces */
+				/* the split pattern's own pieces: gaps are not pieces (general patterns), safe cuts are not piece starts */
+				const uint32_t real = GENERAL ? m & ~(uint32_t) reinterpret_cast<const uint16_t *>(S.dmask)[BH / 16 + ch] : m & reinterpret_cast<const uint16_t *>(S.rmask)[BH / 16 + ch];
 				for (int i = 0; i < 16 && gbase + i < a.total; i++) a.piece_flags[gbase + i] = (real >> i) & 1u;
 			}
 		}
@@ -622,10 +638,14 @@ __global__ void __launch_bounds__(JTK_NT, JTK_SPLIT_CTAS) jtk_split_lookup_kerne
 		if (!GENERAL)
 			for (int w = tid; w < JTK_MASK_WORDS; w += NT) S.dmask[w] = 0;
 		if (tid < TC) S.chunk_pref[tid] = (uint32_t) base;
-		for (uint32_t m = bits; m;) {
-			const int i = __ffs((int) m) - 1;
-			m &= m - 1;
-			S.plist[base++] = (uint16_t) (BH + tid * 16 + i);
+		{
+			/* bit 15 of an entry: the start is a safe cut, not a piece start of the split pattern (region indices need 13 bits) */
+			const uint32_t cut16 = (any_cuts && tid < TC) ? bits & ~(uint32_t) reinterpret_cast<const uint16_t *>(S.rmask)[BH / 16 + tid] : 0u;
+			for (uint32_t m = bits; m;) {
+				const int i = __ffs((int) m) - 1;
+				m &= m - 1;
+				S.plist[base++] = (uint16_t) ((BH + tid * 16 + i) | (((cut16 >> i) & 1u) << 15));
+			}
 		}
 		if (tid == 0) {
 			/* first piece start of the tile (the end of the input counts), for the long-piece bounds kernel */
@@ -647,11 +667,16 @@ __global__ void __launch_bounds__(JTK_NT, JTK_SPLIT_CTAS) jtk_split_lookup_kerne
 			const int q = q0 + tid;
 			int kind = 0; /* 1: key of 9..24 bytes, 2: unusual, 3: miss of the short probe */
 			if (q < npieces) {
-				const int r = S.plist[q];
-				const int e = (q + 1 < npieces) ? (int) S.plist[q + 1] : -1; /* the tile's last piece ends in the halo: unusual */
+				const int pr = S.plist[q], pe = (q + 1 < npieces) ? (int) S.plist[q + 1] : -1; /* the tile's last piece ends in the halo: unusual */
+				const int r = pr & PLIST_POS, e = pe < 0 ? -1 : (pe & PLIST_POS);
 				const int n = e - r;
+				/* a segment between safe cuts is not a piece of the split pattern: no whole-piece shortcut for it (:81-83 looks the PIECE up);
+				 * a single byte is its own token either way */
+				const bool part = n != 1 && pe >= 0 && ((pr | pe) & PLIST_CUT);
 				if (GENERAL && ((S.dmask[r >> 5] >> (r & 31)) & 1u)) {
 					rec[q] = REC_BASE + (int32_t) REC_SKIP;
+				} else if (part) {
+					kind = n <= JTK_INLINE_KEY_MAX ? 3 : 2;
 				} else if ((unsigned) (n - 1) < 8u) {
 					const uint32_t *aw = reinterpret_cast<const uint32_t *>(sb + (r & ~3));
 					const int sh = (r & 3) * 8;
@@ -708,7 +733,7 @@ __global__ void __launch_bounds__(JTK_NT, JTK_SPLIT_CTAS) jtk_split_lookup_kerne
 			int q = 0;
 			if (i < nkeys) {
 				q = wkeys[i];
-				const int r = S.plist[q], n = (int) S.plist[q + 1] - r;
+				const int r = S.plist[q] & PLIST_POS, n = (int) (S.plist[q + 1] & PLIST_POS) - r;
 				uint32_t key[6];
 				jtk_build_key(sb + r, n, key);
 				const int32_t out = jtk_lookup_a(T, key, (uint32_t) n, jtk_hash6(key, (uint32_t) n));
@@ -735,8 +760,8 @@ __global__ void __launch_bounds__(JTK_NT, JTK_SPLIT_CTAS) jtk_split_lookup_kerne
 		nmiss = min(nmiss, WMISS);
 		for (int i = lane; i < nmiss; i += 32) {
 			const int q = wmiss[i];
-			const int r = S.plist[q];
-			hits += split_resolve_miss(a, sb, q, r, (int) S.plist[q + 1] - r, lt);
+			const int r = S.plist[q] & PLIST_POS;
+			hits += split_resolve_miss(a, sb, q, r, (int) (S.plist[q + 1] & PLIST_POS) - r, lt);
 		}
 		hits = __reduce_add_sync(0xFFFFFFFFu, hits);
 		if (lane == 0 && hits) atomicAdd(&misc[M_HITS], (uint32_t) hits);
@@ -1658,7 +1683,8 @@ cudaError_t jtk_launch_tile_first_doc(const int64_t *doc_off, int64_t ndocs, int
 
 static unsigned l2_window_attr(const jtk_encode_args &a, cudaLaunchAttribute *attr) {
 	/* the table-probing kernels run with the hot tables pinned in L2 (persisting hits, streaming misses) */
-	if (a.l2_bytes == 0) return 0;
+	static const bool off = getenv("JTK_L2_WINDOW") && getenv("JTK_L2_WINDOW")[0] == '0'; /* development switch */
+	if (a.l2_bytes == 0 || off) return 0;
 	attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
 	attr[0].val.accessPolicyWindow.base_ptr = const_cast<void *>(a.l2_base);
 	attr[0].val.accessPolicyWindow.num_bytes = a.l2_bytes;
@@ -1692,7 +1718,7 @@ cudaError_t jtk_launch_split(const jtk_encode_args &a, int num_sms, int ctas_per
 }
 
 /* everything after it: sort the unresolved short pieces by length, merge, scan, gather */
-cudaError_t jtk_launch_post(const jtk_encode_args &a, int num_sms, cudaStream_t st, const jtk_side_streams *side) {
+cudaError_t jtk_launch_post(const jtk_encode_args &a, int num_sms, cudaStream_t st, const jtk_side_streams *side, cudaEvent_t *marks) {
 	const int64_t nt = a.tile_end - a.tile_begin;
 	if (nt <= 0) return cudaSuccess;
 	cudaLaunchAttribute attr[1];
@@ -1702,6 +1728,7 @@ cudaError_t jtk_launch_post(const jtk_encode_args &a, int num_sms, cudaStream_t 
 	cfg.numAttrs = l2_window_attr(a, attr);
 	jtk_short_offsets_kernel<<<1, 32, 0, st>>>(a);
 	jtk_short_scatter_kernel<<<(unsigned) nt, SNT, 0, st>>>(a);
+	if (marks) cudaEventRecord(marks[0], st);
 	/* the four merge kernels are independent of each other (own lists, own pieces): longest chains first, side by side */
 	if (side) {
 		cudaEventRecord(side->fork, st);
@@ -1726,8 +1753,11 @@ cudaError_t jtk_launch_post(const jtk_encode_args &a, int num_sms, cudaStream_t 
 			cudaEventRecord(side->join[i], side->s[i]);
 			cudaStreamWaitEvent(st, side->join[i], 0);
 		}
+	if (marks) cudaEventRecord(marks[1], st);
 	jtk_tile_scan_kernel<<<1, 1024, 0, st>>>(a);
+	if (marks) cudaEventRecord(marks[2], st);
 	jtk_gather_kernel<<<(unsigned) nt, GNT, 0, st>>>(a);
+	if (marks) cudaEventRecord(marks[3], st);
 	return cudaGetLastError();
 }
 

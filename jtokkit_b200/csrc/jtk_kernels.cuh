@@ -112,7 +112,8 @@ struct jtk_side_streams {
 /* the kernels of one sub-batch in two parts, so that the second part of sub-batch k can run (on its own stream, other lane of
  * buffers) next to the first part of sub-batch k + 1; k0/k1 (nullable) bracket the split+lookup kernel */
 cudaError_t jtk_launch_split(const jtk_encode_args &a, int num_sms, int ctas_per_sm, cudaEvent_t k0, cudaEvent_t k1, cudaStream_t st);
-cudaError_t jtk_launch_post(const jtk_encode_args &a, int num_sms, cudaStream_t st, const jtk_side_streams *side);
+/* marks (nullable, development aid): four events recorded after the scatter, after the merge kernels have joined, after the scan and after the gather */
+cudaError_t jtk_launch_post(const jtk_encode_args &a, int num_sms, cudaStream_t st, const jtk_side_streams *side, cudaEvent_t *marks = nullptr);
 cudaError_t jtk_launch_finalize(const jtk_encode_args &a, cudaStream_t st);
 /* JTK_PAT_GENERAL: Matcher.find() over every document before the sub-batches, in three passes (speculative per slice, stitch per
  * document, finish per word: jtk_regex.h); rx_start / rx_skip / rx_spec must be zeroed */

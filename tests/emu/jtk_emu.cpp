@@ -52,10 +52,10 @@ void emu_stats(const emu_encoding *e, int64_t *out) {
 
 struct emu_tile_state {
 	std::vector<uint32_t> sbw; /* word aligned staging buffer */
-	std::vector<uint32_t> bmask, dmask, planes;
+	std::vector<uint32_t> bmask, dmask, planes, cmask; /* cmask: safe-cut bits (jtk_cut_chunk), kept apart from the pattern's piece starts */
 	std::vector<int32_t> tok, rk;
 	jtk_tile_ctx c;
-	emu_tile_state() : sbw((JTK_REGION + 32) / 4 + 1), bmask(JTK_MASK_WORDS), dmask(JTK_MASK_WORDS), planes(4 * (JTK_REGION_CHUNKS + 2)), tok(JTK_TILE + JTK_FWD_HALO), rk(JTK_TILE + JTK_FWD_HALO) {
+	emu_tile_state() : sbw((JTK_REGION + 32) / 4 + 1), bmask(JTK_MASK_WORDS), dmask(JTK_MASK_WORDS), cmask(JTK_MASK_WORDS), planes(4 * (JTK_REGION_CHUNKS + 2)), tok(JTK_TILE + JTK_FWD_HALO), rk(JTK_TILE + JTK_FWD_HALO) {
 		c.sb = reinterpret_cast<uint8_t *>(sbw.data());
 		c.bmask = bmask.data();
 		c.dmask = dmask.data();
@@ -77,9 +77,15 @@ struct emu_tile_state {
 		c.rs = jtk_region_first(c);
 		for (int ch = 0; ch <= JTK_REGION_CHUNKS; ch++) jtk_classify_chunk(c, ch);
 		c.carry_n = jtk_region_carry_n(c);
-		for (int ch = JTK_BACK_HALO / 16; ch < JTK_REGION_CHUNKS; ch++) ((uint16_t *) bmask.data())[ch] = (uint16_t) jtk_boundary_chunk(c, ch);
+		std::fill(cmask.begin(), cmask.end(), 0u);
+		for (int ch = JTK_BACK_HALO / 16; ch < JTK_REGION_CHUNKS; ch++) {
+			const uint32_t rb = jtk_boundary_chunk(c, ch);
+			((uint16_t *) bmask.data())[ch] = (uint16_t) rb;
+			((uint16_t *) cmask.data())[ch] = (uint16_t) (jtk_cut_chunk(c, ch) & ~rb);
+		}
 	}
 	bool bit(int r) const { return (bmask[(size_t) (r >> 5)] >> (r & 31)) & 1u; }
+	bool cut(int r) const { return (cmask[(size_t) (r >> 5)] >> (r & 31)) & 1u; }
 };
 
 /*
@@ -93,7 +99,7 @@ int64_t emu_run(const emu_encoding *e, const uint8_t *bytes, int64_t total, cons
                 uint8_t *piece_flags, int32_t *ids, int64_t *tok_off, int32_t *status) {
 	std::vector<uint8_t> in((size_t) total + 64, 0); /* 16-byte aligned copy of the input, as the device buffer is */
 	if (total) memcpy(in.data(), bytes, (size_t) total);
-	std::vector<uint8_t> start((size_t) total + 1, 0), halo((size_t) total + 1, 2);
+	std::vector<uint8_t> start((size_t) total + 1, 0), halo((size_t) total + 1, 2), cutat((size_t) total + 1, 0), hcut((size_t) total + 1, 2);
 	const int64_t ntiles = (total + JTK_TILE - 1) / JTK_TILE;
 	emu_tile_state t;
 	t.c.total = total;
@@ -109,13 +115,16 @@ int64_t emu_run(const emu_encoding *e, const uint8_t *bytes, int64_t total, cons
 		for (int r = JTK_BACK_HALO; r < JTK_BACK_HALO + JTK_TILE + JTK_LONG_PIECE + 1; r++) {
 			const int64_t g = t.c.g0 + r;
 			if (g >= total) break;
-			const uint8_t b = t.bit(r) ? 1 : 0;
+			const uint8_t b = t.bit(r) ? 1 : 0, cb = t.cut(r) ? 1 : 0;
 			if (r < JTK_BACK_HALO + JTK_TILE) {
 				start[(size_t) g] = b;
+				cutat[(size_t) g] = cb;
 				if (halo[(size_t) g] != 2 && halo[(size_t) g] != b) halo_mismatch++;
+				if (hcut[(size_t) g] != 2 && hcut[(size_t) g] != cb) halo_mismatch++; /* the cuts a tile sees in its halo are the owner's */
 			} else if (halo[(size_t) g] == 2) {
 				halo[(size_t) g] = b;
-			} else if (halo[(size_t) g] != b) {
+				hcut[(size_t) g] = cb;
+			} else if (halo[(size_t) g] != b || hcut[(size_t) g] != cb) {
 				halo_mismatch++;
 			}
 		}
@@ -146,20 +155,24 @@ int64_t emu_run(const emu_encoding *e, const uint8_t *bytes, int64_t total, cons
 		const int64_t n = eg - g;
 		const uint8_t *p = in.data() + g;
 		bool unknown = false;
+		bool has_cut = false;
+		for (int64_t i = 1; i < n; i++) has_cut |= cutat[(size_t) (g + i)] != 0;
 		if (n == 1) {
 			int32_t id = e->view.byte_id[p[0]];
 			if (id < JTK_PSEUDO_BASE + 256) unknown = true;
 			ids[out_pos++] = id;
 		} else {
-			int32_t whole = jtk_lookup_piece(e->view, p, (int) n);
+			/* like the split kernel: a piece with a safe cut inside is never looked up as a whole (it cannot be a token), its segments are
+			 * merged one by one; a piece without cuts takes the whole-piece shortcut first (GptBytePairEncoding.java:81-83) */
+			int32_t whole = has_cut ? JTK_RANK_MAX : jtk_lookup_piece(e->view, p, (int) n);
+			if (has_cut && jtk_lookup_piece(e->view, p, (int) n) != JTK_RANK_MAX) return -2000000; /* the argument above must hold */
 			if (whole != JTK_RANK_MAX) {
 				ids[out_pos++] = whole;
 			} else {
-				/* like the merge kernels: independently on the segments between safe cuts (jtk_safe_cut) */
 				std::vector<int32_t> t2((size_t) n), r2((size_t) n), nx((size_t) n + 1);
 				int64_t sa = 0;
 				for (int64_t i = 1; i <= n; i++) {
-					if (i < n && !jtk_safe_cut(e->view.bigram_bits, p[i - 1], p[i])) continue;
+					if (i < n && !cutat[(size_t) (g + i)]) continue;
 					const int64_t len = i - sa;
 					int cnt;
 					if (len <= JTK_SHORT_PIECE) cnt = jtk_merge_short(e->view, p + sa, (int) len, t2.data(), r2.data(), 1, &unknown);

@@ -192,7 +192,7 @@ static int init_device(jtk_encoding *e, int device) {
 	/* hot tables first: they form the persisting window */
 	const size_t o_tab_a = ar.add(h.tab_a), o_pair = ar.add(h.pair), o_bytepair = ar.add(h.bytepair), o_byte_id = ar.add(h.byte_id);
 	const size_t o_ascii = ar.add(h.ascii_cls), o_st1 = ar.add(h.cp_stage1), o_st2 = ar.add(h.cp_stage2), o_tab_b = ar.add(h.tab_b), o_filt = ar.add(h.long_filter);
-	const size_t o_lsp = ar.add(h.lut_sp), o_cls2 = ar.add(h.cls2), o_nib = ar.add(h.bmp_nib), o_big = ar.add(h.bigram_bits);
+	const size_t o_lsp = ar.add(h.lut_sp), o_cls2 = ar.add(h.cls2), o_nib = ar.add(h.bmp_nib), o_big = ar.add(h.bigram_bits), o_tri = ar.add(h.trigram_bits);
 	const size_t hot_bytes = ar.total;
 	const size_t o_tokb = ar.add(h.tok_bytes), o_toko = ar.add(h.tok_off), o_spb = ar.add(h.special_bytes), o_spo = ar.add(h.special_off);
 	const size_t o_deck = ar.add(h.dec_keys), o_decb = ar.add(h.dec_bytes), o_deco = ar.add(h.dec_off);
@@ -214,6 +214,7 @@ static int init_device(jtk_encoding *e, int device) {
 	T.cls2 = base + o_cls2;
 	T.bmp_nib = base + o_nib;
 	T.bigram_bits = reinterpret_cast<const uint32_t *>(base + o_big);
+	T.trigram_bits = reinterpret_cast<const uint32_t *>(base + o_tri);
 	T.tab_b = reinterpret_cast<const jtk_slot *>(base + o_tab_b);
 	T.long_filter = reinterpret_cast<const uint32_t *>(base + o_filt);
 	T.tok_bytes = base + o_tokb;

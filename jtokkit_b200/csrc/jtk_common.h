@@ -135,6 +135,8 @@ struct jtk_tables {
 	const int32_t *bytepair;    /* 65536: rank of the two-byte token b0 b1, or JTK_RANK_MAX */
 	const jtk_slot *pair;       /* slot = {id left, id right, rank, 1} ; empty slot has w == 0 */
 	uint32_t mask_p;
+	const uint32_t *trigram_bits; /* 2^20 bits, hashed (jtk_trigram_slot): set for every three bytes that occur next to each other in some token (a set bit may
+	                               * also be a hash collision: the test errs on the side of "occurs") */
 	const uint32_t *bigram_bits; /* 65536 bits: bit (b0 << 8 | b1) is set when some token contains the bytes b0 b1 next to each other.  Where it is
 	                              * clear no merge can ever join the two bytes, so bytePairMerge runs independently on both sides (jtk_safe_cut) */
 	/* special-token guard (GptBytePairEncoding.java:52-56) */
@@ -195,6 +197,9 @@ JTK_HD uint32_t jtk_hash_pair(int32_t l, int32_t r) {
 	h ^= h >> 13;
 	return h;
 }
+
+/* slot of a byte trigram in jtk_tables::trigram_bits */
+JTK_HD uint32_t jtk_trigram_slot(uint32_t b0, uint32_t b1, uint32_t b2) { return (((b0 << 16) | (b1 << 8) | b2) * 0x9E3779B1u) >> 12; }
 
 /* 64-bit byte-string hash for table B (FNV-1a over bytes, then a finaliser) */
 JTK_HD uint64_t jtk_hash_bytes_step(uint64_t h, uint8_t b) { return (h ^ b) * 0x100000001B3ull; }

@@ -704,6 +704,16 @@ JTK_HD uint32_t jtk_boundary_chunk(const jtk_tile_ctx &c, int chunk) {
  * optional, so only chunks that contain a non-ASCII byte are examined (the 16-byte chunk grid is the same in every tile).
  * ------------------------------------------------------------------------------------------- */
 JTK_HD bool jtk_safe_cut(const uint32_t *bits, uint32_t b0, uint32_t b1);
+/* The finer test with one byte of context on either side: the first merge that crosses the position between b1 and b2 joins a part
+ * that ends with b1 and a part that begins with b2 into a token; that token is b1 b2 itself, or it contains b0 b1 b2 or b1 b2 b3.  If
+ * none of the three exists no merge crosses the position.  (b0 / b3 may belong to a neighbouring document or be padding: the test
+ * can then only say "may cross" too often, never too rarely.) */
+JTK_HD bool jtk_safe_cut4(const jtk_tables &T, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
+	if (jtk_safe_cut(T.bigram_bits, b1, b2)) return true;
+	if (JTK_LDG(T.bytepair + ((b1 << 8) | b2)) != JTK_RANK_MAX) return false;
+	const uint32_t s0 = jtk_trigram_slot(b0, b1, b2), s1 = jtk_trigram_slot(b1, b2, b3);
+	return !(((JTK_LDG(T.trigram_bits + (s0 >> 5)) >> (s0 & 31)) | (JTK_LDG(T.trigram_bits + (s1 >> 5)) >> (s1 & 31))) & 1u);
+}
 /* cut bits of the 16 positions of chunk `chunk` (chunk >= 1); the caller masks document starts / the end of the input.  Only character
  * boundaries next to a non-ASCII character are examined: a third of the positions in CJK text, almost none in English. */
 JTK_HD uint32_t jtk_cut_chunk(const jtk_tile_ctx &c, int chunk) {
@@ -718,7 +728,7 @@ JTK_HD uint32_t jtk_cut_chunk(const jtk_tile_ctx &c, int chunk) {
 	const uint32_t hb = pch >> 16, side = hb | (hb << 1) | (uint32_t) (p[-1] >> 7);
 	for (uint32_t m = side & ~pch & 0xFFFFu; m; m &= m - 1) {
 		const int i = jtk_ctz(m);
-		if (jtk_safe_cut(c.T->bigram_bits, p[i - 1], p[i])) bits |= 1u << i;
+		if (jtk_safe_cut4(*c.T, p[i - 2], p[i - 1], p[i], p[i + 1])) bits |= 1u << i;
 	}
 	return bits;
 }

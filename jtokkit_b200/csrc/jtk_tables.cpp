@@ -299,12 +299,17 @@ int jtk_build_host_tables(const jtk_params *p, jtk_host_tables *t, std::string *
 
 	/* byte bigrams that occur inside some token (see jtk_tables::bigram_bits) */
 	t->bigram_bits.assign(2048, 0);
+	t->trigram_bits.assign(32768, 0);
 	for (int64_t k = 0; k < ntok; k++) {
 		const uint8_t *kb = t->tok_bytes.data() + t->tok_off[(size_t) k];
 		const uint32_t len = t->tok_off[(size_t) k + 1] - t->tok_off[(size_t) k];
 		for (uint32_t i = 0; i + 1 < len; i++) {
 			const uint32_t g = (uint32_t) kb[i] << 8 | kb[i + 1];
 			t->bigram_bits[g >> 5] |= 1u << (g & 31);
+		}
+		for (uint32_t i = 0; i + 2 < len; i++) {
+			const uint32_t g = jtk_trigram_slot(kb[i], kb[i + 1], kb[i + 2]);
+			t->trigram_bits[g >> 5] |= 1u << (g & 31);
 		}
 	}
 
@@ -503,6 +508,7 @@ jtk_tables jtk_host_view(const jtk_host_tables &h) {
 	v.pair = h.pair.data();
 	v.mask_p = h.mask_p;
 	v.bigram_bits = h.bigram_bits.data();
+	v.trigram_bits = h.trigram_bits.data();
 	v.nspecial = h.nspecial;
 	v.special_has_empty = h.special_has_empty;
 	v.special_bytes = h.special_bytes.data();

@@ -36,7 +36,7 @@ struct jtk_host_tables {
 	std::vector<int32_t> bytepair;
 	std::vector<jtk_slot> pair;
 	uint32_t mask_p = 0;
-	std::vector<uint32_t> bigram_bits;
+	std::vector<uint32_t> bigram_bits, trigram_bits;
 	int32_t nspecial = 0;
 	int32_t special_has_empty = 0;
 	std::vector<uint8_t> special_bytes;

@@ -245,9 +245,9 @@ constexpr int COPY_BYTES = JTK_REGION + 16;               /* what the bulk copy 
 constexpr int PLANE_BYTES = 16 * (JTK_REGION_CHUNKS + 2); /* four plane words per chunk */
 constexpr int PLIST_BYTES = ((2 * JTK_TILE > PLANE_BYTES ? 2 * JTK_TILE : PLANE_BYTES) + 15) / 16 * 16; /* plist reuses the planes' memory after P3 */
 /* per-warp lists of the lookup step (what does not fit is resolved in place) */
-constexpr int WKEYS = 128; /* pieces of 9..24 bytes: full-key pass */
+constexpr int WKEYS = 64;  /* pieces of 9..24 bytes: full-key pass (drained 32 at a time: never more than 63 entries) */
 constexpr int WODD = 64;   /* unusual pieces (longer keys, long pieces, the tile's last piece) */
-constexpr int WMISS = 96;  /* table misses: memo / queue pass */
+constexpr int WMISS = 96;  /* table misses: memo / queue pass (drained 32 at a time: never more than 31 + 32 + 32 entries) */
 constexpr int PLIST_POS = 0x7FFF, PLIST_CUT = 0x8000; /* piece list entry: region index | "a safe cut, not a piece start of the split pattern" */
 static_assert(JTK_REGION + 32 <= PLIST_POS, "region indices must fit 15 bits");
 constexpr int DEFCAP = WKEYS * (JTK_NT / 32), ODDCAP = WODD * (JTK_NT / 32), MISSCAP = WMISS * (JTK_NT / 32);
@@ -663,6 +663,40 @@ __global__ void __launch_bounds__(JTK_NT, JTK_SPLIT_CTAS) jtk_split_lookup_kerne
 		int hits = 0;
 		uint16_t *const wkeys = S.deflist + warp * WKEYS, *const wodd = S.oddlist + warp * WODD, *const wmiss = S.misslist + warp * WMISS;
 		int nkeys = 0, nodd = 0, nmiss = 0; /* warp-uniform */
+		/* the lists are worked off 32 entries at a time as soon as 32 have come together (always from the top), so they stay short */
+		auto drain_miss = [&](int cnt) { /* pass 3 on the top cnt <= 32 entries: memo of this call, else the merge kernels' queues */
+			__syncwarp();
+			if (lane < cnt) {
+				const int q = wmiss[nmiss - cnt + lane];
+				const int r = S.plist[q] & PLIST_POS;
+				hits += split_resolve_miss(a, sb, q, r, (int) (S.plist[q + 1] & PLIST_POS) - r, lt);
+			}
+			nmiss -= cnt;
+			__syncwarp();
+		};
+		auto drain_keys = [&](int cnt) { /* pass 2 on the top cnt <= 32 entries: full-key probe of the 9..24-byte keys */
+			__syncwarp();
+			bool miss = false;
+			int q = 0;
+			if (lane < cnt) {
+				q = wkeys[nkeys - cnt + lane];
+				const int r = S.plist[q] & PLIST_POS, n = (int) (S.plist[q + 1] & PLIST_POS) - r;
+				uint32_t key[6];
+				jtk_build_key(sb + r, n, key);
+				const int32_t out = jtk_lookup_a(T, key, (uint32_t) n, jtk_hash6(key, (uint32_t) n));
+				if (out != JTK_RANK_MAX) {
+					rec[q] = out;
+					hits++;
+				} else {
+					miss = true;
+				}
+			}
+			nkeys -= cnt;
+			const unsigned mm = __ballot_sync(0xFFFFFFFFu, miss);
+			if (miss) wmiss[nmiss + __popc(mm & ((1u << lane) - 1u))] = (uint16_t) q; /* (nmiss < 32 here: room for 32 more) */
+			nmiss += __popc(mm);
+			if (nmiss >= 32) drain_miss(32);
+		};
 		for (int q0 = 0; q0 < npieces; q0 += NT) {
 			const int q = q0 + tid;
 			int kind = 0; /* 1: key of 9..24 bytes, 2: unusual, 3: miss of the short probe */
@@ -706,13 +740,9 @@ __global__ void __launch_bounds__(JTK_NT, JTK_SPLIT_CTAS) jtk_split_lookup_kerne
 				const unsigned below = (1u << lane) - 1u;
 				bool placed = true;
 				if (kind == 1) {
-					const int sl = nkeys + __popc(m1 & below);
-					placed = sl < WKEYS;
-					if (placed) wkeys[sl] = (uint16_t) q;
+					wkeys[nkeys + __popc(m1 & below)] = (uint16_t) q; /* (nkeys, nmiss < 32 before the append: always room) */
 				} else if (kind == 3) {
-					const int sl = nmiss + __popc(m3 & below);
-					placed = sl < WMISS;
-					if (placed) wmiss[sl] = (uint16_t) q;
+					wmiss[nmiss + __popc(m3 & below)] = (uint16_t) q;
 				} else if (kind == 2) {
 					const int sl = nodd + __popc(m2 & below);
 					placed = sl < WODD;
@@ -722,47 +752,16 @@ __global__ void __launch_bounds__(JTK_NT, JTK_SPLIT_CTAS) jtk_split_lookup_kerne
 				nmiss += __popc(m3);
 				nodd += __popc(m2);
 				if (!placed) hits += split_slow_piece<GENERAL>(a, sb, q, npieces, lt, tb); /* list full: resolve in place */
+				if (nmiss >= 32) drain_miss(32);
+				if (nkeys >= 32) drain_keys(32);
 			}
 		}
-		__syncwarp();
-		/* pass 2: keys of 9..24 bytes: full-key probe */
-		nkeys = min(nkeys, WKEYS);
-		for (int i0 = 0; i0 < nkeys; i0 += 32) {
-			const int i = i0 + lane;
-			bool miss = false;
-			int q = 0;
-			if (i < nkeys) {
-				q = wkeys[i];
-				const int r = S.plist[q] & PLIST_POS, n = (int) (S.plist[q + 1] & PLIST_POS) - r;
-				uint32_t key[6];
-				jtk_build_key(sb + r, n, key);
-				const int32_t out = jtk_lookup_a(T, key, (uint32_t) n, jtk_hash6(key, (uint32_t) n));
-				if (out != JTK_RANK_MAX) {
-					rec[q] = out;
-					hits++;
-				} else {
-					miss = true;
-				}
-			}
-			const unsigned mm = __ballot_sync(0xFFFFFFFFu, miss);
-			if (miss) {
-				const int sl = nmiss + __popc(mm & ((1u << lane) - 1u));
-				if (sl < WMISS) wmiss[sl] = (uint16_t) q;
-				else hits += split_slow_piece<GENERAL>(a, sb, q, npieces, lt, tb);
-			}
-			nmiss += __popc(mm);
-		}
+		if (nkeys) drain_keys(nkeys);
 		/* the unusual pieces */
+		__syncwarp();
 		nodd = min(nodd, WODD);
 		for (int i = lane; i < nodd; i += 32) hits += split_slow_piece<GENERAL>(a, sb, wodd[i], npieces, lt, tb);
-		__syncwarp();
-		/* pass 3: the table misses: memo of this call, else the merge kernels' queues */
-		nmiss = min(nmiss, WMISS);
-		for (int i = lane; i < nmiss; i += 32) {
-			const int q = wmiss[i];
-			const int r = S.plist[q] & PLIST_POS;
-			hits += split_resolve_miss(a, sb, q, r, (int) (S.plist[q + 1] & PLIST_POS) - r, lt);
-		}
+		if (nmiss) drain_miss(nmiss);
 		hits = __reduce_add_sync(0xFFFFFFFFu, hits);
 		if (lane == 0 && hits) atomicAdd(&misc[M_HITS], (uint32_t) hits);
 		/* tile-local piece index of the documents that start in this tile (the end of the input included);

@@ -366,16 +366,23 @@ def run_ours(args):
     value = tokens_all * args.steps / (dev_ms_max * 1e-3)
     e2e_value = tokens_all * args.steps / e2e_s_max
 
-    # ---- roofline of the dominant kernel (this rank's launch)
+    # ---- roofline.  The headline fraction is the conservative one: the algorithmic bytes of the WHOLE step (bytes in + ids out + offsets,
+    # SURVEY.md section 8d) over the whole step's device time.  The dominant kernel is reported next to it with the part of those bytes it
+    # moves itself (it reads the input; the ids are written by the gather kernel) over its own CUDA-event time.  DRAM traffic: ncu
+    # dram__bytes_read + write summed over every kernel of one step / over the dominant kernel's launches (profiles/r2_step_traffic.json).
     peak, peak_src = measured_peaks()
     algo_bytes = nbytes + 4 * ntok + 16 * (ndocs + 1)
     kms = sum(kernel_ms) / len(kernel_ms)
-    achieved = algo_bytes / (kms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "tile_kernel_traffic.json")
+    step_ms = dev_ms / args.steps
+    achieved = algo_bytes / (step_ms * 1e-3) / 1e9
+    traffic, kernel_traffic = None, None
+    tpath = os.path.join(ROOT, "profiles", "r2_step_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("dram_bytes_per_step")  # ncu --set full capture, all launches of the kernel in one step
+            tj = json.load(f)
+        traffic = tj.get("dram_bytes_per_step")
+        kernel_traffic = tj.get("per_kernel", {}).get("jtk_split_lookup_kernel<0>", {}).get("dram_bytes")
+    kernel_algo = nbytes + 8 * (ndocs + 1)  # what the split+lookup kernel reads of the algorithmic bytes
 
     # ---- CPU baseline on a bounded sample of the same corpus (rank 0, N=1 only) + parity of that sample
     cpu = None
@@ -411,12 +418,20 @@ def run_ours(args):
         "input_gb_per_s": bytes_all * args.steps / (dev_ms_max * 1e-3) / 1e9,
         "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": int(nbytes + 8 * (ndocs + 1)),
                 "d2h_bytes_per_step": int(4 * ntok + 12 * (ndocs + 1)), "input_gb_per_s": bytes_all * args.steps / e2e_s_max / 1e9,
-                "ms_per_step": e2e_s_max / args.steps * 1e3, "api": "jtk_encode_batch (host buffers, pinned input)"},
+                "ms_per_step": e2e_s_max / args.steps * 1e3, "api": "jtk_encode_batch (host buffers, pinned input)",
+                # the link, not the kernels, bounds this number: PCIe rates measured on this pool (profiles/r1_pcie.txt: one GPU, both directions
+                # busy, 43-49 GB/s each; profiles/r2_pcie_8gpu.txt: eight GPUs, 92 GB/s device-to-host in total)
+                "link_floor_ms": max(nbytes / 46e9, 4 * ntok / 46e9) * 1e3 if world == 1 else max(bytes_all / 184e9, 4 * tokens_all / 92e9) * 1e3,
+                "link_floor_note": "max over directions of bytes / measured link rate while both directions are busy (1 GPU: 46 GB/s each; 8 GPUs: 184 GB/s in, 92 GB/s out in total)"},
         "gpu_launches": launches_all,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "jtk_split_lookup_kernel", "kernel_ms": kms, "launches_per_step": int(launches // args.steps),
-                     "frac_whole_step": algo_bytes / (dev_ms / args.steps * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": int(algo_bytes), "peak_source": peak_src,
-                     "frac_of_nominal_8000": achieved / 8000.0},
+                     "scope": "whole step: all %d kernel launches of one pass over the corpus" % int(launches // args.steps),
+                     "algorithmic_bytes_per_step": int(algo_bytes), "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
+                     "traffic_over_algorithmic": (traffic / algo_bytes) if traffic else None,
+                     "dominant_kernel": {"name": "jtk_split_lookup_kernel", "ms_per_step": kms, "share_of_step": kms / step_ms,
+                                         "algorithmic_bytes": int(kernel_algo), "achieved": kernel_algo / (kms * 1e-3) / 1e9,
+                                         "frac": kernel_algo / (kms * 1e-3) / 1e9 / peak, "traffic": kernel_traffic,
+                                         "bound_in_practice": "instruction issue (integer work per byte), not HBM: see profiles/r2_split_lookup_ncu_full.txt"}},
         "strong": strong,
         "decode": {"api": "jtk_decode_batch_device (ids of the step, resident in HBM -> bytes)", "ms_per_step": dec_ms, "tokens_per_s": ntok / (dec_ms * 1e-3),
                    "algorithmic_bytes": int(dec_algo), "achieved_gb_per_s": dec_algo / (dec_ms * 1e-3) / 1e9, "frac_of_hbm_peak": dec_algo / (dec_ms * 1e-3) / 1e9 / peak,

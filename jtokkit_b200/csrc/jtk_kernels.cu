@@ -1087,7 +1087,10 @@ __global__ void __launch_bounds__(1024, 1) jtk_tile_scan_kernel(const jtk_encode
 /* ---------------------------------------------------------------------------------------------
  * kernel 4: ids to their final position (one CTA per tile) + document token offsets
  * ------------------------------------------------------------------------------------------- */
-constexpr int GNT = 256;
+#ifndef JTK_GNT
+#define JTK_GNT 256
+#endif
+constexpr int GNT = JTK_GNT;
 constexpr int GIPT = 8;     /* consecutive pieces per thread and round: one block scan per 2048 pieces */
 constexpr int GCAP = 4096;  /* tokens staged in shared memory at a time for coalesced stores */
 
@@ -1103,7 +1106,7 @@ __device__ __forceinline__ int32_t rec_token_source(int32_t r) {
 	return REC_BASE + (int32_t) ((pl & REC_MEMO) ? (pl & ~15u) : ((pl >> 11) & 0x3FFFu));
 }
 
-__global__ void __launch_bounds__(GNT, 8) jtk_gather_kernel(const __grid_constant__ jtk_encode_args a) {
+__global__ void __launch_bounds__(GNT, 2048 / GNT) jtk_gather_kernel(const __grid_constant__ jtk_encode_args a) {
 	__shared__ __align__(16) int32_t s_tok[GCAP];          /* the round's tokens in order */
 	__shared__ uint16_t s_gpref[RECN / GIPT + 2];            /* tokens of the tile before each group of GIPT pieces */
 	__shared__ int s_w[GNT / 32];

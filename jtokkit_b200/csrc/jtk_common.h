@@ -160,6 +160,11 @@ struct jtk_tables {
 	const uint32_t *rx_ranges;
 	int32_t rx_ninst;
 	uint32_t rx_first[8]; /* bytes with which a match can begin (all ones when the pattern can match the empty string) */
+	/* the same program as a DFA over code-point classes (jtk_dfa.cpp), null when the pattern has no DFA form */
+	const uint16_t *rx_dfa_trans;
+	const uint16_t *rx_dfa_stage1;
+	const uint8_t *rx_dfa_stage2;
+	int32_t rx_dfa_nsym, rx_dfa_nstates, rx_dfa_start, rx_dfa_start_bol, rx_dfa_acc_lo;
 };
 
 /* ---- hashing (identical on host and device) ---------------------------------------------------- */

@@ -825,8 +825,26 @@ struct rx_atomic_or {
 	__device__ void operator()(uint32_t *w, uint32_t m) const { atomicOr(w, m); }
 };
 
+/* the DFA's hot entries staged in shared memory: the whole transition table when it fits (the usual case: tens of states x tens of
+ * classes), and the class of every code point below U+0100 */
+constexpr int RX_DFA_SMEM = 8192;
+__device__ __forceinline__ void rx_stage_dfa(jtk_rx_program &P, const jtk_tables &T, uint16_t *s_trans, uint8_t *s_ascii) {
+	if (!P.dfa_trans) return;
+	const int n = T.rx_dfa_nstates * T.rx_dfa_nsym;
+	if (n <= RX_DFA_SMEM) {
+		for (int i = threadIdx.x; i < n; i += blockDim.x) s_trans[i] = P.dfa_trans[i];
+		P.dfa_trans = s_trans;
+	}
+	for (int i = threadIdx.x; i < 256; i += blockDim.x) s_ascii[i] = P.dfa_ascii[i];
+	P.dfa_ascii = s_ascii;
+	__syncthreads();
+}
+
 __global__ void __launch_bounds__(128) jtk_general_slice_kernel(const __grid_constant__ jtk_encode_args a) {
-	const jtk_rx_program P = jtk_rx_program_of(a.T);
+	__shared__ uint16_t s_trans[RX_DFA_SMEM];
+	__shared__ uint8_t s_ascii[256];
+	jtk_rx_program P = jtk_rx_program_of(a.T);
+	rx_stage_dfa(P, a.T, s_trans, s_ascii);
 	const jtk_rx_split_buffers B = rx_buffers(a);
 	/* eight times the threads of the per-document pass on the same stack memory: what overflows a small stack is redone there */
 	jtk_rx_frame *st = static_cast<jtk_rx_frame *>(a.rx_stacks) + (size_t) (blockIdx.x * blockDim.x + threadIdx.x) * JTK_RX_STACK_SMALL;
@@ -839,7 +857,10 @@ __global__ void __launch_bounds__(128) jtk_general_slice_kernel(const __grid_con
 }
 
 __global__ void __launch_bounds__(128) jtk_general_stitch_kernel(const __grid_constant__ jtk_encode_args a) {
-	const jtk_rx_program P = jtk_rx_program_of(a.T);
+	__shared__ uint16_t s_trans[RX_DFA_SMEM];
+	__shared__ uint8_t s_ascii[256];
+	jtk_rx_program P = jtk_rx_program_of(a.T);
+	rx_stage_dfa(P, a.T, s_trans, s_ascii);
 	const jtk_rx_split_buffers B = rx_buffers(a);
 	jtk_rx_frame *st = static_cast<jtk_rx_frame *>(a.rx_stacks) + (size_t) (blockIdx.x * blockDim.x + threadIdx.x) * JTK_RX_STACK;
 	for (;;) {

@@ -1,6 +1,8 @@
 /*
- * General split patterns: a java.util.regex subset compiled at registration into a small backtracking program that the
- * GPU runs per 512-byte slice and stitches per document (jtk_general_slice / stitch / finish kernels, see below).  This is what makes
+ * General split patterns: a java.util.regex subset compiled at registration into a small program, determinised into a DFA
+ * over code-point classes where the pattern allows it (jtk_dfa.cpp: everything but '$', \\b and multi-character look-ahead) and
+ * run as a backtracking program otherwise; the GPU matches per 512-byte slice and stitches per document
+ * (jtk_general_slice / stitch / finish kernels, see below).  This is what makes
  * EncodingRegistry.registerGptBytePairEncoding (AbstractEncodingRegistry.java:63-66) accept patterns other than the two
  * predefined ones, e.g. Pattern.compile("test") in BaseEncodingRegistryTest.java:110-125.  The predefined patterns never
  * take this path (they compile to class tables + bit-parallel rules, jtk_device.cuh); it is the slow, general one.
@@ -64,6 +66,12 @@ struct jtk_rx_program {
 	const jtk_rx_set *sets;
 	const uint32_t *ranges;
 	const uint32_t *first; /* 256-bit map of the bytes a match can begin with */
+	/* the program as a DFA over code-point classes (jtk_dfa.cpp); null when the pattern has no DFA form: the backtracking program runs */
+	const uint16_t *dfa_trans;  /* state * dfa_nsym + symbol -> next state (0 = dead) | 0x8000: a match ends before the character read */
+	const uint16_t *dfa_stage1; /* code point >> 8 -> block */
+	const uint8_t *dfa_stage2;  /* block * 256 + (code point & 255) -> class */
+	const uint8_t *dfa_ascii;   /* the block of U+0000..U+00FF */
+	int32_t dfa_nsym, dfa_start, dfa_start_bol, dfa_acc_lo;
 };
 
 JTK_HD jtk_rx_program jtk_rx_program_of(const jtk_tables &T) {
@@ -73,6 +81,14 @@ JTK_HD jtk_rx_program jtk_rx_program_of(const jtk_tables &T) {
 	P.ninst = T.rx_ninst;
 	P.sets = static_cast<const jtk_rx_set *>(T.rx_sets);
 	P.ranges = T.rx_ranges;
+	P.dfa_trans = T.rx_dfa_trans;
+	P.dfa_stage1 = T.rx_dfa_stage1;
+	P.dfa_stage2 = T.rx_dfa_stage2;
+	P.dfa_ascii = T.rx_dfa_trans ? T.rx_dfa_stage2 + ((size_t) T.rx_dfa_stage1[0] << 8) : nullptr;
+	P.dfa_nsym = T.rx_dfa_nsym;
+	P.dfa_start = T.rx_dfa_start;
+	P.dfa_start_bol = T.rx_dfa_start_bol;
+	P.dfa_acc_lo = T.rx_dfa_acc_lo;
 	return P;
 }
 
@@ -337,6 +353,44 @@ JTK_HD int64_t jtk_rx_run(const jtk_rx_program &P, const jtk_tables &T, const ui
 	}
 }
 
+/* The same question answered by the DFA (jtk_dfa.cpp): end of the match that begins at `start`, or -1.  One table lookup per
+ * character; the last position at which the most preferred surviving thread matched is the answer (leftmost-first). */
+JTK_HD int64_t jtk_rx_dfa_run(const jtk_rx_program &P, const uint8_t *s, int64_t lo, int64_t n, int64_t start, bool *hit_end) {
+	uint32_t state = (uint32_t) (start == lo ? P.dfa_start_bol : P.dfa_start);
+	const uint32_t nsym = (uint32_t) P.dfa_nsym;
+	int64_t pos = start, last = -1;
+	for (;;) {
+		if (pos >= n) { /* end of the text: the symbol after the last class */
+			*hit_end = true;
+			if (P.dfa_trans[state * nsym + nsym - 1] & 0x8000u) last = pos;
+			return last;
+		}
+		if (pos + 4 > n) *hit_end = true;
+		int len = 1;
+		const uint32_t b0 = s[pos];
+		uint32_t sym;
+		if (b0 < 0x80) {
+			sym = P.dfa_ascii[b0];
+		} else {
+			const uint32_t cp = jtk_rx_decode(s, pos, n, &len);
+			sym = P.dfa_stage2[((uint32_t) P.dfa_stage1[cp >> 8] << 8) | (cp & 255u)];
+		}
+		const uint32_t t = P.dfa_trans[state * nsym + sym];
+		if (t & 0x8000u) last = pos;
+		state = t & 0x7FFFu;
+		if (state == 0) return last;
+		pos += len;
+		if (state >= (uint32_t) P.dfa_acc_lo) return pos;
+	}
+}
+
+/* match at `start`: the DFA when the pattern has one, else the backtracking program */
+JTK_HD int64_t jtk_rx_match_at(const jtk_rx_program &P, const jtk_tables &T, const uint8_t *s, int64_t lo, int64_t n, int64_t start, jtk_rx_frame *st, int cap,
+                               bool *overflow, bool *hit_end) {
+	if (P.dfa_trans) return jtk_rx_dfa_run(P, s, lo, n, start, hit_end);
+	return jtk_rx_run<0>(P, T, s, lo, n, start, 0, st, cap, overflow, hit_end);
+}
+
 /* Matcher.find() over one document s[lo..n): calls emit(match_start, match_end) for every match in order. */
 template <typename Emit>
 JTK_HD void jtk_rx_find_all(const jtk_rx_program &P, const jtk_tables &T, const uint8_t *s, int64_t lo, int64_t n, jtk_rx_frame *st, int cap, Emit emit, bool *overflow) {
@@ -352,7 +406,7 @@ JTK_HD void jtk_rx_find_all(const jtk_rx_program &P, const jtk_tables &T, const 
 		int64_t ms = -1, me = -1;
 		for (int64_t stp = from; stp <= n;) {
 			bool hit_end = false;
-			const int64_t r = jtk_rx_run<0>(P, T, s, lo, n, stp, 0, st, cap, overflow, &hit_end);
+			const int64_t r = jtk_rx_match_at(P, T, s, lo, n, stp, st, cap, overflow, &hit_end);
 			if (*overflow) return;
 			if (r >= 0) {
 				ms = stp;
@@ -419,7 +473,7 @@ JTK_HD int jtk_rx_find_next(const jtk_rx_program &P, const jtk_tables &T, const 
 			if (stp + 4 > view) hit_end = true; /* the last character of a truncated view may have been cut */
 		}
 		if (hit_end && view < n) return JTK_RX_GAVE_UP;
-		const int64_t r = jtk_rx_run<0>(P, T, s, lo, view, stp, 0, st, cap, overflow, &hit_end);
+		const int64_t r = jtk_rx_match_at(P, T, s, lo, view, stp, st, cap, overflow, &hit_end);
 		if (*overflow) return JTK_RX_NONE;
 		if (hit_end && view < n) return JTK_RX_GAVE_UP;
 		if (r >= 0) {

@@ -19,4 +19,17 @@ struct jtk_rx_compiled {
 /* pattern: UTF-8 java.util.regex source; flags: Pattern flag bits.  Returns JTK_OK or JTK_E_PATTERN_UNSUPPORTED with *err. */
 int jtk_rx_compile(const char *pattern, int flags, jtk_rx_compiled *out, std::string *err);
 
+/* The program determinised (jtk_dfa.cpp): transition table over code-point classes, leftmost-first semantics. */
+struct jtk_rx_dfa_host {
+	std::vector<uint16_t> trans; /* nstates x nsym: next state (0 = dead) | 0x8000 when a match ends BEFORE the character read */
+	int nstates = 0, nsym = 0;   /* symbols: the code point classes, then "end of text" */
+	int start = 0, start_bol = 0; /* start state inside a document / at its first byte ('^') */
+	int acc_lo = 0;              /* states >= acc_lo hold nothing but MATCH: the run ends there without another read */
+	std::vector<uint16_t> stage1; /* (code point >> 8) -> block, 8192 entries (four-byte sequences reach 0x1FFFFF) */
+	std::vector<uint8_t> stage2;  /* block * 256 + (code point & 255) -> class */
+};
+
+/* view: a jtk_tables with cp_stage1 / cp_stage2 set (what jtk_rx_in_set reads).  False with *why when the program has no DFA form. */
+bool jtk_rx_build_dfa(const jtk_rx_compiled &prog, const jtk_tables &view, jtk_rx_dfa_host *out, std::string *why);
+
 #endif

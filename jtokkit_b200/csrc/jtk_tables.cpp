@@ -217,9 +217,10 @@ int jtk_build_host_tables(const jtk_params *p, jtk_host_tables *t, std::string *
 	else t->pattern_kind = JTK_PAT_GENERAL;
 	if (p->pattern_flags & JTK_RE_CASE_INSENSITIVE)
 		t->pattern_kind = JTK_PAT_GENERAL; /* the rule kinds restate the patterns as EncodingFactory compiles them (case-sensitive) */
+	jtk_rx_compiled general_prog;
 	if (t->pattern_kind == JTK_PAT_GENERAL) {
 		/* any other pattern: compiled to a backtracking program (jtk_regex.h); constructs outside the subset fail here */
-		jtk_rx_compiled prog;
+		jtk_rx_compiled &prog = general_prog;
 		std::string rerr;
 		int rc = jtk_rx_compile(p->pattern, p->pattern_flags, &prog, &rerr);
 		if (rc != JTK_OK) {
@@ -242,6 +243,28 @@ int jtk_build_host_tables(const jtk_params *p, jtk_host_tables *t, std::string *
 	}
 	/* the general program reads the class table for \p{L}, \p{N} and the Unicode \s only: always White_Space there */
 	build_class_tables(t, t->pattern_kind == JTK_PAT_GENERAL ? (p->pattern_flags | JTK_RE_UNICODE_CHARACTER_CLASS) : p->pattern_flags);
+	if (t->pattern_kind == JTK_PAT_GENERAL) {
+		/* the program determinised (leftmost-first DFA over code-point classes) where the pattern allows it; JTK_RX_DFA=0 keeps the
+		 * backtracking program (development switch: both give the same pieces) */
+		const char *sw = getenv("JTK_RX_DFA");
+		jtk_rx_dfa_host dfa;
+		jtk_tables v;
+		memset(&v, 0, sizeof(v));
+		v.cp_stage1 = t->cp_stage1.data();
+		v.cp_stage2 = t->cp_stage2.data();
+		if (sw && sw[0] == '0') {
+			t->rx_dfa_why = "switched off (JTK_RX_DFA=0)";
+		} else if (jtk_rx_build_dfa(general_prog, v, &dfa, &t->rx_dfa_why)) {
+			t->rx_dfa_trans = std::move(dfa.trans);
+			t->rx_dfa_stage1 = std::move(dfa.stage1);
+			t->rx_dfa_stage2 = std::move(dfa.stage2);
+			t->rx_dfa_nsym = dfa.nsym;
+			t->rx_dfa_nstates = dfa.nstates;
+			t->rx_dfa_start = dfa.start;
+			t->rx_dfa_start_bol = dfa.start_bol;
+			t->rx_dfa_acc_lo = dfa.acc_lo;
+		}
+	}
 
 	/* ---- vocabulary: Map.put semantics (a later duplicate key replaces the value), TokenEncoder.java:41-44 ---- */
 	std::unordered_map<std::string, int32_t> index_of; /* key bytes -> token index */
@@ -526,5 +549,13 @@ jtk_tables jtk_host_view(const jtk_host_tables &h) {
 	v.rx_ranges = h.rx_ranges.data();
 	v.rx_ninst = h.rx_ninst;
 	memcpy(v.rx_first, h.rx_first, sizeof(v.rx_first));
+	v.rx_dfa_trans = h.rx_dfa_trans.empty() ? nullptr : h.rx_dfa_trans.data();
+	v.rx_dfa_stage1 = h.rx_dfa_stage1.data();
+	v.rx_dfa_stage2 = h.rx_dfa_stage2.data();
+	v.rx_dfa_nsym = h.rx_dfa_nsym;
+	v.rx_dfa_nstates = h.rx_dfa_nstates;
+	v.rx_dfa_start = h.rx_dfa_start;
+	v.rx_dfa_start_bol = h.rx_dfa_start_bol;
+	v.rx_dfa_acc_lo = h.rx_dfa_acc_lo;
 	return v;
 }

@@ -44,7 +44,7 @@ def lib():
         L.emu_stats.argtypes = [C.c_void_p, C.c_void_p]
         L.emu_tile.restype = C.c_int
         L.emu_general_split.restype = C.c_int
-        L.emu_general_split.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
+        L.emu_general_split.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.emu_pattern_kind.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
@@ -81,13 +81,22 @@ class EmuEncoding:
     def pattern_kind(self):
         return lib().emu_pattern_kind(self._h)
 
-    def general_split(self, utf8, doc_off, stack_cap=1024):
+    def dfa_info(self):
+        """(states, symbols, reason) of the general pattern's DFA; states == 0 when the pattern keeps the backtracking program."""
+        nsym = C.c_int(0)
+        why = C.create_string_buffer(256)
+        lib().emu_dfa_info.restype = C.c_int
+        lib().emu_dfa_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        n = lib().emu_dfa_info(self._h, C.byref(nsym), why, 256)
+        return n, nsym.value, why.value.decode()
+
+    def general_split(self, utf8, doc_off, stack_cap=1024, no_dfa=False):
         """(start flags, skip flags) per byte from the general-pattern program; raises on backtrack-stack overflow."""
         utf8 = np.ascontiguousarray(utf8, dtype=np.uint8)
         doc_off = np.ascontiguousarray(doc_off, dtype=np.int64)
         start = np.zeros(max(1, utf8.size), dtype=np.uint8)
         skip = np.zeros(max(1, utf8.size), dtype=np.uint8)
-        rc = lib().emu_general_split(self._h, _p(utf8), _p(doc_off), doc_off.size - 1, _p(start), _p(skip), stack_cap)
+        rc = lib().emu_general_split(self._h, _p(utf8), _p(doc_off), doc_off.size - 1, _p(start), _p(skip), stack_cap, 1 if no_dfa else 0)
         if rc != 0:
             raise OverflowError("general split: rc %d" % rc)
         return start[:utf8.size], skip[:utf8.size]

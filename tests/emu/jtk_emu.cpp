@@ -196,9 +196,10 @@ int64_t emu_run(const emu_encoding *e, const uint8_t *bytes, int64_t total, cons
 /* General split patterns: runs the three passes of the sliced Matcher.find() (jtk_regex.h) the way the kernels do, with
  * JTK_RX_SLICE-byte slices (tests/emu/Makefile makes them tiny).  start[g] = 1 at piece starts, skip[g] = 1 where the piece
  * starting at g is a gap.  Returns 0, 1 on stack overflow, -1 if the encoding has no general program. */
-extern "C" int emu_general_split(const emu_encoding *e, const uint8_t *bytes, const int64_t *doc_off, int64_t ndocs, uint8_t *start, uint8_t *skip, int stack_cap) {
+extern "C" int emu_general_split(const emu_encoding *e, const uint8_t *bytes, const int64_t *doc_off, int64_t ndocs, uint8_t *start, uint8_t *skip, int stack_cap, int no_dfa) {
 	if (e->view.pattern_kind != JTK_PAT_GENERAL) return -1;
-	const jtk_rx_program P = jtk_rx_program_of(e->view);
+	jtk_rx_program P = jtk_rx_program_of(e->view);
+	if (no_dfa) P.dfa_trans = nullptr; /* the backtracking program even where the pattern has a DFA */
 	const int64_t total = doc_off[ndocs];
 	const int64_t nslices = (total + JTK_RX_SLICE - 1) / JTK_RX_SLICE, nwords = total / 32 + 2;
 	std::vector<uint32_t> bits((size_t) (5 * nwords), 0);
@@ -234,3 +235,10 @@ extern "C" int emu_general_split(const emu_encoding *e, const uint8_t *bytes, co
 }
 
 extern "C" int emu_pattern_kind(const emu_encoding *e) { return e->view.pattern_kind; }
+
+/* DFA of a general pattern: states (0 = the pattern has no DFA form), symbols; why not, if not */
+extern "C" int emu_dfa_info(const emu_encoding *e, int *nsym, char *why, int why_cap) {
+	*nsym = e->view.rx_dfa_nsym;
+	snprintf(why, (size_t) why_cap, "%s", e->host.rx_dfa_why.c_str());
+	return e->view.rx_dfa_trans ? e->view.rx_dfa_nstates : 0;
+}

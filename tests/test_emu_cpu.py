@@ -136,20 +136,60 @@ def test_general_pattern_program_matches_oracle_matcher(index):
         blob = b"".join(docs)
         off = np.zeros(len(docs) + 1, dtype=np.int64)
         off[1:] = np.cumsum([len(x) for x in docs])
-        start, skip = e.general_split(np.frombuffer(blob, dtype=np.uint8), off)
         exp_start, exp_skip = expected_piece_bits(o, docs, off, len(blob))
-        assert np.array_equal(start, exp_start) and np.array_equal(skip, exp_skip), (pat, docs)
+        # the DFA where the pattern has one (the default), and the backtracking program: both must reproduce Matcher.find()
+        for no_dfa in ([False, True] if e.dfa_info()[0] else [True]):
+            start, skip = e.general_split(np.frombuffer(blob, dtype=np.uint8), off, no_dfa=no_dfa)
+            assert np.array_equal(start, exp_start) and np.array_equal(skip, exp_skip), (pat, docs, "vm" if no_dfa else "dfa")
 
 
 def test_general_pattern_stack_overflow_is_reported():
-    """A group loop keeps one frame per iteration: a long run exhausts a small stack and the call says so instead of mis-splitting."""
+    """The backtracking program keeps one frame per iteration of a group loop: a long run exhausts a small stack and the call says so
+    instead of mis-splitting.  The DFA of the same pattern has no stack (nothing to overflow) and gives the oracle's pieces."""
     import emu
-    e = emu.EmuEncoding("g", r"(?:a|b)+c|.", 0, {b"a": 0}, {})
-    text = np.frombuffer(b"ab" * 400, dtype=np.uint8)
+    from oracle import jo
+    jo.build()
+    pat = r"(?:a|b)+c|."
+    e = emu.EmuEncoding("g", pat, 0, {b"a": 0}, {})
+    assert e.dfa_info()[0] > 0
+    doc = b"ab" * 400
+    text = np.frombuffer(doc, dtype=np.uint8)
     off = np.array([0, text.size], dtype=np.int64)
     with pytest.raises(OverflowError):
-        e.general_split(text, off, stack_cap=64)
-    e.general_split(text, off, stack_cap=4096)
+        e.general_split(text, off, stack_cap=64, no_dfa=True)
+    e.general_split(text, off, stack_cap=4096, no_dfa=True)
+    start, skip = e.general_split(text, off, stack_cap=64)
+    exp_start, exp_skip = expected_piece_bits(jo.OracleEncoding("g", pat, 0, {b"a": 0}, {}), [doc], off, len(doc))
+    assert np.array_equal(start, exp_start) and np.array_equal(skip, exp_skip)
+    # a pattern without a DFA form ('$') keeps the program and its stack
+    e2 = emu.EmuEncoding("g", r"(?:a|b)+c$|.", 0, {b"a": 0}, {})
+    assert e2.dfa_info()[0] == 0 and "$" in e2.dfa_info()[2]
+    with pytest.raises(OverflowError):
+        e2.general_split(text, off, stack_cap=64)
+
+
+def test_dfa_is_built_for_the_predefined_pattern_strings_as_general_patterns():
+    """The two predefined split patterns (possessive quantifiers, \\s+(?!\\S), (?i:...)) have a DFA form when they are registered
+    with a flag that takes them off the rule path: small tables, and the same pieces as the oracle's matcher (checked above for
+    look-alikes; here for the exact strings)."""
+    import emu
+    from oracle import jo
+    jo.build()
+    rng = random.Random(77)
+    for name in ["cl100k_base", "r50k_base"]:
+        pat = jo.BUILTIN[name][0]
+        e = emu.EmuEncoding(name + "_ci", pat, 0x102, {b"a": 0}, {})
+        nstates, nsym, why = e.dfa_info()
+        assert 0 < nstates <= 64 and nsym <= 32, (nstates, nsym, why)
+        o = jo.OracleEncoding(name + "_ci", pat, 0x102, {b"a": 0}, {})
+        for it in range(60):
+            docs = random_docs(rng, rng.randint(1, 4), ascii_only=(it % 3 == 1), utf8_letters=(it % 3 == 2))
+            blob = b"".join(docs)
+            off = np.zeros(len(docs) + 1, dtype=np.int64)
+            off[1:] = np.cumsum([len(x) for x in docs])
+            start, skip = e.general_split(np.frombuffer(blob, dtype=np.uint8), off)
+            exp_start, exp_skip = expected_piece_bits(o, docs, off, len(blob))
+            assert np.array_equal(start, exp_start) and np.array_equal(skip, exp_skip), (name, docs)
 
 
 def test_predefined_patterns_do_not_take_the_general_path():

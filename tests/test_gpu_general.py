@@ -78,10 +78,15 @@ def test_general_pattern_special_tokens_and_split_flags(cl100k_ranks):
 
 
 def test_general_pattern_stack_overflow_flags_the_document(cl100k_ranks):
-    g, _ = make_pair("general_deep", r"(?:a|b)+c|.", 0, cl100k_ranks)
+    """A pattern without a DFA form ('$') runs as a backtracking program: a group loop over a long run exhausts its stack and the
+    document is flagged (the JVM throws StackOverflowError).  The same loop as a DFA has no stack and simply matches."""
+    g, _ = make_pair("general_deep", r"(?:a|b)+c$|.", 0, cl100k_ranks)
     with pytest.raises(RecursionError):
         g.encode_ordinary("ab" * 5000)
     assert g.encode_ordinary("abc") == g.encode_ordinary("abc")
+    g2, o2 = make_pair("general_deep_dfa", r"(?:a|b)+c|.", 0, cl100k_ranks)
+    for text in ["ab" * 5000, "ab" * 3000 + "c" + "ba" * 10, "abc"]:
+        assert g2.encode_ordinary(text) == o2.encode_ordinary(text.encode())
 
 
 def test_case_insensitive_predefined_pattern(cl100k_ranks):

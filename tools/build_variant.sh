@@ -4,4 +4,4 @@
 set -e
 name=$1; shift
 cd "$(dirname "$0")/../jtokkit_b200/csrc"
-nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC "$@" -shared -o ../libjtokkit_b200_$name.so jtk_kernels.cu jtk_capi.cu jtk_tables.cpp jtk_regex.cpp -lpthread
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC "$@" -shared -o ../libjtokkit_b200_$name.so jtk_kernels.cu jtk_capi.cu jtk_tables.cpp jtk_regex.cpp jtk_dfa.cpp -lpthread

@@ -145,11 +145,15 @@ public final class CudaBytePairEncoding implements Encoding, AutoCloseable {
 			// String.getBytes(UTF_8), exactly as ImmutableByteArray.from (ImmutableByteArray.java:16-19): lone surrogates become '?'.
 			// Never GetStringUTFChars / modified UTF-8.
 			final byte[][] utf8 = new byte[texts.size()][];
-			long total = 0;
-			for (int d = 0; d < utf8.length; d++) {
-				utf8[d] = texts.get(d) == null ? new byte[0] : texts.get(d).getBytes(StandardCharsets.UTF_8);
-				total += utf8[d].length;
+			final boolean big = utf8.length >= 4096; // transcoding and flattening are per-document work: spread them over the common pool
+			if (big) {
+				java.util.stream.IntStream.range(0, utf8.length).parallel()
+						.forEach(d -> utf8[d] = texts.get(d) == null ? new byte[0] : texts.get(d).getBytes(StandardCharsets.UTF_8));
+			} else {
+				for (int d = 0; d < utf8.length; d++) utf8[d] = texts.get(d) == null ? new byte[0] : texts.get(d).getBytes(StandardCharsets.UTF_8);
 			}
+			long total = 0;
+			for (int d = 0; d < utf8.length; d++) total += utf8[d].length;
 			// Large batches are flattened into PINNED memory (jtk_host_alloc): the copy-in then runs at PCIe speed (~55 GB/s measured);
 			// ordinary (pageable) native memory is copied in by the driver at ~8 GB/s.  Small batches stay in the arena.
 			final boolean pinned = total >= (1L << 20);
@@ -157,10 +161,17 @@ public final class CudaBytePairEncoding implements Encoding, AutoCloseable {
 			final MemorySegment bytes = pinned ? pinnedBase.reinterpret(total) : arena.allocate(Math.max(total, 1), 16);
 			final MemorySegment off = arena.allocate(JAVA_LONG, utf8.length + 1L);
 			long pos = 0;
+			final long[] starts = new long[utf8.length];
 			for (int d = 0; d < utf8.length; d++) {
 				off.setAtIndex(JAVA_LONG, d, pos);
-				MemorySegment.copy(utf8[d], 0, bytes, JAVA_BYTE, pos, utf8[d].length);
+				starts[d] = pos;
 				pos += utf8[d].length;
+			}
+			if (big && pinned) { // the pinned segment has the global scope (any thread may write it); arena memory is confined to this thread
+				java.util.stream.IntStream.range(0, utf8.length).parallel()
+						.forEach(d -> MemorySegment.copy(utf8[d], 0, bytes, JAVA_BYTE, starts[d], utf8[d].length));
+			} else {
+				for (int d = 0; d < utf8.length; d++) MemorySegment.copy(utf8[d], 0, bytes, JAVA_BYTE, starts[d], utf8[d].length);
 			}
 			off.setAtIndex(JAVA_LONG, utf8.length, pos);
 			final MemorySegment out = arena.allocate(ADDRESS);

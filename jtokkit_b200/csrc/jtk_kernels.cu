@@ -848,11 +848,18 @@ __global__ void __launch_bounds__(128) jtk_general_slice_kernel(const __grid_con
 	const jtk_rx_split_buffers B = rx_buffers(a);
 	/* eight times the threads of the per-document pass on the same stack memory: what overflows a small stack is redone there */
 	jtk_rx_frame *st = static_cast<jtk_rx_frame *>(a.rx_stacks) + (size_t) (blockIdx.x * blockDim.x + threadIdx.x) * JTK_RX_STACK_SMALL;
+	/* a warp takes 32 consecutive slices at a time: its lanes start their (equally long) slices together and stay in step in the matching
+	 * loop instead of drifting apart over tickets taken one by one; neighbouring lanes write neighbouring words of the bit arrays */
+	const int lane = threadIdx.x & 31;
 	for (;;) {
-		const int64_t slice = (int64_t) atomicAdd(&a.hdr->rx_ticket, 1u);
-		if (slice >= a.rx_slices) break;
+		unsigned first = 0;
+		if (lane == 0) first = atomicAdd(&a.hdr->rx_ticket, 32u);
+		first = __shfl_sync(0xFFFFFFFFu, first, 0);
+		if ((int64_t) first >= a.rx_slices) break;
+		const int64_t slice = (int64_t) first + lane;
 		int64_t bad = -1;
-		jtk_rx_slice_pass(P, a.T, a.bytes, a.total, a.doc_off, a.ndocs, slice, B, st, JTK_RX_STACK_SMALL, &bad, rx_atomic_or());
+		if (slice < a.rx_slices) jtk_rx_slice_pass(P, a.T, a.bytes, a.total, a.doc_off, a.ndocs, slice, B, st, JTK_RX_STACK_SMALL, &bad, rx_atomic_or());
+		__syncwarp();
 	}
 }
 
@@ -1877,7 +1884,7 @@ __device__ __forceinline__ bool decode_len(const jtk_tables &T, int32_t id, uint
 }
 
 #ifndef JTK_DECODE_CTAS
-#define JTK_DECODE_CTAS 4 /* resident CTAs per SM the single-pass decode kernel is compiled for (register budget) */
+#define JTK_DECODE_CTAS 6 /* resident CTAs per SM the single-pass decode kernel is compiled for (register budget: 42) */
 #endif
 constexpr int DNT = 256;           /* threads per CTA of the decode kernels */
 #ifndef JTK_DECODE_DPT
@@ -1885,6 +1892,32 @@ constexpr int DNT = 256;           /* threads per CTA of the decode kernels */
 #endif
 constexpr int DPT = JTK_DECODE_DPT; /* consecutive tokens per thread */
 constexpr int DTILE = DNT * DPT;   /* tokens per tile */
+/* how much of a token's 16-byte table entry stays in registers between the length pass and the copy (JTK_DECODE_KEEP = 4: the length
+ * word only, every token is looked up again; 8: + the first four bytes; 16: the whole entry, tokens of up to twelve bytes need no second
+ * read): registers (occupancy) against gathers through L1 */
+#ifndef JTK_DECODE_KEEP
+#define JTK_DECODE_KEEP 4 /* measured on B200, 404 M tokens: 4 at six CTAs per SM 3.90 ms, 8 at eight 4.38 ms, 16 at four 4.26 ms */
+#endif
+constexpr int DKEEP = JTK_DECODE_KEEP;
+#if JTK_DECODE_KEEP == 16
+typedef uint4 dec_ent;
+__device__ __forceinline__ dec_ent dec_ent_load(const uint4 *p) { return __ldg(p); }
+__device__ __forceinline__ dec_ent dec_ent_none(uint32_t x) { return make_uint4(x, 0u, 0u, 0u); }
+__device__ __forceinline__ void dec_ent_bytes(const dec_ent &e, uint32_t *f0, uint32_t *f1, uint32_t *f2) { *f0 = e.y, *f1 = e.z, *f2 = e.w; }
+#elif JTK_DECODE_KEEP == 8
+typedef uint2 dec_ent;
+__device__ __forceinline__ dec_ent dec_ent_load(const uint4 *p) { return __ldg(reinterpret_cast<const uint2 *>(p)); }
+__device__ __forceinline__ dec_ent dec_ent_none(uint32_t x) { return make_uint2(x, 0u); }
+__device__ __forceinline__ void dec_ent_bytes(const dec_ent &e, uint32_t *f0, uint32_t *f1, uint32_t *f2) { *f0 = e.y, *f1 = 0, *f2 = 0; }
+#else
+struct dec_ent {
+	uint32_t x;
+};
+__device__ __forceinline__ dec_ent dec_ent_load(const uint4 *p) { return dec_ent{__ldg(reinterpret_cast<const uint32_t *>(p))}; }
+__device__ __forceinline__ dec_ent dec_ent_none(uint32_t x) { return dec_ent{x}; }
+__device__ __forceinline__ void dec_ent_bytes(const dec_ent &, uint32_t *f0, uint32_t *f1, uint32_t *f2) { *f0 = *f1 = *f2 = 0; }
+#endif
+constexpr int SPAD = 16;           /* front pad of the staging window (a flushed 16-byte group may begin up to 15 bytes before the window) */
 constexpr int DWIN = 12 * 1024;    /* bytes of a tile staged in shared memory at a time (a tile of typical text is ~5.5 KB) */
 
 /* pass 1: bytes per tile of DTILE tokens; unknown ids are reported per document (the smallest position) */
@@ -2011,13 +2044,13 @@ __global__ void jtk_scan_add_kernel(int64_t *data, int64_t n, const int64_t *blo
 
 /* Single pass: tiles of DTILE tokens are taken by ticket (so every predecessor of a tile has started), the tile's byte count is
  * published, the exclusive prefix over all earlier tiles comes from a decoupled look-back over the published words (a warp
- * inspects 32 predecessors at a time), then the token bytes are copied into a shared-memory window that has the same 16-byte
- * misalignment as its place in the output and flushed with 16-byte stores.  Algorithmic bytes: 4 per token read, the bytes written.
+ * inspects 32 predecessors at a time), while the token bytes are already being copied into a shared-memory window at their tile-relative
+ * position; the flush shifts them to the output's 16-byte grid and writes 16-byte stores.  Algorithmic bytes: 4 per token read, the bytes written.
  * status word of a tile: bits 62..63 = 1 aggregate (bytes of the tile) / 2 inclusive prefix, bits 0..61 the value. */
 constexpr unsigned long long DST_AGG = 1ull << 62, DST_PREFIX = 2ull << 62, DST_MASK = (1ull << 62) - 1;
 
 __global__ void __launch_bounds__(DNT, JTK_DECODE_CTAS) jtk_decode_fused_kernel(const __grid_constant__ jtk_decode_args a) {
-	__shared__ __align__(16) uint8_t s_out[DWIN + 32];
+	__shared__ __align__(16) uint8_t s_out[SPAD + DWIN + 32];
 	__shared__ int s_pref[DNT + 1];
 	__shared__ int s_w[DNT / 32];
 	__shared__ long long s_base;
@@ -2039,13 +2072,26 @@ __global__ void __launch_bounds__(DNT, JTK_DECODE_CTAS) jtk_decode_fused_kernel(
 #pragma unroll
 		for (int i = 0; i < DPT; i++) ids[i] = t0 + i < a.nids ? a.ids[t0 + i] : 0;
 	}
-	uint8_t len[DPT]; /* (the bytes themselves are fetched when they are copied: the same table entries again, L1 hits) */
+	/* ONE table read per token: with the direct table the 16-byte entry (length, offset, first twelve bytes) stays in registers across
+	 * the scan; without it (ids that are not small non-negative numbers) only the length is kept and the bytes are looked up again */
+	const bool direct = a.T.dec_direct != nullptr;
+	dec_ent ent[DPT];
 	int sum = 0;
 #pragma unroll
 	for (int i = 0; i < DPT; i++) {
 		uint32_t l = 0;
-		if (t0 + i < a.nids && !decode_len(a.T, ids[i], &l)) {
-			l = 0;
+		bool known;
+		if (direct) {
+			const bool in = t0 + i < a.nids;
+			ent[i] = (in && (uint32_t) ids[i] < a.T.dec_direct_size) ? dec_ent_load(a.T.dec_direct + ids[i]) : dec_ent_none(0xFFFFFFFFu);
+			known = !in || ent[i].x != 0xFFFFFFFFu;
+			l = known && in ? (ent[i].x & 0xFFu) : 0u;
+		} else {
+			known = !(t0 + i < a.nids) || decode_len(a.T, ids[i], &l);
+			if (!known) l = 0;
+			ent[i] = dec_ent_none(0u);
+		}
+		if (!known) {
 			/* unknown id: flag its document (the last d with tok_off[d] <= j) and remember the first one */
 			const int64_t j = t0 + i;
 			int64_t lo = 0, hi = a.ndocs - 1;
@@ -2057,7 +2103,7 @@ __global__ void __launch_bounds__(DNT, JTK_DECODE_CTAS) jtk_decode_fused_kernel(
 			atomicMin(a.bad_pos + lo, (unsigned long long) j);
 			atomicOr(a.doc_status + lo, JTK_DOC_UNKNOWN_ID);
 		}
-		len[i] = (uint8_t) l;
+		ent[i].x = (ent[i].x & ~0xFFu) | l; /* the length in the low byte either way */
 		sum += (int) l;
 	}
 	int x = sum;
@@ -2113,23 +2159,24 @@ __global__ void __launch_bounds__(DNT, JTK_DECODE_CTAS) jtk_decode_fused_kernel(
 			if (tile == a.ntiles - 1) *a.total_out = excl + total;
 		}
 	}
-	__syncthreads();
-	const int64_t base = s_base;
-	const bool fits = base + total <= a.out_capacity;
-	if (!fits && tid == 0) *a.overflow = 1;
-	for (int w0 = 0; fits && w0 < total; w0 += DWIN) {
-		const int mis = (int) ((base + w0) & 15);
+	/* ---- the token bytes go to the staging window at their TILE-RELATIVE position right away: this needs no global prefix, so
+	 * the other warps copy while warp 0 looks back (and warp 0 copies its own tokens afterwards); only the flush waits for `base`.
+	 * Staging byte SPAD + k <-> output byte base + w0 + k. ---- */
+	long long base = 0;
+	bool fits = true;
+	for (int w0 = 0; w0 < total; w0 += DWIN) {
 		const int wn = min(DWIN, total - w0); /* bytes of this window */
 		if (w0) __syncthreads();
 		int pos = mine - w0;
 #pragma unroll
 		for (int i = 0; i < DPT; i++) {
-			const int l = (int) len[i];
+			const int l = (int) (ent[i].x & 0xFFu);
 			if (l && pos + l > 0 && pos < wn) {
-				uint32_t o2, l2, f0, f1, f2;
-				decode_entry(a.T, ids[i], &o2, &l2, &f0, &f1, &f2);
+				uint32_t o2 = ent[i].x >> 8, l2, f0 = 0, f1 = 0, f2 = 0;
+				if (direct && l <= DKEEP - 4) dec_ent_bytes(ent[i], &f0, &f1, &f2); /* the bytes came with the length */
+				else decode_entry(a.T, ids[i], &o2, &l2, &f0, &f1, &f2);
 				if (l <= 12 && pos >= 0 && pos + l <= wn) { /* the table entry holds the bytes: straight-line predicated byte stores */
-					uint8_t *d = s_out + mis + pos;
+					uint8_t *d = s_out + SPAD + pos;
 					d[0] = (uint8_t) f0;
 					if (l > 1) d[1] = (uint8_t) (f0 >> 8);
 					if (l > 2) d[2] = (uint8_t) (f0 >> 16);
@@ -2149,23 +2196,44 @@ __global__ void __launch_bounds__(DNT, JTK_DECODE_CTAS) jtk_decode_fused_kernel(
 				} else {
 					const uint8_t *src = a.T.dec_bytes + o2;
 					const int k0 = pos < 0 ? -pos : 0, k1 = min(l, wn - pos);
-					for (int k = k0; k < k1; k++) s_out[mis + pos + k] = src[k];
+					for (int k = k0; k < k1; k++) s_out[SPAD + pos + k] = src[k];
 				}
 			}
 			pos += l;
 		}
-		__syncthreads();
-		/* flush: staging byte mis + k <-> output byte base + w0 + k; whole 16-byte groups with one store, the ragged ends bytewise */
+		__syncthreads(); /* the window is complete; in the first round this also publishes s_base */
+		if (w0 == 0) {
+			base = s_base;
+			fits = base + total <= a.out_capacity;
+			if (!fits && tid == 0) *a.overflow = 1;
+		}
+		if (!fits) break;
+		/* flush: whole 16-byte groups of the OUTPUT with one store each - the staged bytes of a group start at any byte offset, so a
+		 * group is five aligned shared-memory words funnel-shifted into four; the ragged ends bytewise */
+		const int mis = (int) ((base + w0) & 15);
 		uint8_t *const gout = a.out + (base + w0 - mis);
 		const int nchunk = (mis + wn + 15) >> 4;
+		const int sh = ((SPAD - mis) & 3) * 8;
 		for (int c = tid; c < nchunk; c += DNT) {
 			const int lo = c == 0 ? mis : 0, hi = min(16, mis + wn - 16 * c);
+			const int sa = SPAD + 16 * c - mis; /* staging index of the group's first byte (>= 1) */
 			if (lo == 0 && hi == 16) {
-				*reinterpret_cast<uint4 *>(gout + 16 * c) = *reinterpret_cast<const uint4 *>(s_out + 16 * c);
+				const uint32_t *wp = reinterpret_cast<const uint32_t *>(s_out) + (sa >> 2);
+				const uint32_t x0 = wp[0], x1 = wp[1], x2 = wp[2], x3 = wp[3], x4 = wp[4];
+				uint4 v;
+				v.x = __funnelshift_r(x0, x1, sh);
+				v.y = __funnelshift_r(x1, x2, sh);
+				v.z = __funnelshift_r(x2, x3, sh);
+				v.w = __funnelshift_r(x3, x4, sh);
+				*reinterpret_cast<uint4 *>(gout + 16 * c) = v;
 			} else {
-				for (int k = lo; k < hi; k++) gout[16 * c + k] = s_out[16 * c + k];
+				for (int k = lo; k < hi; k++) gout[16 * c + k] = s_out[sa + k];
 			}
 		}
+	}
+	if (total == 0) { /* (no window round ran: the barrier that publishes s_base) */
+		__syncthreads();
+		base = s_base;
 	}
 	/* documents whose first token lies in this tile (the last tile also takes the documents that start at the very end) */
 	const bool last = tile == a.ntiles - 1;

@@ -491,6 +491,130 @@ JTK_HD int jtk_rx_find_next(const jtk_rx_program &P, const jtk_tables &T, const 
 
 JTK_HD bool jtk_rx_bit(const uint32_t *b, int64_t g) { return (b[g >> 5] >> (g & 31)) & 1u; }
 
+/* Four bytes of s starting at byte position pos (little endian; bytes at or beyond hi read as anything), through a two-word window
+ * over the aligned words of s: sequential matching loads each word once instead of once per byte.  s is 4-byte aligned on the device
+ * (the inputs of the kernels are 16-byte aligned); an aligned word that holds a valid byte lies inside the allocation. */
+struct jtk_rx_window {
+	int64_t idx; /* index of the aligned word in w0; w1 is the next one */
+	uint32_t w0, w1;
+};
+JTK_HD uint32_t jtk_rx_fetch4(const uint8_t *s, int64_t pos, int64_t hi, jtk_rx_window &win) {
+#if defined(__CUDA_ARCH__)
+	const int64_t idx = pos >> 2;
+	if (idx != win.idx) {
+		const uint32_t *wp = reinterpret_cast<const uint32_t *>(s) + idx;
+		const uint32_t a = idx == win.idx + 1 ? win.w1 : wp[0];
+		win.w1 = 4 * (idx + 1) < hi ? wp[1] : 0u;
+		win.w0 = a;
+		win.idx = idx;
+	}
+	return __funnelshift_r(win.w0, win.w1, (uint32_t) (pos & 3) * 8u);
+#else
+	uint32_t x = 0;
+	for (int k = 0; k < 4 && pos + k < hi; k++) x |= (uint32_t) s[pos + k] << (8 * k);
+	return x;
+#endif
+}
+/* jtk_rx_decode on the four bytes x = s[pos .. pos + 4) with avail = n - pos bytes of text left (>= 1): the same code point and length */
+JTK_HD uint32_t jtk_rx_decode_word(uint32_t x, int64_t avail, int *len) {
+	const uint32_t b0 = x & 0xFFu;
+	*len = 1;
+	if (b0 < 0x80) return b0;
+	if (b0 < 0xC0 || b0 >= 0xF8) return 0xFFFD;
+	const int k = b0 < 0xE0 ? 2 : b0 < 0xF0 ? 3 : 4;
+	if (k > avail) return 0xFFFD;
+	const int sh = 8 * (4 - k);
+	if ((x & ((0xC0C0C000u << sh) >> sh)) != ((0x80808000u << sh) >> sh)) return 0xFFFD; /* bytes 1 .. k-1 must be 10xxxxxx */
+	uint32_t cp = b0 & (0xFFu >> (k + 1));
+	cp = (cp << 6) | ((x >> 8) & 0x3Fu);
+	if (k > 2) cp = (cp << 6) | ((x >> 16) & 0x3Fu);
+	if (k > 3) cp = (cp << 6) | ((x >> 24) & 0x3Fu);
+	*len = k;
+	return cp;
+}
+
+/* jtk_rx_chain (below) for a pattern with a DFA, as ONE flat loop: every iteration reads one character and takes one transition,
+ * whatever the lane is in the middle of - a match attempt, the step over a position where nothing matches, the look-ahead past the
+ * end of a match - so the lanes of a warp stay converged; what happens when an attempt ends (record the match, move `from`, give up)
+ * is a short predicated tail.  A position whose first byte cannot begin a match costs one iteration (the start state dies on it), so
+ * the first-byte filter of the program search is not needed.  Same results as jtk_rx_chain with jtk_rx_dfa_run, call by call. */
+template <typename Or>
+JTK_HD int64_t jtk_rx_chain_dfa(const jtk_rx_program &P, const uint8_t *s, int64_t lo, int64_t hi, int64_t from, int64_t end_run, int64_t limit, uint32_t *ms_bits,
+                                uint32_t *me_bits, uint32_t *from_bits, const uint32_t *stop_bits, int64_t *cross_ms, int64_t *cross_me, bool *joined, Or bor) {
+	*cross_ms = *cross_me = -1;
+	*joined = false;
+	if (from >= end_run) return from;
+	const int64_t view = (limit < 0 || end_run + limit > hi) ? hi : end_run + limit;
+	const bool trunc = view < hi;
+	const uint32_t nsym = (uint32_t) P.dfa_nsym, acc_lo = (uint32_t) P.dfa_acc_lo;
+	if (from_bits) bor(from_bits + (from >> 5), 1u << (from & 31));
+	int64_t stp = from, pos = from, last = -1; /* the attempt in progress began at stp, has read up to pos, last match end seen */
+	uint32_t state = (uint32_t) (stp == lo ? P.dfa_start_bol : P.dfa_start);
+	bool hit_end = false;
+	int len0 = 1; /* length of the character at stp (read by the first step of the attempt) */
+	jtk_rx_window win;
+	win.idx = -2; /* (neither this word nor the one before it) */
+	for (;;) {
+		/* ---- one character, one transition ---- */
+		uint32_t sym = nsym - 1; /* end of the (visible) text */
+		int len = 1;
+		if (pos >= view) {
+			hit_end = true;
+		} else {
+			if (pos + 4 > view) hit_end = true;
+			const uint32_t x = jtk_rx_fetch4(s, pos, hi, win);
+			const uint32_t b0 = x & 0xFFu;
+			if (b0 < 0x80) {
+				sym = P.dfa_ascii[b0];
+			} else {
+				const uint32_t cp = jtk_rx_decode_word(x, view - pos, &len);
+				sym = P.dfa_stage2[((uint32_t) P.dfa_stage1[cp >> 8] << 8) | (cp & 255u)];
+			}
+			if (pos == stp) len0 = len;
+		}
+		const uint32_t t = P.dfa_trans[state * nsym + sym];
+		if (t & 0x8000u) last = pos;
+		const uint32_t ns = t & 0x7FFFu;
+		if (sym != nsym - 1 && ns != 0) {
+			pos += len;
+			state = ns;
+			if (ns < acc_lo) continue;
+			last = pos; /* nothing but MATCH is left: the attempt ends here */
+		}
+		/* ---- the attempt at stp is over ---- */
+		if (hit_end && trunc) return JTK_RX_NO_EXIT; /* the matcher saw the end of a truncated view: with the whole text the outcome might differ */
+		if (last < 0) { /* nothing matches at stp: the search moves on by one character */
+			if (stp >= view) return hi;
+			stp += len0;
+		} else {
+			if (last > stp) {
+				if (last >= end_run) { /* its end bit lies outside this run's range: the caller places it */
+					*cross_ms = stp;
+					*cross_me = last;
+					return last;
+				}
+				bor(ms_bits + (stp >> 5), 1u << (stp & 31));
+				bor(me_bits + (last >> 5), 1u << (last & 31));
+				from = last;
+			} else { /* empty match: nothing to emit, the search moves on by one character */
+				if (stp >= hi) return hi;
+				from = stp + len0;
+			}
+			/* the next find() begins at `from` */
+			if (from >= end_run) return from;
+			if (stop_bits && jtk_rx_bit(stop_bits, from)) {
+				*joined = true;
+				return from;
+			}
+			if (from_bits) bor(from_bits + (from >> 5), 1u << (from & 31));
+			stp = from;
+		}
+		pos = stp;
+		last = -1;
+		state = (uint32_t) (stp == lo ? P.dfa_start_bol : P.dfa_start);
+	}
+}
+
 /* Follows the chain from `from` inside the document [lo, hi) until it leaves [.., end_run).  Match bits go to ms / me through
  * `bor` (matches that end inside the run only; the one that crosses end_run is returned in *cross_ms / *cross_me).  from_bits
  * (nullable): every `from` passed is recorded.  stop_bits (nullable): the run stops as soon as it lands on a recorded `from`
@@ -501,6 +625,7 @@ template <typename Or>
 JTK_HD int64_t jtk_rx_chain(const jtk_rx_program &P, const jtk_tables &T, const uint8_t *s, int64_t lo, int64_t hi, int64_t from, int64_t end_run, int64_t limit,
                             uint32_t *ms_bits, uint32_t *me_bits, uint32_t *from_bits, const uint32_t *stop_bits, int64_t *cross_ms, int64_t *cross_me, bool *joined,
                             jtk_rx_frame *st, int cap, bool *overflow, Or bor) {
+	if (P.dfa_trans) return jtk_rx_chain_dfa(P, s, lo, hi, from, end_run, limit, ms_bits, me_bits, from_bits, stop_bits, cross_ms, cross_me, joined, bor);
 	*cross_ms = *cross_me = -1;
 	*joined = false;
 	bool first = true;

@@ -236,6 +236,31 @@ extern "C" int emu_general_split(const emu_encoding *e, const uint8_t *bytes, co
 
 extern "C" int emu_pattern_kind(const emu_encoding *e) { return e->view.pattern_kind; }
 
+/* jtk_rx_decode_word (the flat DFA loop's decoder over a fetched word) against jtk_rx_decode (the byte-wise one) on pseudo-random
+ * four-byte windows, every lead-byte class and every amount of text left; returns the number of disagreements */
+extern "C" int64_t emu_decode_word_check(int64_t samples, uint64_t seed) {
+	int64_t bad = 0;
+	uint64_t x = seed * 2862933555777941757ull + 3037000493ull;
+	for (int64_t i = 0; i < samples; i++) {
+		x = x * 6364136223846793005ull + 1442695040888963407ull;
+		uint8_t b[4];
+		for (int k = 0; k < 4; k++) {
+			const uint32_t r = (uint32_t) (x >> (8 + 12 * k)) & 0xFFFu;
+			/* mostly continuation bytes after the first, all classes of lead byte in front */
+			b[k] = (k > 0 && (r & 0x300u)) ? (uint8_t) (0x80u | (r & 0x3Fu)) : (uint8_t) r;
+		}
+		for (int avail = 1; avail <= 4; avail++) {
+			int l0, l1;
+			const uint32_t c0 = jtk_rx_decode(b, 0, avail, &l0);
+			uint32_t w = 0;
+			for (int k = 0; k < 4; k++) w |= (uint32_t) b[k] << (8 * k); /* (bytes beyond avail are garbage on purpose) */
+			const uint32_t c1 = jtk_rx_decode_word(w, avail, &l1);
+			if (c0 != c1 || l0 != l1) bad++;
+		}
+	}
+	return bad;
+}
+
 /* DFA of a general pattern: states (0 = the pattern has no DFA form), symbols; why not, if not */
 extern "C" int emu_dfa_info(const emu_encoding *e, int *nsym, char *why, int why_cap) {
 	*nsym = e->view.rx_dfa_nsym;

@@ -168,6 +168,15 @@ def test_general_pattern_stack_overflow_is_reported():
         e2.general_split(text, off, stack_cap=64)
 
 
+def test_flat_dfa_loop_decodes_utf8_like_the_bytewise_decoder():
+    import ctypes as C
+    import emu
+    L = emu.lib()
+    L.emu_decode_word_check.restype = C.c_int64
+    L.emu_decode_word_check.argtypes = [C.c_int64, C.c_uint64]
+    assert L.emu_decode_word_check(2_000_000, 7) == 0
+
+
 def test_dfa_is_built_for_the_predefined_pattern_strings_as_general_patterns():
     """The two predefined split patterns (possessive quantifiers, \\s+(?!\\S), (?i:...)) have a DFA form when they are registered
     with a flag that takes them off the rule path: small tables, and the same pieces as the oracle's matcher (checked above for

@@ -905,27 +905,29 @@ __global__ void jtk_short_offsets_kernel(const jtk_encode_args a) {
 }
 
 constexpr int SNT = 128;
+constexpr int STW = SNT / 32; /* tiles per CTA: one warp per tile (a tile queues a few dozen pieces: a whole CTA per tile mostly idled) */
 
 __global__ void __launch_bounds__(SNT) jtk_short_scatter_kernel(const __grid_constant__ jtk_encode_args a) {
-	__shared__ unsigned s_hist[JTK_SHORT_PIECE + 1], s_cur[JTK_SHORT_PIECE + 1];
-	const int tid = threadIdx.x;
-	const long long tile = a.tile_begin + blockIdx.x;
+	__shared__ unsigned s_hist[STW][JTK_SHORT_PIECE + 1], s_cur[STW][JTK_SHORT_PIECE + 1];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const long long tile = a.tile_begin + (long long) blockIdx.x * STW + warp;
 	if (tile >= a.tile_end) return;
 	const int S = a.nslow[tile];
 	if (S == 0) return;
 	const long long lt = tile - a.tile_begin;
 	const int32_t *rec = a.rec + lt * (long long) RECN;
 	const uint16_t *sq = a.slowq + lt * (long long) QCAP;
-	if (tid <= JTK_SHORT_PIECE) s_hist[tid] = 0;
-	__syncthreads();
-	for (int k = tid; k < S; k += SNT) atomicAdd(&s_hist[(rec_payload(rec[sq[k]]) & 0x7FFu) + 1], 1u);
-	__syncthreads();
-	if (tid <= JTK_SHORT_PIECE) s_cur[tid] = s_hist[tid] ? atomicAdd(&a.sub->short_cur[tid], s_hist[tid]) : 0u; /* reserve a range per length */
-	__syncthreads();
-	for (int k = tid; k < S; k += SNT) {
+	unsigned *hist = s_hist[warp], *cur = s_cur[warp];
+	for (int n = lane; n <= JTK_SHORT_PIECE; n += 32) hist[n] = 0;
+	__syncwarp();
+	for (int k = lane; k < S; k += 32) atomicAdd(&hist[(rec_payload(rec[sq[k]]) & 0x7FFu) + 1], 1u);
+	__syncwarp();
+	for (int n = lane; n <= JTK_SHORT_PIECE; n += 32) cur[n] = hist[n] ? atomicAdd(&a.sub->short_cur[n], hist[n]) : 0u; /* reserve a range per length */
+	__syncwarp();
+	for (int k = lane; k < S; k += 32) {
 		const int q = sq[k];
 		const int n = (int) (rec_payload(rec[q]) & 0x7FFu) + 1;
-		a.shortlist[atomicAdd(&s_cur[n], 1u)] = ((uint32_t) lt << 14) | (uint32_t) q;
+		a.shortlist[atomicAdd(&cur[n], 1u)] = ((uint32_t) lt << 14) | (uint32_t) q;
 	}
 }
 
@@ -1077,9 +1079,16 @@ __global__ void __launch_bounds__(1024, 1) jtk_tile_scan_kernel(const jtk_encode
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	if (tid == 0) s_carry = (long long) a.hdr->total_tokens;
 	__syncthreads();
-	for (int64_t base = a.tile_begin; base < a.tile_end; base += 1024) {
-		const int64_t i = base + tid;
-		const long long val = i < a.tile_end ? a.tile_count[i] : 0;
+	constexpr int TSI = 8; /* consecutive tiles per thread and round (one 32-byte sector of counts): eight times fewer rounds of barriers */
+	for (int64_t base = a.tile_begin; base < a.tile_end; base += 1024 * TSI) {
+		const int64_t i0 = base + (int64_t) tid * TSI;
+		int c[TSI];
+		long long val = 0;
+#pragma unroll
+		for (int k = 0; k < TSI; k++) {
+			c[k] = i0 + k < a.tile_end ? a.tile_count[i0 + k] : 0;
+			val += c[k];
+		}
 		long long x = val;
 		for (int o = 1; o < 32; o <<= 1) {
 			long long y = __shfl_up_sync(0xFFFFFFFFu, x, o);
@@ -1097,7 +1106,12 @@ __global__ void __launch_bounds__(1024, 1) jtk_tile_scan_kernel(const jtk_encode
 		}
 		__syncthreads();
 		const long long excl = s_carry + x - val + (warp ? s_w[warp - 1] : 0);
-		if (i < a.tile_end) a.tile_base[i] = excl;
+		long long run = excl;
+#pragma unroll
+		for (int k = 0; k < TSI; k++) {
+			if (i0 + k < a.tile_end) a.tile_base[i0 + k] = run;
+			run += c[k];
+		}
 		__syncthreads();
 		if (tid == 1023) s_carry = excl + val;
 		__syncthreads();
@@ -1162,14 +1176,17 @@ __global__ void __launch_bounds__(GNT, 2048 / GNT) jtk_gather_kernel(const __gri
 			for (int j = 0; j < GIPT; j++) r[j] = qb + j < P ? rec[qb + j] : (int32_t) (REC_BASE + (int32_t) REC_SKIP);
 		}
 		int mine = 0;
+		bool any_empty = false; /* a record without tokens: a long piece (placed later), a gap, or the padding after the tile's last piece */
 #pragma unroll
 		for (int j = 0; j < GIPT; j++) {
 			cnt[j] = rec_count(r[j]);
 			mine += cnt[j];
+			any_empty |= cnt[j] == 0;
 		}
 		int round_total;
 		int excl = carry + block_exclusive_scan<GNT>(mine, s_w, &round_total);
 		if (qb < P) s_gpref[qb / GIPT] = (uint16_t) excl;
+		if (any_empty)
 #pragma unroll
 		for (int j = 0; j < GIPT; j++)
 			if (!cnt[j] && qb + j < P && !rec_is_id(r[j]) && (rec_payload(r[j]) & REC_LONG)) { /* (no tokens here: rare, tested first) */
@@ -1187,9 +1204,17 @@ __global__ void __launch_bounds__(GNT, 2048 / GNT) jtk_gather_kernel(const __gri
 						if (rec_is_id(r[j])) {
 							s_tok[pos] = r[j];
 						} else if (cnt[j]) {
+							/* merged / memoised piece: two to four tokens as a rule - straight-line stores for those, a loop for the rest */
 							int32_t *o = s_tok + pos;
 							const int32_t src = rec_token_source(r[j]);
-							for (int k = 0; k < cnt[j]; k++) o[k] = src + k;
+							const int n = cnt[j];
+							o[0] = src;
+							if (n > 1) o[1] = src + 1;
+							if (n > 2) {
+								o[2] = src + 2;
+								if (n > 3) o[3] = src + 3;
+								for (int k = 4; k < n; k++) o[k] = src + k;
+							}
 						}
 						pos += cnt[j];
 					}
@@ -1757,7 +1782,7 @@ cudaError_t jtk_launch_post(const jtk_encode_args &a, int num_sms, cudaStream_t 
 	cfg.attrs = attr;
 	cfg.numAttrs = l2_window_attr(a, attr);
 	jtk_short_offsets_kernel<<<1, 32, 0, st>>>(a);
-	jtk_short_scatter_kernel<<<(unsigned) nt, SNT, 0, st>>>(a);
+	jtk_short_scatter_kernel<<<(unsigned) ((nt + STW - 1) / STW), SNT, 0, st>>>(a);
 	if (marks) cudaEventRecord(marks[0], st);
 	/* the four merge kernels are independent of each other (own lists, own pieces): longest chains first, side by side */
 	if (side) {

@@ -65,7 +65,7 @@ print("--- by function: instr share, stall-sample share, active threads per inst
 for gname, v in sorted(groups.items(), key=lambda kv: -kv[1][1])[:32]:
     print("  %-36s ins %5.1f%%  smp %5.1f%%  thr/ins %4.1f" % (gname, 100 * v[1] / tot_i, 100 * v[0] / tot_s, v[2] / max(v[1], 1)))
 if len(sys.argv) > 2:
-    print("warp instructions per 8 KiB tile: %.0f" % (tot_i / (int(sys.argv[2]) / 8192)))
+    print("warp instructions per input byte: %.2f (per 7 072-byte tile: %.0f)" % (tot_i / int(sys.argv[2]), tot_i / (int(sys.argv[2]) / 7072)))
 print("--- top lines by stall samples")
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:14]:
     print("  %-16s %4d smp %5.1f%% ins %5.1f%% | %s" % (k[0], k[1], 100 * v[0] / tot_s, 100 * v[1] / tot_i, v[3].strip()[:100]))

@@ -49,27 +49,29 @@ if os.path.exists(L):
     cp(TAG + "_launches.csv")
     table = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "step_table.py"), L, os.path.join(P, TAG + "_step_traffic.json")], capture_output=True, text=True).stdout
     open(os.path.join(P, TAG + "_launches_summary.txt"), "w").write(
-        "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:jtk_ --csv python tools/gpu_one.py mix 1024 1\n"
-        "(one warm-up call + one timed call of jtk_encode_device over the bench's 1 GiB multilingual corpus; the table is the last complete step.\n"
+        "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:jtk_ -s 3*47 -c 2*47 --csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline\n"
+        "(the two timed device-resident steps of the bench command over its 1 GiB multilingual corpus; the table is the first of them.\n"
         " per-launch times are cold-cache and serialised - in production the merge kernels of a sub-batch overlap on forked streams: compare shares, not absolutes)\n\n" + table)
     print(table)
 rep = os.path.join(G, TAG + "_split.ncu-rep")
 if os.path.exists(rep):
-    txt, traffic = describe(rep, ["ncu --set full --clock-control none --import-source on -k regex:jtk_split_lookup -s 4 -c 1 python tools/gpu_one.py mix 256 2",
-                                  "(selected raw metrics; the launch is the last sub-batch (176 MiB.. see Grid Size x 7072-byte tiles) of a call over 256 MiB of the multilingual corpus)"])
+    txt, traffic = describe(rep, ["ncu --set full --clock-control none --import-source on -k regex:jtk_split_lookup -s 17 -c 1 python bench.py --steps 2 --warmup 3 --no-cpu-baseline",
+                                  "(selected raw metrics; the launch is the 256 MiB sub-batch of the first timed step over the 1 GiB multilingual corpus;",
+                                  " a step runs five sub-batches of 16, 64, 256, 512 MiB and the rest)"])
     open(os.path.join(P, TAG + "_split_lookup_ncu_full.txt"), "w").write(txt)
     summ = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep, "268435456"], capture_output=True, text=True).stdout
     open(os.path.join(P, TAG + "_split_lookup_source_hotspots.txt"), "w").write("per-function / per-line shares from the ncu source page\n\n" + summ)
 rep = os.path.join(G, TAG + "_merge_gather.ncu-rep")
 if os.path.exists(rep):
-    txt, _ = describe(rep, ["JTK_SIDE_STREAMS=0 ncu --set full --clock-control none --import-source on -k 'regex:jtk_merge_short|jtk_merge_medium|jtk_gather' -s 20 -c 5 python tools/gpu_one.py mix 256 2",
+    txt, _ = describe(rep, ["JTK_SIDE_STREAMS=0 ncu --set full --clock-control none --import-source on -k 'regex:jtk_merge_short|jtk_merge_medium|jtk_gather' -s 85 -c 5 python bench.py --steps 2 --warmup 3 --no-cpu-baseline",
+                            "(the 256 MiB sub-batch of the first timed step)",
                             "(in production the merge kernels of a sub-batch run side by side on forked streams)"])
     open(os.path.join(P, TAG + "_merge_gather_ncu_full.txt"), "w").write(txt)
 rep = os.path.join(G, TAG + "_decode.ncu-rep")
 if os.path.exists(rep):
-    txt, traffic = describe(rep, ["ncu --set full --clock-control none --import-source on -k regex:jtk_decode_fused -s 2 -c 1 python tools/decode_probe.py 256",
-                                  "(decode of the ids of 256 MiB of the multilingual corpus back to bytes, device-resident)"])
+    txt, traffic = describe(rep, ["ncu --set full --clock-control none --import-source on -k regex:jtk_decode_fused -s 2 -c 1 python bench.py --steps 2 --warmup 3 --no-cpu-baseline",
+                                  "(the bench's decode leg: the 404 M ids of the step back to the 1 GiB corpus, device-resident; first timed launch)"])
     open(os.path.join(P, TAG + "_decode_ncu_full.txt"), "w").write(txt)
-for f in ("per_language.txt", "decode_probe.txt", "configs_8gpu.txt", "pcie_8gpu.txt", "tests_gpu.log", "tests_multi_2gpu.log",
+for f in ("per_language.txt", "decode_probe.txt", "general.txt", "configs_8gpu.txt", "pcie_8gpu.txt", "tests_gpu.log", "tests_multi_2gpu.log",
           "bench_n1.json", "bench_n2.json", "bench_n4.json", "bench_n8.json", "bench_reference.json"):
     cp(TAG + "_" + f)

@@ -25,7 +25,7 @@
 
 namespace {
 
-enum { D_CHAR, D_EPS, D_EPS2, D_LOOK1, D_BOL, D_MATCH };
+enum { D_CHAR, D_EPS, D_EPS2, D_LOOK1, D_BOL, D_EOI /* \\z: passes at the end of the text only */, D_MATCH };
 
 struct dnode {
 	int type, set, neg, a, b;
@@ -59,6 +59,13 @@ struct builder {
 			case JTK_RX_SPLIT: nodes[(size_t) self] = {D_EPS2, -1, 0, node_of_pc[(size_t) in.a], node_of_pc[(size_t) in.b]}; break;
 			case JTK_RX_JMP: nodes[(size_t) self] = {D_EPS, -1, 0, node_of_pc[(size_t) in.a], -1}; break;
 			case JTK_RX_BOL: nodes[(size_t) self] = {D_BOL, -1, 0, next, -1}; break;
+			case JTK_RX_EOL:
+				if (in.a == 0) { /* '$' / \\Z look two characters ahead (\\r\\n before the end) */
+					why = "'$'";
+					return false;
+				}
+				nodes[(size_t) self] = {D_EOI, -1, 0, next, -1};
+				break;
 			case JTK_RX_MATCH: nodes[(size_t) self] = {D_MATCH, -1, 0, -1, -1}; break;
 			case JTK_RX_LOOK: {
 				/* the sub-program must test exactly one character: SET MATCH, or a repeat that needs exactly one */
@@ -101,7 +108,7 @@ struct builder {
 				nodes[(size_t) self] = {D_EPS, -1, 0, tail, -1};
 				break;
 			}
-			default: why = in.op == JTK_RX_EOL ? "'$'" : in.op == JTK_RX_WORDB ? "\\b" : "unknown instruction"; return false;
+			default: why = in.op == JTK_RX_WORDB ? "\\b" : in.op == JTK_RX_LOOKB ? "look-behind" : "unknown instruction"; return false;
 			}
 		}
 		return true;
@@ -239,7 +246,7 @@ bool jtk_rx_build_dfa(const jtk_rx_compiled &prog, const jtk_tables &view, jtk_r
 				const int v = pre.back();
 				pre.pop_back();
 				const dnode &d = N[(size_t) v];
-				if (d.type == D_CHAR || d.type == D_LOOK1 || d.type == D_MATCH) {
+				if (d.type == D_CHAR || d.type == D_LOOK1 || d.type == D_EOI || d.type == D_MATCH) {
 					if (seen_pre[(size_t) v] == 2) continue;
 					seen_pre[(size_t) v] = 2;
 				}
@@ -248,8 +255,8 @@ bool jtk_rx_build_dfa(const jtk_rx_compiled &prog, const jtk_tables &view, jtk_r
 					c.cut = true;
 				} else if (d.type == D_CHAR) {
 					if (in_class(sym, d.set)) closure(d.a, false, c, seen_post, post_leaf);
-				} else if (d.type == D_LOOK1) {
-					if (in_class(sym, d.set) != (d.neg != 0)) {
+				} else if (d.type == D_LOOK1 || d.type == D_EOI) {
+					if (d.type == D_EOI ? sym == eof : in_class(sym, d.set) != (d.neg != 0)) {
 						/* goes on at the same position: its leaves are tried right here, before the less preferred threads */
 						std::vector<int> leaves;
 						ctx tmp;

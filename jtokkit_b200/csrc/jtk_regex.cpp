@@ -11,7 +11,7 @@
 
 namespace {
 
-enum { N_SET, N_CAT, N_ALT, N_REP, N_LOOK, N_EMPTY, N_BOL, N_EOL, N_WORDB };
+enum { N_SET, N_CAT, N_ALT, N_REP, N_LOOK, N_EMPTY, N_BOL, N_EOL /* min = 1: \\z */, N_WORDB, N_LOOKB /* set: the one character before */ };
 
 struct node {
 	int type = N_EMPTY;
@@ -158,6 +158,27 @@ struct parser {
 		}
 		if (next <= 0x10FFFF) dst.emplace_back(next, 0x10FFFF);
 	}
+	/* dst += the code points of the script `name` (or of all others, for neg); false when no such script is known */
+	static bool add_script(std::vector<std::pair<uint32_t, uint32_t>> &dst, const std::string &name, bool neg) {
+		int si = -1;
+		for (int k = 0; k < JTK_UC_SCRIPT_NAME_COUNT && si < 0; k++) {
+			const char *e = JTK_UC_SCRIPT_NAMES[k]; /* "LONG_NAME Code" */
+			const char *sp = strchr(e, ' ');
+			auto same = [](const char *a, size_t n, const std::string &b) {
+				if (b.size() != n) return false;
+				for (size_t i = 0; i < n; i++)
+					if (tolower((unsigned char) a[i]) != tolower((unsigned char) b[i])) return false;
+				return true;
+			};
+			if (same(e, (size_t) (sp - e), name) || same(sp + 1, strlen(sp + 1), name)) si = k;
+		}
+		if (si < 0) return false;
+		std::vector<std::pair<uint32_t, uint32_t>> in;
+		for (int k = 0; k < JTK_UC_SCRIPT_COUNT; k++)
+			if ((int) JTK_UC_SCRIPT[k][2] == si) in.emplace_back(JTK_UC_SCRIPT[k][0], JTK_UC_SCRIPT[k][1]);
+		add_ranges(dst, in, neg);
+		return true;
+	}
 	static std::vector<std::pair<uint32_t, uint32_t>> table_ranges(const uint32_t (*t)[2], int n) {
 		std::vector<std::pair<uint32_t, uint32_t>> v;
 		for (int k = 0; k < n; k++) v.emplace_back(t[k][0], t[k][1]);
@@ -214,6 +235,15 @@ struct parser {
 				b.ranges.emplace_back(14, 31);
 				b.ranges.emplace_back(33, 0x10FFFF);
 			}
+			return -1;
+		case 'h':
+		case 'H': /* horizontal whitespace: [ \t\xA0\u1680\u180e\u2000-\u200a\u202f\u205f\u3000] */
+			add_ranges(b.prop_ranges, {{9, 9}, {' ', ' '}, {0xA0, 0xA0}, {0x1680, 0x1680}, {0x180E, 0x180E}, {0x2000, 0x200A}, {0x202F, 0x202F}, {0x205F, 0x205F}, {0x3000, 0x3000}},
+			           c == 'H');
+			return -1;
+		case 'v':
+		case 'V': /* vertical whitespace: [\n\x0B\f\r\x85\u2028\u2029] */
+			add_ranges(b.prop_ranges, {{0x0A, 0x0D}, {0x85, 0x85}, {0x2028, 0x2029}}, c == 'V');
 			return -1;
 		case 'd':
 		case 'D': { /* [0-9], or \p{Nd} under UNICODE_CHARACTER_CLASS */
@@ -280,13 +310,18 @@ struct parser {
 			else if (name == "N" || name == "IsN" || name == "gc=N" || name == "general_category=N") b.flags |= neg ? JTK_RX_HAS_NOT_N : JTK_RX_HAS_N;
 			else {
 				std::string nm = name;
-				for (const char *pre : {"Is", "gc=", "general_category="})
+				bool is_prefix = false, script_only = false;
+				for (const char *pre : {"Is", "gc=", "general_category=", "script=", "sc="})
 					if (nm.rfind(pre, 0) == 0) {
 						nm = nm.substr(strlen(pre));
+						is_prefix = pre[0] == 'I';
+						script_only = pre[0] == 's';
 						break;
 					}
-				const uint32_t mask = gc_mask_of(nm);
-				if (mask) add_gc(b.prop_ranges, mask, neg);
+				const uint32_t mask = script_only ? 0u : gc_mask_of(nm);
+				if (script_only) { /* \p{script=Han}, \p{sc=Hani} (Character.UnicodeScript.forName: long name or ISO 15924 code, any case) */
+					if (!add_script(b.prop_ranges, nm, neg)) fail("unknown script in \\p{...}");
+				} else if (mask) add_gc(b.prop_ranges, mask, neg);
 				else if (nm == "Alphabetic" || (ucc && nm == "Alpha")) add_ranges(b.prop_ranges, table_ranges(JTK_UC_ALPHA, JTK_UC_ALPHA_COUNT), neg);
 				else if (nm == "Alpha") add_ranges(b.prop_ranges, {{'A', 'Z'}, {'a', 'z'}}, neg);
 				else if (nm == "White_Space" || nm == "WhiteSpace" || (ucc && nm == "Space")) add_ranges(b.prop_ranges, table_ranges(JTK_UC_WS, JTK_UC_WS_COUNT), neg);
@@ -297,7 +332,8 @@ struct parser {
 					else in.emplace_back('0', '9');
 					add_ranges(b.prop_ranges, in, neg);
 				} else if (nm == "ASCII") add_ranges(b.prop_ranges, {{0, 127}}, neg);
-				else fail("unsupported \\p{...} property (general categories, Alphabetic, White_Space, Alpha, Digit, Space and ASCII are supported)");
+				else if (is_prefix && add_script(b.prop_ranges, nm, neg)) { /* \p{IsHan}: binary properties and categories first, then scripts (Pattern.java) */
+				} else fail("unsupported \\p{...} property (general categories, scripts, Alphabetic, White_Space, Alpha, Digit, Space and ASCII are supported)");
 			}
 			return -1;
 		}
@@ -386,9 +422,28 @@ struct parser {
 					look_depth--;
 					if (!eat(')')) fail("missing ) after look-ahead");
 					return lk;
-				} else if (peek() == '<') {
-					fail("look-behind / named groups are not supported");
-					return std::make_unique<node>();
+				} else if (peek() == '<' && i + 1 < p.size() && (p[i + 1] == '=' || p[i + 1] == '!')) {
+					/* look-behind over exactly one character: (?<=[set]) / (?<![set]) */
+					const bool neg = p[i + 1] == '!';
+					i += 2;
+					auto sub = parse_alt(sub_ci);
+					if (!eat(')')) fail("missing ) after look-behind");
+					const node *one = sub.get();
+					while (one->type == N_CAT && one->kids.size() == 1) one = one->kids[0].get();
+					auto lb = std::make_unique<node>();
+					lb->type = N_LOOKB;
+					lb->neg = neg;
+					if (one->type != N_SET) fail("look-behind over anything but one character is not supported");
+					else lb->set = one->set;
+					return lb;
+				} else if (peek() == '<') { /* named group (?<name>X): the name is irrelevant here (no back-references) */
+					i++;
+					int k = 0;
+					while (peek() >= 0 && peek() != '>') i++, k++;
+					if (!k || !eat('>')) {
+						fail("bad group name");
+						return std::make_unique<node>();
+					}
 				} else {
 					bool on = true, seen = false;
 					while (peek() >= 0 && peek() != ')' && peek() != ':') {
@@ -466,8 +521,14 @@ struct parser {
 				nd->set3 = finish_set(ld);
 				return nd;
 			}
-			if (nc == 'A' || nc == 'z' || nc == 'Z' || nc == 'G' || nc == 'R' || nc == 'X' || nc == 'Q' || nc == 'h' || nc == 'H' || nc == 'v' ||
-			    nc == 'V' || nc == 'k' || (nc >= '1' && nc <= '9')) {
+			if (nc == 'A' || nc == 'Z' || nc == 'z') { /* \A: '^' without MULTILINE; \Z: '$' without MULTILINE; \z: the very end of the input */
+				i++;
+				auto nd = std::make_unique<node>();
+				nd->type = nc == 'A' ? N_BOL : N_EOL;
+				nd->min = nc == 'z';
+				return nd;
+			}
+			if (nc == 'G' || nc == 'R' || nc == 'X' || nc == 'Q' || nc == 'k' || (nc >= '1' && nc <= '9')) {
 				fail("unsupported escape (boundary / back-reference / quoting)");
 				return std::make_unique<node>();
 			}
@@ -588,7 +649,8 @@ struct parser {
 		case N_EMPTY: break;
 		case N_SET: code.push_back({JTK_RX_SET, nd->set, 0, 0, 0}); break;
 		case N_BOL: code.push_back({JTK_RX_BOL, 0, 0, 0, 0}); break;
-		case N_EOL: code.push_back({JTK_RX_EOL, 0, 0, 0, 0}); break;
+		case N_EOL: code.push_back({JTK_RX_EOL, nd->min, 0, 0, 0}); break;
+		case N_LOOKB: code.push_back({JTK_RX_LOOKB, nd->neg ? 1 : 0, nd->set, 0, 0}); break;
 		case N_WORDB: code.push_back({JTK_RX_WORDB, nd->min, nd->set, nd->set2, nd->set3}); break;
 		case N_CAT:
 			for (auto &k : nd->kids) emit(k.get());
@@ -709,6 +771,28 @@ int jtk_rx_compile(const char *pattern, int flags, jtk_rx_compiled *out, std::st
 		ps.p.push_back(cp);
 		i += (size_t) len;
 	}
+	{ /* \Q...\E quoting, as Pattern.RemoveQEQuoting does it: the quoted characters become escaped literals (letters and digits as they are) */
+		std::vector<uint32_t> q;
+		bool quoted = false;
+		for (size_t i = 0; i < ps.p.size(); i++) {
+			const uint32_t c = ps.p[i];
+			const bool bs = c == '\\' && i + 1 < ps.p.size();
+			if (!quoted && bs && ps.p[i + 1] == 'Q') {
+				quoted = true;
+				i++;
+			} else if (quoted && bs && ps.p[i + 1] == 'E') {
+				quoted = false;
+				i++;
+			} else if (quoted) {
+				if (!((c >= '0' && c <= '9') || (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || c >= 128)) q.push_back('\\');
+				q.push_back(c);
+			} else {
+				q.push_back(c);
+				if (bs) q.push_back(ps.p[++i]); /* an escaped backslash does not begin a \Q */
+			}
+		}
+		ps.p.swap(q);
+	}
 	bool ci = (flags & JTK_RE_CASE_INSENSITIVE) != 0;
 	auto root = ps.parse_alt(ci);
 	if (!ps.failed() && ps.i < ps.p.size()) ps.fail("unmatched )");
@@ -754,6 +838,7 @@ int jtk_rx_compile(const char *pattern, int flags, jtk_rx_compiled *out, std::st
 			case JTK_RX_LOOK: /* zero width: the sub-program does not consume, matching goes on at pc + 1 */
 			case JTK_RX_BOL:
 			case JTK_RX_EOL:
+			case JTK_RX_LOOKB:
 			case JTK_RX_WORDB: todo.push_back(pc + 1); break;
 			default: any = true; /* MATCH reached without consuming: the pattern can match the empty string */
 			}

@@ -14,9 +14,11 @@
  * Unicode properties: every general category (\p{Lu}, \p{IsLu}, \p{gc=Lu}, one-letter groups, LC), Alphabetic, White_Space and
  * the POSIX names Alpha / Digit / Space / ASCII; \d \D \w \W and \b \B in their ASCII and UNICODE_CHARACTER_CLASS meanings
  * (tables of Unicode 15.0, unicode_ranges.inc; \b as java.util.regex.Pattern.Bound of JDK 11-18 defines it).
- * Not supported (registration fails with JTK_E_PATTERN_UNSUPPORTED, nothing falls back to the CPU): look-behind,
- * back-references, named groups, class intersection / nested classes, script / block properties, \A \z \Z \G \R \X \Q..\E,
- * loops over sub-expressions that can match the empty string, counted loops beyond 16.
+ * Also: named groups (as plain groups), \A \Z \z, \Q..\E, \h \H \v \V, Unicode scripts (\p{IsHan}, \p{script=Han}, \p{sc=Hani}), look-behind
+ * over exactly one character ((?<=[set]) / (?<![set])).
+ * Not supported (registration fails with JTK_E_PATTERN_UNSUPPORTED, nothing falls back to the CPU): longer look-behind,
+ * back-references, atomic groups, class intersection / nested classes, block properties, \G \R \X,
+ * loops over sub-expressions that can match the empty string, counted loops over groups beyond 16.
  */
 #ifndef JTK_REGEX_H
 #define JTK_REGEX_H
@@ -32,9 +34,10 @@ enum {
 	JTK_RX_JMP,        /* a = pc */
 	JTK_RX_LOOK,       /* a = 1 negative / 0 positive, b = pc of the sub-program (ends in MATCH); continues at pc + 1 */
 	JTK_RX_BOL,
-	JTK_RX_EOL,
+	JTK_RX_EOL,        /* a = 0: '$' / \\Z without MULTILINE (the end, or before a final line terminator); a = 1: \\z (the end only) */
 	JTK_RX_MATCH,
-	JTK_RX_WORDB       /* a = 1 for \\B; b, c, d = sets: word characters, non-spacing marks, letters-or-digits (java.util.regex.Pattern.Bound) */
+	JTK_RX_WORDB,      /* a = 1 for \\B; b, c, d = sets: word characters, non-spacing marks, letters-or-digits (java.util.regex.Pattern.Bound) */
+	JTK_RX_LOOKB       /* look-behind over one character: a = 1 negative / 0 positive, b = set the character before the position is tested against */
 };
 
 struct jtk_rx_inst {
@@ -265,7 +268,7 @@ JTK_HD int64_t jtk_rx_run(const jtk_rx_program &P, const jtk_tables &T, const ui
 		case JTK_RX_EOL: { /* Java '$' without MULTILINE: at the end, or before a final line terminator */
 			if (pos + 4 > n) *hit_end = true;
 			bool ok = pos == n;
-			if (!ok && pos < n) {
+			if (!ok && pos < n && in.a == 0) {
 				int len;
 				const uint32_t cp = jtk_rx_decode(s, pos, n, &len);
 				const bool term = cp == '\n' || cp == '\r' || cp == 0x85 || cp == 0x2028 || cp == 0x2029;
@@ -297,6 +300,17 @@ JTK_HD int64_t jtk_rx_run(const jtk_rx_program &P, const jtk_tables &T, const ui
 			const bool left = pos > lo && word_at(jtk_rx_prev(s, pos, lo));
 			const bool right = pos < n && word_at(pos);
 			if ((left != right) == (in.a != 0)) fail = true;
+			else pc++;
+			break;
+		}
+		case JTK_RX_LOOKB: { /* the character before the position (none at the document start) against one set */
+			bool hit = false;
+			if (pos > lo) {
+				int len;
+				const uint32_t cp = jtk_rx_decode(s, jtk_rx_prev(s, pos, lo), n, &len);
+				hit = jtk_rx_in_set(P, T, in.b, cp);
+			}
+			if (hit == (in.a != 0)) fail = true;
 			else pc++;
 			break;
 		}

@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <strings.h>
 
 #include "../jtokkit_b200/csrc/unicode_ranges.inc"
 
@@ -59,13 +60,36 @@ static int uc_word(uint32_t cp) {
 	const int g = uc_category(cp);
 	return uc_alphabetic(cp) || g == 5 || g == 6 || g == 7 || g == 8 || g == 11 || cp == 0x200C || cp == 0x200D;
 }
+/* script index per code point (order of JTK_UC_SCRIPT_NAMES; 255 = no script / unassigned), filled on first use */
+static uint8_t *uc_script;
+static void uc_script_init(void) {
+	uint8_t *t = (uint8_t *) malloc(0x110000);
+	memset(t, 255, 0x110000);
+	for (int k = 0; k < JTK_UC_SCRIPT_COUNT; k++)
+		for (uint32_t cp = JTK_UC_SCRIPT[k][0]; cp <= JTK_UC_SCRIPT[k][1]; cp++) t[cp] = (uint8_t) JTK_UC_SCRIPT[k][2];
+	if (!__sync_bool_compare_and_swap(&uc_script, NULL, t)) free(t);
+}
+static inline int uc_script_of(uint32_t cp) {
+	if (!uc_script) uc_script_init();
+	return cp < 0x110000 ? uc_script[cp] : 255;
+}
+/* Character.UnicodeScript.forName: the long name or the ISO 15924 code, case-insensitive; -1 = unknown */
+static int script_index_of(const char *name) {
+	for (int k = 0; k < JTK_UC_SCRIPT_NAME_COUNT; k++) {
+		const char *e = JTK_UC_SCRIPT_NAMES[k]; /* "LONG_NAME Code" */
+		const char *sp = strchr(e, ' ');
+		const size_t ln = (size_t) (sp - e);
+		if ((strlen(name) == ln && !strncasecmp(name, e, ln)) || !strcasecmp(name, sp + 1)) return k;
+	}
+	return -1;
+}
 int jo_uc_is_letter(uint32_t cp) { return uc_get(cp) & 1; }
 int jo_uc_is_number(uint32_t cp) { return (uc_get(cp) >> 1) & 1; }
 int jo_uc_is_space(uint32_t cp) { return (uc_get(cp) >> 2) & 1; }
 
 /* ------------------------------------------------------------------ node tree */
-enum { N_SET, N_ANY, N_CAT, N_ALT, N_REP, N_LOOK, N_EMPTY, N_BOL, N_EOL, N_WORDB };
-enum { C_L = 1, C_N, C_SPACE, C_DIGIT, C_WORD, C_GC /* mask of general categories */, C_ALPHA, C_ASCII };
+enum { N_SET, N_ANY, N_CAT, N_ALT, N_REP, N_LOOK, N_EMPTY, N_BOL, N_EOL /* min = 1: \z, the very end only */, N_WORDB, N_LOOKB /* sub: one set */ };
+enum { C_L = 1, C_N, C_SPACE, C_DIGIT, C_WORD, C_GC /* mask of general categories */, C_ALPHA, C_ASCII, C_SCRIPT /* mask = script index */, C_HSPACE, C_VSPACE };
 enum { Q_GREEDY, Q_LAZY, Q_POSSESSIVE };
 
 typedef struct cls_item {
@@ -255,6 +279,10 @@ static int parse_escape(parser *ps, node *set, int *lit) {
 	}
 	case 's': add_cls(set, C_SPACE, 0); return 1;
 	case 'S': add_cls(set, C_SPACE, 1); return 1;
+	case 'h': add_cls(set, C_HSPACE, 0); return 1; /* horizontal / vertical whitespace (the same sets with and without UNICODE_CHARACTER_CLASS) */
+	case 'H': add_cls(set, C_HSPACE, 1); return 1;
+	case 'v': add_cls(set, C_VSPACE, 0); return 1;
+	case 'V': add_cls(set, C_VSPACE, 1); return 1;
 	case 'd':
 	case 'D':
 	case 'w':
@@ -264,11 +292,11 @@ static int parse_escape(parser *ps, node *set, int *lit) {
 	case 'p':
 	case 'P': {
 		int neg = (c == 'P');
-		char name[32];
+		char name[48];
 		int k = 0;
 		if (eat(ps, '{')) {
 			if (eat(ps, '^')) neg = !neg;
-			while (peek(ps) >= 0 && peek(ps) != '}' && k < 31) name[k++] = (char) ps->p[ps->i++];
+			while (peek(ps) >= 0 && peek(ps) != '}' && k < 47) name[k++] = (char) ps->p[ps->i++];
 			if (!eat(ps, '}')) {
 				fail(ps, "unterminated \\p{...}");
 				return 0;
@@ -281,9 +309,22 @@ static int parse_escape(parser *ps, node *set, int *lit) {
 		else if (!strcmp(name, "N") || !strcmp(name, "IsN") || !strcmp(name, "gc=N") || !strcmp(name, "general_category=N")) add_cls(set, C_N, neg);
 		else {
 			const char *nm = name;
-			if (!strncmp(nm, "Is", 2)) nm += 2;
+			int is_prefix = 0, script_only = 0;
+			if (!strncmp(nm, "Is", 2)) nm += 2, is_prefix = 1;
 			else if (!strncmp(nm, "gc=", 3)) nm += 3;
 			else if (!strncmp(nm, "general_category=", 17)) nm += 17;
+			else if (!strncmp(nm, "script=", 7)) nm += 7, script_only = 1;
+			else if (!strncmp(nm, "sc=", 3)) nm += 3, script_only = 1;
+			if (script_only) { /* \p{script=Han}, \p{sc=Hani} */
+				const int si = script_index_of(nm);
+				if (si < 0) {
+					fail(ps, "unknown script");
+					return 0;
+				}
+				add_cls(set, C_SCRIPT, neg);
+				set->cls[set->ncls - 1].mask = (uint32_t) si;
+				return 1;
+			}
 			const uint32_t mask = gc_mask_of(nm);
 			const int ucc = (ps->flags & JO_RE_UNICODE_CHARACTER_CLASS) != 0;
 			if (mask) add_gc_cls(set, mask, neg);
@@ -299,6 +340,9 @@ static int parse_escape(parser *ps, node *set, int *lit) {
 			else if (!strcmp(nm, "Digit")) add_cls(set, C_DIGIT, neg);
 			else if (!strcmp(nm, "ASCII")) {
 				add_cls(set, C_ASCII, neg);
+			} else if (is_prefix && script_index_of(nm) >= 0) { /* \p{IsHan}: binary properties and categories first, then scripts (Pattern.java) */
+				add_cls(set, C_SCRIPT, neg);
+				set->cls[set->ncls - 1].mask = (uint32_t) script_index_of(nm);
 			} else {
 				fail(ps, "unsupported \\p{...} property");
 				return 0;
@@ -390,9 +434,26 @@ static node *parse_atom(parser *ps, int *ci) {
 				lk->sub = parse_alt(ps, sub_ci);
 				if (!eat(ps, ')')) fail(ps, "missing ) after look-ahead");
 				return lk;
-			} else if (peek(ps) == '<') {
-				fail(ps, "look-behind / named groups are not supported");
-				return new_node(ps, N_EMPTY);
+			} else if (peek(ps) == '<' && ps->i + 1 < ps->n && (ps->p[ps->i + 1] == '=' || ps->p[ps->i + 1] == '!')) {
+				/* look-behind over exactly one character: (?<=[set]) / (?<![set]) */
+				const int neg = ps->p[ps->i + 1] == '!';
+				ps->i += 2;
+				node *lb = new_node(ps, N_LOOKB);
+				lb->look_neg = neg;
+				node *sub = parse_alt(ps, sub_ci);
+				if (!eat(ps, ')')) fail(ps, "missing ) after look-behind");
+				while (sub->type == N_CAT && sub->nkids == 1) sub = sub->kids[0];
+				if (sub->type != N_SET && sub->type != N_ANY) fail(ps, "look-behind over anything but one character is not supported");
+				lb->sub = sub;
+				return lb;
+			} else if (peek(ps) == '<') { /* named group (?<name>X): the name is irrelevant here (no back-references) */
+				ps->i++;
+				int k = 0;
+				while (peek(ps) >= 0 && peek(ps) != '>') ps->i++, k++;
+				if (!k || !eat(ps, '>')) {
+					fail(ps, "bad group name");
+					return new_node(ps, N_EMPTY);
+				}
 			} else {
 				/* inline flags: (?i) (?-i) (?iu:...) */
 				int on = 1, seen = 0;
@@ -452,8 +513,17 @@ static node *parse_atom(parser *ps, int *ci) {
 			wb->look_neg = nc == 'B';
 			return wb;
 		}
-		if (nc == 'A' || nc == 'z' || nc == 'Z' || nc == 'G' || nc == 'R' || nc == 'X' || nc == 'Q' || nc == 'h' || nc == 'H' || nc == 'v' || nc == 'V' ||
-		    (nc >= '1' && nc <= '9') || nc == 'k') {
+		if (nc == 'A') { /* the beginning of the input: '^' without MULTILINE */
+			ps->i++;
+			return new_node(ps, N_BOL);
+		}
+		if (nc == 'Z' || nc == 'z') { /* \Z: '$' without MULTILINE; \z: the very end */
+			ps->i++;
+			node *e = new_node(ps, N_EOL);
+			e->min = nc == 'z';
+			return e;
+		}
+		if (nc == 'G' || nc == 'R' || nc == 'X' || nc == 'Q' || (nc >= '1' && nc <= '9') || nc == 'k') {
 			fail(ps, "unsupported escape (boundary / back-reference / quoting)");
 			return new_node(ps, N_EMPTY);
 		}
@@ -533,7 +603,7 @@ static node *parse_quantified(parser *ps, int *ci) {
 		rep->mode = Q_GREEDY;
 		if (eat(ps, '?')) rep->mode = Q_LAZY;
 		else if (eat(ps, '+')) rep->mode = Q_POSSESSIVE;
-		if (atom->type == N_LOOK || atom->type == N_EMPTY || atom->type == N_BOL || atom->type == N_EOL || atom->type == N_WORDB) {
+		if (atom->type == N_LOOK || atom->type == N_LOOKB || atom->type == N_EMPTY || atom->type == N_BOL || atom->type == N_EOL || atom->type == N_WORDB) {
 			fail(ps, "quantifier on a zero-width construct is not supported");
 			return atom;
 		}
@@ -584,6 +654,30 @@ jo_regex *jo_regex_compile(const char *pattern, int flags, char *err, int errlen
 		for (int k = 1; k < len && i + (size_t) k < blen; k++) cp = (cp << 6) | ((unsigned char) pattern[i + (size_t) k] & 0x3F);
 		cps[n++] = cp;
 		i += (size_t) len;
+	}
+	/* \Q...\E quoting, as Pattern.RemoveQEQuoting does it: the quoted characters become escaped literals (letters and digits as they are) */
+	{
+		uint32_t *q = (uint32_t *) malloc(sizeof(uint32_t) * (2 * (size_t) n + 1));
+		int m2 = 0, quoted = 0;
+		for (int i = 0; i < n; i++) {
+			if (!quoted && cps[i] == '\\' && i + 1 < n && cps[i + 1] == 'Q') {
+				quoted = 1;
+				i++;
+			} else if (quoted && cps[i] == '\\' && i + 1 < n && cps[i + 1] == 'E') {
+				quoted = 0;
+				i++;
+			} else if (quoted) {
+				const uint32_t c = cps[i];
+				if (!((c >= '0' && c <= '9') || (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || c >= 128)) q[m2++] = '\\';
+				q[m2++] = c;
+			} else {
+				q[m2++] = cps[i];
+				if (cps[i] == '\\' && i + 1 < n) q[m2++] = cps[++i]; /* an escaped backslash does not begin a \Q */
+			}
+		}
+		free(cps);
+		cps = q;
+		n = m2;
 	}
 	jo_regex *re = (jo_regex *) calloc(1, sizeof(jo_regex));
 	if (flags & JO_RE_UNICODE_CHARACTER_CLASS) flags |= JO_RE_UNICODE_CASE; /* Pattern.java: the flag implies UNICODE_CASE */
@@ -644,6 +738,11 @@ static int cls_match(const cls_item *it, uint32_t cp, int ucc) {
 	case C_ASCII:
 		if (it->mask == 3u) return (cp >= 'a' && cp <= 'z') || (cp >= 'A' && cp <= 'Z');
 		return cp < 128;
+	case C_SCRIPT: return uc_script_of(cp) == (int) it->mask;
+	case C_HSPACE: /* [ \t\xA0\u1680\u180e\u2000-\u200a\u202f\u205f\u3000] */
+		return cp == ' ' || cp == '\t' || cp == 0xA0 || cp == 0x1680 || cp == 0x180E || (cp >= 0x2000 && cp <= 0x200A) || cp == 0x202F || cp == 0x205F || cp == 0x3000;
+	case C_VSPACE: /* [\n\x0B\f\r\x85\u2028\u2029] */
+		return (cp >= 0x0A && cp <= 0x0D) || cp == 0x85 || cp == 0x2028 || cp == 0x2029;
 	}
 	return 0;
 }
@@ -729,6 +828,10 @@ static void compute_first(const mctx *m, node *nd) {
 	case N_BOL:
 	case N_EOL:
 	case N_WORDB:
+		nd->nullable = 1;
+		break;
+	case N_LOOKB:
+		compute_first(m, nd->sub); /* (fills the set's ASCII map) */
 		nd->nullable = 1;
 		break;
 	case N_LOOK:
@@ -860,9 +963,14 @@ static int64_t m_node(const mctx *m, const node *nd, int64_t i, const kont *k) {
 	case N_BOL:
 		if (i != 0) return -1;
 		return run_k(m, k, i);
-	case N_EOL: /* Java '$' without MULTILINE: at end, or before a final line terminator */
-		if (i == m->n || (i == m->n - 1 && is_line_term(m->s[i])) || (i == m->n - 2 && m->s[i] == '\r' && m->s[i + 1] == '\n')) return run_k(m, k, i);
+	case N_EOL: /* Java '$' without MULTILINE: at end, or before a final line terminator; \z (min = 1): at the end only */
+		if (i == m->n || (!nd->min && ((i == m->n - 1 && is_line_term(m->s[i])) || (i == m->n - 2 && m->s[i] == '\r' && m->s[i + 1] == '\n')))) return run_k(m, k, i);
 		return -1;
+	case N_LOOKB: { /* the character before position i, if any, against the one set */
+		const int hit = i > 0 && sw_match(m, nd->sub, i - 1);
+		if (hit == (nd->look_neg != 0)) return -1;
+		return run_k(m, k, i);
+	}
 	case N_WORDB: { /* java.util.regex.Pattern.Bound.check (JDK 11-18) */
 		const int left = i > 0 && word_char_at(m, i - 1), right = i < m->n && word_char_at(m, i);
 		if ((left != right) == (nd->look_neg != 0)) return -1;

@@ -101,6 +101,10 @@ GENERAL_PATTERNS = [
     (r"\p{Lu}\p{Ll}+|\p{Nd}+|\s+|.", 0x100), (r"\w+|\W+", 0x100), (r"\d+|\D", 0x100), (r"\p{Lu}+|\p{Ll}+|\P{L}", 0),
     (r"[\p{Sc}\p{Sm}]+|\p{P}|\p{IsAlphabetic}+|\p{Z}+|.", 0x100), (r"\b\w+\b|\W", 0x100), (r"\B.|.", 0x100), (r"\bfoo\b|\w+|\W", 0),
     (r"[^\W\d_]+|\d{1,3}|[\W_]", 0x100), (r"\p{gc=Mn}+|\p{IsLo}|\p{LC}+|\P{M}", 0),
+    # named groups, \A \Z \z, \Q..\E, \h \v, scripts, one-character look-behind
+    (r"(?<word>\w+)|(?<sp>\s+)|.", 0), (r"\Aab|\w+\z|\w+|\W", 0), (r"\w+\Z|\w+|\W", 0), (r"\Qa.b\E+|\w+|.", 0), (r"\h+|\v+|\H", 0),
+    (r"(?<=\d)[a-z]+|(?<![a-z])\d+|.", 0), (r"\p{IsHan}+|\p{script=Cyrillic}+|\p{sc=Latn}+|\P{IsHiragana}", 0),
+    (r"(?<!\p{L})\p{L}{1,3}|.", 0x100), (r"[\p{IsGreek}\p{IsHangul}]+|\p{IsCommon}|.", 0),
 ]
 
 

@@ -121,8 +121,10 @@ def test_custom_patterns_follow_java_regex_semantics(oracles):
     assert o2.encode_ordinary("abb") == [0, 1, 1]
     o3 = jo.OracleEncoding("t3", r"(?i:x+)(?!y)|\s+", 0, {}, {})
     assert o3.split("XXy xx") == [(0, 1), (3, 4), (4, 6)]
+    o4 = jo.OracleEncoding("t4", r"(?<=a)b|.", 0, {}, {})  # look-behind over one character
+    assert o4.split("abb") == [(0, 1), (1, 2), (2, 3)] and o4.split("ab") == [(0, 1), (1, 2)]
     with pytest.raises(ValueError):
-        jo.OracleEncoding("bad", r"(?<=a)b", 0, {}, {})
+        jo.OracleEncoding("bad", r"(?<=ab)c", 0, {}, {})
 
 
 def test_batch_thread_pool_matches_single_calls(oracles):
@@ -178,6 +180,38 @@ def test_oracle_unicode_properties_and_boundaries_against_the_regex_module():
         r = regex.compile(pat.replace(r"\p{IsAlphabetic}", r"\p{Alphabetic}").replace(r"\p{IsLo}", r"\p{Lo}"), regex.V0 | (regex.UNICODE if unicode_mode else regex.ASCII))
         for _ in range(300):
             t = "".join(rng.choice(alph) for _ in range(rng.randint(0, 30)))
+            boff = [0]
+            for ch in t:
+                boff.append(boff[-1] + len(ch.encode()))
+            exp = [(boff[m.start()], boff[m.end()]) for m in r.finditer(t) if m.end() > m.start()]
+            assert [(a, e) for a, e in o.split(t.encode()) if e > a] == exp, (pat, t)
+
+
+def test_oracle_groups_anchors_scripts_and_look_behind_against_the_regex_module():
+    """Named groups, \\A \\Z \\z, \\Q..\\E, \\h \\v, Unicode scripts (\\p{IsHan}, \\p{script=..}, \\p{sc=..}) and one-character look-behind in the
+    oracle's matcher against the `regex` module (Python spells \\z as \\Z, Java's \\Z as (?=\\n?\\Z), scripts without the Is prefix; its `.`
+    also matches \\r, U+0085, U+2028 and U+2029, so the last alternative is written out)."""
+    import random
+    import regex
+    from oracle import jo
+    dot = "[^\\n\\r\\x85\\u2028\\u2029]"
+    hs = "[ \\t\\xA0\\u1680\\u180e\\u2000-\\u200a\\u202f\\u205f\\u3000]"
+    vs = "[\\n\\x0B\\f\\r\\x85\\u2028\\u2029]"
+    pats = [(r"(?<word>\w+)|(?<sp>\s+)|.", 0, None, False), (r"\Aab|\w+\z|\w+|\W", 0, r"\Aab|\w+\Z|\w+|\W", False), (r"\w+\Z|\w+|\W", 0, r"\w+(?=\n?\Z)|\w+|\W", False),
+            (r"\Qa.b\E+|\w+|.", 0, r"a\.b+|\w+|.", False), (r"\h+|\v+|\H", 0, hs + "+|" + vs + "+|[^" + hs[1:], True),
+            (r"(?<=\d)[a-z]+|(?<![a-z])\d+|.", 0, None, False),
+            (r"\p{IsHan}+|\p{script=Cyrillic}+|\p{sc=Latn}+|\P{IsHiragana}", 0, r"\p{Han}+|\p{Script=Cyrillic}+|\p{Script=Latin}+|\P{Hiragana}", True),
+            (r"(?<!\p{L})\p{L}{1,3}|.", 0x100, None, True), (r"[\p{IsGreek}\p{IsHangul}]+|\p{IsCommon}|.", 0, r"[\p{Greek}\p{Hangul}]+|\p{Common}|.", True)]
+    alph = list("abcXYZ 019_-+$.,;!?'\n\r\t") + ["é", "ß", "Ж", "я", "中", "国", "あ", "カ", "١", "२", "　", " ", "—", "𝐀", "🍕", "한", "ा", "\u2028", "\x0b", "α", "Ω"]
+    rng = random.Random(5)
+    for pat, fl, rpat, uni in pats:
+        o = jo.OracleEncoding("t", pat, fl, {bytes([b]): b for b in range(256)}, {})
+        rp = rpat or pat
+        if rp.endswith("|."):
+            rp = rp[:-1] + dot
+        r = regex.compile(rp, regex.V0 | (regex.UNICODE if (fl & 0x100 or uni) else regex.ASCII))
+        for _ in range(300):
+            t = "".join(rng.choice(alph) for _ in range(rng.randint(0, 24)))
             boff = [0]
             for ch in t:
                 boff.append(boff[-1] + len(ch.encode()))

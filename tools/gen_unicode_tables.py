@@ -27,6 +27,39 @@ GC_NAMES = ["Lu", "Ll", "Lt", "Lm", "Lo", "Mn", "Mc", "Me", "Nd", "Nl", "No", "P
             "Zs", "Zl", "Zp", "Cc", "Cf", "Cs", "Co", "Cn"]
 
 
+# Unicode scripts (long name as Character.UnicodeScript spells it, ISO 15924 code); what the `regex` module does not know is skipped
+SCRIPTS = [("Common", "Zyyy"), ("Inherited", "Zinh"), ("Latin", "Latn"), ("Greek", "Grek"), ("Cyrillic", "Cyrl"), ("Armenian", "Armn"), ("Hebrew", "Hebr"),
+           ("Arabic", "Arab"), ("Syriac", "Syrc"), ("Thaana", "Thaa"), ("Devanagari", "Deva"), ("Bengali", "Beng"), ("Gurmukhi", "Guru"),
+           ("Gujarati", "Gujr"), ("Oriya", "Orya"), ("Tamil", "Taml"), ("Telugu", "Telu"), ("Kannada", "Knda"), ("Malayalam", "Mlym"),
+           ("Sinhala", "Sinh"), ("Thai", "Thai"), ("Lao", "Laoo"), ("Tibetan", "Tibt"), ("Myanmar", "Mymr"), ("Georgian", "Geor"),
+           ("Hangul", "Hang"), ("Ethiopic", "Ethi"), ("Cherokee", "Cher"), ("Canadian_Aboriginal", "Cans"), ("Ogham", "Ogam"), ("Runic", "Runr"),
+           ("Khmer", "Khmr"), ("Mongolian", "Mong"), ("Hiragana", "Hira"), ("Katakana", "Kana"), ("Bopomofo", "Bopo"), ("Han", "Hani"),
+           ("Yi", "Yiii"), ("Old_Italic", "Ital"), ("Gothic", "Goth"), ("Deseret", "Dsrt"), ("Tagalog", "Tglg"), ("Hanunoo", "Hano"),
+           ("Buhid", "Buhd"), ("Tagbanwa", "Tagb"), ("Limbu", "Limb"), ("Tai_Le", "Tale"), ("Linear_B", "Linb"), ("Ugaritic", "Ugar"),
+           ("Shavian", "Shaw"), ("Osmanya", "Osma"), ("Cypriot", "Cprt"), ("Braille", "Brai"), ("Buginese", "Bugi"), ("Coptic", "Copt"),
+           ("New_Tai_Lue", "Talu"), ("Glagolitic", "Glag"), ("Tifinagh", "Tfng"), ("Syloti_Nagri", "Sylo"), ("Old_Persian", "Xpeo"),
+           ("Kharoshthi", "Khar"), ("Balinese", "Bali"), ("Cuneiform", "Xsux"), ("Phoenician", "Phnx"), ("Phags_Pa", "Phag"), ("Nko", "Nkoo"),
+           ("Sundanese", "Sund"), ("Lepcha", "Lepc"), ("Ol_Chiki", "Olck"), ("Vai", "Vaii"), ("Saurashtra", "Saur"), ("Kayah_Li", "Kali"),
+           ("Rejang", "Rjng"), ("Lycian", "Lyci"), ("Carian", "Cari"), ("Lydian", "Lydi"), ("Cham", "Cham"), ("Tai_Tham", "Lana"),
+           ("Tai_Viet", "Tavt"), ("Avestan", "Avst"), ("Egyptian_Hieroglyphs", "Egyp"), ("Samaritan", "Samr"), ("Lisu", "Lisu"),
+           ("Bamum", "Bamu"), ("Javanese", "Java"), ("Meetei_Mayek", "Mtei"), ("Imperial_Aramaic", "Armi"), ("Old_South_Arabian", "Sarb"),
+           ("Inscriptional_Parthian", "Prti"), ("Inscriptional_Pahlavi", "Phli"), ("Old_Turkic", "Orkh"), ("Kaithi", "Kthi"), ("Batak", "Batk"),
+           ("Brahmi", "Brah"), ("Mandaic", "Mand"), ("Chakma", "Cakm"), ("Meroitic_Cursive", "Merc"), ("Meroitic_Hieroglyphs", "Mero"),
+           ("Miao", "Plrd"), ("Sharada", "Shrd"), ("Sora_Sompeng", "Sora"), ("Takri", "Takr"), ("Caucasian_Albanian", "Aghb"),
+           ("Bassa_Vah", "Bass"), ("Duployan", "Dupl"), ("Elbasan", "Elba"), ("Grantha", "Gran"), ("Pahawh_Hmong", "Hmng"), ("Khojki", "Khoj"),
+           ("Linear_A", "Lina"), ("Mahajani", "Mahj"), ("Manichaean", "Mani"), ("Mende_Kikakui", "Mend"), ("Modi", "Modi"), ("Mro", "Mroo"),
+           ("Old_North_Arabian", "Narb"), ("Nabataean", "Nbat"), ("Palmyrene", "Palm"), ("Pau_Cin_Hau", "Pauc"), ("Old_Permic", "Perm"),
+           ("Psalter_Pahlavi", "Phlp"), ("Siddham", "Sidd"), ("Khudawadi", "Sind"), ("Tirhuta", "Tirh"), ("Warang_Citi", "Wara"),
+           ("Ahom", "Ahom"), ("Anatolian_Hieroglyphs", "Hluw"), ("Hatran", "Hatr"), ("Multani", "Mult"), ("Old_Hungarian", "Hung"),
+           ("SignWriting", "Sgnw"), ("Adlam", "Adlm"), ("Bhaiksuki", "Bhks"), ("Marchen", "Marc"), ("Newa", "Newa"), ("Osage", "Osge"),
+           ("Tangut", "Tang"), ("Masaram_Gondi", "Gonm"), ("Nushu", "Nshu"), ("Soyombo", "Soyo"), ("Zanabazar_Square", "Zanb"),
+           ("Dogra", "Dogr"), ("Gunjala_Gondi", "Gong"), ("Makasar", "Maka"), ("Medefaidrin", "Medf"), ("Hanifi_Rohingya", "Rohg"),
+           ("Sogdian", "Sogd"), ("Old_Sogdian", "Sogo"), ("Elymaic", "Elym"), ("Nandinagari", "Nand"), ("Nyiakeng_Puachue_Hmong", "Hmnp"),
+           ("Wancho", "Wcho"), ("Chorasmian", "Chrs"), ("Dives_Akuru", "Diak"), ("Khitan_Small_Script", "Kits"), ("Yezidi", "Yezi"),
+           ("Cypro_Minoan", "Cpmn"), ("Old_Uyghur", "Ougr"), ("Tangsa", "Tnsa"), ("Toto", "Toto"), ("Vithkuqi", "Vith"), ("Kawi", "Kawi"),
+           ("Nag_Mundari", "Nagm")]
+
+
 def ranges(pred):
     out, start = [], None
     for cp in range(0x110000):
@@ -87,7 +120,45 @@ def main():
         alpha_re = regex.compile(r"\p{Alphabetic}")
         A = ranges(lambda cp: unicodedata.category(chr(cp)) not in ("Cn", "Cs") and alpha_re.match(chr(cp)) is not None)
         emit(f, "JTK_UC_ALPHA", A)
-    print("wrote %s: %d L ranges, %d N ranges, %d category ranges, %d Alphabetic ranges" % (OUT, len(L), len(N), len(triples), len(A)))
+        # Unicode scripts (java.util.regex \\p{IsHan}, \\p{script=Han}, \\p{sc=Hani}; Character.UnicodeScript): from the `regex` module,
+        # restricted to the code points this Unicode version has assigned; (lo, hi, script index) triples + the names (long name, ISO 15924 code)
+        every = "".join(chr(cp) for cp in range(0x110000) if not 0xD800 <= cp <= 0xDFFF and unicodedata.category(chr(cp)) != "Cn")
+        striples, snames = [], []
+        for long_name, code in SCRIPTS:
+            try:
+                rx = regex.compile(r"\p{Script=%s}+" % long_name)
+            except regex.error:
+                continue
+            rs = [(ord(m.group()[0]), ord(m.group()[-1])) for m in rx.finditer(every)]
+            # (runs of `every` skip unassigned code points: split a run wherever the code points are not consecutive)
+            fixed = []
+            for m in rx.finditer(every):
+                run = m.group()
+                lo = prev = ord(run[0])
+                for ch in run[1:]:
+                    c = ord(ch)
+                    if c != prev + 1:
+                        fixed.append((lo, prev))
+                        lo = c
+                    prev = c
+                fixed.append((lo, prev))
+            if not fixed:
+                continue
+            si = len(snames)
+            snames.append((long_name, code))
+            striples += [(lo, hi, si) for lo, hi in fixed]
+        striples.sort()
+        f.write("/* Unicode scripts: JTK_UC_SCRIPT_NAMES[index] = \"LONG_NAME Code\" */\n")
+        f.write("static const char *const JTK_UC_SCRIPT_NAMES[] = {\n")
+        for i in range(0, len(snames), 6):
+            f.write("  " + " ".join('"%s %s",' % (n.upper(), c) for n, c in snames[i:i + 6]) + "\n")
+        f.write("};\nstatic const int JTK_UC_SCRIPT_NAME_COUNT = %d;\n" % len(snames))
+        f.write("static const uint32_t JTK_UC_SCRIPT[][3] = {\n")
+        for i in range(0, len(striples), 5):
+            f.write("  " + " ".join("{0x%X,0x%X,%d}," % t for t in striples[i:i + 5]) + "\n")
+        f.write("};\nstatic const int JTK_UC_SCRIPT_COUNT = %d;\n\n" % len(striples))
+    print("wrote %s: %d L ranges, %d N ranges, %d category ranges, %d Alphabetic ranges, %d script ranges of %d scripts" %
+          (OUT, len(L), len(N), len(triples), len(A), len(striples), len(snames)))
 
 
 if __name__ == "__main__":

@@ -53,7 +53,14 @@ struct parser {
 	}
 
 	int finish_set(set_builder &b) {
-		/* case-insensitive: close the ranges under ASCII case folding (+ U+017F / U+212A with UNICODE_CASE) */
+		fold_case(b);
+		if (failed()) return 0;
+		b.ranges.insert(b.ranges.end(), b.prop_ranges.begin(), b.prop_ranges.end());
+		return emit_set(b);
+	}
+
+	/* case-insensitive: close the literal ranges under ASCII case folding (+ U+017F / U+212A with UNICODE_CASE) */
+	void fold_case(set_builder &b) {
 		const bool ucase = (flags & (JTK_RE_UNICODE_CASE | JTK_RE_UNICODE_CHARACTER_CLASS)) != 0;
 		if (b.ci) {
 			std::vector<std::pair<uint32_t, uint32_t>> extra;
@@ -74,12 +81,62 @@ struct parser {
 				}
 				if (ucase && r.second >= 0x80 && !(r.first == r.second && (r.first == 0x17F || r.first == 0x212A))) {
 					fail("UNICODE_CASE matching of non-ASCII characters is not supported");
-					return 0;
+					return;
 				}
 			}
 			b.ranges.insert(b.ranges.end(), extra.begin(), extra.end());
+			b.ci = false; /* (folded) */
 		}
-		b.ranges.insert(b.ranges.end(), b.prop_ranges.begin(), b.prop_ranges.end());
+	}
+
+	typedef std::vector<std::pair<uint32_t, uint32_t>> rlist;
+	static rlist norm(rlist v) { /* sorted, disjoint, adjacent ranges joined */
+		std::sort(v.begin(), v.end());
+		rlist m;
+		for (auto &r : v) {
+			if (!m.empty() && r.first <= m.back().second + 1) m.back().second = std::max(m.back().second, r.second);
+			else m.push_back(r);
+		}
+		return m;
+	}
+	static rlist complement(const rlist &v) {
+		rlist out;
+		add_ranges(out, norm(v), true);
+		return out;
+	}
+	static rlist intersect(const rlist &a0, const rlist &b0) {
+		const rlist a = norm(a0), b = norm(b0);
+		rlist out;
+		size_t i = 0, j = 0;
+		while (i < a.size() && j < b.size()) {
+			const uint32_t lo = std::max(a[i].first, b[j].first), hi = std::min(a[i].second, b[j].second);
+			if (lo <= hi) out.emplace_back(lo, hi);
+			if (a[i].second < b[j].second) i++;
+			else j++;
+		}
+		return out;
+	}
+	/* every code point the class accepts, as explicit ranges (case folding, property flags and the negation applied): what nested
+	 * classes and intersections are computed on */
+	rlist materialise(set_builder b) {
+		fold_case(b);
+		rlist r = b.ranges;
+		r.insert(r.end(), b.prop_ranges.begin(), b.prop_ranges.end());
+		const rlist L = table_ranges(JTK_UC_L, JTK_UC_L_COUNT), N = table_ranges(JTK_UC_N, JTK_UC_N_COUNT), S = table_ranges(JTK_UC_WS, JTK_UC_WS_COUNT);
+		auto add = [&](const rlist &t, bool neg) { add_ranges(r, t, neg); };
+		if (b.flags & JTK_RX_HAS_L) add(L, false);
+		if (b.flags & JTK_RX_HAS_N) add(N, false);
+		if (b.flags & JTK_RX_HAS_S) add(S, false);
+		if (b.flags & JTK_RX_HAS_NOT_L) add(L, true);
+		if (b.flags & JTK_RX_HAS_NOT_N) add(N, true);
+		if (b.flags & JTK_RX_HAS_NOT_S) add(S, true);
+		if (b.dot) r = complement({{'\n', '\n'}, {'\r', '\r'}, {0x85, 0x85}, {0x2028, 0x2029}});
+		r = norm(r);
+		return b.neg ? complement(r) : r;
+	}
+
+	/* the jtk_rx_set of a builder whose ranges are final */
+	int emit_set(set_builder &b) {
 		std::sort(b.ranges.begin(), b.ranges.end());
 		std::vector<std::pair<uint32_t, uint32_t>> merged;
 		for (auto &r : b.ranges) {
@@ -353,11 +410,23 @@ struct parser {
 		return nd;
 	}
 
-	std::unique_ptr<node> parse_class(bool ci) {
+	/* after '[': the class up to its ']' (nested classes [a[b-d]] are members of the union, && intersects what stands on either side,
+	 * a leading ^ negates the whole).  Classes without nesting and intersection keep their items as they are. */
+	set_builder parse_class_body(bool ci) {
 		set_builder b;
 		b.ci = ci;
-		if (eat('^')) b.neg = true;
-		bool first = true;
+		const bool neg = eat('^');
+		bool first = true, complex = false, have_acc = false;
+		rlist acc, nested; /* intersection of the operands so far; nested classes of the current operand */
+		auto close_operand = [&]() {
+			rlist op = materialise(b);
+			op.insert(op.end(), nested.begin(), nested.end());
+			acc = have_acc ? intersect(acc, op) : norm(op);
+			have_acc = true;
+			b = set_builder();
+			b.ci = ci;
+			nested.clear();
+		};
 		for (;;) {
 			int c = peek();
 			if (c < 0) {
@@ -370,12 +439,19 @@ struct parser {
 			}
 			first = false;
 			if (c == '[') {
-				fail("nested character classes are not supported");
-				break;
+				i++;
+				set_builder in = parse_class_body(ci);
+				if (failed()) break;
+				const rlist m = materialise(in);
+				nested.insert(nested.end(), m.begin(), m.end());
+				complex = true;
+				continue;
 			}
 			if (c == '&' && i + 1 < p.size() && p[i + 1] == '&') {
-				fail("class intersection is not supported");
-				break;
+				i += 2;
+				close_operand();
+				complex = true;
+				continue;
 			}
 			i++;
 			int lit = c;
@@ -400,6 +476,19 @@ struct parser {
 				b.ranges.emplace_back((uint32_t) lit, (uint32_t) lit);
 			}
 		}
+		if (!complex || failed()) {
+			b.neg = neg;
+			return b;
+		}
+		close_operand();
+		set_builder out_b;
+		out_b.prop_ranges = acc; /* final: no further case folding */
+		out_b.neg = neg;
+		return out_b;
+	}
+
+	std::unique_ptr<node> parse_class(bool ci) {
+		set_builder b = parse_class_body(ci);
 		return set_node(b);
 	}
 

@@ -105,6 +105,9 @@ typedef struct node {
 	int nranges, ncls;
 	uint32_t (*ranges)[2];
 	cls_item *cls;
+	int nnest;             /* N_SET: nested classes [a[b-d]] - members of the union, each with its own negation */
+	struct node **nest;
+	struct node *and_next; /* N_SET: the next operand of an intersection [..&&..] (the negation of the whole class sits on the first) */
 	/* N_CAT / N_ALT */
 	int nkids;
 	struct node **kids;
@@ -361,7 +364,8 @@ static int parse_escape(parser *ps, node *set, int *lit) {
 }
 
 static node *parse_class(parser *ps, int ci) {
-	node *set = new_node(ps, N_SET);
+	node *top = new_node(ps, N_SET);
+	node *set = top; /* the operand that currently collects items */
 	set->ci = ci;
 	if (eat(ps, '^')) set->neg = 1;
 	int first = 1;
@@ -369,7 +373,7 @@ static node *parse_class(parser *ps, int ci) {
 		int c = peek(ps);
 		if (c < 0) {
 			fail(ps, "unterminated character class");
-			return set;
+			return top;
 		}
 		if (c == ']' && !first) {
 			ps->i++;
@@ -377,17 +381,25 @@ static node *parse_class(parser *ps, int ci) {
 		}
 		first = 0;
 		int lit = -1;
-		if (c == '[') {
-			fail(ps, "nested character classes are not supported");
-			return set;
+		if (c == '[') { /* nested class: a member of the union */
+			ps->i++;
+			node *in = parse_class(ps, ci);
+			if (ps->failed) return top;
+			set->nest = (node **) realloc(set->nest, sizeof(node *) * (size_t) (set->nnest + 1));
+			set->nest[set->nnest++] = in;
+			continue;
 		}
-		if (c == '&' && ps->i + 1 < ps->n && ps->p[ps->i + 1] == '&') {
-			fail(ps, "class intersection is not supported");
-			return set;
+		if (c == '&' && ps->i + 1 < ps->n && ps->p[ps->i + 1] == '&') { /* intersection: what follows is the next operand */
+			ps->i += 2;
+			node *op = new_node(ps, N_SET);
+			op->ci = ci;
+			set->and_next = op;
+			set = op;
+			continue;
 		}
 		ps->i++;
 		if (c == '\\') {
-			if (!parse_escape(ps, set, &lit)) return set;
+			if (!parse_escape(ps, set, &lit)) return top;
 			if (lit < 0) continue; /* class item added */
 		} else {
 			lit = c;
@@ -399,23 +411,23 @@ static node *parse_class(parser *ps, int ci) {
 			ps->i++;
 			if (hi == '\\') {
 				int l2 = -1;
-				if (!parse_escape(ps, set, &l2)) return set;
+				if (!parse_escape(ps, set, &l2)) return top;
 				if (l2 < 0) {
 					fail(ps, "bad range end in character class");
-					return set;
+					return top;
 				}
 				hi = l2;
 			}
 			if (hi < lit) {
 				fail(ps, "illegal character range");
-				return set;
+				return top;
 			}
 			add_range(set, (uint32_t) lit, (uint32_t) hi);
 		} else {
 			add_range(set, (uint32_t) lit, (uint32_t) lit);
 		}
 	}
-	return set;
+	return top;
 }
 
 static node *parse_atom(parser *ps, int *ci) {
@@ -706,6 +718,7 @@ void jo_regex_free(jo_regex *re) {
 	for (int i = 0; i < re->nall; i++) {
 		free(re->all[i]->ranges);
 		free(re->all[i]->cls);
+		free(re->all[i]->nest);
 		free(re->all[i]->kids);
 		free(re->all[i]);
 	}
@@ -758,7 +771,9 @@ static int set_match_one(const node *nd, uint32_t cp, int ucc) {
 /* Case-insensitive comparison as java.util.regex does it for single characters: ASCII letters fold
  * onto each other; with UNICODE_CASE, Character.toLowerCase(Character.toUpperCase(c)) additionally
  * folds U+017F (long s) onto s and U+212A (Kelvin sign) onto k. */
-static int set_match(const mctx *m, const node *nd, uint32_t cp) {
+static int set_match(const mctx *m, const node *nd, uint32_t cp);
+/* one operand of a class: its own items (with case folding) or any nested class */
+static int operand_match(const mctx *m, const node *nd, uint32_t cp) {
 	int ucc = (m->re->flags & JO_RE_UNICODE_CHARACTER_CLASS) != 0;
 	int r = set_match_one(nd, cp, ucc);
 	if (!r && nd->ci) {
@@ -771,6 +786,13 @@ static int set_match(const mctx *m, const node *nd, uint32_t cp) {
 			else if (cp == 'k' || cp == 'K') r = set_match_one(nd, 0x212A, ucc);
 		}
 	}
+	for (int i = 0; i < nd->nnest && !r; i++) r = set_match(m, nd->nest[i], cp);
+	return r;
+}
+/* the class: every operand of the intersection chain must accept the character; the negation applies to the whole */
+static int set_match(const mctx *m, const node *nd, uint32_t cp) {
+	int r = 1;
+	for (const node *op = nd; op && r; op = op->and_next) r = operand_match(m, op, cp);
 	return r != nd->neg;
 }
 

@@ -105,6 +105,9 @@ GENERAL_PATTERNS = [
     (r"(?<word>\w+)|(?<sp>\s+)|.", 0), (r"\Aab|\w+\z|\w+|\W", 0), (r"\w+\Z|\w+|\W", 0), (r"\Qa.b\E+|\w+|.", 0), (r"\h+|\v+|\H", 0),
     (r"(?<=\d)[a-z]+|(?<![a-z])\d+|.", 0), (r"\p{IsHan}+|\p{script=Cyrillic}+|\p{sc=Latn}+|\P{IsHiragana}", 0),
     (r"(?<!\p{L})\p{L}{1,3}|.", 0x100), (r"[\p{IsGreek}\p{IsHangul}]+|\p{IsCommon}|.", 0),
+    # nested classes and class intersection
+    (r"[a-z&&[^aeiou]]+|[aeiou]+|.", 0), (r"[\p{L}&&[^\p{IsHan}]]+|\p{IsHan}|.", 0), (r"[a-c[x-z]]+|[^a[0-9]]|.", 0), (r"[^\w&&[^_]]+|.", 0),
+    (r"[a-z&&b-y&&[^m]]+|.", 0), (r"(?i)[a-f&&[^c]]+|\s+|.", 0),
 ]
 
 

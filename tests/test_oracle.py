@@ -217,3 +217,27 @@ def test_oracle_groups_anchors_scripts_and_look_behind_against_the_regex_module(
                 boff.append(boff[-1] + len(ch.encode()))
             exp = [(boff[m.start()], boff[m.end()]) for m in r.finditer(t) if m.end() > m.start()]
             assert [(a, e) for a, e in o.split(t.encode()) if e > a] == exp, (pat, t)
+
+
+def test_oracle_nested_classes_and_intersections_against_the_regex_module():
+    """[a[b-d]] (union), [a-z&&[^aeiou]] (intersection, subtraction), a leading ^ over the whole: against the `regex` module's V1 set
+    operations (which want every operand bracketed)."""
+    import random
+    import regex
+    from oracle import jo
+    dot = "[^\\n\\r\\x85\\u2028\\u2029]"
+    pats = [(r"[a-z&&[^aeiou]]+|[aeiou]+|.", r"[[a-z]&&[^aeiou]]+|[aeiou]+|.", True), (r"[\p{L}&&[^\p{IsHan}]]+|\p{IsHan}|.", r"[\p{L}&&[^\p{Han}]]+|\p{Han}|.", True),
+            (r"[a-c[x-z]]+|[^a[0-9]]|.", r"[a-cx-z]+|[^a0-9]|.", True), (r"[^\w&&[^_]]+|.", r"[^\w&&[^_]]+|.", False),
+            (r"[a-z&&b-y&&[^m]]+|.", r"[[a-z]&&[b-y]&&[^m]]+|.", True)]
+    alph = list("abcmxyzXYZ 019_-+$.,;!?'") + ["é", "ß", "Ж", "я", "中", "国", "あ", "カ", "१"]
+    rng = random.Random(6)
+    for pat, rpat, uni in pats:
+        o = jo.OracleEncoding("t", pat, 0, {bytes([b]): b for b in range(256)}, {})
+        r = regex.compile(rpat[:-1] + dot, regex.V1 | (regex.UNICODE if uni else regex.ASCII))
+        for _ in range(300):
+            t = "".join(rng.choice(alph) for _ in range(rng.randint(0, 24)))
+            boff = [0]
+            for ch in t:
+                boff.append(boff[-1] + len(ch.encode()))
+            exp = [(boff[m.start()], boff[m.end()]) for m in r.finditer(t) if m.end() > m.start()]
+            assert [(a, e) for a, e in o.split(t.encode()) if e > a] == exp, (pat, t)

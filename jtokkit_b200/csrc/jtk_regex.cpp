@@ -375,7 +375,9 @@ struct parser {
 						script_only = pre[0] == 's';
 						break;
 					}
-				const uint32_t mask = script_only ? 0u : gc_mask_of(nm);
+				uint32_t mask = script_only ? 0u : gc_mask_of(nm);
+				/* CharPredicates.forProperty(name, caseIns) of JDK 9+: under CASE_INSENSITIVE Lu, Ll and Lt each stand for all three */
+				if (b.ci && (mask == 1u || mask == 2u || mask == 4u)) mask = 7u;
 				if (script_only) { /* \p{script=Han}, \p{sc=Hani} (Character.UnicodeScript.forName: long name or ISO 15924 code, any case) */
 					if (!add_script(b.prop_ranges, nm, neg)) fail("unknown script in \\p{...}");
 				} else if (mask) add_gc(b.prop_ranges, mask, neg);

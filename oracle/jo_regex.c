@@ -328,7 +328,9 @@ static int parse_escape(parser *ps, node *set, int *lit) {
 				set->cls[set->ncls - 1].mask = (uint32_t) si;
 				return 1;
 			}
-			const uint32_t mask = gc_mask_of(nm);
+			uint32_t mask = gc_mask_of(nm);
+			/* JDK 9+ (CharPredicates.forProperty(name, caseIns)): with CASE_INSENSITIVE each of Lu, Ll, Lt means all cased letters */
+			if (set->ci && (mask == 1u || mask == 2u || mask == 4u)) mask = 7u;
 			const int ucc = (ps->flags & JO_RE_UNICODE_CHARACTER_CLASS) != 0;
 			if (mask) add_gc_cls(set, mask, neg);
 			else if (!strcmp(nm, "Alphabetic") || (ucc && !strcmp(nm, "Alpha"))) add_cls(set, C_ALPHA, neg);

@@ -108,6 +108,8 @@ GENERAL_PATTERNS = [
     # nested classes and class intersection
     (r"[a-z&&[^aeiou]]+|[aeiou]+|.", 0), (r"[\p{L}&&[^\p{IsHan}]]+|\p{IsHan}|.", 0), (r"[a-c[x-z]]+|[^a[0-9]]|.", 0), (r"[^\w&&[^_]]+|.", 0),
     (r"[a-z&&b-y&&[^m]]+|.", 0), (r"(?i)[a-f&&[^c]]+|\s+|.", 0),
+    # CASE_INSENSITIVE and the cased-letter categories (JDK 9+: Lu, Ll, Lt each stand for all three)
+    (r"\p{Lu}+|\P{L}+|.", 2), (r"(?i:\p{Ll})+|\p{Lu}|[\P{Lt}&&[^\s]]", 0),
 ]
 
 

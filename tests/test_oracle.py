@@ -241,3 +241,22 @@ def test_oracle_nested_classes_and_intersections_against_the_regex_module():
                 boff.append(boff[-1] + len(ch.encode()))
             exp = [(boff[m.start()], boff[m.end()]) for m in r.finditer(t) if m.end() > m.start()]
             assert [(a, e) for a, e in o.split(t.encode()) if e > a] == exp, (pat, t)
+
+
+def test_o200k_pattern_as_a_custom_pattern_vs_tiktoken():
+    """The o200k_base split pattern (tiktoken_ext/openai_public.py), registered as a custom pattern over the cl100k vocabulary: the oracle's
+    matcher against tiktoken's (fancy-regex) on the same pattern string and ranks."""
+    tiktoken = pytest.importorskip("tiktoken")
+    from tiktoken.load import load_tiktoken_bpe
+    from oracle import jo
+    pat = "|".join([r"[^\r\n\p{L}\p{N}]?[\p{Lu}\p{Lt}\p{Lm}\p{Lo}\p{M}]*[\p{Ll}\p{Lm}\p{Lo}\p{M}]+(?i:'s|'t|'re|'ve|'m|'ll|'d)?",
+                    r"[^\r\n\p{L}\p{N}]?[\p{Lu}\p{Lt}\p{Lm}\p{Lo}\p{M}]+[\p{Ll}\p{Lm}\p{Lo}\p{M}]*(?i:'s|'t|'re|'ve|'m|'ll|'d)?",
+                    r"\p{N}{1,3}", r" ?[^\s\p{L}\p{N}]+[\r\n/]*", r"\s*[\r\n]+", r"\s+(?!\S)", r"\s+"])
+    ranks = load_tiktoken_bpe(os.path.join(jo.DATA, jo.BUILTIN["cl100k_base"][1]))
+    tk = tiktoken.Encoding("o200k_pat", pat_str=pat, mergeable_ranks=ranks, special_tokens={})
+    o = jo.OracleEncoding("o200k_pat", pat, 0x100, ranks, {})
+    rng = random.Random(11)
+    alph = [c for c in ALPH if c != "ſ"] + ["A", "B", "Z", "É", "Ö", "ǅ", "ʰ", "/"]  # (U+017F: the engines disagree on (?i) long s, as for cl100k)
+    for _ in range(4000):
+        s = "".join(rng.choice(alph) for _ in range(rng.randint(0, 40)))
+        assert o.encode_ordinary(s) == tk.encode_ordinary(s), s

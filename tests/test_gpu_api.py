@@ -62,7 +62,7 @@ def test_registry_registration(registry):
         enc.encode("a test")
     # constructs outside the compiler's subset fail at registration, nothing falls back to the CPU
     with pytest.raises(ValueError):
-        registry.register_gpt_byte_pair_encoding(jt.GptBytePairEncodingParams("lookbehind", jt.Pattern.compile("(?<=a)b"), {}, {}))
+        registry.register_gpt_byte_pair_encoding(jt.GptBytePairEncodingParams("lookbehind", jt.Pattern.compile("(?<=ab)c"), {}, {}))
 
 
 def test_default_registry_is_eager():

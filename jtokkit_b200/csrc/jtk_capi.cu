@@ -198,7 +198,7 @@ static int init_device(jtk_encoding *e, int device) {
 	const size_t o_deck = ar.add(h.dec_keys), o_decb = ar.add(h.dec_bytes), o_deco = ar.add(h.dec_off);
 	const size_t o_decd = ar.add(h.dec_direct);
 	const size_t o_rxi = ar.add(h.rx_inst), o_rxs = ar.add(h.rx_sets), o_rxr = ar.add(h.rx_ranges), o_spi = ar.add(h.special_ids);
-	const size_t o_dft = ar.add(h.rx_dfa_trans), o_df1 = ar.add(h.rx_dfa_stage1), o_df2 = ar.add(h.rx_dfa_stage2);
+	const size_t o_dft = ar.add(h.rx_dfa_trans), o_df1 = ar.add(h.rx_dfa_stage1), o_df2 = ar.add(h.rx_dfa_stage2), o_dfs = ar.add(h.rx_dfa_stay);
 	uint8_t *base = nullptr;
 	CUDA_TRY(cudaMalloc(&base, ar.total));
 	ds->allocs.push_back(base);
@@ -236,6 +236,7 @@ static int init_device(jtk_encoding *e, int device) {
 	T.rx_dfa_trans = h.rx_dfa_trans.empty() ? nullptr : reinterpret_cast<const uint16_t *>(base + o_dft);
 	T.rx_dfa_stage1 = reinterpret_cast<const uint16_t *>(base + o_df1);
 	T.rx_dfa_stage2 = base + o_df2;
+	T.rx_dfa_stay = h.rx_dfa_stay.empty() ? nullptr : base + o_dfs;
 	T.rx_dfa_nsym = h.rx_dfa_nsym;
 	T.rx_dfa_nstates = h.rx_dfa_nstates;
 	T.rx_dfa_start = h.rx_dfa_start;

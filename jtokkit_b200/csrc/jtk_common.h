@@ -164,6 +164,7 @@ struct jtk_tables {
 	const uint16_t *rx_dfa_trans;
 	const uint16_t *rx_dfa_stage1;
 	const uint8_t *rx_dfa_stage2;
+	const uint8_t *rx_dfa_stay; /* nstates x 128 run codes (jtk_regex_compile.h), or null */
 	int32_t rx_dfa_nsym, rx_dfa_nstates, rx_dfa_start, rx_dfa_start_bol, rx_dfa_acc_lo;
 };
 

@@ -294,6 +294,20 @@ bool jtk_rx_build_dfa(const jtk_rx_compiled &prog, const jtk_tables &view, jtk_r
 	out->acc_lo = acc >= 0 ? nstates - 1 : nstates;
 	out->nstates = nstates;
 	out->nsym = nsym;
+	/* ---- runs: what an ASCII byte does in a state, for the sequential passes that step over long runs four bytes at a time ---- */
+	out->stay.clear();
+	if (nstates <= 256) {
+		out->stay.assign((size_t) nstates * 128, 0);
+		for (int s = 1; s < nstates; s++)
+			for (int b = 0; b < 128; b++) {
+				const uint16_t t = out->trans[(size_t) s * (size_t) nsym + cls[(size_t) b]];
+				const int ns = t & 0x7FFF, mb = t >> 15;
+				uint8_t code = 0;
+				if (ns == s && s < out->acc_lo) code = mb ? 2 : 1;
+				else if (s == out->start && ns == 0 && !mb) code = 3;
+				out->stay[(size_t) s * 128 + (size_t) b] = code;
+			}
+	}
 	/* ---- class lookup: ASCII directly, the rest through a two-level table with shared blocks ---- */
 	out->stage1.assign(0x200000 >> 8, 0);
 	out->stage2.clear();

@@ -74,6 +74,7 @@ struct jtk_rx_program {
 	const uint16_t *dfa_stage1; /* code point >> 8 -> block */
 	const uint8_t *dfa_stage2;  /* block * 256 + (code point & 255) -> class */
 	const uint8_t *dfa_ascii;   /* the block of U+0000..U+00FF */
+	const uint8_t *dfa_stay;    /* run codes per (state, ASCII byte), null: runs are matched character by character (jtk_rx_chain_dfa) */
 	int32_t dfa_nsym, dfa_start, dfa_start_bol, dfa_acc_lo;
 };
 
@@ -88,6 +89,7 @@ JTK_HD jtk_rx_program jtk_rx_program_of(const jtk_tables &T) {
 	P.dfa_stage1 = T.rx_dfa_stage1;
 	P.dfa_stage2 = T.rx_dfa_stage2;
 	P.dfa_ascii = T.rx_dfa_trans ? T.rx_dfa_stage2 + ((size_t) T.rx_dfa_stage1[0] << 8) : nullptr;
+	P.dfa_stay = T.rx_dfa_trans ? T.rx_dfa_stay : nullptr;
 	P.dfa_nsym = T.rx_dfa_nsym;
 	P.dfa_start = T.rx_dfa_start;
 	P.dfa_start_bol = T.rx_dfa_start_bol;
@@ -569,6 +571,29 @@ JTK_HD int64_t jtk_rx_chain_dfa(const jtk_rx_program &P, const uint8_t *s, int64
 	jtk_rx_window win;
 	win.idx = -2; /* (neither this word nor the one before it) */
 	for (;;) {
+		/* ---- runs, four ASCII bytes at a time (sequential passes only: P.dfa_stay is null in the slice kernel): a state that loops on
+		 * all four bytes swallows them; at the start of an attempt, four bytes on each of which the attempt dies at once are stepped
+		 * over.  Exactly what four single steps would do, well clear of the end of the view. ---- */
+		if (P.dfa_stay && pos + 8 <= view) {
+			const uint32_t x4 = jtk_rx_fetch4(s, pos, hi, win);
+			if ((x4 & 0x80808080u) == 0) {
+				const uint8_t *row = P.dfa_stay + state * 128u;
+				const uint32_t c = row[x4 & 0x7Fu];
+				if (c && c == row[(x4 >> 8) & 0x7Fu] && c == row[(x4 >> 16) & 0x7Fu] && c == row[x4 >> 24]) {
+					if (c != 3) {
+						if (pos == stp) len0 = 1;
+						if (c == 2) last = pos + 3; /* a match ends before each of the four; the last one counts */
+						pos += 4;
+						continue;
+					}
+					if (pos == stp && state == (uint32_t) P.dfa_start && stp != lo) { /* nothing can begin at these four positions */
+						stp += 4;
+						pos = stp;
+						continue;
+					}
+				}
+			}
+		}
 		/* ---- one character, one transition ---- */
 		uint32_t sym = nsym - 1; /* end of the (visible) text */
 		int len = 1;

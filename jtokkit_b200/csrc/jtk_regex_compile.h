@@ -27,6 +27,8 @@ struct jtk_rx_dfa_host {
 	int acc_lo = 0;              /* states >= acc_lo hold nothing but MATCH: the run ends there without another read */
 	std::vector<uint16_t> stage1; /* (code point >> 8) -> block, 8192 entries (four-byte sequences reach 0x1FFFFF) */
 	std::vector<uint8_t> stage2;  /* block * 256 + (code point & 255) -> class */
+	std::vector<uint8_t> stay;    /* nstates x 128 (empty above 256 states): what an ASCII byte does in a state - 1: the state loops on it, 2: loops and a
+	                               * match ends before it, 3 (row of `start` only): the attempt dies on it at once, 0: anything else */
 };
 
 /* view: a jtk_tables with cp_stage1 / cp_stage2 set (what jtk_rx_in_set reads).  False with *why when the program has no DFA form. */

@@ -258,6 +258,7 @@ int jtk_build_host_tables(const jtk_params *p, jtk_host_tables *t, std::string *
 			t->rx_dfa_trans = std::move(dfa.trans);
 			t->rx_dfa_stage1 = std::move(dfa.stage1);
 			t->rx_dfa_stage2 = std::move(dfa.stage2);
+			t->rx_dfa_stay = std::move(dfa.stay);
 			t->rx_dfa_nsym = dfa.nsym;
 			t->rx_dfa_nstates = dfa.nstates;
 			t->rx_dfa_start = dfa.start;
@@ -552,6 +553,7 @@ jtk_tables jtk_host_view(const jtk_host_tables &h) {
 	v.rx_dfa_trans = h.rx_dfa_trans.empty() ? nullptr : h.rx_dfa_trans.data();
 	v.rx_dfa_stage1 = h.rx_dfa_stage1.data();
 	v.rx_dfa_stage2 = h.rx_dfa_stage2.data();
+	v.rx_dfa_stay = h.rx_dfa_stay.empty() ? nullptr : h.rx_dfa_stay.data();
 	v.rx_dfa_nsym = h.rx_dfa_nsym;
 	v.rx_dfa_nstates = h.rx_dfa_nstates;
 	v.rx_dfa_start = h.rx_dfa_start;

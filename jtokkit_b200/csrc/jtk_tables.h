@@ -55,7 +55,7 @@ struct jtk_host_tables {
 	uint32_t rx_first[8] = {~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u};
 	/* ... and its DFA (empty when the pattern has none; rx_dfa_why says what stood in the way) */
 	std::vector<uint16_t> rx_dfa_trans, rx_dfa_stage1;
-	std::vector<uint8_t> rx_dfa_stage2;
+	std::vector<uint8_t> rx_dfa_stage2, rx_dfa_stay;
 	int32_t rx_dfa_nsym = 0, rx_dfa_nstates = 0, rx_dfa_start = 0, rx_dfa_start_bol = 0, rx_dfa_acc_lo = 0;
 	std::string rx_dfa_why;
 	/* statistics (reported by DESIGN.md / tests) */

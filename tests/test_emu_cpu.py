@@ -180,6 +180,34 @@ def test_general_pattern_stack_overflow_is_reported():
         e2.general_split(text, off, stack_cap=64)
 
 
+def test_dfa_run_shortcuts_on_long_runs_and_gaps():
+    """The sequential DFA passes step over long ASCII runs four bytes at a time (a state that loops on all four; an attempt that dies at
+    once on each of four start positions): documents made of long runs, long gaps and their borders at every alignment, against the
+    oracle and against the backtracking program."""
+    import emu
+    from oracle import jo
+    jo.build()
+    rng = random.Random(9)
+    pats = [(r"[a-z]+|\d{1,3}", 0), (r"\w+|\s+", 0), (r"a+b|a", 0), (r"x*", 0), (r"[a-z]+(?![a-z!])|\s+(?!\S)|\s", 0), (r"^[a-z]+|[0-9]++|!{2,5}", 0),
+            (r"(?i:[a-c]+)z|[a-z]", 0), (r"\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+", 0x100)]
+    units = ["a" * 3, "a" * 9, "a" * 70, "abc" * 30, "!" * 5, "!" * 40, "!" * 131, " " * 17, " " * 64, "123456789" * 7, "x", "b", "z", "é", "中" * 12, "\n", "aB" * 20, "Z" * 33]
+    for pat, flags in pats:
+        e = emu.EmuEncoding("g", pat, flags, {b"a": 0}, {})
+        assert e.dfa_info()[0] > 0
+        o = jo.OracleEncoding("g", pat, flags, {b"a": 0}, {})
+        for it in range(60):
+            docs = []
+            for _ in range(rng.randint(1, 3)):
+                docs.append(("".join(rng.choice(units) for _ in range(rng.randint(1, 8))))[rng.randint(0, 3):].encode())
+            blob = b"".join(docs)
+            off = np.zeros(len(docs) + 1, dtype=np.int64)
+            off[1:] = np.cumsum([len(x) for x in docs])
+            exp_start, exp_skip = expected_piece_bits(o, docs, off, len(blob))
+            for no_dfa in (False, True):
+                start, skip = e.general_split(np.frombuffer(blob, dtype=np.uint8), off, no_dfa=no_dfa)
+                assert np.array_equal(start, exp_start) and np.array_equal(skip, exp_skip), (pat, docs, "vm" if no_dfa else "dfa")
+
+
 def test_flat_dfa_loop_decodes_utf8_like_the_bytewise_decoder():
     import ctypes as C
     import emu

@@ -840,11 +840,13 @@ __device__ __forceinline__ void rx_stage_dfa(jtk_rx_program &P, const jtk_tables
 	__syncthreads();
 }
 
-__global__ void __launch_bounds__(128) jtk_general_slice_kernel(const __grid_constant__ jtk_encode_args a) {
+#ifndef JTK_RX_SLICE_CTAS
+#define JTK_RX_SLICE_CTAS 8 /* resident CTAs per SM the slice kernel is compiled for (64 registers) */
+#endif
+__global__ void __launch_bounds__(128, JTK_RX_SLICE_CTAS) jtk_general_slice_kernel(const __grid_constant__ jtk_encode_args a) {
 	__shared__ uint16_t s_trans[RX_DFA_SMEM];
 	__shared__ uint8_t s_ascii[256];
 	jtk_rx_program P = jtk_rx_program_of(a.T);
-	P.dfa_stay = nullptr; /* (the run shortcut pays in the sequential pass; here it would only add instructions to every lane's loop) */
 	rx_stage_dfa(P, a.T, s_trans, s_ascii);
 	const jtk_rx_split_buffers B = rx_buffers(a);
 	/* eight times the threads of the per-document pass on the same stack memory: what overflows a small stack is redone there */

@@ -571,7 +571,7 @@ JTK_HD int64_t jtk_rx_chain_dfa(const jtk_rx_program &P, const uint8_t *s, int64
 	jtk_rx_window win;
 	win.idx = -2; /* (neither this word nor the one before it) */
 	for (;;) {
-		/* ---- runs, four ASCII bytes at a time (sequential passes only: P.dfa_stay is null in the slice kernel): a state that loops on
+		/* ---- runs, four ASCII bytes at a time (sequential runs only: the speculative runs of the slice pass switch it off): a state that loops on
 		 * all four bytes swallows them; at the start of an attempt, four bytes on each of which the attempt dies at once are stepped
 		 * over.  Exactly what four single steps would do, well clear of the end of the view. ---- */
 		if (P.dfa_stay && pos + 8 <= view) {
@@ -721,7 +721,9 @@ JTK_HD bool jtk_rx_slice_pass(const jtk_rx_program &P, const jtk_tables &T, cons
 	B.join[slice] = s1;
 	if (ndocs > 0 && doc_off[d] < s0 && doc_off[d + 1] > s0) { /* the slice starts inside document d */
 		const int64_t lo = doc_off[d], hi = doc_off[d + 1], end_run = hi < s1 ? hi : s1;
-		const int64_t e = jtk_rx_chain(P, T, s, lo, hi, s0, end_run, JTK_RX_SPEC_LIMIT, B.s_ms, B.s_me, B.s_from, nullptr, &cms, &cme, &joined, st, cap, &overflow, bor);
+		jtk_rx_program Ps = P;
+		Ps.dfa_stay = nullptr; /* (all lanes of a warp run this loop side by side: the run shortcut would only add instructions to it) */
+		const int64_t e = jtk_rx_chain(Ps, T, s, lo, hi, s0, end_run, JTK_RX_SPEC_LIMIT, B.s_ms, B.s_me, B.s_from, nullptr, &cms, &cme, &joined, st, cap, &overflow, bor);
 		if (overflow) { /* only the true chain may condemn a document: this slice is simply matched again by pass 2 */
 			overflow = false;
 		} else {

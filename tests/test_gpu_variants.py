@@ -79,3 +79,32 @@ def test_development_switches_do_not_change_results():
     for env in [{"JTK_MEMO": "0"}, {"JTK_SIDE_STREAMS": "0"}, {"JTK_PIPELINE": "1"}, {"JTK_SUB_TILES": "256", "JTK_CHUNK_MB": "3"}, {"JTK_MEMO_LOG2": "16"},
                 {"JTK_PIPELINE": "1", "JTK_SUB_TILES": "128", "JTK_SPLIT_CTAS": "4"}]:
         assert run_variant(env) == base, env
+
+
+def test_dfa_switch_does_not_change_results():
+    """JTK_RX_DFA=0 keeps the backtracking program for a general pattern that has a DFA: same ids, offsets and statuses on the
+    multilingual corpus (the predefined cl100k string registered with CASE_INSENSITIVE, and a Unicode-category pattern)."""
+    import torch
+    import jtokkit_b200 as jt
+    from jtokkit_b200 import synth
+    p = jt.EncodingFactory.predefined_params(jt.EncodingType.CL100K_BASE)
+    data, off = synth.config3_multilingual(torch.device("cpu"), total=12 << 20, seed=21)
+    d, o = data.numpy(), off.numpy()
+    prev = os.environ.get("JTK_RX_DFA")
+    try:
+        for pat, flags in [(p.get_pattern().pattern(), 0x102), (r"\p{Lu}?\p{Ll}+|\p{N}{1,3}|\s+(?!\S)|\s+|[^\s\p{L}\p{N}]+", 0x100)]:
+            out = []
+            for sw in ("1", "0"):
+                os.environ["JTK_RX_DFA"] = sw
+                enc = jt.EncodingFactory.from_parameters(jt.GptBytePairEncodingParams("sw" + sw, jt.Pattern.compile(pat, flags), p.encoder, p.special_tokens_encoder))
+                res = enc.encode_packed(d, o, ordinary=True)
+                out.append((res.ids.copy(), res.token_offsets.copy(), res.doc_status.copy()))
+                res.close()
+                enc.close()
+            assert all(np.array_equal(a, b) for a, b in zip(out[0], out[1])), pat
+            assert out[0][0].size > 0 and not out[0][2].any()
+    finally:
+        if prev is None:
+            os.environ.pop("JTK_RX_DFA", None)
+        else:
+            os.environ["JTK_RX_DFA"] = prev

@@ -619,7 +619,24 @@ struct parser {
 				nd->min = nc == 'z';
 				return nd;
 			}
-			if (nc == 'G' || nc == 'R' || nc == 'X' || nc == 'Q' || nc == 'k' || (nc >= '1' && nc <= '9')) {
+			if (nc == 'R') { /* linebreak matcher: \r\n|[\n\x0B\f\r\x85\u2028\u2029] (the documented equivalence; JDK 9+ backtracks into it like that) */
+				i++;
+				auto crlf = std::make_unique<node>();
+				crlf->type = N_CAT;
+				for (uint32_t c2 : {(uint32_t) '\r', (uint32_t) '\n'}) {
+					set_builder b1;
+					b1.ranges.emplace_back(c2, c2);
+					crlf->kids.push_back(set_node(b1));
+				}
+				set_builder b2;
+				b2.ranges = {{0x0A, 0x0D}, {0x85, 0x85}, {0x2028, 0x2029}};
+				auto alt = std::make_unique<node>();
+				alt->type = N_ALT;
+				alt->kids.push_back(std::move(crlf));
+				alt->kids.push_back(set_node(b2));
+				return alt;
+			}
+			if (nc == 'G' || nc == 'X' || nc == 'Q' || nc == 'k' || (nc >= '1' && nc <= '9')) {
 				fail("unsupported escape (boundary / back-reference / quoting)");
 				return std::make_unique<node>();
 			}
@@ -793,8 +810,8 @@ struct parser {
 				fail("possessive quantifiers on groups are not supported");
 				break;
 			}
-			if (nd->min > 16 || nd->max > 16) {
-				fail("counted loops beyond 16 are not supported");
+			if (nd->min > 64 || nd->max > 64) {
+				fail("counted loops over groups beyond 64 are not supported");
 				break;
 			}
 			for (int k = 0; k < nd->min; k++) emit(sub);

@@ -14,11 +14,11 @@
  * Unicode properties: every general category (\p{Lu}, \p{IsLu}, \p{gc=Lu}, one-letter groups, LC), Alphabetic, White_Space and
  * the POSIX names Alpha / Digit / Space / ASCII; \d \D \w \W and \b \B in their ASCII and UNICODE_CHARACTER_CLASS meanings
  * (tables of Unicode 15.0, unicode_ranges.inc; \b as java.util.regex.Pattern.Bound of JDK 11-18 defines it).
- * Also: named groups (as plain groups), \A \Z \z, \Q..\E, \h \H \v \V, Unicode scripts (\p{IsHan}, \p{script=Han}, \p{sc=Hani}), look-behind
+ * Also: named groups (as plain groups), \A \Z \z, \Q..\E, \h \H \v \V, \R, Unicode scripts (\p{IsHan}, \p{script=Han}, \p{sc=Hani}), look-behind
  * over exactly one character ((?<=[set]) / (?<![set])), nested classes and class intersection ([a[b-d]], [a-z&&[^aeiou]]).
  * Not supported (registration fails with JTK_E_PATTERN_UNSUPPORTED, nothing falls back to the CPU): longer look-behind,
- * back-references, atomic groups, block properties, \G \R \X,
- * loops over sub-expressions that can match the empty string, counted loops over groups beyond 16.
+ * back-references, atomic groups, block properties, \G \X,
+ * loops over sub-expressions that can match the empty string, counted loops over groups beyond 64.
  */
 #ifndef JTK_REGEX_H
 #define JTK_REGEX_H

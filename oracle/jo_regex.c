@@ -537,7 +537,21 @@ static node *parse_atom(parser *ps, int *ci) {
 			e->min = nc == 'z';
 			return e;
 		}
-		if (nc == 'G' || nc == 'R' || nc == 'X' || nc == 'Q' || (nc >= '1' && nc <= '9') || nc == 'k') {
+		if (nc == 'R') { /* linebreak matcher = \r\n|[\n\x0B\f\r\x85\u2028\u2029] (Pattern javadoc; JDK 9+ matches it as that alternation) */
+			ps->i++;
+			node *alt = new_node(ps, N_ALT), *crlf = new_node(ps, N_CAT), *cr = new_node(ps, N_SET), *lf = new_node(ps, N_SET), *one = new_node(ps, N_SET);
+			add_range(cr, '\r', '\r');
+			add_range(lf, '\n', '\n');
+			add_kid(crlf, cr);
+			add_kid(crlf, lf);
+			add_range(one, 0x0A, 0x0D);
+			add_range(one, 0x85, 0x85);
+			add_range(one, 0x2028, 0x2029);
+			add_kid(alt, crlf);
+			add_kid(alt, one);
+			return alt;
+		}
+		if (nc == 'G' || nc == 'X' || nc == 'Q' || (nc >= '1' && nc <= '9') || nc == 'k') {
 			fail(ps, "unsupported escape (boundary / back-reference / quoting)");
 			return new_node(ps, N_EMPTY);
 		}

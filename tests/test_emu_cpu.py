@@ -110,6 +110,7 @@ GENERAL_PATTERNS = [
     (r"[a-z&&b-y&&[^m]]+|.", 0), (r"(?i)[a-f&&[^c]]+|\s+|.", 0),
     # CASE_INSENSITIVE and the cased-letter categories (JDK 9+: Lu, Ll, Lt each stand for all three)
     (r"\p{Lu}+|\P{L}+|.", 2), (r"(?i:\p{Ll})+|\p{Lu}|[\P{Lt}&&[^\s]]", 0),
+    (r"\R+|\w+|[^\w\r\n]", 0), (r"(?:ab){20}c|(?:[a-c]\d){3,40}|.", 0),
     # split patterns of other tokenizers a JTokkit user may register: o200k_base (as tiktoken publishes it) and a DeepSeek-style one
     (r"[^\r\n\p{L}\p{N}]?[\p{Lu}\p{Lt}\p{Lm}\p{Lo}\p{M}]*[\p{Ll}\p{Lm}\p{Lo}\p{M}]+(?i:'s|'t|'re|'ve|'m|'ll|'d)?|[^\r\n\p{L}\p{N}]?[\p{Lu}\p{Lt}\p{Lm}\p{Lo}\p{M}]+[\p{Ll}\p{Lm}\p{Lo}\p{M}]*(?i:'s|'t|'re|'ve|'m|'ll|'d)?|\p{N}{1,3}| ?[^\s\p{L}\p{N}]+[\r\n/]*|\s*[\r\n]+|\s+(?!\S)|\s+", 0x100),
     (r"[!\"#$%&'()*+,\-./:;<=>?@\[\\\]^_`{|}~][A-Za-z]+|[^\r\n\p{L}\p{P}\p{S}]?[\p{L}\p{M}]+| ?[\p{P}\p{S}]+[\r\n]*|\s*[\r\n]+|\s+(?!\S)|\s+|\p{N}{1,3}|[一-龥぀-ゟ゠-ヿ]+", 0x100),

@@ -201,7 +201,8 @@ def test_oracle_groups_anchors_scripts_and_look_behind_against_the_regex_module(
             (r"\Qa.b\E+|\w+|.", 0, r"a\.b+|\w+|.", False), (r"\h+|\v+|\H", 0, hs + "+|" + vs + "+|[^" + hs[1:], True),
             (r"(?<=\d)[a-z]+|(?<![a-z])\d+|.", 0, None, False),
             (r"\p{IsHan}+|\p{script=Cyrillic}+|\p{sc=Latn}+|\P{IsHiragana}", 0, r"\p{Han}+|\p{Script=Cyrillic}+|\p{Script=Latin}+|\P{Hiragana}", True),
-            (r"(?<!\p{L})\p{L}{1,3}|.", 0x100, None, True), (r"[\p{IsGreek}\p{IsHangul}]+|\p{IsCommon}|.", 0, r"[\p{Greek}\p{Hangul}]+|\p{Common}|.", True)]
+            (r"(?<!\p{L})\p{L}{1,3}|.", 0x100, None, True), (r"[\p{IsGreek}\p{IsHangul}]+|\p{IsCommon}|.", 0, r"[\p{Greek}\p{Hangul}]+|\p{Common}|.", True),
+            (r"\R\n|\R+|\w+|.", 0, "(?:\\r\\n|" + vs + ")\\n|(?:\\r\\n|" + vs + ")+|\\w+|.", False)]
     alph = list("abcXYZ 019_-+$.,;!?'\n\r\t") + ["é", "ß", "Ж", "я", "中", "国", "あ", "カ", "١", "२", "　", " ", "—", "𝐀", "🍕", "한", "ा", "\u2028", "\x0b", "α", "Ω"]
     rng = random.Random(5)
     for pat, fl, rpat, uni in pats:

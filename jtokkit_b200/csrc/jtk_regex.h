@@ -790,10 +790,14 @@ JTK_HD void jtk_rx_finish_word(const jtk_rx_split_buffers &B, int64_t w, int64_t
 	const int64_t slice = (w * 32) / JTK_RX_SLICE;
 	uint32_t ms = B.ms[w], me = B.me[w];
 	if (slice < B.nslices) {
-		const int64_t j = B.join[slice] - w * 32; /* speculative bits at word positions >= j are valid */
+		/* speculative START bits at word positions >= j are valid, END bits at positions > j: an end bit at the join position itself belongs
+		 * to the speculative run's past (the match with which IT arrived there); the true run sets its own - and may have arrived by stepping
+		 * over an empty match, without any match ending there */
+		const int64_t j = B.join[slice] - w * 32;
 		const uint32_t mask = j <= 0 ? 0xFFFFFFFFu : j >= 32 ? 0u : (0xFFFFFFFFu << j);
+		const uint32_t mask_end = j < 0 ? 0xFFFFFFFFu : j >= 31 ? 0u : (0xFFFFFFFEu << j);
 		ms |= B.s_ms[w] & mask;
-		me |= B.s_me[w] & mask;
+		me |= B.s_me[w] & mask_end;
 	}
 	if ((total >> 5) == w) me |= 1u << (total & 31); /* the end of the input ends the last piece */
 	B.ms[w] = ms | me;

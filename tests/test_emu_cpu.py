@@ -209,6 +209,86 @@ def test_dfa_run_shortcuts_on_long_runs_and_gaps():
                 assert np.array_equal(start, exp_start) and np.array_equal(skip, exp_skip), (pat, docs, "vm" if no_dfa else "dfa")
 
 
+def _random_pattern(rng, depth=0):
+    """A random pattern from the supported grammar: literals, classes, greedy / lazy / possessive quantifiers, groups, alternation,
+    one-character look-ahead, anchors."""
+    def atom(depth):
+        r = rng.random()
+        if r < 0.35:
+            return rng.choice(["a", "b", "c", " ", "1", "é"])
+        if r < 0.55:
+            return rng.choice(["[ab]", "[^a]", r"\w", r"\s", r"\d", ".", "[a-c1]", r"\S", r"[^\s1]", r"\p{L}"])
+        if r < 0.62:
+            return rng.choice(["(?=a)", "(?!b)", r"(?!\S)", r"(?=\s)", "(?![ab])"])
+        if r < 0.66:
+            return rng.choice(["^", r"\A", r"\z"])
+        if depth > 2:
+            return "a"
+        return "(?:" + _random_pattern(rng, depth + 1) + ")"
+
+    def quantified(depth):
+        a = atom(depth)
+        if a.startswith("(?=") or a.startswith("(?!") or a in ("^", r"\A", r"\z") or rng.random() < 0.5:
+            return a
+        q = rng.choice(["*", "+", "?", "{1,2}", "{2}", "{0,3}"])
+        return a + q + (rng.choice(["", "", "?", "+"]) if not a.startswith("(?:") else rng.choice(["", "", "?"]))
+
+    return "|".join("".join(quantified(depth) for _ in range(rng.randint(1, 3))) for _ in range(rng.randint(1, 3)))
+
+
+def test_random_patterns_dfa_and_program_against_the_oracle():
+    """Random patterns (what the compiler accepts of them), random short documents in groups that span several 32-byte slices: the DFA and
+    the backtracking program under the sliced find() passes against the oracle's matcher.  (This fuzz found the speculative end bit at a
+    join position reached over an empty match: jtk_rx_finish_word.)"""
+    import emu
+    from oracle import jo
+    jo.build()
+    rng = random.Random(2)
+    alph = ["a", "b", "c", " ", "1", "\n", "é", "ab", "  ", "aa", "b1"]
+    accepted = with_dfa = 0
+    for _ in range(350):
+        pat = _random_pattern(rng)
+        try:
+            e = emu.EmuEncoding("g", pat, 0, {b"a": 0}, {})
+        except ValueError:
+            continue  # outside the subset (a loop over a nullable group, ...)
+        o = jo.OracleEncoding("g", pat, 0, {b"a": 0}, {})
+        accepted += 1
+        has_dfa = e.dfa_info()[0] > 0
+        with_dfa += has_dfa
+        for _ in range(10):
+            docs = [("".join(rng.choice(alph) for _ in range(rng.randint(0, 14)))).encode() for _ in range(rng.randint(1, 3))]
+            blob = b"".join(docs)
+            off = np.zeros(len(docs) + 1, dtype=np.int64)
+            off[1:] = np.cumsum([len(x) for x in docs])
+            exp_start, exp_skip = expected_piece_bits(o, docs, off, len(blob))
+            for no_dfa in ([False, True] if has_dfa else [True]):
+                try:
+                    start, skip = e.general_split(np.frombuffer(blob, dtype=np.uint8), off, no_dfa=no_dfa)
+                except OverflowError:
+                    continue  # (the program's small test stack)
+                assert np.array_equal(start, exp_start) and np.array_equal(skip, exp_skip), (pat, docs, "vm" if no_dfa else "dfa")
+    assert accepted > 150 and with_dfa > 140
+
+
+def test_join_after_an_empty_match_takes_no_speculative_end_bit():
+    """A nullable pattern: the true run reaches position 44 by stepping over an empty match at 43, the speculative run of the slice by a
+    match (40, 44).  The end bit of that speculative match must not become a piece start of the gap [43, 46)."""
+    import emu
+    from oracle import jo
+    jo.build()
+    pat = r"(?:[a-z1 \n]{4})?"
+    docs = [b"c" * 27, b"x" * 16 + "bé".encode()]
+    blob = b"".join(docs)
+    off = np.array([0, 27, 27 + len(docs[1])], dtype=np.int64)
+    e = emu.EmuEncoding("g", pat, 0, {b"a": 0}, {})
+    exp_start, exp_skip = expected_piece_bits(jo.OracleEncoding("g", pat, 0, {b"a": 0}, {}), docs, off, len(blob))
+    for no_dfa in (False, True):
+        start, skip = e.general_split(np.frombuffer(blob, dtype=np.uint8), off, no_dfa=no_dfa)
+        assert np.array_equal(start, exp_start) and np.array_equal(skip, exp_skip)
+    assert np.nonzero(exp_skip)[0].tolist() == [24, 43]
+
+
 def test_flat_dfa_loop_decodes_utf8_like_the_bytewise_decoder():
     import ctypes as C
     import emu

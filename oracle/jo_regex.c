@@ -776,9 +776,15 @@ static int cls_match(const cls_item *it, uint32_t cp, int ucc) {
 	return 0;
 }
 
-static int set_match_one(const node *nd, uint32_t cp, int ucc) {
+/* the literal characters and ranges of a class: what CASE_INSENSITIVE folds (java.util.regex folds single characters and ranges -
+ * SingleI / SingleU / CIRange -, never the predefined classes and properties) */
+static int set_match_ranges(const node *nd, uint32_t cp) {
 	for (int i = 0; i < nd->nranges; i++)
 		if (cp >= nd->ranges[i][0] && cp <= nd->ranges[i][1]) return 1;
+	return 0;
+}
+static int set_match_one(const node *nd, uint32_t cp, int ucc) {
+	if (set_match_ranges(nd, cp)) return 1;
 	for (int i = 0; i < nd->ncls; i++)
 		if (cls_match(&nd->cls[i], cp, ucc) != nd->cls[i].neg) return 1;
 	return 0;
@@ -793,13 +799,13 @@ static int operand_match(const mctx *m, const node *nd, uint32_t cp) {
 	int ucc = (m->re->flags & JO_RE_UNICODE_CHARACTER_CLASS) != 0;
 	int r = set_match_one(nd, cp, ucc);
 	if (!r && nd->ci) {
-		if (cp >= 'a' && cp <= 'z') r = set_match_one(nd, cp - 32, ucc);
-		else if (cp >= 'A' && cp <= 'Z') r = set_match_one(nd, cp + 32, ucc);
+		if (cp >= 'a' && cp <= 'z') r = set_match_ranges(nd, cp - 32);
+		else if (cp >= 'A' && cp <= 'Z') r = set_match_ranges(nd, cp + 32);
 		if (!r && (m->re->flags & JO_RE_UNICODE_CASE)) {
-			if (cp == 0x17F) r = set_match_one(nd, 's', ucc) || set_match_one(nd, 'S', ucc);
-			else if (cp == 0x212A) r = set_match_one(nd, 'k', ucc) || set_match_one(nd, 'K', ucc);
-			else if (cp == 's' || cp == 'S') r = set_match_one(nd, 0x17F, ucc);
-			else if (cp == 'k' || cp == 'K') r = set_match_one(nd, 0x212A, ucc);
+			if (cp == 0x17F) r = set_match_ranges(nd, 's') || set_match_ranges(nd, 'S');
+			else if (cp == 0x212A) r = set_match_ranges(nd, 'k') || set_match_ranges(nd, 'K');
+			else if (cp == 's' || cp == 'S') r = set_match_ranges(nd, 0x17F);
+			else if (cp == 'k' || cp == 'K') r = set_match_ranges(nd, 0x212A);
 		}
 	}
 	for (int i = 0; i < nd->nnest && !r; i++) r = set_match(m, nd->nest[i], cp);

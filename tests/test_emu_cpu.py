@@ -244,15 +244,18 @@ def test_random_patterns_dfa_and_program_against_the_oracle():
     from oracle import jo
     jo.build()
     rng = random.Random(2)
-    alph = ["a", "b", "c", " ", "1", "\n", "é", "ab", "  ", "aa", "b1"]
+    alph = ["a", "b", "c", " ", "1", "\n", "é", "ab", "  ", "aa", "b1", "A", "B", "É", "ſ", "K", "\u212a", "\u00a0", "\u0661"]
     accepted = with_dfa = 0
-    for _ in range(350):
+    for it in range(450):
         pat = _random_pattern(rng)
+        # Pattern flags: none for most, then CASE_INSENSITIVE with and without UNICODE_CASE / UNICODE_CHARACTER_CLASS (the long s and the Kelvin sign
+        # fold onto s and k for literal characters only, never for \\w or a property: this fuzz found the oracle folding those too)
+        flags = 0 if it % 3 else rng.choice([2, 0x100, 0x102, 0x42])
         try:
-            e = emu.EmuEncoding("g", pat, 0, {b"a": 0}, {})
+            e = emu.EmuEncoding("g", pat, flags, {b"a": 0}, {})
         except ValueError:
             continue  # outside the subset (a loop over a nullable group, ...)
-        o = jo.OracleEncoding("g", pat, 0, {b"a": 0}, {})
+        o = jo.OracleEncoding("g", pat, flags, {b"a": 0}, {})
         accepted += 1
         has_dfa = e.dfa_info()[0] > 0
         with_dfa += has_dfa

@@ -210,28 +210,29 @@ def test_dfa_run_shortcuts_on_long_runs_and_gaps():
 
 
 def _random_pattern(rng, depth=0):
-    """A random pattern from the supported grammar: literals, classes, greedy / lazy / possessive quantifiers, groups, alternation,
-    one-character look-ahead, anchors."""
+    """A random pattern from (a little more than) the supported grammar: literals, classes, properties, scripts, class algebra, greedy / lazy /
+    possessive quantifiers, plain / named / capturing / (?i:) groups, alternation, look-ahead, look-behind, anchors, boundaries."""
     def atom(depth):
         r = rng.random()
         if r < 0.35:
             return rng.choice(["a", "b", "c", " ", "1", "é"])
         if r < 0.55:
-            return rng.choice(["[ab]", "[^a]", r"\w", r"\s", r"\d", ".", "[a-c1]", r"\S", r"[^\s1]", r"\p{L}"])
+            return rng.choice(["[ab]", "[^a]", r"\w", r"\s", r"\d", ".", "[a-c1]", r"\S", r"[^\s1]", r"\p{L}", r"\R", r"\h", r"\V", r"\p{IsLatin}", r"\p{Lu}", r"\P{Ll}",
+                               "[a-c&&[^b]]", "[a[1 ]]", r"[\w&&[^\d]]", r"\p{IsGreek}", r"\Qa.\E", "[^é\\n]", r"\x41", r"[\p{L}&&[^\p{Lu}]]"])
         if r < 0.62:
-            return rng.choice(["(?=a)", "(?!b)", r"(?!\S)", r"(?=\s)", "(?![ab])"])
+            return rng.choice(["(?=a)", "(?!b)", r"(?!\S)", r"(?=\s)", "(?![ab])", "(?<=a)", "(?<!b)", r"(?<![\w])", r"(?<=\s)", "(?=ab)", "(?!a1)", r"\b", r"\B", "$", r"\Z"])
         if r < 0.66:
             return rng.choice(["^", r"\A", r"\z"])
         if depth > 2:
             return "a"
-        return "(?:" + _random_pattern(rng, depth + 1) + ")"
+        return rng.choice(["(?:", "(?:", "(?<n>", "(", "(?i:"]) + _random_pattern(rng, depth + 1) + ")"
 
     def quantified(depth):
         a = atom(depth)
-        if a.startswith("(?=") or a.startswith("(?!") or a in ("^", r"\A", r"\z") or rng.random() < 0.5:
+        if a.startswith("(?=") or a.startswith("(?!") or a.startswith("(?<=") or a.startswith("(?<!") or a in ("^", r"\A", r"\z", r"\b", r"\B", "$", r"\Z") or rng.random() < 0.5:
             return a
         q = rng.choice(["*", "+", "?", "{1,2}", "{2}", "{0,3}"])
-        return a + q + (rng.choice(["", "", "?", "+"]) if not a.startswith("(?:") else rng.choice(["", "", "?"]))
+        return a + q + (rng.choice(["", "", "?", "+"]) if not a.startswith("(") else rng.choice(["", "", "?"]))
 
     return "|".join("".join(quantified(depth) for _ in range(rng.randint(1, 3))) for _ in range(rng.randint(1, 3)))
 
@@ -244,7 +245,7 @@ def test_random_patterns_dfa_and_program_against_the_oracle():
     from oracle import jo
     jo.build()
     rng = random.Random(2)
-    alph = ["a", "b", "c", " ", "1", "\n", "é", "ab", "  ", "aa", "b1", "A", "B", "É", "ſ", "K", "\u212a", "\u00a0", "\u0661"]
+    alph = ["a", "b", "c", " ", "1", "\n", "é", "ab", "  ", "aa", "b1", "A", "B", "É", "ſ", "K", "\u212a", "\u00a0", "\u0661", "α", "Ω", "\r\n", "\r", "\t", "\x0b", "中"]
     accepted = with_dfa = 0
     for it in range(450):
         pat = _random_pattern(rng)
@@ -271,7 +272,7 @@ def test_random_patterns_dfa_and_program_against_the_oracle():
                 except OverflowError:
                     continue  # (the program's small test stack)
                 assert np.array_equal(start, exp_start) and np.array_equal(skip, exp_skip), (pat, docs, "vm" if no_dfa else "dfa")
-    assert accepted > 150 and with_dfa > 140
+    assert accepted > 150 and with_dfa > 100
 
 
 def test_join_after_an_empty_match_takes_no_speculative_end_bit():
